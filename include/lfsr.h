@@ -1,0 +1,165 @@
+/*
+ * lfsr.h — C ABI of liblfsr_b200.so: the B200 (sm_100a) kernels behind BasicLFSR's
+ * patch-wise light-field SR inference path
+ *     LFdivide -> get_model(args).forward(lr, data_info) -> LFintegrate -> PSNR/SSIM on Y.
+ *
+ * The reference (darskkaa/NTIRE-2026-...-Track-2-Efficiency) has NO native/FFI layer: its
+ * "plugin ABI" is a Python duck type (model.SR.<name>.get_model / utils.utils.LFdivide ...).
+ * Each entry point below therefore cites the reference Python function whose arithmetic it
+ * replaces (paths relative to /root/reference). The Python host side (package
+ * `..._b200`, re-exported as `lfsr_b200`) binds these with ctypes; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless named host_*.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs.
+ *   - no hidden allocation: workspaces are passed in, sizes come from *_workspace() queries.
+ *   - return 0 on success, negative lfsr_status on error; lfsr_last_error() gives the text
+ *     (thread-local).
+ *   - feature tensors are fp32 NHWC views (`lfsr_tensor`): element (n,y,x,c) lives at
+ *     ptr[((n*h + y)*w + x)*ld + c], ld >= c. A channel slice of a wider buffer is the same
+ *     struct with ptr advanced and c reduced - this is how torch.cat / torch.split are free.
+ *   - single-channel mosaics ([B,1,A*h,A*w] in the reference) are plain dense fp32 images.
+ */
+#ifndef LFSR_B200_H_
+#define LFSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFSR_ABI_VERSION 1
+
+typedef enum {
+  LFSR_OK = 0,
+  LFSR_ERR_INVALID = -1,      /* bad argument / unsupported shape */
+  LFSR_ERR_CUDA = -2,         /* CUDA runtime / driver error, see lfsr_last_error() */
+  LFSR_ERR_UNSUPPORTED = -3,  /* valid request, not handled by this build */
+  LFSR_ERR_WORKSPACE = -4     /* workspace too small */
+} lfsr_status;
+
+typedef struct {
+  void* ptr;
+  int32_t n, h, w, c;
+  int32_t ld; /* floats between consecutive pixels */
+} lfsr_tensor;
+
+enum { LFSR_ACT_NONE = 0, LFSR_ACT_RELU = 1, LFSR_ACT_LRELU = 2, LFSR_ACT_SIGMOID = 3 };
+enum { LFSR_PERM_NONE = 0, LFSR_PERM_MACPI_OVER_SAI = 1 };
+enum { LFSR_SHUF_CHANNEL_MAJOR = 0, /* nn.PixelShuffle: co = c*ry*rx + i*rx + j   */
+       LFSR_SHUF_FACTOR_MAJOR = 1   /* PixelShuffle1D  : co = (i*rx + j)*C + c     */ };
+enum { LFSR_INTERP_BICUBIC = 0, LFSR_INTERP_BILINEAR = 1 };
+
+/* Convolution + fused epilogue descriptor.
+ *   v = sum_taps W[tap][ci][co] * in_scale[n][ci] * in(n, oy*stride_h - pad_h + ky*dil_h, ..., ci) + bias[co]
+ *   v = act(v); v *= mul(n,oy,ox,co); v *= alpha;
+ *   (sy,sx,sc) = shuffle(oy,ox,co); v += res(n,sy,sx,sc); out(n,sy,sx,sc) = v
+ * in_perm / out_perm = LFSR_PERM_MACPI_OVER_SAI: the logical image the convolution walks is the
+ * MacPI arrangement mac[i*A+u][j*A+v] of a tensor stored as SAI sai[u*h+i][v*w+j] (A = perm_a);
+ * this folds SAI2MacPI / MacPI2SAI (DistgSSR.py:134-155, LF_InterNet.py:144-165) into addressing. */
+typedef struct {
+  int32_t kh, kw, stride_h, stride_w, dil_h, dil_w, pad_h, pad_w;
+  int32_t in_perm, out_perm, perm_a;
+  int32_t shuf_ry, shuf_rx, shuf_mode;
+  int32_t block_h, block_w; /* >0: taps leaving the block_h x block_w block of the output pixel read 0
+                               (per-view Conv3d(1,3,3) of EPIT.py:24-31 on SAI-mosaic storage); stride 1 only */
+  int32_t act;
+  float act_slope;
+  float alpha;
+  const float* bias;     /* [cout] or NULL */
+  const float* in_scale; /* [n][cin] or NULL */
+  lfsr_tensor mul;       /* ptr NULL if unused; conv-output geometry */
+  lfsr_tensor res;       /* ptr NULL if unused; stored-output geometry */
+} lfsr_conv_desc;
+
+const char* lfsr_last_error(void);
+int lfsr_abi_version(void);
+/* 1 if this build carries sm_100a code for every kernel (always, for this library). */
+int lfsr_built_for_sm100a(void);
+/* number of kernel launches issued by this library in the calling process since load */
+uint64_t lfsr_launch_count(void);
+
+/* ---- patch pipeline ------------------------------------------------------------------ */
+/* LFdivide + ImageExtend (utils/utils.py:137-166): scene [A*h0, A*w0] -> [numU*numV, A*P, A*P],
+ * numU = (h0 + 2*((P-S)/2) - 1)/S. Bit-exact gather with symmetric mirror padding. */
+int lfsr_divide(const float* scene, float* patches, int ang, int h0, int w0, int patch, int stride,
+                void* stream);
+/* same, restricted to patch-grid rows [u_begin, u_end) (multi-GPU row sharding) */
+int lfsr_divide_rows(const float* scene, float* patches, int ang, int h0, int w0, int patch,
+                     int stride, int u_begin, int u_end, void* stream);
+/* LFintegrate (utils/utils.py:169-178) + train.py:314-319: patches [numU*numV, A*pz, A*pz] ->
+ * SAI mosaic [A*h, A*w] (the 'a1 a2 h w -> (a1 h) (a2 w)' rearrange is folded in).
+ * rows [u_begin,u_end) of the patch grid only; `patches` points at patch (u_begin, 0);
+ * out is the full mosaic (rows outside the shard are untouched). */
+int lfsr_integrate_rows(const float* patches, float* out, int ang, int pz, int stride, int h, int w,
+                        int num_u, int num_v, int u_begin, int u_end, void* stream);
+
+/* ---- interpolation residual ---------------------------------------------------------- */
+/* F.interpolate(mode='bicubic'|'bilinear', align_corners=False) as called at
+ * MyEfficientLFNet.py:88-90 (bicubic, whole mosaic), EPIT.py:164-169 (bicubic, per view),
+ * DistgSSR.py:30 (bilinear, whole mosaic). in [n, h, w] -> out [n, h*s, w*s];
+ * block_h/block_w = size of the independently-clamped block (h,w for whole mosaic; view size
+ * for per-view). */
+int lfsr_interp(const float* in, float* out, int n, int h, int w, int scale, int mode, int block_h,
+                int block_w, void* stream);
+
+/* ---- convolutions --------------------------------------------------------------------- */
+/* fp32 CUDA-core implicit GEMM; weights packed [kh*kw][cin][cout]. */
+int lfsr_conv2d_f32(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out,
+                    const lfsr_conv_desc* d, void* stream);
+/* depthwise conv (groups == channels); weights [kh*kw][c]; optional per-channel affine
+ * (folded BatchNorm) then activation. */
+int lfsr_dwconv_f32(const lfsr_tensor* in, const float* w_packed, const float* scale,
+                    const float* shift, const lfsr_tensor* out, int kh, int kw, int dil_h, int dil_w,
+                    int act, float act_slope, void* stream);
+/* TF32 tcgen05/TMEM implicit GEMM fed by TMA (sm_100a); weights packed by lfsr_pack_conv_tc.
+ * Supports stride 1 (any dilation, "same" zero padding given by pad) and kh*kw <= 25. */
+size_t lfsr_conv2d_tc_packed_floats(int kh, int kw, int cin, int cout);
+int lfsr_pack_conv_tc(const float* w_oihw_host, float* packed_host, int kh, int kw, int cin, int cout);
+int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, const lfsr_tensor* out,
+                   const lfsr_conv_desc* d, void* stream);
+/* 1 if lfsr_conv2d_tc can run this problem (geometry/alignment), else 0 */
+int lfsr_conv2d_tc_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);
+
+/* ---- reductions / gates (MyEfficientLFNet.py:159-173, 471-515) ---------------------------- */
+/* mean over each (block_h x block_w) block: in [n,h,w,c] -> out [n, h/block_h, w/block_w, c] */
+int lfsr_block_mean(const lfsr_tensor* in, const lfsr_tensor* out, int block_h, int block_w,
+                    void* stream);
+/* SAModulator tail (MyEfficientLFNet.py:495-515) fused with the stage residual:
+ *   s = sigmoid(bn_scale*dw3x3_dil(x) + bn_shift); a = amod[n][y/(h/A)][x/(w/A)][c]
+ *   out = x * (w0*s + w1*a) + res */
+int lfsr_sa_modulate(const lfsr_tensor* x, const float* dw_w, const float* bn_scale,
+                     const float* bn_shift, const lfsr_tensor* amod, float w0, float w1,
+                     const lfsr_tensor* res, const lfsr_tensor* out, int dil, void* stream);
+
+/* ---- EPIT token ops (EPIT.py:74-128) ------------------------------------------------------ */
+/* LayerNorm over c (eps, affine) for every pixel/token */
+int lfsr_layernorm(const lfsr_tensor* in, const float* gamma, const float* beta, float eps,
+                   const lfsr_tensor* out, void* stream);
+/* band-masked multi-head attention over EPI sequences. qk: [T, 2E] (q | k), v: [T, E], out [T,E];
+ * tokens are addressed token(seq, a, s) = seq_base(seq) + a*stride_a + s*stride_s with
+ * a in [0,A), s in [0,S): key (a',s') allowed iff |s - s'| <= half_window (EPIT.py:93-108 with
+ * mask_field [2A, 11]). seq enumerates (b, p, q): seq_base = b*stride_b + p*stride_p + q*stride_q */
+typedef struct {
+  int32_t heads, head_dim;
+  int32_t A, S, half_window;
+  int32_t nb, np, nq;
+  int64_t stride_a, stride_s, stride_b, stride_p, stride_q; /* in tokens */
+} lfsr_epi_attn_desc;
+int lfsr_epi_attention(const float* qk, const float* v, float* out, const lfsr_epi_attn_desc* d,
+                       void* stream);
+
+/* ---- metrics (utils/utils.py:91-134) ------------------------------------------------------ */
+/* per-view sums for PSNR/SSIM on SAI mosaics label/out [A*h, A*w] (row stride = A*w):
+ * acc[view] = { sum (a-b)^2 , sum SSIM map over the 5-px-cropped interior } as float64.
+ * acc must be zeroed by the caller (cudaMemsetAsync) - 2*A*A doubles. */
+int lfsr_metric_sums(const float* label, const float* out, int ang, int h, int w, double* acc,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFSR_B200_H_ */

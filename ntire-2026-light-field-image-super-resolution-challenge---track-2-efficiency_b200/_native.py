@@ -1,0 +1,117 @@
+"""ctypes binding of liblfsr_b200.so (C ABI declared in include/lfsr.h).
+
+There is deliberately no fallback: if the shared library is missing or a CUDA device is not
+present the product path raises. Build it with ``python -c "import __graft_entry__ as g; g.build()"``
+(or ``make -C <package>/csrc``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "liblfsr_b200.so")
+CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
+PERM_NONE, PERM_MACPI_OVER_SAI = 0, 1
+SHUF_CHANNEL_MAJOR, SHUF_FACTOR_MAJOR = 0, 1
+INTERP_BICUBIC, INTERP_BILINEAR = 0, 1
+
+
+class LfsrError(RuntimeError):
+    pass
+
+
+class Tensor(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("c", C.c_int32), ("ld", C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("kh", C.c_int32), ("kw", C.c_int32), ("stride_h", C.c_int32), ("stride_w", C.c_int32),
+        ("dil_h", C.c_int32), ("dil_w", C.c_int32), ("pad_h", C.c_int32), ("pad_w", C.c_int32),
+        ("in_perm", C.c_int32), ("out_perm", C.c_int32), ("perm_a", C.c_int32),
+        ("shuf_ry", C.c_int32), ("shuf_rx", C.c_int32), ("shuf_mode", C.c_int32),
+        ("block_h", C.c_int32), ("block_w", C.c_int32),
+        ("act", C.c_int32), ("act_slope", C.c_float), ("alpha", C.c_float),
+        ("bias", C.c_void_p), ("in_scale", C.c_void_p),
+        ("mul", Tensor), ("res", Tensor),
+    ]
+
+
+class EpiAttnDesc(C.Structure):
+    _fields_ = [
+        ("heads", C.c_int32), ("head_dim", C.c_int32), ("A", C.c_int32), ("S", C.c_int32),
+        ("half_window", C.c_int32), ("nb", C.c_int32), ("np", C.c_int32), ("nq", C.c_int32),
+        ("stride_a", C.c_int64), ("stride_s", C.c_int64), ("stride_b", C.c_int64),
+        ("stride_p", C.c_int64), ("stride_q", C.c_int64),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/lfsr.h one to one (tests check the export list)
+_P = C.c_void_p
+_I = C.c_int
+_TP = C.POINTER(Tensor)
+SIGNATURES = {
+    "lfsr_last_error": (C.c_char_p, []),
+    "lfsr_abi_version": (_I, []),
+    "lfsr_built_for_sm100a": (_I, []),
+    "lfsr_launch_count": (C.c_uint64, []),
+    "lfsr_divide": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "lfsr_divide_rows": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "lfsr_integrate_rows": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "lfsr_interp": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "lfsr_conv2d_f32": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
+    "lfsr_dwconv_f32": (_I, [_TP, _P, _P, _P, _TP, _I, _I, _I, _I, _I, C.c_float, _P]),
+    "lfsr_conv2d_tc_packed_floats": (C.c_size_t, [_I, _I, _I, _I]),
+    "lfsr_pack_conv_tc": (_I, [_P, _P, _I, _I, _I, _I]),
+    "lfsr_conv2d_tc": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
+    "lfsr_conv2d_tc_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),
+    "lfsr_block_mean": (_I, [_TP, _TP, _I, _I, _P]),
+    "lfsr_sa_modulate": (_I, [_TP, _P, _P, _P, _TP, C.c_float, C.c_float, _TP, _TP, _I, _P]),
+    "lfsr_layernorm": (_I, [_TP, _P, _P, C.c_float, _TP, _P]),
+    "lfsr_epi_attention": (_I, [_P, _P, _P, C.POINTER(EpiAttnDesc), _P]),
+    "lfsr_metric_sums": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+}
+
+_lib = None
+
+
+def build_native(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into liblfsr_b200.so (nvcc cross-compiles without a GPU)."""
+    proc = subprocess.run(["make", "-C", CSRC_DIR, "-j", str(os.cpu_count() or 4)], capture_output=True, text=True)
+    if verbose or proc.returncode != 0:
+        print(proc.stdout)
+        print(proc.stderr)
+    if proc.returncode != 0:
+        raise LfsrError("nvcc build of liblfsr_b200.so failed")
+    return LIB_PATH
+
+
+def load():
+    """Return the loaded library; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LfsrError(
+            f"{LIB_PATH} is missing: the sm_100a CUDA extension has not been built "
+            "(run __graft_entry__.build()); there is no CPU fallback for this path")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the export is missing - intended
+        fn.restype = res
+        fn.argtypes = args
+    if lib.lfsr_abi_version() != 1:
+        raise LfsrError("liblfsr_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().lfsr_last_error().decode("utf-8", "replace")
+        raise LfsrError(f"{what} failed ({status}): {msg}")

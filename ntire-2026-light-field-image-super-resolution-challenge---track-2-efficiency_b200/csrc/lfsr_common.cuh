@@ -1,0 +1,72 @@
+// Shared helpers for liblfsr_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/lfsr.h"
+
+namespace lfsr {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return LFSR_ERR_CUDA;
+  }
+  return LFSR_OK;
+}
+
+#define LFSR_REQUIRE(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::lfsr::set_error(__VA_ARGS__);      \
+      return LFSR_ERR_INVALID;             \
+    }                                      \
+  } while (0)
+
+inline bool tensor_ok(const lfsr_tensor* t) {
+  return t && t->ptr && t->n > 0 && t->h > 0 && t->w > 0 && t->c > 0 && t->ld >= t->c;
+}
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// device-side view of lfsr_tensor
+struct TView {
+  float* p;
+  int n, h, w, c, ld;
+  __device__ __forceinline__ size_t pix(int in_, int y, int x) const {
+    return ((size_t)((size_t)in_ * h + y) * w + x) * (size_t)ld;
+  }
+};
+inline TView view_of(const lfsr_tensor* t) {
+  TView v;
+  v.p = (float*)t->ptr; v.n = t->n; v.h = t->h; v.w = t->w; v.c = t->c; v.ld = t->ld;
+  return v;
+}
+inline TView null_view() { TView v; v.p = nullptr; v.n = v.h = v.w = v.c = v.ld = 0; return v; }
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  switch (act) {
+    case LFSR_ACT_RELU: return v > 0.f ? v : 0.f;
+    case LFSR_ACT_LRELU: return v > 0.f ? v : v * slope;
+    case LFSR_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+
+// MacPI (i*A+u, j*A+v) logical coordinate -> SAI (u*hh+i, v*ww+j) storage coordinate,
+// H = A*hh, W = A*ww  (DistgSSR.py:134-155)
+__device__ __forceinline__ void macpi_to_sai(int y, int x, int A, int H, int W, int& sy, int& sx) {
+  int hh = H / A, ww = W / A;
+  int i = y / A, u = y - i * A;
+  int j = x / A, v = x - j * A;
+  sy = u * hh + i;
+  sx = v * ww + j;
+}
+
+}  // namespace lfsr

@@ -1,0 +1,88 @@
+// ATen-compatible bicubic (A = -0.75, clamped taps) and bilinear upsampling, align_corners=False,
+// as reached from MyEfficientLFNet.py:88-90, EPIT.py:164-169 and DistgSSR.py:30 via F.interpolate.
+// (utils/imresize.py is a different, MATLAB-style bicubic used only offline - SURVEY 2.2.)
+// One thread per output pixel; HBM-bound on the s*s-times larger output, input rows are L1/L2 hits.
+#include "lfsr_common.cuh"
+
+namespace lfsr {
+
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+
+__device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
+  const float A = -0.75f;
+  c[0] = cubic2(t + 1.f, A);
+  c[1] = cubic1(t, A);
+  c[2] = cubic1(1.f - t, A);
+  c[3] = cubic2(2.f - t, A);
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__global__ void __launch_bounds__(256)
+interp_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int h, int w, int s, int mode, int bh,
+              int bw, long long total) {
+  const int oh = h * s, ow = w * s;
+  const float rs = 1.0f / (float)s;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    int ox = (int)(t % ow);
+    long long r = t / ow;
+    int oy = (int)(r % oh);
+    int img = (int)(r / oh);
+    // independent block (view) handling: clamp inside the block the output pixel falls in
+    int vby = oy / (bh * s), ly = oy - vby * bh * s;
+    int vbx = ox / (bw * s), lx = ox - vbx * bw * s;
+    const float* base = in + (size_t)img * h * w + (size_t)vby * bh * w + (size_t)vbx * bw;
+    float val;
+    if (mode == LFSR_INTERP_BICUBIC) {
+      float ry = rs * ((float)ly + 0.5f) - 0.5f;
+      float rx = rs * ((float)lx + 0.5f) - 0.5f;
+      float fy = floorf(ry), fx = floorf(rx);
+      int iy = (int)fy, ix = (int)fx;
+      float cy[4], cx[4];
+      cubic_coeffs(ry - fy, cy);
+      cubic_coeffs(rx - fx, cx);
+      int xs[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xs[i] = clampi(ix - 1 + i, 0, bw - 1);
+      val = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* row = base + (size_t)clampi(iy - 1 + j, 0, bh - 1) * w;
+        float rsum = __ldg(row + xs[0]) * cx[0] + __ldg(row + xs[1]) * cx[1] + __ldg(row + xs[2]) * cx[2] +
+                     __ldg(row + xs[3]) * cx[3];
+        val += rsum * cy[j];
+      }
+    } else {
+      float ry = fmaxf(rs * ((float)ly + 0.5f) - 0.5f, 0.f);
+      float rx = fmaxf(rs * ((float)lx + 0.5f) - 0.5f, 0.f);
+      int y0 = (int)ry, x0 = (int)rx;
+      int y1 = y0 + (y0 < bh - 1 ? 1 : 0), x1 = x0 + (x0 < bw - 1 ? 1 : 0);
+      float ly1 = ry - (float)y0, lx1 = rx - (float)x0;
+      float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+      const float* r0 = base + (size_t)y0 * w;
+      const float* r1 = base + (size_t)y1 * w;
+      val = ly0 * (lx0 * __ldg(r0 + x0) + lx1 * __ldg(r0 + x1)) + ly1 * (lx0 * __ldg(r1 + x0) + lx1 * __ldg(r1 + x1));
+    }
+    out[t] = val;
+  }
+}
+
+}  // namespace lfsr
+
+using namespace lfsr;
+
+extern "C" int lfsr_interp(const float* in, float* out, int n, int h, int w, int scale, int mode, int block_h,
+                           int block_w, void* stream) {
+  LFSR_REQUIRE(in && out, "lfsr_interp: null pointer");
+  LFSR_REQUIRE(n > 0 && h > 0 && w > 0 && scale >= 1, "lfsr_interp: bad geometry");
+  LFSR_REQUIRE(mode == LFSR_INTERP_BICUBIC || mode == LFSR_INTERP_BILINEAR, "lfsr_interp: bad mode %d", mode);
+  LFSR_REQUIRE(block_h > 0 && block_w > 0 && h % block_h == 0 && w % block_w == 0,
+               "lfsr_interp: block %dx%d does not tile %dx%d", block_h, block_w, h, w);
+  long long total = (long long)n * h * scale * w * scale;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  interp_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n, h, w, scale, mode, block_h, block_w, total);
+  return check_launch("interp_kernel");
+}

@@ -1,0 +1,354 @@
+// Reductions, the SA-modulator tail, LayerNorm, band-masked EPI attention and PSNR/SSIM sums.
+// All HBM/latency-bound fp32 kernels with warp-shuffle reductions.
+#include "lfsr_common.cuh"
+
+namespace lfsr {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- block mean: one CTA per (n, by, bx); AdaptiveAvgPool2d(1) / (angRes) of
+// MyEfficientLFNet.py:159-173,491 when the block tiles the image evenly.
+__global__ void __launch_bounds__(256)
+block_mean_kernel(TView in, TView out, int bh, int bw) {
+  __shared__ float red[256];
+  int blk = blockIdx.x;
+  const int nbx = in.w / bw, nby = in.h / bh;
+  const int bx = blk % nbx; blk /= nbx;
+  const int by = blk % nby;
+  const int img = blk / nby;
+  const int C = in.c;
+  const int CW = C > 32 ? 64 : (C > 16 ? 32 : 16);
+  const int PL = 256 / CW;
+  const int cl = threadIdx.x % CW, pl = threadIdx.x / CW;
+  const int npix = bh * bw;
+  const float inv = 1.f / (float)npix;
+  for (int c0 = 0; c0 < C; c0 += CW) {
+    const int c = c0 + cl;
+    float s = 0.f;
+    if (c < C) {
+      for (int p = pl; p < npix; p += PL) {
+        const int y = by * bh + p / bw, x = bx * bw + p % bw;
+        s += __ldg(in.p + in.pix(img, y, x) + c);
+      }
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (pl == 0 && c < C) {
+      float t = 0.f;
+      for (int q = 0; q < PL; ++q) t += red[q * CW + cl];
+      out.p[out.pix(img, by, bx) + c] = t * inv;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- SA modulator tail + stage residual (MyEfficientLFNet.py:495-515, 207)
+__global__ void __launch_bounds__(256)
+sa_modulate_kernel(TView x, const float* __restrict__ dww, const float* __restrict__ bns,
+                   const float* __restrict__ bnb, TView amod, float w0, float w1, TView res, TView out, int dil,
+                   long long total) {
+  const int C = x.c;
+  const int vh = x.h / amod.h, vw = x.w / amod.w;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(t % C);
+    long long r = t / C;
+    int px = (int)(r % x.w); r /= x.w;
+    int py = (int)(r % x.h);
+    int img = (int)(r / x.h);
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = py + (ky - 1) * dil;
+      if (iy < 0 || iy >= x.h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = px + (kx - 1) * dil;
+        if (ix < 0 || ix >= x.w) continue;
+        acc = fmaf(__ldg(x.p + x.pix(img, iy, ix) + c), __ldg(dww + (ky * 3 + kx) * C + c), acc);
+      }
+    }
+    const float s = 1.f / (1.f + expf(-(acc * __ldg(bns + c) + __ldg(bnb + c))));
+    const float am = __ldg(amod.p + amod.pix(img, py / vh, px / vw) + c);
+    const float xv = __ldg(x.p + x.pix(img, py, px) + c);
+    float v = xv * (w0 * s + w1 * am);
+    if (res.p) v += res.p[res.pix(img, py, px) + c];
+    out.p[out.pix(img, py, px) + c] = v;
+  }
+}
+
+// ---- LayerNorm over channels: one warp per token (EPIT.py:77,84)
+__global__ void __launch_bounds__(256)
+layernorm_kernel(TView in, TView out, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 long long tokens) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int C = in.c;
+  for (long long t = warp; t < tokens; t += nwarps) {
+    const float* src = in.p + (size_t)t * in.ld;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += __ldg(src + c);
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = __ldg(src + c) - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    float* dst = out.p + (size_t)t * out.ld;
+    for (int c = lane; c < C; c += 32) dst[c] = (__ldg(src + c) - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+  }
+}
+
+// ---- band-masked EPI attention: one CTA per (sequence, head), one thread per query.
+// Keys allowed for query (a,s): all a' in [0,A), |s'-s| <= half_window (EPIT.py:93-108 with
+// mask_field=[2A,11]); q is pre-scaled by head_dim^-0.5 as nn.MultiheadAttention does.
+constexpr int ATT_D = 16;       // head_dim (E=128, 8 heads; EPIT.py:78)
+constexpr int ATT_LD = 20;      // padded smem row: conflict-free float4 reads
+__global__ void __launch_bounds__(192)
+epi_attention_kernel(const float* __restrict__ qk, const float* __restrict__ v, float* __restrict__ out,
+                     lfsr_epi_attn_desc d) {
+  extern __shared__ float sm[];
+  const int L = d.A * d.S;
+  float* Ks = sm;                 // [L][ATT_LD]
+  float* Vs = sm + L * ATT_LD;    // [L][ATT_LD]
+  const int E = d.heads * ATT_D;
+  int seq = blockIdx.x;
+  const int head = blockIdx.y;
+  const int q_ = seq % d.nq; seq /= d.nq;
+  const int p_ = seq % d.np;
+  const int b_ = seq / d.np;
+  const long long base = b_ * d.stride_b + p_ * d.stride_p + q_ * d.stride_q;
+  const int tid = threadIdx.x;
+  // stage K and V head slices (float4 granules)
+  for (int i = tid; i < L * 4; i += blockDim.x) {
+    const int tok = i >> 2, part = i & 3;
+    const int a = tok / d.S, s = tok - a * d.S;
+    const long long g = base + a * d.stride_a + s * d.stride_s;
+    const float4 kv = __ldg(reinterpret_cast<const float4*>(qk + (size_t)g * 2 * E + E + head * ATT_D) + part);
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(v + (size_t)g * E + head * ATT_D) + part);
+    *reinterpret_cast<float4*>(Ks + tok * ATT_LD + part * 4) = kv;
+    *reinterpret_cast<float4*>(Vs + tok * ATT_LD + part * 4) = vv;
+  }
+  __syncthreads();
+  if (tid >= L) return;
+  const int qa = tid / d.S, qs = tid - qa * d.S;
+  const long long gq = base + qa * d.stride_a + qs * d.stride_s;
+  float q[ATT_D];
+  const float scale = rsqrtf((float)ATT_D);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(qk + (size_t)gq * 2 * E + head * ATT_D) + j);
+    q[4 * j] = t.x * scale; q[4 * j + 1] = t.y * scale; q[4 * j + 2] = t.z * scale; q[4 * j + 3] = t.w * scale;
+  }
+  const int s_lo = max(qs - d.half_window, 0), s_hi = min(qs + d.half_window, d.S - 1);
+  float m = -INFINITY, l = 0.f;
+  float acc[ATT_D];
+#pragma unroll
+  for (int j = 0; j < ATT_D; ++j) acc[j] = 0.f;
+  for (int a = 0; a < d.A; ++a) {
+    for (int s = s_lo; s <= s_hi; ++s) {
+      const float* kr = Ks + (a * d.S + s) * ATT_LD;
+      float sc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = *reinterpret_cast<const float4*>(kr + 4 * j);
+        sc = fmaf(q[4 * j], t.x, sc); sc = fmaf(q[4 * j + 1], t.y, sc);
+        sc = fmaf(q[4 * j + 2], t.z, sc); sc = fmaf(q[4 * j + 3], t.w, sc);
+      }
+      const float mn = fmaxf(m, sc);
+      const float corr = __expf(m - mn);   // exp(-inf) = 0 on the first key
+      const float pexp = __expf(sc - mn);
+      l = l * corr + pexp;
+      const float* vr = Vs + (a * d.S + s) * ATT_LD;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = *reinterpret_cast<const float4*>(vr + 4 * j);
+        acc[4 * j] = fmaf(pexp, t.x, acc[4 * j] * corr);
+        acc[4 * j + 1] = fmaf(pexp, t.y, acc[4 * j + 1] * corr);
+        acc[4 * j + 2] = fmaf(pexp, t.z, acc[4 * j + 2] * corr);
+        acc[4 * j + 3] = fmaf(pexp, t.w, acc[4 * j + 3] * corr);
+      }
+      m = mn;
+    }
+  }
+  const float inv = 1.f / l;
+  float* dst = out + (size_t)gq * E + head * ATT_D;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    reinterpret_cast<float4*>(dst)[j] =
+        make_float4(acc[4 * j] * inv, acc[4 * j + 1] * inv, acc[4 * j + 2] * inv, acc[4 * j + 3] * inv);
+}
+
+// ---- PSNR / SSIM partial sums (utils/utils.py:91-134 -> skimage.metrics):
+// SSIM: 11x11 Gaussian (sigma 1.5, truncate 3.5), sample covariance (121/120), K1=.01 K2=.03,
+// data_range 1, mean over the interior cropped by 5 px -> the filter never touches the border,
+// so scipy's 'reflect' mode is never exercised.
+constexpr int MT_W = 32, MT_H = 16, MT_R = 5;
+struct Gauss11 { float g[11]; };
+
+__global__ void __launch_bounds__(256)
+metric_kernel(const float* __restrict__ la, const float* __restrict__ ou, int A, int h, int w, double* acc,
+              int tiles_x, int tiles_y, const Gauss11 gw) {
+  __shared__ float sa[MT_H + 2 * MT_R][MT_W + 2 * MT_R];
+  __shared__ float sb[MT_H + 2 * MT_R][MT_W + 2 * MT_R];
+  __shared__ float hz[5][MT_H + 2 * MT_R][MT_W];
+  __shared__ double red[2][8];
+  int blk = blockIdx.x;
+  const int tx = blk % tiles_x; blk /= tiles_x;
+  const int ty = blk % tiles_y;
+  const int view = blk / tiles_y;
+  const int va = view / A, vb = view % A;
+  const size_t rs = (size_t)A * w;
+  const float* pa = la + (size_t)va * h * rs + (size_t)vb * w;
+  const float* pb = ou + (size_t)va * h * rs + (size_t)vb * w;
+  // tile origin in view coordinates; tiles cover the full view, SSIM is only taken on the interior
+  const int x0 = tx * MT_W, y0 = ty * MT_H;
+  const int tid = threadIdx.x;
+  double se = 0.0, ss = 0.0;
+  for (int i = tid; i < (MT_H + 2 * MT_R) * (MT_W + 2 * MT_R); i += 256) {
+    const int ly = i / (MT_W + 2 * MT_R), lx = i % (MT_W + 2 * MT_R);
+    const int y = y0 + ly - MT_R, x = x0 + lx - MT_R;
+    float av = 0.f, bv = 0.f;
+    if (y >= 0 && y < h && x >= 0 && x < w) { av = __ldg(pa + (size_t)y * rs + x); bv = __ldg(pb + (size_t)y * rs + x); }
+    sa[ly][lx] = av; sb[ly][lx] = bv;
+    // squared error over the tile's own pixels
+    if (ly >= MT_R && ly < MT_R + MT_H && lx >= MT_R && lx < MT_R + MT_W && y < h && x < w) {
+      const double dd = (double)av - (double)bv;
+      se += dd * dd;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < (MT_H + 2 * MT_R) * MT_W; i += 256) {
+    const int ly = i / MT_W, lx = i % MT_W;
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const float g = gw.g[k];
+      const float av = sa[ly][lx + k], bv = sb[ly][lx + k];
+      f0 = fmaf(g, av, f0); f1 = fmaf(g, bv, f1);
+      f2 = fmaf(g, av * av, f2); f3 = fmaf(g, bv * bv, f3); f4 = fmaf(g, av * bv, f4);
+    }
+    hz[0][ly][lx] = f0; hz[1][ly][lx] = f1; hz[2][ly][lx] = f2; hz[3][ly][lx] = f3; hz[4][ly][lx] = f4;
+  }
+  __syncthreads();
+  for (int i = tid; i < MT_H * MT_W; i += 256) {
+    const int ly = i / MT_W, lx = i % MT_W;
+    const int y = y0 + ly, x = x0 + lx;
+    if (y < MT_R || y >= h - MT_R || x < MT_R || x >= w - MT_R) continue;
+    float ux = 0.f, uy = 0.f, uxx = 0.f, uyy = 0.f, uxy = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const float g = gw.g[k];
+      ux = fmaf(g, hz[0][ly + k][lx], ux); uy = fmaf(g, hz[1][ly + k][lx], uy);
+      uxx = fmaf(g, hz[2][ly + k][lx], uxx); uyy = fmaf(g, hz[3][ly + k][lx], uyy);
+      uxy = fmaf(g, hz[4][ly + k][lx], uxy);
+    }
+    const float cov_norm = 121.f / 120.f;
+    const float vx = cov_norm * (uxx - ux * ux), vy = cov_norm * (uyy - uy * uy), vxy = cov_norm * (uxy - ux * uy);
+    const float C1 = 0.0001f, C2 = 0.0009f;
+    const float A1 = 2.f * ux * uy + C1, A2 = 2.f * vxy + C2;
+    const float B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
+    ss += (double)((A1 * A2) / (B1 * B2));
+  }
+  se = warp_sum_d(se); ss = warp_sum_d(ss);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = se; red[1][tid >> 5] = ss; }
+  __syncthreads();
+  if (tid == 0) {
+    double e = 0.0, s = 0.0;
+    for (int i = 0; i < 8; ++i) { e += red[0][i]; s += red[1][i]; }
+    atomicAdd(acc + 2 * view, e);
+    atomicAdd(acc + 2 * view + 1, s);
+  }
+}
+
+}  // namespace lfsr
+
+using namespace lfsr;
+
+static long long capped_blocks(long long total) {
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  return blocks < 1 ? 1 : blocks;
+}
+
+extern "C" int lfsr_block_mean(const lfsr_tensor* in, const lfsr_tensor* out, int block_h, int block_w, void* stream) {
+  LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out), "lfsr_block_mean: null/invalid tensor");
+  LFSR_REQUIRE(block_h > 0 && block_w > 0 && in->h % block_h == 0 && in->w % block_w == 0,
+               "lfsr_block_mean: block %dx%d does not tile %dx%d", block_h, block_w, in->h, in->w);
+  LFSR_REQUIRE(out->n == in->n && out->h == in->h / block_h && out->w == in->w / block_w && out->c == in->c,
+               "lfsr_block_mean: out shape mismatch");
+  const int grid = in->n * out->h * out->w;
+  block_mean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(in), view_of(out), block_h, block_w);
+  return check_launch("block_mean_kernel");
+}
+
+extern "C" int lfsr_sa_modulate(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
+                                const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res,
+                                const lfsr_tensor* out, int dil, void* stream) {
+  LFSR_REQUIRE(tensor_ok(x) && tensor_ok(out) && tensor_ok(amod) && dw_w && bn_scale && bn_shift,
+               "lfsr_sa_modulate: null/invalid tensor");
+  LFSR_REQUIRE(out->n == x->n && out->h == x->h && out->w == x->w && out->c == x->c, "lfsr_sa_modulate: out shape");
+  LFSR_REQUIRE(amod->n == x->n && amod->c == x->c && x->h % amod->h == 0 && x->w % amod->w == 0,
+               "lfsr_sa_modulate: amod shape");
+  TView r = null_view();
+  if (res && res->ptr) {
+    LFSR_REQUIRE(res->n == x->n && res->h == x->h && res->w == x->w && res->c == x->c, "lfsr_sa_modulate: res shape");
+    r = view_of(res);
+  }
+  long long total = (long long)x->n * x->h * x->w * x->c;
+  sa_modulate_kernel<<<(int)capped_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+      view_of(x), dw_w, bn_scale, bn_shift, view_of(amod), w0, w1, r, view_of(out), dil, total);
+  return check_launch("sa_modulate_kernel");
+}
+
+extern "C" int lfsr_layernorm(const lfsr_tensor* in, const float* gamma, const float* beta, float eps,
+                              const lfsr_tensor* out, void* stream) {
+  LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && gamma && beta, "lfsr_layernorm: null/invalid tensor");
+  LFSR_REQUIRE(in->n == out->n && in->h == out->h && in->w == out->w && in->c == out->c, "lfsr_layernorm: shape");
+  long long tokens = (long long)in->n * in->h * in->w;
+  long long blocks = (tokens + 7) / 8;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  layernorm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(view_of(in), view_of(out), gamma, beta, eps, tokens);
+  return check_launch("layernorm_kernel");
+}
+
+extern "C" int lfsr_epi_attention(const float* qk, const float* v, float* out, const lfsr_epi_attn_desc* d,
+                                  void* stream) {
+  LFSR_REQUIRE(qk && v && out && d, "lfsr_epi_attention: null pointer");
+  LFSR_REQUIRE(d->head_dim == ATT_D, "lfsr_epi_attention: head_dim %d unsupported (16 only)", d->head_dim);
+  LFSR_REQUIRE(d->heads > 0 && d->A > 0 && d->S > 0 && d->half_window >= 0 && d->nb > 0 && d->np > 0 && d->nq > 0,
+               "lfsr_epi_attention: bad geometry");
+  const int L = d->A * d->S;
+  LFSR_REQUIRE(L <= 192, "lfsr_epi_attention: sequence length %d > 192", L);
+  LFSR_REQUIRE(((uintptr_t)qk % 16 == 0) && ((uintptr_t)v % 16 == 0) && ((uintptr_t)out % 16 == 0),
+               "lfsr_epi_attention: pointers must be 16-byte aligned");
+  dim3 grid(d->nb * d->np * d->nq, d->heads);
+  size_t smem = (size_t)2 * L * ATT_LD * sizeof(float);
+  epi_attention_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(qk, v, out, *d);
+  return check_launch("epi_attention_kernel");
+}
+
+extern "C" int lfsr_metric_sums(const float* label, const float* out, int ang, int h, int w, double* acc,
+                                void* stream) {
+  LFSR_REQUIRE(label && out && acc, "lfsr_metric_sums: null pointer");
+  LFSR_REQUIRE(ang > 0 && h >= 11 && w >= 11, "lfsr_metric_sums: views must be at least 11x11 (skimage win_size)");
+  // scipy.ndimage._gaussian_kernel1d(sigma=1.5, order=0, radius=5): float64 weights, cast to fp32
+  Gauss11 gw;
+  {
+    double g[11], s = 0.0;
+    for (int i = -5; i <= 5; ++i) { g[i + 5] = exp(-0.5 / (1.5 * 1.5) * (double)(i * i)); s += g[i + 5]; }
+    for (int i = 0; i < 11; ++i) gw.g[i] = (float)(g[i] / s);
+  }
+  const int tiles_x = ceil_div(w, MT_W), tiles_y = ceil_div(h, MT_H);
+  metric_kernel<<<ang * ang * tiles_x * tiles_y, 256, 0, (cudaStream_t)stream>>>(label, out, ang, h, w, acc, tiles_x,
+                                                                                 tiles_y, gw);
+  return check_launch("metric_kernel");
+}

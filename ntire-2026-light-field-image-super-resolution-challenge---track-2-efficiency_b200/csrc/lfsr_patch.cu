@@ -1,0 +1,150 @@
+// LFdivide / LFintegrate gather kernels (reference: utils/utils.py:137-178, train.py:300-319).
+// Pure index permutations -> bit-exact by construction. HBM-bound: every output float is written
+// once with 128-bit stores; source reads are contiguous (or mirrored-contiguous) 32-float runs.
+#include <stdarg.h>
+#include "lfsr_common.cuh"
+
+namespace lfsr {
+
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// symmetric (edge-repeating) mirror used by ImageExtend (utils/utils.py:137-149)
+__device__ __forceinline__ int mirror(int i, int n) { return i < 0 ? -i - 1 : (i >= n ? 2 * n - 1 - i : i); }
+
+// one thread = 4 consecutive x of one patch row (same view because P % 4 == 0)
+__global__ void __launch_bounds__(256)
+divide_kernel(const float* __restrict__ scene, float* __restrict__ patches, int A, int h0, int w0, int P,
+              int S, int bdr, int numV, int u_begin, long long total4) {
+  const int row = A * P;            // floats per patch row
+  const int row4 = row >> 2;
+  const int sw = A * w0;            // scene row stride
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total4;
+       t += (long long)gridDim.x * blockDim.x) {
+    int x4 = (int)(t % row4);
+    long long r = t / row4;
+    int py = (int)(r % row);
+    long long pidx = r / row;       // patch index within the shard
+    int n2 = (int)(pidx % numV);
+    int n1 = (int)(pidx / numV) + u_begin;
+    int a1 = py / P, y = py - a1 * P;
+    int px = x4 << 2;
+    int a2 = px / P, x = px - a2 * P;
+    int sy = mirror(n1 * S + y - bdr, h0);
+    const float* src = scene + (size_t)(a1 * h0 + sy) * sw + a2 * w0;
+    int gx = n2 * S + x - bdr;
+    float4 v;
+    v.x = __ldg(src + mirror(gx, w0));
+    v.y = __ldg(src + mirror(gx + 1, w0));
+    v.z = __ldg(src + mirror(gx + 2, w0));
+    v.w = __ldg(src + mirror(gx + 3, w0));
+    reinterpret_cast<float4*>(patches)[t] = v;
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+integrate_kernel(const float* __restrict__ patches, float* __restrict__ out, int A, int pz, int ss, int h,
+                 int w, int numV, int u_begin, int y_begin, int y_count, long long total) {
+  const int wv = w / VEC;           // vectors per view row
+  const int bdr = (pz - ss) / 2;
+  const size_t prow = (size_t)A * pz;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    int xv = (int)(t % wv);
+    long long r = t / wv;
+    int a2 = (int)(r % A); r /= A;
+    int yl = (int)(r % y_count);
+    int a1 = (int)(r / y_count);
+    int Y = y_begin + yl, X = xv * VEC;
+    int n1 = Y / ss, n2 = X / ss;
+    const float* src = patches + ((size_t)(n1 - u_begin) * numV + n2) * prow * prow +
+                       (size_t)(a1 * pz + bdr + (Y - n1 * ss)) * prow + a2 * pz + bdr + (X - n2 * ss);
+    float* dst = out + (size_t)(a1 * h + Y) * ((size_t)A * w) + (size_t)a2 * w + X;
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(src));
+    } else {
+      *dst = __ldg(src);
+    }
+  }
+}
+
+static int grid_for(long long work_items, int block) {
+  long long blocks = (work_items + block - 1) / block;
+  const long long cap = 148LL * 16;  // 16 resident CTAs of 256 threads worth of waves per SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace lfsr
+
+using namespace lfsr;
+
+extern "C" const char* lfsr_last_error(void) { return g_err; }
+extern "C" int lfsr_abi_version(void) { return LFSR_ABI_VERSION; }
+extern "C" int lfsr_built_for_sm100a(void) { return 1; }
+extern "C" uint64_t lfsr_launch_count(void) { return g_launches.load(); }
+
+extern "C" int lfsr_divide_rows(const float* scene, float* patches, int ang, int h0, int w0, int patch,
+                                int stride, int u_begin, int u_end, void* stream) {
+  LFSR_REQUIRE(scene && patches, "lfsr_divide: null pointer");
+  LFSR_REQUIRE(ang > 0 && h0 > 0 && w0 > 0 && patch > 0 && stride > 0 && patch >= stride,
+               "lfsr_divide: bad geometry A=%d h0=%d w0=%d P=%d S=%d", ang, h0, w0, patch, stride);
+  LFSR_REQUIRE(patch % 4 == 0, "lfsr_divide: patch size %d must be a multiple of 4", patch);
+  const int bdr = (patch - stride) / 2;
+  // ImageExtend only mirrors one image period on each side (utils/utils.py:141-147)
+  LFSR_REQUIRE(h0 >= bdr + stride - 1 && w0 >= bdr + stride - 1 && h0 >= bdr && w0 >= bdr,
+               "lfsr_divide: view %dx%d smaller than the mirror border %d", h0, w0, bdr + stride - 1);
+  const int numU = (h0 + 2 * bdr - 1) / stride, numV = (w0 + 2 * bdr - 1) / stride;
+  LFSR_REQUIRE(numU > 0 && numV > 0, "lfsr_divide: view too small for one patch");
+  LFSR_REQUIRE(0 <= u_begin && u_begin <= u_end && u_end <= numU, "lfsr_divide: row shard [%d,%d) outside [0,%d)",
+               u_begin, u_end, numU);
+  if (u_begin == u_end) return LFSR_OK;
+  const long long total4 = (long long)(u_end - u_begin) * numV * (ang * patch) * (ang * patch / 4);
+  divide_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(scene, patches, ang, h0, w0, patch, stride,
+                                                                           bdr, numV, u_begin, total4);
+  return check_launch("divide_kernel");
+}
+
+extern "C" int lfsr_divide(const float* scene, float* patches, int ang, int h0, int w0, int patch, int stride,
+                           void* stream) {
+  if (patch < stride || stride <= 0) { set_error("lfsr_divide: bad patch/stride"); return LFSR_ERR_INVALID; }
+  const int bdr = (patch - stride) / 2;
+  const int numU = (h0 + 2 * bdr - 1) / stride;
+  return lfsr_divide_rows(scene, patches, ang, h0, w0, patch, stride, 0, numU, stream);
+}
+
+extern "C" int lfsr_integrate_rows(const float* patches, float* out, int ang, int pz, int stride, int h, int w,
+                                   int num_u, int num_v, int u_begin, int u_end, void* stream) {
+  LFSR_REQUIRE(patches && out, "lfsr_integrate: null pointer");
+  LFSR_REQUIRE(ang > 0 && pz >= stride && stride > 0 && h > 0 && w > 0, "lfsr_integrate: bad geometry");
+  LFSR_REQUIRE(h <= num_u * stride && w <= num_v * stride,
+               "lfsr_integrate: output %dx%d larger than the stitched grid %dx%d", h, w, num_u * stride,
+               num_v * stride);
+  LFSR_REQUIRE(0 <= u_begin && u_begin <= u_end && u_end <= num_u, "lfsr_integrate: bad row shard");
+  int y_begin = u_begin * stride;
+  int y_end = u_end * stride < h ? u_end * stride : h;
+  if (y_end <= y_begin) return LFSR_OK;
+  const int y_count = y_end - y_begin;
+  const int bdr = (pz - stride) / 2;
+  const bool vec = (w % 4 == 0) && (stride % 4 == 0) && (pz % 4 == 0) && (bdr % 4 == 0) &&
+                   ((uintptr_t)patches % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  if (vec) {
+    long long total = (long long)ang * y_count * ang * (w / 4);
+    integrate_kernel<4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        patches, out, ang, pz, stride, h, w, num_v, u_begin, y_begin, y_count, total);
+  } else {
+    long long total = (long long)ang * y_count * ang * w;
+    integrate_kernel<1><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        patches, out, ang, pz, stride, h, w, num_v, u_begin, y_begin, y_count, total);
+  }
+  return check_launch("integrate_kernel");
+}

@@ -1,0 +1,188 @@
+"""Host-side launchers: torch tensors -> raw pointers -> C ABI (include/lfsr.h).
+
+Feature tensors are fp32 NHWC *views*: ``t[n, y, x, c]`` with ``stride(3) == 1`` and dense rows,
+so a channel slice ``buf[..., a:b]`` of a wider buffer is a valid operand (torch.cat/torch.split
+of the reference become pointer arithmetic). ``CudaOps`` is the only product backend; it raises
+when the tensors are not on a CUDA device. (tests/opref.py implements the same op contracts in
+plain torch to check each kernel and, on CPU, the layer graphs.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+
+def ld_for(c: int) -> int:
+    """pixel stride (floats) for a c-channel buffer: 16-byte aligned rows for float4 / TMA."""
+    return c if c == 1 else (c + 3) // 4 * 4
+
+
+def alloc_nhwc(n: int, h: int, w: int, c: int, device, zero: bool = False) -> torch.Tensor:
+    ld = ld_for(c)
+    buf = (torch.zeros if zero else torch.empty)((n, h, w, ld), dtype=torch.float32, device=device)
+    return buf[..., :c] if ld != c else buf
+
+
+def as_tensor(t: torch.Tensor, what: str = "tensor") -> N.Tensor:
+    """Describe a 4-D fp32 NHWC view to the C ABI; rows must be dense with pixel stride ld = stride(2)."""
+    if t.dtype != torch.float32 or t.dim() != 4:
+        raise N.LfsrError(f"{what}: expected a 4-D float32 NHWC view, got {tuple(t.shape)} {t.dtype}")
+    n, h, w, c = t.shape
+    s = t.stride()
+    ld = s[2]
+    ok = (c == 1 or s[3] == 1) and ld >= c and (h == 1 or s[1] == w * ld) and (n == 1 or s[0] == h * w * ld)
+    if not ok:
+        raise N.LfsrError(f"{what}: not a dense-row NHWC view (shape {tuple(t.shape)}, strides {s})")
+    return N.Tensor(t.data_ptr(), n, h, w, c, ld)
+
+
+_NULL_T = N.Tensor(None, 0, 0, 0, 0, 0)
+
+
+@dataclass
+class PackedConv:
+    """One convolution's constants, packed once per weight version.
+
+    w_f32: [kh*kw*cin, cout] fp32 (tap-major, cout fastest) for lfsr_conv2d_f32.
+    w_tc : TMA/UMMA-friendly packing for lfsr_conv2d_tc, or None when the layer stays on CUDA cores.
+    """
+    w_f32: torch.Tensor
+    bias: Optional[torch.Tensor]
+    kh: int
+    kw: int
+    cin: int
+    cout: int
+    stride: Tuple[int, int] = (1, 1)
+    dil: Tuple[int, int] = (1, 1)
+    pad: Tuple[int, int] = (0, 0)
+    w_tc: Optional[torch.Tensor] = None
+
+
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride=(1, 1), dil=(1, 1), pad=(0, 0),
+              device=None, tc: bool = False) -> PackedConv:
+    """weight is torch-layout [cout, cin, kh, kw] (any device); returns device-resident packing."""
+    w = weight.detach().to(torch.float32)
+    cout, cin, kh, kw = w.shape
+    dev = device if device is not None else w.device
+    w_f32 = w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous().to(dev)
+    b = None if bias is None else bias.detach().to(torch.float32).contiguous().to(dev)
+    w_tc = None
+    if tc:
+        lib = N.load()
+        nfl = lib.lfsr_conv2d_tc_packed_floats(kh, kw, cin, cout)
+        if nfl > 0:
+            src = w.contiguous().cpu()
+            dst = torch.empty(nfl, dtype=torch.float32)
+            N.check(lib.lfsr_pack_conv_tc(src.data_ptr(), dst.data_ptr(), kh, kw, cin, cout), "lfsr_pack_conv_tc")
+            w_tc = dst.to(dev)
+    return PackedConv(w_f32, b, kh, kw, cin, cout, tuple(stride), tuple(dil), tuple(pad), w_tc)
+
+
+class CudaOps:
+    """The product backend: every method enqueues sm_100a kernels on torch's current stream."""
+
+    name = "cuda"
+
+    def __init__(self, use_tc: bool = True):
+        self.lib = N.load()
+        self.use_tc = use_tc
+
+    # -- helpers ---------------------------------------------------------------------------
+    @staticmethod
+    def _stream(t: torch.Tensor) -> int:
+        if not t.is_cuda:
+            raise N.LfsrError("lfsr_b200 kernels need CUDA tensors; there is no CPU fallback")
+        return torch.cuda.current_stream(t.device).cuda_stream
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        return None if t is None else t.data_ptr()
+
+    # -- patch pipeline ----------------------------------------------------------------------
+    def divide_rows(self, scene, patches, ang, h0, w0, patch, stride, u0, u1):
+        N.check(self.lib.lfsr_divide_rows(scene.data_ptr(), patches.data_ptr(), ang, h0, w0, patch, stride, u0, u1,
+                                          self._stream(scene)), "lfsr_divide_rows")
+
+    def integrate_rows(self, patches, out, ang, pz, stride, h, w, num_u, num_v, u0, u1):
+        N.check(self.lib.lfsr_integrate_rows(patches.data_ptr(), out.data_ptr(), ang, pz, stride, h, w, num_u, num_v,
+                                             u0, u1, self._stream(out)), "lfsr_integrate_rows")
+
+    def interp(self, x, out, n, h, w, scale, mode, block_h, block_w):
+        N.check(self.lib.lfsr_interp(x.data_ptr(), out.data_ptr(), n, h, w, scale, mode, block_h, block_w,
+                                     self._stream(x)), "lfsr_interp")
+
+    # -- convolutions ---------------------------------------------------------------------------
+    def conv(self, x, pc: PackedConv, out, act=N.ACT_NONE, slope=0.0, alpha=1.0, mul=None, res=None, in_scale=None,
+             in_perm=0, out_perm=0, perm_a=0, shuffle=(1, 1, 0), block=(0, 0)):
+        d = N.ConvDesc()
+        d.kh, d.kw = pc.kh, pc.kw
+        d.stride_h, d.stride_w = pc.stride
+        d.dil_h, d.dil_w = pc.dil
+        d.pad_h, d.pad_w = pc.pad
+        d.in_perm, d.out_perm, d.perm_a = in_perm, out_perm, perm_a
+        d.shuf_ry, d.shuf_rx, d.shuf_mode = shuffle
+        d.block_h, d.block_w = block
+        d.act, d.act_slope, d.alpha = act, slope, alpha
+        d.bias = self._ptr(pc.bias)
+        d.in_scale = self._ptr(in_scale)
+        d.mul = as_tensor(mul, "conv.mul") if mul is not None else _NULL_T
+        d.res = as_tensor(res, "conv.res") if res is not None else _NULL_T
+        tin, tout = as_tensor(x, "conv.in"), as_tensor(out, "conv.out")
+        if x.shape[3] != pc.cin:
+            raise N.LfsrError(f"conv: input has {x.shape[3]} channels, weights expect {pc.cin}")
+        st = self._stream(x)
+        if (self.use_tc and pc.w_tc is not None and
+                self.lib.lfsr_conv2d_tc_supported(C.byref(tin), C.byref(tout), C.byref(d))):
+            N.check(self.lib.lfsr_conv2d_tc(C.byref(tin), pc.w_tc.data_ptr(), C.byref(tout), C.byref(d), st),
+                    "lfsr_conv2d_tc")
+        else:
+            N.check(self.lib.lfsr_conv2d_f32(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st),
+                    "lfsr_conv2d_f32")
+
+    def dwconv(self, x, w, out, kh, kw, dil=(1, 1), scale=None, shift=None, act=N.ACT_NONE, slope=0.0):
+        N.check(self.lib.lfsr_dwconv_f32(C.byref(as_tensor(x, "dwconv.in")), w.data_ptr(), self._ptr(scale),
+                                         self._ptr(shift), C.byref(as_tensor(out, "dwconv.out")), kh, kw, dil[0],
+                                         dil[1], act, slope, self._stream(x)), "lfsr_dwconv_f32")
+
+    # -- reductions / gates -------------------------------------------------------------------------
+    def block_mean(self, x, out, bh, bw):
+        N.check(self.lib.lfsr_block_mean(C.byref(as_tensor(x, "block_mean.in")), C.byref(as_tensor(out, "block_mean.out")),
+                                         bh, bw, self._stream(x)), "lfsr_block_mean")
+
+    def sa_modulate(self, x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil):
+        rt = as_tensor(res, "sa.res") if res is not None else _NULL_T
+        N.check(self.lib.lfsr_sa_modulate(C.byref(as_tensor(x, "sa.x")), dw_w.data_ptr(), bn_scale.data_ptr(),
+                                          bn_shift.data_ptr(), C.byref(as_tensor(amod, "sa.amod")), w0, w1, C.byref(rt),
+                                          C.byref(as_tensor(out, "sa.out")), dil, self._stream(x)), "lfsr_sa_modulate")
+
+    # -- EPIT token ops ------------------------------------------------------------------------------
+    def layernorm(self, x, gamma, beta, eps, out):
+        N.check(self.lib.lfsr_layernorm(C.byref(as_tensor(x, "ln.in")), gamma.data_ptr(), beta.data_ptr(), eps,
+                                        C.byref(as_tensor(out, "ln.out")), self._stream(x)), "lfsr_layernorm")
+
+    def epi_attention(self, qk, v, out, heads, head_dim, A, S, half_window, nb, np_, nq, stride_a, stride_s, stride_b,
+                      stride_p, stride_q):
+        d = N.EpiAttnDesc(heads, head_dim, A, S, half_window, nb, np_, nq, stride_a, stride_s, stride_b, stride_p,
+                          stride_q)
+        N.check(self.lib.lfsr_epi_attention(qk.data_ptr(), v.data_ptr(), out.data_ptr(), C.byref(d), self._stream(qk)),
+                "lfsr_epi_attention")
+
+    # -- metrics -----------------------------------------------------------------------------------------
+    def metric_sums(self, label, out, ang, h, w, acc):
+        N.check(self.lib.lfsr_metric_sums(label.data_ptr(), out.data_ptr(), ang, h, w, acc.data_ptr(),
+                                          self._stream(label)), "lfsr_metric_sums")
+
+
+_default_ops = None
+
+
+def default_ops() -> CudaOps:
+    global _default_ops
+    if _default_ops is None:
+        _default_ops = CudaOps()
+    return _default_ops

@@ -1,0 +1,126 @@
+"""Shared host logic of the drop-in `get_model(args)` modules.
+
+Every network keeps the reference's parameter tree (same state_dict keys and shapes, so reference
+``.pth`` files load and ``net.apply(weights_init)`` works) but never calls those leaf modules: the
+forward packs the weights once per weight version (BatchNorm folded, RepConv branches merged,
+tap-major layouts) and enqueues the sm_100a kernels of liblfsr_b200 on torch's current stream.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+from .. import kernels as K
+
+
+def slots(mods: Dict[int, nn.Module]) -> nn.ModuleDict:
+    """nn.Sequential-compatible key layout ("0", "2", ...) without placeholder modules."""
+    return nn.ModuleDict({str(i): m for i, m in mods.items()})
+
+
+def bn_affine(bn: nn.BatchNorm2d):
+    """eval-mode BatchNorm as y = x*scale + shift."""
+    scale = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
+    shift = bn.bias.detach() - bn.running_mean.detach() * scale
+    return scale, shift
+
+
+class LFNetBase(nn.Module):
+    """forward(x[B,1,A*h,A*w] float32 cuda, info=None) -> [B,1,A*h*s,A*w*s] (train.py:291-313)."""
+
+    #: channel layouts, tensor-core eligibility etc. are decided per subclass in _pack / _run
+    def __init__(self, args):
+        super().__init__()
+        self.angRes = int(args.angRes_in)
+        self.scale = int(args.scale_factor)
+        self._ops = None
+        self._packed = None
+        self._packed_key = None
+        self._arena: Dict[tuple, torch.Tensor] = {}
+
+    # -- backend ---------------------------------------------------------------------------------
+    def set_backend(self, ops) -> None:
+        """Tests inject tests/opref.RefOps here; the product default is kernels.CudaOps."""
+        self._ops = ops
+        self._packed = None
+
+    def _backend(self, x: torch.Tensor):
+        if self._ops is not None:
+            return self._ops
+        if not x.is_cuda:
+            raise N.LfsrError(
+                f"{type(self).__module__}: input is on {x.device}; this implementation only runs on a CUDA "
+                "(sm_100a) device and has no CPU fallback")
+        return K.default_ops()
+
+    # -- weight packing cache ----------------------------------------------------------------------
+    def _fingerprint(self, device):
+        key = [str(device)]
+        for t in list(self.parameters()) + list(self.buffers()):
+            key.append((t.data_ptr(), t._version))
+        return tuple(key)
+
+    def _get_packed(self, device, ops):
+        key = self._fingerprint(device)
+        if self._packed is None or key != self._packed_key:
+            with torch.no_grad():
+                self._packed = self._pack(device, ops)
+            self._packed_key = key
+        return self._packed
+
+    def _pack(self, device, ops):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def _run(self, ops, pk, x, out):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    # -- workspace arena --------------------------------------------------------------------------
+    def _buf(self, name: str, n: int, h: int, w: int, c: int, device) -> torch.Tensor:
+        key = (name, n, h, w, c, str(device))
+        t = self._arena.get(key)
+        if t is None:
+            t = K.alloc_nhwc(n, h, w, c, device, zero=True)
+            self._arena[key] = t
+        return t
+
+    def release_workspace(self) -> None:
+        self._arena.clear()
+
+    def _apply(self, fn, *a, **kw):  # .to()/.cpu()/.cuda(): packed weights and arena are stale
+        self._packed = None
+        self._arena = {}
+        return super()._apply(fn, *a, **kw)
+
+    # -- forward -------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, info=None) -> torch.Tensor:
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise ValueError(f"expected a [B,1,A*h,A*w] Y-channel SAI mosaic, got {tuple(x.shape)}")
+        if x.dtype != torch.float32:
+            raise ValueError(f"expected float32 input, got {x.dtype}")
+        A = self.angRes
+        B, _, H, W = x.shape
+        if H % A or W % A:
+            raise ValueError(f"mosaic {H}x{W} is not divisible by angRes={A}")
+        ops = self._backend(x)
+        pk = self._get_packed(x.device, ops)
+        x = x.contiguous()
+        out = torch.empty((B, 1, H * self.scale, W * self.scale), dtype=torch.float32, device=x.device)
+        with torch.no_grad():
+            self._run(ops, pk, x, out)
+        return out
+
+
+class L1Loss(nn.Module):
+    """get_loss(args) of EPIT/DistgSSR/LF_InterNet (e.g. DistgSSR.py:158-166): plain L1."""
+
+    def __init__(self, args=None):
+        super().__init__()
+        self.criterion_Loss = nn.L1Loss()
+
+    def forward(self, SR, HR, criterion_data=None):
+        if isinstance(SR, dict):
+            SR = SR["SR"]
+        return self.criterion_Loss(SR, HR)

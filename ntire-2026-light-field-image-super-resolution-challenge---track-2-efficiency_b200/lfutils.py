@@ -1,0 +1,110 @@
+"""Device-side mirrors of the reference's patch-pipeline functions (utils/utils.py:91-178).
+
+Same names, argument meaning and return layouts as the reference so `train.test()` /
+`inference.test()` run unchanged; the arithmetic runs in liblfsr_b200 kernels on the GPU. Tensors
+that arrive on the host (the reference keeps `subLFout`, `Hr_SAI_y` on the CPU, train.py:303,322)
+are staged to the current CUDA device and the result is returned on the caller's device. There is
+no CPU implementation behind these functions.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import kernels as K
+
+
+def _device_for(t: torch.Tensor) -> torch.device:
+    if t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise N.LfsrError("lfsr_b200 needs a CUDA device (sm_100a); there is no CPU fallback for this path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def divide_geometry(h0: int, w0: int, patch_size: int, stride: int):
+    bdr = (patch_size - stride) // 2
+    return bdr, (h0 + bdr * 2 - 1) // stride, (w0 + bdr * 2 - 1) // stride
+
+
+def LFdivide(data: torch.Tensor, angRes: int, patch_size: int, stride: int, rows=None, ops=None) -> torch.Tensor:
+    """data [(a1 h0), (a2 w0)] -> subLF [numU, numV, a1*P, a2*P]  (utils/utils.py:152-166).
+    rows=(u0,u1) returns only that band of the patch grid (multi-GPU scene sharding)."""
+    if data.dim() != 2:
+        raise ValueError(f"LFdivide expects a 2-D SAI mosaic, got {tuple(data.shape)}")
+    ops = ops or K.default_ops()
+    dev = _device_for(data)
+    src = data.to(device=dev, dtype=torch.float32).contiguous()
+    H, W = src.shape
+    h0, w0 = H // angRes, W // angRes
+    _, num_u, num_v = divide_geometry(h0, w0, patch_size, stride)
+    u0, u1 = (0, num_u) if rows is None else rows
+    sub = torch.empty((u1 - u0, num_v, angRes * patch_size, angRes * patch_size), dtype=torch.float32, device=dev)
+    ops.divide_rows(src, sub, angRes, h0, w0, patch_size, stride, u0, u1)
+    return sub if data.is_cuda else sub.to(data.device)
+
+
+def LFintegrate(subLF: torch.Tensor, angRes: int, pz: int, stride: int, h: int, w: int, ops=None) -> torch.Tensor:
+    """subLF [n1, n2, a1*pz, a2*pz] (or 6-D n1 n2 a1 a2 pz pz) -> outLF [a1, a2, h, w]
+    (utils/utils.py:169-178). The result is a view of the stitched SAI mosaic, so the reference's
+    following 'a1 a2 h w -> 1 1 (a1 h) (a2 w)' rearrange (train.py:319) is a cheap copy."""
+    ops = ops or K.default_ops()
+    dev = _device_for(subLF)
+    sub = subLF.to(device=dev, dtype=torch.float32)
+    if sub.dim() == 6:
+        n1, n2, a1, a2, ph, pw = sub.shape
+        sub = sub.permute(0, 1, 2, 4, 3, 5).reshape(n1, n2, a1 * ph, a2 * pw)
+    if sub.dim() != 4:
+        raise ValueError(f"LFintegrate expects a 4-D or 6-D tensor, got {tuple(subLF.shape)}")
+    sub = sub.contiguous()
+    n1, n2 = sub.shape[:2]
+    mosaic = torch.empty((angRes * h, angRes * w), dtype=torch.float32, device=dev)
+    ops.integrate_rows(sub, mosaic, angRes, pz, stride, h, w, n1, n2, 0, n1)
+    out = mosaic.view(angRes, h, angRes, w).permute(0, 2, 1, 3)
+    return out if subLF.is_cuda else out.to(subLF.device)
+
+
+def metric_views(label_sai: torch.Tensor, out_sai: torch.Tensor, angRes: int, ops=None):
+    """per-view PSNR / SSIM of two SAI mosaics [(a1 h), (a2 w)] -> float32 arrays [A, A]."""
+    ops = ops or K.default_ops()
+    dev = _device_for(out_sai if out_sai.is_cuda else label_sai)
+    la = label_sai.to(device=dev, dtype=torch.float32).contiguous()
+    ou = out_sai.to(device=dev, dtype=torch.float32).contiguous()
+    H, W = la.shape
+    h, w = H // angRes, W // angRes
+    acc = torch.zeros(2 * angRes * angRes, dtype=torch.float64, device=dev)
+    ops.metric_sums(la, ou, angRes, h, w, acc)
+    a = acc.cpu().numpy().reshape(angRes, angRes, 2)
+    mse = a[..., 0] / float(h * w)
+    with np.errstate(divide="ignore"):
+        psnr = (10.0 * np.log10(1.0 / mse)).astype(np.float32)
+    ssim = (a[..., 1] / float((h - 10) * (w - 10))).astype(np.float32)
+    return psnr, ssim
+
+
+def cal_metrics(args, label: torch.Tensor, out: torch.Tensor, ops=None):
+    """(PSNR_mean, SSIM_mean) over views with value > 0 (utils/utils.py:91-134, SR task)."""
+    if getattr(args, "task", "SR") != "SR":
+        raise N.LfsrError("cal_metrics: only the SR task is on the accelerated path")
+    A = int(args.angRes_in)
+    if label.dim() == 5:                       # [B, C, U, V?...] -> the reference permutes (0,1,3,2,4) and unsqueezes
+        label = label.permute((0, 1, 3, 2, 4)).unsqueeze(0)
+        out = out.permute((0, 1, 3, 2, 4)).unsqueeze(0)
+    if label.dim() == 6:                       # B C U h V w -> mosaic
+        B, C, U, h, V, w = label.shape
+        label = label.reshape(B, C, U * h, V * w)
+        out = out.reshape(B, C, U * h, V * w)
+        A = U
+    if label.dim() != 4:
+        raise ValueError(f"cal_metrics: unsupported label shape {tuple(label.shape)}")
+    B = label.shape[0]
+    PSNR = np.zeros((B, A, A), dtype="float32")
+    SSIM = np.zeros((B, A, A), dtype="float32")
+    for b in range(B):
+        PSNR[b], SSIM[b] = metric_views(label[b, 0], out[b, 0], A, ops)
+    valid_psnr = np.sum(PSNR > 0)
+    psnr_mean = PSNR.sum() / valid_psnr if valid_psnr > 0 else 0.0
+    valid_ssim = np.sum(SSIM > 0)
+    ssim_mean = SSIM.sum() / valid_ssim if valid_ssim > 0 else 0.0
+    return psnr_mean, ssim_mean

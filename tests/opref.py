@@ -1,0 +1,159 @@
+"""Plain-torch fp32 statement of every kernel contract in include/lfsr.h (test infrastructure).
+
+`RefOps` has the same methods as lfsr_b200.kernels.CudaOps. It is used (a) on the GPU as the
+per-kernel reference each CUDA kernel is compared with, and (b) on CPU, injected through
+`net.set_backend(RefOps())`, to check the host-side launch plans (weight folding, buffer slicing,
+fused epilogue wiring) against the oracle without a GPU. It is never reachable from the product
+path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from einops import rearrange
+
+from oracle import lf_oracle
+
+
+def _act(y, act, slope):
+    if act == 1:
+        return F.relu(y)
+    if act == 2:
+        return F.leaky_relu(y, slope)
+    if act == 3:
+        return torch.sigmoid(y)
+    return y
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+class RefOps:
+    name = "torch-ref"
+
+    # -- patch pipeline ---------------------------------------------------------------------------
+    def divide_rows(self, scene, patches, ang, h0, w0, patch, stride, u0, u1):
+        sub = lf_oracle.lfdivide(scene.detach().cpu().numpy().reshape(ang * h0, ang * w0), ang, patch, stride)
+        sel = torch.from_numpy(sub[u0:u1].reshape(-1)).to(patches.device)
+        patches.view(-1)[: sel.numel()].copy_(sel)
+
+    def integrate_rows(self, patches, out, ang, pz, stride, h, w, num_u, num_v, u0, u1):
+        sub = patches.detach().cpu().numpy().reshape(-1)[: (u1 - u0) * num_v * (ang * pz) ** 2]
+        sub = sub.reshape(u1 - u0, num_v, ang * pz, ang * pz)
+        y0, y1 = u0 * stride, min(u1 * stride, h)
+        if y1 <= y0:
+            return
+        part = lf_oracle.lfintegrate(sub, ang, pz, stride, y1 - y0, w)         # [a1,a2,rows,w]
+        o = out.view(ang, h, ang, w)
+        o[:, y0:y1, :, :] = torch.from_numpy(part).permute(0, 2, 1, 3).to(out.device)
+
+    def interp(self, x, out, n, h, w, scale, mode, block_h, block_w):
+        m = "bicubic" if mode == 0 else "bilinear"
+        xi = x.reshape(n, 1, h // block_h, block_h, w // block_w, block_w)
+        xi = rearrange(xi, "n c a h b w -> (n a b) c h w")
+        y = F.interpolate(xi, scale_factor=scale, mode=m, align_corners=False)
+        y = rearrange(y, "(n a b) c h w -> n c (a h) (b w)", n=n, a=h // block_h, b=w // block_w)
+        out.view(n, 1, h * scale, w * scale).copy_(y)
+
+    # -- convolutions ------------------------------------------------------------------------------
+    def conv(self, x, pc, out, act=0, slope=0.0, alpha=1.0, mul=None, res=None, in_scale=None, in_perm=0, out_perm=0,
+             perm_a=0, shuffle=(1, 1, 0), block=(0, 0)):
+        n = x.shape[0]
+        xi = _nchw(x)
+        if in_perm:
+            xi = rearrange(xi, "b c (u h) (v w) -> b c (h u) (w v)", u=perm_a, v=perm_a)
+        if in_scale is not None:
+            xi = xi * in_scale.reshape(n, pc.cin, 1, 1)
+        w = pc.w_f32.view(pc.kh, pc.kw, pc.cin, pc.cout).permute(3, 2, 0, 1)
+        if block[0] > 0 or block[1] > 0:
+            bh = block[0] if block[0] > 0 else xi.shape[2]
+            bw = block[1] if block[1] > 0 else xi.shape[3]
+            a, b = xi.shape[2] // bh, xi.shape[3] // bw
+            xb = rearrange(xi, "n c (a h) (b w) -> (n a b) c h w", a=a, b=b)
+            y = F.conv2d(xb, w, pc.bias, pc.stride, pc.pad, pc.dil)
+            y = rearrange(y, "(n a b) c h w -> n c (a h) (b w)", n=n, a=a, b=b)
+        else:
+            y = F.conv2d(xi, w, pc.bias, pc.stride, pc.pad, pc.dil)
+        y = _act(y, act, slope)
+        if mul is not None:
+            y = y * _nchw(mul)
+        y = y * alpha
+        if out_perm:
+            y = rearrange(y, "b c (h u) (w v) -> b c (u h) (v w)", u=perm_a, v=perm_a)
+        ry, rx, mode = shuffle
+        if ry * rx > 1:
+            b_, c_, h_, w_ = y.shape
+            cq = c_ // (ry * rx)
+            if mode == 0:
+                y = y.reshape(b_, cq, ry, rx, h_, w_).permute(0, 1, 4, 2, 5, 3)
+            else:
+                y = y.reshape(b_, ry, rx, cq, h_, w_).permute(0, 3, 4, 1, 5, 2)
+            y = y.reshape(b_, cq, h_ * ry, w_ * rx)
+        if res is not None:
+            y = y + _nchw(res)
+        out.copy_(y.permute(0, 2, 3, 1))
+
+    def dwconv(self, x, w, out, kh, kw, dil=(1, 1), scale=None, shift=None, act=0, slope=0.0):
+        c = x.shape[3]
+        wt = w.t().reshape(c, 1, kh, kw)
+        y = F.conv2d(_nchw(x), wt, None, 1, ((kh // 2) * dil[0], (kw // 2) * dil[1]), dil, c)
+        if scale is not None:
+            y = y * scale.view(1, c, 1, 1) + shift.view(1, c, 1, 1)
+        out.copy_(_act(y, act, slope).permute(0, 2, 3, 1))
+
+    # -- reductions / gates --------------------------------------------------------------------------
+    def block_mean(self, x, out, bh, bw):
+        n, h, w, c = x.shape
+        out.copy_(x.reshape(n, h // bh, bh, w // bw, bw, c).mean(dim=(2, 4)))
+
+    def sa_modulate(self, x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil):
+        n, h, w, c = x.shape
+        xi = _nchw(x)
+        s = F.conv2d(xi, dw_w.t().reshape(c, 1, 3, 3), None, 1, dil, dil, c)
+        s = torch.sigmoid(s * bn_scale.view(1, c, 1, 1) + bn_shift.view(1, c, 1, 1))
+        a = F.interpolate(_nchw(amod), size=(h, w), mode="nearest")
+        y = xi * (w0 * s + w1 * a)
+        if res is not None:
+            y = y + _nchw(res)
+        out.copy_(y.permute(0, 2, 3, 1))
+
+    # -- EPIT token ops ---------------------------------------------------------------------------------
+    def layernorm(self, x, gamma, beta, eps, out):
+        out.copy_(F.layer_norm(x, (x.shape[3],), gamma, beta, eps))
+
+    def epi_attention(self, qk, v, out, heads, head_dim, A, S, half_window, nb, np_, nq, stride_a, stride_s, stride_b,
+                      stride_p, stride_q):
+        E = heads * head_dim
+        dev = qk.device
+        b = torch.arange(nb, device=dev).view(nb, 1, 1, 1, 1) * stride_b
+        p = torch.arange(np_, device=dev).view(1, np_, 1, 1, 1) * stride_p
+        q = torch.arange(nq, device=dev).view(1, 1, nq, 1, 1) * stride_q
+        a = torch.arange(A, device=dev).view(1, 1, 1, A, 1) * stride_a
+        s = torch.arange(S, device=dev).view(1, 1, 1, 1, S) * stride_s
+        idx = (b + p + q + a + s).reshape(-1, A * S)                     # [nseq, L]
+        qkf = qk.reshape(-1, 2 * E)
+        vf = v.reshape(-1, E)
+        Q = qkf[idx][..., :E].reshape(-1, A * S, heads, head_dim).transpose(1, 2)
+        Kt = qkf[idx][..., E:].reshape(-1, A * S, heads, head_dim).transpose(1, 2)
+        V = vf[idx].reshape(-1, A * S, heads, head_dim).transpose(1, 2)
+        spos = torch.arange(S, device=dev).repeat(A)
+        allowed = (spos[:, None] - spos[None, :]).abs() <= half_window
+        scores = (Q * head_dim ** -0.5) @ Kt.transpose(-1, -2)
+        scores = scores.masked_fill(~allowed, float("-inf"))
+        o = torch.softmax(scores, dim=-1) @ V                              # [nseq, heads, L, d]
+        o = o.transpose(1, 2).reshape(-1, A * S, E)
+        out.reshape(-1, E)[idx.reshape(-1)] = o.reshape(-1, E)
+
+    # -- metrics ---------------------------------------------------------------------------------------
+    def metric_sums(self, label, out, ang, h, w, acc):
+        la = label.detach().cpu().numpy().reshape(ang, h, ang, w)
+        ou = out.detach().cpu().numpy().reshape(ang, h, ang, w)
+        res = np.zeros((ang * ang, 2))
+        for u in range(ang):
+            for v in range(ang):
+                a, b = la[u, :, v, :], ou[u, :, v, :]
+                res[u * ang + v, 0] = ((a.astype(np.float64) - b.astype(np.float64)) ** 2).sum()
+                res[u * ang + v, 1] = lf_oracle.ssim_view(a, b) * (h - 10) * (w - 10)
+        acc.copy_(acc + torch.from_numpy(res.reshape(-1)).to(acc.device))

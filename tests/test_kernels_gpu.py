@@ -1,0 +1,252 @@
+"""GPU parity of every C-ABI kernel against the torch statement of its contract (tests/opref.py)
+and, for the bit-exact ones, against the numpy oracle and the committed reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+import lfsr_b200
+from lfsr_b200 import kernels as K
+from lfsr_b200 import _native as N
+from opref import RefOps
+from oracle import lf_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    return K.CudaOps(use_tc=False)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return RefOps()
+
+
+def rnd(*shape, seed=0, lo=-1.0, hi=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(*shape, generator=g) * (hi - lo) + lo).to(DEV)
+
+
+def nhwc(n, h, w, c, seed=0, ld=None):
+    ld = ld or K.ld_for(c)
+    return rnd(n, h, w, ld, seed=seed)[..., :c]
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("h0,w0", [(32, 32), (47, 61), (64, 40), (125, 125), (108, 156)])
+def test_divide_integrate_bit_exact(ops, h0, w0):
+    A, P, S, s = 5, 32, 16, 2
+    scene = np.random.RandomState(h0 * 1000 + w0).random_sample((A * h0, A * w0)).astype(np.float32)
+    want = lf_oracle.lfdivide(scene, A, P, S)
+    got = lfsr_b200.lfutils.LFdivide(torch.from_numpy(scene).to(DEV), A, P, S)
+    assert got.shape == want.shape
+    assert np.array_equal(got.cpu().numpy(), want)
+    # integrate on nearest-upsampled patches: integrate(up(divide(x))) == up(x)  
+    up = got.view(*got.shape[:2], A, P, 1, A, P, 1).expand(-1, -1, -1, -1, s, -1, -1, s).reshape(
+        got.shape[0], got.shape[1], A * P * s, A * P * s).contiguous()
+    lf = lfsr_b200.lfutils.LFintegrate(up, A, P * s, S * s, h0 * s, w0 * s)
+    want_i = lf_oracle.lfintegrate(up.cpu().numpy(), A, P * s, S * s, h0 * s, w0 * s)
+    assert np.array_equal(lf.cpu().numpy(), want_i)
+    views = scene.reshape(A, h0, A, w0).transpose(0, 2, 1, 3)
+    assert np.array_equal(want_i, np.repeat(np.repeat(views, s, axis=2), s, axis=3))
+
+
+def test_divide_integrate_goldens(ops, golden_dir):
+    g = np.load(f"{golden_dir}/pipeline.npz")
+    for (h0, w0) in ((32, 32), (47, 61), (64, 40)):
+        scene = g[f"div_{h0}x{w0}_scene"]
+        got = lfsr_b200.lfutils.LFdivide(torch.from_numpy(scene).to(DEV), 5, 32, 16).cpu().numpy()
+        assert tuple(g[f"div_{h0}x{w0}_shape"]) == got.shape
+        assert np.array_equal(got[0, min(1, got.shape[1] - 1)], g[f"div_{h0}x{w0}_sub_u0v1"])
+        assert np.array_equal(got[-1, -1], g[f"div_{h0}x{w0}_sub_last"])
+        assert float(got.astype(np.float64).sum()) == float(g[f"div_{h0}x{w0}_sum"])
+        up = np.repeat(np.repeat(got, 2, axis=2), 2, axis=3).reshape(got.shape[0], got.shape[1], 5, 32, 2, 5, 32, 2)
+        up = np.ascontiguousarray(up).reshape(got.shape[0], got.shape[1], 320, 320)
+        lf = lfsr_b200.lfutils.LFintegrate(torch.from_numpy(up).to(DEV), 5, 64, 32, h0 * 2, w0 * 2)
+        assert np.array_equal(lf.cpu().numpy(), g[f"int_{h0}x{w0}_out"])
+
+
+def test_divide_row_shards_and_6d(ops):
+    A, P, S = 5, 32, 16
+    scene = rnd(A * 70, A * 52, seed=5, lo=0.0)
+    full = lfsr_b200.lfutils.LFdivide(scene, A, P, S)
+    nu = full.shape[0]
+    parts = [lfsr_b200.lfutils.LFdivide(scene, A, P, S, rows=(u, min(u + 2, nu))) for u in range(0, nu, 2)]
+    assert torch.equal(torch.cat(parts, 0), full)
+    six = full.view(nu, full.shape[1], A, P, A, P).permute(0, 1, 2, 4, 3, 5).contiguous()
+    a = lfsr_b200.lfutils.LFintegrate(full, A, P, S, 70, 52)
+    b = lfsr_b200.lfutils.LFintegrate(six, A, P, S, 70, 52)
+    assert torch.equal(a, b)
+    with pytest.raises(N.LfsrError):
+        lfsr_b200.lfutils.LFdivide(rnd(A * 10, A * 10), A, P, S)   # smaller than the mirror border
+
+
+@pytest.mark.parametrize("mode,block", [(0, None), (0, 8), (1, None)])
+@pytest.mark.parametrize("scale", [2, 4])
+def test_interp(ops, ref, mode, block, scale):
+    n, h, w = 3, 40, 40
+    x = rnd(n, 1, h, w, seed=1, lo=0.0)
+    bh = block or h
+    a = torch.empty(n, 1, h * scale, w * scale, device=DEV)
+    b = torch.empty_like(a)
+    ops.interp(x, a, n, h, w, scale, mode, bh, bh)
+    ref.interp(x, b, n, h, w, scale, mode, bh, bh)
+    assert (a - b).abs().max().item() <= 2e-6
+
+
+CONV_CASES = [
+    # cin cout kh kw stride dil pad extra
+    dict(cin=1, cout=54, k=(3, 3), dil=(5, 5), pad=(5, 5), bias=True),
+    dict(cin=18, cout=18, k=(3, 3), dil=(5, 5), pad=(5, 5), bias=True, act=2),
+    dict(cin=18, cout=18, k=(5, 5), stride=(5, 5)),
+    dict(cin=18, cout=16, k=(1, 1), act=1),
+    dict(cin=16, cout=18, k=(1, 1), act=3, mul=True),
+    dict(cin=18, cout=450, k=(1, 1), act=2, alpha=0.1, res=True, shuffle=(5, 5, 0)),
+    dict(cin=54, cout=54, k=(1, 1), act=2, in_scale=True),
+    dict(cin=54, cout=54, k=(3, 3), dil=(5, 5), pad=(5, 5), res=True, bias=True),
+    dict(cin=54, cout=216, k=(3, 3), pad=(1, 1), act=2, shuffle=(2, 2, 0)),
+    dict(cin=54, cout=1, k=(3, 3), pad=(1, 1), bias=True, res=True),
+    dict(cin=64, cout=32, k=(1, 25), stride=(1, 5), pad=(0, 10), act=2),
+    dict(cin=64, cout=32, k=(25, 1), stride=(5, 1), pad=(10, 0), act=2),
+    dict(cin=32, cout=160, k=(1, 1), act=2, shuffle=(1, 5, 1)),
+    dict(cin=32, cout=160, k=(1, 1), act=2, shuffle=(5, 1, 1)),
+    dict(cin=1, cout=64, k=(3, 3), dil=(5, 5), pad=(5, 5), in_perm=True),
+    dict(cin=1, cout=64, k=(5, 5), stride=(5, 5), in_perm=True),
+    dict(cin=64, cout=64, k=(3, 3), dil=(5, 5), pad=(5, 5), res=True, out_perm=True),
+    dict(cin=64, cout=64, k=(3, 3), dil=(5, 5), pad=(5, 5), out_perm=True, shuffle=(2, 2, 0)),
+    dict(cin=64, cout=64, k=(3, 3), pad=(1, 1), act=2, block=(8, 8)),
+    dict(cin=144, cout=64, k=(1, 1), act=2),
+    dict(cin=128, cout=64, k=(3, 3), dil=(5, 5), pad=(5, 5), act=1, res=True),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_f32(ops, ref, case):
+    n, h, w = 2, 40, 40
+    cin, cout = case["cin"], case["cout"]
+    kh, kw = case["k"]
+    stride, dil, pad = case.get("stride", (1, 1)), case.get("dil", (1, 1)), case.get("pad", (0, 0))
+    g = torch.Generator().manual_seed(cin * 131 + cout)
+    wt = (torch.rand(cout, cin, kh, kw, generator=g) - 0.5) * (2.0 / (cin * kh * kw) ** 0.5)
+    bias = (torch.rand(cout, generator=g) - 0.5) if case.get("bias") else None
+    pc = K.pack_conv(wt, bias, stride=stride, dil=dil, pad=pad, device=DEV)
+    x = nhwc(n, h, w, cin, seed=3)
+    oh = (h + 2 * pad[0] - dil[0] * (kh - 1) - 1) // stride[0] + 1
+    ow = (w + 2 * pad[1] - dil[1] * (kw - 1) - 1) // stride[1] + 1
+    ry, rx, sm = case.get("shuffle", (1, 1, 0))
+    co = cout // (ry * rx)
+    kw_args = dict(act=case.get("act", 0), slope=0.1, alpha=case.get("alpha", 1.0), shuffle=(ry, rx, sm),
+                   block=case.get("block", (0, 0)))
+    if case.get("mul"):
+        kw_args["mul"] = nhwc(n, oh, ow, cout, seed=4)
+    if case.get("res"):
+        kw_args["res"] = nhwc(n, oh * ry, ow * rx, co, seed=5)
+    if case.get("in_scale"):
+        kw_args["in_scale"] = rnd(n, 1, 1, cin, seed=6, lo=0.0)
+    if case.get("in_perm"):
+        kw_args.update(in_perm=1, perm_a=5)
+    if case.get("out_perm"):
+        kw_args.update(out_perm=1, perm_a=5)
+    a = nhwc(n, oh * ry, ow * rx, co, seed=7)
+    b = a.clone()
+    ops.conv(x, pc, a, **kw_args)
+    ref.conv(x, pc, b, **kw_args)
+    err = (a - b).abs().max().item()
+    assert err <= 2e-5, f"max err {err}"
+
+
+def test_conv_residual_in_place(ops, ref):
+    n, h, w, c = 1, 24, 24, 54
+    wt = (torch.rand(1, c, 3, 3) - 0.5) * 0.1
+    pc = K.pack_conv(wt, torch.tensor([0.25]), pad=(1, 1), device=DEV)
+    x = nhwc(n, h, w, c, seed=9)
+    y = rnd(n, h, w, 1, seed=10)
+    y2 = y.clone()
+    ops.conv(x, pc, y, res=y)
+    ref.conv(x, pc, y2, res=y2.clone())
+    assert (y - y2).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("kh,kw,dil", [(1, 11, (1, 1)), (11, 1, (1, 1)), (3, 3, (5, 5)), (3, 3, (1, 1))])
+def test_dwconv(ops, ref, kh, kw, dil):
+    n, h, w, c = 2, 40, 40, 18
+    x = nhwc(n, h, w, c, seed=1)
+    wt = rnd(kh * kw, c, seed=2)
+    sc, sh = rnd(c, seed=3, lo=0.5, hi=1.5), rnd(c, seed=4)
+    for scale, shift, act in ((None, None, 0), (sc, sh, 3), (None, None, 1)):
+        a, b = nhwc(n, h, w, c, seed=5), nhwc(n, h, w, c, seed=5)
+        ops.dwconv(x, wt, a, kh, kw, dil, scale, shift, act, 0.1)
+        ref.dwconv(x, wt, b, kh, kw, dil, scale, shift, act, 0.1)
+        assert (a - b).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("h,w,c,bh,bw", [(40, 40, 54, 8, 8), (5, 5, 54, 5, 5), (160, 160, 54, 32, 32), (20, 30, 130, 4, 5)])
+def test_block_mean(ops, ref, h, w, c, bh, bw):
+    x = nhwc(3, h, w, c, seed=1)
+    a, b = nhwc(3, h // bh, w // bw, c, seed=2), nhwc(3, h // bh, w // bw, c, seed=2)
+    ops.block_mean(x, a, bh, bw)
+    ref.block_mean(x, b, bh, bw)
+    assert (a - b).abs().max().item() <= 1e-5
+
+
+def test_sa_modulate(ops, ref):
+    n, h, w, c, A = 2, 40, 40, 54, 5
+    x, res = nhwc(n, h, w, c, seed=1), nhwc(n, h, w, c, seed=2)
+    dw, bs, bb = rnd(9, c, seed=3), rnd(c, seed=4, lo=0.5, hi=1.5), rnd(c, seed=5)
+    am = nhwc(n, A, A, c, seed=6)
+    a, b = nhwc(n, h, w, c, seed=7), nhwc(n, h, w, c, seed=7)
+    ops.sa_modulate(x, dw, bs, bb, am, 0.4, 0.6, res, a, A)
+    ref.sa_modulate(x, dw, bs, bb, am, 0.4, 0.6, res, b, A)
+    assert (a - b).abs().max().item() <= 1e-5
+
+
+def test_layernorm(ops, ref):
+    x = nhwc(1, 1, 5000, 128, seed=1)
+    g, bta = rnd(128, seed=2, lo=0.5, hi=1.5), rnd(128, seed=3)
+    a, b = nhwc(1, 1, 5000, 128, seed=4), nhwc(1, 1, 5000, 128, seed=4)
+    ops.layernorm(x, g, bta, 1e-5, a)
+    ref.layernorm(x, g, bta, 1e-5, b)
+    assert (a - b).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("direction", ["h", "v"])
+def test_epi_attention(ops, ref, direction):
+    B, A, S, E, heads = 2, 5, 8, 128, 8
+    HW = A * S
+    T = B * HW * HW
+    qk = rnd(T, 2 * E, seed=1)
+    v = rnd(T, E, seed=2)
+    a = torch.zeros(T, E, device=DEV)
+    b = torch.zeros(T, E, device=DEV)
+    # SAI-mosaic token index = (b*HW + u*S + h)*HW + v*S + w
+    if direction == "h":   # sequences over (u, h) for fixed (v, w)  (EPIT.py:150-151)
+        args = dict(stride_a=S * HW, stride_s=HW, stride_b=HW * HW, stride_p=S, stride_q=1)
+    else:                  # sequences over (v, w) for fixed (u, h)  (EPIT.py:156-157)
+        args = dict(stride_a=S, stride_s=1, stride_b=HW * HW, stride_p=S * HW, stride_q=HW)
+    ops.epi_attention(qk, v, a, heads, E // heads, A, S, 5, B, A, S, **args)
+    ref.epi_attention(qk, v, b, heads, E // heads, A, S, 5, B, A, S, **args)
+    assert (a - b).abs().max().item() <= 2e-5
+
+
+def test_metrics_vs_oracle_and_golden(ops, golden_dir):
+    g = np.load(f"{golden_dir}/pipeline.npz")
+    lab, noisy = g["met_label"], g["met_out"]
+
+    class MA:
+        angRes_in = 5
+        task = "SR"
+    p, s = lfsr_b200.lfutils.cal_metrics(MA, torch.from_numpy(lab).to(DEV), torch.from_numpy(noisy).to(DEV))
+    assert abs(p - float(g["met_psnr"])) <= 1e-3       # dB; tolerance budget is 0.01 dB
+    assert abs(s - float(g["met_ssim"])) <= 1e-5
+    # host tensors are staged transparently (reference keeps Hr_SAI_y on the CPU, train.py:322)
+    p2, s2 = lfsr_b200.lfutils.cal_metrics(MA, torch.from_numpy(lab), torch.from_numpy(noisy))
+    assert abs(p2 - p) < 1e-9 and abs(s2 - s) < 1e-9
+    # odd view sizes, per-view values
+    rs = np.random.RandomState(1)
+    la = rs.random_sample((5 * 37, 5 * 53)).astype(np.float32)
+    ou = np.clip(la + rs.normal(0, 0.02, la.shape), 0, 1).astype(np.float32)
+    pv, sv = lfsr_b200.lfutils.metric_views(torch.from_numpy(la).to(DEV), torch.from_numpy(ou).to(DEV), 5)
+    _, _, po, so = lf_oracle.cal_metrics(la, ou, 5)
+    assert np.abs(pv - po).max() <= 1e-3 and np.abs(sv - so).max() <= 1e-5

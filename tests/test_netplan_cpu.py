@@ -1,0 +1,59 @@
+"""CPU checks of the host-side launch plans: each drop-in module, with the torch statement of the
+kernel contracts (tests/opref.RefOps) injected as backend, must reproduce the oracle (and through
+it the reference - oracle/make_golden.py pins oracle == reference bit-exactly) and the goldens."""
+import numpy as np
+import pytest
+import torch
+
+import lfsr_b200
+from opref import RefOps
+from oracle import nets as onets, weights
+
+CASES = [("MyEfficientLFNet", 4), ("MyEfficientLFNet", 2), ("EPIT", 4), ("DistgSSR", 4), ("DistgSSR", 2),
+         ("LF_InterNet", 4)]
+
+
+def _have(name):
+    try:
+        lfsr_b200.net_module(name)
+        return True
+    except ModuleNotFoundError:
+        return False
+
+
+@pytest.mark.parametrize("name,scale", CASES)
+def test_state_dict_matches_reference_spec(name, scale):
+    if not _have(name):
+        pytest.skip(f"{name} not built yet")
+    net = lfsr_b200.load_net(name, 5, scale)
+    spec = weights.load_spec(name, scale)
+    sd = net.state_dict()
+    assert list(sorted(sd.keys())) == sorted(n for n, _, _ in spec)
+    for n, shape, dtype in spec:
+        assert tuple(sd[n].shape) == tuple(shape), n
+        assert str(sd[n].dtype).replace("torch.", "") == dtype, n
+    gold = np.load(f"{weights.GOLDEN_DIR}/{name}_x{scale}.npz")
+    assert sum(p.numel() for p in net.parameters()) == int(gold["nparams"])
+
+
+@pytest.mark.parametrize("name,scale", CASES)
+def test_launch_plan_matches_oracle_p8(name, scale):
+    if not _have(name):
+        pytest.skip(f"{name} not built yet")
+    net = lfsr_b200.load_net(name, 5, scale).eval()
+    sd = weights.make_state_dict(name, scale, 1234)
+    net.load_state_dict(sd, strict=True)
+    net.set_backend(RefOps())
+    x = weights.synthetic_patches(2, 5, 8, seed=7)
+    y = net(x, [5, 5])
+    gold = np.load(f"{weights.GOLDEN_DIR}/{name}_x{scale}.npz")["p8_out"]
+    y_or = onets.forward(name, x, sd, 5, scale)
+    assert y.shape == y_or.shape
+    assert np.abs(y_or.numpy() - gold).max() <= 1e-5          # oracle == committed reference output
+    assert (y - y_or).abs().max().item() <= 2e-5              # launch plan == oracle
+
+
+def test_cpu_input_without_backend_raises():
+    net = lfsr_b200.load_net("MyEfficientLFNet", 5, 4)
+    with pytest.raises(lfsr_b200.LfsrError):
+        net(torch.zeros(1, 1, 40, 40))

@@ -1,0 +1,101 @@
+"""GPU parity of the drop-in networks: CUDA forward vs the oracle (== reference, bit-exact on CPU)
+on seeded weights/inputs, and vs the committed outputs of the unmodified reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import lfsr_b200
+from oracle import lf_oracle, nets as onets, weights
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-3          # north_star: max abs error <= 1e-3 on [0,1] outputs
+CASES = [("MyEfficientLFNet", 4), ("MyEfficientLFNet", 2), ("EPIT", 4), ("DistgSSR", 4), ("DistgSSR", 2),
+         ("LF_InterNet", 4)]
+REPORT = {}
+
+
+def _have(name):
+    try:
+        lfsr_b200.net_module(name)
+        return True
+    except ModuleNotFoundError:
+        return False
+
+
+def _net(name, scale):
+    net = lfsr_b200.load_net(name, 5, scale).eval()
+    sd = weights.make_state_dict(name, scale, 1234)
+    net.load_state_dict(sd, strict=True)
+    return net.to(DEV), sd
+
+
+def _dump():
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/net_parity.json", "w") as f:
+        json.dump(REPORT, f, indent=1)
+
+
+@pytest.mark.parametrize("name,scale", CASES)
+def test_forward_p8_vs_reference_golden(name, scale, golden_dir):
+    if not _have(name):
+        pytest.skip(f"{name} not built yet")
+    net, sd = _net(name, scale)
+    x = weights.synthetic_patches(2, 5, 8, seed=7)
+    y = net(x.to(DEV), [5, 5]).cpu().numpy()
+    gold = np.load(f"{golden_dir}/{name}_x{scale}.npz")["p8_out"]
+    err = float(np.abs(y - gold).max())
+    REPORT[f"{name}_x{scale}_p8_maxabs"] = err
+    _dump()
+    assert err <= TOL, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("name,scale", CASES)
+def test_forward_p32_vs_oracle(name, scale, golden_dir):
+    if not _have(name):
+        pytest.skip(f"{name} not built yet")
+    net, sd = _net(name, scale)
+    x = weights.synthetic_patches(3, 5, 32, seed=0)          # patch 0 == the golden's input
+    y = net(x.to(DEV), [5, 5]).cpu()
+    g = np.load(f"{golden_dir}/{name}_x{scale}.npz")
+    err_g = float(np.abs(y[0, 0].numpy()[::8, ::8] - g["p32_sub"][0, 0]).max())
+    torch.set_num_threads(os.cpu_count() or 1)
+    y_or = onets.forward(name, x[1:2], sd, 5, scale)
+    err_o = float((y[1:2] - y_or).abs().max())
+    # |dPSNR| against a fixed pseudo ground truth
+    hr = np.random.RandomState(5).random_sample(y_or.shape[-2:]).astype(np.float32)
+    dpsnr = abs(lf_oracle.psnr_view(hr, y[1, 0].numpy()) - lf_oracle.psnr_view(hr, y_or[0, 0].numpy()))
+    REPORT[f"{name}_x{scale}_p32"] = dict(maxabs_vs_golden=err_g, maxabs_vs_oracle=err_o, dpsnr=dpsnr,
+                                          sum=float(y[0].double().sum()), golden_sum=float(g["p32_sum"]))
+    _dump()
+    assert err_g <= TOL and err_o <= TOL, (err_g, err_o)
+    assert dpsnr <= 0.01
+
+
+def test_batch_slices_and_repeatability():
+    net, _ = _net("MyEfficientLFNet", 4)
+    x = weights.synthetic_patches(4, 5, 8, seed=3).to(DEV)
+    full = net(x)
+    one = torch.cat([net(x[i:i + 1]) for i in range(4)])
+    assert (full - one).abs().max().item() <= 1e-5
+    assert torch.equal(net(x), full)
+
+
+def test_scene_loop_vs_reference_test_golden(golden_dir):
+    """row L: reference train.test() on a synthetic 5x5x40x48 scene (oracle/make_golden.py)."""
+    g = np.load(f"{golden_dir}/test_loop.npz")
+    h0, w0 = int(g["h0"]), int(g["w0"])
+    lr = np.random.RandomState(int(g["lr_seed"])).random_sample((1, 1, 5 * h0, 5 * w0)).astype(np.float32)
+    hr = np.random.RandomState(int(g["hr_seed"])).random_sample((1, 1, 20 * h0, 20 * w0)).astype(np.float32)
+    net, _ = _net("MyEfficientLFNet", 4)
+    psnr, ssim, sr = lfsr_b200.scene.test_scene(net, torch.from_numpy(lr[0, 0]).to(DEV), torch.from_numpy(hr[0, 0]).to(DEV),
+                                                5, 4, minibatch=5)
+    err = float(np.abs(sr.cpu().numpy()[::4, ::4] - g["sr_sub"]).max())
+    REPORT["test_loop"] = dict(maxabs=err, psnr=float(psnr), psnr_ref=float(g["psnr"]), ssim=float(ssim),
+                               ssim_ref=float(g["ssim"]))
+    _dump()
+    assert err <= TOL
+    assert abs(psnr - float(g["psnr"])) <= 0.01 and abs(ssim - float(g["ssim"])) <= 1e-4
