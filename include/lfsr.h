@@ -70,7 +70,8 @@ typedef struct {
   float act_slope;
   float alpha;
   const float* bias;     /* [cout] or NULL */
-  const float* in_scale; /* [n][cin] or NULL */
+  const float* in_scale; /* [n][in_scale_ld] (first cin used) or NULL */
+  int64_t in_scale_ld;   /* floats between samples of in_scale; 0 = cin */
   lfsr_tensor mul;       /* ptr NULL if unused; conv-output geometry */
   lfsr_tensor res;       /* ptr NULL if unused; stored-output geometry */
 } lfsr_conv_desc;

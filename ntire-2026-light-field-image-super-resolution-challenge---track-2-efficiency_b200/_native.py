@@ -37,7 +37,7 @@ class ConvDesc(C.Structure):
         ("shuf_ry", C.c_int32), ("shuf_rx", C.c_int32), ("shuf_mode", C.c_int32),
         ("block_h", C.c_int32), ("block_w", C.c_int32),
         ("act", C.c_int32), ("act_slope", C.c_float), ("alpha", C.c_float),
-        ("bias", C.c_void_p), ("in_scale", C.c_void_p),
+        ("bias", C.c_void_p), ("in_scale", C.c_void_p), ("in_scale_ld", C.c_int64),
         ("mul", Tensor), ("res", Tensor),
     ]
 

@@ -15,6 +15,7 @@ struct ConvArgs {
   const float* w;
   const float* bias;
   const float* in_scale;
+  long long in_scale_ld;
   int kh, kw, sh, sw, dh, dw, ph, pw;
   int in_perm, out_perm, A;
   int ry, rx, shuf_mode;
@@ -56,7 +57,7 @@ conv_igemm_f32(const ConvArgs a) {
   const int loy = ty0 + lp / TILE_W, lox = tx0 + lp % TILE_W;
   const bool lvalid = loy < a.OH && lox < a.OW;
   const int iy0 = loy * a.sh - a.ph, ix0 = lox * a.sw - a.pw;
-  const float* scale_row = a.in_scale ? a.in_scale + (size_t)img * a.cin : nullptr;
+  const float* scale_row = a.in_scale ? a.in_scale + (size_t)img * a.in_scale_ld : nullptr;
 
   float areg[KPT];
   float breg[WPT];
@@ -280,6 +281,7 @@ extern "C" int lfsr_conv2d_f32(const lfsr_tensor* in, const float* w_packed, con
   a.mul = d->mul.ptr ? view_of(&d->mul) : null_view();
   a.res = d->res.ptr ? view_of(&d->res) : null_view();
   a.w = w_packed; a.bias = d->bias; a.in_scale = d->in_scale;
+  a.in_scale_ld = d->in_scale_ld > 0 ? d->in_scale_ld : in->c;
   a.kh = d->kh; a.kw = d->kw; a.sh = d->stride_h; a.sw = d->stride_w; a.dh = d->dil_h; a.dw = d->dil_w;
   a.ph = d->pad_h; a.pw = d->pad_w;
   a.in_perm = d->in_perm; a.out_perm = d->out_perm; a.A = d->perm_a > 0 ? d->perm_a : 1;

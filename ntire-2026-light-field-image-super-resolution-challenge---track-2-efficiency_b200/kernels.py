@@ -130,6 +130,8 @@ class CudaOps:
         d.act, d.act_slope, d.alpha = act, slope, alpha
         d.bias = self._ptr(pc.bias)
         d.in_scale = self._ptr(in_scale)
+        if in_scale is not None:      # [n,1,1,cin] NHWC view (possibly padded rows) or dense [n,cin]
+            d.in_scale_ld = in_scale.stride(0) if in_scale.shape[0] > 1 else pc.cin
         d.mul = as_tensor(mul, "conv.mul") if mul is not None else _NULL_T
         d.res = as_tensor(res, "conv.res") if res is not None else _NULL_T
         tin, tout = as_tensor(x, "conv.in"), as_tensor(out, "conv.out")
