@@ -274,6 +274,29 @@ class get_model(LFNetBase):
         ops.conv(cur, pk["out"], Y, res=Y)
 
 
+    # -- measurement hook --------------------------------------------------------------------------
+    def dominant_kernel(self, batch: int, h: int = 32):
+        """(callable, info) for the layer that dominates HBM bytes and FLOPs: the last upsampler
+        conv 3x3 C->4C + PixelShuffle(2) + LReLU (MyEfficientLFNet.py:560-565): 55 % of the MACs,
+        reads C x (2H)^2, writes C x (4H)^2 per patch. Used by bench.py's roofline entry."""
+        dev = next(self.parameters()).device
+        ops = K.default_ops()
+        pk = self._get_packed(dev, ops)
+        A, C = self.angRes, self.channels
+        pcv, r = pk["up"][-1]
+        hin = A * h * (self.scale // r)
+        src = self._buf(f"up{len(pk['up']) - 2}", batch, hin, hin, C, dev) if len(pk["up"]) > 1 else \
+            self._buf("fu2", batch, hin, hin, C, dev)
+        dst = self._buf(f"up{len(pk['up']) - 1}", batch, hin * r, hin * r, C, dev)
+        info = {
+            "name": "conv3x3 %d->%d + PixelShuffle(%d) + LReLU @%dx%d (upsampler.up.%s)" % (C, pcv.cout, r, hin, hin,
+                                                                                        self.upsampler.steps[-1][0]),
+            "bytes": batch * (hin * hin * C + hin * r * hin * r * C) * 4 + pcv.w_f32.numel() * 4,
+            "flops": 2 * batch * hin * hin * pcv.kh * pcv.kw * pcv.cin * pcv.cout,
+        }
+        return (lambda: ops.conv(src, pcv, dst, act=N.ACT_LRELU, slope=0.1, shuffle=(r, r, N.SHUF_CHANNEL_MAJOR))), info
+
+
 class get_loss(nn.Module):
     """L1 + 0.05 * L1 of rFFT magnitudes (MyEfficientLFNet.py:585-609); training only."""
 
