@@ -1,7 +1,490 @@
-// placeholder until the tcgen05 path lands (replaced below in this round)
+// TF32 implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA, for the dense stride-1 convolutions that carry >90 % of the MACs of every
+// network on the path (3x3 d=1 / d=A, 1x1; MyEfficientLFNet.py:555-565, DistgSSR.py:78-100,
+// LF_InterNet.py:55, EPIT.py:24-31,76-90).
+//
+// GEMM view per tile:  D[128 pixels, NC couts] += A_tap[128 pixels, 32 ch] * W_tap[NC, 32 ch]^T
+//   * M tile = TH x TW output pixels (TH*TW = 128). For tap (ky,kx) the A operand is ONE TMA box of the
+//     NHWC input shifted by (ky*dil - pad, kx*dil - pad); out-of-image (and, with view blocking,
+//     out-of-view) taps are zero-filled by the TMA unit, so padding and EPIT's per-view convs cost
+//     nothing. The tensor map is 5-D (c, x-in-block, block-x, y-in-block, image*block-y).
+//   * K loop = taps x 32-channel groups; each stage holds A (16 KB) and W (NC x 128 B), both K-major
+//     with the 128-byte swizzle that TMA writes and the UMMA descriptors read.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = epilogue
+//     (TMEM -> registers -> bias/act/alpha/PixelShuffle/residual -> global). Two TMEM accumulator
+//     stages let the epilogue of tile i overlap the MMAs of tile i+1. Persistent CTAs, one per SM.
+// TF32: activations are converted by the TMA unit (tensor map type TFLOAT32), weights are rounded
+// to nearest-even at pack time; accumulation is fp32.
+#include <cuda.h>
+#include <string.h>
+#include <mutex>
 #include "lfsr_common.cuh"
+
+namespace lfsr {
+namespace tc {
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kABytes = 128 * 128;     // 128 pixels x 32 floats
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;        // TMEM columns per accumulator stage
+constexpr int kSmemBudget = 200 * 1024;
+
+struct Params {
+  int nb_total, nby, nbx, bh, bw;      // blocks: nb_total = images * nby
+  int C, cgs, kh, kw, dil_h, dil_w, pad_h, pad_w;
+  int cout, NC, nchunks;
+  int TH, TW, tw_shift, tiles_y, tiles_x, total_tiles;
+  int stages, b_stage_bytes;
+  TView out, res;
+  const float* bias;
+  int act;
+  float slope, alpha;
+  int ry, rx, shuf_mode, cq, vec2;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  // bounded spin: a protocol bug must fault, not hang the GPU
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+struct TileCoord {
+  int chunk, nb, y0, vx, x0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const Params& p, int t) {
+  TileCoord c;
+  c.chunk = t % p.nchunks; t /= p.nchunks;
+  c.x0 = (t % p.tiles_x) * p.TW; t /= p.tiles_x;
+  c.vx = t % p.nbx; t /= p.nbx;
+  c.y0 = (t % p.tiles_y) * p.TH;
+  c.nb = t / p.tiles_y;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + p.stages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.stages * p.b_stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps = p.kh * p.kw;
+  const int nks = taps * p.cgs;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    uint32_t it = 0;
+    const uint32_t stage_bytes = kABytes + p.NC * 128;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc_ = decode_tile(p, t);
+      for (int ks = 0; ks < nks; ++ks, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(empty + s, ph ^ 1);
+        if (lane == 0) {
+          const int tap = ks / p.cgs, cg = ks - tap * p.cgs;
+          const int ky = tap / p.kw, kx = tap - ky * p.kw;
+          mbar_expect_tx(full + s, stage_bytes);
+          tma_load_5d(sA + s * kABytes, &tmA, full + s, cg * 32, tc_.x0 + kx * p.dil_w - p.pad_w, tc_.vx,
+                      tc_.y0 + ky * p.dil_h - p.pad_h, tc_.nb);
+          tma_load_2d(sB + s * p.b_stage_bytes, &tmB, full + s, 0, ((tc_.chunk * taps + tap) * p.cgs + cg) * p.NC);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    uint32_t it = 0, tcount = 0;
+    const uint32_t idesc = make_idesc(p.NC);
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
+      const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait(tempty + a, aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + a * kAccStride;
+      for (int ks = 0; ks < nks; ++ks, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(full + s, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const int cg = ks % p.cgs;
+          const int rem = p.C - cg * 32;
+          const int ksteps = rem >= 32 ? 4 : (rem + 7) >> 3;
+          const uint32_t a_addr = smem_u32(sA + s * kABytes);
+          const uint32_t b_addr = smem_u32(sB + s * p.b_stage_bytes);
+          for (int k = 0; k < ksteps; ++k)
+            umma_tf32(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, (ks | k) != 0);
+          umma_commit(empty + s);                      // frees the smem stage when these MMAs retire
+          if (ks == nks - 1) umma_commit(tfull + a);   // accumulator complete -> epilogue
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5 <-> TMEM lane quarters) =================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ty = m >> p.tw_shift, tx = m & (p.TW - 1);
+    const int r2 = p.ry * p.rx;
+    uint32_t tcount = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
+      const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+      const TileCoord tc_ = decode_tile(p, t);
+      const int yb = tc_.y0 + ty, xb = tc_.x0 + tx;
+      const bool valid = yb < p.bh && xb < p.bw;
+      const int img = tc_.nb / p.nby;
+      const int oy = (tc_.nb - img * p.nby) * p.bh + yb, ox = tc_.vx * p.bw + xb;
+      mbar_wait(tfull + a, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccStride;
+      // packed channel pc = sub*cq + c ("factor-major": weights are packed in that order when a
+      // PixelShuffle is fused), sub = i*rx + j selects the output pixel of the shuffle
+      int pc = tc_.chunk * p.NC;
+      int sub = pc / p.cq, c = pc - sub * p.cq;
+      size_t obase = 0, rbase = 0;
+      auto set_sub = [&]() {
+        const int si = sub / p.rx, sj = sub - si * p.rx;
+        obase = p.out.pix(img, oy * p.ry + si, ox * p.rx + sj);
+        if (p.res.p) rbase = p.res.pix(img, oy * p.ry + si, ox * p.rx + sj);
+      };
+      if (valid) set_sub();
+      for (int g = 0; g < p.NC / 16; ++g) {
+        float v[16];
+        tmem_ld16(taddr + g * 16, v);
+        if (!valid) continue;
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          if (pc >= p.cout) break;
+          if (p.vec2) {
+            // cq even: the pair (c, c+1) shares `sub`
+            const int l0 = (r2 > 1 && p.shuf_mode == LFSR_SHUF_CHANNEL_MAJOR) ? c * r2 + sub : pc;
+            const int l1 = (r2 > 1 && p.shuf_mode == LFSR_SHUF_CHANNEL_MAJOR) ? l0 + r2 : pc + 1;
+            float a0 = v[e], a1 = v[e + 1];
+            if (p.bias) { a0 += __ldg(p.bias + l0); a1 += __ldg(p.bias + l1); }
+            a0 = apply_act(a0, p.act, p.slope) * p.alpha;
+            a1 = apply_act(a1, p.act, p.slope) * p.alpha;
+            if (p.res.p) {
+              const float2 r = *reinterpret_cast<const float2*>(p.res.p + rbase + c);
+              a0 += r.x; a1 += r.y;
+            }
+            *reinterpret_cast<float2*>(p.out.p + obase + c) = make_float2(a0, a1);
+            pc += 2; c += 2;
+            if (c >= p.cq) { c -= p.cq; ++sub; if (pc < p.cout) set_sub(); }
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (pc < p.cout) {
+                const int l0 = (r2 > 1 && p.shuf_mode == LFSR_SHUF_CHANNEL_MAJOR) ? c * r2 + sub : pc;
+                float a0 = v[e + h];
+                if (p.bias) a0 += __ldg(p.bias + l0);
+                a0 = apply_act(a0, p.act, p.slope) * p.alpha;
+                if (p.res.p) a0 += p.res.p[rbase + c];
+                p.out.p[obase + c] = a0;
+                ++pc; ++c;
+                if (c >= p.cq) { c = 0; ++sub; if (pc < p.cout) set_sub(); }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + a);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct Plan {
+  int nchunks, NC, cgs;
+};
+static Plan plan_for(int cin, int cout) {
+  Plan pl;
+  pl.nchunks = (cout + 255) / 256;
+  const int per = (cout + pl.nchunks - 1) / pl.nchunks;
+  pl.NC = (per + 15) / 16 * 16;
+  pl.cgs = (cin + 31) / 32;
+  return pl;
+}
+
+static float round_tf32(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;   // inf / nan
+  u += 0xFFFu + ((u >> 13) & 1u);
+  u &= ~0x1FFFu;
+  float y;
+  memcpy(&y, &u, 4);
+  return y;
+}
+
+}  // namespace tc
+}  // namespace lfsr
+
 using namespace lfsr;
-extern "C" size_t lfsr_conv2d_tc_packed_floats(int, int, int, int) { return 0; }
-extern "C" int lfsr_pack_conv_tc(const float*, float*, int, int, int, int) { set_error("tc path not built"); return LFSR_ERR_UNSUPPORTED; }
-extern "C" int lfsr_conv2d_tc(const lfsr_tensor*, const float*, const lfsr_tensor*, const lfsr_conv_desc*, void*) { set_error("tc path not built"); return LFSR_ERR_UNSUPPORTED; }
-extern "C" int lfsr_conv2d_tc_supported(const lfsr_tensor*, const lfsr_tensor*, const lfsr_conv_desc*) { return 0; }
+using namespace lfsr::tc;
+
+extern "C" size_t lfsr_conv2d_tc_packed_floats(int kh, int kw, int cin, int cout) {
+  if (kh <= 0 || kw <= 0 || cin <= 0 || cout <= 0) return 0;
+  const Plan pl = plan_for(cin, cout);
+  return (size_t)pl.nchunks * kh * kw * pl.cgs * pl.NC * 32;
+}
+
+// packed[chunk][tap][cg][NC][32]: row r of chunk holds output channel chunk*NC + r (zero rows beyond cout),
+// 32 consecutive input channels of group cg (zero beyond cin), TF32-rounded.
+extern "C" int lfsr_pack_conv_tc(const float* w, float* packed, int kh, int kw, int cin, int cout) {
+  LFSR_REQUIRE(w && packed && kh > 0 && kw > 0 && cin > 0 && cout > 0, "lfsr_pack_conv_tc: bad arguments");
+  const Plan pl = plan_for(cin, cout);
+  const int taps = kh * kw;
+  const size_t total = lfsr_conv2d_tc_packed_floats(kh, kw, cin, cout);
+  memset(packed, 0, total * sizeof(float));
+  for (int co = 0; co < cout; ++co) {
+    const int chunk = co / pl.NC, r = co - chunk * pl.NC;
+    for (int tap = 0; tap < taps; ++tap)
+      for (int ci = 0; ci < cin; ++ci) {
+        const int cg = ci / 32, k = ci - cg * 32;
+        const size_t dst = ((((size_t)chunk * taps + tap) * pl.cgs + cg) * pl.NC + r) * 32 + k;
+        packed[dst] = round_tf32(w[((size_t)co * cin + ci) * taps + tap]);
+      }
+  }
+  return LFSR_OK;
+}
+
+static bool tc_geometry_ok(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d) {
+  if (!tensor_ok(in) || !tensor_ok(out) || !d) return false;
+  if (d->stride_h != 1 || d->stride_w != 1 || d->in_perm || d->out_perm || d->mul.ptr || d->in_scale) return false;
+  if (d->kh * d->kw > 25 || d->kh < 1 || d->kw < 1) return false;
+  if (2 * d->pad_h != d->dil_h * (d->kh - 1) || 2 * d->pad_w != d->dil_w * (d->kw - 1)) return false;  // "same"
+  if (in->c < 32 || in->ld % 4 != 0 || ((uintptr_t)in->ptr & 15)) return false;
+  const int ry = d->shuf_ry > 0 ? d->shuf_ry : 1, rx = d->shuf_rx > 0 ? d->shuf_rx : 1;
+  if (out->n != in->n || out->h != in->h * ry || out->w != in->w * rx) return false;
+  const int cout = out->c * ry * rx;
+  if (cout < 16) return false;
+  const int bh = d->block_h > 0 ? d->block_h : in->h, bw = d->block_w > 0 ? d->block_w : in->w;
+  if (in->h % bh || in->w % bw) return false;
+  if ((long long)in->n * (in->h / bh) > 0x7fffffffLL) return false;
+  return true;
+}
+
+extern "C" int lfsr_conv2d_tc_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d) {
+  return tc_geometry_ok(in, out, d) && get_encode() != nullptr ? 1 : 0;
+}
+
+extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, const lfsr_tensor* out,
+                              const lfsr_conv_desc* d, void* stream) {
+  LFSR_REQUIRE(w_packed_tc, "lfsr_conv2d_tc: null weights");
+  LFSR_REQUIRE(tc_geometry_ok(in, out, d), "lfsr_conv2d_tc: unsupported geometry (query lfsr_conv2d_tc_supported)");
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { set_error("lfsr_conv2d_tc: cuTensorMapEncodeTiled unavailable"); return LFSR_ERR_CUDA; }
+  const int ry = d->shuf_ry > 0 ? d->shuf_ry : 1, rx = d->shuf_rx > 0 ? d->shuf_rx : 1;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.bh = d->block_h > 0 ? d->block_h : in->h;
+  p.bw = d->block_w > 0 ? d->block_w : in->w;
+  p.nby = in->h / p.bh; p.nbx = in->w / p.bw;
+  p.nb_total = in->n * p.nby;
+  p.C = in->c; p.kh = d->kh; p.kw = d->kw; p.dil_h = d->dil_h; p.dil_w = d->dil_w; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
+  p.cout = out->c * ry * rx;
+  const Plan pl = plan_for(p.C, p.cout);
+  p.NC = pl.NC; p.nchunks = pl.nchunks; p.cgs = pl.cgs;
+  // tile shape TH x TW = 128 minimising padding waste inside a block (prefer wide tiles)
+  {
+    double best = 1e30;
+    for (int tw = 128; tw >= 8; tw >>= 1) {
+      const int th = 128 / tw;
+      const double waste = (double)(ceil_div(p.bh, th) * th) * (ceil_div(p.bw, tw) * tw) / ((double)p.bh * p.bw);
+      if (waste < best - 1e-9) { best = waste; p.TW = tw; p.TH = th; }
+    }
+    p.tw_shift = 0;
+    while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
+  }
+  p.tiles_y = ceil_div(p.bh, p.TH); p.tiles_x = ceil_div(p.bw, p.TW);
+  const long long tiles = (long long)p.nb_total * p.tiles_y * p.nbx * p.tiles_x * p.nchunks;
+  LFSR_REQUIRE(tiles > 0 && tiles < 0x7fffffffLL, "lfsr_conv2d_tc: tile count out of range");
+  p.total_tiles = (int)tiles;
+  p.b_stage_bytes = p.NC * 128;
+  p.stages = kSmemBudget / (kABytes + p.b_stage_bytes);
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  LFSR_REQUIRE(p.stages >= 2, "lfsr_conv2d_tc: not enough shared memory for two stages");
+  p.out = view_of(out);
+  p.res = d->res.ptr ? view_of(&d->res) : null_view();
+  if (d->res.ptr)
+    LFSR_REQUIRE(d->res.n == out->n && d->res.h == out->h && d->res.w == out->w && d->res.c == out->c,
+                 "lfsr_conv2d_tc: res tensor geometry");
+  p.bias = d->bias; p.act = d->act; p.slope = d->act_slope; p.alpha = d->alpha;
+  p.ry = ry; p.rx = rx; p.shuf_mode = d->shuf_mode; p.cq = out->c;
+  p.vec2 = (p.cq % 2 == 0) && (out->ld % 2 == 0) && (((uintptr_t)out->ptr & 7) == 0) &&
+           (!d->res.ptr || ((d->res.ld % 2 == 0) && (((uintptr_t)d->res.ptr & 7) == 0)));
+
+  CUtensorMap tmA, tmB;
+  {
+    const cuuint64_t ld_b = (cuuint64_t)in->ld * 4;
+    cuuint64_t dims[5] = {(cuuint64_t)p.C, (cuuint64_t)p.bw, (cuuint64_t)p.nbx, (cuuint64_t)p.bh, (cuuint64_t)p.nb_total};
+    cuuint64_t strides[4] = {ld_b, ld_b * p.bw, ld_b * in->w, ld_b * in->w * p.bh};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, in->ptr, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("lfsr_conv2d_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r); return LFSR_ERR_CUDA; }
+  }
+  {
+    const cuuint64_t rows = (cuuint64_t)p.nchunks * p.kh * p.kw * p.cgs * p.NC;
+    cuuint64_t dims[2] = {32, rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {32, (cuuint32_t)p.NC};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w_packed_tc), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("lfsr_conv2d_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return LFSR_ERR_CUDA; }
+  }
+  static int sm_count = 0;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  const size_t smem = 1024 + (size_t)p.stages * (kABytes + p.b_stage_bytes) + (2 * kMaxStages + 4) * 8 + 16;
+  LFSR_REQUIRE(smem <= 227 * 1024, "lfsr_conv2d_tc: shared memory plan too large");
+  const int grid = p.total_tiles < sm_count ? p.total_tiles : sm_count;
+  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  return check_launch("conv_tc_kernel");
+}

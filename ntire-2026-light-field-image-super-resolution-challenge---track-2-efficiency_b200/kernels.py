@@ -61,26 +61,38 @@ class PackedConv:
     dil: Tuple[int, int] = (1, 1)
     pad: Tuple[int, int] = (0, 0)
     w_tc: Optional[torch.Tensor] = None
+    tc_perm_r2: int = 0   # >0: w_tc rows were permuted to factor-major for a fused nn.PixelShuffle of r2 sub-pixels
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride=(1, 1), dil=(1, 1), pad=(0, 0),
-              device=None, tc: bool = False) -> PackedConv:
-    """weight is torch-layout [cout, cin, kh, kw] (any device); returns device-resident packing."""
+              device=None, tc: bool = False, tc_shuffle=(1, 1, 0)) -> PackedConv:
+    """weight is torch-layout [cout, cin, kh, kw] (any device); returns device-resident packing.
+    tc_shuffle: the PixelShuffle (ry, rx, mode) this layer will always be launched with; for
+    nn.PixelShuffle order the tensor-core packing stores output channels sub-pixel-major so the
+    epilogue writes contiguous channel runs per output pixel."""
     w = weight.detach().to(torch.float32)
     cout, cin, kh, kw = w.shape
     dev = device if device is not None else w.device
     w_f32 = w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous().to(dev)
     b = None if bias is None else bias.detach().to(torch.float32).contiguous().to(dev)
     w_tc = None
+    perm_r2 = 0
     if tc:
         lib = N.load()
         nfl = lib.lfsr_conv2d_tc_packed_floats(kh, kw, cin, cout)
         if nfl > 0:
-            src = w.contiguous().cpu()
+            src = w
+            r2 = tc_shuffle[0] * tc_shuffle[1]
+            if r2 > 1 and tc_shuffle[2] == N.SHUF_CHANNEL_MAJOR:
+                cq = cout // r2
+                perm = torch.arange(cout).view(cq, r2).t().reshape(-1)      # packed row sub*cq+c <- logical c*r2+sub
+                src = w[perm.to(w.device)]
+                perm_r2 = r2
+            src = src.contiguous().cpu()
             dst = torch.empty(nfl, dtype=torch.float32)
             N.check(lib.lfsr_pack_conv_tc(src.data_ptr(), dst.data_ptr(), kh, kw, cin, cout), "lfsr_pack_conv_tc")
             w_tc = dst.to(dev)
-    return PackedConv(w_f32, b, kh, kw, cin, cout, tuple(stride), tuple(dil), tuple(pad), w_tc)
+    return PackedConv(w_f32, b, kh, kw, cin, cout, tuple(stride), tuple(dil), tuple(pad), w_tc, perm_r2)
 
 
 class CudaOps:
@@ -138,7 +150,9 @@ class CudaOps:
         if x.shape[3] != pc.cin:
             raise N.LfsrError(f"conv: input has {x.shape[3]} channels, weights expect {pc.cin}")
         st = self._stream(x)
-        if (self.use_tc and pc.w_tc is not None and
+        r2 = shuffle[0] * shuffle[1]
+        perm_ok = pc.tc_perm_r2 == (r2 if (r2 > 1 and shuffle[2] == N.SHUF_CHANNEL_MAJOR) else 0)
+        if (self.use_tc and pc.w_tc is not None and perm_ok and
                 self.lib.lfsr_conv2d_tc_supported(C.byref(tin), C.byref(tout), C.byref(d))):
             N.check(self.lib.lfsr_conv2d_tc(C.byref(tin), pc.w_tc.data_ptr(), C.byref(tout), C.byref(d), st),
                     "lfsr_conv2d_tc")

@@ -79,7 +79,7 @@ class get_model(LFNetBase):
                 ln2=(vec(t.feed_forward["0"].weight), vec(t.feed_forward["0"].bias), t.feed_forward["0"].eps),
                 ff1=lin(t.feed_forward["1"].weight), ff2=lin(t.feed_forward["4"].weight), lin_out=lin(t.linear_out.weight),
                 conv=[c3(af.conv[k]) for k in ("0", "2", "4")], heads=t.num_heads, E=E))
-        pk["up0"] = pc(self.upsampling["0"].weight, tc=True)
+        pk["up0"] = pc(self.upsampling["0"].weight, tc=True, tc_shuffle=(self.scale, self.scale, N.SHUF_CHANNEL_MAJOR))
         pk["up3"] = pc(self.upsampling["3"].weight, pad=(1, 1))
         return pk
 

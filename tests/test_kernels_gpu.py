@@ -250,3 +250,58 @@ def test_metrics_vs_oracle_and_golden(ops, golden_dir):
     pv, sv = lfsr_b200.lfutils.metric_views(torch.from_numpy(la).to(DEV), torch.from_numpy(ou).to(DEV), 5)
     _, _, po, so = lf_oracle.cal_metrics(la, ou, 5)
     assert np.abs(pv - po).max() <= 1e-3 and np.abs(sv - so).max() <= 1e-5
+
+
+# ---- tcgen05 / TMEM / TMA TF32 implicit GEMM -----------------------------------------------------
+TC_CASES = [
+    dict(cin=54, cout=216, k=(3, 3), pad=(1, 1), act=2, shuffle=(2, 2, 0), hw=(40, 40)),
+    dict(cin=54, cout=216, k=(3, 3), pad=(1, 1), act=2, shuffle=(2, 2, 0), hw=(160, 160)),
+    dict(cin=54, cout=54, k=(3, 3), dil=(5, 5), pad=(5, 5), res=True, bias=True, hw=(160, 160)),
+    dict(cin=64, cout=64, k=(3, 3), dil=(5, 5), pad=(5, 5), act=2, hw=(40, 40)),
+    dict(cin=64, cout=64, k=(3, 3), pad=(1, 1), act=2, block=(8, 8), res=True, hw=(40, 40)),
+    dict(cin=64, cout=64, k=(3, 3), pad=(1, 1), act=2, block=(32, 32), hw=(160, 160)),
+    dict(cin=128, cout=64, k=(3, 3), dil=(5, 5), pad=(5, 5), act=1, res=True, hw=(160, 160)),
+    dict(cin=320, cout=64, k=(3, 3), dil=(5, 5), pad=(5, 5), act=1, res=True, hw=(40, 40)),
+    dict(cin=144, cout=64, k=(1, 1), act=2, hw=(160, 160)),
+    dict(cin=64, cout=1024, k=(1, 1), act=2, shuffle=(4, 4, 0), hw=(40, 40)),
+    dict(cin=64, cout=1600, k=(1, 1), shuffle=(5, 5, 0), hw=(32, 32)),
+    dict(cin=32, cout=160, k=(1, 1), act=2, shuffle=(1, 5, 1), hw=(40, 8)),
+    dict(cin=32, cout=160, k=(1, 1), act=2, shuffle=(5, 1, 1), hw=(8, 40)),
+    dict(cin=128, cout=256, k=(1, 1), hw=(1, 5000)),
+    dict(cin=256, cout=128, k=(1, 1), res=True, hw=(1, 5000)),
+    dict(cin=64, cout=128, k=(1, 1), hw=(1, 25600)),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_tc(ref, case):
+    tc_ops = K.CudaOps(use_tc=True)
+    n = 2
+    h, w = case["hw"]
+    cin, cout = case["cin"], case["cout"]
+    kh, kw = case["k"]
+    dil, pad = case.get("dil", (1, 1)), case.get("pad", (0, 0))
+    g = torch.Generator().manual_seed(cin * 131 + cout)
+    wt = (torch.rand(cout, cin, kh, kw, generator=g) - 0.5) * (2.0 / (cin * kh * kw) ** 0.5)
+    bias = (torch.rand(cout, generator=g) - 0.5) if case.get("bias") else None
+    ry, rx, sm = case.get("shuffle", (1, 1, 0))
+    pc = K.pack_conv(wt, bias, dil=dil, pad=pad, device=DEV, tc=True, tc_shuffle=(ry, rx, sm))
+    assert pc.w_tc is not None
+    x = nhwc(n, h, w, cin, seed=3)
+    co = cout // (ry * rx)
+    kw_args = dict(act=case.get("act", 0), slope=0.1, alpha=case.get("alpha", 1.0), shuffle=(ry, rx, sm),
+                   block=case.get("block", (0, 0)))
+    if case.get("res"):
+        kw_args["res"] = nhwc(n, h * ry, w * rx, co, seed=5)
+    a = nhwc(n, h * ry, w * rx, co, seed=7)
+    b = a.clone()
+    lib = tc_ops.lib
+    l0 = lib.lfsr_launch_count()
+    tc_ops.conv(x, pc, a, **kw_args)
+    torch.cuda.synchronize()
+    ref.conv(x, pc, b, **kw_args)
+    err = (a - b).abs().max().item()
+    scale = max(1.0, b.abs().max().item())
+    print(f"tc conv {case}: max err {err:.3e} (ref max {scale:.3f})")
+    assert lib.lfsr_launch_count() == l0 + 1
+    assert err <= 2e-3 * scale, f"max err {err}"
