@@ -36,11 +36,12 @@ struct Params {
   int cout, NC, nchunks;
   int TH, TW, tw_shift, tiles_y, tiles_x, total_tiles;
   int stages, b_stage_bytes;
+  int resident, m_tiles;               // resident: all K-stages of W stay in smem for the CTA's lifetime
   TView out, res;
   const float* bias;
   int act;
   float slope, alpha;
-  int ry, rx, shuf_mode, cq, vec2;
+  int ry, rx, shuf_mode, cq, vec;      // vec: floats per lane in the coalesced write-out (4, 2 or 1)
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -143,14 +144,75 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 struct TileCoord {
   int chunk, nb, y0, vx, x0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const Params& p, int t) {
+// i-th tile of this CTA. Streaming mode: round-robin over (m-tile, cout-chunk). Resident mode: the CTA
+// keeps one cout-chunk's weights in smem, so its chunk is fixed and only the m-tile advances.
+__device__ __forceinline__ bool next_tile(const Params& p, int i, int& m, int& chunk) {
+  if (p.resident) {
+    chunk = blockIdx.x % p.nchunks;
+    m = blockIdx.x / p.nchunks + i * (gridDim.x / p.nchunks);
+    return m < p.m_tiles;
+  }
+  const int t = blockIdx.x + i * gridDim.x;
+  if (t >= p.total_tiles) return false;
+  chunk = t % p.nchunks;
+  m = t / p.nchunks;
+  return true;
+}
+__device__ __forceinline__ TileCoord decode_tile(const Params& p, int t, int chunk) {
   TileCoord c;
-  c.chunk = t % p.nchunks; t /= p.nchunks;
+  c.chunk = chunk;
   c.x0 = (t % p.tiles_x) * p.TW; t /= p.tiles_x;
   c.vx = t % p.nbx; t /= p.nbx;
   c.y0 = (t % p.tiles_y) * p.TH;
   c.nb = t / p.tiles_y;
   return c;
+}
+
+// Coalesced write-out of a warp's staged [32 pixels][<=32 packed channels] block. V floats per lane.
+// packed channel pc = sub*cq + c ("factor-major": the weights are packed in that order when an
+// nn.PixelShuffle is fused), sub = i*rx + j selects the output pixel of the shuffle.
+template <int V>
+__device__ __forceinline__ void epi_writeout(const Params& p, const float* stg, int lane, int q, const TileCoord& tc_, int pc0,
+                                             int ncols) {
+  constexpr int LPR = 32 / V;   // lanes per pixel row
+  const int r2 = p.ry * p.rx;
+  const int img = tc_.nb / p.nby;
+  const int ybase = (tc_.nb - img * p.nby) * p.bh;
+  const int col = (lane % LPR) * V;
+  const int pc = pc0 + col;
+  if (col >= ncols || pc >= p.cout) return;
+  int sub = 0, c = pc;
+  if (r2 > 1) { sub = pc / p.cq; c = pc - sub * p.cq; }
+  const int si = r2 > 1 ? sub / p.rx : 0, sj = r2 > 1 ? sub - si * p.rx : 0;
+  const bool chan_major = r2 > 1 && p.shuf_mode == LFSR_SHUF_CHANNEL_MAJOR;
+  float bv[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) bv[e] = p.bias ? __ldg(p.bias + (chan_major ? (c + e) * r2 + sub : pc + e)) : 0.f;
+#pragma unroll 4
+  for (int it = 0; it < LPR; ++it) {
+    const int r = it * V + lane / LPR;
+    const int m = q * 32 + r;
+    const int yb = tc_.y0 + (m >> p.tw_shift), xb = tc_.x0 + (m & (p.TW - 1));
+    if (yb >= p.bh || xb >= p.bw) continue;
+    const float* src = stg + r * 32 + ((((col >> 2) ^ (r & 7)) << 2) | (col & 3));
+    float v[V];
+    if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(src); v[0] = t.x; v[1] = t.y; v[2 % V] = t.z; v[3 % V] = t.w; }
+    else if (V == 2) { const float2 t = *reinterpret_cast<const float2*>(src); v[0] = t.x; v[1 % V] = t.y; }
+    else v[0] = *src;
+    const int sy = (ybase + yb) * p.ry + si, sx = (tc_.vx * p.bw + xb) * p.rx + sj;
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = apply_act(v[e] + bv[e], p.act, p.slope) * p.alpha;
+    float* dst = p.out.p + p.out.pix(img, sy, sx) + c;
+    if (p.res.p) {
+      const float* rs = p.res.p + p.res.pix(img, sy, sx) + c;
+      if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(rs); v[0] += t.x; v[1] += t.y; v[2 % V] += t.z; v[3 % V] += t.w; }
+      else if (V == 2) { const float2 t = *reinterpret_cast<const float2*>(rs); v[0] += t.x; v[1 % V] += t.y; }
+      else v[0] += *rs;
+    }
+    if (V == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2 % V], v[3 % V]);
+    else if (V == 2) *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1 % V]);
+    else *dst = v[0];
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -160,20 +222,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.stages * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.stages * p.b_stage_bytes);
+  const int taps = p.kh * p.kw;
+  const int nks = taps * p.cgs;
+  float* sEpi = reinterpret_cast<float*>(sB + (p.resident ? nks : p.stages) * p.b_stage_bytes);   // 4 warps x 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 4 * 1024);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* bfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int taps = p.kh * p.kw;
-  const int nks = taps * p.cgs;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+    mbar_init(bfull, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -187,9 +252,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ================= TMA producer =================
     uint32_t it = 0;
-    const uint32_t stage_bytes = kABytes + p.NC * 128;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TileCoord tc_ = decode_tile(p, t);
+    const uint32_t stage_bytes = kABytes + (p.resident ? 0 : p.NC * 128);
+    int m, chunk;
+    if (p.resident && lane == 0 && next_tile(p, 0, m, chunk)) {
+      // one-time load of this CTA's whole weight set
+      mbar_expect_tx(bfull, (uint32_t)nks * p.b_stage_bytes);
+      for (int ks = 0; ks < nks; ++ks)
+        tma_load_2d(sB + ks * p.b_stage_bytes, &tmB, bfull, 0, (chunk * nks + ks) * p.NC);
+    }
+    __syncwarp();
+    for (int i = 0; next_tile(p, i, m, chunk); ++i) {
+      const TileCoord tc_ = decode_tile(p, m, chunk);
       for (int ks = 0; ks < nks; ++ks, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
@@ -200,7 +273,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(full + s, stage_bytes);
           tma_load_5d(sA + s * kABytes, &tmA, full + s, cg * 32, tc_.x0 + kx * p.dil_w - p.pad_w, tc_.vx,
                       tc_.y0 + ky * p.dil_h - p.pad_h, tc_.nb);
-          tma_load_2d(sB + s * p.b_stage_bytes, &tmB, full + s, 0, ((tc_.chunk * taps + tap) * p.cgs + cg) * p.NC);
+          if (!p.resident)
+            tma_load_2d(sB + s * p.b_stage_bytes, &tmB, full + s, 0, (tc_.chunk * nks + ks) * p.NC);
         }
         __syncwarp();
       }
@@ -209,7 +283,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================= MMA issuer =================
     uint32_t it = 0, tcount = 0;
     const uint32_t idesc = make_idesc(p.NC);
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
+    int m, chunk;
+    if (p.resident && next_tile(p, 0, m, chunk)) mbar_wait(bfull, 0);
+    for (int i = 0; next_tile(p, i, m, chunk); ++i, ++tcount) {
       const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(tempty + a, aph ^ 1);
       tc_fence_after();
@@ -224,7 +300,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int rem = p.C - cg * 32;
           const int ksteps = rem >= 32 ? 4 : (rem + 7) >> 3;
           const uint32_t a_addr = smem_u32(sA + s * kABytes);
-          const uint32_t b_addr = smem_u32(sB + s * p.b_stage_bytes);
+          const uint32_t b_addr = smem_u32(sB + (p.resident ? ks : s) * p.b_stage_bytes);
           for (int k = 0; k < ksteps; ++k)
             umma_tf32(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, (ks | k) != 0);
           umma_commit(empty + s);                      // frees the smem stage when these MMAs retire
@@ -235,70 +311,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ================= epilogue (warps 2..5 <-> TMEM lane quarters) =================
+    // TMEM -> registers (one pixel row per lane) -> 4 KB swizzled smem transpose per warp ->
+    // coalesced vector stores (consecutive lanes write consecutive bytes of a pixel's channel run).
     const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const int ty = m >> p.tw_shift, tx = m & (p.TW - 1);
-    const int r2 = p.ry * p.rx;
+    float* stg = sEpi + (warp - 2) * 1024;
     uint32_t tcount = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
+    int m_, chunk_;
+    for (int i = 0; next_tile(p, i, m_, chunk_); ++i, ++tcount) {
       const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
-      const TileCoord tc_ = decode_tile(p, t);
-      const int yb = tc_.y0 + ty, xb = tc_.x0 + tx;
-      const bool valid = yb < p.bh && xb < p.bw;
-      const int img = tc_.nb / p.nby;
-      const int oy = (tc_.nb - img * p.nby) * p.bh + yb, ox = tc_.vx * p.bw + xb;
+      const TileCoord tc_ = decode_tile(p, m_, chunk_);
       mbar_wait(tfull + a, aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccStride;
-      // packed channel pc = sub*cq + c ("factor-major": weights are packed in that order when a
-      // PixelShuffle is fused), sub = i*rx + j selects the output pixel of the shuffle
-      int pc = tc_.chunk * p.NC;
-      int sub = pc / p.cq, c = pc - sub * p.cq;
-      size_t obase = 0, rbase = 0;
-      auto set_sub = [&]() {
-        const int si = sub / p.rx, sj = sub - si * p.rx;
-        obase = p.out.pix(img, oy * p.ry + si, ox * p.rx + sj);
-        if (p.res.p) rbase = p.res.pix(img, oy * p.ry + si, ox * p.rx + sj);
-      };
-      if (valid) set_sub();
-      for (int g = 0; g < p.NC / 16; ++g) {
-        float v[16];
-        tmem_ld16(taddr + g * 16, v);
-        if (!valid) continue;
+      for (int g = 0; g * 32 < p.NC; ++g) {
+        const int ncols = p.NC - g * 32 < 32 ? p.NC - g * 32 : 32;
+        float v[32];
+        tmem_ld16(taddr + g * 32, v);
+        if (ncols > 16) tmem_ld16(taddr + g * 32 + 16, v + 16);
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-          if (pc >= p.cout) break;
-          if (p.vec2) {
-            // cq even: the pair (c, c+1) shares `sub`
-            const int l0 = (r2 > 1 && p.shuf_mode == LFSR_SHUF_CHANNEL_MAJOR) ? c * r2 + sub : pc;
-            const int l1 = (r2 > 1 && p.shuf_mode == LFSR_SHUF_CHANNEL_MAJOR) ? l0 + r2 : pc + 1;
-            float a0 = v[e], a1 = v[e + 1];
-            if (p.bias) { a0 += __ldg(p.bias + l0); a1 += __ldg(p.bias + l1); }
-            a0 = apply_act(a0, p.act, p.slope) * p.alpha;
-            a1 = apply_act(a1, p.act, p.slope) * p.alpha;
-            if (p.res.p) {
-              const float2 r = *reinterpret_cast<const float2*>(p.res.p + rbase + c);
-              a0 += r.x; a1 += r.y;
-            }
-            *reinterpret_cast<float2*>(p.out.p + obase + c) = make_float2(a0, a1);
-            pc += 2; c += 2;
-            if (c >= p.cq) { c -= p.cq; ++sub; if (pc < p.cout) set_sub(); }
-          } else {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (pc < p.cout) {
-                const int l0 = (r2 > 1 && p.shuf_mode == LFSR_SHUF_CHANNEL_MAJOR) ? c * r2 + sub : pc;
-                float a0 = v[e + h];
-                if (p.bias) a0 += __ldg(p.bias + l0);
-                a0 = apply_act(a0, p.act, p.slope) * p.alpha;
-                if (p.res.p) a0 += p.res.p[rbase + c];
-                p.out.p[obase + c] = a0;
-                ++pc; ++c;
-                if (c >= p.cq) { c = 0; ++sub; if (pc < p.cout) set_sub(); }
-              }
-            }
-          }
-        }
+        for (int j = 0; j < 8; ++j)
+          if (j * 4 < ncols)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int pc0 = tc_.chunk * p.NC + g * 32;
+        if (p.vec == 4) epi_writeout<4>(p, stg, lane, q, tc_, pc0, ncols);
+        else if (p.vec == 2) epi_writeout<2>(p, stg, lane, q, tc_, pc0, ncols);
+        else epi_writeout<1>(p, stg, lane, q, tc_, pc0, ncols);
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -394,7 +434,7 @@ static bool tc_geometry_ok(const lfsr_tensor* in, const lfsr_tensor* out, const 
   const int ry = d->shuf_ry > 0 ? d->shuf_ry : 1, rx = d->shuf_rx > 0 ? d->shuf_rx : 1;
   if (out->n != in->n || out->h != in->h * ry || out->w != in->w * rx) return false;
   const int cout = out->c * ry * rx;
-  if (cout < 16) return false;
+  if (cout < 1) return false;
   const int bh = d->block_h > 0 ? d->block_h : in->h, bw = d->block_w > 0 ? d->block_w : in->w;
   if (in->h % bh || in->w % bw) return false;
   if ((long long)in->n * (in->h / bh) > 0x7fffffffLL) return false;
@@ -437,8 +477,14 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   const long long tiles = (long long)p.nb_total * p.tiles_y * p.nbx * p.tiles_x * p.nchunks;
   LFSR_REQUIRE(tiles > 0 && tiles < 0x7fffffffLL, "lfsr_conv2d_tc: tile count out of range");
   p.total_tiles = (int)tiles;
+  p.m_tiles = (int)(tiles / p.nchunks);
   p.b_stage_bytes = p.NC * 128;
-  p.stages = kSmemBudget / (kABytes + p.b_stage_bytes);
+  const int nks = p.kh * p.kw * p.cgs;
+  const int kSmemMax = 227 * 1024 - 1024 - 256 - 16 * 1024;  // minus alignment slack, barriers, epilogue staging
+  const long long b_all = (long long)nks * p.b_stage_bytes;
+  p.resident = b_all + 3 * kABytes <= kSmemMax ? 1 : 0;     // whole weight set + >= 3 activation stages fit
+  if (p.resident) p.stages = (int)((kSmemMax - b_all) / kABytes);
+  else p.stages = (kSmemBudget - 16 * 1024) / (kABytes + p.b_stage_bytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   LFSR_REQUIRE(p.stages >= 2, "lfsr_conv2d_tc: not enough shared memory for two stages");
   p.out = view_of(out);
@@ -448,8 +494,15 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
                  "lfsr_conv2d_tc: res tensor geometry");
   p.bias = d->bias; p.act = d->act; p.slope = d->act_slope; p.alpha = d->alpha;
   p.ry = ry; p.rx = rx; p.shuf_mode = d->shuf_mode; p.cq = out->c;
-  p.vec2 = (p.cq % 2 == 0) && (out->ld % 2 == 0) && (((uintptr_t)out->ptr & 7) == 0) &&
-           (!d->res.ptr || ((d->res.ld % 2 == 0) && (((uintptr_t)d->res.ptr & 7) == 0)));
+  p.vec = 1;
+  for (int v = 2; v <= 4; v *= 2) {
+    const uintptr_t mask = (uintptr_t)v * 4 - 1;
+    if ((p.cq % v == 0) && (out->ld % v == 0) && (((uintptr_t)out->ptr & mask) == 0) &&
+        (!d->res.ptr || ((d->res.ld % v == 0) && (((uintptr_t)d->res.ptr & mask) == 0))))
+      p.vec = v;
+    else
+      break;
+  }
 
   CUtensorMap tmA, tmB;
   {
@@ -482,9 +535,14 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
-  const size_t smem = 1024 + (size_t)p.stages * (kABytes + p.b_stage_bytes) + (2 * kMaxStages + 4) * 8 + 16;
+  const size_t smem = 1024 + (size_t)p.stages * kABytes + (size_t)(p.resident ? nks : p.stages) * p.b_stage_bytes +
+                      16 * 1024 + (2 * kMaxStages + 5) * 8 + 16;
   LFSR_REQUIRE(smem <= 227 * 1024, "lfsr_conv2d_tc: shared memory plan too large");
-  const int grid = p.total_tiles < sm_count ? p.total_tiles : sm_count;
+  int grid = p.total_tiles < sm_count ? p.total_tiles : sm_count;
+  if (p.resident && p.nchunks > 1) {
+    grid = grid / p.nchunks * p.nchunks;                   // every CTA owns one cout-chunk for its lifetime
+    if (grid < p.nchunks) grid = p.nchunks;
+  }
   conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   return check_launch("conv_tc_kernel");
 }

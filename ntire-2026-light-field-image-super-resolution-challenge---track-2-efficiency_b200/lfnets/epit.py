@@ -80,7 +80,7 @@ class get_model(LFNetBase):
                 ff1=lin(t.feed_forward["1"].weight), ff2=lin(t.feed_forward["4"].weight), lin_out=lin(t.linear_out.weight),
                 conv=[c3(af.conv[k]) for k in ("0", "2", "4")], heads=t.num_heads, E=E))
         pk["up0"] = pc(self.upsampling["0"].weight, tc=True, tc_shuffle=(self.scale, self.scale, N.SHUF_CHANNEL_MAJOR))
-        pk["up3"] = pc(self.upsampling["3"].weight, pad=(1, 1))
+        pk["up3"] = pc(self.upsampling["3"].weight, pad=(1, 1), tc=True)
         return pk
 
     def _run(self, ops, pk, x, out):

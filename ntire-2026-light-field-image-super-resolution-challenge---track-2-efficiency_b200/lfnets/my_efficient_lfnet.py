@@ -200,7 +200,7 @@ class get_model(LFNetBase):
         pk["gf2"] = pc(w, b, tc=True, **dil)
         pk["up"] = [(pc(self.upsampler.up[str(i)].weight, pad=(1, 1), tc=True, tc_shuffle=(r, r, N.SHUF_CHANNEL_MAJOR)), r)
                     for i, r in self.upsampler.steps]
-        pk["out"] = pc(self.output_conv.weight, self.output_conv.bias, pad=(1, 1))
+        pk["out"] = pc(self.output_conv.weight, self.output_conv.bias, pad=(1, 1), tc=True)
         return pk
 
     # -- run ------------------------------------------------------------------------------------------

@@ -1,0 +1,88 @@
+"""Per-op device-time breakdown of one forward (CUDA events around every C-ABI call).
+usage: python profiles/op_breakdown.py [model] [batch]   (run on the GPU box)"""
+import collections
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import lfsr_b200
+from lfsr_b200 import kernels as K
+from oracle import weights
+
+
+class ProfilingOps(K.CudaOps):
+    def __init__(self):
+        super().__init__(use_tc=True)
+        self.records = []
+        self.lib_calls = collections.Counter()
+
+    def _wrap(self, name, fn, label):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        before = self.lib.lfsr_launch_count()
+        e0.record()
+        fn()
+        e1.record()
+        self.records.append((name, label, e0, e1))
+
+    def conv(self, x, pc, out, **kw):
+        tc = "tc" if (pc.w_tc is not None) else "f32"
+        label = f"conv {pc.kh}x{pc.kw} {pc.cin}->{pc.cout} s{pc.stride[0]} d{pc.dil[0]} @{x.shape[1]}x{x.shape[2]} [{tc}]"
+        self._wrap("conv", lambda: K.CudaOps.conv(self, x, pc, out, **kw), label)
+
+    def dwconv(self, x, w, out, kh, kw, **k2):
+        self._wrap("dwconv", lambda: K.CudaOps.dwconv(self, x, w, out, kh, kw, **k2), f"dwconv {kh}x{kw} c{x.shape[3]} @{x.shape[1]}x{x.shape[2]}")
+
+    def block_mean(self, x, out, bh, bw):
+        self._wrap("block_mean", lambda: K.CudaOps.block_mean(self, x, out, bh, bw), f"block_mean {bh}x{bw} c{x.shape[3]} @{x.shape[1]}")
+
+    def sa_modulate(self, *a):
+        self._wrap("sa_modulate", lambda: K.CudaOps.sa_modulate(self, *a), "sa_modulate")
+
+    def interp(self, *a):
+        self._wrap("interp", lambda: K.CudaOps.interp(self, *a), "interp")
+
+    def layernorm(self, *a):
+        self._wrap("layernorm", lambda: K.CudaOps.layernorm(self, *a), "layernorm")
+
+    def epi_attention(self, *a):
+        self._wrap("epi_attention", lambda: K.CudaOps.epi_attention(self, *a), "epi_attention")
+
+
+def main():
+    model = sys.argv[1] if len(sys.argv) > 1 else "MyEfficientLFNet"
+    batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    dev = torch.device("cuda:0")
+    net = lfsr_b200.load_net(model, 5, 4).eval()
+    net.load_state_dict(weights.make_state_dict(model, 4, 1234))
+    net = net.to(dev)
+    ops = ProfilingOps()
+    net.set_backend(ops)
+    x = weights.synthetic_patches(batch, 5, 32, 0).to(dev)
+    for _ in range(2):
+        net(x)
+    torch.cuda.synchronize()
+    ops.records.clear()
+    net(x)
+    torch.cuda.synchronize()
+    agg = collections.OrderedDict()
+    total = 0.0
+    for name, label, e0, e1 in ops.records:
+        ms = e0.elapsed_time(e1)
+        total += ms
+        a = agg.setdefault(label, [0, 0.0])
+        a[0] += 1
+        a[1] += ms
+    rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+    print(f"{model} batch {batch}: {len(ops.records)} launches, {total:.2f} ms summed device time")
+    for label, (cnt, ms) in rows:
+        print(f"  {ms:9.3f} ms  {100 * ms / total:5.1f}%  x{cnt:<3d} {label}")
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump({"model": model, "batch": batch, "total_ms": total, "rows": [[l, c, m] for l, (c, m) in rows]},
+              open(f"gpurun_out/op_breakdown_{model}.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -270,6 +270,10 @@ TC_CASES = [
     dict(cin=128, cout=256, k=(1, 1), hw=(1, 5000)),
     dict(cin=256, cout=128, k=(1, 1), res=True, hw=(1, 5000)),
     dict(cin=64, cout=128, k=(1, 1), hw=(1, 25600)),
+    dict(cin=54, cout=1, k=(3, 3), pad=(1, 1), bias=True, res=True, hw=(160, 160)),
+    dict(cin=64, cout=1, k=(3, 3), pad=(1, 1), res=True, hw=(40, 40)),
+    dict(cin=64, cout=1024, k=(1, 1), act=2, shuffle=(4, 4, 0), hw=(160, 160)),
+    dict(cin=128, cout=384, k=(1, 1), hw=(1, 25600)),
 ]
 
 
