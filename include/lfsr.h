@@ -116,6 +116,16 @@ int lfsr_conv2d_f32(const lfsr_tensor* in, const float* w_packed, const lfsr_ten
 int lfsr_dwconv_f32(const lfsr_tensor* in, const float* w_packed, const float* scale,
                     const float* shift, const lfsr_tensor* out, int kh, int kw, int dil_h, int dil_w,
                     int act, float act_slope, void* stream);
+/* direct conv for 1..4 output channels (reconstruction heads 54->1 / 64->1: MyEfficientLFNet.py:70-73,
+ * EPIT.py:48): stride 1, "same" padding; weights packed as for lfsr_conv2d_f32; bias/act/alpha/res fused. */
+int lfsr_conv2d_small_cout_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);
+int lfsr_conv2d_small_cout(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out,
+                           const lfsr_conv_desc* d, void* stream);
+/* MultiScaleEPIBlock (MyEfficientLFNet.py:278-327) in one pass over 18-channel splits:
+ *   out = LReLU(fuse . concat_b LReLU(pw_b . dw_b(x))),  b in {1 x klen, klen x 1, 3x3 dilated `dil`}.
+ * w_packed = dw_h[klen][18] | dw_v[klen][18] | dw_d[9][18] | pw_h[18 in][18 out] | pw_v | pw_d | fuse[54 in][18 out]. */
+int lfsr_mel_epi_branch(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out, int klen, int dil,
+                        float slope, void* stream);
 /* TF32 tcgen05/TMEM implicit GEMM fed by TMA (sm_100a); weights packed by lfsr_pack_conv_tc.
  * Supports stride 1 (any dilation, "same" zero padding given by pad) and kh*kw <= 25. */
 size_t lfsr_conv2d_tc_packed_floats(int kh, int kw, int cin, int cout);

@@ -66,6 +66,9 @@ SIGNATURES = {
     "lfsr_interp": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "lfsr_conv2d_f32": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
     "lfsr_dwconv_f32": (_I, [_TP, _P, _P, _P, _TP, _I, _I, _I, _I, _I, C.c_float, _P]),
+    "lfsr_conv2d_small_cout_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),
+    "lfsr_conv2d_small_cout": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
+    "lfsr_mel_epi_branch": (_I, [_TP, _P, _TP, _I, _I, C.c_float, _P]),
     "lfsr_conv2d_tc_packed_floats": (C.c_size_t, [_I, _I, _I, _I]),
     "lfsr_pack_conv_tc": (_I, [_P, _P, _I, _I, _I, _I]),
     "lfsr_conv2d_tc": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),

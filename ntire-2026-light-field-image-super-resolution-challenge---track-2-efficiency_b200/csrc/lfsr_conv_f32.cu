@@ -218,16 +218,15 @@ static int launch_conv(const ConvArgs& a, bool vec, cudaStream_t st) {
 // one thread = one pixel x 2 channels (float2 when aligned); taps are L1/L2 hits.
 __global__ void __launch_bounds__(256)
 dwconv_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ scale,
-              const float* __restrict__ shift, int kh, int kw, int dh, int dw, int act, float slope,
-              long long total) {
+              const float* __restrict__ shift, int kh, int kw, int dh, int dw, int act, float slope) {
   const int C = in.c;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(t % C);
-    long long r = t / C;
-    int x = (int)(r % in.w); r /= in.w;
-    int y = (int)(r % in.h);
-    int img = (int)(r / in.h);
+  const int img = blockIdx.y;                 // 32-bit index math inside one image
+  const int per = in.h * in.w * C;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per; t += gridDim.x * blockDim.x) {
+    const int c = t % C;
+    const int r = t / C;
+    const int x = r % in.w;
+    const int y = r / in.w;
     const int ph = (kh / 2) * dh, pw = (kw / 2) * dw;
     float acc = 0.f;
     for (int ky = 0; ky < kh; ++ky) {
@@ -311,10 +310,9 @@ extern "C" int lfsr_dwconv_f32(const lfsr_tensor* in, const float* w_packed, con
                "lfsr_dwconv_f32: in/out shape mismatch");
   LFSR_REQUIRE(kh > 0 && kw > 0 && (kh & 1) && (kw & 1) && dil_h > 0 && dil_w > 0, "lfsr_dwconv_f32: odd kernels only");
   LFSR_REQUIRE((scale == nullptr) == (shift == nullptr), "lfsr_dwconv_f32: scale/shift must come together");
-  long long total = (long long)in->n * in->h * in->w * in->c;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
-  dwconv_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(view_of(in), view_of(out), w_packed, scale, shift, kh, kw,
-                                                                dil_h, dil_w, act, act_slope, total);
+  LFSR_REQUIRE(in->n <= 65535 && (long long)in->h * in->w * in->c < 0x7fffffffLL, "lfsr_dwconv_f32: tensor too large");
+  dim3 blocks(ceil_div(in->h * in->w * in->c, 256), in->n);
+  dwconv_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(view_of(in), view_of(out), w_packed, scale, shift, kh, kw, dil_h,
+                                                          dil_w, act, act_slope);
   return check_launch("dwconv_kernel");
 }

@@ -430,7 +430,7 @@ static bool tc_geometry_ok(const lfsr_tensor* in, const lfsr_tensor* out, const 
   if (d->stride_h != 1 || d->stride_w != 1 || d->in_perm || d->out_perm || d->mul.ptr || d->in_scale) return false;
   if (d->kh * d->kw > 25 || d->kh < 1 || d->kw < 1) return false;
   if (2 * d->pad_h != d->dil_h * (d->kh - 1) || 2 * d->pad_w != d->dil_w * (d->kw - 1)) return false;  // "same"
-  if (in->c < 32 || in->ld % 4 != 0 || ((uintptr_t)in->ptr & 15)) return false;
+  if (in->c < 8 || in->ld % 4 != 0 || ((uintptr_t)in->ptr & 15)) return false;
   const int ry = d->shuf_ry > 0 ? d->shuf_ry : 1, rx = d->shuf_rx > 0 ? d->shuf_rx : 1;
   if (out->n != in->n || out->h != in->h * ry || out->w != in->w * rx) return false;
   const int cout = out->c * ry * rx;

@@ -21,15 +21,14 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 
 __global__ void __launch_bounds__(256)
 interp_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int h, int w, int s, int mode, int bh,
-              int bw, long long total) {
+              int bw) {
   const int oh = h * s, ow = w * s;
   const float rs = 1.0f / (float)s;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    int ox = (int)(t % ow);
-    long long r = t / ow;
-    int oy = (int)(r % oh);
-    int img = (int)(r / oh);
+  const int img = blockIdx.y;                 // 32-bit index math inside one image
+  out += (size_t)img * oh * ow;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < oh * ow; t += gridDim.x * blockDim.x) {
+    const int ox = t % ow;
+    const int oy = t / ow;
     // independent block (view) handling: clamp inside the block the output pixel falls in
     int vby = oy / (bh * s), ly = oy - vby * bh * s;
     int vbx = ox / (bw * s), lx = ox - vbx * bw * s;
@@ -80,9 +79,9 @@ extern "C" int lfsr_interp(const float* in, float* out, int n, int h, int w, int
   LFSR_REQUIRE(mode == LFSR_INTERP_BICUBIC || mode == LFSR_INTERP_BILINEAR, "lfsr_interp: bad mode %d", mode);
   LFSR_REQUIRE(block_h > 0 && block_w > 0 && h % block_h == 0 && w % block_w == 0,
                "lfsr_interp: block %dx%d does not tile %dx%d", block_h, block_w, h, w);
-  long long total = (long long)n * h * scale * w * scale;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
-  interp_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n, h, w, scale, mode, block_h, block_w, total);
+  LFSR_REQUIRE(n <= 65535 && (long long)h * scale * w * scale < 0x7fffffffLL, "lfsr_interp: image too large");
+  const int per = h * scale * w * scale;
+  dim3 grid(ceil_div(per, 256) < 1184 ? ceil_div(per, 256) : 1184, n);
+  interp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, n, h, w, scale, mode, block_h, block_w);
   return check_launch("interp_kernel");
 }

@@ -1,0 +1,241 @@
+// HBM/L1-bound kernels for the thin layers of the path:
+//   * conv_small_cout: KxK conv with 1..4 output channels (the 54->1 / 64->1 reconstruction heads,
+//     MyEfficientLFNet.py:70-73, EPIT.py:48): one thread per output pixel, channel-vectorised loads,
+//     weights broadcast from shared memory, residual add fused (in place on the interpolation skip).
+//   * mel_epi_branch: the whole MultiScaleEPIBlock (MyEfficientLFNet.py:278-327) in one pass:
+//     dw 1xK / Kx1 / 3x3-dilated -> 1x1 + LReLU each -> concat -> 1x1 + LReLU. One thread per pixel.
+#include "lfsr_common.cuh"
+
+namespace lfsr {
+
+// ---- small-cout conv -------------------------------------------------------------------------
+struct SmallArgs {
+  TView in, out, res;
+  const float* w;      // [tap][cin][cout]
+  const float* bias;
+  int kh, kw, dh, dw, ph, pw, cout, act;
+  float slope, alpha;
+  int tiles_x, tiles_y;
+};
+
+// Block = 32x8 output pixels. The input tile with halo is staged in shared memory with fully coalesced
+// loads (consecutive threads read consecutive 8 bytes of a pixel's channel vector); the per-pixel channel
+// stride CS satisfies CS % 8 == 4, which makes the 128-bit reads of the compute phase (lane = pixel,
+// stride CS floats) bank-conflict free. Weights are broadcast from shared memory.
+constexpr int ST_W = 32, ST_H = 8;
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv_small_cout_kernel(const SmallArgs a, int CS) {
+  extern __shared__ __align__(16) float smem[];
+  const int C = a.in.c, taps = a.kh * a.kw;
+  const int hw = ST_W + a.dw * (a.kw - 1), hh = ST_H + a.dh * (a.kh - 1);
+  float* tile = smem;                          // [hh*hw][CS]
+  float* wsm = smem + hh * hw * CS;            // [taps][COUT][CS]
+  int t_ = blockIdx.x;
+  const int tx0 = (t_ % a.tiles_x) * ST_W; t_ /= a.tiles_x;
+  const int ty0 = (t_ % a.tiles_y) * ST_H;
+  const int img = t_ / a.tiles_y;
+  const int C2 = C >> 1, CS2 = CS >> 1;
+  // weights: [tap][cin][cout] -> [tap][cout][CS] (zero padded)
+  for (int i = threadIdx.x; i < taps * COUT * CS; i += 256) {
+    const int c = i % CS, r = i / CS;
+    const int o = r % COUT, t = r / COUT;
+    wsm[i] = c < C ? __ldg(a.w + ((size_t)t * C + c) * COUT + o) : 0.f;
+  }
+  // input tile (zero outside the image = conv zero padding; zero in the CS padding lanes); a flat index keeps
+  // many independent 8-byte loads in flight per thread (a warp-per-pixel staging loop measured 1.6x slower)
+  for (int i = threadIdx.x; i < hh * hw * CS2; i += 256) {
+    const int c2 = i % CS2, pix = i / CS2;
+    const int ly = pix / hw, lx = pix - ly * hw;
+    const int iy = ty0 - a.ph + ly, ix = tx0 - a.pw + lx;
+    float2 v = make_float2(0.f, 0.f);
+    if (c2 < C2 && iy >= 0 && iy < a.in.h && ix >= 0 && ix < a.in.w)
+      v = __ldg(reinterpret_cast<const float2*>(a.in.p + a.in.pix(img, iy, ix)) + c2);
+    reinterpret_cast<float2*>(tile)[i] = v;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int ox = tx0 + lx, oy = ty0 + ly;
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+  for (int ky = 0; ky < a.kh; ++ky)
+    for (int kx = 0; kx < a.kw; ++kx) {
+      const float4* src = reinterpret_cast<const float4*>(tile + ((ly + ky * a.dh) * hw + lx + kx * a.dw) * CS);
+      const float4* wt = reinterpret_cast<const float4*>(wsm + (ky * a.kw + kx) * COUT * CS);
+#pragma unroll 4
+      for (int c4 = 0; c4 < (CS >> 2); ++c4) {
+        const float4 v = src[c4];
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+          const float4 w = wt[o * (CS >> 2) + c4];
+          acc[o] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[o]))));
+        }
+      }
+    }
+  if (ox >= a.out.w || oy >= a.out.h) return;
+  const size_t ob = a.out.pix(img, oy, ox);
+  const size_t rb = a.res.p ? a.res.pix(img, oy, ox) : 0;
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+    float v = acc[o] + (a.bias ? __ldg(a.bias + o) : 0.f);
+    v = apply_act(v, a.act, a.slope) * a.alpha;
+    if (a.res.p) v += a.res.p[rb + o];
+    a.out.p[ob + o] = v;
+  }
+}
+
+// ---- fused MultiScaleEPIBlock ---------------------------------------------------------------------
+constexpr int EC = 18;   // channels of the EPI split (54 - 2*18, MyEfficientLFNet.py:129)
+struct EpiArgs {
+  TView in, out;
+  const float* w;      // packed: dw_h[KL][EC] | dw_v[KL][EC] | dw_d[9][EC] | pw_h[EC][EC] | pw_v | pw_d | fuse[3*EC][EC]
+  int KL, dil;
+  float slope;
+  int tiles_x, tiles_y;
+};
+
+__device__ __forceinline__ void load18(const float* src, float* v) {
+#pragma unroll
+  for (int i = 0; i < EC / 2; ++i) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(src) + i);
+    v[2 * i] = t.x; v[2 * i + 1] = t.y;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mel_epi_branch_kernel(const EpiArgs a) {
+  extern __shared__ float sw[];
+  const int KL = a.KL;
+  const int n_w = (2 * KL + 9) * EC + 3 * EC * EC + 3 * EC * EC;
+  for (int i = threadIdx.x; i < n_w; i += 256) sw[i] = __ldg(a.w + i);
+  __syncthreads();
+  const float* dwh = sw;
+  const float* dwv = dwh + KL * EC;
+  const float* dwd = dwv + KL * EC;
+  const float* pw = dwd + 9 * EC;            // 3 x [EC in][EC out]
+  const float* fu = pw + 3 * EC * EC;        // [3*EC in][EC out]
+  int tile = blockIdx.x;
+  const int tx = tile % a.tiles_x; tile /= a.tiles_x;
+  const int ty = tile % a.tiles_y;
+  const int img = tile / a.tiles_y;
+  const int ox = tx * 32 + (threadIdx.x & 31), oy = ty * 8 + (threadIdx.x >> 5);
+  if (ox >= a.in.w || oy >= a.in.h) return;
+  float outv[EC];
+#pragma unroll
+  for (int o = 0; o < EC; ++o) outv[o] = 0.f;
+  const int half = KL / 2;
+#pragma unroll 1
+  for (int br = 0; br < 3; ++br) {
+    float t[EC];
+#pragma unroll
+    for (int c = 0; c < EC; ++c) t[c] = 0.f;
+    const int ntap = br == 2 ? 9 : KL;
+    for (int k = 0; k < ntap; ++k) {
+      int iy = oy, ix = ox;
+      if (br == 0) ix = ox - half + k;
+      else if (br == 1) iy = oy - half + k;
+      else { iy = oy + (k / 3 - 1) * a.dil; ix = ox + (k % 3 - 1) * a.dil; }
+      if (iy < 0 || iy >= a.in.h || ix < 0 || ix >= a.in.w) continue;
+      float v[EC];
+      load18(a.in.p + a.in.pix(img, iy, ix), v);
+      const float* wk = (br == 0 ? dwh : (br == 1 ? dwv : dwd)) + k * EC;
+#pragma unroll
+      for (int c = 0; c < EC; ++c) t[c] = fmaf(v[c], wk[c], t[c]);
+    }
+    // pointwise 1x1 + LReLU, then straight into the fuse 1x1 accumulation
+    const float* pwb = pw + br * EC * EC;
+    const float* fub = fu + br * EC * EC;
+#pragma unroll 2
+    for (int o = 0; o < EC; ++o) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < EC; ++c) s = fmaf(t[c], pwb[c * EC + o], s);
+      s = s > 0.f ? s : s * a.slope;
+#pragma unroll
+      for (int o2 = 0; o2 < EC; ++o2) outv[o2] = fmaf(s, fub[o * EC + o2], outv[o2]);
+    }
+  }
+  float* dst = a.out.p + a.out.pix(img, oy, ox);
+#pragma unroll
+  for (int i = 0; i < EC / 2; ++i) {
+    float x0 = outv[2 * i], x1 = outv[2 * i + 1];
+    x0 = x0 > 0.f ? x0 : x0 * a.slope;
+    x1 = x1 > 0.f ? x1 : x1 * a.slope;
+    reinterpret_cast<float2*>(dst)[i] = make_float2(x0, x1);
+  }
+}
+
+}  // namespace lfsr
+
+using namespace lfsr;
+
+static int small_cs(int c) { int cs = c; while (cs % 8 != 4) ++cs; return cs; }
+static size_t small_smem(const lfsr_tensor* in, const lfsr_conv_desc* d, int cout) {
+  const int cs = small_cs(in->c);
+  const int hw = ST_W + d->dil_w * (d->kw - 1), hh = ST_H + d->dil_h * (d->kh - 1);
+  return ((size_t)hh * hw * cs + (size_t)d->kh * d->kw * cout * cs) * sizeof(float);
+}
+
+extern "C" int lfsr_conv2d_small_cout_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d) {
+  if (!tensor_ok(in) || !tensor_ok(out) || !d) return 0;
+  if (out->c > 4 || d->stride_h != 1 || d->stride_w != 1 || d->in_perm || d->out_perm || d->mul.ptr || d->in_scale) return 0;
+  if (d->shuf_ry > 1 || d->shuf_rx > 1 || d->block_h > 0 || d->block_w > 0) return 0;
+  if (2 * d->pad_h != d->dil_h * (d->kh - 1) || 2 * d->pad_w != d->dil_w * (d->kw - 1)) return 0;
+  if (out->n != in->n || out->h != in->h || out->w != in->w) return 0;
+  if (in->c < 8 || (in->c & 1) || (in->ld & 1) || ((uintptr_t)in->ptr & 7)) return 0;
+  if (small_smem(in, d, out->c) > 110 * 1024) return 0;
+  return 1;
+}
+
+extern "C" int lfsr_conv2d_small_cout(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out,
+                                      const lfsr_conv_desc* d, void* stream) {
+  LFSR_REQUIRE(w_packed && lfsr_conv2d_small_cout_supported(in, out, d), "lfsr_conv2d_small_cout: unsupported problem");
+  SmallArgs a;
+  a.in = view_of(in); a.out = view_of(out);
+  a.res = d->res.ptr ? view_of(&d->res) : null_view();
+  if (d->res.ptr)
+    LFSR_REQUIRE(d->res.n == out->n && d->res.h == out->h && d->res.w == out->w && d->res.c == out->c,
+                 "lfsr_conv2d_small_cout: res geometry");
+  a.w = w_packed; a.bias = d->bias;
+  a.kh = d->kh; a.kw = d->kw; a.dh = d->dil_h; a.dw = d->dil_w; a.ph = d->pad_h; a.pw = d->pad_w;
+  a.cout = out->c; a.act = d->act; a.slope = d->act_slope; a.alpha = d->alpha;
+  a.tiles_x = ceil_div(out->w, ST_W); a.tiles_y = ceil_div(out->h, ST_H);
+  const int blocks = out->n * a.tiles_x * a.tiles_y;
+  const int cs = small_cs(in->c);
+  const size_t smem = small_smem(in, d, out->c);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_SMALL(CO)                                                                                         \
+  do {                                                                                                           \
+    static bool attr_done = false;                                                                               \
+    if (!attr_done) {                                                                                            \
+      cudaFuncSetAttribute(conv_small_cout_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); \
+      attr_done = true;                                                                                          \
+    }                                                                                                            \
+    conv_small_cout_kernel<CO><<<blocks, 256, smem, st>>>(a, cs);                                                \
+  } while (0)
+  switch (out->c) {
+    case 1: LAUNCH_SMALL(1); break;
+    case 2: LAUNCH_SMALL(2); break;
+    case 3: LAUNCH_SMALL(3); break;
+    default: LAUNCH_SMALL(4); break;
+  }
+#undef LAUNCH_SMALL
+  return check_launch("conv_small_cout_kernel");
+}
+
+extern "C" int lfsr_mel_epi_branch(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out, int klen, int dil,
+                                   float slope, void* stream) {
+  LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && w_packed, "lfsr_mel_epi_branch: null/invalid tensor");
+  LFSR_REQUIRE(in->c == EC && out->c == EC, "lfsr_mel_epi_branch: built for %d-channel EPI splits, got %d", EC, in->c);
+  LFSR_REQUIRE(in->n == out->n && in->h == out->h && in->w == out->w, "lfsr_mel_epi_branch: shape mismatch");
+  LFSR_REQUIRE(klen > 0 && (klen & 1) && klen <= 31 && dil > 0, "lfsr_mel_epi_branch: bad kernel length");
+  LFSR_REQUIRE(in->ld % 2 == 0 && out->ld % 2 == 0 && ((uintptr_t)in->ptr & 7) == 0 && ((uintptr_t)out->ptr & 7) == 0,
+               "lfsr_mel_epi_branch: 8-byte aligned channel slices required");
+  EpiArgs a;
+  a.in = view_of(in); a.out = view_of(out); a.w = w_packed; a.KL = klen; a.dil = dil; a.slope = slope;
+  a.tiles_x = ceil_div(in->w, 32); a.tiles_y = ceil_div(in->h, 8);
+  const size_t smem = ((size_t)(2 * klen + 9) * EC + 6 * EC * EC) * sizeof(float);
+  mel_epi_branch_kernel<<<in->n * a.tiles_x * a.tiles_y, 256, smem, (cudaStream_t)stream>>>(a);
+  return check_launch("mel_epi_branch_kernel");
+}

@@ -52,20 +52,23 @@ block_mean_kernel(TView in, TView out, int bh, int bw) {
 }
 
 // ---- SA modulator tail + stage residual (MyEfficientLFNet.py:495-515, 207)
+// one thread = one pixel x V consecutive channels (V = 4/2/1 by alignment)
+template <int V>
 __global__ void __launch_bounds__(256)
 sa_modulate_kernel(TView x, const float* __restrict__ dww, const float* __restrict__ bns,
-                   const float* __restrict__ bnb, TView amod, float w0, float w1, TView res, TView out, int dil,
-                   long long total) {
-  const int C = x.c;
+                   const float* __restrict__ bnb, TView amod, float w0, float w1, TView res, TView out, int dil) {
+  const int CV = x.c / V;
   const int vh = x.h / amod.h, vw = x.w / amod.w;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(t % C);
-    long long r = t / C;
-    int px = (int)(r % x.w); r /= x.w;
-    int py = (int)(r % x.h);
-    int img = (int)(r / x.h);
-    float acc = 0.f;
+  const int img = blockIdx.y;                 // 32-bit index math inside one image
+  const int per = x.h * x.w * CV;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per; t += gridDim.x * blockDim.x) {
+    const int c = (t % CV) * V;
+    const int r = t / CV;
+    const int px = r % x.w;
+    const int py = r / x.w;
+    float acc[V], xc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) { acc[e] = 0.f; xc[e] = 0.f; }
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = py + (ky - 1) * dil;
@@ -74,15 +77,36 @@ sa_modulate_kernel(TView x, const float* __restrict__ dww, const float* __restri
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = px + (kx - 1) * dil;
         if (ix < 0 || ix >= x.w) continue;
-        acc = fmaf(__ldg(x.p + x.pix(img, iy, ix) + c), __ldg(dww + (ky * 3 + kx) * C + c), acc);
+        const float* src = x.p + x.pix(img, iy, ix) + c;
+        const float* wk = dww + (ky * 3 + kx) * x.c + c;
+        float v[V];
+        if (V == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(src)); v[0] = q.x; v[1 % V] = q.y; v[2 % V] = q.z; v[3 % V] = q.w; }
+        else if (V == 2) { const float2 q = __ldg(reinterpret_cast<const float2*>(src)); v[0] = q.x; v[1 % V] = q.y; }
+        else v[0] = __ldg(src);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = fmaf(v[e], __ldg(wk + e), acc[e]);
+        if (ky == 1 && kx == 1) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) xc[e] = v[e];
+        }
       }
     }
-    const float s = 1.f / (1.f + expf(-(acc * __ldg(bns + c) + __ldg(bnb + c))));
-    const float am = __ldg(amod.p + amod.pix(img, py / vh, px / vw) + c);
-    const float xv = __ldg(x.p + x.pix(img, py, px) + c);
-    float v = xv * (w0 * s + w1 * am);
-    if (res.p) v += res.p[res.pix(img, py, px) + c];
-    out.p[out.pix(img, py, px) + c] = v;
+    const float* am = amod.p + amod.pix(img, py / vh, px / vw) + c;
+    float o[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float s = 1.f / (1.f + expf(-(acc[e] * __ldg(bns + c + e) + __ldg(bnb + c + e))));
+      o[e] = xc[e] * (w0 * s + w1 * __ldg(am + e));
+    }
+    if (res.p) {
+      const float* rs = res.p + res.pix(img, py, px) + c;
+#pragma unroll
+      for (int e = 0; e < V; ++e) o[e] += rs[e];
+    }
+    float* dst = out.p + out.pix(img, py, px) + c;
+    if (V == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]);
+    else if (V == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1 % V]);
+    else dst[0] = o[0];
   }
 }
 
@@ -303,9 +327,19 @@ extern "C" int lfsr_sa_modulate(const lfsr_tensor* x, const float* dw_w, const f
     LFSR_REQUIRE(res->n == x->n && res->h == x->h && res->w == x->w && res->c == x->c, "lfsr_sa_modulate: res shape");
     r = view_of(res);
   }
-  long long total = (long long)x->n * x->h * x->w * x->c;
-  sa_modulate_kernel<<<(int)capped_blocks(total), 256, 0, (cudaStream_t)stream>>>(
-      view_of(x), dw_w, bn_scale, bn_shift, view_of(amod), w0, w1, r, view_of(out), dil, total);
+  auto al = [](const lfsr_tensor* t, int v) { return t->ld % v == 0 && (((uintptr_t)t->ptr) & (uintptr_t)(4 * v - 1)) == 0; };
+  int V = 1;
+  for (int v = 2; v <= 4; v *= 2) {
+    if (x->c % v == 0 && al(x, v) && al(out, v) && al(amod, v) && (!r.p || al(res, v))) V = v;
+    else break;
+  }
+  LFSR_REQUIRE(x->n <= 65535, "lfsr_sa_modulate: batch too large");
+  const int per = x->h * x->w * (x->c / V);
+  dim3 blocks(ceil_div(per, 256), x->n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (V == 4) sa_modulate_kernel<4><<<blocks, 256, 0, st>>>(view_of(x), dw_w, bn_scale, bn_shift, view_of(amod), w0, w1, r, view_of(out), dil);
+  else if (V == 2) sa_modulate_kernel<2><<<blocks, 256, 0, st>>>(view_of(x), dw_w, bn_scale, bn_shift, view_of(amod), w0, w1, r, view_of(out), dil);
+  else sa_modulate_kernel<1><<<blocks, 256, 0, st>>>(view_of(x), dw_w, bn_scale, bn_shift, view_of(amod), w0, w1, r, view_of(out), dil);
   return check_launch("sa_modulate_kernel");
 }
 

@@ -19,70 +19,65 @@ void set_error(const char* fmt, ...) {
 // symmetric (edge-repeating) mirror used by ImageExtend (utils/utils.py:137-149)
 __device__ __forceinline__ int mirror(int i, int n) { return i < 0 ? -i - 1 : (i >= n ? 2 * n - 1 - i : i); }
 
-// one thread = 4 consecutive x of one patch row (same view because P % 4 == 0)
+// one thread = 4 consecutive x of one patch row (same view because P % 4 == 0);
+// blockIdx.y walks the patches of the shard so all index math is 32-bit
 __global__ void __launch_bounds__(256)
 divide_kernel(const float* __restrict__ scene, float* __restrict__ patches, int A, int h0, int w0, int P,
-              int S, int bdr, int numV, int u_begin, long long total4) {
+              int S, int bdr, int numV, int u_begin, int npatch) {
   const int row = A * P;            // floats per patch row
   const int row4 = row >> 2;
+  const int per_patch4 = row * row4;
   const int sw = A * w0;            // scene row stride
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total4;
-       t += (long long)gridDim.x * blockDim.x) {
-    int x4 = (int)(t % row4);
-    long long r = t / row4;
-    int py = (int)(r % row);
-    long long pidx = r / row;       // patch index within the shard
-    int n2 = (int)(pidx % numV);
-    int n1 = (int)(pidx / numV) + u_begin;
-    int a1 = py / P, y = py - a1 * P;
-    int px = x4 << 2;
-    int a2 = px / P, x = px - a2 * P;
-    int sy = mirror(n1 * S + y - bdr, h0);
-    const float* src = scene + (size_t)(a1 * h0 + sy) * sw + a2 * w0;
-    int gx = n2 * S + x - bdr;
-    float4 v;
-    v.x = __ldg(src + mirror(gx, w0));
-    v.y = __ldg(src + mirror(gx + 1, w0));
-    v.z = __ldg(src + mirror(gx + 2, w0));
-    v.w = __ldg(src + mirror(gx + 3, w0));
-    reinterpret_cast<float4*>(patches)[t] = v;
-  }
-}
-
-template <int VEC>
-__global__ void __launch_bounds__(256)
-integrate_kernel(const float* __restrict__ patches, float* __restrict__ out, int A, int pz, int ss, int h,
-                 int w, int numV, int u_begin, int y_begin, int y_count, long long total) {
-  const int wv = w / VEC;           // vectors per view row
-  const int bdr = (pz - ss) / 2;
-  const size_t prow = (size_t)A * pz;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    int xv = (int)(t % wv);
-    long long r = t / wv;
-    int a2 = (int)(r % A); r /= A;
-    int yl = (int)(r % y_count);
-    int a1 = (int)(r / y_count);
-    int Y = y_begin + yl, X = xv * VEC;
-    int n1 = Y / ss, n2 = X / ss;
-    const float* src = patches + ((size_t)(n1 - u_begin) * numV + n2) * prow * prow +
-                       (size_t)(a1 * pz + bdr + (Y - n1 * ss)) * prow + a2 * pz + bdr + (X - n2 * ss);
-    float* dst = out + (size_t)(a1 * h + Y) * ((size_t)A * w) + (size_t)a2 * w + X;
-    if (VEC == 4) {
-      *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(src));
-    } else {
-      *dst = __ldg(src);
+  for (int pidx = blockIdx.y; pidx < npatch; pidx += gridDim.y) {
+    const int n2 = pidx % numV;
+    const int n1 = pidx / numV + u_begin;
+    float4* dst = reinterpret_cast<float4*>(patches) + (size_t)pidx * per_patch4;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per_patch4; t += gridDim.x * blockDim.x) {
+      const int x4 = t % row4;
+      const int py = t / row4;
+      const int a1 = py / P, y = py - a1 * P;
+      const int px = x4 << 2;
+      const int a2 = px / P, x = px - a2 * P;
+      const int sy = mirror(n1 * S + y - bdr, h0);
+      const float* src = scene + (size_t)(a1 * h0 + sy) * sw + a2 * w0;
+      const int gx = n2 * S + x - bdr;
+      float4 v;
+      v.x = __ldg(src + mirror(gx, w0));
+      v.y = __ldg(src + mirror(gx + 1, w0));
+      v.z = __ldg(src + mirror(gx + 2, w0));
+      v.w = __ldg(src + mirror(gx + 3, w0));
+      dst[t] = v;
     }
   }
 }
 
-static int grid_for(long long work_items, int block) {
-  long long blocks = (work_items + block - 1) / block;
-  const long long cap = 148LL * 16;  // 16 resident CTAs of 256 threads worth of waves per SM
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return (int)blocks;
+// blockIdx.y walks (view row a1, output row Y); x covers (a2, X / VEC)
+template <int VEC>
+__global__ void __launch_bounds__(256)
+integrate_kernel(const float* __restrict__ patches, float* __restrict__ out, int A, int pz, int ss, int h,
+                 int w, int numV, int u_begin, int y_begin, int y_count) {
+  const int wv = w / VEC;           // vectors per view row
+  const int bdr = (pz - ss) / 2;
+  const size_t prow = (size_t)A * pz;
+  for (int ry = blockIdx.y; ry < A * y_count; ry += gridDim.y) {
+    const int a1 = ry / y_count;
+    const int Y = y_begin + (ry - a1 * y_count);
+    const int n1 = Y / ss;
+    const float* prow_base = patches + (size_t)(n1 - u_begin) * numV * prow * prow +
+                             (size_t)(a1 * pz + bdr + (Y - n1 * ss)) * prow;
+    float* orow = out + (size_t)(a1 * h + Y) * ((size_t)A * w);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < A * wv; t += gridDim.x * blockDim.x) {
+      const int a2 = t / wv;
+      const int X = (t - a2 * wv) * VEC;
+      const int n2 = X / ss;
+      const float* src = prow_base + (size_t)n2 * prow * prow + a2 * pz + bdr + (X - n2 * ss);
+      float* dst = orow + (size_t)a2 * w + X;
+      if (VEC == 4) *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(src));
+      else *dst = __ldg(src);
+    }
+  }
 }
+
 
 }  // namespace lfsr
 
@@ -108,9 +103,11 @@ extern "C" int lfsr_divide_rows(const float* scene, float* patches, int ang, int
   LFSR_REQUIRE(0 <= u_begin && u_begin <= u_end && u_end <= numU, "lfsr_divide: row shard [%d,%d) outside [0,%d)",
                u_begin, u_end, numU);
   if (u_begin == u_end) return LFSR_OK;
-  const long long total4 = (long long)(u_end - u_begin) * numV * (ang * patch) * (ang * patch / 4);
-  divide_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(scene, patches, ang, h0, w0, patch, stride,
-                                                                           bdr, numV, u_begin, total4);
+  const int npatch = (u_end - u_begin) * numV;
+  const int per_patch4 = (ang * patch) * (ang * patch / 4);
+  dim3 grid(ceil_div(per_patch4, 256 * 4), npatch < 32768 ? npatch : 32768);
+  divide_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(scene, patches, ang, h0, w0, patch, stride, bdr, numV, u_begin,
+                                                        npatch);
   return check_launch("divide_kernel");
 }
 
@@ -137,14 +134,15 @@ extern "C" int lfsr_integrate_rows(const float* patches, float* out, int ang, in
   const int bdr = (pz - stride) / 2;
   const bool vec = (w % 4 == 0) && (stride % 4 == 0) && (pz % 4 == 0) && (bdr % 4 == 0) &&
                    ((uintptr_t)patches % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  const int rows = ang * y_count;
   if (vec) {
-    long long total = (long long)ang * y_count * ang * (w / 4);
-    integrate_kernel<4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        patches, out, ang, pz, stride, h, w, num_v, u_begin, y_begin, y_count, total);
+    dim3 grid(ceil_div(ang * (w / 4), 256), rows < 32768 ? rows : 32768);
+    integrate_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(patches, out, ang, pz, stride, h, w, num_v, u_begin,
+                                                                y_begin, y_count);
   } else {
-    long long total = (long long)ang * y_count * ang * w;
-    integrate_kernel<1><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        patches, out, ang, pz, stride, h, w, num_v, u_begin, y_begin, y_count, total);
+    dim3 grid(ceil_div(ang * w, 256), rows < 32768 ? rows : 32768);
+    integrate_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(patches, out, ang, pz, stride, h, w, num_v, u_begin,
+                                                                y_begin, y_count);
   }
   return check_launch("integrate_kernel");
 }

@@ -150,6 +150,10 @@ class CudaOps:
         if x.shape[3] != pc.cin:
             raise N.LfsrError(f"conv: input has {x.shape[3]} channels, weights expect {pc.cin}")
         st = self._stream(x)
+        if pc.cout <= 4 and self.lib.lfsr_conv2d_small_cout_supported(C.byref(tin), C.byref(tout), C.byref(d)):
+            N.check(self.lib.lfsr_conv2d_small_cout(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st),
+                    "lfsr_conv2d_small_cout")
+            return
         r2 = shuffle[0] * shuffle[1]
         perm_ok = pc.tc_perm_r2 == (r2 if (r2 > 1 and shuffle[2] == N.SHUF_CHANNEL_MAJOR) else 0)
         if (self.use_tc and pc.w_tc is not None and perm_ok and
@@ -164,6 +168,11 @@ class CudaOps:
         N.check(self.lib.lfsr_dwconv_f32(C.byref(as_tensor(x, "dwconv.in")), w.data_ptr(), self._ptr(scale),
                                          self._ptr(shift), C.byref(as_tensor(out, "dwconv.out")), kh, kw, dil[0],
                                          dil[1], act, slope, self._stream(x)), "lfsr_dwconv_f32")
+
+    def mel_epi_branch(self, x, w_packed, out, klen, dil, slope):
+        N.check(self.lib.lfsr_mel_epi_branch(C.byref(as_tensor(x, "epi.in")), w_packed.data_ptr(),
+                                             C.byref(as_tensor(out, "epi.out")), klen, dil, slope, self._stream(x)),
+                "lfsr_mel_epi_branch")
 
     # -- reductions / gates -------------------------------------------------------------------------
     def block_mean(self, x, out, bh, bw):

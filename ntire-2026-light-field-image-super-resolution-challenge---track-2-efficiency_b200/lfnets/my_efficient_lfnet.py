@@ -141,71 +141,102 @@ class get_model(LFNetBase):
         self.upsampler = _UpsamplerParams(c, self.scale)
         self.output_conv = _conv(c, 1, 3, stride=1, padding=1, bias=True)
 
+    # -- channel layout ------------------------------------------------------------------------------
+    # The 54 trunk channels are the concat of three 18-channel branches. They live in HBM as three groups
+    # of GS = 20 floats (18 real + 2 always-zero pad): every branch slice then starts 16-byte aligned, which
+    # is what lets the 18-channel convs run on the TMA/tcgen05 path and the elementwise kernels use 128-bit
+    # accesses. Weights of 54-channel producers/consumers are expanded with zero rows/columns accordingly.
+    def _groups(self):
+        c = self.channels
+        sp = [c // 3, c // 3, c - 2 * (c // 3)]
+        gs = (max(sp) + 3) // 4 * 4
+        return sp, gs
+
+    def _exp(self, t, dim, fill=0.0):
+        """insert the pad channels along `dim` of a tensor whose size there is self.channels"""
+        sp, gs = self._groups()
+        shape = list(t.shape)
+        shape[dim] = gs * len(sp)
+        out = t.new_full(shape, fill)
+        o = 0
+        for g, n in enumerate(sp):
+            out.narrow(dim, g * gs, n).copy_(t.narrow(dim, o, n))
+            o += n
+        return out
+
     # -- pack ---------------------------------------------------------------------------------------
     def _pack(self, device, ops):
         A = self.angRes
-        pc = lambda w, b=None, **kw: K.pack_conv(w, b, device=device, **kw)
+        pc = lambda w, b=None, **kw: K.pack_conv(w.detach().float().cpu(), None if b is None else b.detach().float().cpu(),
+                                                 device=device, **kw)
         dil = dict(dil=(A, A), pad=(A, A))
+        dev_t = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
         pk = {}
         w, b = self.shallow_feat.merged()
-        pk["stem"] = pc(w, b, **dil)
+        pk["stem"] = pc(self._exp(w, 0), self._exp(b, 0), **dil)
         stages = []
         for st in self.stages:
             s = {}
             w, b = st.spatial_branch["0"].merged()
-            s["spa0"] = pc(w, b, **dil)
-            s["spa2"] = pc(st.spatial_branch["2"].weight, **dil)
+            s["spa0"] = pc(w, b, tc=True, **dil)
+            s["spa2"] = pc(st.spatial_branch["2"].weight, tc=True, **dil)
             ab = st.angular_branch
             s["ang_to"] = pc(ab.to_angular.weight, stride=(A, A))
             s["ang_a0"] = pc(ab.attention["0"].weight)
             s["ang_a2"] = _dw_pack(ab.attention["2"].weight, device)
             s["ang_a4"] = pc(ab.attention["4"].weight)
             s["ang_cv"] = pc(ab.cross_view["0"].weight, pad=(1, 1))
-            s["ang_ex"] = pc(ab.expand["0"].weight)
+            s["ang_ex"] = pc(ab.expand["0"].weight, tc=True, tc_shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
             s["ang_scale"] = float(ab.scale.detach().item())
             eb = st.epi_branch
-            s["epi_h_dw"] = _dw_pack(eb.epi_h["0"].weight, device)
-            s["epi_v_dw"] = _dw_pack(eb.epi_v["0"].weight, device)
-            s["epi_d_dw"] = _dw_pack(eb.epi_diag["0"].weight, device)
-            s["epi_h_pw"] = pc(eb.epi_h["1"].weight)
-            s["epi_v_pw"] = pc(eb.epi_v["1"].weight)
-            s["epi_d_pw"] = pc(eb.epi_diag["1"].weight)
-            s["epi_fuse"] = pc(eb.fuse["0"].weight)
-            # three gate FCs as one block-diagonal 1x1 (MyEfficientLFNet.py:159-173)
-            sp = st.split
-            C = sum(sp)
-            gw = torch.zeros(C, C, 1, 1)
-            gb = torch.zeros(C)
-            o = 0
-            for g, n in zip((st.gate_spatial, st.gate_angular, st.gate_epi), sp):
-                gw[o:o + n, o:o + n] = g["1"].weight.detach().cpu()
-                gb[o:o + n] = g["1"].bias.detach().cpu()
-                o += n
+            pw_t = lambda m: m.weight.detach().float()[:, :, 0, 0].t().contiguous().reshape(-1).cpu()   # [in][out]
+            dw_t = lambda m: _dw_pack(m.weight, "cpu").reshape(-1)
+            s["epi_w"] = torch.cat([dw_t(eb.epi_h["0"]), dw_t(eb.epi_v["0"]), dw_t(eb.epi_diag["0"]),
+                                    pw_t(eb.epi_h["1"]), pw_t(eb.epi_v["1"]), pw_t(eb.epi_diag["1"]),
+                                    pw_t(eb.fuse["0"])]).to(device)
+            s["epi_klen"] = eb.epi_h["0"].weight.shape[-1]
+            # three gate FCs as one block-diagonal 1x1 over the grouped layout (MyEfficientLFNet.py:159-173)
+            sp, gs = self._groups()
+            CP = gs * len(sp)
+            gw = torch.zeros(CP, CP, 1, 1)
+            gb = torch.zeros(CP)
+            for g, (gate, n) in enumerate(zip((st.gate_spatial, st.gate_angular, st.gate_epi), sp)):
+                gw[g * gs:g * gs + n, g * gs:g * gs + n] = gate["1"].weight.detach().float().cpu()
+                gb[g * gs:g * gs + n] = gate["1"].bias.detach().float().cpu()
             s["gate"] = pc(gw, gb)
-            s["fus0"] = pc(st.fusion["0"].weight)
-            s["fus2"] = pc(st.fusion["2"].weight, tc=True, **dil)
+            s["fus0"] = pc(self._exp(st.fusion["0"].weight.detach().float().cpu(), 1))
+            s["fus2"] = pc(self._exp(st.fusion["2"].weight.detach().float().cpu(), 0), tc=True, **dil)
             sm = st.sa_modulator
-            s["sa_dw"] = _dw_pack(sm.spatial_mod["0"].weight, device)
+            s["sa_dw"] = dev_t(self._exp(_dw_pack(sm.spatial_mod["0"].weight, "cpu"), 1))
             sc, sh = bn_affine(sm.spatial_mod["1"])
-            s["sa_bns"] = sc.to(device=device, dtype=torch.float32).contiguous()
-            s["sa_bnb"] = sh.to(device=device, dtype=torch.float32).contiguous()
-            s["sa_c0"] = pc(sm.angular_conv["0"].weight)
-            s["sa_c2"] = pc(sm.angular_conv["2"].weight)
+            s["sa_bns"] = dev_t(self._exp(sc.float().cpu(), 0, 1.0))
+            s["sa_bnb"] = dev_t(self._exp(sh.float().cpu(), 0))
+            s["sa_c0"] = pc(self._exp(sm.angular_conv["0"].weight.detach().float().cpu(), 1))
+            s["sa_c2"] = pc(self._exp(sm.angular_conv["2"].weight.detach().float().cpu(), 0))
             wts = torch.softmax(sm.combine.detach().float(), dim=0)
             s["sa_w"] = (float(wts[0]), float(wts[1]))
             stages.append(s)
         pk["stages"] = stages
-        pk["gf0"] = pc(self.global_fusion["0"].weight)
+        pk["gf0"] = pc(self._exp(self.global_fusion["0"].weight.detach().float().cpu(), 1), tc=True)
         w, b = self.global_fusion["2"].merged()
-        pk["gf2"] = pc(w, b, tc=True, **dil)
-        pk["up"] = [(pc(self.upsampler.up[str(i)].weight, pad=(1, 1), tc=True, tc_shuffle=(r, r, N.SHUF_CHANNEL_MAJOR)), r)
-                    for i, r in self.upsampler.steps]
-        pk["out"] = pc(self.output_conv.weight, self.output_conv.bias, pad=(1, 1), tc=True)
+        pk["gf2"] = pc(self._exp(w.float().cpu(), 0), self._exp(b.float().cpu(), 0), tc=True, **dil)
+        ups = []
+        for j, (i, r) in enumerate(self.upsampler.steps):
+            w = self.upsampler.up[str(i)].weight.detach().float().cpu()
+            if j == 0:
+                w = self._exp(w, 1)          # reads the grouped trunk
+            ups.append((pc(w, pad=(1, 1), tc=True, tc_shuffle=(r, r, N.SHUF_CHANNEL_MAJOR)), r))
+        pk["up"] = ups
+        pk["out"] = pc(self.output_conv.weight, self.output_conv.bias, pad=(1, 1))
         return pk
 
     # -- run ------------------------------------------------------------------------------------------
     def _run(self, ops, pk, x, out):
         A, s, C = self.angRes, self.scale, self.channels
+        sp, gs = self._groups()
+        CP = gs * len(sp)
+        c0 = sp[0]
+        sl = [slice(g * gs, g * gs + n) for g, n in enumerate(sp)]
         B, _, H, W = x.shape
         dev = x.device
         buf = lambda name, h, w, c: self._buf(name, B, h, w, c, dev)
@@ -214,56 +245,46 @@ class get_model(LFNetBase):
         Y = out.view(B, H * s, W * s, 1)
         ops.interp(x, out, B, H, W, s, N.INTERP_BICUBIC, H, W)
 
-        shallow = buf("shallow", H, W, C)
+        shallow = buf("shallow", H, W, CP)
         ops.conv(xin, pk["stem"], shallow)
         feat = shallow
-        pp = [buf("feat_a", H, W, C), buf("feat_b", H, W, C)]
-        c0 = C // 3
+        pp = [buf("feat_a", H, W, CP), buf("feat_b", H, W, CP)]
         hA, wA = H // A, W // A
-        cat = buf("cat", H, W, C)
+        cat = buf("cat", H, W, CP)
         t18 = buf("t18", H, W, c0)
-        ecat = buf("ecat", H, W, 3 * (C - 2 * c0))
         hid = pk["stages"][0]["ang_a0"].cout
         ang1, ang4, ang5 = buf("ang1", hA, wA, c0), buf("ang4", hA, wA, c0), buf("ang5", hA, wA, c0)
         ang2, ang3 = buf("ang2", hA, wA, hid), buf("ang3", hA, wA, hid)
-        vmean, gmean, gate = buf("vmean", A, A, C), buf("gmean", 1, 1, C), buf("gate", 1, 1, C)
-        fu1, fu2 = buf("fu1", H, W, C), buf("fu2", H, W, C)
-        pm, am1, am = buf("pm", A, A, C), buf("am1", A, A, C // 4), buf("am", A, A, C)
-        for i, sp in enumerate(pk["stages"]):
-            xs, xa, xe = feat[..., 0:c0], feat[..., c0:2 * c0], feat[..., 2 * c0:C]
-            ce = C - 2 * c0
+        vmean, gmean, gate = buf("vmean", A, A, CP), buf("gmean", 1, 1, CP), buf("gate", 1, 1, CP)
+        fu1, fu2 = buf("fu1", H, W, C), buf("fu2", H, W, CP)
+        pm, am1, am = buf("pm", A, A, CP), buf("am1", A, A, C // 4), buf("am", A, A, CP)
+        for i, st in enumerate(pk["stages"]):
+            xs, xa, xe = feat[..., sl[0]], feat[..., sl[1]], feat[..., sl[2]]
             # spatial branch
-            ops.conv(xs, sp["spa0"], t18, act=LR, slope=0.1)
-            ops.conv(t18, sp["spa2"], cat[..., 0:c0])
+            ops.conv(xs, st["spa0"], t18, act=LR, slope=0.1)
+            ops.conv(t18, st["spa2"], cat[..., sl[0]])
             # angular branch
-            ops.conv(xa, sp["ang_to"], ang1)
-            ops.conv(ang1, sp["ang_a0"], ang2, act=N.ACT_RELU)
-            ops.dwconv(ang2, sp["ang_a2"], ang3, 3, 3, act=N.ACT_RELU)
-            ops.conv(ang3, sp["ang_a4"], ang4, act=N.ACT_SIGMOID, mul=ang1)
-            ops.conv(ang4, sp["ang_cv"], ang5, act=LR, slope=0.1)
-            ops.conv(ang5, sp["ang_ex"], cat[..., c0:2 * c0], act=LR, slope=0.1, alpha=sp["ang_scale"], res=xa,
+            ops.conv(xa, st["ang_to"], ang1)
+            ops.conv(ang1, st["ang_a0"], ang2, act=N.ACT_RELU)
+            ops.dwconv(ang2, st["ang_a2"], ang3, 3, 3, act=N.ACT_RELU)
+            ops.conv(ang3, st["ang_a4"], ang4, act=N.ACT_SIGMOID, mul=ang1)
+            ops.conv(ang4, st["ang_cv"], ang5, act=LR, slope=0.1)
+            ops.conv(ang5, st["ang_ex"], cat[..., sl[1]], act=LR, slope=0.1, alpha=st["ang_scale"], res=xa,
                      shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
-            # EPI branch
-            te = t18[..., 0:ce] if ce == c0 else buf("te", H, W, ce)
-            ops.dwconv(xe, sp["epi_h_dw"], te, 1, 2 * A + 1)
-            ops.conv(te, sp["epi_h_pw"], ecat[..., 0:ce], act=LR, slope=0.1)
-            ops.dwconv(xe, sp["epi_v_dw"], te, 2 * A + 1, 1)
-            ops.conv(te, sp["epi_v_pw"], ecat[..., ce:2 * ce], act=LR, slope=0.1)
-            ops.dwconv(xe, sp["epi_d_dw"], te, 3, 3, dil=(A, A))
-            ops.conv(te, sp["epi_d_pw"], ecat[..., 2 * ce:3 * ce], act=LR, slope=0.1)
-            ops.conv(ecat, sp["epi_fuse"], cat[..., 2 * c0:C], act=LR, slope=0.1)
+            # EPI branch: three depthwise+pointwise paths and their fuse conv in one kernel
+            ops.mel_epi_branch(xe, st["epi_w"], cat[..., sl[2]], st["epi_klen"], A, 0.1)
             # gates -> per-sample channel scale of the fusion 1x1
             ops.block_mean(cat, vmean, hA, wA)
             ops.block_mean(vmean, gmean, A, A)
-            ops.conv(gmean, sp["gate"], gate, act=N.ACT_SIGMOID)
-            ops.conv(cat, sp["fus0"], fu1, act=LR, slope=0.1, in_scale=gate)
-            ops.conv(fu1, sp["fus2"], fu2)
+            ops.conv(gmean, st["gate"], gate, act=N.ACT_SIGMOID)
+            ops.conv(cat, st["fus0"], fu1, act=LR, slope=0.1, in_scale=gate)
+            ops.conv(fu1, st["fus2"], fu2)
             # SA modulator + stage residual
             ops.block_mean(fu2, pm, hA, wA)
-            ops.conv(pm, sp["sa_c0"], am1, act=N.ACT_RELU)
-            ops.conv(am1, sp["sa_c2"], am, act=N.ACT_SIGMOID)
+            ops.conv(pm, st["sa_c0"], am1, act=N.ACT_RELU)
+            ops.conv(am1, st["sa_c2"], am, act=N.ACT_SIGMOID)
             nxt = pp[i & 1]
-            ops.sa_modulate(fu2, sp["sa_dw"], sp["sa_bns"], sp["sa_bnb"], am, sp["sa_w"][0], sp["sa_w"][1], feat, nxt, A)
+            ops.sa_modulate(fu2, st["sa_dw"], st["sa_bns"], st["sa_bnb"], am, st["sa_w"][0], st["sa_w"][1], feat, nxt, A)
             feat = nxt
         ops.conv(feat, pk["gf0"], fu1, act=LR, slope=0.1)
         ops.conv(fu1, pk["gf2"], fu2, res=shallow)
@@ -273,7 +294,6 @@ class get_model(LFNetBase):
             ops.conv(cur, pcv, nb, act=LR, slope=0.1, shuffle=(r, r, N.SHUF_CHANNEL_MAJOR))
             cur, ch, cw = nb, ch * r, cw * r
         ops.conv(cur, pk["out"], Y, res=Y)
-
 
     # -- measurement hook --------------------------------------------------------------------------
     def dominant_kernel(self, batch: int, h: int = 32):
@@ -287,7 +307,7 @@ class get_model(LFNetBase):
         pcv, r = pk["up"][-1]
         hin = A * h * (self.scale // r)
         src = self._buf(f"up{len(pk['up']) - 2}", batch, hin, hin, C, dev) if len(pk["up"]) > 1 else \
-            self._buf("fu2", batch, hin, hin, C, dev)
+            self._buf("fu2", batch, hin, hin, pcv.cin, dev)
         dst = self._buf(f"up{len(pk['up']) - 1}", batch, hin * r, hin * r, C, dev)
         info = {
             "name": "conv3x3 %d->%d + PixelShuffle(%d) + LReLU @%dx%d (upsampler.up.%s)" % (C, pcv.cout, r, hin, hin,

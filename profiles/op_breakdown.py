@@ -35,6 +35,9 @@ class ProfilingOps(K.CudaOps):
     def dwconv(self, x, w, out, kh, kw, **k2):
         self._wrap("dwconv", lambda: K.CudaOps.dwconv(self, x, w, out, kh, kw, **k2), f"dwconv {kh}x{kw} c{x.shape[3]} @{x.shape[1]}x{x.shape[2]}")
 
+    def mel_epi_branch(self, x, w, out, klen, dil, slope):
+        self._wrap("mel_epi_branch", lambda: K.CudaOps.mel_epi_branch(self, x, w, out, klen, dil, slope), f"mel_epi_branch c{x.shape[3]} @{x.shape[1]}x{x.shape[2]}")
+
     def block_mean(self, x, out, bh, bw):
         self._wrap("block_mean", lambda: K.CudaOps.block_mean(self, x, out, bh, bw), f"block_mean {bh}x{bw} c{x.shape[3]} @{x.shape[1]}")
 

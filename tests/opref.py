@@ -103,6 +103,25 @@ class RefOps:
             y = y * scale.view(1, c, 1, 1) + shift.view(1, c, 1, 1)
         out.copy_(_act(y, act, slope).permute(0, 2, 3, 1))
 
+    def mel_epi_branch(self, x, w_packed, out, klen, dil, slope):
+        c = x.shape[3]
+        o = 0
+        def take(n, shape):
+            nonlocal o
+            t = w_packed[o:o + n].view(*shape)
+            o += n
+            return t
+        dwh, dwv, dwd = take(klen * c, (klen, c)), take(klen * c, (klen, c)), take(9 * c, (9, c))
+        pws = [take(c * c, (c, c)) for _ in range(3)]
+        fu = take(3 * c * c, (3 * c, c))
+        xi = _nchw(x)
+        h = F.conv2d(xi, dwh.t().reshape(c, 1, 1, klen), None, 1, (0, klen // 2), 1, c)
+        v = F.conv2d(xi, dwv.t().reshape(c, 1, klen, 1), None, 1, (klen // 2, 0), 1, c)
+        d = F.conv2d(xi, dwd.t().reshape(c, 1, 3, 3), None, 1, dil, dil, c)
+        outs = [F.leaky_relu(F.conv2d(t, pw.t().reshape(c, c, 1, 1)), slope) for t, pw in zip((h, v, d), pws)]
+        y = F.leaky_relu(F.conv2d(torch.cat(outs, 1), fu.t().reshape(c, 3 * c, 1, 1)), slope)
+        out.copy_(y.permute(0, 2, 3, 1))
+
     # -- reductions / gates --------------------------------------------------------------------------
     def block_mean(self, x, out, bh, bw):
         n, h, w, c = x.shape

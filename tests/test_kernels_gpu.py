@@ -309,3 +309,54 @@ def test_conv_tc(ref, case):
     print(f"tc conv {case}: max err {err:.3e} (ref max {scale:.3f})")
     assert lib.lfsr_launch_count() == l0 + 1
     assert err <= 2e-3 * scale, f"max err {err}"
+
+
+def test_mel_epi_branch(ops, ref):
+    n, h, w, c, klen, A = 2, 40, 40, 18, 11, 5
+    full = nhwc(n, h, w, 60, seed=1)
+    x = full[..., 40:58]
+    wts = rnd((2 * klen + 9) * c + 6 * c * c, seed=2) * 0.3
+    a_full, b_full = nhwc(n, h, w, 60, seed=3), nhwc(n, h, w, 60, seed=3)
+    ops.mel_epi_branch(x, wts, a_full[..., 40:58], klen, A, 0.1)
+    ref.mel_epi_branch(x, wts, b_full[..., 40:58], klen, A, 0.1)
+    assert (a_full - b_full).abs().max().item() <= 2e-5
+    assert torch.equal(a_full[..., 58:], b_full[..., 58:]) and torch.equal(a_full[..., :40], b_full[..., :40])
+
+
+@pytest.mark.parametrize("cin,cout,k,dil", [(54, 1, 3, 1), (64, 1, 3, 1), (64, 3, 3, 5), (18, 2, 1, 1), (60, 4, 3, 1)])
+def test_conv_small_cout(ops, ref, cin, cout, k, dil):
+    n, h, w = 2, 50, 70
+    g = torch.Generator().manual_seed(cin + cout)
+    wt = (torch.rand(cout, cin, k, k, generator=g) - 0.5) * 0.2
+    bias = torch.rand(cout, generator=g) - 0.5
+    pad = dil * (k - 1) // 2
+    pc = K.pack_conv(wt, bias, dil=(dil, dil), pad=(pad, pad), device=DEV)
+    x = nhwc(n, h, w, cin, seed=3)
+    a = rnd(n, h, w, cout, seed=4)
+    b = a.clone()
+    l0 = ops.lib.lfsr_launch_count()
+    ops.conv(x, pc, a, res=a, act=2, slope=0.2, alpha=0.5)
+    ref.conv(x, pc, b, res=b.clone(), act=2, slope=0.2, alpha=0.5)
+    assert ops.lib.lfsr_launch_count() == l0 + 1
+    assert (a - b).abs().max().item() <= 2e-5
+
+
+def test_conv_tc_18ch_slices(ref):
+    """18-channel branch slices of the grouped 60-channel trunk run on the tensor-core path."""
+    tc_ops = K.CudaOps(use_tc=True)
+    n, h, w = 2, 160, 160
+    trunk = nhwc(n, h, w, 60, seed=1)
+    cat_a, cat_b = nhwc(n, h, w, 60, seed=2), nhwc(n, h, w, 60, seed=2)
+    wt = (torch.rand(18, 18, 3, 3) - 0.5) * 0.3
+    pc = K.pack_conv(wt, torch.rand(18) - 0.5, dil=(5, 5), pad=(5, 5), device=DEV, tc=True)
+    for sl in (slice(0, 18), slice(20, 38), slice(40, 58)):
+        tc_ops.conv(trunk[..., sl], pc, cat_a[..., sl], act=2, slope=0.1)
+        ref.conv(trunk[..., sl], pc, cat_b[..., sl], act=2, slope=0.1)
+    assert (cat_a - cat_b).abs().max().item() <= 2e-3
+    ang = nhwc(n, 32, 32, 18, seed=5)
+    wt2 = (torch.rand(450, 18, 1, 1) - 0.5) * 0.3
+    pc2 = K.pack_conv(wt2, device=DEV, tc=True, tc_shuffle=(5, 5, 0))
+    kw = dict(act=2, slope=0.1, alpha=0.1, res=trunk[..., 20:38], shuffle=(5, 5, 0))
+    tc_ops.conv(ang, pc2, cat_a[..., 20:38], **kw)
+    ref.conv(ang, pc2, cat_b[..., 20:38], **kw)
+    assert (cat_a - cat_b).abs().max().item() <= 2e-3
