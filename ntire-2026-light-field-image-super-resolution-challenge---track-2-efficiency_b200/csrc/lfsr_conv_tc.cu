@@ -16,6 +16,7 @@
 // TF32: activations are converted by the TMA unit (tensor map type TFLOAT32), weights are rounded
 // to nearest-even at pack time; accumulation is fp32.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include "lfsr_common.cuh"
@@ -171,13 +172,20 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int t, int chu
 // Coalesced write-out of a warp's staged [32 pixels][<=32 packed channels] block. V floats per lane.
 // packed channel pc = sub*cq + c ("factor-major": the weights are packed in that order when an
 // nn.PixelShuffle is fused), sub = i*rx + j selects the output pixel of the shuffle.
-template <int V>
+// Everything that does not depend on the pixel row is hoisted: the loop body is ~25 instructions.
+template <int ACT>
+__device__ __forceinline__ float act_t(float v, float slope) {
+  if (ACT == LFSR_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == LFSR_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (ACT == LFSR_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+
+template <int V, int ACT>
 __device__ __forceinline__ void epi_writeout(const Params& p, const float* stg, int lane, int q, const TileCoord& tc_, int pc0,
                                              int ncols) {
   constexpr int LPR = 32 / V;   // lanes per pixel row
   const int r2 = p.ry * p.rx;
-  const int img = tc_.nb / p.nby;
-  const int ybase = (tc_.nb - img * p.nby) * p.bh;
   const int col = (lane % LPR) * V;
   const int pc = pc0 + col;
   if (col >= ncols || pc >= p.cout) return;
@@ -188,30 +196,51 @@ __device__ __forceinline__ void epi_writeout(const Params& p, const float* stg, 
   float bv[V];
 #pragma unroll
   for (int e = 0; e < V; ++e) bv[e] = p.bias ? __ldg(p.bias + (chan_major ? (c + e) * r2 + sub : pc + e)) : 0.f;
+  const int img = tc_.nb / p.nby;
+  const int oy0 = ((tc_.nb - img * p.nby) * p.bh + tc_.y0) * p.ry + si;      // output row of tile pixel (0,0)
+  const int ox0 = (tc_.vx * p.bw + tc_.x0) * p.rx + sj;
+  float* const obase = p.out.p + p.out.pix(img, oy0, ox0) + c;
+  const float* const rbase = p.res.p ? p.res.p + p.res.pix(img, oy0, ox0) + c : nullptr;
+  const int o_py = p.ry * p.out.w * p.out.ld, o_px = p.rx * p.out.ld;         // float pitch per tile row / column
+  const int r_py = p.ry * p.res.w * p.res.ld, r_px = p.rx * p.res.ld;
+  const bool full = tc_.y0 + p.TH <= p.bh && tc_.x0 + p.TW <= p.bw;
+  const int tw_mask = p.TW - 1;
+  const float slope = p.slope, alpha = p.alpha;
+  const int swz_hi = col >> 2, swz_lo = col & 3;
 #pragma unroll 4
   for (int it = 0; it < LPR; ++it) {
     const int r = it * V + lane / LPR;
     const int m = q * 32 + r;
-    const int yb = tc_.y0 + (m >> p.tw_shift), xb = tc_.x0 + (m & (p.TW - 1));
-    if (yb >= p.bh || xb >= p.bw) continue;
-    const float* src = stg + r * 32 + ((((col >> 2) ^ (r & 7)) << 2) | (col & 3));
+    const int ty = m >> p.tw_shift, tx = m & tw_mask;
+    if (!full && (tc_.y0 + ty >= p.bh || tc_.x0 + tx >= p.bw)) continue;
+    const float* src = stg + r * 32 + (((swz_hi ^ (r & 7)) << 2) | swz_lo);
     float v[V];
-    if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(src); v[0] = t.x; v[1] = t.y; v[2 % V] = t.z; v[3 % V] = t.w; }
+    if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(src); v[0] = t.x; v[1 % V] = t.y; v[2 % V] = t.z; v[3 % V] = t.w; }
     else if (V == 2) { const float2 t = *reinterpret_cast<const float2*>(src); v[0] = t.x; v[1 % V] = t.y; }
     else v[0] = *src;
-    const int sy = (ybase + yb) * p.ry + si, sx = (tc_.vx * p.bw + xb) * p.rx + sj;
 #pragma unroll
-    for (int e = 0; e < V; ++e) v[e] = apply_act(v[e] + bv[e], p.act, p.slope) * p.alpha;
-    float* dst = p.out.p + p.out.pix(img, sy, sx) + c;
-    if (p.res.p) {
-      const float* rs = p.res.p + p.res.pix(img, sy, sx) + c;
-      if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(rs); v[0] += t.x; v[1] += t.y; v[2 % V] += t.z; v[3 % V] += t.w; }
+    for (int e = 0; e < V; ++e) v[e] = act_t<ACT>(v[e] + bv[e], slope) * alpha;
+    if (rbase) {
+      const float* rs = rbase + ty * r_py + tx * r_px;
+      if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(rs); v[0] += t.x; v[1 % V] += t.y; v[2 % V] += t.z; v[3 % V] += t.w; }
       else if (V == 2) { const float2 t = *reinterpret_cast<const float2*>(rs); v[0] += t.x; v[1 % V] += t.y; }
       else v[0] += *rs;
     }
-    if (V == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2 % V], v[3 % V]);
+    float* dst = obase + ty * o_py + tx * o_px;
+    if (V == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1 % V], v[2 % V], v[3 % V]);
     else if (V == 2) *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1 % V]);
     else *dst = v[0];
+  }
+}
+
+template <int V>
+__device__ __forceinline__ void epi_writeout_act(const Params& p, const float* stg, int lane, int q, const TileCoord& tc_,
+                                                 int pc0, int ncols) {
+  switch (p.act) {
+    case LFSR_ACT_RELU: epi_writeout<V, LFSR_ACT_RELU>(p, stg, lane, q, tc_, pc0, ncols); break;
+    case LFSR_ACT_LRELU: epi_writeout<V, LFSR_ACT_LRELU>(p, stg, lane, q, tc_, pc0, ncols); break;
+    case LFSR_ACT_SIGMOID: epi_writeout<V, LFSR_ACT_SIGMOID>(p, stg, lane, q, tc_, pc0, ncols); break;
+    default: epi_writeout<V, LFSR_ACT_NONE>(p, stg, lane, q, tc_, pc0, ncols); break;
   }
 }
 
@@ -335,9 +364,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
         const int pc0 = tc_.chunk * p.NC + g * 32;
-        if (p.vec == 4) epi_writeout<4>(p, stg, lane, q, tc_, pc0, ncols);
-        else if (p.vec == 2) epi_writeout<2>(p, stg, lane, q, tc_, pc0, ncols);
-        else epi_writeout<1>(p, stg, lane, q, tc_, pc0, ncols);
+        if (p.vec == 4) epi_writeout_act<4>(p, stg, lane, q, tc_, pc0, ncols);
+        else if (p.vec == 2) epi_writeout_act<2>(p, stg, lane, q, tc_, pc0, ncols);
+        else epi_writeout_act<1>(p, stg, lane, q, tc_, pc0, ncols);
         __syncwarp();
       }
       tc_fence_before();
@@ -483,15 +512,20 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   const int kSmemMax = 227 * 1024 - 1024 - 256 - 16 * 1024;  // minus alignment slack, barriers, epilogue staging
   const long long b_all = (long long)nks * p.b_stage_bytes;
   p.resident = b_all + 3 * kABytes <= kSmemMax ? 1 : 0;     // whole weight set + >= 3 activation stages fit
+  static const bool no_resident = getenv("LFSR_TC_NO_RESIDENT") != nullptr;   // tuning knobs (profiles/ experiments)
+  static const int max_stages_env = getenv("LFSR_TC_STAGES") ? atoi(getenv("LFSR_TC_STAGES")) : 0;
+  if (no_resident) p.resident = 0;
   if (p.resident) p.stages = (int)((kSmemMax - b_all) / kABytes);
   else p.stages = (kSmemBudget - 16 * 1024) / (kABytes + p.b_stage_bytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (max_stages_env >= 2 && p.stages > max_stages_env) p.stages = max_stages_env;
   LFSR_REQUIRE(p.stages >= 2, "lfsr_conv2d_tc: not enough shared memory for two stages");
   p.out = view_of(out);
   p.res = d->res.ptr ? view_of(&d->res) : null_view();
   if (d->res.ptr)
     LFSR_REQUIRE(d->res.n == out->n && d->res.h == out->h && d->res.w == out->w && d->res.c == out->c,
                  "lfsr_conv2d_tc: res tensor geometry");
+  LFSR_REQUIRE((long long)out->h * out->w * out->ld < 0x7fffffffLL, "lfsr_conv2d_tc: output image too large for 32-bit pitches");
   p.bias = d->bias; p.act = d->act; p.slope = d->act_slope; p.alpha = d->alpha;
   p.ry = ry; p.rx = rx; p.shuf_mode = d->shuf_mode; p.cq = out->c;
   p.vec = 1;
@@ -511,7 +545,9 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
     cuuint64_t strides[4] = {ld_b, ld_b * p.bw, ld_b * in->w, ld_b * in->w * p.bh};
     cuuint32_t box[5] = {32, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, in->ptr, dims, strides, box, estr,
+    static const bool a_trunc = getenv("LFSR_TC_A_TRUNC") != nullptr;   // experiment: plain fp32 loads (MMA truncates)
+    CUresult r = encode(&tmA, a_trunc ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, in->ptr, dims,
+                        strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("lfsr_conv2d_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r); return LFSR_ERR_CUDA; }

@@ -108,3 +108,66 @@ extern "C" int lfsr_debug_umma_shift(const float* a_dev, const float* b_dev, flo
   lfsr::dbg::probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tmA, tmB, out_dev, shift, variant);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
+
+// ---- probe 2: issue-to-completion time of a chain of tf32 UMMAs (cycles), same vs alternating accumulators,
+// K-advance inside one 128 B swizzle atom (kstep 32 B) vs one MMA per fresh atom row block.
+namespace lfsr { namespace dbg {
+__global__ void __launch_bounds__(128, 1)
+mma_rate_kernel(long long* out, int N, int chain, int alternate, int kmode) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t r0 = smem_u32(raw);
+  uint8_t* smem = raw + (((r0 + 1023u) & ~1023u) - r0);
+  uint8_t* sA = smem;                  // 4 x 16 KB
+  uint8_t* sB = smem + 4 * 16384;      // 4 x 32 KB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 4 * 32768);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < (4 * 16384 + 4 * 32768) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const long long t0 = clock64();
+    for (int i = 0; i < chain; ++i) {
+      const int st = (i >> 2) & 3, k = i & 3;
+      const uint32_t a_addr = smem_u32(sA) + st * 16384 + (kmode ? 0 : k * 32);
+      const uint32_t b_addr = smem_u32(sB) + st * 32768 + (kmode ? 0 : k * 32);
+      const uint64_t da = ((uint64_t)((a_addr & 0x3FFFFu) >> 4)) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      const uint64_t db = ((uint64_t)((b_addr & 0x3FFFFu) >> 4)) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      const uint32_t d = tmem + ((alternate && (i & 1)) ? 256 : 0);
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                   ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(i > 1)) : "memory");
+    }
+    const long long t1 = clock64();
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+    const long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+}}  // namespace
+
+extern "C" int lfsr_debug_mma_rate(long long* out_dev, int n, int chain, int alternate, int kmode, void* stream) {
+  const size_t smem = 1024 + 4 * 16384 + 4 * 32768 + 64;
+  cudaFuncSetAttribute(lfsr::dbg::mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  lfsr::dbg::mma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(out_dev, n, chain, alternate, kmode);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}

@@ -220,14 +220,26 @@ class get_model(LFNetBase):
         pk["gf0"] = pc(self._exp(self.global_fusion["0"].weight.detach().float().cpu(), 1), tc=True)
         w, b = self.global_fusion["2"].merged()
         pk["gf2"] = pc(self._exp(w.float().cpu(), 0), self._exp(b.float().cpu(), 0), tc=True, **dil)
+        # upsampler activations carry CU = 56 channels (54 + 2 zero): 128-bit epilogue stores, and 4*56 = 224 is
+        # exactly the MMA N the 216 real output channels were padded to anyway
+        C = self.channels
+        CU = (C + 3) // 4 * 4
+        def pad_ch(w, dim, r2=1):
+            """zero-pad the channel dim from C(*r2) to CU(*r2); nn.PixelShuffle order keeps r2 innermost"""
+            shape = list(w.shape)
+            wv = w.reshape(shape[:dim] + [C, r2] + shape[dim + 1:])
+            padshape = list(wv.shape)
+            padshape[dim] = CU - C
+            return torch.cat([wv, wv.new_zeros(padshape)], dim).reshape(shape[:dim] + [CU * r2] + shape[dim + 1:])
         ups = []
         for j, (i, r) in enumerate(self.upsampler.steps):
             w = self.upsampler.up[str(i)].weight.detach().float().cpu()
-            if j == 0:
-                w = self._exp(w, 1)          # reads the grouped trunk
+            w = self._exp(w, 1) if j == 0 else pad_ch(w, 1)          # reads the grouped trunk / the padded up buffer
+            w = pad_ch(w, 0, r * r)
             ups.append((pc(w, pad=(1, 1), tc=True, tc_shuffle=(r, r, N.SHUF_CHANNEL_MAJOR)), r))
         pk["up"] = ups
-        pk["out"] = pc(self.output_conv.weight, self.output_conv.bias, pad=(1, 1))
+        pk["out"] = pc(pad_ch(self.output_conv.weight.detach().float().cpu(), 1), self.output_conv.bias, pad=(1, 1))
+        pk["CU"] = CU
         return pk
 
     # -- run ------------------------------------------------------------------------------------------
@@ -290,7 +302,7 @@ class get_model(LFNetBase):
         ops.conv(fu1, pk["gf2"], fu2, res=shallow)
         cur, ch, cw = fu2, H, W
         for j, (pcv, r) in enumerate(pk["up"]):
-            nb = buf(f"up{j}", ch * r, cw * r, C)
+            nb = buf(f"up{j}", ch * r, cw * r, pk["CU"])
             ops.conv(cur, pcv, nb, act=LR, slope=0.1, shuffle=(r, r, N.SHUF_CHANNEL_MAJOR))
             cur, ch, cw = nb, ch * r, cw * r
         ops.conv(cur, pk["out"], Y, res=Y)
@@ -306,14 +318,15 @@ class get_model(LFNetBase):
         A, C = self.angRes, self.channels
         pcv, r = pk["up"][-1]
         hin = A * h * (self.scale // r)
-        src = self._buf(f"up{len(pk['up']) - 2}", batch, hin, hin, C, dev) if len(pk["up"]) > 1 else \
+        src = self._buf(f"up{len(pk['up']) - 2}", batch, hin, hin, pcv.cin, dev) if len(pk["up"]) > 1 else \
             self._buf("fu2", batch, hin, hin, pcv.cin, dev)
-        dst = self._buf(f"up{len(pk['up']) - 1}", batch, hin * r, hin * r, C, dev)
+        dst = self._buf(f"up{len(pk['up']) - 1}", batch, hin * r, hin * r, pk["CU"], dev)
         info = {
-            "name": "conv3x3 %d->%d + PixelShuffle(%d) + LReLU @%dx%d (upsampler.up.%s)" % (C, pcv.cout, r, hin, hin,
+            "name": "conv3x3 %d->%d + PixelShuffle(%d) + LReLU @%dx%d (upsampler.up.%s)" % (C, C * r * r, r, hin, hin,
                                                                                         self.upsampler.steps[-1][0]),
-            "bytes": batch * (hin * hin * C + hin * r * hin * r * C) * 4 + pcv.w_f32.numel() * 4,
-            "flops": 2 * batch * hin * hin * pcv.kh * pcv.kw * pcv.cin * pcv.cout,
+            # algorithmic figures use the reference layer's real 54 -> 216 channels, not the padded buffers
+            "bytes": batch * (hin * hin * C + hin * r * hin * r * C) * 4 + pcv.kh * pcv.kw * C * C * r * r * 4,
+            "flops": 2 * batch * hin * hin * pcv.kh * pcv.kw * C * C * r * r,
         }
         return (lambda: ops.conv(src, pcv, dst, act=N.ACT_LRELU, slope=0.1, shuffle=(r, r, N.SHUF_CHANNEL_MAJOR))), info
 
