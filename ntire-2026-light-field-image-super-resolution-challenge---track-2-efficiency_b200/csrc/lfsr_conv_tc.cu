@@ -43,6 +43,10 @@ struct Params {
   int act;
   float slope, alpha;
   int ry, rx, shuf_mode, cq, vec;      // vec: floats per lane in the coalesced write-out (4, 2 or 1)
+  // halo-block mode (conv_tc_halo_kernel): the input block with halo is staged ONCE per 32-channel group as
+  // [Rin][P] padded pixels and every tap's A operand is a row-shifted view of it
+  long long* dbg;                      // optional per-CTA cycle counters (profiles/ experiments), else null
+  int halo, TWo, Rout, P, Rin, ntiles, strips_x, blocks_y, total_blocks, a_cg_bytes, bstages, acc_stages, pdiv_mul;
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -110,6 +114,29 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// same with the accumulate flag known at compile time (keeps the single issuing thread's instruction stream short:
+// that thread retires one dependent instruction every ~5 cycles, so descriptor arithmetic is what bounds the issue rate)
+template <int ACC>
+__device__ __forceinline__ void umma_tf32_c(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  if (ACC)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc) : "memory");
+}
+// issue the K-steps of one (tap, channel-group) stage: descriptors advance by 32 B (= 2 in the >>4 address field)
+template <bool FIRST>
+__device__ __forceinline__ void umma_stage(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, int ksteps) {
+  umma_tf32_c<FIRST ? 0 : 1>(tmem_d, a_desc, b_desc, idesc);
+  if (ksteps == 4) {
+    umma_tf32_c<1>(tmem_d, a_desc + 2, b_desc + 2, idesc);
+    umma_tf32_c<1>(tmem_d, a_desc + 4, b_desc + 4, idesc);
+    umma_tf32_c<1>(tmem_d, a_desc + 6, b_desc + 6, idesc);
+  } else {
+    for (int k = 1; k < ksteps; ++k) umma_tf32_c<1>(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc);
+  }
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -183,7 +210,7 @@ __device__ __forceinline__ float act_t(float v, float slope) {
 
 template <int V, int ACT>
 __device__ __forceinline__ void epi_writeout(const Params& p, const float* stg, int lane, int q, const TileCoord& tc_, int pc0,
-                                             int ncols) {
+                                             int ncols, int tile_j) {
   constexpr int LPR = 32 / V;   // lanes per pixel row
   const int r2 = p.ry * p.rx;
   const int col = (lane % LPR) * V;
@@ -203,16 +230,24 @@ __device__ __forceinline__ void epi_writeout(const Params& p, const float* stg, 
   const float* const rbase = p.res.p ? p.res.p + p.res.pix(img, oy0, ox0) + c : nullptr;
   const int o_py = p.ry * p.out.w * p.out.ld, o_px = p.rx * p.out.ld;         // float pitch per tile row / column
   const int r_py = p.ry * p.res.w * p.res.ld, r_px = p.rx * p.res.ld;
-  const bool full = tc_.y0 + p.TH <= p.bh && tc_.x0 + p.TW <= p.bw;
+  const bool full = !p.halo && tc_.y0 + p.TH <= p.bh && tc_.x0 + p.TW <= p.bw;
   const int tw_mask = p.TW - 1;
+  const int rows_valid = min(p.halo ? p.Rout : p.TH, p.bh - tc_.y0), cols_valid = min(p.halo ? p.TWo : p.TW, p.bw - tc_.x0);
   const float slope = p.slope, alpha = p.alpha;
   const int swz_hi = col >> 2, swz_lo = col & 3;
 #pragma unroll 4
   for (int it = 0; it < LPR; ++it) {
     const int r = it * V + lane / LPR;
     const int m = q * 32 + r;
-    const int ty = m >> p.tw_shift, tx = m & tw_mask;
-    if (!full && (tc_.y0 + ty >= p.bh || tc_.x0 + tx >= p.bw)) continue;
+    int ty, tx;
+    if (p.halo) {                      // flattened padded position g = ty*P + tx (tx >= TWo are halo garbage)
+      const int g = tile_j * 128 + m;
+      ty = (g * p.pdiv_mul) >> 16;
+      tx = g - ty * p.P;
+    } else {
+      ty = m >> p.tw_shift; tx = m & tw_mask;
+    }
+    if (!full && (ty >= rows_valid || tx >= cols_valid)) continue;
     const float* src = stg + r * 32 + (((swz_hi ^ (r & 7)) << 2) | swz_lo);
     float v[V];
     if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(src); v[0] = t.x; v[1 % V] = t.y; v[2 % V] = t.z; v[3 % V] = t.w; }
@@ -235,12 +270,34 @@ __device__ __forceinline__ void epi_writeout(const Params& p, const float* stg, 
 
 template <int V>
 __device__ __forceinline__ void epi_writeout_act(const Params& p, const float* stg, int lane, int q, const TileCoord& tc_,
-                                                 int pc0, int ncols) {
+                                                 int pc0, int ncols, int tile_j) {
   switch (p.act) {
-    case LFSR_ACT_RELU: epi_writeout<V, LFSR_ACT_RELU>(p, stg, lane, q, tc_, pc0, ncols); break;
-    case LFSR_ACT_LRELU: epi_writeout<V, LFSR_ACT_LRELU>(p, stg, lane, q, tc_, pc0, ncols); break;
-    case LFSR_ACT_SIGMOID: epi_writeout<V, LFSR_ACT_SIGMOID>(p, stg, lane, q, tc_, pc0, ncols); break;
-    default: epi_writeout<V, LFSR_ACT_NONE>(p, stg, lane, q, tc_, pc0, ncols); break;
+    case LFSR_ACT_RELU: epi_writeout<V, LFSR_ACT_RELU>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
+    case LFSR_ACT_LRELU: epi_writeout<V, LFSR_ACT_LRELU>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
+    case LFSR_ACT_SIGMOID: epi_writeout<V, LFSR_ACT_SIGMOID>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
+    default: epi_writeout<V, LFSR_ACT_NONE>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
+  }
+}
+
+// TMEM accumulator (32 lanes x NC columns of this warp) -> staged transpose -> coalesced global stores
+__device__ __forceinline__ void epilogue_tile(const Params& p, float* stg, uint32_t taddr, int lane, int q, const TileCoord& tc_,
+                                              int tile_j) {
+  for (int g = 0; g * 32 < p.NC; ++g) {
+    const int ncols = p.NC - g * 32 < 32 ? p.NC - g * 32 : 32;
+    float v[32];
+    tmem_ld16(taddr + g * 32, v);
+    if (ncols > 16) tmem_ld16(taddr + g * 32 + 16, v + 16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j * 4 < ncols)
+        *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int pc0 = tc_.chunk * p.NC + g * 32;
+    if (p.vec == 4) epi_writeout_act<4>(p, stg, lane, q, tc_, pc0, ncols, tile_j);
+    else if (p.vec == 2) epi_writeout_act<2>(p, stg, lane, q, tc_, pc0, ncols, tile_j);
+    else epi_writeout_act<1>(p, stg, lane, q, tc_, pc0, ncols, tile_j);
+    __syncwarp();
   }
 }
 
@@ -281,6 +338,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ================= TMA producer =================
     uint32_t it = 0;
+    int s_ring = 0;
+    uint32_t ph_ring = 0;
+    long long dbg_prod_wait = 0;
+    const long long dbg_t0 = clock64();
     const uint32_t stage_bytes = kABytes + (p.resident ? 0 : p.NC * 128);
     int m, chunk;
     if (p.resident && lane == 0 && next_tile(p, 0, m, chunk)) {
@@ -292,51 +353,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
     for (int i = 0; next_tile(p, i, m, chunk); ++i) {
       const TileCoord tc_ = decode_tile(p, m, chunk);
+      int cg = 0, ky = 0, kx = 0;
       for (int ks = 0; ks < nks; ++ks, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
+        if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
+        const int s = s_ring++;
+        const uint32_t ph = ph_ring;
+        const long long tw0 = clock64();
         mbar_wait(empty + s, ph ^ 1);
+        dbg_prod_wait += clock64() - tw0;
         if (lane == 0) {
-          const int tap = ks / p.cgs, cg = ks - tap * p.cgs;
-          const int ky = tap / p.kw, kx = tap - ky * p.kw;
           mbar_expect_tx(full + s, stage_bytes);
           tma_load_5d(sA + s * kABytes, &tmA, full + s, cg * 32, tc_.x0 + kx * p.dil_w - p.pad_w, tc_.vx,
                       tc_.y0 + ky * p.dil_h - p.pad_h, tc_.nb);
           if (!p.resident)
             tma_load_2d(sB + s * p.b_stage_bytes, &tmB, full + s, 0, (tc_.chunk * nks + ks) * p.NC);
         }
+        if (++cg == p.cgs) { cg = 0; if (++kx == p.kw) { kx = 0; ++ky; } }
         __syncwarp();
       }
     }
+    if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = dbg_prod_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - dbg_t0; }
   } else if (warp == 1) {
     // ================= MMA issuer =================
+    long long dbg_full_wait = 0, dbg_acc_wait = 0, dbg_issue = 0;
+    const long long dbg_t0 = clock64();
     uint32_t it = 0, tcount = 0;
+    int s_ring = 0;
+    uint32_t ph_ring = 0;
     const uint32_t idesc = make_idesc(p.NC);
+    const uint64_t a_desc0 = make_smem_desc(smem_u32(sA)), b_desc0 = make_smem_desc(smem_u32(sB));
+    const int rem_last = p.C - (p.cgs - 1) * 32;
+    const int ksteps_last = rem_last >= 32 ? 4 : (rem_last + 7) >> 3;
     int m, chunk;
     if (p.resident && next_tile(p, 0, m, chunk)) mbar_wait(bfull, 0);
     for (int i = 0; next_tile(p, i, m, chunk); ++i, ++tcount) {
       const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+      long long tw0 = clock64();
       mbar_wait(tempty + a, aph ^ 1);
+      dbg_acc_wait += clock64() - tw0;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + a * kAccStride;
-      for (int ks = 0; ks < nks; ++ks, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
+      int cg_i = 0;
+      for (int ks = 0; ks < nks; ++ks, ++it, cg_i = (cg_i + 1 == p.cgs) ? 0 : cg_i + 1) {
+        if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
+        const int s = s_ring++;
+        const uint32_t ph = ph_ring;
+        tw0 = clock64();
         mbar_wait(full + s, ph);
+        const long long tw1 = clock64();
+        dbg_full_wait += tw1 - tw0;
         tc_fence_after();
         if (lane == 0) {
-          const int cg = ks % p.cgs;
-          const int rem = p.C - cg * 32;
-          const int ksteps = rem >= 32 ? 4 : (rem + 7) >> 3;
-          const uint32_t a_addr = smem_u32(sA + s * kABytes);
-          const uint32_t b_addr = smem_u32(sB + (p.resident ? ks : s) * p.b_stage_bytes);
-          for (int k = 0; k < ksteps; ++k)
-            umma_tf32(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, (ks | k) != 0);
+          const int ksteps = (cg_i == p.cgs - 1) ? ksteps_last : 4;
+          const uint64_t a_d = a_desc0 + (uint64_t)(s * (kABytes >> 4));
+          const uint64_t b_d = b_desc0 + (uint64_t)((p.resident ? ks : s) * (p.b_stage_bytes >> 4));
+          if (ks == 0) umma_stage<true>(d_tmem, a_d, b_d, idesc, ksteps);
+          else umma_stage<false>(d_tmem, a_d, b_d, idesc, ksteps);
           umma_commit(empty + s);                      // frees the smem stage when these MMAs retire
           if (ks == nks - 1) umma_commit(tfull + a);   // accumulator complete -> epilogue
         }
         __syncwarp();
+        dbg_issue += clock64() - tw1;
       }
+    }
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 2] = dbg_full_wait; p.dbg[blockIdx.x * 8 + 3] = dbg_acc_wait;
+      p.dbg[blockIdx.x * 8 + 4] = dbg_issue; p.dbg[blockIdx.x * 8 + 5] = clock64() - dbg_t0;
     }
   } else {
     // ================= epilogue (warps 2..5 <-> TMEM lane quarters) =================
@@ -352,22 +434,165 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull + a, aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccStride;
-      for (int g = 0; g * 32 < p.NC; ++g) {
-        const int ncols = p.NC - g * 32 < 32 ? p.NC - g * 32 : 32;
-        float v[32];
-        tmem_ld16(taddr + g * 32, v);
-        if (ncols > 16) tmem_ld16(taddr + g * 32 + 16, v + 16);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j * 4 < ncols)
-            *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      epilogue_tile(p, stg, taddr, lane, q, tc_, 0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + a);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ======================= halo-block kernel =======================================================
+// 7 warps: 0 = A (activation block) producer, 1 = MMA issuer, 2..5 = epilogue, 6 = B (weights) producer.
+constexpr int kHaloThreads = 224;
+
+struct BlockCoord { int nb, y0, vx, x0; };
+__device__ __forceinline__ BlockCoord decode_block(const Params& p, int b) {
+  BlockCoord c;
+  c.x0 = (b % p.strips_x) * p.TWo; b /= p.strips_x;
+  c.vx = b % p.nbx; b /= p.nbx;
+  c.y0 = (b % p.blocks_y) * p.Rout;
+  c.nb = b / p.blocks_y;
+  return c;
+}
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const int taps = p.kh * p.kw;
+  const int nks = taps * p.cgs;
+  uint8_t* sA = smem;                                   // cgs x a_cg_bytes
+  uint8_t* sB = sA + p.cgs * p.a_cg_bytes;              // resident: nks stages, else bstages
+  float* sEpi = reinterpret_cast<float*>(sB + (p.resident ? nks : p.bstages) * p.b_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 4 * 1024);
+  uint64_t* afull = bars;            // [2]
+  uint64_t* aempty = bars + 2;       // [2]
+  uint64_t* bfull = bars + 4;        // [kMaxStages]
+  uint64_t* bempty = bfull + kMaxStages;
+  uint64_t* tfull = bempty + kMaxStages;   // [2]
+  uint64_t* tempty = tfull + 2;            // [2]
+  uint64_t* bres = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < 2; ++c) { mbar_init(afull + c, 1); mbar_init(aempty + c, 1); }
+    for (int s_ = 0; s_ < kMaxStages; ++s_) { mbar_init(bfull + s_, 1); mbar_init(bempty + s_, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+    mbar_init(bres, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool has_work = (int)blockIdx.x < p.total_blocks;
+
+  if (warp == 0) {
+    // ---- A producer: one TMA box per (block, 32-channel group): [Rin][P] padded pixels
+    const uint32_t a_bytes = (uint32_t)p.Rin * p.P * 128;
+    int i = 0;
+    for (int b = blockIdx.x; b < p.total_blocks; b += gridDim.x, ++i) {
+      const BlockCoord bc = decode_block(p, b);
+      for (int cg = 0; cg < p.cgs; ++cg) {
+        mbar_wait(aempty + cg, (i & 1) ^ 1);
+        if (lane == 0) {
+          mbar_expect_tx(afull + cg, a_bytes);
+          tma_load_5d(sA + cg * p.a_cg_bytes, &tmA, afull + cg, cg * 32, bc.x0 - p.pad_w, bc.vx, bc.y0 - p.pad_h, bc.nb);
+        }
         __syncwarp();
-        const int pc0 = tc_.chunk * p.NC + g * 32;
-        if (p.vec == 4) epi_writeout_act<4>(p, stg, lane, q, tc_, pc0, ncols);
-        else if (p.vec == 2) epi_writeout_act<2>(p, stg, lane, q, tc_, pc0, ncols);
-        else epi_writeout_act<1>(p, stg, lane, q, tc_, pc0, ncols);
-        __syncwarp();
+      }
+    }
+  } else if (warp == 6) {
+    // ---- B producer: weights of K-stage (cg, tap); resident mode loads all of them once
+    if (p.resident) {
+      if (lane == 0 && has_work) {
+        mbar_expect_tx(bres, (uint32_t)nks * p.b_stage_bytes);
+        for (int ks = 0; ks < nks; ++ks) tma_load_2d(sB + ks * p.b_stage_bytes, &tmB, bres, 0, ks * p.NC);
+      }
+    } else {
+      uint32_t it = 0;
+      for (int b = blockIdx.x; b < p.total_blocks; b += gridDim.x) {
+        for (int cg = 0; cg < p.cgs; ++cg)
+          for (int tap = 0; tap < taps; ++tap, ++it) {
+            const int s_ = it % p.bstages;
+            mbar_wait(bempty + s_, ((it / p.bstages) & 1) ^ 1);
+            if (lane == 0) {
+              mbar_expect_tx(bfull + s_, (uint32_t)p.b_stage_bytes);
+              tma_load_2d(sB + s_ * p.b_stage_bytes, &tmB, bfull + s_, 0, (tap * p.cgs + cg) * p.NC);
+            }
+            __syncwarp();
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer
+    const uint32_t idesc = make_idesc(p.NC);
+    if (p.resident && has_work) mbar_wait(bres, 0);
+    uint32_t it = 0;
+    int b_ring = 0;
+    uint32_t b_ph = 0;
+    const uint64_t b_desc0 = make_smem_desc(smem_u32(sB));
+    int i = 0;
+    for (int b = blockIdx.x; b < p.total_blocks; b += gridDim.x, ++i) {
+      const uint32_t a = p.acc_stages == 2 ? (i & 1) : 0;
+      const uint32_t aph = p.acc_stages == 2 ? ((i >> 1) & 1) : (i & 1);
+      mbar_wait(tempty + a, aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + a * (p.ntiles * p.NC);
+      for (int cg = 0; cg < p.cgs; ++cg) {
+        mbar_wait(afull + cg, i & 1);
+        tc_fence_after();
+        const int rem = p.C - cg * 32;
+        const int ksteps = rem >= 32 ? 4 : (rem + 7) >> 3;
+        const uint64_t a_cg_desc = make_smem_desc(smem_u32(sA + cg * p.a_cg_bytes));
+        int ky = 0, kx = 0;
+        for (int tap = 0; tap < taps; ++tap, ++it) {
+          if (b_ring == p.bstages) { b_ring = 0; b_ph ^= 1; }
+          const int s_ = p.resident ? (tap * p.cgs + cg) : b_ring++;
+          if (!p.resident) { mbar_wait(bfull + s_, b_ph); tc_fence_after(); }
+          if (lane == 0) {
+            const uint64_t a_d = a_cg_desc + (uint64_t)((ky * p.dil_h * p.P + kx * p.dil_w) * 8);      // rows * 128 B >> 4
+            const uint64_t b_d = b_desc0 + (uint64_t)(s_ * (p.b_stage_bytes >> 4));
+            for (int j = 0; j < p.ntiles; ++j) {
+              if ((cg | tap) == 0) umma_stage<true>(d_base + j * p.NC, a_d + (uint64_t)(j * 1024), b_d, idesc, ksteps);
+              else umma_stage<false>(d_base + j * p.NC, a_d + (uint64_t)(j * 1024), b_d, idesc, ksteps);
+            }
+            if (!p.resident) umma_commit(bempty + s_);
+            if (tap == taps - 1) umma_commit(aempty + cg);       // this group's block may be overwritten
+            if (tap == taps - 1 && cg == p.cgs - 1) umma_commit(tfull + a);
+          }
+          if (++kx == p.kw) { kx = 0; ++ky; }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..5
+    const int q = warp & 3;
+    float* stg = sEpi + (warp - 2) * 1024;
+    int i = 0;
+    for (int b = blockIdx.x; b < p.total_blocks; b += gridDim.x, ++i) {
+      const uint32_t a = p.acc_stages == 2 ? (i & 1) : 0;
+      const uint32_t aph = p.acc_stages == 2 ? ((i >> 1) & 1) : (i & 1);
+      const BlockCoord bc = decode_block(p, b);
+      TileCoord tc_;
+      tc_.chunk = 0; tc_.nb = bc.nb; tc_.y0 = bc.y0; tc_.vx = bc.vx; tc_.x0 = bc.x0;
+      mbar_wait(tfull + a, aph);
+      tc_fence_after();
+      for (int j = 0; j < p.ntiles; ++j) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * (p.ntiles * p.NC) + j * p.NC;
+        epilogue_tile(p, stg, taddr, lane, q, tc_, j);
       }
       tc_fence_before();
       __syncwarp();
@@ -491,35 +716,6 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   p.cout = out->c * ry * rx;
   const Plan pl = plan_for(p.C, p.cout);
   p.NC = pl.NC; p.nchunks = pl.nchunks; p.cgs = pl.cgs;
-  // tile shape TH x TW = 128 minimising padding waste inside a block (prefer wide tiles)
-  {
-    double best = 1e30;
-    for (int tw = 128; tw >= 8; tw >>= 1) {
-      const int th = 128 / tw;
-      const double waste = (double)(ceil_div(p.bh, th) * th) * (ceil_div(p.bw, tw) * tw) / ((double)p.bh * p.bw);
-      if (waste < best - 1e-9) { best = waste; p.TW = tw; p.TH = th; }
-    }
-    p.tw_shift = 0;
-    while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
-  }
-  p.tiles_y = ceil_div(p.bh, p.TH); p.tiles_x = ceil_div(p.bw, p.TW);
-  const long long tiles = (long long)p.nb_total * p.tiles_y * p.nbx * p.tiles_x * p.nchunks;
-  LFSR_REQUIRE(tiles > 0 && tiles < 0x7fffffffLL, "lfsr_conv2d_tc: tile count out of range");
-  p.total_tiles = (int)tiles;
-  p.m_tiles = (int)(tiles / p.nchunks);
-  p.b_stage_bytes = p.NC * 128;
-  const int nks = p.kh * p.kw * p.cgs;
-  const int kSmemMax = 227 * 1024 - 1024 - 256 - 16 * 1024;  // minus alignment slack, barriers, epilogue staging
-  const long long b_all = (long long)nks * p.b_stage_bytes;
-  p.resident = b_all + 3 * kABytes <= kSmemMax ? 1 : 0;     // whole weight set + >= 3 activation stages fit
-  static const bool no_resident = getenv("LFSR_TC_NO_RESIDENT") != nullptr;   // tuning knobs (profiles/ experiments)
-  static const int max_stages_env = getenv("LFSR_TC_STAGES") ? atoi(getenv("LFSR_TC_STAGES")) : 0;
-  if (no_resident) p.resident = 0;
-  if (p.resident) p.stages = (int)((kSmemMax - b_all) / kABytes);
-  else p.stages = (kSmemBudget - 16 * 1024) / (kABytes + p.b_stage_bytes);
-  if (p.stages > kMaxStages) p.stages = kMaxStages;
-  if (max_stages_env >= 2 && p.stages > max_stages_env) p.stages = max_stages_env;
-  LFSR_REQUIRE(p.stages >= 2, "lfsr_conv2d_tc: not enough shared memory for two stages");
   p.out = view_of(out);
   p.res = d->res.ptr ? view_of(&d->res) : null_view();
   if (d->res.ptr)
@@ -537,7 +733,120 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
     else
       break;
   }
+  p.b_stage_bytes = p.NC * 128;
+  p.dbg = getenv("LFSR_TC_DBG_PTR") ? (long long*)strtoull(getenv("LFSR_TC_DBG_PTR"), nullptr, 0) : nullptr;
+  static int sm_count = 0;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
 
+  // ---- halo-block plan: multi-tap kernels whose haloed input block fits in shared memory -------------
+  // Measured on B200 (profiles/r01_notes.md): correct, but not yet faster than the per-tap kernel below - the single
+  // accumulator stage at N = 224 serialises epilogue and MMAs - so it is opt-in (LFSR_TC_HALO=1) until that is fixed.
+  static const bool use_halo = getenv("LFSR_TC_HALO") != nullptr;
+  if (use_halo && p.kh * p.kw > 1 && p.cgs <= 2 && p.nchunks == 1) {
+    const int taps = p.kh * p.kw, nks = taps * p.cgs;
+    const int kSmemAvail = 227 * 1024 - 1024 - 512 - 16 * 1024;
+    const int TWo = p.bw < 32 ? p.bw : 32;
+    const int P = TWo + 2 * p.pad_w;
+    double best = 0.0;
+    int bestR = 0;
+    for (int R = p.bh < 64 ? p.bh : 64; R >= 1; --R) {
+      const int Rin = R + 2 * p.pad_h;
+      if (Rin > 256 || P > 256) continue;
+      const int nt = ceil_div(R * P, 128);
+      if (nt * p.NC > 512) continue;
+      const long long a_bytes = ((long long)(128 * nt + 2 * p.pad_h * P + 2 * p.pad_w) * 128 + 1023) / 1024 * 1024;
+      const long long need = a_bytes * p.cgs + 2LL * p.b_stage_bytes;
+      if (need > kSmemAvail) continue;
+      // useful outputs per MMA row, times the fraction of loaded rows that are not halo, with a mild
+      // preference for blocks that tile the view height evenly
+      const int nblk = ceil_div(p.bh, R);
+      const double eff = ((double)p.bh * TWo / ((double)nblk * nt * 128)) * ((double)p.bh / ((double)nblk * Rin));
+      if (eff > best + 1e-9) { best = eff; bestR = R; }
+    }
+    if (bestR > 0 && best >= 0.35) {
+      p.halo = 1; p.TWo = TWo; p.P = P; p.Rout = bestR; p.Rin = bestR + 2 * p.pad_h;
+      p.ntiles = ceil_div(p.Rout * P, 128);
+      p.a_cg_bytes = (int)(((long long)(128 * p.ntiles + 2 * p.pad_h * P + 2 * p.pad_w) * 128 + 1023) / 1024 * 1024);
+      p.pdiv_mul = (65536 + P - 1) / P;
+      bool div_ok = true;
+      for (int g = 0; g < 128 * p.ntiles && div_ok; ++g) div_ok = ((g * p.pdiv_mul) >> 16) == g / P;
+      const long long b_all = (long long)nks * p.b_stage_bytes;
+      const long long left = kSmemAvail - (long long)p.a_cg_bytes * p.cgs;
+      p.resident = b_all <= left ? 1 : 0;
+      p.bstages = p.resident ? 0 : (int)(left / p.b_stage_bytes);
+      if (p.bstages > kMaxStages) p.bstages = kMaxStages;
+      p.acc_stages = 2 * p.ntiles * p.NC <= 512 ? 2 : 1;
+      p.strips_x = ceil_div(p.bw, TWo); p.blocks_y = ceil_div(p.bh, p.Rout);
+      const long long blocks = (long long)p.nb_total * p.blocks_y * p.nbx * p.strips_x;
+      if (div_ok && (p.resident || p.bstages >= 2) && blocks < 0x7fffffffLL) {
+        p.total_blocks = (int)blocks;
+        CUtensorMap tmA, tmB;
+        const cuuint64_t ld_b = (cuuint64_t)in->ld * 4;
+        {
+          cuuint64_t dims[5] = {(cuuint64_t)p.C, (cuuint64_t)p.bw, (cuuint64_t)p.nbx, (cuuint64_t)p.bh, (cuuint64_t)p.nb_total};
+          cuuint64_t strides[4] = {ld_b, ld_b * p.bw, ld_b * in->w, ld_b * in->w * p.bh};
+          cuuint32_t box[5] = {32, (cuuint32_t)p.P, 1, (cuuint32_t)p.Rin, 1};
+          cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+          CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, in->ptr, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (r != CUDA_SUCCESS) { set_error("lfsr_conv2d_tc: cuTensorMapEncodeTiled(A halo) failed with %d", (int)r); return LFSR_ERR_CUDA; }
+        }
+        {
+          cuuint64_t dims[2] = {32, (cuuint64_t)nks * p.NC};
+          cuuint64_t strides[1] = {128};
+          cuuint32_t box[2] = {32, (cuuint32_t)p.NC};
+          cuuint32_t estr[2] = {1, 1};
+          CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w_packed_tc), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (r != CUDA_SUCCESS) { set_error("lfsr_conv2d_tc: cuTensorMapEncodeTiled(B halo) failed with %d", (int)r); return LFSR_ERR_CUDA; }
+        }
+        const size_t smem = 1024 + (size_t)p.cgs * p.a_cg_bytes + (size_t)(p.resident ? nks : p.bstages) * p.b_stage_bytes +
+                            16 * 1024 + (4 + 2 * kMaxStages + 5) * 8 + 16;
+        const int grid = p.total_blocks < sm_count ? p.total_blocks : sm_count;
+        conv_tc_halo_kernel<<<grid, kHaloThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+        return check_launch("conv_tc_halo_kernel");
+      }
+      p.halo = 0;
+    }
+  }
+
+  // tile shape TH x TW = 128 minimising padding waste inside a block (prefer wide tiles)
+  {
+    double best = 1e30;
+    for (int tw = 128; tw >= 8; tw >>= 1) {
+      const int th = 128 / tw;
+      const double waste = (double)(ceil_div(p.bh, th) * th) * (ceil_div(p.bw, tw) * tw) / ((double)p.bh * p.bw);
+      if (waste < best - 1e-9) { best = waste; p.TW = tw; p.TH = th; }
+    }
+    p.tw_shift = 0;
+    while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
+  }
+  p.tiles_y = ceil_div(p.bh, p.TH); p.tiles_x = ceil_div(p.bw, p.TW);
+  const long long tiles = (long long)p.nb_total * p.tiles_y * p.nbx * p.tiles_x * p.nchunks;
+  LFSR_REQUIRE(tiles > 0 && tiles < 0x7fffffffLL, "lfsr_conv2d_tc: tile count out of range");
+  p.total_tiles = (int)tiles;
+  p.m_tiles = (int)(tiles / p.nchunks);
+  const int nks = p.kh * p.kw * p.cgs;
+  const int kSmemMax = 227 * 1024 - 1024 - 256 - 16 * 1024;  // minus alignment slack, barriers, epilogue staging
+  const long long b_all = (long long)nks * p.b_stage_bytes;
+  p.resident = b_all + 3 * kABytes <= kSmemMax ? 1 : 0;     // whole weight set + >= 3 activation stages fit
+  static const bool no_resident = getenv("LFSR_TC_NO_RESIDENT") != nullptr;   // tuning knobs (profiles/ experiments)
+  static const int max_stages_env = getenv("LFSR_TC_STAGES") ? atoi(getenv("LFSR_TC_STAGES")) : 0;
+  if (no_resident) p.resident = 0;
+  if (p.resident) p.stages = (int)((kSmemMax - b_all) / kABytes);
+  else p.stages = (kSmemBudget - 16 * 1024) / (kABytes + p.b_stage_bytes);
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (max_stages_env >= 2 && p.stages > max_stages_env) p.stages = max_stages_env;
+  LFSR_REQUIRE(p.stages >= 2, "lfsr_conv2d_tc: not enough shared memory for two stages");
   CUtensorMap tmA, tmB;
   {
     const cuuint64_t ld_b = (cuuint64_t)in->ld * 4;
@@ -563,14 +872,6 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("lfsr_conv2d_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return LFSR_ERR_CUDA; }
   }
-  static int sm_count = 0;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
   const size_t smem = 1024 + (size_t)p.stages * kABytes + (size_t)(p.resident ? nks : p.stages) * p.b_stage_bytes +
                       16 * 1024 + (2 * kMaxStages + 5) * 8 + 16;
   LFSR_REQUIRE(smem <= 227 * 1024, "lfsr_conv2d_tc: shared memory plan too large");

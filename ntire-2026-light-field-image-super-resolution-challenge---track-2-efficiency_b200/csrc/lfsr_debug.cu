@@ -120,11 +120,12 @@ mma_rate_kernel(long long* out, int N, int chain, int alternate, int kmode) {
   uint8_t* sA = smem;                  // 4 x 16 KB
   uint8_t* sB = smem + 4 * 16384;      // 4 x 32 KB
   uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 4 * 32768);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 4);
   for (int i = threadIdx.x; i < (4 * 16384 + 4 * 32768) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1000000;" ::"r"(smem_u32(bar + 2)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -141,13 +142,16 @@ mma_rate_kernel(long long* out, int N, int chain, int alternate, int kmode) {
     const long long t0 = clock64();
     for (int i = 0; i < chain; ++i) {
       const int st = (i >> 2) & 3, k = i & 3;
-      const uint32_t a_addr = smem_u32(sA) + st * 16384 + (kmode ? 0 : k * 32);
-      const uint32_t b_addr = smem_u32(sB) + st * 32768 + (kmode ? 0 : k * 32);
+      const uint32_t a_addr = smem_u32(sA) + st * 8192 + kmode * 128 + k * 32;   // kmode = row shift of the A view
+      const uint32_t b_addr = smem_u32(sB) + st * 32768 + k * 32;
       const uint64_t da = ((uint64_t)((a_addr & 0x3FFFFu) >> 4)) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
       const uint64_t db = ((uint64_t)((b_addr & 0x3FFFFu) >> 4)) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-      const uint32_t d = tmem + ((alternate && (i & 1)) ? 256 : 0);
+      const uint32_t d = tmem + ((alternate == 1 && (i & 1)) ? 256 : 0);
       asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                    ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(i > 1)) : "memory");
+      // alternate >= 2: commit to a scratch mbarrier after every `alternate` MMAs (cost of tcgen05.commit in the issue stream)
+      if (alternate >= 2 && (i % alternate) == alternate - 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar + 2)) : "memory");
     }
     const long long t1 = clock64();
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -279,6 +279,22 @@ TC_CASES = [
 
 @pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
 def test_conv_tc(ref, case):
+    _run_tc_case(ref, case)
+
+
+def test_conv_tc_halo_block_kernel(ref):
+    """the opt-in halo-block kernel (LFSR_TC_HALO=1) in a subprocess so the env switch is seen at first use"""
+    import subprocess, sys, os
+    env = dict(os.environ, LFSR_TC_HALO="1")
+    code = ("import sys; sys.path[:0]=['.','tests']; import torch, opref, test_kernels_gpu as t; "
+            "torch.backends.cudnn.allow_tf32=False; torch.backends.cuda.matmul.allow_tf32=False; r=opref.RefOps();\n"
+            "for c in t.TC_CASES:\n    if c['k']==(3,3) and c['cin']<=64: t._run_tc_case(r, c)\nprint('halo ok')")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0 and "halo ok" in out.stdout, out.stderr[-2000:]
+
+
+def _run_tc_case(ref, case):
     tc_ops = K.CudaOps(use_tc=True)
     n = 2
     h, w = case["hw"]
