@@ -45,6 +45,12 @@ struct Params {
   int ry, rx, shuf_mode, cq, vec;      // vec: floats per lane in the coalesced write-out (4, 2 or 1)
   // halo-block mode (conv_tc_halo_kernel): the input block with halo is staged ONCE per 32-channel group as
   // [Rin][P] padded pixels and every tap's A operand is a row-shifted view of it
+  // A-operand addressing: TMA coordinate d (1..4) of tap t = base_d(tile) + tap_off[t][d-1]; `amode` picks which tile
+  // variable feeds which tensor-map dimension (0: same-size conv, dims (c, x, view-x, y, image*view-y);
+  // 1: stride along x, dims (c, x%s, x/s, y, image); 2: stride along y, dims (c, x, y%s, y/s, image);
+  // 3: stride along both, dims (c, x%s, x/s, y%s, image*y/s))
+  int amode, out_rows_per_img;
+  short tap_off[25][4];
   long long* dbg;                      // optional per-CTA cycle counters (profiles/ experiments), else null
   int halo, TWo, Rout, P, Rin, ntiles, strips_x, blocks_y, total_blocks, a_cg_bytes, bstages, acc_stages, pdiv_mul;
 };
@@ -354,6 +360,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; next_tile(p, i, m, chunk); ++i) {
       const TileCoord tc_ = decode_tile(p, m, chunk);
       int cg = 0, ky = 0, kx = 0;
+      int b1, b2, b3, b4;      // tile part of the TMA coordinates
+      if (p.amode == 0) { b1 = tc_.x0; b2 = tc_.vx; b3 = tc_.y0; b4 = tc_.nb; }
+      else if (p.amode == 1) { b1 = 0; b2 = tc_.x0; b3 = tc_.y0; b4 = tc_.nb; }
+      else if (p.amode == 2) { b1 = tc_.x0; b2 = 0; b3 = tc_.y0; b4 = tc_.nb; }
+      else { b1 = 0; b2 = tc_.x0; b3 = 0; b4 = tc_.nb * p.out_rows_per_img + tc_.y0; }
       for (int ks = 0; ks < nks; ++ks, ++it) {
         if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
         const int s = s_ring++;
@@ -363,8 +374,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         dbg_prod_wait += clock64() - tw0;
         if (lane == 0) {
           mbar_expect_tx(full + s, stage_bytes);
-          tma_load_5d(sA + s * kABytes, &tmA, full + s, cg * 32, tc_.x0 + kx * p.dil_w - p.pad_w, tc_.vx,
-                      tc_.y0 + ky * p.dil_h - p.pad_h, tc_.nb);
+          const short* to = p.tap_off[ky * p.kw + kx];
+          tma_load_5d(sA + s * kABytes, &tmA, full + s, cg * 32, b1 + to[0], b2 + to[1], b3 + to[2], b4 + to[3]);
           if (!p.resident)
             tma_load_2d(sB + s * p.b_stage_bytes, &tmB, full + s, 0, (tc_.chunk * nks + ks) * p.NC);
         }
@@ -679,14 +690,25 @@ extern "C" int lfsr_pack_conv_tc(const float* w, float* packed, int kh, int kw, 
   return LFSR_OK;
 }
 
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
 static bool tc_geometry_ok(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d) {
   if (!tensor_ok(in) || !tensor_ok(out) || !d) return false;
-  if (d->stride_h != 1 || d->stride_w != 1 || d->in_perm || d->out_perm || d->mul.ptr || d->in_scale) return false;
+  if (d->in_perm || d->out_perm || d->mul.ptr || d->in_scale) return false;
   if (d->kh * d->kw > 25 || d->kh < 1 || d->kw < 1) return false;
-  if (2 * d->pad_h != d->dil_h * (d->kh - 1) || 2 * d->pad_w != d->dil_w * (d->kw - 1)) return false;  // "same"
   if (in->c < 8 || in->ld % 4 != 0 || ((uintptr_t)in->ptr & 15)) return false;
   const int ry = d->shuf_ry > 0 ? d->shuf_ry : 1, rx = d->shuf_rx > 0 ? d->shuf_rx : 1;
-  if (out->n != in->n || out->h != in->h * ry || out->w != in->w * rx) return false;
+  const int sh = d->stride_h, sw = d->stride_w;
+  if (sh < 1 || sw < 1 || in->h % sh || in->w % sw) return false;
+  const int OH = (in->h + 2 * d->pad_h - d->dil_h * (d->kh - 1) - 1) / sh + 1;
+  const int OW = (in->w + 2 * d->pad_w - d->dil_w * (d->kw - 1) - 1) / sw + 1;
+  if (OH != in->h / sh || OW != in->w / sw) return false;                 // "same" geometry (per stride)
+  if (out->n != in->n || out->h != OH * ry || out->w != OW * rx) return false;
+  if (sh > 1 || sw > 1) {
+    if (d->dil_h != 1 || d->dil_w != 1 || d->block_h > 0 || d->block_w > 0) return false;
+    if (sh > 1 && sw > 1 && (d->pad_h || d->pad_w)) return false;         // image and row-block share one TMA dim there
+    if (sh > 8 || sw > 8) return false;
+  }
   const int cout = out->c * ry * rx;
   if (cout < 1) return false;
   const int bh = d->block_h > 0 ? d->block_h : in->h, bw = d->block_w > 0 ? d->block_w : in->w;
@@ -708,10 +730,25 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   const int ry = d->shuf_ry > 0 ? d->shuf_ry : 1, rx = d->shuf_rx > 0 ? d->shuf_rx : 1;
   Params p;
   memset(&p, 0, sizeof(p));
-  p.bh = d->block_h > 0 ? d->block_h : in->h;
-  p.bw = d->block_w > 0 ? d->block_w : in->w;
-  p.nby = in->h / p.bh; p.nbx = in->w / p.bw;
+  const int sh = d->stride_h, sw = d->stride_w;
+  const bool strided = sh > 1 || sw > 1;
+  // "block" = the region tiles may not straddle: a view (EPIT), else the whole (output-resolution) image
+  p.bh = strided ? in->h / sh : (d->block_h > 0 ? d->block_h : in->h);
+  p.bw = strided ? in->w / sw : (d->block_w > 0 ? d->block_w : in->w);
+  p.nby = strided ? 1 : in->h / p.bh; p.nbx = strided ? 1 : in->w / p.bw;
   p.nb_total = in->n * p.nby;
+  p.amode = !strided ? 0 : (sh == 1 ? 1 : (sw == 1 ? 2 : 3));
+  p.out_rows_per_img = in->h / sh;
+  for (int ky = 0; ky < d->kh; ++ky)
+    for (int kx = 0; kx < d->kw; ++kx) {
+      short* to = p.tap_off[ky * d->kw + kx];
+      const int dy = ky * d->dil_h - d->pad_h, dx = kx * d->dil_w - d->pad_w;
+      const int ay = floordiv(dy, sh), ry_ = dy - ay * sh, ax = floordiv(dx, sw), rx_ = dx - ax * sw;
+      if (p.amode == 0) { to[0] = (short)dx; to[1] = 0; to[2] = (short)dy; to[3] = 0; }
+      else if (p.amode == 1) { to[0] = (short)rx_; to[1] = (short)ax; to[2] = (short)dy; to[3] = 0; }
+      else if (p.amode == 2) { to[0] = (short)dx; to[1] = (short)ry_; to[2] = (short)ay; to[3] = 0; }
+      else { to[0] = (short)rx_; to[1] = (short)ax; to[2] = (short)ry_; to[3] = (short)ay; }
+    }
   p.C = in->c; p.kh = d->kh; p.kw = d->kw; p.dil_h = d->dil_h; p.dil_w = d->dil_w; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
   p.cout = out->c * ry * rx;
   const Plan pl = plan_for(p.C, p.cout);
@@ -850,9 +887,23 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   CUtensorMap tmA, tmB;
   {
     const cuuint64_t ld_b = (cuuint64_t)in->ld * 4;
+    const cuuint64_t W_ = in->w, H_ = in->h, N_ = in->n;
     cuuint64_t dims[5] = {(cuuint64_t)p.C, (cuuint64_t)p.bw, (cuuint64_t)p.nbx, (cuuint64_t)p.bh, (cuuint64_t)p.nb_total};
     cuuint64_t strides[4] = {ld_b, ld_b * p.bw, ld_b * in->w, ld_b * in->w * p.bh};
     cuuint32_t box[5] = {32, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH, 1};
+    if (p.amode == 1) {          // (c, x%s, x/s, y, image)
+      dims[1] = sw; dims[2] = W_ / sw; dims[3] = H_; dims[4] = N_;
+      strides[0] = ld_b; strides[1] = ld_b * sw; strides[2] = ld_b * W_; strides[3] = ld_b * W_ * H_;
+      box[1] = 1; box[2] = p.TW; box[3] = p.TH; box[4] = 1;
+    } else if (p.amode == 2) {   // (c, x, y%s, y/s, image)
+      dims[1] = W_; dims[2] = sh; dims[3] = H_ / sh; dims[4] = N_;
+      strides[0] = ld_b; strides[1] = ld_b * W_; strides[2] = ld_b * W_ * sh; strides[3] = ld_b * W_ * H_;
+      box[1] = p.TW; box[2] = 1; box[3] = p.TH; box[4] = 1;
+    } else if (p.amode == 3) {   // (c, x%s, x/s, y%s, image*y/s)
+      dims[1] = sw; dims[2] = W_ / sw; dims[3] = sh; dims[4] = N_ * (H_ / sh);
+      strides[0] = ld_b; strides[1] = ld_b * sw; strides[2] = ld_b * W_; strides[3] = ld_b * W_ * sh;
+      box[1] = 1; box[2] = p.TW; box[3] = 1; box[4] = p.TH;
+    }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     static const bool a_trunc = getenv("LFSR_TC_A_TRUNC") != nullptr;   // experiment: plain fp32 loads (MMA truncates)
     CUresult r = encode(&tmA, a_trunc ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, in->ptr, dims,

@@ -76,9 +76,10 @@ class get_model(LFNetBase):
                 we = b.EPIConv["0"].weight
                 blocks.append(dict(
                     spa0=pc(b.SpaConv["0"].weight, tc=True, **dil), spa2=pc(b.SpaConv["2"].weight, tc=True, **dil),
-                    ang0=pc(b.AngConv["0"].weight, stride=(A, A)), ang2=pc(b.AngConv["2"].weight),
-                    epi_h=pc(we, stride=(1, A), pad=(0, A * (A - 1) // 2)),
-                    epi_v=pc(we.permute(0, 1, 3, 2), stride=(A, 1), pad=(A * (A - 1) // 2, 0)),
+                    ang0=pc(b.AngConv["0"].weight, stride=(A, A), tc=True),
+                    ang2=pc(b.AngConv["2"].weight, tc=True, tc_shuffle=(A, A, N.SHUF_CHANNEL_MAJOR)),
+                    epi_h=pc(we, stride=(1, A), pad=(0, A * (A - 1) // 2), tc=True),
+                    epi_v=pc(we.permute(0, 1, 3, 2), stride=(A, 1), pad=(A * (A - 1) // 2, 0), tc=True),
                     epi2=pc(b.EPIConv["2"].weight, tc=True, tc_shuffle=(1, A, N.SHUF_FACTOR_MAJOR)),
                     fuse0=pc(b.fuse["0"].weight, tc=True), fuse2=pc(b.fuse["2"].weight, tc=True, **dil)))
             pk["groups"].append(dict(blocks=blocks, conv=pc(g.conv.weight, tc=True, **dil)))

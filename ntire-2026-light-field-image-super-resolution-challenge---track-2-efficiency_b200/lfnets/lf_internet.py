@@ -81,11 +81,11 @@ class get_model(LFNetBase):
         dil = dict(dil=(A, A), pad=(A, A))
         pk = {"ang_fe": pc(self.AngFE["0"].weight, stride=(A, A)), "spa_fe": pc(self.SpaFE["0"].weight, **dil), "chains": []}
         for blk in self.CascadeInterBlock.body:
-            pk["chains"].append([dict(s2a=pc(c.Spa2Ang.weight, stride=(A, A)), a2s=pc(c.Ang2Spa["0"].weight, tc=True, tc_shuffle=(A, A, N.SHUF_CHANNEL_MAJOR)),
-                                      asq=pc(c.AngConvSq.weight), ssq=pc(c.SpaConvSq.weight, tc=True, **dil))
+            pk["chains"].append([dict(s2a=pc(c.Spa2Ang.weight, stride=(A, A), tc=True), a2s=pc(c.Ang2Spa["0"].weight, tc=True, tc_shuffle=(A, A, N.SHUF_CHANNEL_MAJOR)),
+                                      asq=pc(c.AngConvSq.weight, tc=True), ssq=pc(c.SpaConvSq.weight, tc=True, **dil))
                                  for c in blk.chained_layers])
         bn = self.BottleNeck
-        pk["bn_ang"] = pc(bn.AngBottle.weight)
+        pk["bn_ang"] = pc(bn.AngBottle.weight, tc=True)
         pk["bn_a2s"] = pc(bn.Ang2Spa["0"].weight, tc=True, tc_shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
         pk["bn_spa"] = pc(bn.SpaBottle.weight, tc=True, **dil)
         wp = self.ReconBlock.PreConv.weight.detach().double()                     # [64 s^2, 64, 3, 3]

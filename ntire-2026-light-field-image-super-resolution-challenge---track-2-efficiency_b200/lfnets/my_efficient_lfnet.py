@@ -181,7 +181,7 @@ class get_model(LFNetBase):
             s["spa0"] = pc(w, b, tc=True, **dil)
             s["spa2"] = pc(st.spatial_branch["2"].weight, tc=True, **dil)
             ab = st.angular_branch
-            s["ang_to"] = pc(ab.to_angular.weight, stride=(A, A))
+            s["ang_to"] = pc(ab.to_angular.weight, stride=(A, A), tc=True)
             s["ang_a0"] = pc(ab.attention["0"].weight)
             s["ang_a2"] = _dw_pack(ab.attention["2"].weight, device)
             s["ang_a4"] = pc(ab.attention["4"].weight)

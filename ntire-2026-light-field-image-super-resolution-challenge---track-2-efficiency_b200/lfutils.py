@@ -15,9 +15,11 @@ from . import _native as N
 from . import kernels as K
 
 
-def _device_for(t: torch.Tensor) -> torch.device:
+def _device_for(t: torch.Tensor, ops=None) -> torch.device:
     if t.is_cuda:
         return t.device
+    if ops is not None and getattr(ops, "name", "cuda") != "cuda":
+        return t.device          # an injected test backend (tests/opref.RefOps) works where the tensors live
     if not torch.cuda.is_available():
         raise N.LfsrError("lfsr_b200 needs a CUDA device (sm_100a); there is no CPU fallback for this path")
     return torch.device("cuda", torch.cuda.current_device())
@@ -33,8 +35,8 @@ def LFdivide(data: torch.Tensor, angRes: int, patch_size: int, stride: int, rows
     rows=(u0,u1) returns only that band of the patch grid (multi-GPU scene sharding)."""
     if data.dim() != 2:
         raise ValueError(f"LFdivide expects a 2-D SAI mosaic, got {tuple(data.shape)}")
+    dev = _device_for(data, ops)
     ops = ops or K.default_ops()
-    dev = _device_for(data)
     src = data.to(device=dev, dtype=torch.float32).contiguous()
     H, W = src.shape
     h0, w0 = H // angRes, W // angRes
@@ -49,8 +51,8 @@ def LFintegrate(subLF: torch.Tensor, angRes: int, pz: int, stride: int, h: int, 
     """subLF [n1, n2, a1*pz, a2*pz] (or 6-D n1 n2 a1 a2 pz pz) -> outLF [a1, a2, h, w]
     (utils/utils.py:169-178). The result is a view of the stitched SAI mosaic, so the reference's
     following 'a1 a2 h w -> 1 1 (a1 h) (a2 w)' rearrange (train.py:319) is a cheap copy."""
+    dev = _device_for(subLF, ops)
     ops = ops or K.default_ops()
-    dev = _device_for(subLF)
     sub = subLF.to(device=dev, dtype=torch.float32)
     if sub.dim() == 6:
         n1, n2, a1, a2, ph, pw = sub.shape
@@ -67,8 +69,8 @@ def LFintegrate(subLF: torch.Tensor, angRes: int, pz: int, stride: int, h: int, 
 
 def metric_views(label_sai: torch.Tensor, out_sai: torch.Tensor, angRes: int, ops=None):
     """per-view PSNR / SSIM of two SAI mosaics [(a1 h), (a2 w)] -> float32 arrays [A, A]."""
+    dev = _device_for(out_sai if out_sai.is_cuda else label_sai, ops)
     ops = ops or K.default_ops()
-    dev = _device_for(out_sai if out_sai.is_cuda else label_sai)
     la = label_sai.to(device=dev, dtype=torch.float32).contiguous()
     ou = out_sai.to(device=dev, dtype=torch.float32).contiguous()
     H, W = la.shape

@@ -271,6 +271,13 @@ TC_CASES = [
     dict(cin=256, cout=128, k=(1, 1), res=True, hw=(1, 5000)),
     dict(cin=64, cout=128, k=(1, 1), hw=(1, 25600)),
     dict(cin=54, cout=1, k=(3, 3), pad=(1, 1), bias=True, res=True, hw=(160, 160)),
+    dict(cin=64, cout=32, k=(1, 25), stride=(1, 5), pad=(0, 10), act=2, hw=(160, 160)),
+    dict(cin=64, cout=32, k=(25, 1), stride=(5, 1), pad=(10, 0), act=2, hw=(160, 160)),
+    dict(cin=64, cout=32, k=(1, 25), stride=(1, 5), pad=(0, 10), act=2, hw=(40, 40)),
+    dict(cin=64, cout=32, k=(25, 1), stride=(5, 1), pad=(10, 0), act=2, hw=(40, 40)),
+    dict(cin=64, cout=16, k=(5, 5), stride=(5, 5), act=2, hw=(160, 160)),
+    dict(cin=64, cout=64, k=(5, 5), stride=(5, 5), act=1, hw=(40, 40)),
+    dict(cin=16, cout=400, k=(1, 1), act=2, shuffle=(5, 5, 0), hw=(32, 32)),
     dict(cin=64, cout=1, k=(3, 3), pad=(1, 1), res=True, hw=(40, 40)),
     dict(cin=64, cout=1024, k=(1, 1), act=2, shuffle=(4, 4, 0), hw=(160, 160)),
     dict(cin=128, cout=384, k=(1, 1), hw=(1, 25600)),
@@ -300,20 +307,21 @@ def _run_tc_case(ref, case):
     h, w = case["hw"]
     cin, cout = case["cin"], case["cout"]
     kh, kw = case["k"]
-    dil, pad = case.get("dil", (1, 1)), case.get("pad", (0, 0))
+    dil, pad, stride = case.get("dil", (1, 1)), case.get("pad", (0, 0)), case.get("stride", (1, 1))
     g = torch.Generator().manual_seed(cin * 131 + cout)
     wt = (torch.rand(cout, cin, kh, kw, generator=g) - 0.5) * (2.0 / (cin * kh * kw) ** 0.5)
     bias = (torch.rand(cout, generator=g) - 0.5) if case.get("bias") else None
     ry, rx, sm = case.get("shuffle", (1, 1, 0))
-    pc = K.pack_conv(wt, bias, dil=dil, pad=pad, device=DEV, tc=True, tc_shuffle=(ry, rx, sm))
+    pc = K.pack_conv(wt, bias, stride=stride, dil=dil, pad=pad, device=DEV, tc=True, tc_shuffle=(ry, rx, sm))
     assert pc.w_tc is not None
     x = nhwc(n, h, w, cin, seed=3)
     co = cout // (ry * rx)
     kw_args = dict(act=case.get("act", 0), slope=0.1, alpha=case.get("alpha", 1.0), shuffle=(ry, rx, sm),
                    block=case.get("block", (0, 0)))
+    oh, ow = h // stride[0], w // stride[1]
     if case.get("res"):
-        kw_args["res"] = nhwc(n, h * ry, w * rx, co, seed=5)
-    a = nhwc(n, h * ry, w * rx, co, seed=7)
+        kw_args["res"] = nhwc(n, oh * ry, ow * rx, co, seed=5)
+    a = nhwc(n, oh * ry, ow * rx, co, seed=7)
     b = a.clone()
     lib = tc_ops.lib
     l0 = lib.lfsr_launch_count()
