@@ -271,8 +271,16 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         gbs = info["bytes"] / (kms * 1e-3) / 1e9
+        # DRAM traffic of this kernel per launch from the committed `ncu --set full` capture (taken at batch 64)
+        traffic = None
+        try:
+            nc = json.load(open(os.path.join(ROOT, "profiles", "r01_dominant_kernel_ncu.json")))
+            gb = lambda k: float(nc[k]["value"]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[nc[k]["unit"]]
+            traffic = (gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")) * a.batch / 64.0
+        except (OSError, KeyError, ValueError):
+            pass
         roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                "traffic": None, "kernel": info["name"], "kernel_ms": kms, "algorithmic_bytes": info["bytes"],
+                "traffic": traffic, "kernel": info["name"], "kernel_ms": kms, "algorithmic_bytes": info["bytes"],
                 "tflops": info["flops"] / (kms * 1e-3) / 1e12,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
 
