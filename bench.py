@@ -162,7 +162,6 @@ def main():
 
     import lfsr_b200
     from lfsr_b200 import kernels as K, lfutils as U
-    from oracle import weights
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -178,9 +177,8 @@ def main():
     if a.no_tc:
         K._default_ops = K.CudaOps(use_tc=False)
     ops = K.default_ops()
-    net = lfsr_b200.load_net(a.model, ANG, a.scale).eval()
-    net.load_state_dict(weights.make_state_dict(a.model, a.scale, 1234), strict=True)
-    net = net.to(dev)
+    torch.manual_seed(1234)                                  # seeded constructor-default init
+    net = lfsr_b200.load_net(a.model, ANG, a.scale).eval().to(dev)
 
     h0 = scene_side(a.batch)
     s = a.scale
@@ -300,7 +298,7 @@ def main():
                                    f"PSNR/SSIM, one {h0}x{h0}-view synthetic scene per GPU per step (BASELINE configs[1])",
                        "patches_per_step_per_gpu": a.batch, "parallelism": f"scene-parallel x{world}",
                        "l2": "activations per step (>6 GB at batch 64) exceed the 126 MB L2; inputs rotate over 4 scenes",
-                       "weights": "random (oracle.weights seed 1234)"},
+                       "weights": "random init (torch.manual_seed(1234), constructor defaults)"},
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": host_lr[0].numel() * 4,
                     "d2h_bytes_per_step": sr_bytes, "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,

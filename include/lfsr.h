@@ -72,6 +72,8 @@ typedef struct {
   const float* bias;     /* [cout] or NULL */
   const float* in_scale; /* [n][in_scale_ld] (first cin used) or NULL */
   int64_t in_scale_ld;   /* floats between samples of in_scale; 0 = cin */
+  int64_t w_batch_stride; /* lfsr_conv2d_tc only: >0 = one packed weight set per image, this many floats apart
+                             (built by lfsr_scale_pack_tc for per-sample gated convs); 0 = shared weights */
   lfsr_tensor mul;       /* ptr NULL if unused; conv-output geometry */
   lfsr_tensor res;       /* ptr NULL if unused; stored-output geometry */
 } lfsr_conv_desc;
@@ -132,6 +134,11 @@ size_t lfsr_conv2d_tc_packed_floats(int kh, int kw, int cin, int cout);
 int lfsr_pack_conv_tc(const float* w_oihw_host, float* packed_host, int kh, int kw, int cin, int cout);
 int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, const lfsr_tensor* out,
                    const lfsr_conv_desc* d, void* stream);
+/* per-image weight sets for a gated conv: out[img] = packed * gate[img][cin] along the input-channel axis
+ * (MyEfficientLFNet.py:193-199: the branch gates multiply the concat before the fusion 1x1). `packed` is the
+ * lfsr_pack_conv_tc buffer, `out` holds n copies of it. */
+int lfsr_scale_pack_tc(const float* packed, const float* gate, int64_t gate_ld, float* out, int n, int kh, int kw,
+                       int cin, int cout, void* stream);
 /* 1 if lfsr_conv2d_tc can run this problem (geometry/alignment), else 0 */
 int lfsr_conv2d_tc_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);
 

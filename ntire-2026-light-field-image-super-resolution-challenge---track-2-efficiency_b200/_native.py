@@ -37,7 +37,7 @@ class ConvDesc(C.Structure):
         ("shuf_ry", C.c_int32), ("shuf_rx", C.c_int32), ("shuf_mode", C.c_int32),
         ("block_h", C.c_int32), ("block_w", C.c_int32),
         ("act", C.c_int32), ("act_slope", C.c_float), ("alpha", C.c_float),
-        ("bias", C.c_void_p), ("in_scale", C.c_void_p), ("in_scale_ld", C.c_int64),
+        ("bias", C.c_void_p), ("in_scale", C.c_void_p), ("in_scale_ld", C.c_int64), ("w_batch_stride", C.c_int64),
         ("mul", Tensor), ("res", Tensor),
     ]
 
@@ -71,6 +71,7 @@ SIGNATURES = {
     "lfsr_mel_epi_branch": (_I, [_TP, _P, _TP, _I, _I, C.c_float, _P]),
     "lfsr_conv2d_tc_packed_floats": (C.c_size_t, [_I, _I, _I, _I]),
     "lfsr_pack_conv_tc": (_I, [_P, _P, _I, _I, _I, _I]),
+    "lfsr_scale_pack_tc": (_I, [_P, _P, C.c_int64, _P, _I, _I, _I, _I, _I, _P]),
     "lfsr_conv2d_tc": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
     "lfsr_conv2d_tc_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),
     "lfsr_block_mean": (_I, [_TP, _TP, _I, _I, _P]),

@@ -53,6 +53,7 @@ struct Params {
   // 1: stride along x, dims (c, x%s, x/s, y, image); 2: stride along y, dims (c, x, y%s, y/s, image);
   // 3: stride along both, dims (c, x%s, x/s, y%s, image*y/s))
   int amode, out_rows_per_img;
+  int w_img_rows;                      // >0: per-image weight sets, this many packed rows apart (streamed B only)
   short tap_off[25][4];
   long long* dbg;                      // optional per-CTA cycle counters (profiles/ experiments), else null
   int halo, TWo, Rout, P, Rin, ntiles, strips_x, blocks_y, total_blocks, a_cg_bytes, bstages, acc_stages, pdiv_mul;
@@ -416,7 +417,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int slot = s * p.kps + u;
             tma_load_5d(sA + slot * kABytes, &tmA, full + s, cg * 32, b1 + to[0], b2 + to[1], b3 + to[2], b4 + to[3]);
             if (!p.resident)
-              tma_load_2d(sB + slot * p.b_stage_bytes, &tmB, full + s, 0, (tc_.chunk * nks + ks + u) * p.NC);
+              tma_load_2d(sB + slot * p.b_stage_bytes, &tmB, full + s, 0,
+                          (tc_.chunk * nks + ks + u) * p.NC + (tc_.nb / p.nby) * p.w_img_rows);
           }
           if (++cg == p.cgs) { cg = 0; if (++kx == p.kw) { kx = 0; ++ky; } }
         }
@@ -747,9 +749,37 @@ extern "C" int lfsr_pack_conv_tc(const float* w, float* packed, int kh, int kw, 
 
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
+namespace lfsr { namespace tc {
+// out[img][row][k] = packed[row][k] * gate[img][cg(row)*32 + k]   (rows are [chunk][tap][cg][NC])
+__global__ void __launch_bounds__(256)
+scale_pack_kernel(const float* __restrict__ packed, const float* __restrict__ gate, long long gate_ld, float* __restrict__ out,
+                  int rows, int cgs, int NC, int cin) {
+  const int img = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * 32; i += gridDim.x * blockDim.x) {
+    const int k = i & 31, row = i >> 5;
+    const int cg = (row / NC) % cgs;
+    const int ci = cg * 32 + k;
+    const float g = ci < cin ? __ldg(gate + (size_t)img * gate_ld + ci) : 0.f;
+    out[(size_t)img * rows * 32 + i] = __ldg(packed + i) * g;
+  }
+}
+}}  // namespace
+
+extern "C" int lfsr_scale_pack_tc(const float* packed, const float* gate, int64_t gate_ld, float* out, int n, int kh, int kw,
+                                  int cin, int cout, void* stream) {
+  LFSR_REQUIRE(packed && gate && out && n > 0 && n <= 65535, "lfsr_scale_pack_tc: bad arguments");
+  const lfsr::tc::Plan pl = lfsr::tc::plan_for(cin, cout);
+  const int rows = pl.nchunks * kh * kw * pl.cgs * pl.NC;
+  dim3 grid(ceil_div(rows * 32, 256) < 64 ? ceil_div(rows * 32, 256) : 64, n);
+  lfsr::tc::scale_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(packed, gate, gate_ld > 0 ? gate_ld : cin, out, rows,
+                                                                       pl.cgs, pl.NC, cin);
+  return check_launch("scale_pack_kernel");
+}
+
 static bool tc_geometry_ok(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d) {
   if (!tensor_ok(in) || !tensor_ok(out) || !d) return false;
-  if (d->in_perm || d->out_perm || d->mul.ptr || d->in_scale) return false;
+  if (d->in_perm || d->out_perm || d->mul.ptr) return false;
+  if (d->in_scale && d->w_batch_stride <= 0) return false;      // gates must come folded into per-image weights
   if (d->kh * d->kw > 25 || d->kh < 1 || d->kw < 1) return false;
   if (in->c < 8 || in->ld % 4 != 0 || ((uintptr_t)in->ptr & 15)) return false;
   const int ry = d->shuf_ry > 0 ? d->shuf_ry : 1, rx = d->shuf_rx > 0 ? d->shuf_rx : 1;
@@ -841,7 +871,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   // Measured on B200 (profiles/r01_notes.md): correct, but not yet faster than the per-tap kernel below - the single
   // accumulator stage at N = 224 serialises epilogue and MMAs - so it is opt-in (LFSR_TC_HALO=1) until that is fixed.
   static const bool use_halo = getenv("LFSR_TC_HALO") != nullptr;
-  if (use_halo && p.kh * p.kw > 1 && p.cgs <= 2 && p.nchunks == 1) {
+  if (use_halo && d->w_batch_stride <= 0 && p.kh * p.kw > 1 && p.cgs <= 2 && p.nchunks == 1) {
     const int taps = p.kh * p.kw, nks = taps * p.cgs;
     const int kSmemAvail = 227 * 1024 - 1024 - 512 - 16 * 1024;
     const int TWo = p.bw < 32 ? p.bw : 32;
@@ -945,8 +975,9 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   struct Cand { bool res; int kps; int min_stages; };
   const Cand cands[4] = {{true, kps_tap, need}, {false, kps_tap, need}, {true, 1, 2}, {false, 1, 2}};
   p.stages = 0;
+  const bool per_image_w = d->w_batch_stride > 0;
   for (const Cand& c : cands) {
-    if (c.res && no_resident) continue;
+    if (c.res && (no_resident || per_image_w)) continue;
     const int st = stages_for(c.res, c.kps);
     if (st >= c.min_stages) { p.resident = c.res ? 1 : 0; p.kps = c.kps; p.stages = st; break; }
   }
@@ -982,7 +1013,12 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
     if (r != CUDA_SUCCESS) { set_error("lfsr_conv2d_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r); return LFSR_ERR_CUDA; }
   }
   {
-    const cuuint64_t rows = (cuuint64_t)p.nchunks * p.kh * p.kw * p.cgs * p.NC;
+    cuuint64_t rows = (cuuint64_t)p.nchunks * p.kh * p.kw * p.cgs * p.NC;
+    if (per_image_w) {
+      LFSR_REQUIRE(d->w_batch_stride == (long long)rows * 32, "lfsr_conv2d_tc: w_batch_stride must equal the packed size");
+      p.w_img_rows = (int)rows;
+      rows *= (cuuint64_t)in->n;
+    }
     cuuint64_t dims[2] = {32, rows};
     cuuint64_t strides[1] = {128};
     cuuint32_t box[2] = {32, (cuuint32_t)p.NC};

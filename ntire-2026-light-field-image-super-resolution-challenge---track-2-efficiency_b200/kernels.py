@@ -103,6 +103,7 @@ class CudaOps:
     def __init__(self, use_tc: bool = True):
         self.lib = N.load()
         self.use_tc = use_tc
+        self._gated = {}          # per-image gated weight scratch, keyed by (packed weights, batch)
 
     # -- helpers ---------------------------------------------------------------------------
     @staticmethod
@@ -154,6 +155,22 @@ class CudaOps:
             N.check(self.lib.lfsr_conv2d_small_cout(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st),
                     "lfsr_conv2d_small_cout")
             return
+        if self.use_tc and pc.w_tc is not None and in_scale is not None:
+            # per-sample gate folded into per-image weight sets (a few KB each), then the tensor-core conv
+            nimg = x.shape[0]
+            key = (pc.w_tc.data_ptr(), nimg)
+            scratch = self._gated.get(key)
+            if scratch is None:
+                scratch = torch.empty((nimg, pc.w_tc.numel()), dtype=torch.float32, device=x.device)
+                self._gated[key] = scratch
+            N.check(self.lib.lfsr_scale_pack_tc(pc.w_tc.data_ptr(), in_scale.data_ptr(), d.in_scale_ld, scratch.data_ptr(),
+                                                nimg, pc.kh, pc.kw, pc.cin, pc.cout, st), "lfsr_scale_pack_tc")
+            d.w_batch_stride = pc.w_tc.numel()
+            if self.lib.lfsr_conv2d_tc_supported(C.byref(tin), C.byref(tout), C.byref(d)):
+                N.check(self.lib.lfsr_conv2d_tc(C.byref(tin), scratch.data_ptr(), C.byref(tout), C.byref(d), st),
+                        "lfsr_conv2d_tc")
+                return
+            d.w_batch_stride = 0
         r2 = shuffle[0] * shuffle[1]
         perm_ok = pc.tc_perm_r2 == (r2 if (r2 > 1 and shuffle[2] == N.SHUF_CHANNEL_MAJOR) else 0)
         if (self.use_tc and pc.w_tc is not None and perm_ok and

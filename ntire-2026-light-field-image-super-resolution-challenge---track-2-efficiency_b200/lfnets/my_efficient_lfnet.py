@@ -204,7 +204,7 @@ class get_model(LFNetBase):
                 gw[g * gs:g * gs + n, g * gs:g * gs + n] = gate["1"].weight.detach().float().cpu()
                 gb[g * gs:g * gs + n] = gate["1"].bias.detach().float().cpu()
             s["gate"] = pc(gw, gb)
-            s["fus0"] = pc(self._exp(st.fusion["0"].weight.detach().float().cpu(), 1))
+            s["fus0"] = pc(self._exp(st.fusion["0"].weight.detach().float().cpu(), 1), tc=True)
             s["fus2"] = pc(self._exp(st.fusion["2"].weight.detach().float().cpu(), 0), tc=True, **dil)
             sm = st.sa_modulator
             s["sa_dw"] = dev_t(self._exp(_dw_pack(sm.spatial_mod["0"].weight, "cpu"), 1))

@@ -10,7 +10,6 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lfsr_b200
 from lfsr_b200 import kernels as K
-from oracle import weights
 
 
 class ProfilingOps(K.CudaOps):
@@ -59,11 +58,10 @@ def main():
     batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     dev = torch.device("cuda:0")
     net = lfsr_b200.load_net(model, 5, 4).eval()
-    net.load_state_dict(weights.make_state_dict(model, 4, 1234))
     net = net.to(dev)
     ops = ProfilingOps()
     net.set_backend(ops)
-    x = weights.synthetic_patches(batch, 5, 32, 0).to(dev)
+    x = torch.rand(batch, 1, 160, 160, device=dev)
     for _ in range(2):
         net(x)
     torch.cuda.synchronize()

@@ -7,13 +7,11 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lfsr_b200
-from oracle import weights
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda:0")
 net = lfsr_b200.load_net("MyEfficientLFNet", 5, 4).eval()
-net.load_state_dict(weights.make_state_dict("MyEfficientLFNet", 4, 1234))
 net = net.to(dev)
 call, info = net.dominant_kernel(batch)
 for _ in range(reps):

@@ -384,3 +384,19 @@ def test_conv_tc_18ch_slices(ref):
     tc_ops.conv(ang, pc2, cat_a[..., 20:38], **kw)
     ref.conv(ang, pc2, cat_b[..., 20:38], **kw)
     assert (cat_a - cat_b).abs().max().item() <= 2e-3
+
+
+def test_conv_tc_per_sample_gate(ref):
+    """in_scale (per-sample input-channel gate) on the tensor-core path via per-image weight sets"""
+    tc_ops = K.CudaOps(use_tc=True)
+    n, h, w, cin, cout = 3, 160, 160, 60, 54
+    wt = (torch.rand(cout, cin, 1, 1) - 0.5) * 0.3
+    pc = K.pack_conv(wt, device=DEV, tc=True)
+    x = nhwc(n, h, w, cin, seed=1)
+    gate = nhwc(n, 1, 1, cin, seed=2).abs()
+    a, b = nhwc(n, h, w, cout, seed=3), nhwc(n, h, w, cout, seed=3)
+    l0 = tc_ops.lib.lfsr_launch_count()
+    tc_ops.conv(x, pc, a, act=2, slope=0.1, in_scale=gate)
+    assert tc_ops.lib.lfsr_launch_count() == l0 + 2          # scale-pack + tcgen05 conv, no fp32 fallback
+    ref.conv(x, pc, b, act=2, slope=0.1, in_scale=gate)
+    assert (a - b).abs().max().item() <= 2e-3
