@@ -378,115 +378,112 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kTmaWarp) {
-    // ================= TMA producer =================
-    uint32_t it = 0;
-    int s_ring = 0;
-    uint32_t ph_ring = 0;
-    long long dbg_prod_wait = 0;
-    const long long dbg_t0 = clock64();
-    const uint32_t stage_bytes = kABytes + (p.resident ? 0 : p.NC * 128);
-    int m, chunk;
-    if (p.resident && lane == 0 && next_tile(p, 0, m, chunk)) {
-      // one-time load of this CTA's whole weight set
-      mbar_expect_tx(bfull, (uint32_t)nks * p.b_stage_bytes);
-      for (int ks = 0; ks < nks; ++ks)
-        tma_load_2d(sB + ks * p.b_stage_bytes, &tmB, bfull, 0, (chunk * nks + ks) * p.NC);
-    }
-    __syncwarp();
-    for (int i = 0; next_tile(p, i, m, chunk); ++i) {
-      const TileCoord tc_ = decode_tile(p, m, chunk);
-      int cg = 0, ky = 0, kx = 0;
-      int b1, b2, b3, b4;      // tile part of the TMA coordinates
-      if (p.amode == 0) { b1 = tc_.x0; b2 = tc_.vx; b3 = tc_.y0; b4 = tc_.nb; }
-      else if (p.amode == 1) { b1 = 0; b2 = tc_.x0; b3 = tc_.y0; b4 = tc_.nb; }
-      else if (p.amode == 2) { b1 = tc_.x0; b2 = 0; b3 = tc_.y0; b4 = tc_.nb; }
-      else { b1 = 0; b2 = tc_.x0; b3 = 0; b4 = tc_.nb * p.out_rows_per_img + tc_.y0; }
-      for (int ks = 0; ks < nks; ks += p.kps, ++it) {
-        if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
-        const int s = s_ring++;
-        const uint32_t ph = ph_ring;
-        long long tw0 = 0;
-        if (p.dbg) tw0 = clock64();
-        mbar_wait(empty + s, ph ^ 1);
-        if (p.dbg) dbg_prod_wait += clock64() - tw0;
-        const int nsub = nks - ks < p.kps ? nks - ks : p.kps;
-        if (lane == 0) mbar_expect_tx(full + s, (uint32_t)nsub * stage_bytes);
-        for (int u = 0; u < nsub; ++u) {
-          if (lane == 0) {
-            const short* to = p.tap_off[ky * p.kw + kx];
+    // ================= TMA producer (one thread) =================
+    if (lane == 0) {
+      int s_ring = 0;
+      uint32_t ph_ring = 0;
+      const uint32_t stage_bytes = kABytes + (p.resident ? 0 : p.NC * 128);
+      int m, chunk;
+      if (p.resident && next_tile(p, 0, m, chunk)) {
+        // one-time load of this CTA's whole weight set
+        mbar_expect_tx(bfull, (uint32_t)nks * p.b_stage_bytes);
+        for (int ks = 0; ks < nks; ++ks)
+          tma_load_2d(sB + ks * p.b_stage_bytes, &tmB, bfull, 0, (chunk * nks + ks) * p.NC);
+      }
+      for (int i = 0; next_tile(p, i, m, chunk); ++i) {
+        const TileCoord tc_ = decode_tile(p, m, chunk);
+        int cg = 0, tap = 0;
+        int b1, b2, b3, b4;      // tile part of the TMA coordinates
+        if (p.amode == 0) { b1 = tc_.x0; b2 = tc_.vx; b3 = tc_.y0; b4 = tc_.nb; }
+        else if (p.amode == 1) { b1 = 0; b2 = tc_.x0; b3 = tc_.y0; b4 = tc_.nb; }
+        else if (p.amode == 2) { b1 = tc_.x0; b2 = 0; b3 = tc_.y0; b4 = tc_.nb; }
+        else { b1 = 0; b2 = tc_.x0; b3 = 0; b4 = tc_.nb * p.out_rows_per_img + tc_.y0; }
+        const int w_row0 = tc_.chunk * nks * p.NC + (tc_.nb / p.nby) * p.w_img_rows;
+        for (int ks = 0; ks < nks; ks += p.kps) {
+          if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
+          const int s = s_ring++;
+          mbar_wait(empty + s, ph_ring ^ 1);
+          const int nsub = nks - ks < p.kps ? nks - ks : p.kps;
+          mbar_expect_tx(full + s, (uint32_t)nsub * stage_bytes);
+          for (int u = 0; u < nsub; ++u) {
+            const short* to = p.tap_off[tap];
             const int slot = s * p.kps + u;
             tma_load_5d(sA + slot * kABytes, &tmA, full + s, cg * 32, b1 + to[0], b2 + to[1], b3 + to[2], b4 + to[3]);
-            if (!p.resident)
-              tma_load_2d(sB + slot * p.b_stage_bytes, &tmB, full + s, 0,
-                          (tc_.chunk * nks + ks + u) * p.NC + (tc_.nb / p.nby) * p.w_img_rows);
+            if (!p.resident) tma_load_2d(sB + slot * p.b_stage_bytes, &tmB, full + s, 0, w_row0 + (ks + u) * p.NC);
+            if (++cg == p.cgs) { cg = 0; ++tap; }
           }
-          if (++cg == p.cgs) { cg = 0; if (++kx == p.kw) { kx = 0; ++ky; } }
         }
-        __syncwarp();
       }
     }
-    if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = dbg_prod_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - dbg_t0; }
+    __syncwarp();
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
-    long long dbg_full_wait = 0, dbg_acc_wait = 0, dbg_issue = 0;
-    const long long dbg_t0 = clock64();
-    uint32_t it = 0, tcount = 0;
-    int s_ring = 0;
-    uint32_t ph_ring = 0;
-    const uint32_t idesc = make_idesc(p.NC);
-    const uint64_t a_desc0 = make_smem_desc(smem_u32(sA)), b_desc0 = make_smem_desc(smem_u32(sB));
-    const int rem_last = p.C - (p.cgs - 1) * 32;
-    const int ksteps_last = rem_last >= 32 ? 4 : (rem_last + 7) >> 3;
-    int m, chunk;
-    if (p.resident && next_tile(p, 0, m, chunk)) mbar_wait(bfull, 0);
-    for (int i = 0; next_tile(p, i, m, chunk); ++i, ++tcount) {
-      const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
-      long long tw0 = clock64();
-      mbar_wait(tempty + a, aph ^ 1);
-      dbg_acc_wait += clock64() - tw0;
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + a * kAccStride;
-      int cg_i = 0;
-      for (int ks = 0; ks < nks; ks += p.kps, ++it) {
-        if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
-        const int s = s_ring++;
-        const uint32_t ph = ph_ring;
+    // The whole loop runs in ONE thread (no per-stage __syncwarp, no divergent waits). That thread is in lock-step with
+    // the tensor pipe (the MMA queue is ~4 instructions deep), so everything here that is not a tcgen05.mma is overhead.
+    if (lane == 0) {
+      long long dbg_full_wait = 0, dbg_acc_wait = 0, dbg_mma = 0;
+      const long long dbg_t0 = clock64();
+      uint32_t tcount = 0;
+      int s_ring = 0;
+      uint32_t ph_ring = 0;
+      const uint32_t idesc = make_idesc(p.NC);
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(sA)), b_desc0 = make_smem_desc(smem_u32(sB));
+      const int rem_last = p.C - (p.cgs - 1) * 32;
+      const int ksteps_last = rem_last >= 32 ? 4 : (rem_last + 7) >> 3;
+      const uint32_t b_step = (uint32_t)(p.b_stage_bytes >> 4);
+      const uint32_t a_stage_step = (uint32_t)(p.kps * (kABytes >> 4)), b_stage_step = (uint32_t)p.kps * b_step;
+      const bool tap_stages = p.kps == p.cgs;
+      int m, chunk;
+      if (p.resident && next_tile(p, 0, m, chunk)) mbar_wait(bfull, 0);
+      for (int i = 0; next_tile(p, i, m, chunk); ++i, ++tcount) {
+        const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+        long long tw0 = 0;
         if (p.dbg) tw0 = clock64();
-        mbar_wait(full + s, ph);
-        long long tw1 = 0;
-        if (p.dbg) { tw1 = clock64(); dbg_full_wait += tw1 - tw0; }
+        mbar_wait(tempty + a, aph ^ 1);
+        if (p.dbg) dbg_acc_wait += clock64() - tw0;
         tc_fence_after();
-        const int nsub = nks - ks < p.kps ? nks - ks : p.kps;
-        if (lane == 0) {
-          const uint32_t b_step = (uint32_t)(p.b_stage_bytes >> 4);
-          const uint64_t a_d0 = a_desc0 + (uint64_t)(s * p.kps * (kABytes >> 4));
-          const uint64_t b_d0 = b_desc0 + (uint64_t)((p.resident ? ks : s * p.kps) * b_step);
-          if (p.kps == p.cgs) {          // stage == tap: unrolled issue
+        const uint32_t d_tmem = tmem_base + a * kAccStride;
+        int cg_i = 0;
+        for (int ks = 0; ks < nks; ks += p.kps) {
+          if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
+          const int s = s_ring++;
+          if (p.dbg) tw0 = clock64();
+          mbar_wait(full + s, ph_ring);
+          long long tw1 = 0;
+          if (p.dbg) { tw1 = clock64(); dbg_full_wait += tw1 - tw0; }
+          tc_fence_after();
+          const uint64_t a_d0 = a_desc0 + (uint64_t)(s * a_stage_step);
+          const uint64_t b_d0 = b_desc0 + (uint64_t)(p.resident ? ks * b_step : s * b_stage_step);
+          if (tap_stages) {              // stage == one tap with all channel groups: fully unrolled issue
             if (ks == 0) umma_tap_dispatch<true>(p.cgs, d_tmem, a_d0, b_d0, b_step, idesc, ksteps_last);
             else umma_tap_dispatch<false>(p.cgs, d_tmem, a_d0, b_d0, b_step, idesc, ksteps_last);
+          } else if (p.kps == 1) {       // stage == one (tap, channel group)
+            const int ksteps = (cg_i == p.cgs - 1) ? ksteps_last : 4;
+            if (ks == 0) umma_stage<true>(d_tmem, a_d0, b_d0, idesc, ksteps);
+            else umma_stage<false>(d_tmem, a_d0, b_d0, idesc, ksteps);
+            if (++cg_i == p.cgs) cg_i = 0;
           } else {
-            int cgu = cg_i;
+            const int nsub = nks - ks < p.kps ? nks - ks : p.kps;
             for (int u = 0; u < nsub; ++u) {
-              const int ksteps = (cgu == p.cgs - 1) ? ksteps_last : 4;
+              const int ksteps = (cg_i == p.cgs - 1) ? ksteps_last : 4;
               const uint64_t a_d = a_d0 + (uint64_t)(u * (kABytes >> 4));
               const uint64_t b_d = b_d0 + (uint64_t)(u * b_step);
               if (ks + u == 0) umma_stage<true>(d_tmem, a_d, b_d, idesc, ksteps);
               else umma_stage<false>(d_tmem, a_d, b_d, idesc, ksteps);
-              if (++cgu == p.cgs) cgu = 0;
+              if (++cg_i == p.cgs) cg_i = 0;
             }
           }
           umma_commit(empty + s);                            // frees the smem stage when these MMAs retire
-          if (ks + nsub >= nks) umma_commit(tfull + a);      // accumulator complete -> epilogue
+          if (ks + p.kps >= nks) umma_commit(tfull + a);     // accumulator complete -> epilogue
+          if (p.dbg) dbg_mma += clock64() - tw1;
         }
-        if (p.kps != p.cgs) cg_i = (cg_i + nsub) % p.cgs;
-        __syncwarp();
-        if (p.dbg) dbg_issue += clock64() - tw1;
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 2] = dbg_full_wait; p.dbg[blockIdx.x * 8 + 3] = dbg_acc_wait;
+        p.dbg[blockIdx.x * 8 + 4] = dbg_mma; p.dbg[blockIdx.x * 8 + 5] = clock64() - dbg_t0;
       }
     }
-    if (p.dbg && lane == 0) {
-      p.dbg[blockIdx.x * 8 + 2] = dbg_full_wait; p.dbg[blockIdx.x * 8 + 3] = dbg_acc_wait;
-      p.dbg[blockIdx.x * 8 + 4] = dbg_issue; p.dbg[blockIdx.x * 8 + 5] = clock64() - dbg_t0;
-    }
+    __syncwarp();
   } else {
     // ================= epilogue (warps 0..7 <-> TMEM lane quarters, two warps each) =================
     // TMEM -> registers (one pixel row per lane) -> 4 KB swizzled smem transpose per warp ->

@@ -149,8 +149,9 @@ mma_rate_kernel(long long* out, int N, int chain, int alternate, int kmode) {
       const uint32_t d = tmem + ((alternate == 1 && (i & 1)) ? 256 : 0);
       asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                    ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(i > 1)) : "memory");
-      // alternate >= 2: commit to a scratch mbarrier after every `alternate` MMAs (cost of tcgen05.commit in the issue stream)
-      if (alternate >= 2 && (i % alternate) == alternate - 1)
+      // alternate == 4 / 8: commit to a scratch mbarrier after every 4th / 8th MMA (cost of tcgen05.commit in the issue
+      // stream; mask test instead of a modulo so the probe itself stays cheap)
+      if ((alternate == 4 && (i & 3) == 3) || (alternate == 8 && (i & 7) == 7))
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar + 2)) : "memory");
     }
     const long long t1 = clock64();

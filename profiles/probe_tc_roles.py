@@ -18,5 +18,6 @@ for (cin, cout, hw, dil) in ((64, 64, 160, 5), (56, 224, 320, 1)):
     torch.cuda.synchronize()
     d = dbg.view(148, 8).double().mean(0).tolist()
     ntile = B * hw * hw / 128 / 148
-    print(f"{cin}->{cout} @{hw} d{dil}: tiles/CTA {ntile:.0f} | producer: wait-empty {d[0]:.0f} of {d[1]:.0f} cyc | "
-          f"MMA: wait-full {d[2]:.0f}, wait-acc {d[3]:.0f}, issue {d[4]:.0f} of {d[5]:.0f} cyc | per stage {d[5]/ntile/18:.0f}")
+    print(f"{cin}->{cout} @{hw} d{dil}: tiles/CTA {ntile:.0f} | "
+          f"MMA thread: wait-full {d[2]:.0f}, wait-acc {d[3]:.0f}, fence+issue+commit {d[4]:.0f} of {d[5]:.0f} cyc | "
+          f"per k-stage {d[5]/ntile/18:.0f}")
