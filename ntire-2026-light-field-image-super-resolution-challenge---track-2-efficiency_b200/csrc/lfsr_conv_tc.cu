@@ -967,7 +967,11 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
     if (res) return b_all >= kSmemMax ? 0 : (int)((kSmemMax - b_all) / ((long long)kps * kABytes));
     return (kSmemBudget - kEpiWarps * 4096) / (kps * (kABytes + p.b_stage_bytes));
   };
-  const int kps_tap = kps_env > 0 ? kps_env : (p.cgs <= 4 ? p.cgs : 1);
+  // narrow layers (N <= 64) are bound by the per-stage barrier round trip of the issuing thread: pack up to 4
+  // K-stages (whole taps) into one smem stage; wide layers keep one tap per stage so that >= 3 stages fit
+  int kps_auto = p.cgs <= 4 ? p.cgs : 1;
+  if (p.NC <= 64 && p.cgs <= 2) kps_auto = 4 / p.cgs * p.cgs;
+  const int kps_tap = kps_env > 0 ? kps_env : kps_auto;
   const int need = p.NC <= 64 ? 2 : 3;
   struct Cand { bool res; int kps; int min_stages; };
   const Cand cands[4] = {{true, kps_tap, need}, {false, kps_tap, need}, {true, 1, 2}, {false, 1, 2}};
