@@ -125,28 +125,59 @@ __device__ __forceinline__ void load18(const float* src, float* v) {
   }
 }
 
+// Block = 32x8 output pixels. The 18-channel input tile with a halo of max(klen/2, dil) pixels is staged with
+// cp.async as 20-float pixels (18 + the 2 zero pad lanes of the grouped trunk layout) - 80 B = five 16-byte chunks -
+// and every tap is then five conflict-free LDS.128 (stride 20 floats) instead of nine strided 8-byte global loads.
+constexpr int EP_W = 32, EP_H = 8, EP_CS = 20;
+__device__ __forceinline__ void lds20(const float* src, float* v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = reinterpret_cast<const float4*>(src)[i];
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+  const float2 t = *reinterpret_cast<const float2*>(src + 16);
+  v[16] = t.x; v[17] = t.y;
+}
+
 __global__ void __launch_bounds__(256)
 mel_epi_branch_kernel(const EpiArgs a) {
-  extern __shared__ float sw[];
+  extern __shared__ __align__(16) float sw[];
   const int KL = a.KL;
+  const int half = KL / 2;
+  const int halo = half > a.dil ? half : a.dil;
+  const int hw = EP_W + 2 * halo, hh = EP_H + 2 * halo;
   const int n_w = (2 * KL + 9) * EC + 3 * EC * EC + 3 * EC * EC;
+  const int n_w4 = (n_w + 3) & ~3;
+  float* tile = sw + n_w4;                              // [hh*hw][EP_CS]
+  int t_ = blockIdx.x;
+  const int tx0 = (t_ % a.tiles_x) * EP_W; t_ /= a.tiles_x;
+  const int ty0 = (t_ % a.tiles_y) * EP_H;
+  const int img = t_ / a.tiles_y;
+  for (int i = threadIdx.x; i < hh * hw * 5; i += 256) {
+    const int ch = i % 5, pix = i / 5;
+    const int ly = pix / hw, lx = pix - ly * hw;
+    const int iy = ty0 - halo + ly, ix = tx0 - halo + lx;
+    const bool inside = iy >= 0 && iy < a.in.h && ix >= 0 && ix < a.in.w;
+    const float* src = a.in.p + (inside ? a.in.pix(img, iy, ix) : 0) + ch * 4;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + pix * EP_CS + ch * 4);
+    const int nbytes = inside ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = threadIdx.x; i < n_w; i += 256) sw[i] = __ldg(a.w + i);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   const float* dwh = sw;
   const float* dwv = dwh + KL * EC;
   const float* dwd = dwv + KL * EC;
   const float* pw = dwd + 9 * EC;            // 3 x [EC in][EC out]
   const float* fu = pw + 3 * EC * EC;        // [3*EC in][EC out]
-  int tile = blockIdx.x;
-  const int tx = tile % a.tiles_x; tile /= a.tiles_x;
-  const int ty = tile % a.tiles_y;
-  const int img = tile / a.tiles_y;
-  const int ox = tx * 32 + (threadIdx.x & 31), oy = ty * 8 + (threadIdx.x >> 5);
-  if (ox >= a.in.w || oy >= a.in.h) return;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int ox = tx0 + lx, oy = ty0 + ly;
+  const float* centre = tile + ((ly + halo) * hw + lx + halo) * EP_CS;
   float outv[EC];
 #pragma unroll
   for (int o = 0; o < EC; ++o) outv[o] = 0.f;
-  const int half = KL / 2;
 #pragma unroll 1
   for (int br = 0; br < 3; ++br) {
     float t[EC];
@@ -154,13 +185,12 @@ mel_epi_branch_kernel(const EpiArgs a) {
     for (int c = 0; c < EC; ++c) t[c] = 0.f;
     const int ntap = br == 2 ? 9 : KL;
     for (int k = 0; k < ntap; ++k) {
-      int iy = oy, ix = ox;
-      if (br == 0) ix = ox - half + k;
-      else if (br == 1) iy = oy - half + k;
-      else { iy = oy + (k / 3 - 1) * a.dil; ix = ox + (k % 3 - 1) * a.dil; }
-      if (iy < 0 || iy >= a.in.h || ix < 0 || ix >= a.in.w) continue;
+      int dy = 0, dx = 0;
+      if (br == 0) dx = k - half;
+      else if (br == 1) dy = k - half;
+      else { dy = (k / 3 - 1) * a.dil; dx = (k % 3 - 1) * a.dil; }
       float v[EC];
-      load18(a.in.p + a.in.pix(img, iy, ix), v);
+      lds20(centre + (dy * hw + dx) * EP_CS, v);           // out-of-image pixels were zero-filled
       const float* wk = (br == 0 ? dwh : (br == 1 ? dwv : dwd)) + k * EC;
 #pragma unroll
       for (int c = 0; c < EC; ++c) t[c] = fmaf(v[c], wk[c], t[c]);
@@ -178,6 +208,7 @@ mel_epi_branch_kernel(const EpiArgs a) {
       for (int o2 = 0; o2 < EC; ++o2) outv[o2] = fmaf(s, fub[o * EC + o2], outv[o2]);
     }
   }
+  if (ox >= a.in.w || oy >= a.in.h) return;
   float* dst = a.out.p + a.out.pix(img, oy, ox);
 #pragma unroll
   for (int i = 0; i < EC / 2; ++i) {
@@ -253,12 +284,18 @@ extern "C" int lfsr_mel_epi_branch(const lfsr_tensor* in, const float* w_packed,
   LFSR_REQUIRE(in->c == EC && out->c == EC, "lfsr_mel_epi_branch: built for %d-channel EPI splits, got %d", EC, in->c);
   LFSR_REQUIRE(in->n == out->n && in->h == out->h && in->w == out->w, "lfsr_mel_epi_branch: shape mismatch");
   LFSR_REQUIRE(klen > 0 && (klen & 1) && klen <= 31 && dil > 0, "lfsr_mel_epi_branch: bad kernel length");
-  LFSR_REQUIRE(in->ld % 2 == 0 && out->ld % 2 == 0 && ((uintptr_t)in->ptr & 7) == 0 && ((uintptr_t)out->ptr & 7) == 0,
-               "lfsr_mel_epi_branch: 8-byte aligned channel slices required");
+  LFSR_REQUIRE(in->ld % 4 == 0 && in->ld >= EC + 2 && ((uintptr_t)in->ptr & 15) == 0,
+               "lfsr_mel_epi_branch: input slice must be 16-byte aligned with 2 readable pad floats (grouped trunk layout)");
+  LFSR_REQUIRE(out->ld % 2 == 0 && ((uintptr_t)out->ptr & 7) == 0, "lfsr_mel_epi_branch: 8-byte aligned output slice required");
   EpiArgs a;
   a.in = view_of(in); a.out = view_of(out); a.w = w_packed; a.KL = klen; a.dil = dil; a.slope = slope;
-  a.tiles_x = ceil_div(in->w, 32); a.tiles_y = ceil_div(in->h, 8);
-  const size_t smem = ((size_t)(2 * klen + 9) * EC + 6 * EC * EC) * sizeof(float);
+  a.tiles_x = ceil_div(in->w, EP_W); a.tiles_y = ceil_div(in->h, EP_H);
+  const int halo = klen / 2 > dil ? klen / 2 : dil;
+  const int n_w = (2 * klen + 9) * EC + 6 * EC * EC;
+  const size_t smem = ((size_t)((n_w + 3) & ~3) + (size_t)(EP_W + 2 * halo) * (EP_H + 2 * halo) * EP_CS) * sizeof(float);
+  LFSR_REQUIRE(smem <= 200 * 1024, "lfsr_mel_epi_branch: kernel length / dilation too large for the staged tile");
+  static bool attr_done = false;
+  if (!attr_done) { cudaFuncSetAttribute(mel_epi_branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; }
   mel_epi_branch_kernel<<<in->n * a.tiles_x * a.tiles_y, 256, smem, (cudaStream_t)stream>>>(a);
   return check_launch("mel_epi_branch_kernel");
 }

@@ -17,37 +17,77 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 // ---- block mean: one CTA per (n, by, bx); AdaptiveAvgPool2d(1) / (angRes) of
 // MyEfficientLFNet.py:159-173,491 when the block tiles the image evenly.
+// VEC4 path: 16 lanes x float4 cover up to 64 channels of a pixel (coalesced 256 B), 16 pixel lanes, 4 loads in flight.
+template <bool VEC4>
 __global__ void __launch_bounds__(256)
 block_mean_kernel(TView in, TView out, int bh, int bw) {
-  __shared__ float red[256];
+  __shared__ float red[16][68];
   int blk = blockIdx.x;
   const int nbx = in.w / bw, nby = in.h / bh;
   const int bx = blk % nbx; blk /= nbx;
   const int by = blk % nby;
   const int img = blk / nby;
   const int C = in.c;
-  const int CW = C > 32 ? 64 : (C > 16 ? 32 : 16);
-  const int PL = 256 / CW;
-  const int cl = threadIdx.x % CW, pl = threadIdx.x / CW;
   const int npix = bh * bw;
   const float inv = 1.f / (float)npix;
-  for (int c0 = 0; c0 < C; c0 += CW) {
-    const int c = c0 + cl;
-    float s = 0.f;
-    if (c < C) {
-      for (int p = pl; p < npix; p += PL) {
-        const int y = by * bh + p / bw, x = bx * bw + p % bw;
-        s += __ldg(in.p + in.pix(img, y, x) + c);
+  if (VEC4) {
+    const int c4 = threadIdx.x & 15, pl = threadIdx.x >> 4;      // channel chunk, pixel lane
+    for (int c0 = 0; c0 < C; c0 += 64) {
+      const int c = c0 + c4 * 4;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C) {
+        const float* base = in.p + in.pix(img, by * bh, bx * bw) + c;
+        int p = pl;
+        for (; p + 48 < npix; p += 64) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int q = p + 16 * u;
+            const int y = q / bw, x = q - y * bw;
+            v[u] = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y * in.w + x) * in.ld));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+        }
+        for (; p < npix; p += 16) {
+          const int y = p / bw, x = p - y * bw;
+          const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y * in.w + x) * in.ld));
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
       }
+      red[pl][c4 * 4] = s.x; red[pl][c4 * 4 + 1] = s.y; red[pl][c4 * 4 + 2] = s.z; red[pl][c4 * 4 + 3] = s.w;
+      __syncthreads();
+      if (threadIdx.x < 64 && c0 + threadIdx.x < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) t += red[q][threadIdx.x];
+        out.p[out.pix(img, by, bx) + c0 + threadIdx.x] = t * inv;
+      }
+      __syncthreads();
     }
-    red[threadIdx.x] = s;
-    __syncthreads();
-    if (pl == 0 && c < C) {
-      float t = 0.f;
-      for (int q = 0; q < PL; ++q) t += red[q * CW + cl];
-      out.p[out.pix(img, by, bx) + c] = t * inv;
+  } else {
+    const int CW = C > 32 ? 64 : (C > 16 ? 32 : 16);
+    const int PL = 256 / CW;
+    const int cl = threadIdx.x % CW, pl = threadIdx.x / CW;
+    float* redf = &red[0][0];
+    for (int c0 = 0; c0 < C; c0 += CW) {
+      const int c = c0 + cl;
+      float s = 0.f;
+      if (c < C) {
+        for (int p = pl; p < npix; p += PL) {
+          const int y = by * bh + p / bw, x = bx * bw + p % bw;
+          s += __ldg(in.p + in.pix(img, y, x) + c);
+        }
+      }
+      redf[threadIdx.x] = s;
+      __syncthreads();
+      if (pl == 0 && c < C) {
+        float t = 0.f;
+        for (int q = 0; q < PL; ++q) t += redf[q * CW + cl];
+        out.p[out.pix(img, by, bx) + c] = t * inv;
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -310,7 +350,9 @@ extern "C" int lfsr_block_mean(const lfsr_tensor* in, const lfsr_tensor* out, in
   LFSR_REQUIRE(out->n == in->n && out->h == in->h / block_h && out->w == in->w / block_w && out->c == in->c,
                "lfsr_block_mean: out shape mismatch");
   const int grid = in->n * out->h * out->w;
-  block_mean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(in), view_of(out), block_h, block_w);
+  const bool vec4 = (in->c % 4 == 0) && (in->ld % 4 == 0) && (((uintptr_t)in->ptr & 15) == 0);
+  if (vec4) block_mean_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(in), view_of(out), block_h, block_w);
+  else block_mean_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(in), view_of(out), block_h, block_w);
   return check_launch("block_mean_kernel");
 }
 
