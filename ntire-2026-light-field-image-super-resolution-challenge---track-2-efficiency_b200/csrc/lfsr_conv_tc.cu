@@ -53,6 +53,7 @@ struct Params {
   // 1: stride along x, dims (c, x%s, x/s, y, image); 2: stride along y, dims (c, x, y%s, y/s, image);
   // 3: stride along both, dims (c, x%s, x/s, y%s, image*y/s))
   int amode, out_rows_per_img;
+  int pair;                            // 1: launched as 2-CTA clusters that share every weight stage via TMA multicast
   int w_img_rows;                      // >0: per-image weight sets, this many packed rows apart (streamed B only)
   short tap_off[25][4];
   long long* dbg;                      // optional per-CTA cycle counters (profiles/ experiments), else null
@@ -104,6 +105,26 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// weights for a CTA pair: each CTA fetches half of the rows and the TMA unit writes them into BOTH CTAs' shared
+// memory (same offset) and signals both CTAs' mbarriers
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -220,14 +241,23 @@ __device__ __forceinline__ bool next_tile(const Params& p, int i, int& m, int& c
     m = blockIdx.x / p.nchunks + i * (gridDim.x / p.nchunks);
     return m < p.m_tiles;
   }
-  const int t = blockIdx.x + i * gridDim.x;
-  if (t >= p.total_tiles) return false;
+  int t = blockIdx.x + i * gridDim.x;
+  if (p.pair) {
+    // both CTAs of a pair must step through the same number of stages: iterate while the pair's first CTA has work
+    // and clamp the partner to the last tile (its stores are suppressed through m < 0)
+    const int t0 = (int)(blockIdx.x & ~1u) + i * gridDim.x;
+    if (t0 >= p.total_tiles) return false;
+    if (t >= p.total_tiles) { chunk = (p.total_tiles - 1) % p.nchunks; m = -1; return true; }
+  } else if (t >= p.total_tiles) {
+    return false;
+  }
   chunk = t % p.nchunks;
   m = t / p.nchunks;
   return true;
 }
 __device__ __forceinline__ TileCoord decode_tile(const Params& p, int t, int chunk) {
   TileCoord c;
+  if (t < 0) t = p.m_tiles - 1;      // dummy tile of a CTA pair: valid coordinates, nothing is stored
   c.chunk = chunk;
   c.x0 = (t % p.tiles_x) * p.TW; t /= p.tiles_x;
   c.vx = t % p.nbx; t /= p.nbx;
@@ -342,7 +372,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, float* stg, uint3
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmBh, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -362,7 +393,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, p.pair ? 2 : 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, kEpiWarps); }
     mbar_init(bfull, 1);
     fence_barrier_init();
@@ -374,6 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (p.pair) cluster_sync_all();     // the partner's barriers must be initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -382,6 +414,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int s_ring = 0;
       uint32_t ph_ring = 0;
+      const int crank = p.pair ? (int)cluster_ctarank() : 0;
       const uint32_t stage_bytes = kABytes + (p.resident ? 0 : p.NC * 128);
       int m, chunk;
       if (p.resident && next_tile(p, 0, m, chunk)) {
@@ -409,7 +442,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const short* to = p.tap_off[tap];
             const int slot = s * p.kps + u;
             tma_load_5d(sA + slot * kABytes, &tmA, full + s, cg * 32, b1 + to[0], b2 + to[1], b3 + to[2], b4 + to[3]);
-            if (!p.resident) tma_load_2d(sB + slot * p.b_stage_bytes, &tmB, full + s, 0, w_row0 + (ks + u) * p.NC);
+            if (!p.resident) {
+              if (p.pair) {        // my half of the rows, written into both CTAs of the pair
+                const int half_rows = p.NC >> 1;
+                tma_load_2d_mc(sB + slot * p.b_stage_bytes + crank * half_rows * 128, &tmBh, full + s, 0,
+                               w_row0 + (ks + u) * p.NC + crank * half_rows, (uint16_t)3);
+              } else {
+                tma_load_2d(sB + slot * p.b_stage_bytes, &tmB, full + s, 0, w_row0 + (ks + u) * p.NC);
+              }
+            }
             if (++cg == p.cgs) { cg = 0; ++tap; }
           }
         }
@@ -473,7 +514,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (++cg_i == p.cgs) cg_i = 0;
             }
           }
-          umma_commit(empty + s);                            // frees the smem stage when these MMAs retire
+          if (p.pair) umma_commit_mc(empty + s, (uint16_t)3);   // both CTAs must be done before either refills the stage
+          else umma_commit(empty + s);                       // frees the smem stage when these MMAs retire
           if (ks + p.kps >= nks) umma_commit(tfull + a);     // accumulator complete -> epilogue
           if (p.dbg) dbg_mma += clock64() - tw1;
         }
@@ -499,13 +541,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull + a, aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccStride;
-      epilogue_tile(p, stg, taddr, lane, q, tc_, 0, half, 2);
+      if (m_ >= 0) epilogue_tile(p, stg, taddr, lane, q, tc_, 0, half, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + a);
     }
   }
   __syncthreads();
+  if (p.pair) cluster_sync_all();     // no CTA may exit while its partner can still multicast into it
   if (warp == kMmaWarp) {
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -1037,6 +1080,36 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
     grid = grid / p.nchunks * p.nchunks;                   // every CTA owns one cout-chunk for its lifetime
     if (grid < p.nchunks) grid = p.nchunks;
   }
-  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  // CTA pairs with multicast weights for wide streamed layers (weights are 64 % of their L2->SM traffic)
+  // (measured on B200: parity-green but no gain - 3.90 ms with and without at batch 64, the weight stages are L2 hits
+  //  that were not the limiter - so it is opt-in: LFSR_TC_PAIR=1)
+  static const bool use_pair = getenv("LFSR_TC_PAIR") != nullptr;
+  p.pair = (use_pair && !p.resident && !per_image_w && p.NC >= 128 && p.NC % 16 == 0 && grid >= 2 && p.nchunks == 1) ? 1 : 0;
+  CUtensorMap tmBh = tmB;
+  if (p.pair) {
+    grid &= ~1;
+    cuuint64_t rows = (cuuint64_t)p.nchunks * p.kh * p.kw * p.cgs * p.NC;
+    cuuint64_t dims[2] = {32, rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {32, (cuuint32_t)(p.NC / 2)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmBh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w_packed_tc), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("lfsr_conv2d_tc: cuTensorMapEncodeTiled(B half) failed with %d", (int)r); return LFSR_ERR_CUDA; }
+  }
+  static const bool verbose = getenv("LFSR_TC_VERBOSE") != nullptr;
+  if (verbose)
+    fprintf(stderr, "[lfsr tc] C=%d cout=%d NC=%d k=%dx%d tiles=%d grid=%d stages=%d kps=%d resident=%d pair=%d TH=%d TW=%d vec=%d smem=%zu\n",
+            p.C, p.cout, p.NC, p.kh, p.kw, p.total_tiles, grid, p.stages, p.kps, p.resident, p.pair, p.TH, p.TW, p.vec, smem);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel, tmA, tmB, tmBh, p);
+  if (le != cudaSuccess) { set_error("lfsr_conv2d_tc: launch failed: %s", cudaGetErrorString(le)); return LFSR_ERR_CUDA; }
   return check_launch("conv_tc_kernel");
 }

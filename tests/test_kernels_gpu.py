@@ -289,10 +289,12 @@ def test_conv_tc(ref, case):
     _run_tc_case(ref, case)
 
 
-def test_conv_tc_halo_block_kernel(ref):
-    """the opt-in halo-block kernel (LFSR_TC_HALO=1) in a subprocess so the env switch is seen at first use"""
+@pytest.mark.parametrize("switch", ["LFSR_TC_HALO", "LFSR_TC_PAIR"])
+def test_conv_tc_halo_block_kernel(ref, switch):
+    """the opt-in variants (halo-block kernel, CTA-pair weight multicast) in a subprocess so the env switch is seen
+    at first use"""
     import subprocess, sys, os
-    env = dict(os.environ, LFSR_TC_HALO="1")
+    env = dict(os.environ, **{switch: "1"})
     code = ("import sys; sys.path[:0]=['.','tests']; import torch, opref, test_kernels_gpu as t; "
             "torch.backends.cudnn.allow_tf32=False; torch.backends.cuda.matmul.allow_tf32=False; r=opref.RefOps();\n"
             "for c in t.TC_CASES:\n    if c['k']==(3,3) and c['cin']<=64: t._run_tc_case(r, c)\nprint('halo ok')")
