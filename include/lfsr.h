@@ -47,7 +47,9 @@ typedef struct {
   int32_t ld; /* floats between consecutive pixels */
 } lfsr_tensor;
 
-enum { LFSR_ACT_NONE = 0, LFSR_ACT_RELU = 1, LFSR_ACT_LRELU = 2, LFSR_ACT_SIGMOID = 3 };
+enum { LFSR_ACT_NONE = 0, LFSR_ACT_RELU = 1, LFSR_ACT_LRELU = 2, LFSR_ACT_SIGMOID = 3,
+       LFSR_ACT_GELU = 4,      /* nn.GELU() (erf form), MyEfficientLFNetV4_5.py:213,231 */
+       LFSR_ACT_SILU = 5       /* F.silu, as `mul_act` on the FastConvSSM gate (:242) */ };
 enum { LFSR_PERM_NONE = 0, LFSR_PERM_MACPI_OVER_SAI = 1 };
 enum { LFSR_SHUF_CHANNEL_MAJOR = 0, /* nn.PixelShuffle: co = c*ry*rx + i*rx + j   */
        LFSR_SHUF_FACTOR_MAJOR = 1   /* PixelShuffle1D  : co = (i*rx + j)*C + c     */ };
@@ -55,7 +57,7 @@ enum { LFSR_INTERP_BICUBIC = 0, LFSR_INTERP_BILINEAR = 1 };
 
 /* Convolution + fused epilogue descriptor.
  *   v = sum_taps W[tap][ci][co] * in_scale[n][ci] * in(n, oy*stride_h - pad_h + ky*dil_h, ..., ci) + bias[co]
- *   v = act(v); v *= mul(n,oy,ox,co); v *= alpha;
+ *   v = act(v); v *= mul_act(mul(n,oy,ox,co)); v *= alpha;
  *   (sy,sx,sc) = shuffle(oy,ox,co); v += res(n,sy,sx,sc); out(n,sy,sx,sc) = v
  * in_perm / out_perm = LFSR_PERM_MACPI_OVER_SAI: the logical image the convolution walks is the
  * MacPI arrangement mac[i*A+u][j*A+v] of a tensor stored as SAI sai[u*h+i][v*w+j] (A = perm_a);
@@ -69,6 +71,7 @@ typedef struct {
   int32_t act;
   float act_slope;
   float alpha;
+  int32_t mul_act;       /* activation applied to the `mul` operand before the product (LFSR_ACT_*) */
   const float* bias;     /* [cout] or NULL */
   const float* in_scale; /* [n][in_scale_ld] (first cin used) or NULL */
   int64_t in_scale_ld;   /* floats between samples of in_scale; 0 = cin */
@@ -152,6 +155,11 @@ int lfsr_block_mean(const lfsr_tensor* in, const lfsr_tensor* out, int block_h, 
 int lfsr_sa_modulate(const lfsr_tensor* x, const float* dw_w, const float* bn_scale,
                      const float* bn_shift, const lfsr_tensor* amod, float w0, float w1,
                      const lfsr_tensor* res, const lfsr_tensor* out, int dil, void* stream);
+
+/* out = x * scale[n][c] + res  (ChannelAttention + block residual, MyEfficientLFNetV4_5.py:148,291-299);
+ * scale is an [n,1,1,c] tensor view, res may be NULL. */
+int lfsr_scale_add(const lfsr_tensor* x, const lfsr_tensor* scale, const lfsr_tensor* res, const lfsr_tensor* out,
+                   void* stream);
 
 /* ---- EPIT token ops (EPIT.py:74-128) ------------------------------------------------------ */
 /* LayerNorm over c (eps, affine) for every pixel/token */

@@ -15,6 +15,7 @@ __all__ = ["_native", "kernels", "LfsrError", "build_native", "load_net", "NETS"
 #: reference model name (model/SR/<name>.py) -> module under lfnets/
 NETS = {
     "MyEfficientLFNet": "my_efficient_lfnet",
+    "MyEfficientLFNetV4_5": "my_efficient_lfnet_v4_5",
     "EPIT": "epit",
     "DistgSSR": "distgssr",
     "LF_InterNet": "lf_internet",

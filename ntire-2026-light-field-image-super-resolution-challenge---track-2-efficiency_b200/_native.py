@@ -14,7 +14,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "liblfsr_b200.so")
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
-ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_GELU, ACT_SILU = 0, 1, 2, 3, 4, 5
 PERM_NONE, PERM_MACPI_OVER_SAI = 0, 1
 SHUF_CHANNEL_MAJOR, SHUF_FACTOR_MAJOR = 0, 1
 INTERP_BICUBIC, INTERP_BILINEAR = 0, 1
@@ -36,7 +36,7 @@ class ConvDesc(C.Structure):
         ("in_perm", C.c_int32), ("out_perm", C.c_int32), ("perm_a", C.c_int32),
         ("shuf_ry", C.c_int32), ("shuf_rx", C.c_int32), ("shuf_mode", C.c_int32),
         ("block_h", C.c_int32), ("block_w", C.c_int32),
-        ("act", C.c_int32), ("act_slope", C.c_float), ("alpha", C.c_float),
+        ("act", C.c_int32), ("act_slope", C.c_float), ("alpha", C.c_float), ("mul_act", C.c_int32),
         ("bias", C.c_void_p), ("in_scale", C.c_void_p), ("in_scale_ld", C.c_int64), ("w_batch_stride", C.c_int64),
         ("mul", Tensor), ("res", Tensor),
     ]
@@ -76,6 +76,7 @@ SIGNATURES = {
     "lfsr_conv2d_tc_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),
     "lfsr_block_mean": (_I, [_TP, _TP, _I, _I, _P]),
     "lfsr_sa_modulate": (_I, [_TP, _P, _P, _P, _TP, C.c_float, C.c_float, _TP, _TP, _I, _P]),
+    "lfsr_scale_add": (_I, [_TP, _TP, _TP, _TP, _P]),
     "lfsr_layernorm": (_I, [_TP, _P, _P, C.c_float, _TP, _P]),
     "lfsr_epi_attention": (_I, [_P, _P, _P, C.POINTER(EpiAttnDesc), _P]),
     "lfsr_metric_sums": (_I, [_P, _P, _I, _I, _I, _P, _P]),

@@ -55,6 +55,8 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     case LFSR_ACT_RELU: return v > 0.f ? v : 0.f;
     case LFSR_ACT_LRELU: return v > 0.f ? v : v * slope;
     case LFSR_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    case LFSR_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    case LFSR_ACT_SILU: return v / (1.f + __expf(-v));
     default: return v;
   }
 }

@@ -20,7 +20,7 @@ struct ConvArgs {
   int in_perm, out_perm, A;
   int ry, rx, shuf_mode;
   int bh, bw;  // view blocking (0 = off)
-  int act;
+  int act, mul_act;
   float slope, alpha;
   int OH, OW, cin, cout, K;
   int tiles_x, tiles_y;
@@ -189,7 +189,7 @@ conv_igemm_f32(const ConvArgs a) {
       float v = acc[i][j];
       if (a.bias) v += __ldg(a.bias + co);
       v = apply_act(v, a.act, a.slope);
-      if (a.mul.p) v *= __ldg(a.mul.p + mul_base + co);
+      if (a.mul.p) v *= apply_act(__ldg(a.mul.p + mul_base + co), a.mul_act, 0.f);
       v *= a.alpha;
       int sy = py, sx = px, sc = co;
       if (r2 > 1) {
@@ -286,7 +286,7 @@ extern "C" int lfsr_conv2d_f32(const lfsr_tensor* in, const float* w_packed, con
   a.in_perm = d->in_perm; a.out_perm = d->out_perm; a.A = d->perm_a > 0 ? d->perm_a : 1;
   a.ry = ry; a.rx = rx; a.shuf_mode = d->shuf_mode;
   a.bh = d->block_h; a.bw = d->block_w;
-  a.act = d->act; a.slope = d->act_slope; a.alpha = d->alpha;
+  a.act = d->act; a.slope = d->act_slope; a.alpha = d->alpha; a.mul_act = d->mul_act;
   a.OH = OH; a.OW = OW; a.cin = in->c; a.cout = cout; a.K = d->kh * d->kw * in->c;
   const bool vec = (in->c % 4 == 0) && (in->ld % 4 == 0) && ((uintptr_t)in->ptr % 16 == 0);
   cudaStream_t st = (cudaStream_t)stream;

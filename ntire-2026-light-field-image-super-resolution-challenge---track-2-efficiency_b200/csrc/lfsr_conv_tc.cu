@@ -41,9 +41,9 @@ struct Params {
   int stages, b_stage_bytes;
   int kps;                             // K-stages (tap x 32-channel group) per smem stage / barrier round trip
   int resident, m_tiles;               // resident: all K-stages of W stay in smem for the CTA's lifetime
-  TView out, res;
+  TView out, res, mul;                 // mul: optional elementwise multiplier (conv-output geometry, no shuffle)
   const float* bias;
-  int act;
+  int act, mul_act;
   float slope, alpha;
   int ry, rx, shuf_mode, cq, vec;      // vec: floats per lane in the coalesced write-out (4, 2 or 1)
   // halo-block mode (conv_tc_halo_kernel): the input block with halo is staged ONCE per 32-channel group as
@@ -275,6 +275,8 @@ __device__ __forceinline__ float act_t(float v, float slope) {
   if (ACT == LFSR_ACT_RELU) return fmaxf(v, 0.f);
   if (ACT == LFSR_ACT_LRELU) return v > 0.f ? v : v * slope;
   if (ACT == LFSR_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  if (ACT == LFSR_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  if (ACT == LFSR_ACT_SILU) return v / (1.f + __expf(-v));
   return v;
 }
 
@@ -298,12 +300,15 @@ __device__ __forceinline__ void epi_writeout(const Params& p, const float* stg, 
   const int ox0 = (tc_.vx * p.bw + tc_.x0) * p.rx + sj;
   float* const obase = p.out.p + p.out.pix(img, oy0, ox0) + c;
   const float* const rbase = p.res.p ? p.res.p + p.res.pix(img, oy0, ox0) + c : nullptr;
+  const float* const mbase = p.mul.p ? p.mul.p + p.mul.pix(img, oy0, ox0) + c : nullptr;
+  const int m_py = p.mul.w * p.mul.ld, m_px = p.mul.ld;
   const int o_py = p.ry * p.out.w * p.out.ld, o_px = p.rx * p.out.ld;         // float pitch per tile row / column
   const int r_py = p.ry * p.res.w * p.res.ld, r_px = p.rx * p.res.ld;
   const bool full = !p.halo && tc_.y0 + p.TH <= p.bh && tc_.x0 + p.TW <= p.bw;
   const int tw_mask = p.TW - 1;
   const int rows_valid = min(p.halo ? p.Rout : p.TH, p.bh - tc_.y0), cols_valid = min(p.halo ? p.TWo : p.TW, p.bw - tc_.x0);
   const float slope = p.slope, alpha = p.alpha;
+  const int mul_act = p.mul_act;
   const int swz_hi = col >> 2, swz_lo = col & 3;
 #pragma unroll 4
   for (int it = 0; it < LPR; ++it) {
@@ -324,7 +329,18 @@ __device__ __forceinline__ void epi_writeout(const Params& p, const float* stg, 
     else if (V == 2) { const float2 t = *reinterpret_cast<const float2*>(src); v[0] = t.x; v[1 % V] = t.y; }
     else v[0] = *src;
 #pragma unroll
-    for (int e = 0; e < V; ++e) v[e] = act_t<ACT>(v[e] + bv[e], slope) * alpha;
+    for (int e = 0; e < V; ++e) v[e] = act_t<ACT>(v[e] + bv[e], slope);
+    if (mbase) {
+      const float* ms = mbase + ty * m_py + tx * m_px;
+      float mv[V];
+      if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(ms); mv[0] = t.x; mv[1 % V] = t.y; mv[2 % V] = t.z; mv[3 % V] = t.w; }
+      else if (V == 2) { const float2 t = *reinterpret_cast<const float2*>(ms); mv[0] = t.x; mv[1 % V] = t.y; }
+      else mv[0] = *ms;
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] *= mul_act ? apply_act(mv[e], mul_act, 0.f) : mv[e];
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] *= alpha;
     if (rbase) {
       const float* rs = rbase + ty * r_py + tx * r_px;
       if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(rs); v[0] += t.x; v[1 % V] += t.y; v[2 % V] += t.z; v[3 % V] += t.w; }
@@ -345,6 +361,8 @@ __device__ __forceinline__ void epi_writeout_act(const Params& p, const float* s
     case LFSR_ACT_RELU: epi_writeout<V, LFSR_ACT_RELU>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
     case LFSR_ACT_LRELU: epi_writeout<V, LFSR_ACT_LRELU>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
     case LFSR_ACT_SIGMOID: epi_writeout<V, LFSR_ACT_SIGMOID>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
+    case LFSR_ACT_GELU: epi_writeout<V, LFSR_ACT_GELU>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
+    case LFSR_ACT_SILU: epi_writeout<V, LFSR_ACT_SILU>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
     default: epi_writeout<V, LFSR_ACT_NONE>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
   }
 }
@@ -818,7 +836,8 @@ extern "C" int lfsr_scale_pack_tc(const float* packed, const float* gate, int64_
 
 static bool tc_geometry_ok(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d) {
   if (!tensor_ok(in) || !tensor_ok(out) || !d) return false;
-  if (d->in_perm || d->out_perm || d->mul.ptr) return false;
+  if (d->in_perm || d->out_perm) return false;
+  if (d->mul.ptr && ((d->shuf_ry > 1) || (d->shuf_rx > 1))) return false;      // mul is only fused for unshuffled outputs
   if (d->in_scale && d->w_batch_stride <= 0) return false;      // gates must come folded into per-image weights
   if (d->kh * d->kw > 25 || d->kh < 1 || d->kw < 1) return false;
   if (in->c < 8 || in->ld % 4 != 0 || ((uintptr_t)in->ptr & 15)) return false;
@@ -880,17 +899,22 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   p.NC = pl.NC; p.nchunks = pl.nchunks; p.cgs = pl.cgs;
   p.out = view_of(out);
   p.res = d->res.ptr ? view_of(&d->res) : null_view();
+  p.mul = d->mul.ptr ? view_of(&d->mul) : null_view();
   if (d->res.ptr)
     LFSR_REQUIRE(d->res.n == out->n && d->res.h == out->h && d->res.w == out->w && d->res.c == out->c,
                  "lfsr_conv2d_tc: res tensor geometry");
+  if (d->mul.ptr)
+    LFSR_REQUIRE(d->mul.n == out->n && d->mul.h == out->h && d->mul.w == out->w && d->mul.c == out->c,
+                 "lfsr_conv2d_tc: mul tensor geometry");
   LFSR_REQUIRE((long long)out->h * out->w * out->ld < 0x7fffffffLL, "lfsr_conv2d_tc: output image too large for 32-bit pitches");
-  p.bias = d->bias; p.act = d->act; p.slope = d->act_slope; p.alpha = d->alpha;
+  p.bias = d->bias; p.act = d->act; p.slope = d->act_slope; p.alpha = d->alpha; p.mul_act = d->mul_act;
   p.ry = ry; p.rx = rx; p.shuf_mode = d->shuf_mode; p.cq = out->c;
   p.vec = 1;
   for (int v = 2; v <= 4; v *= 2) {
     const uintptr_t mask = (uintptr_t)v * 4 - 1;
     if ((p.cq % v == 0) && (out->ld % v == 0) && (((uintptr_t)out->ptr & mask) == 0) &&
-        (!d->res.ptr || ((d->res.ld % v == 0) && (((uintptr_t)d->res.ptr & mask) == 0))))
+        (!d->res.ptr || ((d->res.ld % v == 0) && (((uintptr_t)d->res.ptr & mask) == 0))) &&
+        (!d->mul.ptr || ((d->mul.ld % v == 0) && (((uintptr_t)d->mul.ptr & mask) == 0))))
       p.vec = v;
     else
       break;

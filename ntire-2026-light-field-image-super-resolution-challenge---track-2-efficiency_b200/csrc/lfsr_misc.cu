@@ -150,6 +150,35 @@ sa_modulate_kernel(TView x, const float* __restrict__ dww, const float* __restri
   }
 }
 
+// ---- out = x * scale[n][c] + res : ChannelAttention scaling fused with the block residual
+template <int V>
+__global__ void __launch_bounds__(256)
+scale_add_kernel(TView x, const float* __restrict__ scale, int scale_ld, TView res, TView out) {
+  const int CV = x.c / V;
+  const int img = blockIdx.y;
+  const int per = x.h * x.w * CV;
+  const float* sc = scale + (size_t)img * scale_ld;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per; t += gridDim.x * blockDim.x) {
+    const int c = (t % CV) * V;
+    const int r = t / CV;
+    const int px = r % x.w, py = r / x.w;
+    const float* src = x.p + x.pix(img, py, px) + c;
+    float v[V];
+    if (V == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(src)); v[0] = q.x; v[1 % V] = q.y; v[2 % V] = q.z; v[3 % V] = q.w; }
+    else v[0] = __ldg(src);
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] *= __ldg(sc + c + e);
+    if (res.p) {
+      const float* rs = res.p + res.pix(img, py, px) + c;
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] += rs[e];
+    }
+    float* dst = out.p + out.pix(img, py, px) + c;
+    if (V == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1 % V], v[2 % V], v[3 % V]);
+    else dst[0] = v[0];
+  }
+}
+
 // ---- LayerNorm over channels: one warp per token (EPIT.py:77,84)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(TView in, TView out, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -383,6 +412,26 @@ extern "C" int lfsr_sa_modulate(const lfsr_tensor* x, const float* dw_w, const f
   else if (V == 2) sa_modulate_kernel<2><<<blocks, 256, 0, st>>>(view_of(x), dw_w, bn_scale, bn_shift, view_of(amod), w0, w1, r, view_of(out), dil);
   else sa_modulate_kernel<1><<<blocks, 256, 0, st>>>(view_of(x), dw_w, bn_scale, bn_shift, view_of(amod), w0, w1, r, view_of(out), dil);
   return check_launch("sa_modulate_kernel");
+}
+
+extern "C" int lfsr_scale_add(const lfsr_tensor* x, const lfsr_tensor* scale, const lfsr_tensor* res, const lfsr_tensor* out,
+                              void* stream) {
+  LFSR_REQUIRE(tensor_ok(x) && tensor_ok(scale) && tensor_ok(out), "lfsr_scale_add: null/invalid tensor");
+  LFSR_REQUIRE(out->n == x->n && out->h == x->h && out->w == x->w && out->c == x->c, "lfsr_scale_add: out shape");
+  LFSR_REQUIRE(scale->n == x->n && scale->h == 1 && scale->w == 1 && scale->c == x->c, "lfsr_scale_add: scale must be [n,1,1,c]");
+  LFSR_REQUIRE(x->n <= 65535, "lfsr_scale_add: batch too large");
+  TView r = null_view();
+  if (res && res->ptr) {
+    LFSR_REQUIRE(res->n == x->n && res->h == x->h && res->w == x->w && res->c == x->c, "lfsr_scale_add: res shape");
+    r = view_of(res);
+  }
+  auto al = [](const lfsr_tensor* t) { return t->ld % 4 == 0 && (((uintptr_t)t->ptr) & 15) == 0; };
+  const bool v4 = x->c % 4 == 0 && al(x) && al(out) && (!r.p || al(res));
+  const int per = x->h * x->w * (x->c / (v4 ? 4 : 1));
+  dim3 blocks(ceil_div(per, 256), x->n);
+  if (v4) scale_add_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(view_of(x), (const float*)scale->ptr, scale->ld, r, view_of(out));
+  else scale_add_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(view_of(x), (const float*)scale->ptr, scale->ld, r, view_of(out));
+  return check_launch("scale_add_kernel");
 }
 
 extern "C" int lfsr_layernorm(const lfsr_tensor* in, const float* gamma, const float* beta, float eps,

@@ -130,7 +130,8 @@ class CudaOps:
                                      self._stream(x)), "lfsr_interp")
 
     # -- convolutions ---------------------------------------------------------------------------
-    def conv(self, x, pc: PackedConv, out, act=N.ACT_NONE, slope=0.0, alpha=1.0, mul=None, res=None, in_scale=None,
+    def conv(self, x, pc: PackedConv, out, act=N.ACT_NONE, slope=0.0, alpha=1.0, mul=None, mul_act=N.ACT_NONE, res=None,
+             in_scale=None,
              in_perm=0, out_perm=0, perm_a=0, shuffle=(1, 1, 0), block=(0, 0)):
         d = N.ConvDesc()
         d.kh, d.kw = pc.kh, pc.kw
@@ -140,7 +141,7 @@ class CudaOps:
         d.in_perm, d.out_perm, d.perm_a = in_perm, out_perm, perm_a
         d.shuf_ry, d.shuf_rx, d.shuf_mode = shuffle
         d.block_h, d.block_w = block
-        d.act, d.act_slope, d.alpha = act, slope, alpha
+        d.act, d.act_slope, d.alpha, d.mul_act = act, slope, alpha, mul_act
         d.bias = self._ptr(pc.bias)
         d.in_scale = self._ptr(in_scale)
         if in_scale is not None:      # [n,1,1,cin] NHWC view (possibly padded rows) or dense [n,cin]
@@ -201,6 +202,12 @@ class CudaOps:
         N.check(self.lib.lfsr_sa_modulate(C.byref(as_tensor(x, "sa.x")), dw_w.data_ptr(), bn_scale.data_ptr(),
                                           bn_shift.data_ptr(), C.byref(as_tensor(amod, "sa.amod")), w0, w1, C.byref(rt),
                                           C.byref(as_tensor(out, "sa.out")), dil, self._stream(x)), "lfsr_sa_modulate")
+
+    def scale_add(self, x, scale, res, out):
+        rt = as_tensor(res, "scale_add.res") if res is not None else _NULL_T
+        N.check(self.lib.lfsr_scale_add(C.byref(as_tensor(x, "scale_add.x")), C.byref(as_tensor(scale, "scale_add.scale")),
+                                        C.byref(rt), C.byref(as_tensor(out, "scale_add.out")), self._stream(x)),
+                "lfsr_scale_add")
 
     # -- EPIT token ops ------------------------------------------------------------------------------
     def layernorm(self, x, gamma, beta, eps, out):

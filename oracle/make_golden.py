@@ -26,7 +26,7 @@ sys.path.insert(0, REPO)
 from oracle import ref_shim  # noqa: E402
 
 MODELS = [("MyEfficientLFNet", 4), ("MyEfficientLFNet", 2), ("EPIT", 4), ("DistgSSR", 4), ("DistgSSR", 2),
-          ("LF_InterNet", 4)]
+          ("LF_InterNet", 4), ("MyEfficientLFNetV4_5", 4)]
 
 
 def main():

@@ -98,6 +98,61 @@ def my_efficient_lfnet(x, sd, ang=5, scale=4):
 
 
 # ---------------------------------------------------------------------------------------------
+# MyEfficientLFNetV4_5 with its in-repo FastConvSSM branch (mamba_ssm absent) — MyEfficientLFNetV4_5.py
+# ---------------------------------------------------------------------------------------------
+def _v45_block(x, sd, p):
+    """MambaLFBlock.forward (MyEfficientLFNetV4_5.py:143-148)."""
+    C = x.shape[1]
+    c = C // 4
+    # MultiScaleSpatial (:262-282)
+    q = p + ".ms_spatial"
+    y = torch.cat([F.conv2d(x[:, :c], sd[q + ".conv1.weight"]),
+                   F.conv2d(x[:, c:2 * c], sd[q + ".conv3.weight"], None, 1, 1, 1, c),
+                   F.conv2d(x[:, 2 * c:3 * c], sd[q + ".conv5.weight"], None, 1, 2, 1, c),
+                   F.conv2d(x[:, 3 * c:], sd[q + ".conv7.weight"], None, 1, 3, 1, c)], 1)
+    f_local = _lrelu(_bn(F.conv2d(y, sd[q + ".pw.weight"]), sd, q + ".bn"), 0.1) + x
+    # FastConvSSM (:208-244)
+    q = p + ".ssm"
+    yn = _bn(x, sd, q + ".norm")
+    g = F.gelu(F.conv2d(yn, sd[q + ".gate_conv.weight"]))
+    gate, yv = g.chunk(2, dim=1)
+    fs = [F.conv2d(yv, sd[q + f".conv{d}.weight"], None, 1, d, d, C) for d in (1, 2, 4, 8)]
+    yv = F.conv2d(torch.cat(fs, 1), sd[q + ".fuse.weight"]) * F.silu(gate)
+    f_global = x + sd[q + ".scale"] * F.conv2d(yv, sd[q + ".proj.weight"])
+    fused = F.conv2d(torch.cat([f_local, f_global], 1), sd[p + ".fuse.weight"])
+    # ChannelAttention (:285-299)
+    a = F.adaptive_avg_pool2d(fused, 1)
+    a = torch.sigmoid(F.conv2d(F.relu(F.conv2d(a, sd[p + ".ca.fc1.weight"], sd[p + ".ca.fc1.bias"])),
+                               sd[p + ".ca.fc2.weight"], sd[p + ".ca.fc2.bias"]))
+    return fused * a + x
+
+
+def my_efficient_lfnet_v4_5(x, sd, ang=5, scale=4):
+    """get_model.forward (MyEfficientLFNetV4_5.py:65-109), use_macpi=False (its default, :39)."""
+    x_up = F.interpolate(x, scale_factor=scale, mode="bicubic", align_corners=False)
+    feat = _lrelu(F.conv2d(x, sd["shallow.0.weight"], None, 1, 1), 0.1)
+    C = feat.shape[1]
+    t = _lrelu(_bn(F.conv2d(feat, sd["shallow.2.dw.weight"], None, 1, 1, 1, C), sd, "shallow.2.bn"), 0.1)
+    feat = feat + F.conv2d(t, sd["shallow.2.pw.weight"])                         # LocalPixelEnhancement (:285-294)
+    shallow = feat
+    n_blocks = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
+    outs = []
+    for i in range(n_blocks):
+        feat = _v45_block(feat, sd, f"blocks.{i}")
+        outs.append(feat)
+    early = F.conv2d(torch.cat(outs[:4], 1), sd["fuse_early.weight"])
+    late = F.conv2d(torch.cat(outs[4:], 1), sd["fuse_late.weight"])
+    feat = F.conv2d(torch.cat([early, late], 1), sd["fuse_final.weight"]) + shallow
+    feat = _lrelu(F.conv2d(feat, sd["refine.weight"], None, 1, 1), 0.1)
+    if scale == 4:
+        feat = _lrelu(F.pixel_shuffle(F.conv2d(feat, sd["upsampler.up.0.weight"], None, 1, 1), 2), 0.1)
+        feat = _lrelu(F.pixel_shuffle(F.conv2d(feat, sd["upsampler.up.3.weight"], None, 1, 1), 2), 0.1)
+    else:
+        feat = _lrelu(F.pixel_shuffle(F.conv2d(feat, sd["upsampler.up.0.weight"], None, 1, 1), scale), 0.1)
+    return F.conv2d(feat, sd["output.weight"], sd["output.bias"], 1, 1) + x_up
+
+
+# ---------------------------------------------------------------------------------------------
 # EPIT — EPIT.py
 # ---------------------------------------------------------------------------------------------
 def _epit_mask(v, w, k_h, k_w):
@@ -262,6 +317,7 @@ def lf_internet(x, sd, ang=5, scale=4):
 
 FORWARD = {
     "MyEfficientLFNet": my_efficient_lfnet,
+    "MyEfficientLFNetV4_5": my_efficient_lfnet_v4_5,
     "EPIT": epit,
     "DistgSSR": distgssr,
     "LF_InterNet": lf_internet,

@@ -32,6 +32,13 @@ def install(argv=("--angRes", "5", "--scale_factor", "4", "--use_pre_ckpt", "", 
     sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") not in (repo,)]
     sys.path.insert(0, REF_ROOT)
     sys.path.append(repo)  # for `oracle.*` only; the reference's names win
+    # The reference's model/ and model/SR/ have no __init__.py (namespace packages), and a regular package of the
+    # same name (this repo's drop-in model/) would beat them whatever the sys.path order: pin both by hand.
+    for name, sub in (("model", "model"), ("model.SR", os.path.join("model", "SR")), ("utils", "utils")):
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(REF_ROOT, sub)]
+        sys.modules[name] = m
+    sys.modules["model"].SR = sys.modules["model.SR"]
 
     def stub(name):
         m = types.ModuleType(name)
@@ -53,6 +60,7 @@ def install(argv=("--angRes", "5", "--scale_factor", "4", "--use_pre_ckpt", "", 
 
 def ref_model(name: str, ang: int, scale: int):
     mod = importlib.import_module("model.SR." + name)
+    assert os.path.abspath(mod.__file__).startswith(os.path.abspath(REF_ROOT)), mod.__file__
 
     class A:
         angRes_in = ang

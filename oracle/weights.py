@@ -20,7 +20,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file
 
 # per-model gain on conv/linear weights, chosen so the network branch is O(0.1..1) next to the
 # interpolation skip (tune with oracle/make_golden.py --stats)
-GAIN = {"MyEfficientLFNet": 0.7, "EPIT": 0.6, "DistgSSR": 0.6, "LF_InterNet": 0.55}
+GAIN = {"MyEfficientLFNet": 0.7, "EPIT": 0.6, "DistgSSR": 0.6, "LF_InterNet": 0.55, "MyEfficientLFNetV4_5": 0.7}
 
 
 def spec_path(model: str, scale: int) -> str:

@@ -32,7 +32,7 @@ class ProfilingOps(K.CudaOps):
         self._wrap("conv", lambda: K.CudaOps.conv(self, x, pc, out, **kw), label)
 
     def dwconv(self, x, w, out, kh, kw, **k2):
-        self._wrap("dwconv", lambda: K.CudaOps.dwconv(self, x, w, out, kh, kw, **k2), f"dwconv {kh}x{kw} c{x.shape[3]} @{x.shape[1]}x{x.shape[2]}")
+        self._wrap("dwconv", lambda: K.CudaOps.dwconv(self, x, w, out, kh, kw, **k2), f"dwconv {kh}x{kw} d{k2.get('dil', (1, 1))[0]} c{x.shape[3]} @{x.shape[1]}x{x.shape[2]}")
 
     def mel_epi_branch(self, x, w, out, klen, dil, slope):
         self._wrap("mel_epi_branch", lambda: K.CudaOps.mel_epi_branch(self, x, w, out, klen, dil, slope), f"mel_epi_branch c{x.shape[3]} @{x.shape[1]}x{x.shape[2]}")
@@ -42,6 +42,9 @@ class ProfilingOps(K.CudaOps):
 
     def sa_modulate(self, *a):
         self._wrap("sa_modulate", lambda: K.CudaOps.sa_modulate(self, *a), "sa_modulate")
+
+    def scale_add(self, *a):
+        self._wrap("scale_add", lambda: K.CudaOps.scale_add(self, *a), f"scale_add c{a[0].shape[3]} @{a[0].shape[1]}")
 
     def interp(self, *a):
         self._wrap("interp", lambda: K.CudaOps.interp(self, *a), "interp")

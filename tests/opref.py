@@ -23,6 +23,10 @@ def _act(y, act, slope):
         return F.leaky_relu(y, slope)
     if act == 3:
         return torch.sigmoid(y)
+    if act == 4:
+        return F.gelu(y)
+    if act == 5:
+        return F.silu(y)
     return y
 
 
@@ -58,7 +62,7 @@ class RefOps:
         out.view(n, 1, h * scale, w * scale).copy_(y)
 
     # -- convolutions ------------------------------------------------------------------------------
-    def conv(self, x, pc, out, act=0, slope=0.0, alpha=1.0, mul=None, res=None, in_scale=None, in_perm=0, out_perm=0,
+    def conv(self, x, pc, out, act=0, slope=0.0, alpha=1.0, mul=None, mul_act=0, res=None, in_scale=None, in_perm=0, out_perm=0,
              perm_a=0, shuffle=(1, 1, 0), block=(0, 0)):
         n = x.shape[0]
         xi = _nchw(x)
@@ -78,7 +82,7 @@ class RefOps:
             y = F.conv2d(xi, w, pc.bias, pc.stride, pc.pad, pc.dil)
         y = _act(y, act, slope)
         if mul is not None:
-            y = y * _nchw(mul)
+            y = y * _act(_nchw(mul), mul_act, 0.0)
         y = y * alpha
         if out_perm:
             y = rearrange(y, "b c (h u) (w v) -> b c (u h) (v w)", u=perm_a, v=perm_a)
@@ -137,6 +141,12 @@ class RefOps:
         if res is not None:
             y = y + _nchw(res)
         out.copy_(y.permute(0, 2, 3, 1))
+
+    def scale_add(self, x, scale, res, out):
+        y = x * scale
+        if res is not None:
+            y = y + res
+        out.copy_(y)
 
     # -- EPIT token ops ---------------------------------------------------------------------------------
     def layernorm(self, x, gamma, beta, eps, out):

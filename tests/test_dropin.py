@@ -47,7 +47,8 @@ import importlib, option
 a = option.args
 assert a.use_pre_ckpt is False and a.angRes_in == 5 and a.angRes_out == 5 and not hasattr(a, 'angRes')
 assert (a.patch_size_for_test, a.stride_for_test, a.minibatch_for_test) == (32, 16, 1)
-for name, n in (('MyEfficientLFNet', 547540), ('EPIT', 1470080), ('DistgSSR', 3581568), ('LF_InterNet', 5482688)):
+for name, n in (('MyEfficientLFNet', 547540), ('EPIT', 1470080), ('DistgSSR', 3581568), ('LF_InterNet', 5482688),
+                ('MyEfficientLFNetV4_5', 756553)):
     m = importlib.import_module('model.SR.' + name)
     net = m.get_model(a); net.apply(m.weights_init); m.get_loss(a)
     assert sum(p.numel() for p in net.parameters()) == n, name

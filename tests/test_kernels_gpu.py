@@ -119,6 +119,9 @@ CONV_CASES = [
     dict(cin=64, cout=64, k=(3, 3), pad=(1, 1), act=2, block=(8, 8)),
     dict(cin=144, cout=64, k=(1, 1), act=2),
     dict(cin=128, cout=64, k=(3, 3), dil=(5, 5), pad=(5, 5), act=1, res=True),
+    dict(cin=64, cout=128, k=(1, 1), act=4, bias=True),                 # FastConvSSM gate conv + GELU
+    dict(cin=256, cout=64, k=(1, 1), mul=True, mul_act=5),              # ... fuse conv * silu(gate)
+    dict(cin=64, cout=16, k=(1, 1), act=5),
 ]
 
 
@@ -141,6 +144,7 @@ def test_conv_f32(ops, ref, case):
                    block=case.get("block", (0, 0)))
     if case.get("mul"):
         kw_args["mul"] = nhwc(n, oh, ow, cout, seed=4)
+        kw_args["mul_act"] = case.get("mul_act", 0)
     if case.get("res"):
         kw_args["res"] = nhwc(n, oh * ry, ow * rx, co, seed=5)
     if case.get("in_scale"):
@@ -169,9 +173,10 @@ def test_conv_residual_in_place(ops, ref):
     assert (y - y2).abs().max().item() <= 2e-5
 
 
-@pytest.mark.parametrize("kh,kw,dil", [(1, 11, (1, 1)), (11, 1, (1, 1)), (3, 3, (5, 5)), (3, 3, (1, 1))])
-def test_dwconv(ops, ref, kh, kw, dil):
-    n, h, w, c = 2, 40, 40, 18
+@pytest.mark.parametrize("kh,kw,dil,c", [(1, 11, (1, 1), 18), (11, 1, (1, 1), 18), (3, 3, (5, 5), 18), (3, 3, (1, 1), 18),
+                                         (7, 7, (1, 1), 64), (3, 3, (8, 8), 64), (3, 3, (4, 4), 64)])
+def test_dwconv(ops, ref, kh, kw, dil, c):
+    n, h, w = 2, 40, 40
     x = nhwc(n, h, w, c, seed=1)
     wt = rnd(kh * kw, c, seed=2)
     sc, sh = rnd(c, seed=3, lo=0.5, hi=1.5), rnd(c, seed=4)
@@ -200,6 +205,21 @@ def test_sa_modulate(ops, ref):
     ops.sa_modulate(x, dw, bs, bb, am, 0.4, 0.6, res, a, A)
     ref.sa_modulate(x, dw, bs, bb, am, 0.4, 0.6, res, b, A)
     assert (a - b).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("c,sliced,with_res", [(64, False, True), (64, True, True), (54, False, False), (18, True, True)])
+def test_scale_add(ops, ref, c, sliced, with_res):
+    """out = x * scale[n, c] + res (ChannelAttention + block residual, MyEfficientLFNetV4_5.py:147-148, :297-299)"""
+    n, h, w = 3, 40, 40
+    x = nhwc(n, h, w, c, seed=1)
+    sc = nhwc(n, 1, 1, c, seed=2)
+    res = nhwc(n, h, w, 4 * c, seed=3)[..., c:2 * c] if sliced else nhwc(n, h, w, c, seed=3)
+    res = res if with_res else None
+    fa, fb = nhwc(n, h, w, 4 * c, seed=4), nhwc(n, h, w, 4 * c, seed=4)
+    a, b = (fa[..., 2 * c:3 * c], fb[..., 2 * c:3 * c]) if sliced else (fa[..., :c], fb[..., :c])
+    ops.scale_add(x, sc, res, a)
+    ref.scale_add(x, sc, res, b)
+    assert torch.equal(fa, fb) or (fa - fb).abs().max().item() <= 1e-6
 
 
 def test_layernorm(ops, ref):
@@ -281,6 +301,10 @@ TC_CASES = [
     dict(cin=64, cout=1, k=(3, 3), pad=(1, 1), res=True, hw=(40, 40)),
     dict(cin=64, cout=1024, k=(1, 1), act=2, shuffle=(4, 4, 0), hw=(160, 160)),
     dict(cin=128, cout=384, k=(1, 1), hw=(1, 25600)),
+    dict(cin=64, cout=128, k=(1, 1), act=4, bias=True, hw=(160, 160)),               # V4_5 gate conv + GELU
+    dict(cin=256, cout=64, k=(1, 1), mul=True, mul_act=5, hw=(160, 160)),            # V4_5 fuse * silu(gate)
+    dict(cin=64, cout=64, k=(1, 1), mul=True, alpha=0.1, res=True, hw=(40, 40)),
+    dict(cin=128, cout=64, k=(1, 1), act=5, hw=(40, 40)),
 ]
 
 
@@ -323,6 +347,9 @@ def _run_tc_case(ref, case):
     oh, ow = h // stride[0], w // stride[1]
     if case.get("res"):
         kw_args["res"] = nhwc(n, oh * ry, ow * rx, co, seed=5)
+    if case.get("mul"):      # a channel window of a wider buffer, like the gate half of FastConvSSM's [gate | y]
+        kw_args["mul"] = nhwc(n, oh, ow, 2 * cout, seed=4)[..., :cout]
+        kw_args["mul_act"] = case.get("mul_act", 0)
     a = nhwc(n, oh * ry, ow * rx, co, seed=7)
     b = a.clone()
     lib = tc_ops.lib

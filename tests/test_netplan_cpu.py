@@ -10,7 +10,7 @@ from opref import RefOps
 from oracle import nets as onets, weights
 
 CASES = [("MyEfficientLFNet", 4), ("MyEfficientLFNet", 2), ("EPIT", 4), ("DistgSSR", 4), ("DistgSSR", 2),
-         ("LF_InterNet", 4)]
+         ("LF_InterNet", 4), ("MyEfficientLFNetV4_5", 4)]
 
 
 def _have(name):

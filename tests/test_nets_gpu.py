@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TOL = 1e-3          # north_star: max abs error <= 1e-3 on [0,1] outputs
 CASES = [("MyEfficientLFNet", 4), ("MyEfficientLFNet", 2), ("EPIT", 4), ("DistgSSR", 4), ("DistgSSR", 2),
-         ("LF_InterNet", 4)]
+         ("LF_InterNet", 4), ("MyEfficientLFNetV4_5", 4)]
 REPORT = {}
 
 
