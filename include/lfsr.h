@@ -121,6 +121,21 @@ int lfsr_conv2d_f32(const lfsr_tensor* in, const float* w_packed, const lfsr_ten
 int lfsr_dwconv_f32(const lfsr_tensor* in, const float* w_packed, const float* scale,
                     const float* shift, const lfsr_tensor* out, int kh, int kw, int dil_h, int dil_w,
                     int act, float act_slope, void* stream);
+/* several depthwise branches of one input in one launch: branch b convolves the channel window
+ * in[..., in_c0 : in_c0+c] with its own taps / dilation and writes out[..., out_c0 : out_c0+c]
+ * ("same" zero padding, stride 1). Replaces MultiScaleSpatial's conv3/conv5/conv7 on 16-channel slices
+ * (MyEfficientLFNetV4_5.py:268-280) and FastConvSSM's conv1/2/4/8 + torch.cat (:218-221, :235-240). */
+typedef struct {
+  const float* w;      /* [kh*kw][c] */
+  const float* scale;  /* [c] folded BatchNorm, or NULL (then shift is NULL too) */
+  const float* shift;
+  int32_t kh, kw, dil_h, dil_w;
+  int32_t in_c0, out_c0, c;
+  int32_t act;
+  float act_slope;
+} lfsr_dw_branch;
+int lfsr_dwconv_multi(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_dw_branch* branches,
+                      int n_branches, void* stream);
 /* direct conv for 1..4 output channels (reconstruction heads 54->1 / 64->1: MyEfficientLFNet.py:70-73,
  * EPIT.py:48): stride 1, "same" padding; weights packed as for lfsr_conv2d_f32; bias/act/alpha/res fused. */
 int lfsr_conv2d_small_cout_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);

@@ -42,6 +42,13 @@ class ConvDesc(C.Structure):
     ]
 
 
+class DwBranch(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("kh", C.c_int32), ("kw", C.c_int32), ("dil_h", C.c_int32), ("dil_w", C.c_int32),
+                ("in_c0", C.c_int32), ("out_c0", C.c_int32), ("c", C.c_int32),
+                ("act", C.c_int32), ("act_slope", C.c_float)]
+
+
 class EpiAttnDesc(C.Structure):
     _fields_ = [
         ("heads", C.c_int32), ("head_dim", C.c_int32), ("A", C.c_int32), ("S", C.c_int32),
@@ -66,6 +73,7 @@ SIGNATURES = {
     "lfsr_interp": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "lfsr_conv2d_f32": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
     "lfsr_dwconv_f32": (_I, [_TP, _P, _P, _P, _TP, _I, _I, _I, _I, _I, C.c_float, _P]),
+    "lfsr_dwconv_multi": (_I, [_TP, _TP, C.POINTER(DwBranch), _I, _P]),
     "lfsr_conv2d_small_cout_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),
     "lfsr_conv2d_small_cout": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
     "lfsr_mel_epi_branch": (_I, [_TP, _P, _TP, _I, _I, C.c_float, _P]),

@@ -214,35 +214,6 @@ static int launch_conv(const ConvArgs& a, bool vec, cudaStream_t st) {
   return check_launch("conv_igemm_f32");
 }
 
-// ---- depthwise ------------------------------------------------------------------------
-// one thread = one pixel x 2 channels (float2 when aligned); taps are L1/L2 hits.
-__global__ void __launch_bounds__(256)
-dwconv_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ scale,
-              const float* __restrict__ shift, int kh, int kw, int dh, int dw, int act, float slope) {
-  const int C = in.c;
-  const int img = blockIdx.y;                 // 32-bit index math inside one image
-  const int per = in.h * in.w * C;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per; t += gridDim.x * blockDim.x) {
-    const int c = t % C;
-    const int r = t / C;
-    const int x = r % in.w;
-    const int y = r / in.w;
-    const int ph = (kh / 2) * dh, pw = (kw / 2) * dw;
-    float acc = 0.f;
-    for (int ky = 0; ky < kh; ++ky) {
-      const int iy = y - ph + ky * dh;
-      if (iy < 0 || iy >= in.h) continue;
-      for (int kx = 0; kx < kw; ++kx) {
-        const int ix = x - pw + kx * dw;
-        if (ix < 0 || ix >= in.w) continue;
-        acc = fmaf(__ldg(in.p + in.pix(img, iy, ix) + c), __ldg(w + (ky * kw + kx) * C + c), acc);
-      }
-    }
-    if (scale) acc = acc * __ldg(scale + c) + __ldg(shift + c);
-    out.p[out.pix(img, y, x) + c] = apply_act(acc, act, slope);
-  }
-}
-
 }  // namespace lfsr
 
 using namespace lfsr;
@@ -300,19 +271,4 @@ extern "C" int lfsr_conv2d_f32(const lfsr_tensor* in, const float* w_packed, con
     a.tiles_x = ceil_div(OW, 16); a.tiles_y = ceil_div(OH, 16);
     return launch_conv<16, 16, 16, 4, 4>(a, vec, st);
   }
-}
-
-extern "C" int lfsr_dwconv_f32(const lfsr_tensor* in, const float* w_packed, const float* scale, const float* shift,
-                               const lfsr_tensor* out, int kh, int kw, int dil_h, int dil_w, int act, float act_slope,
-                               void* stream) {
-  LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && w_packed, "lfsr_dwconv_f32: null/invalid tensor");
-  LFSR_REQUIRE(in->n == out->n && in->h == out->h && in->w == out->w && in->c == out->c,
-               "lfsr_dwconv_f32: in/out shape mismatch");
-  LFSR_REQUIRE(kh > 0 && kw > 0 && (kh & 1) && (kw & 1) && dil_h > 0 && dil_w > 0, "lfsr_dwconv_f32: odd kernels only");
-  LFSR_REQUIRE((scale == nullptr) == (shift == nullptr), "lfsr_dwconv_f32: scale/shift must come together");
-  LFSR_REQUIRE(in->n <= 65535 && (long long)in->h * in->w * in->c < 0x7fffffffLL, "lfsr_dwconv_f32: tensor too large");
-  dim3 blocks(ceil_div(in->h * in->w * in->c, 256), in->n);
-  dwconv_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(view_of(in), view_of(out), w_packed, scale, shift, kh, kw, dil_h,
-                                                          dil_w, act, act_slope);
-  return check_launch("dwconv_kernel");
 }

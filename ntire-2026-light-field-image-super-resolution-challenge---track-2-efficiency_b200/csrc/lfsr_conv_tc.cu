@@ -33,7 +33,21 @@ constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;        // TMEM columns per accumulator stage
 constexpr int kSmemBudget = 225 * 1024;      // stages + epilogue staging (barriers and alignment slack come on top)
 
+// n / d for 0 <= n < 2^31 and a divisor fixed at launch: q = (umulhi(n, mul) + n) >> shift  (round-up method);
+// the per-tile coordinate decode of every role would otherwise spend ~100 dependent instructions per division
+struct FastDiv { uint32_t mul, shift; };
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  int s = 0;
+  while ((1ll << s) < d) ++s;
+  f.shift = (uint32_t)s;
+  f.mul = (uint32_t)((((unsigned long long)1 << 32) * (((unsigned long long)1 << s) - (unsigned long long)d)) / (unsigned long long)d + 1);
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, FastDiv f) { return (int)((__umulhi((uint32_t)n, f.mul) + (uint32_t)n) >> f.shift); }
+
 struct Params {
+  FastDiv fd_tiles_x, fd_nbx, fd_tiles_y, fd_nby, fd_nchunks, fd_cq;
   int nb_total, nby, nbx, bh, bw;      // blocks: nb_total = images * nby
   int C, cgs, kh, kw, dil_h, dil_w, pad_h, pad_w;
   int cout, NC, nchunks;
@@ -237,8 +251,9 @@ struct TileCoord {
 // keeps one cout-chunk's weights in smem, so its chunk is fixed and only the m-tile advances.
 __device__ __forceinline__ bool next_tile(const Params& p, int i, int& m, int& chunk) {
   if (p.resident) {
-    chunk = blockIdx.x % p.nchunks;
-    m = blockIdx.x / p.nchunks + i * (gridDim.x / p.nchunks);
+    const int b = fdiv((int)blockIdx.x, p.fd_nchunks);
+    chunk = (int)blockIdx.x - b * p.nchunks;
+    m = b + i * fdiv((int)gridDim.x, p.fd_nchunks);
     return m < p.m_tiles;
   }
   int t = blockIdx.x + i * gridDim.x;
@@ -247,22 +262,25 @@ __device__ __forceinline__ bool next_tile(const Params& p, int i, int& m, int& c
     // and clamp the partner to the last tile (its stores are suppressed through m < 0)
     const int t0 = (int)(blockIdx.x & ~1u) + i * gridDim.x;
     if (t0 >= p.total_tiles) return false;
-    if (t >= p.total_tiles) { chunk = (p.total_tiles - 1) % p.nchunks; m = -1; return true; }
+    if (t >= p.total_tiles) { chunk = (p.total_tiles - 1) - fdiv(p.total_tiles - 1, p.fd_nchunks) * p.nchunks; m = -1; return true; }
   } else if (t >= p.total_tiles) {
     return false;
   }
-  chunk = t % p.nchunks;
-  m = t / p.nchunks;
+  m = fdiv(t, p.fd_nchunks);
+  chunk = t - m * p.nchunks;
   return true;
 }
 __device__ __forceinline__ TileCoord decode_tile(const Params& p, int t, int chunk) {
   TileCoord c;
   if (t < 0) t = p.m_tiles - 1;      // dummy tile of a CTA pair: valid coordinates, nothing is stored
   c.chunk = chunk;
-  c.x0 = (t % p.tiles_x) * p.TW; t /= p.tiles_x;
-  c.vx = t % p.nbx; t /= p.nbx;
-  c.y0 = (t % p.tiles_y) * p.TH;
-  c.nb = t / p.tiles_y;
+  int u = fdiv(t, p.fd_tiles_x);
+  c.x0 = (t - u * p.tiles_x) * p.TW; t = u;
+  u = fdiv(t, p.fd_nbx);
+  c.vx = t - u * p.nbx; t = u;
+  u = fdiv(t, p.fd_tiles_y);
+  c.y0 = (t - u * p.tiles_y) * p.TH;
+  c.nb = u;
   return c;
 }
 
@@ -274,33 +292,37 @@ template <int ACT>
 __device__ __forceinline__ float act_t(float v, float slope) {
   if (ACT == LFSR_ACT_RELU) return fmaxf(v, 0.f);
   if (ACT == LFSR_ACT_LRELU) return v > 0.f ? v : v * slope;
-  if (ACT == LFSR_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  if (ACT == LFSR_ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-v));
   if (ACT == LFSR_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
-  if (ACT == LFSR_ACT_SILU) return v / (1.f + __expf(-v));
+  if (ACT == LFSR_ACT_SILU) return __fdividef(v, 1.f + __expf(-v));
   return v;
 }
 
-template <int V, int ACT>
+template <int V, bool HAS_MUL, bool HAS_RES>
 __device__ __forceinline__ void epi_writeout(const Params& p, const float* stg, int lane, int q, const TileCoord& tc_, int pc0,
                                              int ncols, int tile_j) {
   constexpr int LPR = 32 / V;   // lanes per pixel row
+  // rows handled together. The loop is written in phases (coordinates, global loads, shared loads, math, stores), each
+  // over all NB rows, so that NB independent memory operations are in flight: with two epilogue warps per scheduler
+  // the write-out is latency-bound, not issue-bound.
+  constexpr int NB = (V == 4 && !(HAS_MUL && HAS_RES)) ? 8 : 4;
   const int r2 = p.ry * p.rx;
   const int col = (lane % LPR) * V;
   const int pc = pc0 + col;
   if (col >= ncols || pc >= p.cout) return;
   int sub = 0, c = pc;
-  if (r2 > 1) { sub = pc / p.cq; c = pc - sub * p.cq; }
+  if (r2 > 1) { sub = fdiv(pc, p.fd_cq); c = pc - sub * p.cq; }
   const int si = r2 > 1 ? sub / p.rx : 0, sj = r2 > 1 ? sub - si * p.rx : 0;
   const bool chan_major = r2 > 1 && p.shuf_mode == LFSR_SHUF_CHANNEL_MAJOR;
   float bv[V];
 #pragma unroll
   for (int e = 0; e < V; ++e) bv[e] = p.bias ? __ldg(p.bias + (chan_major ? (c + e) * r2 + sub : pc + e)) : 0.f;
-  const int img = tc_.nb / p.nby;
+  const int img = fdiv(tc_.nb, p.fd_nby);
   const int oy0 = ((tc_.nb - img * p.nby) * p.bh + tc_.y0) * p.ry + si;      // output row of tile pixel (0,0)
   const int ox0 = (tc_.vx * p.bw + tc_.x0) * p.rx + sj;
   float* const obase = p.out.p + p.out.pix(img, oy0, ox0) + c;
-  const float* const rbase = p.res.p ? p.res.p + p.res.pix(img, oy0, ox0) + c : nullptr;
-  const float* const mbase = p.mul.p ? p.mul.p + p.mul.pix(img, oy0, ox0) + c : nullptr;
+  const float* const rbase = HAS_RES ? p.res.p + p.res.pix(img, oy0, ox0) + c : nullptr;
+  const float* const mbase = HAS_MUL ? p.mul.p + p.mul.pix(img, oy0, ox0) + c : nullptr;
   const int m_py = p.mul.w * p.mul.ld, m_px = p.mul.ld;
   const int o_py = p.ry * p.out.w * p.out.ld, o_px = p.rx * p.out.ld;         // float pitch per tile row / column
   const int r_py = p.ry * p.res.w * p.res.ld, r_px = p.rx * p.res.ld;
@@ -308,71 +330,125 @@ __device__ __forceinline__ void epi_writeout(const Params& p, const float* stg, 
   const int tw_mask = p.TW - 1;
   const int rows_valid = min(p.halo ? p.Rout : p.TH, p.bh - tc_.y0), cols_valid = min(p.halo ? p.TWo : p.TW, p.bw - tc_.x0);
   const float slope = p.slope, alpha = p.alpha;
-  const int mul_act = p.mul_act;
+  const bool mul_silu = p.mul_act == LFSR_ACT_SILU;   // the one multiplier activation the networks use (checked on the host)
   const int swz_hi = col >> 2, swz_lo = col & 3;
-#pragma unroll 4
-  for (int it = 0; it < LPR; ++it) {
-    const int r = it * V + lane / LPR;
-    const int m = q * 32 + r;
-    int ty, tx;
-    if (p.halo) {                      // flattened padded position g = ty*P + tx (tx >= TWo are halo garbage)
-      const int g = tile_j * 128 + m;
-      ty = (g * p.pdiv_mul) >> 16;
-      tx = g - ty * p.P;
-    } else {
-      ty = m >> p.tw_shift; tx = m & tw_mask;
-    }
-    if (!full && (ty >= rows_valid || tx >= cols_valid)) continue;
-    const float* src = stg + r * 32 + (((swz_hi ^ (r & 7)) << 2) | swz_lo);
-    float v[V];
-    if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(src); v[0] = t.x; v[1 % V] = t.y; v[2 % V] = t.z; v[3 % V] = t.w; }
-    else if (V == 2) { const float2 t = *reinterpret_cast<const float2*>(src); v[0] = t.x; v[1 % V] = t.y; }
-    else v[0] = *src;
+  const int lrow = lane / LPR;
+#pragma unroll 1
+  for (int it0 = 0; it0 < LPR; it0 += NB) {
+    int tyx[NB];                       // (ty << 16) | tx of the row's tile pixel, or -1 when it lies outside the image
 #pragma unroll
-    for (int e = 0; e < V; ++e) v[e] = act_t<ACT>(v[e] + bv[e], slope);
-    if (mbase) {
-      const float* ms = mbase + ty * m_py + tx * m_px;
-      float mv[V];
-      if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(ms); mv[0] = t.x; mv[1 % V] = t.y; mv[2 % V] = t.z; mv[3 % V] = t.w; }
-      else if (V == 2) { const float2 t = *reinterpret_cast<const float2*>(ms); mv[0] = t.x; mv[1 % V] = t.y; }
-      else mv[0] = *ms;
+    for (int j = 0; j < NB; ++j) {
+      const int m = q * 32 + (it0 + j) * V + lrow;
+      int ty, tx;
+      if (p.halo) {                    // flattened padded position g = ty*P + tx (tx >= TWo are halo garbage)
+        const int g = tile_j * 128 + m;
+        ty = (g * p.pdiv_mul) >> 16;
+        tx = g - ty * p.P;
+      } else {
+        ty = m >> p.tw_shift; tx = m & tw_mask;
+      }
+      tyx[j] = (full || (ty < rows_valid && tx < cols_valid)) ? ((ty << 16) | tx) : -1;
+    }
+    // residual / multiplier operands first (longest latency). The stores below may alias `res` (in-place residuals),
+    // which is why the compiler cannot hoist these itself; every lane reads exactly the addresses it later writes.
+    float mv[HAS_MUL ? NB : 1][V], rv[HAS_RES ? NB : 1][V];
+    if (HAS_MUL) {
 #pragma unroll
-      for (int e = 0; e < V; ++e) v[e] *= mul_act ? apply_act(mv[e], mul_act, 0.f) : mv[e];
+      for (int j = 0; j < NB; ++j) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) mv[j][e] = 1.f;
+        if (tyx[j] >= 0) {
+          const float* ms = mbase + (tyx[j] >> 16) * m_py + (tyx[j] & 0xffff) * m_px;
+          if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(ms); mv[j][0] = t.x; mv[j][1 % V] = t.y; mv[j][2 % V] = t.z; mv[j][3 % V] = t.w; }
+          else if (V == 2) { const float2 t = *reinterpret_cast<const float2*>(ms); mv[j][0] = t.x; mv[j][1 % V] = t.y; }
+          else mv[j][0] = *ms;
+        }
+      }
+    }
+    if (HAS_RES) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) rv[j][e] = 0.f;
+        if (tyx[j] >= 0) {
+          const float* rs = rbase + (tyx[j] >> 16) * r_py + (tyx[j] & 0xffff) * r_px;
+          if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(rs); rv[j][0] = t.x; rv[j][1 % V] = t.y; rv[j][2 % V] = t.z; rv[j][3 % V] = t.w; }
+          else if (V == 2) { const float2 t = *reinterpret_cast<const float2*>(rs); rv[j][0] = t.x; rv[j][1 % V] = t.y; }
+          else rv[j][0] = *rs;
+        }
+      }
+    }
+    float v[NB][V];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int r = (it0 + j) * V + lrow;
+      const float* src = stg + r * 32 + (((swz_hi ^ (r & 7)) << 2) | swz_lo);
+      if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(src); v[j][0] = t.x; v[j][1 % V] = t.y; v[j][2 % V] = t.z; v[j][3 % V] = t.w; }
+      else if (V == 2) { const float2 t = *reinterpret_cast<const float2*>(src); v[j][0] = t.x; v[j][1 % V] = t.y; }
+      else v[j][0] = *src;
+    }
+#define LFSR_EPI_ACT(A)                                                                  \
+  _Pragma("unroll") for (int j = 0; j < NB; ++j) {                                       \
+    _Pragma("unroll") for (int e = 0; e < V; ++e) v[j][e] = act_t<A>(v[j][e] + bv[e], slope); \
+  }
+    switch (p.act) {                   // one uniform branch per NB rows
+      case LFSR_ACT_RELU: LFSR_EPI_ACT(LFSR_ACT_RELU) break;
+      case LFSR_ACT_LRELU: LFSR_EPI_ACT(LFSR_ACT_LRELU) break;
+      case LFSR_ACT_SIGMOID: LFSR_EPI_ACT(LFSR_ACT_SIGMOID) break;
+      case LFSR_ACT_GELU: LFSR_EPI_ACT(LFSR_ACT_GELU) break;
+      case LFSR_ACT_SILU: LFSR_EPI_ACT(LFSR_ACT_SILU) break;
+      default: LFSR_EPI_ACT(LFSR_ACT_NONE) break;
+    }
+#undef LFSR_EPI_ACT
+    if (HAS_MUL) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[j][e] *= mul_silu ? __fdividef(mv[j][e], 1.f + __expf(-mv[j][e])) : mv[j][e];
+      }
     }
 #pragma unroll
-    for (int e = 0; e < V; ++e) v[e] *= alpha;
-    if (rbase) {
-      const float* rs = rbase + ty * r_py + tx * r_px;
-      if (V == 4) { const float4 t = *reinterpret_cast<const float4*>(rs); v[0] += t.x; v[1 % V] += t.y; v[2 % V] += t.z; v[3 % V] += t.w; }
-      else if (V == 2) { const float2 t = *reinterpret_cast<const float2*>(rs); v[0] += t.x; v[1 % V] += t.y; }
-      else v[0] += *rs;
+    for (int j = 0; j < NB; ++j) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[j][e] *= alpha;
     }
-    float* dst = obase + ty * o_py + tx * o_px;
-    if (V == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1 % V], v[2 % V], v[3 % V]);
-    else if (V == 2) *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1 % V]);
-    else *dst = v[0];
+    if (HAS_RES) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[j][e] += rv[j][e];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (tyx[j] >= 0) {
+        float* dst = obase + (tyx[j] >> 16) * o_py + (tyx[j] & 0xffff) * o_px;
+        if (V == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[j][0], v[j][1 % V], v[j][2 % V], v[j][3 % V]);
+        else if (V == 2) *reinterpret_cast<float2*>(dst) = make_float2(v[j][0], v[j][1 % V]);
+        else *dst = v[j][0];
+      }
+    }
   }
 }
 
 template <int V>
 __device__ __forceinline__ void epi_writeout_act(const Params& p, const float* stg, int lane, int q, const TileCoord& tc_,
                                                  int pc0, int ncols, int tile_j) {
-  switch (p.act) {
-    case LFSR_ACT_RELU: epi_writeout<V, LFSR_ACT_RELU>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
-    case LFSR_ACT_LRELU: epi_writeout<V, LFSR_ACT_LRELU>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
-    case LFSR_ACT_SIGMOID: epi_writeout<V, LFSR_ACT_SIGMOID>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
-    case LFSR_ACT_GELU: epi_writeout<V, LFSR_ACT_GELU>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
-    case LFSR_ACT_SILU: epi_writeout<V, LFSR_ACT_SILU>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
-    default: epi_writeout<V, LFSR_ACT_NONE>(p, stg, lane, q, tc_, pc0, ncols, tile_j); break;
-  }
+  const bool m = p.mul.p != nullptr, r = p.res.p != nullptr;
+  if (m && r) epi_writeout<V, true, true>(p, stg, lane, q, tc_, pc0, ncols, tile_j);
+  else if (m) epi_writeout<V, true, false>(p, stg, lane, q, tc_, pc0, ncols, tile_j);
+  else if (r) epi_writeout<V, false, true>(p, stg, lane, q, tc_, pc0, ncols, tile_j);
+  else epi_writeout<V, false, false>(p, stg, lane, q, tc_, pc0, ncols, tile_j);
 }
 
 // TMEM accumulator (32 lanes x NC columns of this warp) -> staged transpose -> coalesced global stores
 __device__ __forceinline__ void epilogue_tile(const Params& p, float* stg, uint32_t taddr, int lane, int q, const TileCoord& tc_,
-                                              int tile_j, int g_first = 0, int g_step = 1) {
+                                              int tile_j, int g_first = 0, int g_step = 1, long long* dbg_ld = nullptr) {
   for (int g = g_first; g * 32 < p.NC; g += g_step) {
     const int ncols = p.NC - g * 32 < 32 ? p.NC - g * 32 : 32;
     float v[32];
+    long long t0 = 0;
+    if (dbg_ld) t0 = clock64();
     tmem_ld16(taddr + g * 32, v);
     if (ncols > 16) tmem_ld16(taddr + g * 32 + 16, v + 16);
 #pragma unroll
@@ -381,6 +457,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, float* stg, uint3
         *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
             make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     __syncwarp();
+    if (dbg_ld) *dbg_ld += clock64() - t0;
     const int pc0 = tc_.chunk * p.NC + g * 32;
     if (p.vec == 4) epi_writeout_act<4>(p, stg, lane, q, tc_, pc0, ncols, tile_j);
     else if (p.vec == 2) epi_writeout_act<2>(p, stg, lane, q, tc_, pc0, ncols, tile_j);
@@ -553,16 +630,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* stg = sEpi + warp * 1024;
     uint32_t tcount = 0;
     int m_, chunk_;
+    long long dbg_wait = 0, dbg_t0 = 0, tw0 = 0, dbg_ld = 0, dbg_epi = 0;
+    if (p.dbg) dbg_t0 = clock64();
     for (int i = 0; next_tile(p, i, m_, chunk_); ++i, ++tcount) {
       const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
       const TileCoord tc_ = decode_tile(p, m_, chunk_);
+      if (p.dbg) tw0 = clock64();
       mbar_wait(tfull + a, aph);
+      if (p.dbg) dbg_wait += clock64() - tw0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccStride;
-      if (m_ >= 0) epilogue_tile(p, stg, taddr, lane, q, tc_, 0, half, 2);
+      long long tw1 = 0;
+      if (p.dbg) tw1 = clock64();
+      if (m_ >= 0) epilogue_tile(p, stg, taddr, lane, q, tc_, 0, half, 2, p.dbg ? &dbg_ld : nullptr);
+      if (p.dbg) dbg_epi += clock64() - tw1;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + a);
+    }
+    if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 8 + 0] = dbg_epi;       // warp 2: no role warp on its sub-partition
+    if (p.dbg && threadIdx.x == 0) {
+      p.dbg[blockIdx.x * 8 + 1] = dbg_epi;
+      p.dbg[blockIdx.x * 8 + 6] = dbg_wait; p.dbg[blockIdx.x * 8 + 7] = clock64() - dbg_t0;
     }
   }
   __syncthreads();
@@ -838,6 +927,7 @@ static bool tc_geometry_ok(const lfsr_tensor* in, const lfsr_tensor* out, const 
   if (!tensor_ok(in) || !tensor_ok(out) || !d) return false;
   if (d->in_perm || d->out_perm) return false;
   if (d->mul.ptr && ((d->shuf_ry > 1) || (d->shuf_rx > 1))) return false;      // mul is only fused for unshuffled outputs
+  if (d->mul.ptr && d->mul_act != LFSR_ACT_NONE && d->mul_act != LFSR_ACT_SILU) return false;
   if (d->in_scale && d->w_batch_stride <= 0) return false;      // gates must come folded into per-image weights
   if (d->kh * d->kw > 25 || d->kh < 1 || d->kw < 1) return false;
   if (in->c < 8 || in->ld % 4 != 0 || ((uintptr_t)in->ptr & 15)) return false;
@@ -909,6 +999,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   LFSR_REQUIRE((long long)out->h * out->w * out->ld < 0x7fffffffLL, "lfsr_conv2d_tc: output image too large for 32-bit pitches");
   p.bias = d->bias; p.act = d->act; p.slope = d->act_slope; p.alpha = d->alpha; p.mul_act = d->mul_act;
   p.ry = ry; p.rx = rx; p.shuf_mode = d->shuf_mode; p.cq = out->c;
+  p.fd_cq = make_fastdiv(p.cq); p.fd_nby = make_fastdiv(p.nby); p.fd_nbx = make_fastdiv(p.nbx);
   p.vec = 1;
   for (int v = 2; v <= 4; v *= 2) {
     const uintptr_t mask = (uintptr_t)v * 4 - 1;
@@ -1021,6 +1112,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   LFSR_REQUIRE(tiles > 0 && tiles < 0x7fffffffLL, "lfsr_conv2d_tc: tile count out of range");
   p.total_tiles = (int)tiles;
   p.m_tiles = (int)(tiles / p.nchunks);
+  p.fd_tiles_x = make_fastdiv(p.tiles_x); p.fd_tiles_y = make_fastdiv(p.tiles_y); p.fd_nchunks = make_fastdiv(p.nchunks);
   const int nks = p.kh * p.kw * p.cgs;
   const int kSmemMax = 227 * 1024 - 1024 - 256 - kEpiWarps * 4096;  // minus alignment slack, barriers, epilogue staging
   const long long b_all = (long long)nks * p.b_stage_bytes;
@@ -1038,6 +1130,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   // K-stages (whole taps) into one smem stage; wide layers keep one tap per stage so that >= 3 stages fit
   int kps_auto = p.cgs <= 4 ? p.cgs : 1;
   if (p.NC <= 64 && p.cgs <= 2) kps_auto = 4 / p.cgs * p.cgs;
+  if (kps_auto > nks) kps_auto = nks;          // 1x1 layers: a stage never holds more than one tile's K-stages
   const int kps_tap = kps_env > 0 ? kps_env : kps_auto;
   const int need = p.NC <= 64 ? 2 : 3;
   struct Cand { bool res; int kps; int min_stages; };

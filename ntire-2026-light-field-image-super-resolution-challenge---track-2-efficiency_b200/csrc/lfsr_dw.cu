@@ -1,0 +1,258 @@
+// Depthwise convolutions (groups == channels) of the SR networks, NHWC fp32, sm_100a.
+//
+//   dw_tile_kernel   channel counts that are multiples of 16 on 16-byte aligned rows (the 64-channel trunks):
+//                    one CTA = one 16x32 output tile x 16 channels of one branch. The tile plus its dilation
+//                    halo is staged once in shared memory with 16-byte cp.async (out-of-image pixels zero
+//                    filled = the conv's zero padding), each thread then owns one channel quad (float4) of one
+//                    pixel column and walks the tile rows; a warp reads 8 pixels x 64 B = 512 contiguous bytes
+//                    per tap, conflict-free. Several branches (different taps / dilations / channel windows)
+//                    share one launch: MultiScaleSpatial's 1/3/5/7 kernels on four 16-channel slices and
+//                    FastConvSSM's four dilations of one input (MyEfficientLFNetV4_5.py:218-221, :268-271).
+//   dwconv_kernel    anything else (18-channel groups of the Track-2 model): one thread per pixel x channel.
+//
+// HBM-bound: algorithmic traffic is one read of the input window and one write per branch output.
+#include "lfsr_common.cuh"
+
+namespace lfsr {
+
+__global__ void __launch_bounds__(256)
+dwconv_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ scale,
+              const float* __restrict__ shift, int kh, int kw, int dh, int dw, int act, float slope) {
+  const int C = in.c;
+  const int img = blockIdx.y;                 // 32-bit index math inside one image
+  const int per = in.h * in.w * C;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per; t += gridDim.x * blockDim.x) {
+    const int c = t % C;
+    const int r = t / C;
+    const int x = r % in.w;
+    const int y = r / in.w;
+    const int ph = (kh / 2) * dh, pw = (kw / 2) * dw;
+    float acc = 0.f;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int iy = y - ph + ky * dh;
+      if (iy < 0 || iy >= in.h) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int ix = x - pw + kx * dw;
+        if (ix < 0 || ix >= in.w) continue;
+        acc = fmaf(__ldg(in.p + in.pix(img, iy, ix) + c), __ldg(w + (ky * kw + kx) * C + c), acc);
+      }
+    }
+    if (scale) acc = acc * __ldg(scale + c) + __ldg(shift + c);
+    out.p[out.pix(img, y, x) + c] = apply_act(acc, act, slope);
+  }
+}
+
+constexpr int DW_TH = 16, DW_TW = 32, DW_CH = 16, DW_MAXB = 8;
+
+struct DwBranch {
+  const float* w;
+  const float* scale;
+  const float* shift;
+  int kh, kw, dh, dw;
+  int in_c0, out_c0, c;
+  int act;
+  float slope;
+  int item0;              // first grid.y index of this branch (one item = one 16-channel chunk)
+};
+
+struct DwParams {
+  TView in, out;
+  DwBranch br[DW_MAXB];
+  int nbr, tiles_x, w_floats;   // w_floats: shared-memory floats reserved for the taps ahead of the tile
+};
+
+__device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, bool ok) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int sz = ok ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+__device__ __forceinline__ void fma4(float4& a, const float4& v, const float4& w) {
+  a.x = fmaf(v.x, w.x, a.x); a.y = fmaf(v.y, w.y, a.y); a.z = fmaf(v.z, w.z, a.z); a.w = fmaf(v.w, w.w, a.w);
+}
+
+template <int KH, int KW>   // 0,0 = runtime kernel size, taps read from shared memory
+__device__ __forceinline__ void dw_compute(const DwParams& p, const DwBranch& B, const float* wS, const float* tS,
+                                           int SW, int img, int ty0, int tx0, int cout0, int wofs) {
+  const int tid = threadIdx.x;
+  const int q = tid & 3, lx = (tid >> 2) & 31, ly0 = tid >> 7;
+  const int kh = KH ? KH : B.kh, kw = KW ? KW : B.kw;
+  const int ox = tx0 + lx;
+  if (ox >= p.in.w) return;
+  float4 wr[KH * KW ? KH * KW : 1];
+  if (KH) {
+#pragma unroll
+    for (int t = 0; t < KH * KW; ++t) wr[t] = *reinterpret_cast<const float4*>(wS + t * DW_CH + q * 4);
+  }
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (B.scale) {
+    sc = __ldg(reinterpret_cast<const float4*>(B.scale + wofs + q * 4));
+    sh = __ldg(reinterpret_cast<const float4*>(B.shift + wofs + q * 4));
+  }
+  const int row_f = SW * DW_CH;
+  const int dyf = B.dh * row_f, dxf = B.dw * DW_CH;
+  for (int r = ly0; r < DW_TH; r += 2) {
+    const int oy = ty0 + r;
+    if (oy >= p.in.h) break;
+    const float* base = tS + r * row_f + lx * DW_CH + q * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KH) {
+#pragma unroll
+      for (int ky = 0; ky < KH; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < KW; ++kx)
+          fma4(acc, *reinterpret_cast<const float4*>(base + ky * dyf + kx * dxf), wr[ky * KW + kx]);
+    } else {
+      for (int ky = 0; ky < kh; ++ky) {
+        const float* rowp = base + ky * dyf;
+        const float* wp = wS + ky * kw * DW_CH + q * 4;
+#pragma unroll 7
+        for (int kx = 0; kx < kw; ++kx)
+          fma4(acc, *reinterpret_cast<const float4*>(rowp + kx * dxf), *reinterpret_cast<const float4*>(wp + kx * DW_CH));
+      }
+    }
+    if (B.scale) {
+      acc.x = acc.x * sc.x + sh.x; acc.y = acc.y * sc.y + sh.y; acc.z = acc.z * sc.z + sh.z; acc.w = acc.w * sc.w + sh.w;
+    }
+    if (B.act) {
+      acc.x = apply_act(acc.x, B.act, B.slope); acc.y = apply_act(acc.y, B.act, B.slope);
+      acc.z = apply_act(acc.z, B.act, B.slope); acc.w = apply_act(acc.w, B.act, B.slope);
+    }
+    *reinterpret_cast<float4*>(p.out.p + p.out.pix(img, oy, ox) + cout0 + q * 4) = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dw_tile_kernel(const __grid_constant__ DwParams p) {
+  extern __shared__ __align__(16) float dw_smem[];
+  const int tid = threadIdx.x;
+  int b = 0;
+  while (b + 1 < p.nbr && (int)blockIdx.y >= p.br[b + 1].item0) ++b;
+  const DwBranch& B = p.br[b];
+  const int chunk = blockIdx.y - B.item0;
+  const int wofs = chunk * DW_CH;
+  const int cin0 = B.in_c0 + wofs, cout0 = B.out_c0 + wofs;
+  const int hy = (B.kh / 2) * B.dh, hx = (B.kw / 2) * B.dw;
+  const int SH = DW_TH + 2 * hy, SW = DW_TW + 2 * hx;
+  const int img = blockIdx.z;
+  const int tyi = blockIdx.x / p.tiles_x;
+  const int ty0 = tyi * DW_TH, tx0 = (blockIdx.x - tyi * p.tiles_x) * DW_TW;
+  float* wS = dw_smem;
+  float* tS = dw_smem + p.w_floats;
+  const int taps = B.kh * B.kw;
+  for (int i = tid; i < taps * DW_CH; i += 256) wS[i] = __ldg(B.w + (i >> 4) * B.c + wofs + (i & 15));
+  // rows of the halo'd tile that lie inside the image; everything else is zero padding
+  const int H = p.in.h, W = p.in.w;
+  const int quads_per_row = SW * 4;
+  for (int sy = tid >> 7; sy < SH; sy += 2) {       // 128 threads per tile row
+    const int gy = ty0 - hy + sy;
+    const bool yok = gy >= 0 && gy < H;
+    const float* grow = p.in.p + p.in.pix(img, yok ? gy : 0, 0) + cin0;
+    float* srow = tS + sy * SW * DW_CH;
+    for (int i = tid & 127; i < quads_per_row; i += 128) {
+      const int sx = i >> 2, qq = i & 3;
+      const int gx = tx0 - hx + sx;
+      const bool ok = yok && gx >= 0 && gx < W;
+      cp_async16_zfill(srow + i * 4, ok ? grow + (size_t)gx * p.in.ld + qq * 4 : p.in.p, ok);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (B.kh == 3 && B.kw == 3) dw_compute<3, 3>(p, B, wS, tS, SW, img, ty0, tx0, cout0, wofs);
+  else if (B.kh == 1 && B.kw == 1) dw_compute<1, 1>(p, B, wS, tS, SW, img, ty0, tx0, cout0, wofs);
+  else dw_compute<0, 0>(p, B, wS, tS, SW, img, ty0, tx0, cout0, wofs);
+}
+
+static bool dw_tile_ok(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_dw_branch* br, int nbr) {
+  if (nbr > DW_MAXB) return false;
+  if (((uintptr_t)in->ptr & 15) || ((uintptr_t)out->ptr & 15) || (in->ld & 3) || (out->ld & 3)) return false;
+  for (int i = 0; i < nbr; ++i) {
+    const lfsr_dw_branch& b = br[i];
+    if ((b.c % DW_CH) || (b.in_c0 & 3) || (b.out_c0 & 3)) return false;
+    if (b.scale && (((uintptr_t)b.scale & 15) || ((uintptr_t)b.shift & 15))) return false;
+    const int hy = (b.kh / 2) * b.dil_h, hx = (b.kw / 2) * b.dil_w;
+    const size_t bytes = ((size_t)(DW_TH + 2 * hy) * (DW_TW + 2 * hx) * DW_CH + (size_t)b.kh * b.kw * DW_CH) * 4;
+    if (bytes > 200 * 1024) return false;
+  }
+  return true;
+}
+
+}  // namespace lfsr
+
+using namespace lfsr;
+
+extern "C" int lfsr_dwconv_multi(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_dw_branch* br, int nbr,
+                                 void* stream) {
+  LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && br && nbr > 0, "lfsr_dwconv_multi: null/invalid argument");
+  LFSR_REQUIRE(in->n == out->n && in->h == out->h && in->w == out->w, "lfsr_dwconv_multi: in/out geometry mismatch");
+  LFSR_REQUIRE(in->n <= 65535 && (long long)in->h * in->w * in->ld < 0x7fffffffLL &&
+                   (long long)out->h * out->w * out->ld < 0x7fffffffLL, "lfsr_dwconv_multi: tensor too large");
+  for (int i = 0; i < nbr; ++i) {
+    const lfsr_dw_branch& b = br[i];
+    LFSR_REQUIRE(b.w && b.kh > 0 && b.kw > 0 && (b.kh & 1) && (b.kw & 1) && b.dil_h > 0 && b.dil_w > 0,
+                 "lfsr_dwconv_multi: branch %d: odd kernels only", i);
+    LFSR_REQUIRE(b.c > 0 && b.in_c0 >= 0 && b.out_c0 >= 0 && b.in_c0 + b.c <= in->c && b.out_c0 + b.c <= out->c,
+                 "lfsr_dwconv_multi: branch %d: channel window [%d,+%d) -> [%d,+%d) outside %d / %d channels", i, b.in_c0,
+                 b.c, b.out_c0, b.c, in->c, out->c);
+    LFSR_REQUIRE((b.scale == nullptr) == (b.shift == nullptr), "lfsr_dwconv_multi: scale/shift must come together");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!dw_tile_ok(in, out, br, nbr)) {
+    for (int i = 0; i < nbr; ++i) {
+      const lfsr_dw_branch& b = br[i];
+      TView vi = view_of(in), vo = view_of(out);
+      vi.p += b.in_c0; vi.c = b.c;
+      vo.p += b.out_c0; vo.c = b.c;
+      dim3 blocks(ceil_div(in->h * in->w * b.c, 256), in->n);
+      dwconv_kernel<<<blocks, 256, 0, st>>>(vi, vo, b.w, b.scale, b.shift, b.kh, b.kw, b.dil_h, b.dil_w, b.act, b.act_slope);
+      int rc = check_launch("dwconv_kernel");
+      if (rc != LFSR_OK) return rc;
+    }
+    return LFSR_OK;
+  }
+  DwParams p;
+  p.in = view_of(in); p.out = view_of(out);
+  p.nbr = nbr;
+  int items = 0, w_floats = 0;
+  size_t tile_floats = 0;
+  for (int i = 0; i < nbr; ++i) {
+    const lfsr_dw_branch& b = br[i];
+    DwBranch& d = p.br[i];
+    d.w = b.w; d.scale = b.scale; d.shift = b.shift;
+    d.kh = b.kh; d.kw = b.kw; d.dh = b.dil_h; d.dw = b.dil_w;
+    d.in_c0 = b.in_c0; d.out_c0 = b.out_c0; d.c = b.c; d.act = b.act; d.slope = b.act_slope;
+    d.item0 = items;
+    items += b.c / DW_CH;
+    const int hy = (b.kh / 2) * b.dil_h, hx = (b.kw / 2) * b.dil_w;
+    const size_t tf = (size_t)(DW_TH + 2 * hy) * (DW_TW + 2 * hx) * DW_CH;
+    if (tf > tile_floats) tile_floats = tf;
+    if (b.kh * b.kw * DW_CH > w_floats) w_floats = b.kh * b.kw * DW_CH;
+  }
+  LFSR_REQUIRE(items <= 65535, "lfsr_dwconv_multi: too many channel chunks");
+  p.tiles_x = ceil_div(in->w, DW_TW);
+  p.w_floats = w_floats;
+  const size_t smem = (tile_floats + (size_t)w_floats) * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(dw_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 4096);
+    if (e != cudaSuccess) { set_error("lfsr_dwconv_multi: %s", cudaGetErrorString(e)); return LFSR_ERR_CUDA; }
+    smem_set = 200 * 1024 + 4096;
+  }
+  dim3 grid(p.tiles_x * ceil_div(in->h, DW_TH), items, in->n);
+  dw_tile_kernel<<<grid, 256, smem, st>>>(p);
+  return check_launch("dw_tile_kernel");
+}
+
+extern "C" int lfsr_dwconv_f32(const lfsr_tensor* in, const float* w_packed, const float* scale, const float* shift,
+                               const lfsr_tensor* out, int kh, int kw, int dil_h, int dil_w, int act, float act_slope,
+                               void* stream) {
+  LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && w_packed, "lfsr_dwconv_f32: null/invalid tensor");
+  LFSR_REQUIRE(in->c == out->c, "lfsr_dwconv_f32: in/out shape mismatch");
+  lfsr_dw_branch b;
+  b.w = w_packed; b.scale = scale; b.shift = shift;
+  b.kh = kh; b.kw = kw; b.dil_h = dil_h; b.dil_w = dil_w;
+  b.in_c0 = 0; b.out_c0 = 0; b.c = in->c;
+  b.act = act; b.act_slope = act_slope;
+  return lfsr_dwconv_multi(in, out, &b, 1, stream);
+}

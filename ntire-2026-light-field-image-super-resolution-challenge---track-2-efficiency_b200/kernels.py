@@ -187,6 +187,18 @@ class CudaOps:
                                          self._ptr(shift), C.byref(as_tensor(out, "dwconv.out")), kh, kw, dil[0],
                                          dil[1], act, slope, self._stream(x)), "lfsr_dwconv_f32")
 
+    def dwconv_multi(self, x, out, branches):
+        """branches: dicts(w, kh, kw, dil=(1,1), in_c0=0, out_c0=0, c, scale=None, shift=None, act=0, slope=0.0)"""
+        arr = (N.DwBranch * len(branches))()
+        for d, b in zip(arr, branches):
+            d.w, d.scale, d.shift = b["w"].data_ptr(), self._ptr(b.get("scale")), self._ptr(b.get("shift"))
+            d.kh, d.kw = b["kh"], b["kw"]
+            d.dil_h, d.dil_w = b.get("dil", (1, 1))
+            d.in_c0, d.out_c0, d.c = b.get("in_c0", 0), b.get("out_c0", 0), b["c"]
+            d.act, d.act_slope = b.get("act", N.ACT_NONE), b.get("slope", 0.0)
+        N.check(self.lib.lfsr_dwconv_multi(C.byref(as_tensor(x, "dwconv_multi.in")), C.byref(as_tensor(out, "dwconv_multi.out")),
+                                           arr, len(branches), self._stream(x)), "lfsr_dwconv_multi")
+
     def mel_epi_branch(self, x, w_packed, out, klen, dil, slope):
         N.check(self.lib.lfsr_mel_epi_branch(C.byref(as_tensor(x, "epi.in")), w_packed.data_ptr(),
                                              C.byref(as_tensor(out, "epi.out")), klen, dil, slope, self._stream(x)),

@@ -2,16 +2,16 @@
 /root/reference/model/SR/MyEfficientLFNetV4_5.py as it runs when mamba_ssm is absent (:17-25), which is
 the only way it runs in the reference's own environment list and in this image.
 
-64-channel trunk at LR resolution, NHWC fp32. Per MambaLFBlock (:143-148), 13 launches:
+64-channel trunk at LR resolution, NHWC fp32. Per MambaLFBlock (:143-148), 11 launches:
 
-  MultiScaleSpatial (:262-282)   one 7x7 depthwise launch over all 64 channels: the identity / 3x3 /
-                                 5x5 / 7x7 kernels of the four 16-channel slices are zero-padded to 7x7
-                                 (adding exact zeros), and the slice-0 1x1 conv is composed into the
-                                 pointwise conv at pack time -> lfsr_dwconv_f32, then lfsr_conv2d_tc
-                                 1x1 64->64 with folded BN + LReLU + residual
+  MultiScaleSpatial (:262-282)   one lfsr_dwconv_multi launch: identity / 3x3 / 5x5 / 7x7 depthwise branches
+                                 on the four 16-channel slices (the slice-0 1x1 conv is composed into the
+                                 pointwise conv at pack time), then lfsr_conv2d_tc 1x1 64->64 with folded
+                                 BN + LReLU + residual
   FastConvSSM (:208-244)         BN folded into gate_conv (weights and a bias); ONE 1x1 64->128 conv
-                                 with GELU writes [gate | y]; four dilated depthwise 3x3 into the four
-                                 windows of a 256-channel buffer (the torch.cat); fuse 1x1 256->64 with
+                                 with GELU writes [gate | y]; the four dilated depthwise 3x3 in one
+                                 lfsr_dwconv_multi launch into the four windows of a 256-channel buffer
+                                 (the torch.cat); fuse 1x1 256->64 with
                                  the `* silu(gate)` product in its epilogue (mul, mul_act); proj 1x1
                                  with alpha = scale and residual x
   fuse + ChannelAttention        1x1 128->64; two-level lfsr_block_mean; fc1/fc2 on the [B,1,1,C] means;
@@ -131,11 +131,10 @@ class get_model(LFNetBase):
             ms, ssm = blk.ms_spatial, blk.ssm
             c = ms.c
             ch = 4 * c
-            w7 = torch.zeros(ch, 7, 7, dtype=torch.float32)
-            w7[:c, 3, 3] = 1.0
-            w7[c:2 * c, 2:5, 2:5] = ms.conv3.weight.detach().float().cpu()[:, 0]
-            w7[2 * c:3 * c, 1:6, 1:6] = ms.conv5.weight.detach().float().cpu()[:, 0]
-            w7[3 * c:] = ms.conv7.weight.detach().float().cpu()[:, 0]
+            ms_br = [dict(w=torch.ones(1, c, dtype=torch.float32, device=device), kh=1, kw=1, in_c0=0, out_c0=0, c=c)]
+            for j, cv in enumerate((ms.conv3, ms.conv5, ms.conv7), 1):
+                k = cv.kernel_size[0]
+                ms_br.append(dict(w=dw_taps(cv.weight), kh=k, kw=k, in_c0=j * c, out_c0=j * c, c=c))
             pw = f64(ms.pw.weight)[:, :, 0, 0].clone()                            # [out, in]
             pw[:, :c] = pw[:, :c] @ f64(ms.conv1.weight)[:, :, 0, 0]
             s, t = bn_affine(ms.bn)
@@ -143,10 +142,11 @@ class get_model(LFNetBase):
             sn, tn = bn_affine(ssm.norm)
             wg = f64(ssm.gate_conv.weight)[:, :, 0, 0]
             b = dict(
-                ms_dw=w7.reshape(ch, 49).t().contiguous().to(device),
+                ms_dw=ms_br,
                 ms_pw=pc(pw.float()[:, :, None, None], t.detach().float(), tc=True),
                 gate=pc((wg * f64(sn)[None, :]).float()[:, :, None, None], (wg @ f64(tn)).float(), tc=True),
-                dws=[(dw_taps(getattr(ssm, f"conv{d}").weight), d) for d in ssm.DILS],
+                dws=[dict(w=dw_taps(getattr(ssm, f"conv{d}").weight), kh=3, kw=3, dil=(d, d), in_c0=ch, out_c0=k * ch, c=ch)
+                     for k, d in enumerate(ssm.DILS)],
                 ssm_fuse=pc(ssm.fuse.weight, tc=True), proj=pc(ssm.proj.weight, tc=True),
                 ssm_scale=float(ssm.scale.detach().float().cpu()),
                 fuse=pc(blk.fuse.weight, tc=True),
@@ -189,12 +189,11 @@ class get_model(LFNetBase):
         feat = shallow
         for i, b in enumerate(pk["blocks"]):
             # multi-scale spatial -> f_local = cat2[..., :C]
-            ops.dwconv(feat, b["ms_dw"], ms, 7, 7)
+            ops.dwconv_multi(feat, ms, b["ms_dw"])
             ops.conv(ms, b["ms_pw"], cat2[..., 0:C], act=LR, slope=0.1, res=feat)
             # gated multi-dilation branch -> f_global = cat2[..., C:]
             ops.conv(feat, b["gate"], g, act=N.ACT_GELU)
-            for k, (w, d) in enumerate(b["dws"]):
-                ops.dwconv(g[..., C:2 * C], w, cat4[..., k * C:(k + 1) * C], 3, 3, dil=(d, d))
+            ops.dwconv_multi(g, cat4, b["dws"])
             ops.conv(cat4, b["ssm_fuse"], yf, mul=g[..., 0:C], mul_act=N.ACT_SILU)
             ops.conv(yf, b["proj"], cat2[..., C:2 * C], alpha=b["ssm_scale"], res=feat)
             # fuse + channel attention + block residual

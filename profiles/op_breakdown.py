@@ -34,6 +34,10 @@ class ProfilingOps(K.CudaOps):
     def dwconv(self, x, w, out, kh, kw, **k2):
         self._wrap("dwconv", lambda: K.CudaOps.dwconv(self, x, w, out, kh, kw, **k2), f"dwconv {kh}x{kw} d{k2.get('dil', (1, 1))[0]} c{x.shape[3]} @{x.shape[1]}x{x.shape[2]}")
 
+    def dwconv_multi(self, x, out, branches):
+        lab = "+".join(f"{b['kh']}x{b['kw']}d{b.get('dil', (1, 1))[0]}c{b['c']}" for b in branches)
+        self._wrap("dwconv_multi", lambda: K.CudaOps.dwconv_multi(self, x, out, branches), f"dwconv_multi {lab} @{x.shape[1]}x{x.shape[2]}")
+
     def mel_epi_branch(self, x, w, out, klen, dil, slope):
         self._wrap("mel_epi_branch", lambda: K.CudaOps.mel_epi_branch(self, x, w, out, klen, dil, slope), f"mel_epi_branch c{x.shape[3]} @{x.shape[1]}x{x.shape[2]}")
 

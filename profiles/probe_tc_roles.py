@@ -1,4 +1,5 @@
-"""Per-role cycle accounting of the tiled tcgen05 conv kernel (producer / MMA-issuer waits), via LFSR_TC_DBG_PTR."""
+"""Per-role cycle accounting of the tiled tcgen05 conv kernel (MMA-issuer and epilogue waits), via LFSR_TC_DBG_PTR.
+usage: python profiles/probe_tc_roles.py [batch]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,17 +8,21 @@ os.environ["LFSR_TC_DBG_PTR"] = hex(dbg.data_ptr())
 import lfsr_b200
 from lfsr_b200 import kernels as K
 ops = K.CudaOps()
-B = 16
-for (cin, cout, hw, dil) in ((64, 64, 160, 5), (56, 224, 320, 1)):
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+for (cin, cout, hw, k, dil, res) in ((64, 64, 160, 1, 1, False), (64, 64, 160, 1, 1, True), (128, 64, 160, 1, 1, False),
+                                     (64, 128, 160, 1, 1, False), (256, 64, 160, 1, 1, False),
+                                     (64, 64, 160, 3, 5, False), (56, 224, 320, 3, 1, False)):
     x = torch.rand(B, hw, hw, cin, device="cuda")
     y = torch.empty(B, hw, hw, cout, device="cuda")
-    w = (torch.rand(cout, cin, 3, 3) - 0.5) * 0.1
-    pc = K.pack_conv(w, dil=(dil, dil), pad=(dil, dil), device="cuda", tc=True)
+    r = torch.rand(B, hw, hw, cout, device="cuda") if res else None
+    w = (torch.rand(cout, cin, k, k) - 0.5) * 0.1
+    p = dil * (k // 2)
+    pc = K.pack_conv(w, dil=(dil, dil), pad=(p, p), device="cuda", tc=True)
     for _ in range(2):
-        ops.conv(x, pc, y)
+        ops.conv(x, pc, y, res=r)
     torch.cuda.synchronize()
     d = dbg.view(148, 8).double().mean(0).tolist()
     ntile = B * hw * hw / 128 / 148
-    print(f"{cin}->{cout} @{hw} d{dil}: tiles/CTA {ntile:.0f} | "
-          f"MMA thread: wait-full {d[2]:.0f}, wait-acc {d[3]:.0f}, fence+issue+commit {d[4]:.0f} of {d[5]:.0f} cyc | "
-          f"per k-stage {d[5]/ntile/18:.0f}")
+    print(f"{k}x{k} {cin}->{cout} @{hw} d{dil} res={int(res)}: tiles/CTA {ntile:.0f} | "
+          f"MMA thread: wait-full {d[2]/ntile:.0f}, wait-acc {d[3]/ntile:.0f}, issue {d[4]/ntile:.0f} of {d[5]/ntile:.0f} cyc/tile | "
+          f"epilogue warp0: wait-acc-full {d[6]/ntile:.0f}, tile work warp2 {d[0]/ntile:.0f}, warp0 {d[1]/ntile:.0f} of {d[7]/ntile:.0f} cyc/tile")

@@ -107,6 +107,12 @@ class RefOps:
             y = y * scale.view(1, c, 1, 1) + shift.view(1, c, 1, 1)
         out.copy_(_act(y, act, slope).permute(0, 2, 3, 1))
 
+    def dwconv_multi(self, x, out, branches):
+        for b in branches:
+            i0, o0, c = b.get("in_c0", 0), b.get("out_c0", 0), b["c"]
+            self.dwconv(x[..., i0:i0 + c], b["w"], out[..., o0:o0 + c], b["kh"], b["kw"], b.get("dil", (1, 1)),
+                        b.get("scale"), b.get("shift"), b.get("act", 0), b.get("slope", 0.0))
+
     def mel_epi_branch(self, x, w_packed, out, klen, dil, slope):
         c = x.shape[3]
         o = 0

@@ -187,6 +187,31 @@ def test_dwconv(ops, ref, kh, kw, dil, c):
         assert (a - b).abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("h,w", [(40, 40), (37, 53), (160, 160)])
+def test_dwconv_multi(ops, ref, h, w):
+    """MultiScaleSpatial's sliced 1/3/5/7 branches and FastConvSSM's four dilations of the y half of [gate | y]
+    (MyEfficientLFNetV4_5.py:218-221, :268-280), including tiles that overhang the image"""
+    n, C, c = 2, 64, 16
+    x = nhwc(n, h, w, C, seed=1)
+    br = [dict(w=torch.ones(1, c, device=DEV), kh=1, kw=1, in_c0=0, out_c0=0, c=c)]
+    for j, k in enumerate((3, 5, 7), 1):
+        br.append(dict(w=rnd(k * k, c, seed=10 + j), kh=k, kw=k, in_c0=j * c, out_c0=j * c, c=c))
+    a, b = nhwc(n, h, w, C, seed=2), nhwc(n, h, w, C, seed=2)
+    l0 = ops.lib.lfsr_launch_count()
+    ops.dwconv_multi(x, a, br)
+    assert ops.lib.lfsr_launch_count() == l0 + 1
+    ref.dwconv_multi(x, b, br)
+    assert (a - b).abs().max().item() <= 1e-5
+    g = nhwc(n, h, w, 2 * C, seed=3)
+    br = [dict(w=rnd(9, C, seed=20 + k), kh=3, kw=3, dil=(d, d), in_c0=C, out_c0=k * C, c=C, act=(2 if k == 1 else 0), slope=0.1,
+               scale=(rnd(C, seed=30, lo=0.5, hi=1.5) if k == 2 else None), shift=(rnd(C, seed=31) if k == 2 else None))
+          for k, d in enumerate((1, 2, 4, 8))]
+    a, b = nhwc(n, h, w, 4 * C, seed=4), nhwc(n, h, w, 4 * C, seed=4)
+    ops.dwconv_multi(g, a, br)
+    ref.dwconv_multi(g, b, br)
+    assert (a - b).abs().max().item() <= 1e-5
+
+
 @pytest.mark.parametrize("h,w,c,bh,bw", [(40, 40, 54, 8, 8), (5, 5, 54, 5, 5), (160, 160, 54, 32, 32), (20, 30, 130, 4, 5)])
 def test_block_mean(ops, ref, h, w, c, bh, bw):
     x = nhwc(3, h, w, c, seed=1)
