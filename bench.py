@@ -226,14 +226,14 @@ def main():
             step(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = lib.lfsr_launch_count()
+        l0 = lib.lfsr_launch_count() + net.graph_launches     # direct launches + kernels replayed from CUDA graphs
         e0.record()
         for i in range(steps):
             step(warmup + i)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        launches = lib.lfsr_launch_count() - l0
+        launches = lib.lfsr_launch_count() + net.graph_launches - l0
         if dist is not None:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -7,6 +7,7 @@ tap-major layouts) and enqueues the sm_100a kernels of liblfsr_b200 on torch's c
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -14,6 +15,10 @@ import torch.nn as nn
 
 from .. import _native as N
 from .. import kernels as K
+
+
+#: LFSR_CUDA_GRAPH=0 launches every kernel of a forward individually (profiling per-op, debugging)
+USE_CUDA_GRAPH = os.environ.get("LFSR_CUDA_GRAPH", "1") != "0"
 
 
 def slots(mods: Dict[int, nn.Module]) -> nn.ModuleDict:
@@ -40,12 +45,15 @@ class LFNetBase(nn.Module):
         self._packed = None
         self._packed_key = None
         self._arena: Dict[tuple, torch.Tensor] = {}
+        self._graphs: Dict[tuple, tuple] = {}
+        self.graph_launches = 0       # kernels launched through graph replays (the C-side counter only sees direct launches)
 
     # -- backend ---------------------------------------------------------------------------------
     def set_backend(self, ops) -> None:
         """Tests inject tests/opref.RefOps here; the product default is kernels.CudaOps."""
         self._ops = ops
         self._packed = None
+        self._graphs = {}
 
     def _backend(self, x: torch.Tensor):
         if self._ops is not None:
@@ -69,6 +77,7 @@ class LFNetBase(nn.Module):
             with torch.no_grad():
                 self._packed = self._pack(device, ops)
             self._packed_key = key
+            self._graphs = {}          # captured graphs hold pointers into the previous packing
         return self._packed
 
     def _pack(self, device, ops):  # pragma: no cover - abstract
@@ -87,10 +96,12 @@ class LFNetBase(nn.Module):
         return t
 
     def release_workspace(self) -> None:
+        self._graphs = {}
         self._arena.clear()
 
     def _apply(self, fn, *a, **kw):  # .to()/.cpu()/.cuda(): packed weights and arena are stale
         self._packed = None
+        self._graphs = {}
         self._arena = {}
         return super()._apply(fn, *a, **kw)
 
@@ -107,10 +118,40 @@ class LFNetBase(nn.Module):
         ops = self._backend(x)
         pk = self._get_packed(x.device, ops)
         x = x.contiguous()
+        if (USE_CUDA_GRAPH and self._ops is None and x.is_cuda and not torch.cuda.is_current_stream_capturing()):
+            return self._forward_graphed(ops, pk, x)
         out = torch.empty((B, 1, H * self.scale, W * self.scale), dtype=torch.float32, device=x.device)
         with torch.no_grad():
             self._run(ops, pk, x, out)
         return out
+
+    def _forward_graphed(self, ops, pk, x: torch.Tensor) -> torch.Tensor:
+        """One CUDA graph per input shape: a forward is ~100 launches of a few microseconds of host work each, which at the
+        reference's minibatch sizes (train.py:303-314 feeds ONE patch per call) costs more than the kernels themselves.
+        The workspace arena makes every pointer of a forward stable, so the launch sequence is captured once and replayed
+        with the input copied into / the result copied out of two static tensors."""
+        key = tuple(x.shape)
+        ent = self._graphs.get(key)
+        if ent is None:
+            B, _, H, W = x.shape
+            sx = torch.empty_like(x)
+            so = torch.empty((B, 1, H * self.scale, W * self.scale), dtype=torch.float32, device=x.device)
+            sx.copy_(x)
+            with torch.no_grad():
+                self._run(ops, pk, sx, so)        # allocates the workspace and sets kernel attributes outside the capture
+                torch.cuda.current_stream(x.device).synchronize()
+                l0 = ops.lib.lfsr_launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run(ops, pk, sx, so)
+                n = ops.lib.lfsr_launch_count() - l0
+            ent = (g, sx, so, n)
+            self._graphs[key] = ent
+        g, sx, so, n = ent
+        sx.copy_(x)
+        g.replay()
+        self.graph_launches += n
+        return so.clone()
 
 
 class L1Loss(nn.Module):

@@ -99,3 +99,32 @@ def test_scene_loop_vs_reference_test_golden(golden_dir):
     _dump()
     assert err <= TOL
     assert abs(psnr - float(g["psnr"])) <= 0.01 and abs(ssim - float(g["ssim"])) <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["MyEfficientLFNet", "MyEfficientLFNetV4_5", "EPIT"])
+def test_graph_replay_equals_direct_launches(name, monkeypatch):
+    """the per-shape CUDA graph of a forward gives bit-identical results to launching every kernel,
+    survives shape changes, and is dropped when the weights change."""
+    import sys
+    net, _ = _net(name, 4)
+    common = sys.modules[[c for c in type(net).__mro__ if c.__name__ == "LFNetBase"][0].__module__]
+    xa = weights.synthetic_patches(2, 5, 8, seed=11).to(DEV)
+    xb = weights.synthetic_patches(1, 5, 16, seed=12).to(DEV)
+    monkeypatch.setattr(common, "USE_CUDA_GRAPH", False)
+    da, db = net(xa), net(xb)
+    assert not net._graphs
+    monkeypatch.setattr(common, "USE_CUDA_GRAPH", True)
+    for _ in range(3):
+        assert torch.equal(net(xa), da) and torch.equal(net(xb), db)
+    assert len(net._graphs) == 2 and net.graph_launches > 0
+    xa2 = weights.synthetic_patches(2, 5, 8, seed=13).to(DEV)          # same shape, new data -> same graph, new result
+    ga2 = net(xa2)
+    monkeypatch.setattr(common, "USE_CUDA_GRAPH", False)
+    assert torch.equal(ga2, net(xa2)) and not torch.equal(ga2, da)
+    monkeypatch.setattr(common, "USE_CUDA_GRAPH", True)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(0.5)
+    out = net(xa)                                                       # repacks and re-captures
+    monkeypatch.setattr(common, "USE_CUDA_GRAPH", False)
+    assert torch.equal(out, net(xa)) and not torch.equal(out, da)
