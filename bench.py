@@ -273,6 +273,8 @@ def main():
         traffic = None
         try:
             nc = json.load(open(os.path.join(ROOT, "profiles", "r01_dominant_kernel_ncu.json")))
+            if nc.get("kernel_variant", "") != ("fused-tail" if "bytes_conv_layer_only" in info else "conv"):
+                raise KeyError("capture is of the other kernel variant")
             gb = lambda k: float(nc[k]["value"]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[nc[k]["unit"]]
             traffic = (gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")) * a.batch / 64.0
         except (OSError, KeyError, ValueError):
@@ -280,6 +282,9 @@ def main():
         roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                 "traffic": traffic, "kernel": info["name"], "kernel_ms": kms, "algorithmic_bytes": info["bytes"],
                 "tflops": info["flops"] / (kms * 1e-3) / 1e12,
+                # when the kernel fuses the head conv's contraction, also the fraction counted on this conv layer alone
+                "frac_conv_layer_only": (info["bytes_conv_layer_only"] / (kms * 1e-3) / 1e9 / hbm_peak
+                                         if "bytes_conv_layer_only" in info else None),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
 
     cpu = None

@@ -79,6 +79,13 @@ typedef struct {
                              (built by lfsr_scale_pack_tc for per-sample gated convs); 0 = shared weights */
   lfsr_tensor mul;       /* ptr NULL if unused; conv-output geometry */
   lfsr_tensor res;       /* ptr NULL if unused; stored-output geometry */
+  /* lfsr_conv2d_tc only, with a PixelShuffle: do not store the tail_c-channel shuffled activation at all but its
+   * projection onto tail_taps vectors, out(n, y, x, t) = sum_c tail_w[c][t] * act(shuffle(conv))(n, y, x, c), fp32.
+   * With tail_w[c][ky*3+kx] = W_head[0][c][ky][kx] this is the per-tap response of the 3x3 reconstruction conv that
+   * follows the last upsampler stage (MyEfficientLFNet.py:70-73,104-109; MyEfficientLFNetV4_5.py:62,98-109), which
+   * lfsr_tap_gather then sums over the 9 shifted positions: the widest activation of the network is never written. */
+  const float* tail_w;   /* [tail_c][12] (columns >= tail_taps zero) or NULL */
+  int32_t tail_taps, tail_c;
 } lfsr_conv_desc;
 
 const char* lfsr_last_error(void);
@@ -136,6 +143,10 @@ typedef struct {
 } lfsr_dw_branch;
 int lfsr_dwconv_multi(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_dw_branch* branches,
                       int n_branches, void* stream);
+/* out(n,y,x) = bias + res(n,y,x) + sum_{ky,kx} taps(n, y+ky-kh/2, x+kx-kw/2, ky*kw+kx), zero outside the image: the
+ * second half of a kh x kw convolution to ONE channel whose per-tap responses were produced by a `tail_w` epilogue. */
+int lfsr_tap_gather(const lfsr_tensor* taps, int kh, int kw, const float* bias, const lfsr_tensor* res,
+                    const lfsr_tensor* out, void* stream);
 /* direct conv for 1..4 output channels (reconstruction heads 54->1 / 64->1: MyEfficientLFNet.py:70-73,
  * EPIT.py:48): stride 1, "same" padding; weights packed as for lfsr_conv2d_f32; bias/act/alpha/res fused. */
 int lfsr_conv2d_small_cout_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);

@@ -39,6 +39,7 @@ class ConvDesc(C.Structure):
         ("act", C.c_int32), ("act_slope", C.c_float), ("alpha", C.c_float), ("mul_act", C.c_int32),
         ("bias", C.c_void_p), ("in_scale", C.c_void_p), ("in_scale_ld", C.c_int64), ("w_batch_stride", C.c_int64),
         ("mul", Tensor), ("res", Tensor),
+        ("tail_w", C.c_void_p), ("tail_taps", C.c_int32), ("tail_c", C.c_int32),
     ]
 
 
@@ -74,6 +75,7 @@ SIGNATURES = {
     "lfsr_conv2d_f32": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
     "lfsr_dwconv_f32": (_I, [_TP, _P, _P, _P, _TP, _I, _I, _I, _I, _I, C.c_float, _P]),
     "lfsr_dwconv_multi": (_I, [_TP, _TP, C.POINTER(DwBranch), _I, _P]),
+    "lfsr_tap_gather": (_I, [_TP, _I, _I, _P, _TP, _TP, _P]),
     "lfsr_conv2d_small_cout_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),
     "lfsr_conv2d_small_cout": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
     "lfsr_mel_epi_branch": (_I, [_TP, _P, _TP, _I, _I, C.c_float, _P]),

@@ -49,6 +49,8 @@ __device__ __forceinline__ int fdiv(int n, FastDiv f) { return (int)((__umulhi((
 struct Params {
   FastDiv fd_tiles_x, fd_nbx, fd_tiles_y, fd_nby, fd_nchunks, fd_cq, fd_rx;
   int tma_epi, OHc;                    // tma_epi: epilogue stores go through the output tensor map; OHc: conv-output rows per image
+  const float* tail_w;                 // tail projection (lfsr_conv_desc.tail_w): [cq][12] in global memory, else null
+  int tail_rows;                       // rows of the zero-padded copy in shared memory (cq rounded up to 32)
   int nb_total, nby, nbx, bh, bw;      // blocks: nb_total = images * nby
   int C, cgs, kh, kw, dil_h, dil_w, pad_h, pad_w;
   int cout, NC, nchunks;
@@ -607,6 +609,70 @@ __device__ __forceinline__ void epilogue_tile_tma(const Params& p, const CUtenso
   if (!waited) { mbar_wait(tfull_bar, tfull_parity); tc_fence_after(); }
 }
 
+// Epilogue of one tile for one warp when the layer ends in a tail projection (Params::tail_w): the warp owns whole
+// PixelShuffle sub-pixels (alternating with its partner warp), a lane owns one pixel, and instead of storing the cq
+// activated channels of that output pixel it accumulates their dot products with the <= 12 tail vectors (weights
+// broadcast from shared memory) and stores those 12 floats - 48 bytes instead of 4*cq per output pixel.
+__device__ __forceinline__ void epilogue_tile_tail(const Params& p, const float* sTail, uint32_t taddr, int lane, int q,
+                                                   const TileCoord& tc_, int g_first, int g_step, uint64_t* tfull_bar,
+                                                   uint32_t tfull_parity) {
+  const int m = q * 32 + lane;
+  const int ty = m >> p.tw_shift, tx = m & (p.TW - 1);
+  const bool pix_ok = tc_.y0 + ty < p.bh && tc_.x0 + tx < p.bw;
+  const int img = fdiv(tc_.nb, p.fd_nby);
+  const int Y = (tc_.nb - img * p.nby) * p.bh + tc_.y0 + ty, X = tc_.vx * p.bw + tc_.x0 + tx;
+  const int r2 = p.ry * p.rx;
+  const bool chan_major = p.shuf_mode == LFSR_SHUF_CHANNEL_MAJOR;
+  const float slope = p.slope;
+  mbar_wait(tfull_bar, tfull_parity);
+  tc_fence_after();
+  for (int sub = g_first; sub < r2; sub += g_step) {
+    float r[12];
+#pragma unroll
+    for (int t = 0; t < 12; ++t) r[t] = 0.f;
+    for (int c0 = 0; c0 < p.cq; c0 += 32) {
+      const int pc0 = sub * p.cq + c0;
+      float bcol = 0.f;
+      if (p.bias && c0 + lane < p.cq) bcol = __ldg(p.bias + (chan_major ? (c0 + lane) * r2 + sub : pc0 + lane));
+      float v[32];
+      tmem_ld16(taddr + pc0, v);
+      tmem_ld16(taddr + pc0 + 16, v + 16);
+      if (p.bias) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] += __shfl_sync(0xffffffffu, bcol, k);
+      }
+#define LFSR_EPI_ACT32(A) _Pragma("unroll") for (int k = 0; k < 32; ++k) v[k] = act_t<A>(v[k], slope);
+      switch (p.act) {
+        case LFSR_ACT_RELU: LFSR_EPI_ACT32(LFSR_ACT_RELU) break;
+        case LFSR_ACT_LRELU: LFSR_EPI_ACT32(LFSR_ACT_LRELU) break;
+        case LFSR_ACT_SIGMOID: LFSR_EPI_ACT32(LFSR_ACT_SIGMOID) break;
+        case LFSR_ACT_GELU: LFSR_EPI_ACT32(LFSR_ACT_GELU) break;
+        case LFSR_ACT_SILU: LFSR_EPI_ACT32(LFSR_ACT_SILU) break;
+        default: break;
+      }
+#undef LFSR_EPI_ACT32
+      // rows >= cq of the shared-memory table are zero, so the columns a short last block shares with the next
+      // sub-pixel contribute nothing
+      const float4* wt = reinterpret_cast<const float4*>(sTail + c0 * 12);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float4 w0 = wt[3 * k], w1 = wt[3 * k + 1], w2 = wt[3 * k + 2];
+        const float a = v[k] * p.alpha;
+        r[0] = fmaf(a, w0.x, r[0]); r[1] = fmaf(a, w0.y, r[1]); r[2] = fmaf(a, w0.z, r[2]); r[3] = fmaf(a, w0.w, r[3]);
+        r[4] = fmaf(a, w1.x, r[4]); r[5] = fmaf(a, w1.y, r[5]); r[6] = fmaf(a, w1.z, r[6]); r[7] = fmaf(a, w1.w, r[7]);
+        r[8] = fmaf(a, w2.x, r[8]); r[9] = fmaf(a, w2.y, r[9]); r[10] = fmaf(a, w2.z, r[10]); r[11] = fmaf(a, w2.w, r[11]);
+      }
+    }
+    if (pix_ok) {
+      const int si = fdiv(sub, p.fd_rx), sj = sub - si * p.rx;
+      float4* dst = reinterpret_cast<float4*>(p.out.p + p.out.pix(img, Y * p.ry + si, X * p.rx + sj));
+      dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+      dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+      dst[2] = make_float4(r[8], r[9], r[10], r[11]);
+    }
+  }
+}
+
 // (register files are allocated for 4-warp groups: 320 threads cost what 384 do, i.e. at most 168 registers each)
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -619,7 +685,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int taps = p.kh * p.kw;
   const int nks = taps * p.cgs;
   float* sEpi = reinterpret_cast<float*>(sB + (p.resident ? nks : p.stages * p.kps) * p.b_stage_bytes);   // 8 warps x 4 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + kEpiWarps * 1024);
+  float* sTail = sEpi + kEpiWarps * 1024;                                                                  // tail_rows x 12
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sTail + p.tail_rows * 12);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
@@ -629,6 +696,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  for (int i = threadIdx.x; i < p.tail_rows * 12; i += kThreads) sTail[i] = i < p.cq * 12 ? __ldg(p.tail_w + i) : 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, p.pair ? 2 : 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, kEpiWarps); }
@@ -780,7 +848,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const TileCoord tc_ = decode_tile(p, m_, chunk_);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccStride;
       long long tw1 = 0;
-      if (p.tma_epi && m_ >= 0) {
+      if (p.tail_w && m_ >= 0) {
+        epilogue_tile_tail(p, sTail, taddr, lane, q, tc_, half, 2, tfull + a, aph);
+      } else if (p.tma_epi && m_ >= 0) {
         if (p.dbg) tw1 = clock64();
         epilogue_tile_tma(p, &tmO, stg, taddr, lane, q, tc_, half, 2, tfull + a, aph);
         if (p.dbg) dbg_epi += clock64() - tw1;
@@ -1093,8 +1163,13 @@ static bool tc_geometry_ok(const lfsr_tensor* in, const lfsr_tensor* out, const 
     if (sh > 1 && sw > 1 && (d->pad_h || d->pad_w)) return false;         // image and row-block share one TMA dim there
     if (sh > 8 || sw > 8) return false;
   }
-  const int cout = out->c * ry * rx;
+  const int cout = (d->tail_w ? d->tail_c : out->c) * ry * rx;
   if (cout < 1) return false;
+  if (d->tail_w) {      // tail projection: one cout-chunk whose sub-pixel blocks stay inside a 256-column accumulator stage
+    if (ry * rx < 2 || d->tail_c < 4 || d->tail_c % 4 || d->tail_taps < 1 || d->tail_taps > 12 || out->c != d->tail_taps) return false;
+    if (cout > 256 || (cout > 240 && d->tail_c % 32) || out->ld < 12 || out->ld % 4 || ((uintptr_t)out->ptr & 15) || ((uintptr_t)d->tail_w & 15)) return false;
+    if (d->res.ptr || d->mul.ptr || sh > 1 || sw > 1 || d->block_h > 0 || d->block_w > 0) return false;
+  }
   const int bh = d->block_h > 0 ? d->block_h : in->h, bw = d->block_w > 0 ? d->block_w : in->w;
   if (in->h % bh || in->w % bw) return false;
   if ((long long)in->n * (in->h / bh) > 0x7fffffffLL) return false;
@@ -1134,7 +1209,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
       else { to[0] = (short)rx_; to[1] = (short)ax; to[2] = (short)ry_; to[3] = (short)ay; }
     }
   p.C = in->c; p.kh = d->kh; p.kw = d->kw; p.dil_h = d->dil_h; p.dil_w = d->dil_w; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
-  p.cout = out->c * ry * rx;
+  p.cout = (d->tail_w ? d->tail_c : out->c) * ry * rx;
   const Plan pl = plan_for(p.C, p.cout);
   p.NC = pl.NC; p.nchunks = pl.nchunks; p.cgs = pl.cgs;
   p.out = view_of(out);
@@ -1148,7 +1223,10 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
                  "lfsr_conv2d_tc: mul tensor geometry");
   LFSR_REQUIRE((long long)out->h * out->w * out->ld < 0x7fffffffLL, "lfsr_conv2d_tc: output image too large for 32-bit pitches");
   p.bias = d->bias; p.act = d->act; p.slope = d->act_slope; p.alpha = d->alpha; p.mul_act = d->mul_act;
-  p.ry = ry; p.rx = rx; p.shuf_mode = d->shuf_mode; p.cq = out->c;
+  p.ry = ry; p.rx = rx; p.shuf_mode = d->shuf_mode; p.cq = d->tail_w ? d->tail_c : out->c;
+  p.tail_w = d->tail_w; p.tail_rows = d->tail_w ? (d->tail_c + 31) / 32 * 32 : 0;
+  // (a short last block of a sub-pixel run reads up to 31 accumulator columns past it: keep that inside the 256-column stage)
+  if (d->tail_w) LFSR_REQUIRE(p.nchunks == 1 && (p.NC <= 240 || p.cq % 32 == 0), "lfsr_conv2d_tc: tail projection needs a single cout chunk");
   p.fd_cq = make_fastdiv(p.cq); p.fd_nby = make_fastdiv(p.nby); p.fd_nbx = make_fastdiv(p.nbx); p.fd_rx = make_fastdiv(rx);
   p.vec = 1;
   for (int v = 2; v <= 4; v *= 2) {
@@ -1176,7 +1254,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   // Measured on B200 (profiles/r01_notes.md): correct, but not yet faster than the per-tap kernel below - the single
   // accumulator stage at N = 224 serialises epilogue and MMAs - so it is opt-in (LFSR_TC_HALO=1) until that is fixed.
   static const bool use_halo = getenv("LFSR_TC_HALO") != nullptr;
-  if (use_halo && d->w_batch_stride <= 0 && p.kh * p.kw > 1 && p.cgs <= 2 && p.nchunks == 1) {
+  if (use_halo && !d->tail_w && d->w_batch_stride <= 0 && p.kh * p.kw > 1 && p.cgs <= 2 && p.nchunks == 1) {
     const int taps = p.kh * p.kw, nks = taps * p.cgs;
     const int kSmemAvail = 227 * 1024 - 1024 - 512 - 16 * 1024;
     const int TWo = p.bw < 32 ? p.bw : 32;
@@ -1264,7 +1342,8 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   p.m_tiles = (int)(tiles / p.nchunks);
   p.fd_tiles_x = make_fastdiv(p.tiles_x); p.fd_tiles_y = make_fastdiv(p.tiles_y); p.fd_nchunks = make_fastdiv(p.nchunks);
   const int nks = p.kh * p.kw * p.cgs;
-  const int kSmemMax = 227 * 1024 - 1024 - 256 - kEpiWarps * 4096;  // minus alignment slack, barriers, epilogue staging
+  const int tail_bytes = p.tail_rows * 48;
+  const int kSmemMax = 227 * 1024 - 1024 - 256 - kEpiWarps * 4096 - tail_bytes;  // minus alignment slack, barriers, epilogue staging, tail table
   const long long b_all = (long long)nks * p.b_stage_bytes;
   // Plan = (weights resident?, K-stages per smem stage). Preference: one tap with all its channel groups per stage
   // (short unrolled issue stream, fewer barrier round trips) with enough stages in flight; weights resident when
@@ -1274,7 +1353,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   static const int kps_env = getenv("LFSR_TC_KPS") ? atoi(getenv("LFSR_TC_KPS")) : 0;
   auto stages_for = [&](bool res, int kps) -> int {
     if (res) return b_all >= kSmemMax ? 0 : (int)((kSmemMax - b_all) / ((long long)kps * kABytes));
-    return (kSmemBudget - kEpiWarps * 4096) / (kps * (kABytes + p.b_stage_bytes));
+    return (kSmemBudget - kEpiWarps * 4096 - tail_bytes) / (kps * (kABytes + p.b_stage_bytes));
   };
   // narrow layers (N <= 64) are bound by the per-stage barrier round trip of the issuing thread: pack up to 4
   // K-stages (whole taps) into one smem stage; wide layers keep one tap per stage so that >= 3 stages fit
@@ -1340,7 +1419,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
     if (r != CUDA_SUCCESS) { set_error("lfsr_conv2d_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return LFSR_ERR_CUDA; }
   }
   const size_t smem = 1024 + (size_t)p.stages * p.kps * kABytes + (size_t)(p.resident ? nks : p.stages * p.kps) * p.b_stage_bytes +
-                      kEpiWarps * 4096 + (2 * kMaxStages + 5) * 8 + 16;
+                      kEpiWarps * 4096 + (size_t)tail_bytes + (2 * kMaxStages + 5) * 8 + 16;
   LFSR_REQUIRE(smem <= 227 * 1024, "lfsr_conv2d_tc: shared memory plan too large");
   int grid = p.total_tiles < sm_count ? p.total_tiles : sm_count;
   if (p.resident && p.nchunks > 1) {

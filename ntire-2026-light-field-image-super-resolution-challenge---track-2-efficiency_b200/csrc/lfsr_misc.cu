@@ -179,6 +179,26 @@ scale_add_kernel(TView x, const float* __restrict__ scale, int scale_ld, TView r
   }
 }
 
+// ---- second half of a KxK conv to one channel: sum of the per-tap responses at the shifted positions
+__global__ void __launch_bounds__(256)
+tap_gather_kernel(TView taps, TView res, TView out, int kh, int kw, const float* __restrict__ bias) {
+  const int img = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= out.w || y >= out.h) return;
+  float acc = bias ? __ldg(bias) : 0.f;
+  for (int ky = 0; ky < kh; ++ky) {
+    const int iy = y + ky - kh / 2;
+    if (iy < 0 || iy >= taps.h) continue;
+    for (int kx = 0; kx < kw; ++kx) {
+      const int ix = x + kx - kw / 2;
+      if (ix < 0 || ix >= taps.w) continue;
+      acc += __ldg(taps.p + taps.pix(img, iy, ix) + ky * kw + kx);
+    }
+  }
+  if (res.p) acc += res.p[res.pix(img, y, x)];
+  out.p[out.pix(img, y, x)] = acc;
+}
+
 // ---- LayerNorm over channels: one warp per token (EPIT.py:77,84)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(TView in, TView out, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -432,6 +452,20 @@ extern "C" int lfsr_scale_add(const lfsr_tensor* x, const lfsr_tensor* scale, co
   if (v4) scale_add_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(view_of(x), (const float*)scale->ptr, scale->ld, r, view_of(out));
   else scale_add_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(view_of(x), (const float*)scale->ptr, scale->ld, r, view_of(out));
   return check_launch("scale_add_kernel");
+}
+
+extern "C" int lfsr_tap_gather(const lfsr_tensor* taps, int kh, int kw, const float* bias, const lfsr_tensor* res,
+                               const lfsr_tensor* out, void* stream) {
+  LFSR_REQUIRE(tensor_ok(taps) && tensor_ok(out), "lfsr_tap_gather: null/invalid tensor");
+  LFSR_REQUIRE(kh > 0 && kw > 0 && (kh & 1) && (kw & 1) && taps->c == kh * kw, "lfsr_tap_gather: taps tensor must have kh*kw channels");
+  LFSR_REQUIRE(out->c == 1 && out->n == taps->n && out->h == taps->h && out->w == taps->w, "lfsr_tap_gather: out geometry");
+  const bool has_res = res && res->ptr;
+  if (has_res)
+    LFSR_REQUIRE(res->c == 1 && res->n == out->n && res->h == out->h && res->w == out->w, "lfsr_tap_gather: res geometry");
+  LFSR_REQUIRE(out->n <= 65535 && (long long)taps->h * taps->w * taps->ld < 0x7fffffffLL, "lfsr_tap_gather: tensor too large");
+  dim3 grid(ceil_div(out->w, 32), ceil_div(out->h, 8), out->n);
+  tap_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(taps), has_res ? view_of(res) : null_view(), view_of(out), kh, kw, bias);
+  return check_launch("tap_gather_kernel");
 }
 
 extern "C" int lfsr_layernorm(const lfsr_tensor* in, const float* gamma, const float* beta, float eps,

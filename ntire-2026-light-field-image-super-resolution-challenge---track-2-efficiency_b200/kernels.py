@@ -132,7 +132,9 @@ class CudaOps:
     # -- convolutions ---------------------------------------------------------------------------
     def conv(self, x, pc: PackedConv, out, act=N.ACT_NONE, slope=0.0, alpha=1.0, mul=None, mul_act=N.ACT_NONE, res=None,
              in_scale=None,
-             in_perm=0, out_perm=0, perm_a=0, shuffle=(1, 1, 0), block=(0, 0)):
+             in_perm=0, out_perm=0, perm_a=0, shuffle=(1, 1, 0), block=(0, 0), tail=None):
+        """tail = (tail_w [c][12] device tensor, taps, c): store the projection of the shuffled activation onto `taps`
+        vectors instead of the activation (lfsr_conv_desc.tail_w); tensor-core path only."""
         d = N.ConvDesc()
         d.kh, d.kw = pc.kh, pc.kw
         d.stride_h, d.stride_w = pc.stride
@@ -148,10 +150,17 @@ class CudaOps:
             d.in_scale_ld = in_scale.stride(0) if in_scale.shape[0] > 1 else pc.cin
         d.mul = as_tensor(mul, "conv.mul") if mul is not None else _NULL_T
         d.res = as_tensor(res, "conv.res") if res is not None else _NULL_T
+        if tail is not None:
+            d.tail_w, d.tail_taps, d.tail_c = tail[0].data_ptr(), tail[1], tail[2]
         tin, tout = as_tensor(x, "conv.in"), as_tensor(out, "conv.out")
         if x.shape[3] != pc.cin:
             raise N.LfsrError(f"conv: input has {x.shape[3]} channels, weights expect {pc.cin}")
         st = self._stream(x)
+        if tail is not None:
+            if not (self.use_tc and pc.w_tc is not None and self.lib.lfsr_conv2d_tc_supported(C.byref(tin), C.byref(tout), C.byref(d))):
+                raise N.LfsrError("conv: tail projection is only available on the tensor-core path (query tail_supported first)")
+            N.check(self.lib.lfsr_conv2d_tc(C.byref(tin), pc.w_tc.data_ptr(), C.byref(tout), C.byref(d), st), "lfsr_conv2d_tc")
+            return
         if pc.cout <= 4 and self.lib.lfsr_conv2d_small_cout_supported(C.byref(tin), C.byref(tout), C.byref(d)):
             N.check(self.lib.lfsr_conv2d_small_cout(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st),
                     "lfsr_conv2d_small_cout")
@@ -181,6 +190,16 @@ class CudaOps:
         else:
             N.check(self.lib.lfsr_conv2d_f32(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st),
                     "lfsr_conv2d_f32")
+
+    def tail_supported(self, pc: PackedConv, cq: int, shuffle) -> bool:
+        """can `pc` (a conv + PixelShuffle to cq channels) end in a tail projection on this backend?"""
+        return bool(self.use_tc and pc.w_tc is not None and shuffle[0] * shuffle[1] > 1 and cq % 4 == 0
+                    and (pc.cout <= 240 or (pc.cout <= 256 and cq % 32 == 0)) and pc.stride == (1, 1))
+
+    def tap_gather(self, taps, kh, kw, bias, res, out):
+        rt = as_tensor(res, "tap_gather.res") if res is not None else _NULL_T
+        N.check(self.lib.lfsr_tap_gather(C.byref(as_tensor(taps, "tap_gather.taps")), kh, kw, self._ptr(bias), C.byref(rt),
+                                         C.byref(as_tensor(out, "tap_gather.out")), self._stream(taps)), "lfsr_tap_gather")
 
     def dwconv(self, x, w, out, kh, kw, dil=(1, 1), scale=None, shift=None, act=N.ACT_NONE, slope=0.0):
         N.check(self.lib.lfsr_dwconv_f32(C.byref(as_tensor(x, "dwconv.in")), w.data_ptr(), self._ptr(scale),

@@ -33,6 +33,33 @@ def bn_affine(bn: nn.BatchNorm2d):
     return scale, shift
 
 
+def tail_table(w_head: torch.Tensor, channels: int, device) -> torch.Tensor:
+    """[channels][12] projection table of a 3x3 reconstruction conv to one channel (weight [1, c, 3, 3], c <= channels):
+    column ky*3+kx holds W[0, :, ky, kx]; used as lfsr_conv_desc.tail_w by the last upsampler conv."""
+    w = w_head.detach().float().cpu()
+    t = torch.zeros(channels, 12, dtype=torch.float32)
+    t[: w.shape[1], :9] = w[0].reshape(w.shape[1], 9)
+    return t.contiguous().to(device)
+
+
+def upsample_tail(net, ops, pk, cur, ch, cw, Y, width, LR, shuf_mode):
+    """PixelShuffleUpsampler stages + 3x3 head + skip (MyEfficientLFNet.py:104-109, MyEfficientLFNetV4_5.py:100-109).
+    The last stage does not write its `width`-channel activation: its epilogue projects every output pixel onto the 9
+    taps of the head conv and lfsr_tap_gather sums the shifted responses onto the interpolated skip already in Y."""
+    n_up = len(pk["up"])
+    for j, (pcv, r) in enumerate(pk["up"]):
+        shuffle = (r, r, shuf_mode)
+        if j == n_up - 1 and pk.get("tail_w") is not None and ops.tail_supported(pcv, width, shuffle):
+            taps = net._buf("head_taps", cur.shape[0], ch * r, cw * r, 9, cur.device)
+            ops.conv(cur, pcv, taps, act=LR, slope=0.1, shuffle=shuffle, tail=(pk["tail_w"], 9, width))
+            ops.tap_gather(taps, 3, 3, pk["out"].bias, Y, Y)
+            return
+        nb = net._buf(f"up{j}", cur.shape[0], ch * r, cw * r, width, cur.device)
+        ops.conv(cur, pcv, nb, act=LR, slope=0.1, shuffle=shuffle)
+        cur, ch, cw = nb, ch * r, cw * r
+    ops.conv(cur, pk["out"], Y, res=Y)
+
+
 class LFNetBase(nn.Module):
     """forward(x[B,1,A*h,A*w] float32 cuda, info=None) -> [B,1,A*h*s,A*w*s] (train.py:291-313)."""
 

@@ -26,7 +26,7 @@ import torch.nn as nn
 
 from .. import _native as N
 from .. import kernels as K
-from .common import LFNetBase, bn_affine, slots
+from .common import LFNetBase, bn_affine, slots, tail_table, upsample_tail
 
 
 def _conv(cin, cout, k, **kw):
@@ -240,6 +240,7 @@ class get_model(LFNetBase):
         pk["up"] = ups
         pk["out"] = pc(pad_ch(self.output_conv.weight.detach().float().cpu(), 1), self.output_conv.bias, pad=(1, 1))
         pk["CU"] = CU
+        pk["tail_w"] = tail_table(self.output_conv.weight, CU, device)
         return pk
 
     # -- run ------------------------------------------------------------------------------------------
@@ -300,12 +301,7 @@ class get_model(LFNetBase):
             feat = nxt
         ops.conv(feat, pk["gf0"], fu1, act=LR, slope=0.1)
         ops.conv(fu1, pk["gf2"], fu2, res=shallow)
-        cur, ch, cw = fu2, H, W
-        for j, (pcv, r) in enumerate(pk["up"]):
-            nb = buf(f"up{j}", ch * r, cw * r, pk["CU"])
-            ops.conv(cur, pcv, nb, act=LR, slope=0.1, shuffle=(r, r, N.SHUF_CHANNEL_MAJOR))
-            cur, ch, cw = nb, ch * r, cw * r
-        ops.conv(cur, pk["out"], Y, res=Y)
+        upsample_tail(self, ops, pk, fu2, H, W, Y, pk["CU"], LR, N.SHUF_CHANNEL_MAJOR)
 
     # -- measurement hook --------------------------------------------------------------------------
     def dominant_kernel(self, batch: int, h: int = 32):
@@ -320,15 +316,27 @@ class get_model(LFNetBase):
         hin = A * h * (self.scale // r)
         src = self._buf(f"up{len(pk['up']) - 2}", batch, hin, hin, pcv.cin, dev) if len(pk["up"]) > 1 else \
             self._buf("fu2", batch, hin, hin, pcv.cin, dev)
-        dst = self._buf(f"up{len(pk['up']) - 1}", batch, hin * r, hin * r, pk["CU"], dev)
+        shuffle = (r, r, N.SHUF_CHANNEL_MAJOR)
+        conv_bytes = batch * (hin * hin * C + hin * r * hin * r * C) * 4 + pcv.kh * pcv.kw * C * C * r * r * 4
         info = {
             "name": "conv3x3 %d->%d + PixelShuffle(%d) + LReLU @%dx%d (upsampler.up.%s)" % (C, C * r * r, r, hin, hin,
                                                                                         self.upsampler.steps[-1][0]),
             # algorithmic figures use the reference layer's real 54 -> 216 channels, not the padded buffers
-            "bytes": batch * (hin * hin * C + hin * r * hin * r * C) * 4 + pcv.kh * pcv.kw * C * C * r * r * 4,
+            "bytes": conv_bytes,
             "flops": 2 * batch * hin * hin * pcv.kh * pcv.kw * C * C * r * r,
         }
-        return (lambda: ops.conv(src, pcv, dst, act=N.ACT_LRELU, slope=0.1, shuffle=(r, r, N.SHUF_CHANNEL_MAJOR))), info
+        if pk.get("tail_w") is not None and ops.tail_supported(pcv, pk["CU"], shuffle):
+            # the forward runs this layer with the head conv's channel contraction in its epilogue (common.upsample_tail):
+            # per-layer bytes of what the kernel covers = this layer + the head conv's input read and weights
+            dst = self._buf("head_taps", batch, hin * r, hin * r, 9, dev)
+            info["name"] += " + 3x3 head-conv tap projection (output_conv) fused in the epilogue"
+            info["bytes_conv_layer_only"] = conv_bytes
+            info["bytes"] = conv_bytes + batch * hin * r * hin * r * C * 4 + 9 * C * 4
+            info["flops"] += 2 * batch * hin * r * hin * r * 9 * C
+            tail = (pk["tail_w"], 9, pk["CU"])
+            return (lambda: ops.conv(src, pcv, dst, act=N.ACT_LRELU, slope=0.1, shuffle=shuffle, tail=tail)), info
+        dst = self._buf(f"up{len(pk['up']) - 1}", batch, hin * r, hin * r, pk["CU"], dev)
+        return (lambda: ops.conv(src, pcv, dst, act=N.ACT_LRELU, slope=0.1, shuffle=shuffle)), info
 
 
 class get_loss(nn.Module):

@@ -29,7 +29,7 @@ import torch.nn.functional as F
 
 from .. import _native as N
 from .. import kernels as K
-from .common import LFNetBase, bn_affine, slots
+from .common import LFNetBase, bn_affine, slots, tail_table, upsample_tail
 
 
 def _c(cin, cout, k, bias=False, **kw):
@@ -159,6 +159,7 @@ class get_model(LFNetBase):
         pk["up"] = [(pc(self.upsampler.up[str(i)].weight, pad=(1, 1), tc=True, tc_shuffle=(r, r, N.SHUF_CHANNEL_MAJOR)), r)
                     for i, r in self.upsampler.steps]
         pk["out"] = pc(self.output.weight, self.output.bias, pad=(1, 1))
+        pk["tail_w"] = tail_table(self.output.weight, self.channels, device)
         return pk
 
     # -- run ---------------------------------------------------------------------------------------------
@@ -212,12 +213,7 @@ class get_model(LFNetBase):
         ops.conv(late, pk["fuse_late"], el[..., C:2 * C])
         ops.conv(el, pk["fuse_final"], f0, res=shallow)
         ops.conv(f0, pk["refine"], f1, act=LR, slope=0.1)
-        cur, ch, cw = f1, H, W
-        for j, (pcv, r) in enumerate(pk["up"]):
-            nbuf = buf(f"up{j}", ch * r, cw * r, C)
-            ops.conv(cur, pcv, nbuf, act=LR, slope=0.1, shuffle=(r, r, N.SHUF_CHANNEL_MAJOR))
-            cur, ch, cw = nbuf, ch * r, cw * r
-        ops.conv(cur, pk["out"], Y, res=Y)
+        upsample_tail(self, ops, pk, f1, H, W, Y, C, LR, N.SHUF_CHANNEL_MAJOR)
 
 
 class get_loss(nn.Module):

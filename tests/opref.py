@@ -63,7 +63,7 @@ class RefOps:
 
     # -- convolutions ------------------------------------------------------------------------------
     def conv(self, x, pc, out, act=0, slope=0.0, alpha=1.0, mul=None, mul_act=0, res=None, in_scale=None, in_perm=0, out_perm=0,
-             perm_a=0, shuffle=(1, 1, 0), block=(0, 0)):
+             perm_a=0, shuffle=(1, 1, 0), block=(0, 0), tail=None):
         n = x.shape[0]
         xi = _nchw(x)
         if in_perm:
@@ -95,6 +95,23 @@ class RefOps:
             else:
                 y = y.reshape(b_, ry, rx, cq, h_, w_).permute(0, 3, 4, 1, 5, 2)
             y = y.reshape(b_, cq, h_ * ry, w_ * rx)
+        if res is not None:
+            y = y + _nchw(res)
+        if tail is not None:
+            tw, taps, c = tail
+            y = torch.einsum("bchw,ct->bthw", y, tw[:c, :taps])
+        out.copy_(y.permute(0, 2, 3, 1))
+
+    def tail_supported(self, pc, cq, shuffle):
+        return shuffle[0] * shuffle[1] > 1 and cq % 4 == 0
+
+    def tap_gather(self, taps, kh, kw, bias, res, out):
+        t = _nchw(taps)
+        n, _, h, w = t.shape
+        tp = F.pad(t, (kw // 2, kw // 2, kh // 2, kh // 2))
+        y = sum(tp[:, ky * kw + kx, ky:ky + h, kx:kx + w] for ky in range(kh) for kx in range(kw)).unsqueeze(1)
+        if bias is not None:
+            y = y + bias.view(1, 1, 1, 1)
         if res is not None:
             y = y + _nchw(res)
         out.copy_(y.permute(0, 2, 3, 1))

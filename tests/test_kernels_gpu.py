@@ -454,3 +454,39 @@ def test_conv_tc_per_sample_gate(ref):
     assert tc_ops.lib.lfsr_launch_count() == l0 + 2          # scale-pack + tcgen05 conv, no fp32 fallback
     ref.conv(x, pc, b, act=2, slope=0.1, in_scale=gate)
     assert (a - b).abs().max().item() <= 2e-3
+
+
+@pytest.mark.parametrize("cin,cq,hw,bias", [(56, 56, (80, 80), True), (64, 64, (40, 48), False), (56, 56, (37, 45), False)])
+def test_conv_tc_tail_projection_and_tap_gather(ref, cin, cq, hw, bias):
+    """last upsampler conv + PixelShuffle + LReLU with the 3x3 head conv's channel contraction in its epilogue, then the
+    9-tap gather (MyEfficientLFNet.py:104-109): equals conv -> shuffle -> act -> conv3x3(cq->1) + bias + skip"""
+    tc_ops = K.CudaOps(use_tc=True)
+    n, (h, w), r = 2, hw, 2
+    g = torch.Generator().manual_seed(cin + cq)
+    wt = (torch.rand(cq * r * r, cin, 3, 3, generator=g) - 0.5) * (2.0 / (cin * 9) ** 0.5)
+    b = (torch.rand(cq * r * r, generator=g) - 0.5) if bias else None
+    pc = K.pack_conv(wt, b, pad=(1, 1), device=DEV, tc=True, tc_shuffle=(r, r, 0))
+    head = (torch.rand(1, cq, 3, 3, generator=g) - 0.5) * 0.2
+    tw = torch.zeros(cq, 12)
+    tw[:, :9] = head[0].reshape(cq, 9)
+    tw = tw.to(DEV)
+    hb = torch.tensor([0.125], device=DEV)
+    x = nhwc(n, h, w, cin, seed=3)
+    assert tc_ops.tail_supported(pc, cq, (r, r, 0))
+    ta, tb = nhwc(n, h * r, w * r, 9, seed=4), nhwc(n, h * r, w * r, 9, seed=4)
+    kw = dict(act=2, slope=0.1, shuffle=(r, r, 0), tail=(tw, 9, cq))
+    l0 = tc_ops.lib.lfsr_launch_count()
+    tc_ops.conv(x, pc, ta, **kw)
+    assert tc_ops.lib.lfsr_launch_count() == l0 + 1
+    ref.conv(x, pc, tb, **kw)
+    assert (ta - tb).abs().max().item() <= 2e-3
+    ya, yb = rnd(n, h * r, w * r, 1, seed=5), rnd(n, h * r, w * r, 1, seed=5)
+    tc_ops.tap_gather(ta, 3, 3, hb, ya, ya)
+    ref.tap_gather(ta, 3, 3, hb, yb.clone(), yb)
+    assert (ya - yb).abs().max().item() <= 1e-5
+    # and the whole thing against the unfused layer pair
+    full = nhwc(n, h * r, w * r, cq, seed=6)
+    ref.conv(x, pc, full, act=2, slope=0.1, shuffle=(r, r, 0))
+    y2 = rnd(n, h * r, w * r, 1, seed=5)
+    ref.conv(full, K.pack_conv(head, hb, pad=(1, 1), device=DEV), y2, res=y2.clone())
+    assert (ya - y2).abs().max().item() <= 2e-3
