@@ -171,6 +171,16 @@ class get_model(LFNetBase):
                                                  device=device, **kw)
         dil = dict(dil=(A, A), pad=(A, A))
         dev_t = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+        def pad_out(w, b=None):
+            """zero output rows up to a multiple of 4 channels: the layer then writes its pad floats too (with zeros, the
+            value they must hold) and qualifies for the 16-byte-granular TMA-store epilogue"""
+            w = w.detach().float().cpu()
+            n = (w.shape[0] + 3) // 4 * 4 - w.shape[0]
+            if n:
+                w = torch.cat([w, w.new_zeros((n,) + tuple(w.shape[1:]))], 0)
+                b = None if b is None else torch.cat([b.detach().float().cpu(), torch.zeros(n)])
+            return w, b
         pk = {}
         w, b = self.shallow_feat.merged()
         pk["stem"] = pc(self._exp(w, 0), self._exp(b, 0), **dil)
@@ -178,8 +188,8 @@ class get_model(LFNetBase):
         for st in self.stages:
             s = {}
             w, b = st.spatial_branch["0"].merged()
-            s["spa0"] = pc(w, b, tc=True, **dil)
-            s["spa2"] = pc(st.spatial_branch["2"].weight, tc=True, **dil)
+            s["spa0"] = pc(*pad_out(w, b), tc=True, **dil)
+            s["spa2"] = pc(*pad_out(st.spatial_branch["2"].weight), tc=True, **dil)
             ab = st.angular_branch
             s["ang_to"] = pc(ab.to_angular.weight, stride=(A, A), tc=True)
             s["ang_a0"] = pc(ab.attention["0"].weight)
@@ -204,7 +214,7 @@ class get_model(LFNetBase):
                 gw[g * gs:g * gs + n, g * gs:g * gs + n] = gate["1"].weight.detach().float().cpu()
                 gb[g * gs:g * gs + n] = gate["1"].bias.detach().float().cpu()
             s["gate"] = pc(gw, gb)
-            s["fus0"] = pc(self._exp(st.fusion["0"].weight.detach().float().cpu(), 1), tc=True)
+            s["fus0"] = pc(*pad_out(self._exp(st.fusion["0"].weight.detach().float().cpu(), 1)), tc=True)
             s["fus2"] = pc(self._exp(st.fusion["2"].weight.detach().float().cpu(), 0), tc=True, **dil)
             sm = st.sa_modulator
             s["sa_dw"] = dev_t(self._exp(_dw_pack(sm.spatial_mod["0"].weight, "cpu"), 1))
@@ -217,7 +227,7 @@ class get_model(LFNetBase):
             s["sa_w"] = (float(wts[0]), float(wts[1]))
             stages.append(s)
         pk["stages"] = stages
-        pk["gf0"] = pc(self._exp(self.global_fusion["0"].weight.detach().float().cpu(), 1), tc=True)
+        pk["gf0"] = pc(*pad_out(self._exp(self.global_fusion["0"].weight.detach().float().cpu(), 1)), tc=True)
         w, b = self.global_fusion["2"].merged()
         pk["gf2"] = pc(self._exp(w.float().cpu(), 0), self._exp(b.float().cpu(), 0), tc=True, **dil)
         # upsampler activations carry CU = 56 channels (54 + 2 zero): 128-bit epilogue stores, and 4*56 = 224 is
@@ -264,18 +274,19 @@ class get_model(LFNetBase):
         pp = [buf("feat_a", H, W, CP), buf("feat_b", H, W, CP)]
         hA, wA = H // A, W // A
         cat = buf("cat", H, W, CP)
-        t18 = buf("t18", H, W, c0)
+        t18 = buf("t18", H, W, gs)                 # c0 real channels + zero pad, written whole by spa0
         hid = pk["stages"][0]["ang_a0"].cout
         ang1, ang4, ang5 = buf("ang1", hA, wA, c0), buf("ang4", hA, wA, c0), buf("ang5", hA, wA, c0)
         ang2, ang3 = buf("ang2", hA, wA, hid), buf("ang3", hA, wA, hid)
         vmean, gmean, gate = buf("vmean", A, A, CP), buf("gmean", 1, 1, CP), buf("gate", 1, 1, CP)
-        fu1, fu2 = buf("fu1", H, W, C), buf("fu2", H, W, CP)
+        CU = pk["CU"]
+        fu1, fu2 = buf("fu1", H, W, CU), buf("fu2", H, W, CP)
         pm, am1, am = buf("pm", A, A, CP), buf("am1", A, A, C // 4), buf("am", A, A, CP)
         for i, st in enumerate(pk["stages"]):
             xs, xa, xe = feat[..., sl[0]], feat[..., sl[1]], feat[..., sl[2]]
             # spatial branch
             ops.conv(xs, st["spa0"], t18, act=LR, slope=0.1)
-            ops.conv(t18, st["spa2"], cat[..., sl[0]])
+            ops.conv(t18[..., 0:c0], st["spa2"], cat[..., 0:gs])
             # angular branch
             ops.conv(xa, st["ang_to"], ang1)
             ops.conv(ang1, st["ang_a0"], ang2, act=N.ACT_RELU)
@@ -291,7 +302,7 @@ class get_model(LFNetBase):
             ops.block_mean(vmean, gmean, A, A)
             ops.conv(gmean, st["gate"], gate, act=N.ACT_SIGMOID)
             ops.conv(cat, st["fus0"], fu1, act=LR, slope=0.1, in_scale=gate)
-            ops.conv(fu1, st["fus2"], fu2)
+            ops.conv(fu1[..., 0:C], st["fus2"], fu2)
             # SA modulator + stage residual
             ops.block_mean(fu2, pm, hA, wA)
             ops.conv(pm, st["sa_c0"], am1, act=N.ACT_RELU)
@@ -300,7 +311,7 @@ class get_model(LFNetBase):
             ops.sa_modulate(fu2, st["sa_dw"], st["sa_bns"], st["sa_bnb"], am, st["sa_w"][0], st["sa_w"][1], feat, nxt, A)
             feat = nxt
         ops.conv(feat, pk["gf0"], fu1, act=LR, slope=0.1)
-        ops.conv(fu1, pk["gf2"], fu2, res=shallow)
+        ops.conv(fu1[..., 0:C], pk["gf2"], fu2, res=shallow)
         upsample_tail(self, ops, pk, fu2, H, W, Y, pk["CU"], LR, N.SHUF_CHANNEL_MAJOR)
 
     # -- measurement hook --------------------------------------------------------------------------
