@@ -54,11 +54,26 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   switch (act) {
     case LFSR_ACT_RELU: return v > 0.f ? v : 0.f;
     case LFSR_ACT_LRELU: return v > 0.f ? v : v * slope;
-    case LFSR_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    case LFSR_ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-v));
     case LFSR_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
-    case LFSR_ACT_SILU: return v / (1.f + __expf(-v));
+    case LFSR_ACT_SILU: return __fdividef(v, 1.f + __expf(-v));
     default: return v;
   }
+}
+
+// packed 2 x fp32 FMA (FFMA2 on sm_100): each half is an ordinary fma.rn, so results equal two scalar FMAs bit for bit
+// while the issue-bound CUDA-core kernels retire half as many instructions
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
 }
 
 // MacPI (i*A+u, j*A+v) logical coordinate -> SAI (u*hh+i, v*ww+j) storage coordinate,

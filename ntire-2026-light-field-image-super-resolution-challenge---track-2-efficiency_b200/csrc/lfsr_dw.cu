@@ -1,16 +1,20 @@
 // Depthwise convolutions (groups == channels) of the SR networks, NHWC fp32, sm_100a.
 //
-//   dw_tile_kernel   channel counts that are multiples of 16 on 16-byte aligned rows (the 64-channel trunks):
-//                    one CTA = one 16x32 output tile x 16 channels of one branch. The tile plus its dilation
+//   dw_tile_kernel   channel counts that are multiples of 4 on 16-byte aligned rows (the 64- and 60-channel trunks):
+//                    one CTA = one 16x32 output tile x (up to) 16 channels of one branch. The tile plus its dilation
 //                    halo is staged once in shared memory with 16-byte cp.async (out-of-image pixels zero
 //                    filled = the conv's zero padding), each thread then owns one channel quad (float4) of one
 //                    pixel column and walks the tile rows; a warp reads 8 pixels x 64 B = 512 contiguous bytes
 //                    per tap, conflict-free. Several branches (different taps / dilations / channel windows)
 //                    share one launch: MultiScaleSpatial's 1/3/5/7 kernels on four 16-channel slices and
-//                    FastConvSSM's four dilations of one input (MyEfficientLFNetV4_5.py:218-221, :268-271).
+//                    FastConvSSM's four dilations of one input (MyEfficientLFNetV4_5.py:218-221, :268-271). With
+//                    DwParams::sa the epilogue is the SA-modulator tail of the Track-2 model (lfsr_sa_modulate).
 //   dwconv_kernel    anything else (18-channel groups of the Track-2 model): one thread per pixel x channel.
 //
 // HBM-bound: algorithmic traffic is one read of the input window and one write per branch output.
+#include <cuda.h>
+#include <stdlib.h>
+#include <mutex>
 #include "lfsr_common.cuh"
 
 namespace lfsr {
@@ -59,6 +63,16 @@ struct DwParams {
   TView in, out;
   DwBranch br[DW_MAXB];
   int nbr, tiles_x, w_floats;   // w_floats: shared-memory floats reserved for the taps ahead of the tile
+  // SA-modulator tail (MyEfficientLFNet.py:495-515, :207): with s = act(affine(dw(x))) the kernel stores
+  // x * (sa_w0 * s + sa_w1 * amod[view of the pixel]) + res instead of s
+  int sa;
+  float sa_w0, sa_w1;
+  TView amod, res;
+  // use_tma: the halo'd tile of branch b is fetched by ONE thread with a 4-D tensor load through tm[b] (box = 16 channels
+  // x tile+halo, out-of-image elements zero filled) instead of ~25 cp.async per thread: staging cost as many
+  // instructions as the stencil itself and the kernel is issue-bound at its low (shared-memory limited) occupancy
+  int use_tma, tile_floats;
+  CUtensorMap tm[DW_MAXB];
 };
 
 __device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, bool ok) {
@@ -67,8 +81,23 @@ __device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, b
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
 }
 
-__device__ __forceinline__ void fma4(float4& a, const float4& v, const float4& w) {
-  a.x = fmaf(v.x, w.x, a.x); a.y = fmaf(v.y, w.y, a.y); a.z = fmaf(v.z, w.z, a.z); a.w = fmaf(v.w, w.w, a.w);
+__device__ __forceinline__ uint32_t dw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dw_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = dw_smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 26); ++it) {      // bounded: a protocol bug must fault, not hang the GPU
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+// float4 accumulators live as two packed pairs: acc += v * w costs two FFMA2
+struct Acc4 { f32x2 lo, hi; };
+__device__ __forceinline__ void fma4(Acc4& a, const float4& v, const float4& w) {
+  a.lo = fma2(pack2(v.x, v.y), pack2(w.x, w.y), a.lo);
+  a.hi = fma2(pack2(v.z, v.w), pack2(w.z, w.w), a.hi);
 }
 
 template <int KH, int KW>   // 0,0 = runtime kernel size, taps read from shared memory
@@ -78,7 +107,7 @@ __device__ __forceinline__ void dw_compute(const DwParams& p, const DwBranch& B,
   const int q = tid & 3, lx = (tid >> 2) & 31, ly0 = tid >> 7;
   const int kh = KH ? KH : B.kh, kw = KW ? KW : B.kw;
   const int ox = tx0 + lx;
-  if (ox >= p.in.w) return;
+  if (ox >= p.in.w || wofs + q * 4 >= B.c) return;
   float4 wr[KH * KW ? KH * KW : 1];
   if (KH) {
 #pragma unroll
@@ -91,32 +120,51 @@ __device__ __forceinline__ void dw_compute(const DwParams& p, const DwBranch& B,
   }
   const int row_f = SW * DW_CH;
   const int dyf = B.dh * row_f, dxf = B.dw * DW_CH;
+  // SA tail: view column of this thread's pixel column, and the view height as a float (row / vh for rows < 2^20 is
+  // exact through (row + 0.5) / vh in fp32)
+  const int sa_ax = p.sa ? ox / (p.in.w / p.amod.w) : 0;
+  const float sa_vh = p.sa ? (float)(p.in.h / p.amod.h) : 1.f;
   for (int r = ly0; r < DW_TH; r += 2) {
     const int oy = ty0 + r;
     if (oy >= p.in.h) break;
     const float* base = tS + r * row_f + lx * DW_CH + q * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    Acc4 a2;
+    a2.lo = pack2(0.f, 0.f); a2.hi = a2.lo;
     if (KH) {
 #pragma unroll
       for (int ky = 0; ky < KH; ++ky)
 #pragma unroll
         for (int kx = 0; kx < KW; ++kx)
-          fma4(acc, *reinterpret_cast<const float4*>(base + ky * dyf + kx * dxf), wr[ky * KW + kx]);
+          fma4(a2, *reinterpret_cast<const float4*>(base + ky * dyf + kx * dxf), wr[ky * KW + kx]);
     } else {
       for (int ky = 0; ky < kh; ++ky) {
         const float* rowp = base + ky * dyf;
         const float* wp = wS + ky * kw * DW_CH + q * 4;
 #pragma unroll 7
         for (int kx = 0; kx < kw; ++kx)
-          fma4(acc, *reinterpret_cast<const float4*>(rowp + kx * dxf), *reinterpret_cast<const float4*>(wp + kx * DW_CH));
+          fma4(a2, *reinterpret_cast<const float4*>(rowp + kx * dxf), *reinterpret_cast<const float4*>(wp + kx * DW_CH));
       }
     }
+    float4 acc;
+    unpack2(a2.lo, acc.x, acc.y);
+    unpack2(a2.hi, acc.z, acc.w);
     if (B.scale) {
       acc.x = acc.x * sc.x + sh.x; acc.y = acc.y * sc.y + sh.y; acc.z = acc.z * sc.z + sh.z; acc.w = acc.w * sc.w + sh.w;
     }
     if (B.act) {
       acc.x = apply_act(acc.x, B.act, B.slope); acc.y = apply_act(acc.y, B.act, B.slope);
       acc.z = apply_act(acc.z, B.act, B.slope); acc.w = apply_act(acc.w, B.act, B.slope);
+    }
+    if (p.sa) {
+      const float4 xc = *reinterpret_cast<const float4*>(base + (kh / 2) * dyf + (kw / 2) * dxf);
+      const float4 am = __ldg(reinterpret_cast<const float4*>(p.amod.p + p.amod.pix(img, (int)__fdividef((float)oy + 0.5f, sa_vh), sa_ax) +
+                                                              cout0 + q * 4));
+      acc.x = xc.x * (p.sa_w0 * acc.x + p.sa_w1 * am.x); acc.y = xc.y * (p.sa_w0 * acc.y + p.sa_w1 * am.y);
+      acc.z = xc.z * (p.sa_w0 * acc.z + p.sa_w1 * am.z); acc.w = xc.w * (p.sa_w0 * acc.w + p.sa_w1 * am.w);
+      if (p.res.p) {
+        const float4 r = *reinterpret_cast<const float4*>(p.res.p + p.res.pix(img, oy, ox) + cout0 + q * 4);
+        acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+      }
     }
     *reinterpret_cast<float4*>(p.out.p + p.out.pix(img, oy, ox) + cout0 + q * 4) = acc;
   }
@@ -137,31 +185,63 @@ dw_tile_kernel(const __grid_constant__ DwParams p) {
   const int img = blockIdx.z;
   const int tyi = blockIdx.x / p.tiles_x;
   const int ty0 = tyi * DW_TH, tx0 = (blockIdx.x - tyi * p.tiles_x) * DW_TW;
-  float* wS = dw_smem;
-  float* tS = dw_smem + p.w_floats;
+  // tile first (TMA destination: 128-byte aligned), taps behind it
+  float* tS = dw_smem + ((128u - (dw_smem_u32(dw_smem) & 127u)) & 127u) / 4;
+  float* wS = tS + p.tile_floats;
+  __shared__ uint64_t bar;
   const int taps = B.kh * B.kw;
-  for (int i = tid; i < taps * DW_CH; i += 256) wS[i] = __ldg(B.w + (i >> 4) * B.c + wofs + (i & 15));
-  // rows of the halo'd tile that lie inside the image; everything else is zero padding
   const int H = p.in.h, W = p.in.w;
-  const int quads_per_row = SW * 4;
-  for (int sy = tid >> 7; sy < SH; sy += 2) {       // 128 threads per tile row
-    const int gy = ty0 - hy + sy;
-    const bool yok = gy >= 0 && gy < H;
-    const float* grow = p.in.p + p.in.pix(img, yok ? gy : 0, 0) + cin0;
-    float* srow = tS + sy * SW * DW_CH;
-    for (int i = tid & 127; i < quads_per_row; i += 128) {
-      const int sx = i >> 2, qq = i & 3;
-      const int gx = tx0 - hx + sx;
-      const bool ok = yok && gx >= 0 && gx < W;
-      cp_async16_zfill(srow + i * 4, ok ? grow + (size_t)gx * p.in.ld + qq * 4 : p.in.p, ok);
+  if (p.use_tma) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dw_smem_u32(&bar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dw_smem_u32(&bar)), "r"(SH * SW * DW_CH * 4) : "memory");
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                   ::"r"(dw_smem_u32(tS)), "l"(&p.tm[b]), "r"(dw_smem_u32(&bar)), "r"(cin0), "r"(tx0 - hx), "r"(ty0 - hy), "r"(img)
+                   : "memory");
     }
+    for (int i = tid; i < taps * DW_CH; i += 256) wS[i] = wofs + (i & 15) < B.c ? __ldg(B.w + (i >> 4) * B.c + wofs + (i & 15)) : 0.f;
+    __syncthreads();                   // taps visible; the barrier was initialised before anybody polls it
+    dw_mbar_wait(&bar, 0);
+  } else {
+    for (int i = tid; i < taps * DW_CH; i += 256) wS[i] = wofs + (i & 15) < B.c ? __ldg(B.w + (i >> 4) * B.c + wofs + (i & 15)) : 0.f;
+    // rows of the halo'd tile that lie inside the image; everything else is zero padding
+    const int quads_per_row = SW * 4;
+    for (int sy = tid >> 7; sy < SH; sy += 2) {       // 128 threads per tile row
+      const int gy = ty0 - hy + sy;
+      const bool yok = gy >= 0 && gy < H;
+      const float* grow = p.in.p + p.in.pix(img, yok ? gy : 0, 0) + cin0;
+      float* srow = tS + sy * SW * DW_CH;
+      for (int i = tid & 127; i < quads_per_row; i += 128) {
+        const int sx = i >> 2, qq = i & 3;
+        const int gx = tx0 - hx + sx;
+        const bool ok = yok && gx >= 0 && gx < W && wofs + qq * 4 < B.c;     // (the last chunk of a branch may be partial)
+        cp_async16_zfill(srow + i * 4, ok ? grow + (size_t)gx * p.in.ld + qq * 4 : p.in.p, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
   if (B.kh == 3 && B.kw == 3) dw_compute<3, 3>(p, B, wS, tS, SW, img, ty0, tx0, cout0, wofs);
   else if (B.kh == 1 && B.kw == 1) dw_compute<1, 1>(p, B, wS, tS, SW, img, ty0, tx0, cout0, wofs);
   else dw_compute<0, 0>(p, B, wS, tS, SW, img, ty0, tx0, cout0, wofs);
+}
+
+typedef CUresult (*DwEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static DwEncodeFn dw_get_encode() {
+  static DwEncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<DwEncodeFn>(p);
+  });
+  return fn;
 }
 
 static bool dw_tile_ok(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_dw_branch* br, int nbr) {
@@ -169,10 +249,10 @@ static bool dw_tile_ok(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr
   if (((uintptr_t)in->ptr & 15) || ((uintptr_t)out->ptr & 15) || (in->ld & 3) || (out->ld & 3)) return false;
   for (int i = 0; i < nbr; ++i) {
     const lfsr_dw_branch& b = br[i];
-    if ((b.c % DW_CH) || (b.in_c0 & 3) || (b.out_c0 & 3)) return false;
+    if ((b.c & 3) || (b.in_c0 & 3) || (b.out_c0 & 3)) return false;
     if (b.scale && (((uintptr_t)b.scale & 15) || ((uintptr_t)b.shift & 15))) return false;
     const int hy = (b.kh / 2) * b.dil_h, hx = (b.kw / 2) * b.dil_w;
-    const size_t bytes = ((size_t)(DW_TH + 2 * hy) * (DW_TW + 2 * hx) * DW_CH + (size_t)b.kh * b.kw * DW_CH) * 4;
+    const size_t bytes = ((size_t)(DW_TH + 2 * hy) * (DW_TW + 2 * hx) * DW_CH + (size_t)b.kh * b.kw * DW_CH) * 4 + 128;
     if (bytes > 200 * 1024) return false;
   }
   return true;
@@ -182,8 +262,10 @@ static bool dw_tile_ok(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr
 
 using namespace lfsr;
 
-extern "C" int lfsr_dwconv_multi(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_dw_branch* br, int nbr,
-                                 void* stream) {
+// shared by lfsr_dwconv_multi and lfsr_sa_modulate (sa != null: the SA-modulator tail on a single branch)
+struct SaTail { float w0, w1; const lfsr_tensor* amod; const lfsr_tensor* res; };
+static int dw_launch(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_dw_branch* br, int nbr, const SaTail* sa,
+                     bool* used_tile, void* stream) {
   LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && br && nbr > 0, "lfsr_dwconv_multi: null/invalid argument");
   LFSR_REQUIRE(in->n == out->n && in->h == out->h && in->w == out->w, "lfsr_dwconv_multi: in/out geometry mismatch");
   LFSR_REQUIRE(in->n <= 65535 && (long long)in->h * in->w * in->ld < 0x7fffffffLL &&
@@ -198,7 +280,9 @@ extern "C" int lfsr_dwconv_multi(const lfsr_tensor* in, const lfsr_tensor* out, 
     LFSR_REQUIRE((b.scale == nullptr) == (b.shift == nullptr), "lfsr_dwconv_multi: scale/shift must come together");
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (used_tile) *used_tile = dw_tile_ok(in, out, br, nbr);
   if (!dw_tile_ok(in, out, br, nbr)) {
+    if (sa) return LFSR_OK;       // the caller falls back to its own kernel
     for (int i = 0; i < nbr; ++i) {
       const lfsr_dw_branch& b = br[i];
       TView vi = view_of(in), vo = view_of(out);
@@ -214,6 +298,10 @@ extern "C" int lfsr_dwconv_multi(const lfsr_tensor* in, const lfsr_tensor* out, 
   DwParams p;
   p.in = view_of(in); p.out = view_of(out);
   p.nbr = nbr;
+  p.sa = sa ? 1 : 0;
+  p.sa_w0 = sa ? sa->w0 : 0.f; p.sa_w1 = sa ? sa->w1 : 0.f;
+  p.amod = sa ? view_of(sa->amod) : null_view();
+  p.res = sa && sa->res && sa->res->ptr ? view_of(sa->res) : null_view();
   int items = 0, w_floats = 0;
   size_t tile_floats = 0;
   for (int i = 0; i < nbr; ++i) {
@@ -223,7 +311,7 @@ extern "C" int lfsr_dwconv_multi(const lfsr_tensor* in, const lfsr_tensor* out, 
     d.kh = b.kh; d.kw = b.kw; d.dh = b.dil_h; d.dw = b.dil_w;
     d.in_c0 = b.in_c0; d.out_c0 = b.out_c0; d.c = b.c; d.act = b.act; d.slope = b.act_slope;
     d.item0 = items;
-    items += b.c / DW_CH;
+    items += ceil_div(b.c, DW_CH);
     const int hy = (b.kh / 2) * b.dil_h, hx = (b.kw / 2) * b.dil_w;
     const size_t tf = (size_t)(DW_TH + 2 * hy) * (DW_TW + 2 * hx) * DW_CH;
     if (tf > tile_floats) tile_floats = tf;
@@ -232,7 +320,24 @@ extern "C" int lfsr_dwconv_multi(const lfsr_tensor* in, const lfsr_tensor* out, 
   LFSR_REQUIRE(items <= 65535, "lfsr_dwconv_multi: too many channel chunks");
   p.tiles_x = ceil_div(in->w, DW_TW);
   p.w_floats = w_floats;
-  const size_t smem = (tile_floats + (size_t)w_floats) * sizeof(float);
+  p.tile_floats = (int)tile_floats;
+  static const bool no_tma = getenv("LFSR_DW_NO_TMA") != nullptr;
+  DwEncodeFn encode = no_tma ? nullptr : dw_get_encode();
+  p.use_tma = encode != nullptr;
+  for (int i = 0; i < nbr && p.use_tma; ++i) {
+    const lfsr_dw_branch& b = br[i];
+    const int hy = (b.kh / 2) * b.dil_h, hx = (b.kw / 2) * b.dil_w;
+    const cuuint64_t ld_b = (cuuint64_t)in->ld * 4;
+    cuuint64_t dims[4] = {(cuuint64_t)in->c, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
+    cuuint64_t strides[3] = {ld_b, ld_b * in->w, ld_b * in->w * in->h};
+    cuuint32_t box[4] = {(cuuint32_t)DW_CH, (cuuint32_t)(DW_TW + 2 * hx), (cuuint32_t)(DW_TH + 2 * hy), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (box[1] > 256 || box[2] > 256 ||
+        encode(&p.tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      p.use_tma = 0;
+  }
+  const size_t smem = (tile_floats + (size_t)w_floats) * sizeof(float) + 128;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(dw_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 4096);
@@ -242,6 +347,30 @@ extern "C" int lfsr_dwconv_multi(const lfsr_tensor* in, const lfsr_tensor* out, 
   dim3 grid(p.tiles_x * ceil_div(in->h, DW_TH), items, in->n);
   dw_tile_kernel<<<grid, 256, smem, st>>>(p);
   return check_launch("dw_tile_kernel");
+}
+
+extern "C" int lfsr_dwconv_multi(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_dw_branch* br, int nbr,
+                                 void* stream) {
+  return dw_launch(in, out, br, nbr, nullptr, nullptr, stream);
+}
+
+// SA-modulator tail on the tiled depthwise kernel; *handled = 0 when the tensors do not qualify (caller falls back)
+int lfsr_sa_modulate_tiled(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
+                           const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res, const lfsr_tensor* out, int dil,
+                           int* handled, void* stream) {
+  lfsr_dw_branch b;
+  b.w = dw_w; b.scale = bn_scale; b.shift = bn_shift;
+  b.kh = 3; b.kw = 3; b.dil_h = dil; b.dil_w = dil;
+  b.in_c0 = 0; b.out_c0 = 0; b.c = x->c;
+  b.act = LFSR_ACT_SIGMOID; b.act_slope = 0.f;
+  auto al = [](const lfsr_tensor* t) { return t && t->ptr && t->ld % 4 == 0 && (((uintptr_t)t->ptr) & 15) == 0; };
+  *handled = 0;
+  if (!al(amod) || (res && res->ptr && !al(res))) return LFSR_OK;
+  SaTail sa{w0, w1, amod, res};
+  bool used = false;
+  int rc = dw_launch(x, out, &b, 1, &sa, &used, stream);
+  *handled = used ? 1 : 0;
+  return rc;
 }
 
 extern "C" int lfsr_dwconv_f32(const lfsr_tensor* in, const float* w_packed, const float* scale, const float* shift,

@@ -150,6 +150,55 @@ sa_modulate_kernel(TView x, const float* __restrict__ dww, const float* __restri
   }
 }
 
+// Same, for float4-aligned tensors of <= 64 channels (the 60-channel grouped trunk): a CTA owns a 16 x 16 pixel tile,
+// thread = (channel quad, pixel column) walking the 16 rows with its 9 tap weights and BN constants in registers; the
+// rows a tap needs again 5 and 10 iterations later come out of L1, and there is no index division anywhere.
+__global__ void __launch_bounds__(256)
+sa_modulate_tile_kernel(TView x, const float* __restrict__ dww, const float* __restrict__ bns,
+                        const float* __restrict__ bnb, TView amod, float w0, float w1, TView res, TView out, int dil) {
+  const int q = threadIdx.x & 15, lx = threadIdx.x >> 4;
+  const int c = q * 4;
+  const int px = blockIdx.x * 16 + lx, py0 = blockIdx.y * 16, img = blockIdx.z;
+  if (c >= x.c || px >= x.w) return;
+  float4 wk[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wk[t] = __ldg(reinterpret_cast<const float4*>(dww + t * x.c + c));
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(bns + c)), sh = __ldg(reinterpret_cast<const float4*>(bnb + c));
+  const int vh = x.h / amod.h, vw = x.w / amod.w;
+  const int ax = px / vw;
+  const int row_f = x.w * x.ld;
+  const float* xcol = x.p + x.pix(img, 0, px) + c;
+  const bool xl = px - dil >= 0, xr = px + dil < x.w;
+  const int ymax = min(py0 + 16, x.h);
+  for (int py = py0; py < ymax; ++py) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), xc = acc;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = py + (ky - 1) * dil;
+      if (iy < 0 || iy >= x.h) continue;
+      const float* rowp = xcol + (size_t)iy * row_f;
+      if (xl) { const float4 v = __ldg(reinterpret_cast<const float4*>(rowp - dil * x.ld)); const float4 w = wk[ky * 3];
+                acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y); acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w); }
+      { const float4 v = __ldg(reinterpret_cast<const float4*>(rowp)); const float4 w = wk[ky * 3 + 1];
+        acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y); acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w);
+        if (ky == 1) xc = v; }
+      if (xr) { const float4 v = __ldg(reinterpret_cast<const float4*>(rowp + dil * x.ld)); const float4 w = wk[ky * 3 + 2];
+                acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y); acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w); }
+    }
+    const float4 am = __ldg(reinterpret_cast<const float4*>(amod.p + amod.pix(img, py / vh, ax) + c));
+    float4 o;
+    o.x = xc.x * (w0 * __fdividef(1.f, 1.f + __expf(-(acc.x * sc.x + sh.x))) + w1 * am.x);
+    o.y = xc.y * (w0 * __fdividef(1.f, 1.f + __expf(-(acc.y * sc.y + sh.y))) + w1 * am.y);
+    o.z = xc.z * (w0 * __fdividef(1.f, 1.f + __expf(-(acc.z * sc.z + sh.z))) + w1 * am.z);
+    o.w = xc.w * (w0 * __fdividef(1.f, 1.f + __expf(-(acc.w * sc.w + sh.w))) + w1 * am.w);
+    if (res.p) {
+      const float4 r = *reinterpret_cast<const float4*>(res.p + res.pix(img, py, px) + c);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    *reinterpret_cast<float4*>(out.p + out.pix(img, py, px) + c) = o;
+  }
+}
+
 // ---- out = x * scale[n][c] + res : ChannelAttention scaling fused with the block residual
 template <int V>
 __global__ void __launch_bounds__(256)
@@ -405,6 +454,10 @@ extern "C" int lfsr_block_mean(const lfsr_tensor* in, const lfsr_tensor* out, in
   return check_launch("block_mean_kernel");
 }
 
+int lfsr_sa_modulate_tiled(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
+                           const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res, const lfsr_tensor* out, int dil,
+                           int* handled, void* stream);     // lfsr_dw.cu
+
 extern "C" int lfsr_sa_modulate(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
                                 const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res,
                                 const lfsr_tensor* out, int dil, void* stream) {
@@ -425,6 +478,18 @@ extern "C" int lfsr_sa_modulate(const lfsr_tensor* x, const float* dw_w, const f
     else break;
   }
   LFSR_REQUIRE(x->n <= 65535, "lfsr_sa_modulate: batch too large");
+  if (V == 4) {        // shared-memory tiled depthwise kernel with the modulator tail in its epilogue
+    int handled = 0;
+    int rc = lfsr_sa_modulate_tiled(x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil, &handled, stream);
+    if (rc != LFSR_OK || handled) return rc;
+  }
+  if (V == 4 && x->c <= 64 && (((uintptr_t)dw_w | (uintptr_t)bn_scale | (uintptr_t)bn_shift) & 15) == 0 &&
+      (long long)x->h * x->w * x->ld < 0x7fffffffLL) {
+    dim3 grid(ceil_div(x->w, 16), ceil_div(x->h, 16), x->n);
+    sa_modulate_tile_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(x), dw_w, bn_scale, bn_shift, view_of(amod), w0, w1, r,
+                                                                    view_of(out), dil);
+    return check_launch("sa_modulate_tile_kernel");
+  }
   const int per = x->h * x->w * (x->c / V);
   dim3 blocks(ceil_div(per, 256), x->n);
   cudaStream_t st = (cudaStream_t)stream;

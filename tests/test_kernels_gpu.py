@@ -221,8 +221,9 @@ def test_block_mean(ops, ref, h, w, c, bh, bw):
     assert (a - b).abs().max().item() <= 1e-5
 
 
-def test_sa_modulate(ops, ref):
-    n, h, w, c, A = 2, 40, 40, 54, 5
+@pytest.mark.parametrize("c,h,w", [(54, 40, 40), (60, 40, 40), (60, 45, 35), (64, 160, 160)])
+def test_sa_modulate(ops, ref, c, h, w):
+    n, A = 2, 5
     x, res = nhwc(n, h, w, c, seed=1), nhwc(n, h, w, c, seed=2)
     dw, bs, bb = rnd(9, c, seed=3), rnd(c, seed=4, lo=0.5, hi=1.5), rnd(c, seed=5)
     am = nhwc(n, A, A, c, seed=6)
