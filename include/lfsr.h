@@ -147,6 +147,13 @@ int lfsr_dwconv_multi(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_
  * second half of a kh x kw convolution to ONE channel whose per-tap responses were produced by a `tail_w` epilogue. */
 int lfsr_tap_gather(const lfsr_tensor* taps, int kh, int kw, const float* bias, const lfsr_tensor* res,
                     const lfsr_tensor* out, void* stream);
+/* thin dense conv on the FP32 pipe (packed FFMA2): 16/18/20 input channels read as 20-float pixels, exactly 20 output
+ * channels, stride 1, "same" padding, <= 9 taps, any dilation; bias + activation fused; weights packed as for
+ * lfsr_conv2d_f32. The spatial branch of the Track-2 model (MyEfficientLFNet.py:134-141), where a K=8 tf32 MMA costs
+ * the same for N=32 as for N=128 and the CUDA cores win. fp32-exact. */
+int lfsr_conv2d_thin_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);
+int lfsr_conv2d_thin(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out,
+                     const lfsr_conv_desc* d, void* stream);
 /* direct conv for 1..4 output channels (reconstruction heads 54->1 / 64->1: MyEfficientLFNet.py:70-73,
  * EPIT.py:48): stride 1, "same" padding; weights packed as for lfsr_conv2d_f32; bias/act/alpha/res fused. */
 int lfsr_conv2d_small_cout_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);

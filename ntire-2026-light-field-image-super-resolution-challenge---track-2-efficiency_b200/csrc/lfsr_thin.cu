@@ -1,0 +1,204 @@
+// Thin dense convolutions (<= 20 input channels, 20 output channels) of the Track-2 model's spatial branch
+// (MyEfficientLFNet.py:134-141: RepConv 3x3 d=A 18->18 + LReLU, conv 3x3 d=A 18->18), fp32 on CUDA cores.
+//
+// On the tensor-core path these layers are bound by the fixed cost of a K=8 tf32 MMA (128 rows of the A operand are
+// fetched whatever N is): 27 MMAs of N=32 per 128-pixel tile, 0.39 ms per layer at batch 64. With 18x18x9 = 2916 MACs
+// per pixel they are cheap enough for the FP32 pipe when every instruction is a packed FFMA2 on an output-channel pair
+// and weights arrive as broadcast LDS.128:
+//   CTA = 32 x 16 output pixels, 256 threads, thread = 2 pixels (same column, 8 rows apart) sharing every weight load;
+//   the 20-float pixels (18 channels + the 2 pad floats of the grouped trunk layout) of the tile + dilation halo are
+//   fetched by ONE thread with a 4-D TMA box load (out-of-image = zero = the conv's padding); pixel pitch 20 floats
+//   makes the per-lane 128-bit tile reads bank-conflict free; weights [tap][cin][20] sit in shared memory.
+// Results are fp32-exact (no TF32 rounding), summed tap by tap, input channel by input channel.
+#include <cuda.h>
+#include <mutex>
+#include "lfsr_common.cuh"
+
+namespace lfsr {
+
+constexpr int TH_W = 32, TH_H = 16, TH_CP = 20, TH_NP = TH_CP / 2;   // tile, pixel pitch (floats), output pairs
+
+struct ThinArgs {
+  TView in, out;
+  const float* w;        // [kh*kw][cin][20]
+  const float* bias;     // [20] or null
+  int kh, kw, dh, dw, cin, act;
+  float slope;
+  int tiles_x, tiles_y;
+  CUtensorMap tm;
+};
+
+__device__ __forceinline__ uint32_t th_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void th_ld20(const float* src, float* v) {
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const float4 t = reinterpret_cast<const float4*>(src)[i];
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void th_ldw(const float* row, f32x2* w) {
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const float4 t = reinterpret_cast<const float4*>(row)[i];
+    w[2 * i] = pack2(t.x, t.y); w[2 * i + 1] = pack2(t.z, t.w);
+  }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv_thin_kernel(const __grid_constant__ ThinArgs a) {
+  extern __shared__ __align__(16) float th_smem[];
+  __shared__ uint64_t bar;
+  const int tid = threadIdx.x;
+  const int hy = (a.kh / 2) * a.dh, hx = (a.kw / 2) * a.dw;
+  const int SH = TH_H + 2 * hy, SW = TH_W + 2 * hx;
+  float* tile = th_smem + ((128u - (th_smem_u32(th_smem) & 127u)) & 127u) / 4;      // [SH][SW][20], TMA destination
+  float* wsm = tile + SH * SW * TH_CP;                                               // [taps][CIN][20]
+  int t_ = blockIdx.x;
+  const int tx0 = (t_ % a.tiles_x) * TH_W; t_ /= a.tiles_x;
+  const int ty0 = (t_ % a.tiles_y) * TH_H;
+  const int img = t_ / a.tiles_y;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(th_smem_u32(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(th_smem_u32(&bar)), "r"(SH * SW * TH_CP * 4) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(th_smem_u32(tile)), "l"(&a.tm), "r"(th_smem_u32(&bar)), "r"(0), "r"(tx0 - hx), "r"(ty0 - hy), "r"(img)
+                 : "memory");
+  }
+  const int taps = a.kh * a.kw;
+  for (int i = tid; i < taps * CIN * (TH_CP / 4); i += 256)
+    reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(a.w) + i);
+  __syncthreads();
+  {
+    const uint32_t addr = th_smem_u32(&bar);
+    uint32_t done = 0;
+    for (uint32_t it = 0; it < (1u << 26) && !done; ++it)       // bounded: a protocol bug must fault, not hang the GPU
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(addr) : "memory");
+    if (!done) __trap();
+  }
+  const int lx = tid & 31, ly = tid >> 5;               // pixels (lx, ly) and (lx, ly + 8)
+  f32x2 acc0[TH_NP], acc1[TH_NP];
+#pragma unroll
+  for (int i = 0; i < TH_NP; ++i) {
+    const f32x2 b = a.bias ? pack2(__ldg(a.bias + 2 * i), __ldg(a.bias + 2 * i + 1)) : pack2(0.f, 0.f);
+    acc0[i] = b; acc1[i] = b;
+  }
+  for (int ky = 0; ky < a.kh; ++ky)
+    for (int kx = 0; kx < a.kw; ++kx) {
+      const float* p0 = tile + ((ly + ky * a.dh) * SW + lx + kx * a.dw) * TH_CP;
+      float v0[TH_CP], v1[TH_CP];
+      th_ld20(p0, v0);
+      th_ld20(p0 + 8 * SW * TH_CP, v1);
+      const float* wt = wsm + (ky * a.kw + kx) * CIN * TH_CP;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        f32x2 w[TH_NP];
+        th_ldw(wt + c * TH_CP, w);
+        const f32x2 b0 = pack2(v0[c], v0[c]), b1 = pack2(v1[c], v1[c]);
+#pragma unroll
+        for (int i = 0; i < TH_NP; ++i) { acc0[i] = fma2(b0, w[i], acc0[i]); acc1[i] = fma2(b1, w[i], acc1[i]); }
+      }
+    }
+  const int ox = tx0 + lx;
+  if (ox >= a.out.w) return;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int oy = ty0 + ly + 8 * h;
+    if (oy >= a.out.h) continue;
+    float o[TH_CP];
+#pragma unroll
+    for (int i = 0; i < TH_NP; ++i) unpack2(h ? acc1[i] : acc0[i], o[2 * i], o[2 * i + 1]);
+    if (a.act) {
+#pragma unroll
+      for (int i = 0; i < TH_CP; ++i) o[i] = apply_act(o[i], a.act, a.slope);
+    }
+    float4* dst = reinterpret_cast<float4*>(a.out.p + a.out.pix(img, oy, ox));
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+  }
+}
+
+typedef CUresult (*ThEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static ThEncodeFn th_get_encode() {
+  static ThEncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<ThEncodeFn>(p);
+  });
+  return fn;
+}
+
+static size_t thin_smem(const lfsr_tensor* in, const lfsr_conv_desc* d) {
+  const int hy = (d->kh / 2) * d->dil_h, hx = (d->kw / 2) * d->dil_w;
+  return ((size_t)(TH_H + 2 * hy) * (TH_W + 2 * hx) * TH_CP + (size_t)d->kh * d->kw * in->c * TH_CP) * sizeof(float) + 128;
+}
+
+}  // namespace lfsr
+
+using namespace lfsr;
+
+extern "C" int lfsr_conv2d_thin_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d) {
+  if (!tensor_ok(in) || !tensor_ok(out) || !d) return 0;
+  if (in->c != 16 && in->c != 18 && in->c != 20) return 0;
+  if (out->c != TH_CP || out->ld % 4 || ((uintptr_t)out->ptr & 15)) return 0;
+  // the tile is read as 20-float pixels: the floats behind an 18- or 16-channel view must exist (grouped trunk slices)
+  if (in->ld < TH_CP || in->ld % 4 || ((uintptr_t)in->ptr & 15)) return 0;
+  if (d->stride_h != 1 || d->stride_w != 1 || d->in_perm || d->out_perm || d->mul.ptr || d->res.ptr || d->in_scale || d->tail_w) return 0;
+  if (d->shuf_ry > 1 || d->shuf_rx > 1 || d->block_h > 0 || d->block_w > 0 || d->alpha != 1.f) return 0;
+  if (!(d->kh & 1) || !(d->kw & 1) || d->kh * d->kw > 9) return 0;
+  if (2 * d->pad_h != d->dil_h * (d->kh - 1) || 2 * d->pad_w != d->dil_w * (d->kw - 1)) return 0;
+  if (out->n != in->n || out->h != in->h || out->w != in->w) return 0;
+  if (TH_W + d->dil_w * (d->kw - 1) > 256 || TH_H + d->dil_h * (d->kh - 1) > 256) return 0;
+  if (thin_smem(in, d) > 110 * 1024) return 0;
+  return th_get_encode() != nullptr;
+}
+
+extern "C" int lfsr_conv2d_thin(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out, const lfsr_conv_desc* d,
+                                void* stream) {
+  LFSR_REQUIRE(w_packed && lfsr_conv2d_thin_supported(in, out, d), "lfsr_conv2d_thin: unsupported problem");
+  LFSR_REQUIRE(((uintptr_t)w_packed & 15) == 0, "lfsr_conv2d_thin: weights must be 16-byte aligned");
+  ThinArgs a;
+  a.in = view_of(in); a.out = view_of(out);
+  a.w = w_packed; a.bias = d->bias;
+  a.kh = d->kh; a.kw = d->kw; a.dh = d->dil_h; a.dw = d->dil_w; a.cin = in->c; a.act = d->act; a.slope = d->act_slope;
+  a.tiles_x = ceil_div(out->w, TH_W); a.tiles_y = ceil_div(out->h, TH_H);
+  {
+    const cuuint64_t ld_b = (cuuint64_t)in->ld * 4;
+    cuuint64_t dims[4] = {(cuuint64_t)TH_CP, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
+    cuuint64_t strides[3] = {ld_b, ld_b * in->w, ld_b * in->w * in->h};
+    cuuint32_t box[4] = {(cuuint32_t)TH_CP, (cuuint32_t)(TH_W + d->dil_w * (d->kw - 1)), (cuuint32_t)(TH_H + d->dil_h * (d->kh - 1)), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = th_get_encode()(&a.tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in->ptr, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("lfsr_conv2d_thin: cuTensorMapEncodeTiled failed with %d", (int)r); return LFSR_ERR_CUDA; }
+  }
+  const size_t smem = thin_smem(in, d);
+  const int blocks = out->n * a.tiles_x * a.tiles_y;
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_THIN(CIN)                                                                                       \
+  do {                                                                                                         \
+    static bool attr_done = false;                                                                             \
+    if (!attr_done) {                                                                                          \
+      cudaFuncSetAttribute(conv_thin_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);    \
+      attr_done = true;                                                                                        \
+    }                                                                                                          \
+    conv_thin_kernel<CIN><<<blocks, 256, smem, st>>>(a);                                                       \
+  } while (0)
+  switch (in->c) {
+    case 16: LAUNCH_THIN(16); break;
+    case 18: LAUNCH_THIN(18); break;
+    default: LAUNCH_THIN(20); break;
+  }
+#undef LAUNCH_THIN
+  return check_launch("conv_thin_kernel");
+}

@@ -103,6 +103,7 @@ class CudaOps:
     def __init__(self, use_tc: bool = True):
         self.lib = N.load()
         self.use_tc = use_tc
+        self.use_thin = True      # FFMA2 kernel for the 18 -> 20 channel layers (tests switch it off to reach the TC path)
         self._gated = {}          # per-image gated weight scratch, keyed by (packed weights, batch)
 
     # -- helpers ---------------------------------------------------------------------------
@@ -160,6 +161,10 @@ class CudaOps:
             if not (self.use_tc and pc.w_tc is not None and self.lib.lfsr_conv2d_tc_supported(C.byref(tin), C.byref(tout), C.byref(d))):
                 raise N.LfsrError("conv: tail projection is only available on the tensor-core path (query tail_supported first)")
             N.check(self.lib.lfsr_conv2d_tc(C.byref(tin), pc.w_tc.data_ptr(), C.byref(tout), C.byref(d), st), "lfsr_conv2d_tc")
+            return
+        if (pc.cout == 20 and pc.cin <= 20 and self.use_thin and
+                self.lib.lfsr_conv2d_thin_supported(C.byref(tin), C.byref(tout), C.byref(d))):
+            N.check(self.lib.lfsr_conv2d_thin(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st), "lfsr_conv2d_thin")
             return
         if pc.cout <= 4 and self.lib.lfsr_conv2d_small_cout_supported(C.byref(tin), C.byref(tout), C.byref(d)):
             N.check(self.lib.lfsr_conv2d_small_cout(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st),

@@ -491,3 +491,23 @@ def test_conv_tc_tail_projection_and_tap_gather(ref, cin, cq, hw, bias):
     y2 = rnd(n, h * r, w * r, 1, seed=5)
     ref.conv(full, K.pack_conv(head, hb, pad=(1, 1), device=DEV), y2, res=y2.clone())
     assert (ya - y2).abs().max().item() <= 2e-3
+
+
+@pytest.mark.parametrize("cin,k,dil,hw,bias,act", [(18, 3, 5, (160, 160), True, 2), (18, 3, 5, (37, 45), False, 0), (20, 3, 1, (40, 40), True, 1),
+                                                   (16, 1, 1, (40, 40), False, 0)])
+def test_conv_thin(ops, ref, cin, k, dil, hw, bias, act):
+    """18 -> 20 channel slices of the grouped trunk on the FFMA2 kernel (fp32-exact), pads of the output slot written"""
+    n, (h, w) = 2, hw
+    g = torch.Generator().manual_seed(cin * 7 + k)
+    wt = (torch.rand(20, cin, k, k, generator=g) - 0.5) * (2.0 / (cin * k * k) ** 0.5)
+    b = (torch.rand(20, generator=g) - 0.5) if bias else None
+    p = dil * (k // 2)
+    pc = K.pack_conv(wt, b, dil=(dil, dil), pad=(p, p), device=DEV)
+    trunk = nhwc(n, h, w, 60, seed=1)
+    x = trunk[..., 20:20 + cin]
+    fa, fb = nhwc(n, h, w, 60, seed=2), nhwc(n, h, w, 60, seed=2)
+    l0 = ops.lib.lfsr_launch_count()
+    ops.conv(x, pc, fa[..., 40:60], act=act, slope=0.1)
+    assert ops.lib.lfsr_launch_count() == l0 + 1
+    ref.conv(x, pc, fb[..., 40:60], act=act, slope=0.1)
+    assert (fa - fb).abs().max().item() <= 2e-5
