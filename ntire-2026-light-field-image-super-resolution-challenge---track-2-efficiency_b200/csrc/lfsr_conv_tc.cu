@@ -497,10 +497,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const Params& p, const CUtenso
   // so one 32-register operand run per block is prefetched
   const bool is_mul = p.mul.p != nullptr;
   const float* xpix = nullptr;
-  if (pix_ok && (p.res.p || p.mul.p)) {            // the host enables these only without a PixelShuffle
-    const int Y = (tc_.nb - img * p.nby) * p.bh + tc_.y0 + ty, X = tc_.vx * p.bw + tc_.x0 + tx;
+  const int Y = (tc_.nb - img * p.nby) * p.bh + tc_.y0 + ty, X = tc_.vx * p.bw + tc_.x0 + tx;
+  const bool shuf_res = p.res.p && p.ry * p.rx > 1;     // residual in stored-output geometry: its pixel depends on the block's sub-pixel
+  if (pix_ok && (p.res.p || p.mul.p) && !shuf_res)
     xpix = is_mul ? p.mul.p + p.mul.pix(img, Y, X) : p.res.p + p.res.pix(img, Y, X);
-  }
   const int ty_w = (q * 32) >> p.tw_shift, tx_w = (q * 32) & tw_mask;      // origin of the warp's 32-pixel box in the tile
   const int r2 = p.ry * p.rx;
   const bool chan_major = r2 > 1 && p.shuf_mode == LFSR_SHUF_CHANNEL_MAJOR;
@@ -527,6 +527,13 @@ __device__ __forceinline__ void epilogue_tile_tma(const Params& p, const CUtenso
       for (int k = 0; k < 8; ++k) {
         xv[k] = make_float4(fill, fill, fill, fill);
         if (xpix && pc0 + 4 * k < p.cout) xv[k] = *reinterpret_cast<const float4*>(xpix + pc0 + 4 * k);
+      }
+      if (shuf_res && pix_ok) {
+        const int si = fdiv(sub, p.fd_rx), sj = sub - si * p.rx;
+        const float* rp = p.res.p + p.res.pix(img, Y * p.ry + si, X * p.rx + sj) + c0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (c0 + 4 * k < p.cq) xv[k] = *reinterpret_cast<const float4*>(rp + 4 * k);
       }
       if (p.bias) {
         const int pcl = pc0 + lane;
@@ -1458,11 +1465,21 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
     // spill into the pad floats of grouped layouts, so those layers keep the per-row write-out)
     bool ok = !no_tma_epi && (((uintptr_t)out->ptr & 15) == 0) && (out->ld % 4 == 0) && (p.cq % 4 == 0) &&
               !(d->res.ptr && d->mul.ptr);
-    if (d->res.ptr) ok = ok && r2 == 1 && (((uintptr_t)d->res.ptr & 15) == 0) && (d->res.ld % 4 == 0);
+    if (d->res.ptr) ok = ok && (((uintptr_t)d->res.ptr & 15) == 0) && (d->res.ld % 4 == 0);
     if (d->mul.ptr) ok = ok && r2 == 1 && (((uintptr_t)d->mul.ptr & 15) == 0) && (d->mul.ld % 4 == 0);
     // (a short last block reads up to 15 accumulator columns past NC: keep that inside the 256-column stage)
-    if (r2 > 1) ok = ok && p.nbx == 1 && p.nby == 1 && (OHc % p.TH == 0) && (long long)out->n * OHc < 0x7fffffffLL &&
-                  (p.NC <= 240 || p.cq % 32 == 0);
+    if (r2 > 1) ok = ok && p.nbx == 1 && p.nby == 1 && (OHc % p.TH == 0) && (long long)out->n * OHc < 0x7fffffffLL;
+    // the epilogue reads a column block with one or two 16-column TMEM loads: replay its block enumeration and keep
+    // every load inside the 256-column accumulator stage
+    for (int chunk = 0; chunk < p.nchunks && ok; ++chunk) {
+      const int lo = chunk * p.NC, hi = lo + p.NC < p.cout ? lo + p.NC : p.cout;
+      for (int pc0 = lo, ncols = 0; pc0 < hi && ok; pc0 += ncols) {
+        const int c0 = r2 > 1 ? pc0 % p.cq : pc0;
+        ncols = p.cq - c0 < 32 ? p.cq - c0 : 32;
+        if (hi - pc0 < ncols) ncols = hi - pc0;
+        if (pc0 - lo + (ncols > 16 ? 32 : 16) > kAccStride) ok = false;
+      }
+    }
     if (ok) {
       const cuuint64_t ld_b = (cuuint64_t)out->ld * 4;
       const cuuint32_t box_w = (cuuint32_t)(p.TW < 32 ? p.TW : 32), box_h = 32 / box_w;

@@ -185,6 +185,7 @@ class get_model(LFNetBase):
         w, b = self.shallow_feat.merged()
         pk["stem"] = pc(self._exp(w, 0), self._exp(b, 0), **dil)
         stages = []
+        gs_ = self._groups()[1]
         for st in self.stages:
             s = {}
             w, b = st.spatial_branch["0"].merged()
@@ -196,7 +197,12 @@ class get_model(LFNetBase):
             s["ang_a2"] = _dw_pack(ab.attention["2"].weight, device)
             s["ang_a4"] = pc(ab.attention["4"].weight)
             s["ang_cv"] = pc(ab.cross_view["0"].weight, pad=(1, 1))
-            s["ang_ex"] = pc(ab.expand["0"].weight, tc=True, tc_shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
+            # expand conv + PixelShuffle(A): output channels padded 18 -> 20 per sub-pixel (nn.PixelShuffle order keeps the
+            # A*A sub-pixels innermost), so that the layer writes whole 20-float slots through the TMA-store epilogue
+            we = ab.expand["0"].weight.detach().float().cpu()
+            ce = we.shape[0] // (A * A)
+            we = torch.cat([we.view(ce, A * A, *we.shape[1:]), we.new_zeros((gs_ - ce, A * A) + tuple(we.shape[1:]))], 0)
+            s["ang_ex"] = pc(we.reshape(gs_ * A * A, *we.shape[2:]), tc=True, tc_shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
             s["ang_scale"] = float(ab.scale.detach().item())
             eb = st.epi_branch
             pw_t = lambda m: m.weight.detach().float()[:, :, 0, 0].t().contiguous().reshape(-1).cpu()   # [in][out]
@@ -293,7 +299,7 @@ class get_model(LFNetBase):
             ops.dwconv(ang2, st["ang_a2"], ang3, 3, 3, act=N.ACT_RELU)
             ops.conv(ang3, st["ang_a4"], ang4, act=N.ACT_SIGMOID, mul=ang1)
             ops.conv(ang4, st["ang_cv"], ang5, act=LR, slope=0.1)
-            ops.conv(ang5, st["ang_ex"], cat[..., sl[1]], act=LR, slope=0.1, alpha=st["ang_scale"], res=xa,
+            ops.conv(ang5, st["ang_ex"], cat[..., gs:2 * gs], act=LR, slope=0.1, alpha=st["ang_scale"], res=feat[..., gs:2 * gs],
                      shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
             # EPI branch: three depthwise+pointwise paths and their fuse conv in one kernel
             ops.mel_epi_branch(xe, st["epi_w"], cat[..., sl[2]], st["epi_klen"], A, 0.1)
