@@ -154,6 +154,11 @@ int lfsr_tap_gather(const lfsr_tensor* taps, int kh, int kw, const float* bias, 
 int lfsr_conv2d_thin_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);
 int lfsr_conv2d_thin(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out,
                      const lfsr_conv_desc* d, void* stream);
+/* stems: 1 input channel -> <= 64 output channels (multiple of 4), <= 9 taps, stride 1, "same" padding; bias +
+ * activation fused (MyEfficientLFNet.py:40-43, MyEfficientLFNetV4_5.py:42). Weights packed as for lfsr_conv2d_f32. */
+int lfsr_conv2d_stem_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);
+int lfsr_conv2d_stem(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out,
+                     const lfsr_conv_desc* d, void* stream);
 /* direct conv for 1..4 output channels (reconstruction heads 54->1 / 64->1: MyEfficientLFNet.py:70-73,
  * EPIT.py:48): stride 1, "same" padding; weights packed as for lfsr_conv2d_f32; bias/act/alpha/res fused. */
 int lfsr_conv2d_small_cout_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);

@@ -76,6 +76,8 @@ SIGNATURES = {
     "lfsr_dwconv_f32": (_I, [_TP, _P, _P, _P, _TP, _I, _I, _I, _I, _I, C.c_float, _P]),
     "lfsr_dwconv_multi": (_I, [_TP, _TP, C.POINTER(DwBranch), _I, _P]),
     "lfsr_tap_gather": (_I, [_TP, _I, _I, _P, _TP, _TP, _P]),
+    "lfsr_conv2d_stem_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),
+    "lfsr_conv2d_stem": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
     "lfsr_conv2d_thin_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),
     "lfsr_conv2d_thin": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
     "lfsr_conv2d_small_cout_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),

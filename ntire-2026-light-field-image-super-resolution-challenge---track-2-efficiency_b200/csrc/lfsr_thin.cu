@@ -121,6 +121,59 @@ conv_thin_kernel(const __grid_constant__ ThinArgs a) {
   }
 }
 
+// ---- stems: ONE input channel (the Y mosaic), <= 64 output channels, <= 9 taps ---------------------------------------
+// (MyEfficientLFNet.py:40-43 RepConv(1, C) d=A; MyEfficientLFNetV4_5.py:42.) HBM-bound on the output write: thread = (pixel, output-channel quad), tap weights of the quad in registers,
+// the 9 input taps are L1 hits shared by the 16 quads of a pixel.
+struct StemArgs {
+  TView in, out;
+  const float* w;        // [taps][cout]
+  const float* bias;
+  int kh, kw, dh, dw, ph, pw, act;
+  float slope;
+};
+
+__global__ void __launch_bounds__(256)
+conv_stem_kernel(const StemArgs a) {
+  const int q = threadIdx.x & 15, lx = threadIdx.x >> 4;
+  const int c = q * 4;
+  const int ox = blockIdx.x * 16 + lx, oy0 = blockIdx.y * 8, img = blockIdx.z;
+  if (c >= a.out.c || ox >= a.out.w) return;
+  const int taps = a.kh * a.kw;
+  const int H = a.in.h, W = a.in.w;
+  float4 wk[9];
+  int off[9], dy[9];
+  unsigned xmask = 0;                  // taps whose column lies inside the image (fixed per thread)
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int ky = t / a.kw, kx = t - ky * a.kw;
+    const int dx = kx * a.dw - a.pw;
+    dy[t] = ky * a.dh - a.ph;
+    off[t] = dy[t] * W + dx;
+    if (t < taps && ox + dx >= 0 && ox + dx < W) xmask |= 1u << t;
+    wk[t] = t < taps ? __ldg(reinterpret_cast<const float4*>(a.w + t * a.out.c + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float4 b = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* colp = a.in.p + (size_t)img * H * W + ox;          // one input channel: pixel pitch 1
+  float* dst = a.out.p + a.out.pix(img, oy0, ox) + c;
+  const int orow = a.out.w * a.out.ld;
+  const int ymax = min(oy0 + 8, a.out.h);
+  for (int oy = oy0; oy < ymax; ++oy, dst += orow) {
+    float4 acc = b;
+    const float* rowp = colp + oy * W;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const bool ok = ((xmask >> t) & 1u) && (unsigned)(oy + dy[t]) < (unsigned)H;
+      const float v = ok ? __ldg(rowp + off[t]) : 0.f;
+      acc.x = fmaf(v, wk[t].x, acc.x); acc.y = fmaf(v, wk[t].y, acc.y); acc.z = fmaf(v, wk[t].z, acc.z); acc.w = fmaf(v, wk[t].w, acc.w);
+    }
+    if (a.act) {
+      acc.x = apply_act(acc.x, a.act, a.slope); acc.y = apply_act(acc.y, a.act, a.slope);
+      acc.z = apply_act(acc.z, a.act, a.slope); acc.w = apply_act(acc.w, a.act, a.slope);
+    }
+    *reinterpret_cast<float4*>(dst) = acc;
+  }
+}
+
 typedef CUresult (*ThEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -201,4 +254,30 @@ extern "C" int lfsr_conv2d_thin(const lfsr_tensor* in, const float* w_packed, co
   }
 #undef LAUNCH_THIN
   return check_launch("conv_thin_kernel");
+}
+
+extern "C" int lfsr_conv2d_stem_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d) {
+  if (!tensor_ok(in) || !tensor_ok(out) || !d) return 0;
+  if (in->c != 1 || out->c > 64 || out->c % 4 || out->ld % 4 || ((uintptr_t)out->ptr & 15)) return 0;
+  if (d->stride_h != 1 || d->stride_w != 1 || d->out_perm || d->mul.ptr || d->res.ptr || d->in_scale || d->tail_w) return 0;
+  if (d->shuf_ry > 1 || d->shuf_rx > 1 || d->block_h > 0 || d->block_w > 0 || d->alpha != 1.f) return 0;
+  if (d->kh * d->kw > 9 || d->kh < 1 || d->kw < 1) return 0;
+  if (2 * d->pad_h != d->dil_h * (d->kh - 1) || 2 * d->pad_w != d->dil_w * (d->kw - 1)) return 0;
+  if (out->n != in->n || out->h != in->h || out->w != in->w || out->n > 65535) return 0;
+  if (d->in_perm || in->ld != 1 || (long long)in->h * in->w >= 0x7fffffffLL) return 0;   // MacPI-addressed stems stay on the generic kernel
+  return 1;
+}
+
+extern "C" int lfsr_conv2d_stem(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out, const lfsr_conv_desc* d,
+                                void* stream) {
+  LFSR_REQUIRE(w_packed && lfsr_conv2d_stem_supported(in, out, d), "lfsr_conv2d_stem: unsupported problem");
+  LFSR_REQUIRE((((uintptr_t)w_packed | (uintptr_t)d->bias) & 15) == 0, "lfsr_conv2d_stem: weights and bias must be 16-byte aligned");
+  StemArgs a;
+  a.in = view_of(in); a.out = view_of(out);
+  a.w = w_packed; a.bias = d->bias;
+  a.kh = d->kh; a.kw = d->kw; a.dh = d->dil_h; a.dw = d->dil_w; a.ph = d->pad_h; a.pw = d->pad_w;
+  a.act = d->act; a.slope = d->act_slope;
+  dim3 grid(ceil_div(out->w, 16), ceil_div(out->h, 8), out->n);
+  conv_stem_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("conv_stem_kernel");
 }

@@ -162,6 +162,9 @@ class CudaOps:
                 raise N.LfsrError("conv: tail projection is only available on the tensor-core path (query tail_supported first)")
             N.check(self.lib.lfsr_conv2d_tc(C.byref(tin), pc.w_tc.data_ptr(), C.byref(tout), C.byref(d), st), "lfsr_conv2d_tc")
             return
+        if pc.cin == 1 and self.lib.lfsr_conv2d_stem_supported(C.byref(tin), C.byref(tout), C.byref(d)):
+            N.check(self.lib.lfsr_conv2d_stem(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st), "lfsr_conv2d_stem")
+            return
         if (pc.cout == 20 and pc.cin <= 20 and self.use_thin and
                 self.lib.lfsr_conv2d_thin_supported(C.byref(tin), C.byref(tout), C.byref(d))):
             N.check(self.lib.lfsr_conv2d_thin(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st), "lfsr_conv2d_thin")
