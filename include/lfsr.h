@@ -148,7 +148,7 @@ int lfsr_dwconv_multi(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_
 int lfsr_tap_gather(const lfsr_tensor* taps, int kh, int kw, const float* bias, const lfsr_tensor* res,
                     const lfsr_tensor* out, void* stream);
 /* thin dense conv on the FP32 pipe (packed FFMA2): 16/18/20 input channels read as 20-float pixels, exactly 20 output
- * channels, stride 1, "same" padding, <= 9 taps, any dilation; bias + activation fused; weights packed as for
+ * channels, stride 1, "same" padding, <= 9 taps, any dilation; bias + activation (+ 20-channel multiplier) fused; weights packed as for
  * lfsr_conv2d_f32. The spatial branch of the Track-2 model (MyEfficientLFNet.py:134-141), where a K=8 tf32 MMA costs
  * the same for N=32 as for N=128 and the CUDA cores win. fp32-exact. */
 int lfsr_conv2d_thin_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);

@@ -19,7 +19,7 @@ namespace lfsr {
 constexpr int TH_W = 32, TH_H = 16, TH_CP = 20, TH_NP = TH_CP / 2;   // tile, pixel pitch (floats), output pairs
 
 struct ThinArgs {
-  TView in, out;
+  TView in, out, mul;    // mul: optional elementwise multiplier of the activated output (20 readable floats per pixel)
   const float* w;        // [kh*kw][cin][20]
   const float* bias;     // [20] or null
   int kh, kw, dh, dw, cin, act;
@@ -115,6 +115,14 @@ conv_thin_kernel(const __grid_constant__ ThinArgs a) {
 #pragma unroll
       for (int i = 0; i < TH_CP; ++i) o[i] = apply_act(o[i], a.act, a.slope);
     }
+    if (a.mul.p) {
+      const float4* mp = reinterpret_cast<const float4*>(a.mul.p + a.mul.pix(img, oy, ox));
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const float4 m = mp[i];
+        o[4 * i] *= m.x; o[4 * i + 1] *= m.y; o[4 * i + 2] *= m.z; o[4 * i + 3] *= m.w;
+      }
+    }
     float4* dst = reinterpret_cast<float4*>(a.out.p + a.out.pix(img, oy, ox));
 #pragma unroll
     for (int i = 0; i < 5; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
@@ -205,7 +213,9 @@ extern "C" int lfsr_conv2d_thin_supported(const lfsr_tensor* in, const lfsr_tens
   if (out->c != TH_CP || out->ld % 4 || ((uintptr_t)out->ptr & 15)) return 0;
   // the tile is read as 20-float pixels: the floats behind an 18- or 16-channel view must exist (grouped trunk slices)
   if (in->ld < TH_CP || in->ld % 4 || ((uintptr_t)in->ptr & 15)) return 0;
-  if (d->stride_h != 1 || d->stride_w != 1 || d->in_perm || d->out_perm || d->mul.ptr || d->res.ptr || d->in_scale || d->tail_w) return 0;
+  if (d->stride_h != 1 || d->stride_w != 1 || d->in_perm || d->out_perm || d->res.ptr || d->in_scale || d->tail_w) return 0;
+  if (d->mul.ptr && (d->mul_act || d->mul.c != TH_CP || d->mul.ld % 4 || ((uintptr_t)d->mul.ptr & 15) || d->mul.n != out->n ||
+                     d->mul.h != out->h || d->mul.w != out->w)) return 0;
   if (d->shuf_ry > 1 || d->shuf_rx > 1 || d->block_h > 0 || d->block_w > 0 || d->alpha != 1.f) return 0;
   if (!(d->kh & 1) || !(d->kw & 1) || d->kh * d->kw > 9) return 0;
   if (2 * d->pad_h != d->dil_h * (d->kh - 1) || 2 * d->pad_w != d->dil_w * (d->kw - 1)) return 0;
@@ -221,6 +231,7 @@ extern "C" int lfsr_conv2d_thin(const lfsr_tensor* in, const float* w_packed, co
   LFSR_REQUIRE(((uintptr_t)w_packed & 15) == 0, "lfsr_conv2d_thin: weights must be 16-byte aligned");
   ThinArgs a;
   a.in = view_of(in); a.out = view_of(out);
+  a.mul = d->mul.ptr ? view_of(&d->mul) : null_view();
   a.w = w_packed; a.bias = d->bias;
   a.kh = d->kh; a.kw = d->kw; a.dh = d->dil_h; a.dw = d->dil_w; a.cin = in->c; a.act = d->act; a.slope = d->act_slope;
   a.tiles_x = ceil_div(out->w, TH_W); a.tiles_y = ceil_div(out->h, TH_H);

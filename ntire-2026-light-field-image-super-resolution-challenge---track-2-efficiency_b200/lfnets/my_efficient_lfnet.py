@@ -172,11 +172,11 @@ class get_model(LFNetBase):
         dil = dict(dil=(A, A), pad=(A, A))
         dev_t = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
 
-        def pad_out(w, b=None):
-            """zero output rows up to a multiple of 4 channels: the layer then writes its pad floats too (with zeros, the
-            value they must hold) and qualifies for the 16-byte-granular TMA-store epilogue"""
+        def pad_out(w, b=None, to=None):
+            """zero output rows up to a multiple of 4 channels (or `to`): the layer then writes its pad floats too (with
+            zeros, the value they must hold) and qualifies for the 16-byte-granular TMA-store epilogue / the thin kernel"""
             w = w.detach().float().cpu()
-            n = (w.shape[0] + 3) // 4 * 4 - w.shape[0]
+            n = (to if to is not None else (w.shape[0] + 3) // 4 * 4) - w.shape[0]
             if n:
                 w = torch.cat([w, w.new_zeros((n,) + tuple(w.shape[1:]))], 0)
                 b = None if b is None else torch.cat([b.detach().float().cpu(), torch.zeros(n)])
@@ -192,11 +192,15 @@ class get_model(LFNetBase):
             s["spa0"] = pc(*pad_out(w, b), tc=True, **dil)
             s["spa2"] = pc(*pad_out(st.spatial_branch["2"].weight), tc=True, **dil)
             ab = st.angular_branch
-            s["ang_to"] = pc(ab.to_angular.weight, stride=(A, A), tc=True)
-            s["ang_a0"] = pc(ab.attention["0"].weight)
-            s["ang_a2"] = _dw_pack(ab.attention["2"].weight, device)
-            s["ang_a4"] = pc(ab.attention["4"].weight)
-            s["ang_cv"] = pc(ab.cross_view["0"].weight, pad=(1, 1))
+            # the small angular-resolution tensors are all 20-float pixels (real channels + zeros): every layer of the
+            # attention runs on the thin FFMA2 kernel / the tiled depthwise kernel
+            s["ang_to"] = pc(*pad_out(ab.to_angular.weight), stride=(A, A), tc=True)
+            s["ang_a0"] = pc(*pad_out(ab.attention["0"].weight, to=gs_))
+            dwp = _dw_pack(ab.attention["2"].weight, "cpu")                          # [9][hid]
+            s["ang_a2"] = torch.cat([dwp, dwp.new_zeros(dwp.shape[0], gs_ - dwp.shape[1])], 1).contiguous().to(device)
+            s["ang_hid"] = dwp.shape[1]
+            s["ang_a4"] = pc(*pad_out(ab.attention["4"].weight, to=gs_))
+            s["ang_cv"] = pc(*pad_out(ab.cross_view["0"].weight, to=gs_), pad=(1, 1))
             # expand conv + PixelShuffle(A): output channels padded 18 -> 20 per sub-pixel (nn.PixelShuffle order keeps the
             # A*A sub-pixels innermost), so that the layer writes whole 20-float slots through the TMA-store epilogue
             we = ab.expand["0"].weight.detach().float().cpu()
@@ -281,9 +285,9 @@ class get_model(LFNetBase):
         hA, wA = H // A, W // A
         cat = buf("cat", H, W, CP)
         t18 = buf("t18", H, W, gs)                 # c0 real channels + zero pad, written whole by spa0
-        hid = pk["stages"][0]["ang_a0"].cout
-        ang1, ang4, ang5 = buf("ang1", hA, wA, c0), buf("ang4", hA, wA, c0), buf("ang5", hA, wA, c0)
-        ang2, ang3 = buf("ang2", hA, wA, hid), buf("ang3", hA, wA, hid)
+        hid = pk["stages"][0]["ang_hid"]
+        ang1, ang4, ang5 = buf("ang1", hA, wA, gs), buf("ang4", hA, wA, gs), buf("ang5", hA, wA, gs)
+        ang2, ang3 = buf("ang2", hA, wA, gs), buf("ang3", hA, wA, gs)
         vmean, gmean, gate = buf("vmean", A, A, CP), buf("gmean", 1, 1, CP), buf("gate", 1, 1, CP)
         CU = pk["CU"]
         fu1, fu2 = buf("fu1", H, W, CU), buf("fu2", H, W, CP)
@@ -295,11 +299,11 @@ class get_model(LFNetBase):
             ops.conv(t18[..., 0:c0], st["spa2"], cat[..., 0:gs])
             # angular branch
             ops.conv(xa, st["ang_to"], ang1)
-            ops.conv(ang1, st["ang_a0"], ang2, act=N.ACT_RELU)
+            ops.conv(ang1[..., 0:c0], st["ang_a0"], ang2, act=N.ACT_RELU)
             ops.dwconv(ang2, st["ang_a2"], ang3, 3, 3, act=N.ACT_RELU)
-            ops.conv(ang3, st["ang_a4"], ang4, act=N.ACT_SIGMOID, mul=ang1)
-            ops.conv(ang4, st["ang_cv"], ang5, act=LR, slope=0.1)
-            ops.conv(ang5, st["ang_ex"], cat[..., gs:2 * gs], act=LR, slope=0.1, alpha=st["ang_scale"], res=feat[..., gs:2 * gs],
+            ops.conv(ang3[..., 0:hid], st["ang_a4"], ang4, act=N.ACT_SIGMOID, mul=ang1)
+            ops.conv(ang4[..., 0:c0], st["ang_cv"], ang5, act=LR, slope=0.1)
+            ops.conv(ang5[..., 0:c0], st["ang_ex"], cat[..., gs:2 * gs], act=LR, slope=0.1, alpha=st["ang_scale"], res=feat[..., gs:2 * gs],
                      shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
             # EPI branch: three depthwise+pointwise paths and their fuse conv in one kernel
             ops.mel_epi_branch(xe, st["epi_w"], cat[..., sl[2]], st["epi_klen"], A, 0.1)
