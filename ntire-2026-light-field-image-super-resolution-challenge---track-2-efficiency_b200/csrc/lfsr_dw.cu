@@ -72,6 +72,9 @@ struct DwParams {
   // x tile+halo, out-of-image elements zero filled) instead of ~25 cp.async per thread: staging cost as many
   // instructions as the stencil itself and the kernel is issue-bound at its low (shared-memory limited) occupancy
   int use_tma, tile_floats;
+  // share: all branches read the same channel window (FastConvSSM's four dilations of one tensor): a CTA stages ONE tile
+  // with the largest halo (branch share_b) and runs every branch on it; grid.y then enumerates channel chunks only
+  int share, share_b;
   CUtensorMap tm[DW_MAXB];
 };
 
@@ -170,14 +173,30 @@ __device__ __forceinline__ void dw_compute(const DwParams& p, const DwBranch& B,
   }
 }
 
-__global__ void __launch_bounds__(256)
+// tap weights of this CTA's 16-channel chunk into shared memory: [tap][16] per branch (all branches in share mode)
+__device__ __forceinline__ void dw_stage_taps(const DwParams& p, const DwBranch& B, float* wS, int wofs, int tid) {
+  int wo = 0;
+  const int nrun = p.share ? p.nbr : 1;
+  for (int j = 0; j < nrun; ++j) {
+    const DwBranch& Bj = p.share ? p.br[j] : B;
+    const int nt = Bj.kh * Bj.kw * DW_CH;
+    for (int i = tid; i < nt; i += 256) wS[wo + i] = wofs + (i & 15) < Bj.c ? __ldg(Bj.w + (i >> 4) * Bj.c + wofs + (i & 15)) : 0.f;
+    wo += nt;
+  }
+}
+
+// SHARE = false: 3 CTAs per SM (the stencil is issue/latency bound, occupancy matters more than registers);
+// SHARE = true (one staged tile, all branches): shared memory allows 2 CTAs anyway, so it keeps its registers
+template <bool SHARE>
+__global__ void __launch_bounds__(256, SHARE ? 2 : 3)
 dw_tile_kernel(const __grid_constant__ DwParams p) {
   extern __shared__ __align__(16) float dw_smem[];
   const int tid = threadIdx.x;
   int b = 0;
-  while (b + 1 < p.nbr && (int)blockIdx.y >= p.br[b + 1].item0) ++b;
-  const DwBranch& B = p.br[b];
-  const int chunk = blockIdx.y - B.item0;
+  if (SHARE) b = p.share_b;
+  else while (b + 1 < p.nbr && (int)blockIdx.y >= p.br[b + 1].item0) ++b;
+  const DwBranch& B = p.br[b];                       // the branch whose geometry defines the staged tile
+  const int chunk = SHARE ? (int)blockIdx.y : (int)blockIdx.y - B.item0;
   const int wofs = chunk * DW_CH;
   const int cin0 = B.in_c0 + wofs, cout0 = B.out_c0 + wofs;
   const int hy = (B.kh / 2) * B.dh, hx = (B.kw / 2) * B.dw;
@@ -200,11 +219,11 @@ dw_tile_kernel(const __grid_constant__ DwParams p) {
                    ::"r"(dw_smem_u32(tS)), "l"(&p.tm[b]), "r"(dw_smem_u32(&bar)), "r"(cin0), "r"(tx0 - hx), "r"(ty0 - hy), "r"(img)
                    : "memory");
     }
-    for (int i = tid; i < taps * DW_CH; i += 256) wS[i] = wofs + (i & 15) < B.c ? __ldg(B.w + (i >> 4) * B.c + wofs + (i & 15)) : 0.f;
+    dw_stage_taps(p, B, wS, wofs, tid);
     __syncthreads();                   // taps visible; the barrier was initialised before anybody polls it
     dw_mbar_wait(&bar, 0);
   } else {
-    for (int i = tid; i < taps * DW_CH; i += 256) wS[i] = wofs + (i & 15) < B.c ? __ldg(B.w + (i >> 4) * B.c + wofs + (i & 15)) : 0.f;
+    dw_stage_taps(p, B, wS, wofs, tid);
     // rows of the halo'd tile that lie inside the image; everything else is zero padding
     const int quads_per_row = SW * 4;
     for (int sy = tid >> 7; sy < SH; sy += 2) {       // 128 threads per tile row
@@ -223,9 +242,19 @@ dw_tile_kernel(const __grid_constant__ DwParams p) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
   }
-  if (B.kh == 3 && B.kw == 3) dw_compute<3, 3>(p, B, wS, tS, SW, img, ty0, tx0, cout0, wofs);
-  else if (B.kh == 1 && B.kw == 1) dw_compute<1, 1>(p, B, wS, tS, SW, img, ty0, tx0, cout0, wofs);
-  else dw_compute<0, 0>(p, B, wS, tS, SW, img, ty0, tx0, cout0, wofs);
+  const int nrun = SHARE ? p.nbr : 1;
+  int wo = 0;
+  for (int j = 0; j < nrun; ++j) {
+    const DwBranch& Bj = SHARE ? p.br[j] : B;
+    // a branch with a smaller halo starts further inside the staged tile
+    const int oy_ = hy - (Bj.kh / 2) * Bj.dh, ox_ = hx - (Bj.kw / 2) * Bj.dw;
+    const float* tj = tS + (oy_ * SW + ox_) * DW_CH;
+    const int co = Bj.out_c0 + wofs;
+    if (Bj.kh == 3 && Bj.kw == 3) dw_compute<3, 3>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
+    else if (Bj.kh == 1 && Bj.kw == 1) dw_compute<1, 1>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
+    else dw_compute<0, 0>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
+    wo += Bj.kh * Bj.kw * DW_CH;
+  }
 }
 
 typedef CUresult (*DwEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -317,6 +346,27 @@ static int dw_launch(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_d
     if (tf > tile_floats) tile_floats = tf;
     if (b.kh * b.kw * DW_CH > w_floats) w_floats = b.kh * b.kw * DW_CH;
   }
+  p.share = 0; p.share_b = 0;
+  if (!sa && nbr > 1 && !getenv("LFSR_DW_NO_SHARE")) {
+    bool same = true;
+    size_t best = 0;
+    int wsum = 0;
+    for (int i = 0; i < nbr; ++i) {
+      same = same && br[i].in_c0 == br[0].in_c0 && br[i].c == br[0].c;
+      const size_t tf = (size_t)(DW_TH + 2 * (br[i].kh / 2) * br[i].dil_h) * (DW_TW + 2 * (br[i].kw / 2) * br[i].dil_w);
+      if (tf > best) { best = tf; p.share_b = i; }
+      wsum += br[i].kh * br[i].kw * DW_CH;
+    }
+    // the widest branch must cover the others in both directions
+    for (int i = 0; i < nbr && same; ++i)
+      same = (br[i].kh / 2) * br[i].dil_h <= (br[p.share_b].kh / 2) * br[p.share_b].dil_h &&
+             (br[i].kw / 2) * br[i].dil_w <= (br[p.share_b].kw / 2) * br[p.share_b].dil_w;
+    if (same && (tile_floats + (size_t)wsum) * sizeof(float) + 128 <= 200 * 1024) {
+      p.share = 1;
+      w_floats = wsum;
+      items = ceil_div(br[0].c, DW_CH);
+    }
+  }
   LFSR_REQUIRE(items <= 65535, "lfsr_dwconv_multi: too many channel chunks");
   p.tiles_x = ceil_div(in->w, DW_TW);
   p.w_floats = w_floats;
@@ -340,12 +390,14 @@ static int dw_launch(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_d
   const size_t smem = (tile_floats + (size_t)w_floats) * sizeof(float) + 128;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(dw_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 4096);
+    cudaError_t e = cudaFuncSetAttribute(dw_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 4096);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 4096);
     if (e != cudaSuccess) { set_error("lfsr_dwconv_multi: %s", cudaGetErrorString(e)); return LFSR_ERR_CUDA; }
     smem_set = 200 * 1024 + 4096;
   }
   dim3 grid(p.tiles_x * ceil_div(in->h, DW_TH), items, in->n);
-  dw_tile_kernel<<<grid, 256, smem, st>>>(p);
+  if (p.share) dw_tile_kernel<true><<<grid, 256, smem, st>>>(p);
+  else dw_tile_kernel<false><<<grid, 256, smem, st>>>(p);
   return check_launch("dw_tile_kernel");
 }
 
