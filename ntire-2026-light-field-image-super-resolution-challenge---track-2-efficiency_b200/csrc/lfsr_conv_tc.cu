@@ -71,6 +71,8 @@ struct Params {
   // 3: stride along both, dims (c, x%s, x/s, y%s, image*y/s))
   int amode, out_rows_per_img;
   int pair;                            // 1: launched as 2-CTA clusters that share every weight stage via TMA multicast
+  int twin;                            // 1: a CTA walks PAIRS of M-tiles: one streamed weight stage feeds two activation tiles and both
+                                       //    TMEM accumulator stages (weights are written to / read from shared memory half as often per MMA)
   int w_img_rows;                      // >0: per-image weight sets, this many packed rows apart (streamed B only)
   short tap_off[25][4];
   long long* dbg;                      // optional per-CTA cycle counters (profiles/ experiments), else null
@@ -262,6 +264,14 @@ struct TileCoord {
 // i-th tile of this CTA. Streaming mode: round-robin over (m-tile, cout-chunk). Resident mode: the CTA
 // keeps one cout-chunk's weights in smem, so its chunk is fixed and only the m-tile advances.
 __device__ __forceinline__ bool next_tile(const Params& p, int i, int& m, int& chunk) {
+  if (p.twin) {           // tiles 2*pair, 2*pair + 1 of pair = blockIdx + (i / 2) * gridDim; an odd tail gets a dummy partner
+    const int pr = (int)blockIdx.x + (i >> 1) * (int)gridDim.x;
+    if (2 * pr >= p.m_tiles) return false;
+    m = 2 * pr + (i & 1);
+    if (m >= p.m_tiles) m = -1;
+    chunk = 0;
+    return true;
+  }
   if (p.resident) {
     const int b = fdiv((int)blockIdx.x, p.fd_nchunks);
     chunk = (int)blockIdx.x - b * p.nchunks;
@@ -487,7 +497,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, float* stg, uint3
 // channels of the next cout-chunk take the per-row write-out instead.
 __device__ __forceinline__ void epilogue_tile_tma(const Params& p, const CUtensorMap* tmO, float* stg, uint32_t taddr, int lane, int q,
                                                   const TileCoord& tc_, int g_first, int g_step, uint64_t* tfull_bar,
-                                                  uint32_t tfull_parity) {
+                                                  uint32_t tfull_parity, long long* dbg_rd = nullptr) {
   const int tw_mask = p.TW - 1;
   const int m = q * 32 + lane;
   const int ty = m >> p.tw_shift, tx = m & tw_mask;
@@ -587,8 +597,11 @@ __device__ __forceinline__ void epilogue_tile_tma(const Params& p, const CUtenso
         v[4 * k + 2] = fmaf(v[4 * k + 2], alpha, xv[k].z); v[4 * k + 3] = fmaf(v[4 * k + 3], alpha, xv[k].w);
       }
     }
+    long long trd = 0;
+    if (dbg_rd) trd = clock64();
     if (lane == 0) bulk_wait_read0();          // the TMA unit has finished reading the previous block out of `stg`
     __syncwarp();
+    if (dbg_rd) *dbg_rd += clock64() - trd;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
@@ -688,7 +701,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + p.stages * p.kps * kABytes;
+  uint8_t* sB = smem + p.stages * (p.twin ? 2 : p.kps) * kABytes;
   const int taps = p.kh * p.kw;
   const int nks = taps * p.cgs;
   float* sEpi = reinterpret_cast<float*>(sB + (p.resident ? nks : p.stages * p.kps) * p.b_stage_bytes);   // 8 warps x 4 KB
@@ -736,6 +749,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int ks = 0; ks < nks; ++ks)
           tma_load_2d(sB + ks * p.b_stage_bytes, &tmB, bfull, 0, (chunk * nks + ks) * p.NC);
       }
+      if (p.twin) {        // stage = {A of tile 2p, A of tile 2p+1, one (tap, channel group) of B}; amode 0, streamed B, one chunk
+        int m1, c1;
+        for (int i = 0; next_tile(p, i, m, chunk); i += 2) {
+          next_tile(p, i + 1, m1, c1);
+          const TileCoord t0 = decode_tile(p, m, 0), t1 = decode_tile(p, m1, 0);
+          int cg = 0, tap = 0;
+          for (int ks = 0; ks < nks; ++ks) {
+            if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
+            const int s = s_ring++;
+            mbar_wait(empty + s, ph_ring ^ 1);
+            mbar_expect_tx(full + s, 2u * kABytes + (uint32_t)p.NC * 128u);
+            const short* to = p.tap_off[tap];
+            tma_load_5d(sA + (2 * s) * kABytes, &tmA, full + s, cg * 32, t0.x0 + to[0], t0.vx + to[1], t0.y0 + to[2], t0.nb + to[3]);
+            tma_load_5d(sA + (2 * s + 1) * kABytes, &tmA, full + s, cg * 32, t1.x0 + to[0], t1.vx + to[1], t1.y0 + to[2], t1.nb + to[3]);
+            tma_load_2d(sB + s * p.b_stage_bytes, &tmB, full + s, 0, ks * p.NC);
+            if (++cg == p.cgs) { cg = 0; ++tap; }
+          }
+        }
+      } else
       for (int i = 0; next_tile(p, i, m, chunk); ++i) {
         const TileCoord tc_ = decode_tile(p, m, chunk);
         int cg = 0, tap = 0;
@@ -789,6 +821,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool tap_stages = p.kps == p.cgs;
       int m, chunk;
       if (p.resident && next_tile(p, 0, m, chunk)) mbar_wait(bfull, 0);
+      if (p.twin) {
+        for (int i = 0; next_tile(p, i, m, chunk); i += 2, tcount += 2) {
+          const uint32_t aph = (tcount >> 1) & 1;
+          int cg_i = 0;
+          for (int ks = 0; ks < nks; ++ks) {
+            if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
+            const int s = s_ring++;
+            long long tw0 = 0, tw1 = 0;
+            if (ks == 0) {                       // accumulator 0 drained by the epilogue of the previous pair's first tile
+              if (p.dbg) tw0 = clock64();
+              mbar_wait(tempty + 0, aph ^ 1);
+              if (p.dbg) dbg_acc_wait += clock64() - tw0;
+            }
+            if (p.dbg) tw0 = clock64();
+            mbar_wait(full + s, ph_ring);
+            if (p.dbg) { tw1 = clock64(); dbg_full_wait += tw1 - tw0; }
+            tc_fence_after();
+            const uint64_t a_d0 = a_desc0 + (uint64_t)(2 * s) * (kABytes >> 4), a_d1 = a_d0 + (uint64_t)(kABytes >> 4);
+            const uint64_t b_d = b_desc0 + (uint64_t)s * b_step;
+            const int ksteps = (cg_i == p.cgs - 1) ? ksteps_last : 4;
+            if (ks == 0) umma_stage<true>(tmem_base, a_d0, b_d, idesc, ksteps);
+            else umma_stage<false>(tmem_base, a_d0, b_d, idesc, ksteps);
+            if (ks == 0) {                       // ... and accumulator 1 by the epilogue of its second tile
+              if (p.dbg) tw0 = clock64();
+              mbar_wait(tempty + 1, aph ^ 1);
+              if (p.dbg) { const long long t = clock64() - tw0; dbg_acc_wait += t; tw1 += t; }
+              tc_fence_after();
+              umma_stage<true>(tmem_base + kAccStride, a_d1, b_d, idesc, ksteps);
+            } else {
+              umma_stage<false>(tmem_base + kAccStride, a_d1, b_d, idesc, ksteps);
+            }
+            if (++cg_i == p.cgs) cg_i = 0;
+            umma_commit(empty + s);
+            if (ks + 1 == nks) { umma_commit(tfull + 0); umma_commit(tfull + 1); }
+            if (p.dbg) dbg_mma += clock64() - tw1;
+          }
+        }
+      } else
       for (int i = 0; next_tile(p, i, m, chunk); ++i, ++tcount) {
         const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
         long long tw0 = 0;
@@ -859,7 +929,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         epilogue_tile_tail(p, sTail, taddr, lane, q, tc_, half, 2, tfull + a, aph);
       } else if (p.tma_epi && m_ >= 0) {
         if (p.dbg) tw1 = clock64();
-        epilogue_tile_tma(p, &tmO, stg, taddr, lane, q, tc_, half, 2, tfull + a, aph);
+        epilogue_tile_tma(p, &tmO, stg, taddr, lane, q, tc_, half, 2, tfull + a, aph, p.dbg ? &dbg_ld : nullptr);
         if (p.dbg) dbg_epi += clock64() - tw1;
       } else {
         if (p.dbg) tw0 = clock64();
@@ -875,7 +945,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(tempty + a);
     }
     if (p.tma_epi && lane == 0) bulk_wait0();     // all of this warp's tensor stores have landed
-    if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 8 + 0] = dbg_epi;       // warp 2: no role warp on its sub-partition
+    if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 0] = dbg_ld;        // TMA path: cycles waiting for the store unit to release the staging buffer
     if (p.dbg && threadIdx.x == 0) {
       p.dbg[blockIdx.x * 8 + 1] = dbg_epi;
       p.dbg[blockIdx.x * 8 + 6] = dbg_wait; p.dbg[blockIdx.x * 8 + 7] = clock64() - dbg_t0;
@@ -1381,6 +1451,15 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (max_stages_env >= 2 && p.stages > max_stages_env) p.stages = max_stages_env;
   LFSR_REQUIRE(p.stages >= 2, "lfsr_conv2d_tc: not enough shared memory for two stages");
+  // wide layers whose weights are streamed (they do not fit next to the activation stages) are bound by shared-memory
+  // traffic: per K=8 MMA the weight slice is written by TMA and read by the tensor core (2 x N x 32 B) next to 2 x 4 KB
+  // of activations. Walking M-tile PAIRS halves the weight writes per MMA: one stage = two activation tiles + one slice.
+  static const bool no_twin = getenv("LFSR_TC_NO_TWIN") != nullptr;
+  p.twin = 0;
+  if (!no_twin && !p.resident && !per_image_w && p.kps == 1 && p.nchunks == 1 && p.amode == 0 && p.NC >= 128 && p.m_tiles >= 4) {
+    const int st = (kSmemBudget - kEpiWarps * 4096 - tail_bytes) / (2 * kABytes + p.b_stage_bytes);
+    if (st >= 2) { p.twin = 1; p.stages = st > kMaxStages ? kMaxStages : st; }
+  }
   CUtensorMap tmA, tmB;
   {
     const cuuint64_t ld_b = (cuuint64_t)in->ld * 4;
@@ -1425,10 +1504,11 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("lfsr_conv2d_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return LFSR_ERR_CUDA; }
   }
-  const size_t smem = 1024 + (size_t)p.stages * p.kps * kABytes + (size_t)(p.resident ? nks : p.stages * p.kps) * p.b_stage_bytes +
+  const size_t smem = 1024 + (size_t)p.stages * (p.twin ? 2 : p.kps) * kABytes + (size_t)(p.resident ? nks : p.stages * p.kps) * p.b_stage_bytes +
                       kEpiWarps * 4096 + (size_t)tail_bytes + (2 * kMaxStages + 5) * 8 + 16;
   LFSR_REQUIRE(smem <= 227 * 1024, "lfsr_conv2d_tc: shared memory plan too large");
   int grid = p.total_tiles < sm_count ? p.total_tiles : sm_count;
+  if (p.twin && grid > (p.m_tiles + 1) / 2) grid = (p.m_tiles + 1) / 2;
   if (p.resident && p.nchunks > 1) {
     grid = grid / p.nchunks * p.nchunks;                   // every CTA owns one cout-chunk for its lifetime
     if (grid < p.nchunks) grid = p.nchunks;
@@ -1437,7 +1517,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   // (measured on B200: parity-green but no gain - 3.90 ms with and without at batch 64, the weight stages are L2 hits
   //  that were not the limiter - so it is opt-in: LFSR_TC_PAIR=1)
   static const bool use_pair = getenv("LFSR_TC_PAIR") != nullptr;
-  p.pair = (use_pair && !p.resident && !per_image_w && p.NC >= 128 && p.NC % 16 == 0 && grid >= 2 && p.nchunks == 1) ? 1 : 0;
+  p.pair = (use_pair && !p.twin && !p.resident && !per_image_w && p.NC >= 128 && p.NC % 16 == 0 && grid >= 2 && p.nchunks == 1) ? 1 : 0;
   CUtensorMap tmBh = tmB;
   if (p.pair) {
     grid &= ~1;
@@ -1505,8 +1585,8 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   }
   static const bool verbose = getenv("LFSR_TC_VERBOSE") != nullptr;
   if (verbose)
-    fprintf(stderr, "[lfsr tc] C=%d cout=%d NC=%d k=%dx%d tiles=%d grid=%d stages=%d kps=%d resident=%d pair=%d TH=%d TW=%d vec=%d tma_epi=%d smem=%zu\n",
-            p.C, p.cout, p.NC, p.kh, p.kw, p.total_tiles, grid, p.stages, p.kps, p.resident, p.pair, p.TH, p.TW, p.vec, p.tma_epi, smem);
+    fprintf(stderr, "[lfsr tc] C=%d cout=%d NC=%d k=%dx%d tiles=%d grid=%d stages=%d kps=%d resident=%d pair=%d twin=%d TH=%d TW=%d vec=%d tma_epi=%d smem=%zu\n",
+            p.C, p.cout, p.NC, p.kh, p.kw, p.total_tiles, grid, p.stages, p.kps, p.resident, p.pair, p.twin, p.TH, p.TW, p.vec, p.tma_epi, smem);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;

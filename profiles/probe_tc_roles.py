@@ -25,4 +25,4 @@ for (cin, cout, hw, k, dil, res) in ((64, 64, 160, 1, 1, False), (64, 64, 160, 1
     ntile = B * hw * hw / 128 / 148
     print(f"{k}x{k} {cin}->{cout} @{hw} d{dil} res={int(res)}: tiles/CTA {ntile:.0f} | "
           f"MMA thread: wait-full {d[2]/ntile:.0f}, wait-acc {d[3]/ntile:.0f}, issue {d[4]/ntile:.0f} of {d[5]/ntile:.0f} cyc/tile | "
-          f"epilogue warp0: wait-acc-full {d[6]/ntile:.0f}, tile work warp2 {d[0]/ntile:.0f}, warp0 {d[1]/ntile:.0f} of {d[7]/ntile:.0f} cyc/tile")
+          f"epilogue warp0: wait-acc-full {d[6]/ntile:.0f}, staging-buffer wait {d[0]/ntile:.0f}, tile work {d[1]/ntile:.0f} of {d[7]/ntile:.0f} cyc/tile")
