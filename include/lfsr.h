@@ -119,6 +119,12 @@ int lfsr_integrate_rows(const float* patches, float* out, int ang, int pz, int s
 int lfsr_interp(const float* in, float* out, int n, int h, int w, int scale, int mode, int block_h,
                 int block_w, void* stream);
 
+/* One separable pass of the reference's MATLAB-style imresize (utils/imresize.py:57-102 `resizeAlongDim`), fp64:
+ * out[a][i][b] = sum_p weights[i][p] * in[a][indices[i][p]][b] over a tensor viewed as [outer][in_len][inner]
+ * -> [outer][out_len][inner]; weights / border-reflected indices per output sample as imresize.py:32-55 builds them. */
+int lfsr_resample_f64(const double* in, double* out, const double* weights, const int32_t* indices, int outer,
+                      int in_len, int out_len, int inner, int taps, void* stream);
+
 /* ---- convolutions --------------------------------------------------------------------- */
 /* fp32 CUDA-core implicit GEMM; weights packed [kh*kw][cin][cout]. */
 int lfsr_conv2d_f32(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out,

@@ -85,3 +85,36 @@ extern "C" int lfsr_interp(const float* in, float* out, int n, int h, int w, int
   interp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, n, h, w, scale, mode, block_h, block_w);
   return check_launch("interp_kernel");
 }
+
+
+// ---- MATLAB-style imresize (utils/imresize.py): one separable pass in fp64 ------------------------------------------
+// out[a][i][b] = sum_p w[i][p] * in[a][idx[i][p]][b] over a tensor viewed as [outer][length][inner]; the weights and the
+// border-reflected indices of the resampled dimension come from the host (imresize.py:32-55, a few KB). Terms are added
+// in tap order p = 0..P-1 with separate multiply and add (no FMA contraction), like the reference's numpy sum.
+namespace lfsr {
+__global__ void __launch_bounds__(256)
+resample_f64_kernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ w,
+                    const int* __restrict__ idx, int in_len, int out_len, int inner, int P, long long total) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(t % inner);
+    const long long r = t / inner;
+    const int i = (int)(r % out_len);
+    const long long a = r / out_len;
+    const double* src = in + a * in_len * (long long)inner + b;
+    double acc = 0.0;
+    for (int p = 0; p < P; ++p) acc = __dadd_rn(acc, __dmul_rn(w[i * P + p], src[(long long)idx[i * P + p] * inner]));
+    out[t] = acc;
+  }
+}
+}  // namespace lfsr
+
+extern "C" int lfsr_resample_f64(const double* in, double* out, const double* weights, const int32_t* indices, int outer,
+                                 int in_len, int out_len, int inner, int taps, void* stream) {
+  LFSR_REQUIRE(in && out && weights && indices, "lfsr_resample_f64: null pointer");
+  LFSR_REQUIRE(outer > 0 && in_len > 0 && out_len > 0 && inner > 0 && taps > 0, "lfsr_resample_f64: bad geometry");
+  const long long total = (long long)outer * out_len * inner;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  lfsr::resample_f64_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, weights, indices, in_len, out_len, inner, taps, total);
+  return lfsr::check_launch("resample_f64_kernel");
+}

@@ -110,3 +110,68 @@ def cal_metrics(label_sai: np.ndarray, out_sai: np.ndarray, ang: int):
     pm = psnr.sum() / vp if vp > 0 else 0.0
     sm = ssim.sum() / vs if vs > 0 else 0.0
     return float(pm), float(sm), psnr, ssim
+
+
+# ---------------------------------------------------------------------------------------------
+# MATLAB-style imresize (utils/imresize.py): separable, antialiased when shrinking, symmetric border
+# ---------------------------------------------------------------------------------------------
+def _cubic(x):
+    """Keys kernel with A = -0.5 (utils/imresize.py:24-30)."""
+    ax = np.abs(np.asarray(x, dtype=np.float64))
+    ax2, ax3 = ax * ax, ax * ax * ax
+    return (1.5 * ax3 - 2.5 * ax2 + 1) * (ax <= 1) + (-0.5 * ax3 + 2.5 * ax2 - 4 * ax + 2) * ((1 < ax) & (ax <= 2))
+
+
+def _triangle(x):
+    """utils/imresize.py:17-22."""
+    x = np.asarray(x, dtype=np.float64)
+    return (x + 1) * ((x >= -1) & (x < 0)) + (1 - x) * ((x <= 1) & (x >= 0))
+
+
+def imresize_contributions(in_length: int, out_length: int, scale: float, method: str = "bicubic"):
+    """(weights [out, P], indices [out, P] int32) of one dimension (utils/imresize.py:32-55): output sample i (1-based
+    x = i + 1) sits at u = x/scale + 0.5 (1 - 1/scale); when shrinking the kernel is stretched by 1/scale (antialiasing);
+    weights are normalised per output sample; indices are reflected about the borders (symmetric, edge repeated);
+    columns that are zero for every output sample are dropped."""
+    kernel = _cubic if method == "bicubic" else _triangle
+    k_width = 4.0
+    if scale < 1:
+        h = lambda t: scale * kernel(scale * t)
+        kernel_width = k_width / scale
+    else:
+        h, kernel_width = kernel, k_width
+    x = np.arange(1, out_length + 1, dtype=np.float64)
+    u = x / scale + 0.5 * (1 - 1 / scale)
+    left = np.floor(u - kernel_width / 2)
+    P = int(np.ceil(kernel_width)) + 2
+    ind = (left[:, None] + np.arange(P) - 1).astype(np.int32)
+    w = h(u[:, None] - ind - 1)
+    w = w / w.sum(axis=1, keepdims=True)
+    aux = np.concatenate((np.arange(in_length), np.arange(in_length - 1, -1, -1))).astype(np.int32)
+    ind = aux[np.mod(ind, aux.size)]
+    keep = np.nonzero(np.any(w, axis=0))[0]
+    return np.ascontiguousarray(w[:, keep]), np.ascontiguousarray(ind[:, keep])
+
+
+def imresize(img: np.ndarray, scalar_scale=None, method: str = "bicubic", output_shape=None) -> np.ndarray:
+    """utils/imresize.py:104-145 ("vec" mode): float64 arithmetic, the dimension with the smaller scale first, uint8 inputs
+    are clipped to [0, 255] and rounded half-to-even after EACH pass (imresize.py:87-91)."""
+    if scalar_scale is not None:
+        scale = [float(scalar_scale)] * 2
+        out_size = [int(np.ceil(scale[k] * img.shape[k])) for k in range(2)]
+    else:
+        scale = [1.0 * output_shape[k] / img.shape[k] for k in range(2)]
+        out_size = list(output_shape)
+    B = img.copy()
+    two_d = B.ndim == 2
+    if two_d:
+        B = B[:, :, None]
+    for dim in np.argsort(np.array(scale)):
+        w, ind = imresize_contributions(img.shape[dim], out_size[dim], scale[dim], method)
+        src = B.astype(np.float64)
+        if dim == 0:
+            out = np.einsum("op,opwc->owc", w, src[ind])
+        else:
+            out = np.einsum("op,hopc->hoc", w, src[:, ind])
+        B = np.around(np.clip(out, 0, 255)).astype(np.uint8) if img.dtype == np.uint8 else out
+    return B[:, :, 0] if two_d else B

@@ -74,7 +74,7 @@ def main():
                 out[f"{tag}_sumsq"] = np.float64((y.astype(np.float64) ** 2).sum())
         np.savez_compressed(os.path.join(gold, f"{name}_x{scale}.npz"), **out)
 
-    if opts.only:
+    if opts.only and opts.only != "imresize":
         return
     # ---- patch pipeline goldens from the reference's utils/utils.py ------------------------------
     import utils.utils as U  # the reference's
@@ -112,6 +112,26 @@ def main():
     pipe["met_label"], pipe["met_out"] = lab, noisy
     pipe["met_psnr"], pipe["met_ssim"] = np.float64(p_ref), np.float64(s_ref)
     np.savez_compressed(os.path.join(gold, "pipeline.npz"), **pipe)
+
+    # ---- utils/imresize.py: the reference function on seeded arrays ---------------------
+    import utils.imresize as RI  # the reference's
+    assert os.path.abspath(RI.__file__).startswith(os.path.abspath(ref_shim.REF_ROOT)), RI.__file__
+    rr = np.random.RandomState(31)
+    res = {}
+    cases = {"y_down4": (rr.random_sample((64, 80)), dict(scalar_scale=0.25)),
+             "cbcr_up4": (rr.random_sample((24, 20, 2)), dict(scalar_scale=4)),
+             "tri_down2": (rr.random_sample((37, 45)), dict(scalar_scale=0.5, method="bilinear")),
+             "shape": (rr.random_sample((30, 50, 3)), dict(output_shape=(45, 20))),
+             "u8_down3": ((rr.random_sample((48, 39, 3)) * 255).astype(np.uint8), dict(scalar_scale=1.0 / 3))}
+    for key, (arr, kw) in cases.items():
+        ref_out = RI.imresize(arr, **kw)
+        mine_out = lf_oracle.imresize(arr, **kw)
+        d = np.abs(ref_out.astype(np.float64) - mine_out.astype(np.float64)).max()
+        print(f"imresize {key}: {arr.shape} {arr.dtype} -> {ref_out.shape} {ref_out.dtype}, oracle-vs-reference max|d| = {d:.3e}")
+        assert ref_out.shape == mine_out.shape and ref_out.dtype == mine_out.dtype
+        assert d <= (0 if arr.dtype == np.uint8 else 1e-13), key
+        res[key + "_in"], res[key + "_out"] = arr, ref_out
+    np.savez_compressed(os.path.join(gold, "imresize.npz"), **res)
 
     # ---- the reference's train.test() end to end on a synthetic scene (row L of SURVEY 8a) --------
     import train as T  # the reference's

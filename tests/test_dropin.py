@@ -53,6 +53,8 @@ for name, n in (('MyEfficientLFNet', 547540), ('EPIT', 1470080), ('DistgSSR', 35
     net = m.get_model(a); net.apply(m.weights_init); m.get_loss(a)
     assert sum(p.numel() for p in net.parameters()) == n, name
     net.cpu(); net.eval(); net.load_state_dict(net.state_dict())
+import utils.imresize as RI
+assert all(hasattr(RI, n) for n in ('imresize', 'deriveSizeFromScale', 'deriveScaleFromSize'))
 import utils.utils as U
 for sym in ('LFdivide', 'LFintegrate', 'cal_metrics', 'ImageExtend', 'ycbcr2rgb', 'ExcelFile', 'create_dir', 'Logger', 'rearrange', 'np', 'torch', 'os'):
     assert hasattr(U, sym), sym

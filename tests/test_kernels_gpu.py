@@ -511,3 +511,26 @@ def test_conv_thin(ops, ref, cin, k, dil, hw, bias, act):
     assert ops.lib.lfsr_launch_count() == l0 + 1
     ref.conv(x, pc, fb[..., 40:60], act=act, slope=0.1)
     assert (fa - fb).abs().max().item() <= 2e-5
+
+
+def test_imresize_vs_reference_golden_and_oracle(golden_dir):
+    """utils/imresize.py on the GPU against outputs of the unmodified reference (oracle/make_golden.py) and
+    against the oracle on other shapes; uint8 results must match exactly, float64 to 1e-12"""
+    g = np.load(f"{golden_dir}/imresize.npz")
+    kws = {"y_down4": dict(scalar_scale=0.25), "cbcr_up4": dict(scalar_scale=4), "tri_down2": dict(scalar_scale=0.5, method="bilinear"),
+           "shape": dict(output_shape=(45, 20)), "u8_down3": dict(scalar_scale=1.0 / 3)}
+    for key, kw in kws.items():
+        out = lfsr_b200.lfutils.imresize(g[key + "_in"], **kw)
+        ref_out = g[key + "_out"]
+        assert isinstance(out, np.ndarray) and out.shape == ref_out.shape and out.dtype == ref_out.dtype, key
+        if out.dtype == np.uint8:
+            assert np.array_equal(out, ref_out), key
+        else:
+            assert np.abs(out - ref_out).max() <= 1e-12, key
+    rs = np.random.RandomState(3)
+    for shape, kw in (((160, 160), dict(scalar_scale=0.5)), ((33, 47, 3), dict(scalar_scale=2)), ((64, 64), dict(output_shape=(17, 90)))):
+        a = rs.random_sample(shape)
+        assert np.abs(lfsr_b200.lfutils.imresize(a, **kw) - lf_oracle.imresize(a, **kw)).max() <= 1e-12
+    t = torch.from_numpy(g["y_down4_in"]).to(DEV)
+    out_t = lfsr_b200.lfutils.imresize(t, scalar_scale=0.25)
+    assert out_t.is_cuda and out_t.dtype == torch.float64 and np.abs(out_t.cpu().numpy() - g["y_down4_out"]).max() <= 1e-12

@@ -57,3 +57,21 @@ def test_cpu_input_without_backend_raises():
     net = lfsr_b200.load_net("MyEfficientLFNet", 5, 4)
     with pytest.raises(lfsr_b200.LfsrError):
         net(torch.zeros(1, 1, 40, 40))
+
+
+def test_oracle_imresize_matches_reference_golden():
+    """oracle.lf_oracle.imresize == outputs of the unmodified utils/imresize.py (oracle/make_golden.py), and
+    the product's host-side contribution tables equal the oracle's"""
+    from oracle import lf_oracle
+    g = np.load(f"{weights.GOLDEN_DIR}/imresize.npz")
+    kws = {"y_down4": dict(scalar_scale=0.25), "cbcr_up4": dict(scalar_scale=4), "tri_down2": dict(scalar_scale=0.5, method="bilinear"),
+           "shape": dict(output_shape=(45, 20)), "u8_down3": dict(scalar_scale=1.0 / 3)}
+    for key, kw in kws.items():
+        out = lf_oracle.imresize(g[key + "_in"], **kw)
+        assert out.dtype == g[key + "_out"].dtype and np.abs(out.astype(np.float64) - g[key + "_out"].astype(np.float64)).max() <= 1e-13
+    for n_in, n_out, sc, m in ((64, 16, 0.25, "bicubic"), (24, 96, 4.0, "bicubic"), (37, 19, 0.5, "bilinear"), (50, 20, 0.4, "bicubic")):
+        w0, i0 = lf_oracle.imresize_contributions(n_in, n_out, sc, m)
+        w1, i1 = lfsr_b200.lfutils.resize_contributions(n_in, n_out, sc, m)
+        assert np.array_equal(w0, w1) and np.array_equal(i0, i1)
+    with pytest.raises(lfsr_b200.LfsrError):
+        lfsr_b200.lfutils.imresize(np.zeros((8, 8)), scalar_scale=2)        # no CPU fallback
