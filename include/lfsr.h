@@ -119,6 +119,12 @@ int lfsr_integrate_rows(const float* patches, float* out, int ang, int pz, int s
 int lfsr_interp(const float* in, float* out, int n, int h, int w, int scale, int mode, int block_h,
                 int block_w, void* stream);
 
+/* Colour tail of test() (train.py:332-335 + utils/utils.py:191-204 `ycbcr2rgb`): SR Y mosaic [(a1 h), (a2 w)] and the
+ * CbCr mosaics of the same size -> uint8 RGB views [a1][a2][h][w][3]; fp64, uint8 by truncation after clip(0,1)*255.
+ * mat_inv255 = inv(M_BT601) * 255 (row-major 3x3) and offset = inv(M) @ [16,128,128] come from the host (host pointers). */
+int lfsr_ycbcr_to_rgb8(const float* y, const float* cb, const float* cr, unsigned char* rgb, int ang, int h, int w,
+                       const double* mat_inv255, const double* offset, void* stream);
+
 /* One separable pass of the reference's MATLAB-style imresize (utils/imresize.py:57-102 `resizeAlongDim`), fp64:
  * out[a][i][b] = sum_p weights[i][p] * in[a][indices[i][p]][b] over a tensor viewed as [outer][in_len][inner]
  * -> [outer][out_len][inner]; weights / border-reflected indices per output sample as imresize.py:32-55 builds them. */

@@ -37,11 +37,7 @@ def main(args):
                 ang = int(data_info[0][0].item())
                 sr = _scene.super_resolve_scene(net, Lr_SAI_y.squeeze().to(device), ang, args.scale_factor,
                                                 args.patch_size_for_test, args.stride_for_test, args.minibatch)
-                try:
-                    _write_views(save_dir, lf_name[0], sr.cpu()[None, None], cbcr, args.angRes_out)
-                except ImportError:
-                    import numpy as np
-                    np.save(str(save_dir.joinpath(lf_name[0] + "_Sr_SAI_y.npy")), sr.cpu().numpy())
+                _write_views(save_dir, lf_name[0], sr, cbcr, args.angRes_out)
                 print("scene %s -> %s" % (lf_name[0], save_dir))
 
 

@@ -146,3 +146,45 @@ extern "C" int lfsr_integrate_rows(const float* patches, float* out, int ang, in
   }
   return check_launch("integrate_kernel");
 }
+
+
+// ---- colour tail of test() (train.py:329-341, utils/utils.py:191-204): Y mosaic + CbCr mosaic -> uint8 RGB views -------
+// rgb8[u][v][y][x][c] = uint8(clip(M[c][0]*Y + M[c][1]*Cb + M[c][2]*Cr - off[c], 0, 1) * 255), fp64 with separate multiplies and
+// adds in the reference's left-to-right order (no FMA contraction) and truncation like numpy's astype('uint8'); the
+// (a1 h)(a2 w) -> a1 a2 h w view split is folded into the store address. 1 byte per channel leaves the GPU, not 4.
+namespace lfsr {
+struct ColourMat { double m[9]; double off[3]; };
+__global__ void __launch_bounds__(256)
+ycbcr_rgb8_kernel(const float* __restrict__ y, const float* __restrict__ cb, const float* __restrict__ cr,
+                  unsigned char* __restrict__ rgb, int ang, int h, int w, ColourMat cm) {
+  const int W = ang * w;
+  const long long total = (long long)ang * h * W;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(t % W), Y = (int)(t / W);
+    const int u = Y / h, yy = Y - u * h, v = X / w, xx = X - v * w;
+    const double a = (double)y[t], b = (double)cb[t], c = (double)cr[t];
+    unsigned char* dst = rgb + ((((long long)u * ang + v) * h + yy) * w + xx) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double r = __dadd_rn(__dadd_rn(__dmul_rn(cm.m[3 * k], a), __dmul_rn(cm.m[3 * k + 1], b)), __dmul_rn(cm.m[3 * k + 2], c));
+      r = __dadd_rn(r, -cm.off[k]);
+      r = r < 0.0 ? 0.0 : (r > 1.0 ? 1.0 : r);          // numpy clip (NaN propagates there; inputs here are finite)
+      dst[k] = (unsigned char)(int)__dmul_rn(r, 255.0);
+    }
+  }
+}
+}  // namespace lfsr
+
+extern "C" int lfsr_ycbcr_to_rgb8(const float* y, const float* cb, const float* cr, unsigned char* rgb, int ang, int h, int w,
+                                  const double* mat_inv255, const double* offset, void* stream) {
+  LFSR_REQUIRE(y && cb && cr && rgb && mat_inv255 && offset, "lfsr_ycbcr_to_rgb8: null pointer");
+  LFSR_REQUIRE(ang > 0 && h > 0 && w > 0, "lfsr_ycbcr_to_rgb8: bad geometry");
+  lfsr::ColourMat cm;
+  for (int i = 0; i < 9; ++i) cm.m[i] = mat_inv255[i];
+  for (int i = 0; i < 3; ++i) cm.off[i] = offset[i];
+  const long long total = (long long)ang * h * ang * w;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  lfsr::ycbcr_rgb8_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(y, cb, cr, rgb, ang, h, w, cm);
+  return lfsr::check_launch("ycbcr_rgb8_kernel");
+}

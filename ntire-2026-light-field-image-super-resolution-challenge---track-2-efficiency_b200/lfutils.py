@@ -195,3 +195,51 @@ def imresize(I, scalar_scale=None, method="bicubic", output_shape=None, mode="ve
         cur = cur[:, :, 0]
     cur = cur.to(home)
     return cur.numpy() if as_numpy else cur
+
+
+# ---- colour / BMP tail of test() (train.py:329-341) -------------------------------------------------------------------------
+_BT601 = np.array([[65.481, 128.553, 24.966], [-37.797, -74.203, 112.0], [112.0, -93.786, -18.214]])
+
+
+def sai_to_rgb8_views(sr_y: torch.Tensor, sr_cbcr: torch.Tensor, angRes: int) -> torch.Tensor:
+    """Sr_SAI_y [.., (a1 h), (a2 w)] + Sr_SAI_cbcr [.., 2, (a1 h), (a2 w)] -> uint8 [a1, a2, h, w, 3] on the device:
+    torch.cat + ycbcr2rgb (fp64) + clip(0,1)*255 + astype(uint8) + the view rearrange of train.py:332-335 in one kernel."""
+    y = sr_y.reshape(sr_y.shape[-2:])
+    cbcr = sr_cbcr.reshape(2, *sr_cbcr.shape[-2:])
+    if cbcr.shape[-2:] != y.shape:
+        raise ValueError(f"Y {tuple(y.shape)} and CbCr {tuple(cbcr.shape)} mosaics differ in size")
+    dev = _device_for(y)
+    if dev.type != "cuda":
+        raise N.LfsrError("lfsr_b200 needs a CUDA device (sm_100a); there is no CPU fallback for this path")
+    H, W = y.shape
+    if H % angRes or W % angRes:
+        raise ValueError(f"mosaic {H}x{W} is not divisible by angRes={angRes}")
+    y = y.to(dev, torch.float32).contiguous()
+    cbcr = cbcr.to(dev, torch.float32).contiguous()
+    inv = np.linalg.inv(_BT601)                                   # exactly the reference's constants (utils/utils.py:192-198)
+    offset = np.ascontiguousarray(np.matmul(inv, np.array([16, 128, 128])))
+    inv255 = np.ascontiguousarray(inv * 255)
+    out = torch.empty((angRes, angRes, H // angRes, W // angRes, 3), dtype=torch.uint8, device=dev)
+    N.check(N.load().lfsr_ycbcr_to_rgb8(y.data_ptr(), cbcr[0].data_ptr(), cbcr[1].data_ptr(), out.data_ptr(), angRes, H // angRes,
+                                        W // angRes, inv255.ctypes.data, offset.ctypes.data,
+                                        torch.cuda.current_stream(dev).cuda_stream), "lfsr_ycbcr_to_rgb8")
+    return out
+
+
+def write_bmp(path, img) -> None:
+    """[h, w, 3] uint8 RGB -> 24-bit uncompressed BMP, byte-identical to what imageio.imwrite (Pillow's BmpImagePlugin)
+    produces for such an array: 14-byte file header, 40-byte BITMAPINFOHEADER (96 dpi = 3780 px/m), bottom-up BGR rows
+    padded to 4 bytes."""
+    import struct
+    a = np.ascontiguousarray(img.cpu().numpy() if torch.is_tensor(img) else img)
+    if a.ndim != 3 or a.shape[2] != 3 or a.dtype != np.uint8:
+        raise ValueError(f"expected [h, w, 3] uint8, got {a.shape} {a.dtype}")
+    h, w, _ = a.shape
+    stride = (w * 3 + 3) & ~3
+    rows = np.zeros((h, stride), dtype=np.uint8)
+    rows[:, : w * 3] = a[::-1, :, ::-1].reshape(h, w * 3)
+    image = h * stride
+    with open(path, "wb") as f:
+        f.write(b"BM" + struct.pack("<IHHI", 14 + 40 + image, 0, 0, 14 + 40))
+        f.write(struct.pack("<IiiHHIIiiII", 40, w, h, 1, 24, 0, image, 3780, 3780, 0, 0))
+        f.write(rows.tobytes())

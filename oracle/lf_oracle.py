@@ -175,3 +175,26 @@ def imresize(img: np.ndarray, scalar_scale=None, method: str = "bicubic", output
             out = np.einsum("op,hopc->hoc", w, src[:, ind])
         B = np.around(np.clip(out, 0, 255)).astype(np.uint8) if img.dtype == np.uint8 else out
     return B[:, :, 0] if two_d else B
+
+
+# ---------------------------------------------------------------------------------------------
+# colour tail of test() (train.py:329-341, utils/utils.py:191-204)
+# ---------------------------------------------------------------------------------------------
+def ycbcr2rgb(x: np.ndarray) -> np.ndarray:
+    """utils/utils.py:191-204: inverse BT.601 in fp64, term by term, left to right."""
+    mat = np.array([[65.481, 128.553, 24.966], [-37.797, -74.203, 112.0], [112.0, -93.786, -18.214]])
+    mat_inv = np.linalg.inv(mat)
+    offset = np.matmul(mat_inv, np.array([16, 128, 128]))
+    mat_inv = mat_inv * 255
+    y = np.zeros(x.shape, dtype="double")
+    for k in range(3):
+        y[:, :, k] = mat_inv[k, 0] * x[:, :, 0] + mat_inv[k, 1] * x[:, :, 1] + mat_inv[k, 2] * x[:, :, 2] - offset[k]
+    return y
+
+
+def sai_to_rgb8_views(sr_y: np.ndarray, sr_cbcr: np.ndarray, ang: int) -> np.ndarray:
+    """train.py:332-335: cat(Y, CbCr) -> ycbcr2rgb -> clip(0,1)*255 -> uint8 (truncation) -> [a1, a2, h, w, 3]."""
+    ycbcr = np.concatenate([sr_y[None], sr_cbcr], 0).transpose(1, 2, 0)           # float32 [H, W, 3]
+    rgb = (ycbcr2rgb(ycbcr).clip(0, 1) * 255).astype("uint8")
+    H, W, _ = rgb.shape
+    return np.ascontiguousarray(rgb.reshape(ang, H // ang, ang, W // ang, 3).transpose(0, 2, 1, 3, 4))

@@ -133,6 +133,26 @@ def main():
         res[key + "_in"], res[key + "_out"] = arr, ref_out
     np.savez_compressed(os.path.join(gold, "imresize.npz"), **res)
 
+    # ---- colour / BMP tail: the reference's ycbcr2rgb + train.py:332-335, and Pillow's BMP bytes ----------
+    import utils.utils as RU  # the reference's
+    assert os.path.abspath(RU.__file__).startswith(os.path.abspath(ref_shim.REF_ROOT)), RU.__file__
+    from einops import rearrange as _re
+    rc = np.random.RandomState(41)
+    sy = (rc.random_sample((1, 1, 5 * 12, 5 * 14)) * 1.2 - 0.1).astype(np.float32)          # some values outside [0, 1]
+    scbcr = (rc.random_sample((1, 2, 5 * 12, 5 * 14))).astype(np.float32)
+    ycbcr = torch.cat((torch.from_numpy(sy), torch.from_numpy(scbcr)), dim=1)
+    rgb = (RU.ycbcr2rgb(ycbcr.squeeze().permute(1, 2, 0).numpy()).clip(0, 1) * 255).astype("uint8")
+    views = _re(rgb, "(a1 h) (a2 w) c -> a1 a2 h w c", a1=5, a2=5)
+    mine_v = lf_oracle.sai_to_rgb8_views(sy[0, 0], scbcr[0], 5)
+    assert np.array_equal(views, mine_v), "colour tail oracle != reference"
+    import io
+    from PIL import Image          # imageio.imwrite of the reference writes .bmp through Pillow's BmpImagePlugin
+    bio = io.BytesIO()
+    Image.fromarray(views[1, 3]).save(bio, format="BMP")
+    np.savez_compressed(os.path.join(gold, "colour_tail.npz"), sr_y=sy, sr_cbcr=scbcr, views=views,
+                        bmp_view_1_3=np.frombuffer(bio.getvalue(), dtype=np.uint8))
+    print("colour tail: oracle == reference on", views.shape, "; BMP golden", len(bio.getvalue()), "bytes")
+
     # ---- the reference's train.test() end to end on a synthetic scene (row L of SURVEY 8a) --------
     import train as T  # the reference's
     name, scale = "MyEfficientLFNet", 4

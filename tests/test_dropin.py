@@ -102,3 +102,9 @@ def test_entry_point_end_to_end(tmp_path):
                          "--use_pre_ckpt", "", "--synthetic", "1", "--synthetic_size", "32", "--path_log", str(tmp_path) + "/",
                          "--data_name", "Synthetic"], cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r2.returncode == 0, r2.stderr[-3000:]
+    # the BMP tail (train.py:337-341): 25 CodaBench-named views per scene, 24-bit BMP of the x4 / x2 view size
+    for root, side in ((out, 160), (tmp_path / "SR_5x5_2x" / "Synthetic" / "DistgSSR" / "results" / "TEST", 64)):
+        bmps = sorted(root.rglob("View_*_*.bmp"))
+        assert len(bmps) == 25 and bmps[0].name == "View_0_0.bmp", (root, len(bmps))
+        head = bmps[7].read_bytes()[:30]
+        assert head[:2] == b"BM" and int.from_bytes(head[18:22], "little") == side and int.from_bytes(head[28:30], "little") == 24

@@ -534,3 +534,20 @@ def test_imresize_vs_reference_golden_and_oracle(golden_dir):
     t = torch.from_numpy(g["y_down4_in"]).to(DEV)
     out_t = lfsr_b200.lfutils.imresize(t, scalar_scale=0.25)
     assert out_t.is_cuda and out_t.dtype == torch.float64 and np.abs(out_t.cpu().numpy() - g["y_down4_out"]).max() <= 1e-12
+
+
+def test_colour_tail_and_bmp_vs_reference_golden(golden_dir, tmp_path):
+    """Y + CbCr mosaics -> uint8 RGB views on the device, bit-exact to the reference's fp64 numpy tail
+    (oracle/make_golden.py), and BMP files byte-identical to Pillow's (the writer behind imageio.imwrite)"""
+    g = np.load(f"{golden_dir}/colour_tail.npz")
+    sy, sc = torch.from_numpy(g["sr_y"]), torch.from_numpy(g["sr_cbcr"])
+    v = lfsr_b200.lfutils.sai_to_rgb8_views(sy.to(DEV), sc, 5)
+    assert v.is_cuda and v.dtype == torch.uint8 and np.array_equal(v.cpu().numpy(), g["views"])
+    rs = np.random.RandomState(2)
+    y2 = (rs.random_sample((5 * 37, 5 * 29)) * 1.4 - 0.2).astype(np.float32)
+    c2 = rs.random_sample((2, 5 * 37, 5 * 29)).astype(np.float32)
+    v2 = lfsr_b200.lfutils.sai_to_rgb8_views(torch.from_numpy(y2), torch.from_numpy(c2), 5)
+    assert np.array_equal(v2.cpu().numpy(), lf_oracle.sai_to_rgb8_views(y2, c2, 5))
+    p = tmp_path / "View_1_3.bmp"
+    lfsr_b200.lfutils.write_bmp(str(p), v[1, 3])
+    assert np.array_equal(np.frombuffer(p.read_bytes(), dtype=np.uint8), g["bmp_view_1_3"])

@@ -75,3 +75,15 @@ def test_oracle_imresize_matches_reference_golden():
         assert np.array_equal(w0, w1) and np.array_equal(i0, i1)
     with pytest.raises(lfsr_b200.LfsrError):
         lfsr_b200.lfutils.imresize(np.zeros((8, 8)), scalar_scale=2)        # no CPU fallback
+
+
+def test_oracle_colour_tail_and_bmp_writer(tmp_path):
+    """oracle colour tail == the reference's (committed golden); write_bmp == Pillow's bytes (host logic, no GPU)"""
+    from oracle import lf_oracle
+    g = np.load(f"{weights.GOLDEN_DIR}/colour_tail.npz")
+    assert np.array_equal(lf_oracle.sai_to_rgb8_views(g["sr_y"][0, 0], g["sr_cbcr"][0], 5), g["views"])
+    p = tmp_path / "v.bmp"
+    lfsr_b200.lfutils.write_bmp(str(p), g["views"][1, 3])
+    assert np.array_equal(np.frombuffer(p.read_bytes(), dtype=np.uint8), g["bmp_view_1_3"])
+    with pytest.raises(lfsr_b200.LfsrError):
+        lfsr_b200.lfutils.sai_to_rgb8_views(torch.zeros(10, 10), torch.zeros(2, 10, 10), 5)

@@ -3,26 +3,24 @@ imports (`from train import test`). Training (train.py:20-282) is outside this r
 
 `test()` keeps the reference's signature and return value but runs the patch loop on the device:
 LFdivide -> batched forward (args.minibatch patches per call instead of minibatch_for_test = 1 with
-a host round trip per patch) -> LFintegrate -> PSNR/SSIM, all on liblfsr_b200 kernels; one D2H copy
-of the stitched SR mosaic per scene feeds the unchanged YCbCr->RGB->BMP tail."""
-import numpy as np
+a host round trip per patch) -> LFintegrate -> PSNR/SSIM -> YCbCr->RGB uint8 views, all on liblfsr_b200
+kernels; one D2H copy of the uint8 views per scene feeds the BMP writer."""
 import torch
-from einops import rearrange
 
-from utils.utils import ycbcr2rgb
 from lfsr_b200 import scene as _scene
+from lfsr_b200 import lfutils as _lfutils
 
 
 def _write_views(save_dir, name, sr_sai_y, cbcr, ang):
-    import imageio
+    """Colour tail of the reference's test() (train.py:329-341): cat(Y, CbCr) -> ycbcr2rgb -> clip*255 -> uint8 -> one
+    View_i_j.bmp per view. The conversion runs on the device (lfsr_ycbcr_to_rgb8, bit-exact to the reference's fp64 numpy
+    arithmetic) so only 1 byte per channel crosses PCIe; the BMP files are byte-identical to imageio.imwrite's."""
     d = save_dir.joinpath(name)
     d.mkdir(exist_ok=True)
-    ycbcr = torch.cat((sr_sai_y, cbcr), dim=1)
-    rgb = (ycbcr2rgb(ycbcr.squeeze().permute(1, 2, 0).numpy()).clip(0, 1) * 255).astype("uint8")
-    views = rearrange(rgb, "(a1 h) (a2 w) c -> a1 a2 h w c", a1=ang, a2=ang)
+    views = _lfutils.sai_to_rgb8_views(sr_sai_y, cbcr, ang).cpu().numpy()
     for i in range(ang):
         for j in range(ang):
-            imageio.imwrite(str(d) + "/View_%d_%d.bmp" % (i, j), views[i, j])
+            _lfutils.write_bmp(str(d) + "/View_%d_%d.bmp" % (i, j), views[i, j])
 
 
 def test(test_loader, device, net, args, save_dir=None):
@@ -39,8 +37,5 @@ def test(test_loader, device, net, args, save_dir=None):
         ssims.append(ssim)
         names.append(LF_name[0])
         if save_dir is not None:
-            try:
-                _write_views(save_dir, LF_name[0], sr.cpu()[None, None], Sr_SAI_cbcr, args.angRes_out)
-            except ImportError:
-                np.save(str(save_dir.joinpath(LF_name[0] + "_Sr_SAI_y.npy")), sr.cpu().numpy())  # imageio absent
+            _write_views(save_dir, LF_name[0], sr, Sr_SAI_cbcr, args.angRes_out)
     return psnrs, ssims, names
