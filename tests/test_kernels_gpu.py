@@ -551,3 +551,28 @@ def test_colour_tail_and_bmp_vs_reference_golden(golden_dir, tmp_path):
     p = tmp_path / "View_1_3.bmp"
     lfsr_b200.lfutils.write_bmp(str(p), v[1, 3])
     assert np.array_equal(np.frombuffer(p.read_bytes(), dtype=np.uint8), g["bmp_view_1_3"])
+
+
+@pytest.mark.parametrize("tail", [False, True])
+def test_conv_tc_twin_tiles_odd_count(ref, tail):
+    """wide streamed-weight layers walk M-tile pairs (one weight stage feeds two tiles / both accumulator stages): an odd
+    number of 128-pixel tiles leaves a dummy partner whose stores must be suppressed"""
+    tc_ops = K.CudaOps(use_tc=True)
+    n, h, w, cin, cq, r = 3, 20, 32, 64, 64, 2          # 3 * 5 * 1 = 15 tiles, weights 590 KB -> streamed
+    g = torch.Generator().manual_seed(5)
+    wt = (torch.rand(cq * r * r, cin, 3, 3, generator=g) - 0.5) * (2.0 / (cin * 9) ** 0.5)
+    pc = K.pack_conv(wt, None, pad=(1, 1), device=DEV, tc=True, tc_shuffle=(r, r, 0))
+    x = nhwc(n, h, w, cin, seed=3)
+    kw = dict(act=2, slope=0.1, shuffle=(r, r, 0))
+    if tail:
+        tw = torch.zeros(cq, 12)
+        tw[:, :9] = (torch.rand(cq, 9, generator=g) - 0.5) * 0.2
+        kw["tail"] = (tw.to(DEV), 9, cq)
+        a, b = nhwc(n, h * r, w * r, 9, seed=4), nhwc(n, h * r, w * r, 9, seed=4)
+    else:
+        a, b = nhwc(n, h * r, w * r, cq, seed=4), nhwc(n, h * r, w * r, cq, seed=4)
+    guard = a.clone()
+    tc_ops.conv(x, pc, a, **kw)
+    ref.conv(x, pc, b, **kw)
+    assert (a - b).abs().max().item() <= 2e-3
+    assert not torch.equal(a, guard)
