@@ -647,9 +647,9 @@ __device__ __forceinline__ void epilogue_tile_tail(const Params& p, const float*
   mbar_wait(tfull_bar, tfull_parity);
   tc_fence_after();
   for (int sub = g_first; sub < r2; sub += g_step) {
-    float r[12];
+    f32x2 rp[6];                      // 12 tap responses as 6 packed pairs: the projection is FFMA2 throughout
 #pragma unroll
-    for (int t = 0; t < 12; ++t) r[t] = 0.f;
+    for (int t = 0; t < 6; ++t) rp[t] = pack2(0.f, 0.f);
     for (int c0 = 0; c0 < p.cq; c0 += 32) {
       const int pc0 = sub * p.cq + c0;
       float bcol = 0.f;
@@ -678,14 +678,18 @@ __device__ __forceinline__ void epilogue_tile_tail(const Params& p, const float*
       for (int k = 0; k < 32; ++k) {
         const float4 w0 = wt[3 * k], w1 = wt[3 * k + 1], w2 = wt[3 * k + 2];
         const float a = v[k] * p.alpha;
-        r[0] = fmaf(a, w0.x, r[0]); r[1] = fmaf(a, w0.y, r[1]); r[2] = fmaf(a, w0.z, r[2]); r[3] = fmaf(a, w0.w, r[3]);
-        r[4] = fmaf(a, w1.x, r[4]); r[5] = fmaf(a, w1.y, r[5]); r[6] = fmaf(a, w1.z, r[6]); r[7] = fmaf(a, w1.w, r[7]);
-        r[8] = fmaf(a, w2.x, r[8]); r[9] = fmaf(a, w2.y, r[9]); r[10] = fmaf(a, w2.z, r[10]); r[11] = fmaf(a, w2.w, r[11]);
+        const f32x2 aa = pack2(a, a);
+        rp[0] = fma2(aa, pack2(w0.x, w0.y), rp[0]); rp[1] = fma2(aa, pack2(w0.z, w0.w), rp[1]);
+        rp[2] = fma2(aa, pack2(w1.x, w1.y), rp[2]); rp[3] = fma2(aa, pack2(w1.z, w1.w), rp[3]);
+        rp[4] = fma2(aa, pack2(w2.x, w2.y), rp[4]); rp[5] = fma2(aa, pack2(w2.z, w2.w), rp[5]);
       }
     }
     if (pix_ok) {
       const int si = fdiv(sub, p.fd_rx), sj = sub - si * p.rx;
       float4* dst = reinterpret_cast<float4*>(p.out.p + p.out.pix(img, Y * p.ry + si, X * p.rx + sj));
+      float r[12];
+#pragma unroll
+      for (int t = 0; t < 6; ++t) unpack2(rp[t], r[2 * t], r[2 * t + 1]);
       dst[0] = make_float4(r[0], r[1], r[2], r[3]);
       dst[1] = make_float4(r[4], r[5], r[6], r[7]);
       dst[2] = make_float4(r[8], r[9], r[10], r[11]);
