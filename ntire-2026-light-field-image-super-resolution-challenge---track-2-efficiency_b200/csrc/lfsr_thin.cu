@@ -11,6 +11,7 @@
 //   makes the per-lane 128-bit tile reads bank-conflict free; weights [tap][cin][20] sit in shared memory.
 // Results are fp32-exact (no TF32 rounding), summed tap by tap, input channel by input channel.
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include "lfsr_common.cuh"
 
@@ -45,9 +46,14 @@ __device__ __forceinline__ void th_ldw(const float* row, f32x2* w) {
   }
 }
 
-template <int CIN>
-__global__ void __launch_bounds__(256)
+// PPT = pixels per thread (same column, TH_H / PPT rows apart): every weight row read from shared memory is used for PPT
+// pixels. ncu on the PPT = 2 version: L1/TEX (shared-memory) pipe 80 % busy, issue slots 49 % - the weight-row
+// broadcasts bound it. PPT = 4 with 128-thread CTAs has 45 % fewer LDS per FFMA2 but half the warps per SM and measured
+// no faster (LFSR_THIN_PPT=4 selects it); PPT = 2 with 256 threads is the default.
+template <int CIN, int PPT>
+__global__ void __launch_bounds__(512 / PPT)
 conv_thin_kernel(const __grid_constant__ ThinArgs a) {
+  constexpr int NT = 512 / PPT, RSTEP = TH_H / PPT;
   extern __shared__ __align__(16) float th_smem[];
   __shared__ uint64_t bar;
   const int tid = threadIdx.x;
@@ -68,7 +74,7 @@ conv_thin_kernel(const __grid_constant__ ThinArgs a) {
                  : "memory");
   }
   const int taps = a.kh * a.kw;
-  for (int i = tid; i < taps * CIN * (TH_CP / 4); i += 256)
+  for (int i = tid; i < taps * CIN * (TH_CP / 4); i += NT)
     reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(a.w) + i);
   __syncthreads();
   {
@@ -79,38 +85,52 @@ conv_thin_kernel(const __grid_constant__ ThinArgs a) {
                    : "=r"(done) : "r"(addr) : "memory");
     if (!done) __trap();
   }
-  const int lx = tid & 31, ly = tid >> 5;               // pixels (lx, ly) and (lx, ly + 8)
-  f32x2 acc0[TH_NP], acc1[TH_NP];
+  const int lx = tid & 31, ly = tid >> 5;               // pixels (lx, ly + h * RSTEP), h < PPT
+  f32x2 acc[PPT][TH_NP];
 #pragma unroll
   for (int i = 0; i < TH_NP; ++i) {
     const f32x2 b = a.bias ? pack2(__ldg(a.bias + 2 * i), __ldg(a.bias + 2 * i + 1)) : pack2(0.f, 0.f);
-    acc0[i] = b; acc1[i] = b;
+#pragma unroll
+    for (int h = 0; h < PPT; ++h) acc[h][i] = b;
   }
+  const int hstep = RSTEP * SW * TH_CP;
   for (int ky = 0; ky < a.kh; ++ky)
     for (int kx = 0; kx < a.kw; ++kx) {
       const float* p0 = tile + ((ly + ky * a.dh) * SW + lx + kx * a.dw) * TH_CP;
-      float v0[TH_CP], v1[TH_CP];
-      th_ld20(p0, v0);
-      th_ld20(p0 + 8 * SW * TH_CP, v1);
       const float* wt = wsm + (ky * a.kw + kx) * CIN * TH_CP;
 #pragma unroll
-      for (int c = 0; c < CIN; ++c) {
-        f32x2 w[TH_NP];
-        th_ldw(wt + c * TH_CP, w);
-        const f32x2 b0 = pack2(v0[c], v0[c]), b1 = pack2(v1[c], v1[c]);
+      for (int cq = 0; cq < (CIN + 3) / 4; ++cq) {            // four input channels at a time: one LDS.128 per pixel
+        float v[PPT][4];
 #pragma unroll
-        for (int i = 0; i < TH_NP; ++i) { acc0[i] = fma2(b0, w[i], acc0[i]); acc1[i] = fma2(b1, w[i], acc1[i]); }
+        for (int h = 0; h < PPT; ++h) {
+          const float4 t = *reinterpret_cast<const float4*>(p0 + h * hstep + cq * 4);
+          v[h][0] = t.x; v[h][1] = t.y; v[h][2] = t.z; v[h][3] = t.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = cq * 4 + j;
+          if (c < CIN) {
+            f32x2 w[TH_NP];
+            th_ldw(wt + c * TH_CP, w);
+#pragma unroll
+            for (int h = 0; h < PPT; ++h) {
+              const f32x2 bb = pack2(v[h][j], v[h][j]);
+#pragma unroll
+              for (int i = 0; i < TH_NP; ++i) acc[h][i] = fma2(bb, w[i], acc[h][i]);
+            }
+          }
+        }
       }
     }
   const int ox = tx0 + lx;
   if (ox >= a.out.w) return;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int oy = ty0 + ly + 8 * h;
+  for (int h = 0; h < PPT; ++h) {
+    const int oy = ty0 + ly + RSTEP * h;
     if (oy >= a.out.h) continue;
     float o[TH_CP];
 #pragma unroll
-    for (int i = 0; i < TH_NP; ++i) unpack2(h ? acc1[i] : acc0[i], o[2 * i], o[2 * i + 1]);
+    for (int i = 0; i < TH_NP; ++i) unpack2(acc[h][i], o[2 * i], o[2 * i + 1]);
     if (a.act) {
 #pragma unroll
       for (int i = 0; i < TH_CP; ++i) o[i] = apply_act(o[i], a.act, a.slope);
@@ -249,19 +269,28 @@ extern "C" int lfsr_conv2d_thin(const lfsr_tensor* in, const float* w_packed, co
   const size_t smem = thin_smem(in, d);
   const int blocks = out->n * a.tiles_x * a.tiles_y;
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_THIN(CIN)                                                                                       \
-  do {                                                                                                         \
-    static bool attr_done = false;                                                                             \
-    if (!attr_done) {                                                                                          \
-      cudaFuncSetAttribute(conv_thin_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);    \
-      attr_done = true;                                                                                        \
-    }                                                                                                          \
-    conv_thin_kernel<CIN><<<blocks, 256, smem, st>>>(a);                                                       \
+#define LAUNCH_THIN(CIN, PPT)                                                                                       \
+  do {                                                                                                              \
+    static bool attr_done = false;                                                                                  \
+    if (!attr_done) {                                                                                               \
+      cudaFuncSetAttribute(conv_thin_kernel<CIN, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);    \
+      attr_done = true;                                                                                             \
+    }                                                                                                               \
+    conv_thin_kernel<CIN, PPT><<<blocks, 512 / PPT, smem, st>>>(a);                                                 \
   } while (0)
-  switch (in->c) {
-    case 16: LAUNCH_THIN(16); break;
-    case 18: LAUNCH_THIN(18); break;
-    default: LAUNCH_THIN(20); break;
+  static const int ppt = getenv("LFSR_THIN_PPT") ? atoi(getenv("LFSR_THIN_PPT")) : 2;   // measured: 0.261 ms (2) vs 0.273 ms (4) per layer
+  if (ppt == 2) {
+    switch (in->c) {
+      case 16: LAUNCH_THIN(16, 2); break;
+      case 18: LAUNCH_THIN(18, 2); break;
+      default: LAUNCH_THIN(20, 2); break;
+    }
+  } else {
+    switch (in->c) {
+      case 16: LAUNCH_THIN(16, 4); break;
+      case 18: LAUNCH_THIN(18, 4); break;
+      default: LAUNCH_THIN(20, 4); break;
+    }
   }
 #undef LAUNCH_THIN
   return check_launch("conv_thin_kernel");
