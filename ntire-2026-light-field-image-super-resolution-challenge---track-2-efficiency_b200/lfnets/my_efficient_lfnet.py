@@ -26,7 +26,7 @@ import torch.nn as nn
 
 from .. import _native as N
 from .. import kernels as K
-from .common import LFNetBase, bn_affine, slots, tail_table, upsample_tail
+from .common import LFNetBase, bn_affine, slots, tail_table, upsample_tail, SideStream
 
 
 def _conv(cin, cout, k, **kw):
@@ -292,21 +292,25 @@ class get_model(LFNetBase):
         CU = pk["CU"]
         fu1, fu2 = buf("fu1", H, W, CU), buf("fu2", H, W, CP)
         pm, am1, am = buf("pm", A, A, CP), buf("am1", A, A, C // 4), buf("am", A, A, CP)
+        fork = SideStream(dev if x.is_cuda and getattr(ops, "name", "") == "cuda" else None)
         for i, st in enumerate(pk["stages"]):
             xs, xa, xe = feat[..., sl[0]], feat[..., sl[1]], feat[..., sl[2]]
             # spatial branch
             ops.conv(xs, st["spa0"], t18, act=LR, slope=0.1)
             ops.conv(t18[..., 0:c0], st["spa2"], cat[..., 0:gs])
-            # angular branch
-            ops.conv(xa, st["ang_to"], ang1)
-            ops.conv(ang1[..., 0:c0], st["ang_a0"], ang2, act=N.ACT_RELU)
-            ops.dwconv(ang2, st["ang_a2"], ang3, 3, 3, act=N.ACT_RELU)
-            ops.conv(ang3[..., 0:hid], st["ang_a4"], ang4, act=N.ACT_SIGMOID, mul=ang1)
-            ops.conv(ang4[..., 0:c0], st["ang_cv"], ang5, act=LR, slope=0.1)
-            ops.conv(ang5[..., 0:c0], st["ang_ex"], cat[..., gs:2 * gs], act=LR, slope=0.1, alpha=st["ang_scale"], res=feat[..., gs:2 * gs],
-                     shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
+            # angular branch: six small launches on 32x32 maps that do not fill the GPU - on a side stream (when the backend
+            # is the CUDA one) they run under the spatial / EPI kernels; the three branches write disjoint slots of `cat`
+            with fork():
+                ops.conv(xa, st["ang_to"], ang1)
+                ops.conv(ang1[..., 0:c0], st["ang_a0"], ang2, act=N.ACT_RELU)
+                ops.dwconv(ang2, st["ang_a2"], ang3, 3, 3, act=N.ACT_RELU)
+                ops.conv(ang3[..., 0:hid], st["ang_a4"], ang4, act=N.ACT_SIGMOID, mul=ang1)
+                ops.conv(ang4[..., 0:c0], st["ang_cv"], ang5, act=LR, slope=0.1)
+                ops.conv(ang5[..., 0:c0], st["ang_ex"], cat[..., gs:2 * gs], act=LR, slope=0.1, alpha=st["ang_scale"],
+                         res=feat[..., gs:2 * gs], shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
             # EPI branch: three depthwise+pointwise paths and their fuse conv in one kernel
             ops.mel_epi_branch(xe, st["epi_w"], cat[..., sl[2]], st["epi_klen"], A, 0.1)
+            fork.join()
             # gates -> per-sample channel scale of the fusion 1x1
             ops.block_mean(cat, vmean, hA, wA)
             ops.block_mean(vmean, gmean, A, A)
