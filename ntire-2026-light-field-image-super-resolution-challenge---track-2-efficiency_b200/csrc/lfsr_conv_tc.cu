@@ -1570,10 +1570,11 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   // leader's MMA thread issues for both; unlike twin tiles this keeps both accumulator stages per SM (epilogue overlapped)
   static const bool use_cta2 = getenv("LFSR_TC_NO_CTA2") == nullptr;
   p.cta2 = 0;
-  if (use_cta2 && !p.resident && !per_image_w && p.kps == 1 && p.nchunks == 1 && p.amode == 0 && p.NC >= 128 && p.NC % 16 == 0 &&
+  static const int cta2_min_nc = getenv("LFSR_TC_CTA2_MIN_NC") ? atoi(getenv("LFSR_TC_CTA2_MIN_NC")) : 128;
+  if (use_cta2 && !p.resident && !per_image_w && p.nchunks == 1 && p.amode == 0 && p.NC >= cta2_min_nc && p.NC % 16 == 0 &&
       p.m_tiles >= 4 && sm_count >= 2) {
     const int st = (kSmemBudget - kEpiWarps * 4096 - tail_bytes) / (kABytes + p.b_stage_bytes / 2);
-    if (st >= 2) { p.cta2 = 1; p.stages = st > kMaxStages ? kMaxStages : st; }
+    if (st >= 2) { p.cta2 = 1; p.kps = 1; p.stages = st > kMaxStages ? kMaxStages : st; }
   }
   static const bool no_twin = getenv("LFSR_TC_NO_TWIN") != nullptr;
   p.twin = 0;
