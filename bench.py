@@ -139,7 +139,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    patches = 4            # bounded sample: a 2x2-patch scene per step
+    patches = 16           # bounded sample: a 4x4-patch scene per step (~1.5 s of host work on the GPU box)
     rate, ms, per_step = cpu_reference_rate(a.model, a.scale, patches, max(a.steps, 1), a.warmup)
     cores = os.cpu_count() or 1
     sample = f"{per_step}-patch scene (5x5x32x32 views) per step, minibatch 1 as option.py:45, {a.steps} steps"
@@ -309,9 +309,9 @@ def main():
 
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
-        rate, ms_cpu, per_step = cpu_reference_rate(a.model, a.scale, 4, 2, 1)
+        rate, ms_cpu, per_step = cpu_reference_rate(a.model, a.scale, 16, 8, 1)     # ~128 patches, 10-20 s of host work
         cpu = {"value": rate, "unit": "patches/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"2 steps of a {per_step}-patch scene (same pipeline, minibatch 1), torch-CPU oracle port"}
+               "sample": f"8 steps of a {per_step}-patch scene (same pipeline, minibatch 1), torch-CPU oracle port"}
 
     if rank == 0:
         sr_bytes = host_sr.numel() * 4 + host_acc.numel() * 8
