@@ -248,6 +248,38 @@ tap_gather_kernel(TView taps, TView res, TView out, int kh, int kw, const float*
   out.p[out.pix(img, y, x)] = acc;
 }
 
+// 3x3 taps stored as 12-float records (what the tail-projection epilogue writes): the 34 x 10 records a 32 x 8 tile
+// needs are staged with coalesced 16-byte cp.async (zero fill outside the image = the conv's padding) and every output
+// is then nine shared-memory reads - the records are read from HBM once instead of through nine strided 4-byte loads.
+__global__ void __launch_bounds__(256)
+tap_gather3x3_kernel(TView taps, TView res, TView out, const float* __restrict__ bias) {
+  __shared__ __align__(16) float rec[10 * 34 * 12];
+  const int img = blockIdx.z;
+  const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < 10 * 34 * 3; i += 256) {
+    const int q = i % 3, pix = i / 3;
+    const int ly = pix / 34, lx = pix - ly * 34;
+    const int iy = ty0 - 1 + ly, ix = tx0 - 1 + lx;
+    const bool ok = iy >= 0 && iy < taps.h && ix >= 0 && ix < taps.w;
+    const float* src = ok ? taps.p + taps.pix(img, iy, ix) + q * 4 : taps.p;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(rec + pix * 12 + q * 4);
+    const int nbytes = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int x = tx0 + lx, y = ty0 + ly;
+  if (x >= out.w || y >= out.h) return;
+  float acc = bias ? __ldg(bias) : 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) acc += rec[((ly + ky) * 34 + lx + kx) * 12 + ky * 3 + kx];
+  if (res.p) acc += res.p[res.pix(img, y, x)];
+  out.p[out.pix(img, y, x)] = acc;
+}
+
 // ---- LayerNorm over channels: one warp per token (EPIT.py:77,84)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(TView in, TView out, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -529,6 +561,10 @@ extern "C" int lfsr_tap_gather(const lfsr_tensor* taps, int kh, int kw, const fl
     LFSR_REQUIRE(res->c == 1 && res->n == out->n && res->h == out->h && res->w == out->w, "lfsr_tap_gather: res geometry");
   LFSR_REQUIRE(out->n <= 65535 && (long long)taps->h * taps->w * taps->ld < 0x7fffffffLL, "lfsr_tap_gather: tensor too large");
   dim3 grid(ceil_div(out->w, 32), ceil_div(out->h, 8), out->n);
+  if (kh == 3 && kw == 3 && taps->ld == 12 && (((uintptr_t)taps->ptr) & 15) == 0) {
+    tap_gather3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(taps), has_res ? view_of(res) : null_view(), view_of(out), bias);
+    return check_launch("tap_gather3x3_kernel");
+  }
   tap_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(taps), has_res ? view_of(res) : null_view(), view_of(out), kh, kw, bias);
   return check_launch("tap_gather_kernel");
 }

@@ -50,6 +50,9 @@ class ProfilingOps(K.CudaOps):
     def scale_add(self, *a):
         self._wrap("scale_add", lambda: K.CudaOps.scale_add(self, *a), f"scale_add c{a[0].shape[3]} @{a[0].shape[1]}")
 
+    def tap_gather(self, *a):
+        self._wrap("tap_gather", lambda: K.CudaOps.tap_gather(self, *a), f"tap_gather @{a[0].shape[1]}x{a[0].shape[2]}")
+
     def interp(self, *a):
         self._wrap("interp", lambda: K.CudaOps.interp(self, *a), "interp")
 
