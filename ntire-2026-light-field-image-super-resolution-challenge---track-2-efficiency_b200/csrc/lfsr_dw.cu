@@ -173,6 +173,58 @@ __device__ __forceinline__ void dw_compute(const DwParams& p, const DwBranch& B,
   }
 }
 
+// Large undilated kernels (5x5, 7x7 of MultiScaleSpatial): a thread owns 8 CONSECUTIVE output rows of one pixel column and
+// channel quad. Per kernel column kx the K row-weights sit in registers and each of the 8 + K - 1 input rows is read once
+// and accumulated into every output row it contributes to: 18 shared-memory reads per output at K = 7 instead of 98.
+template <int K>
+__device__ __forceinline__ void dw_compute_col(const DwParams& p, const DwBranch& B, const float* wS, const float* tS,
+                                               int SW, int img, int ty0, int tx0, int cout0, int wofs) {
+  const int tid = threadIdx.x;
+  const int q = tid & 3, lx = (tid >> 2) & 31, r0 = (tid >> 7) * 8;
+  const int ox = tx0 + lx;
+  if (ox >= p.in.w || wofs + q * 4 >= B.c) return;
+  const int row_f = SW * DW_CH;
+  Acc4 acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) { acc[r].lo = pack2(0.f, 0.f); acc[r].hi = acc[r].lo; }
+  const float* col = tS + r0 * row_f + lx * DW_CH + q * 4;
+#pragma unroll 1
+  for (int kx = 0; kx < K; ++kx) {
+    float4 w[K];
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) w[ky] = *reinterpret_cast<const float4*>(wS + (ky * K + kx) * DW_CH + q * 4);
+    const float* cp = col + kx * DW_CH;
+#pragma unroll
+    for (int ir = 0; ir < 8 + K - 1; ++ir) {
+      const float4 v = *reinterpret_cast<const float4*>(cp + ir * row_f);
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        const int r = ir - ky;                      // output row (relative to r0) this input row feeds through tap ky
+        if (r >= 0 && r < 8) fma4(acc[r], v, w[ky]);
+      }
+    }
+  }
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (B.scale) {
+    sc = __ldg(reinterpret_cast<const float4*>(B.scale + wofs + q * 4));
+    sh = __ldg(reinterpret_cast<const float4*>(B.shift + wofs + q * 4));
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int oy = ty0 + r0 + r;
+    if (oy >= p.in.h) break;
+    float4 o;
+    unpack2(acc[r].lo, o.x, o.y);
+    unpack2(acc[r].hi, o.z, o.w);
+    if (B.scale) { o.x = o.x * sc.x + sh.x; o.y = o.y * sc.y + sh.y; o.z = o.z * sc.z + sh.z; o.w = o.w * sc.w + sh.w; }
+    if (B.act) {
+      o.x = apply_act(o.x, B.act, B.slope); o.y = apply_act(o.y, B.act, B.slope);
+      o.z = apply_act(o.z, B.act, B.slope); o.w = apply_act(o.w, B.act, B.slope);
+    }
+    *reinterpret_cast<float4*>(p.out.p + p.out.pix(img, oy, ox) + cout0 + q * 4) = o;
+  }
+}
+
 // tap weights of this CTA's 16-channel chunk into shared memory: [tap][16] per branch (all branches in share mode)
 __device__ __forceinline__ void dw_stage_taps(const DwParams& p, const DwBranch& B, float* wS, int wofs, int tid) {
   int wo = 0;
@@ -252,6 +304,8 @@ dw_tile_kernel(const __grid_constant__ DwParams p) {
     const int co = Bj.out_c0 + wofs;
     if (Bj.kh == 3 && Bj.kw == 3) dw_compute<3, 3>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
     else if (Bj.kh == 1 && Bj.kw == 1) dw_compute<1, 1>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
+    else if (!p.sa && Bj.kh == 5 && Bj.kw == 5 && Bj.dh == 1 && Bj.dw == 1) dw_compute_col<5>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
+    else if (!p.sa && Bj.kh == 7 && Bj.kw == 7 && Bj.dh == 1 && Bj.dw == 1) dw_compute_col<7>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
     else dw_compute<0, 0>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
     wo += Bj.kh * Bj.kw * DW_CH;
   }
