@@ -175,8 +175,9 @@ __device__ __forceinline__ void dw_compute(const DwParams& p, const DwBranch& B,
 
 // Large undilated kernels (5x5, 7x7 of MultiScaleSpatial): a thread owns 8 CONSECUTIVE output rows of one pixel column and
 // channel quad. Per kernel column kx the K row-weights sit in registers and each of the 8 + K - 1 input rows is read once
-// and accumulated into every output row it contributes to: 18 shared-memory reads per output at K = 7 instead of 98.
-template <int K>
+// and accumulated into every output row it contributes to: 18 shared-memory reads per output at K = 7 instead of 98
+// (dilated 3x3: 4.5 / 6 instead of 9 at dilation 2 / 4; nothing to gain at dilation 8).
+template <int K, int D>      // K x K taps, dilation D (compile time: the row bookkeeping must unroll)
 __device__ __forceinline__ void dw_compute_col(const DwParams& p, const DwBranch& B, const float* wS, const float* tS,
                                                int SW, int img, int ty0, int tx0, int cout0, int wofs) {
   const int tid = threadIdx.x;
@@ -193,13 +194,13 @@ __device__ __forceinline__ void dw_compute_col(const DwParams& p, const DwBranch
     float4 w[K];
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) w[ky] = *reinterpret_cast<const float4*>(wS + (ky * K + kx) * DW_CH + q * 4);
-    const float* cp = col + kx * DW_CH;
+    const float* cp = col + kx * D * DW_CH;
 #pragma unroll
-    for (int ir = 0; ir < 8 + K - 1; ++ir) {
+    for (int ir = 0; ir < 8 + (K - 1) * D; ++ir) {
       const float4 v = *reinterpret_cast<const float4*>(cp + ir * row_f);
 #pragma unroll
       for (int ky = 0; ky < K; ++ky) {
-        const int r = ir - ky;                      // output row (relative to r0) this input row feeds through tap ky
+        const int r = ir - ky * D;                  // output row (relative to r0) this input row feeds through tap ky
         if (r >= 0 && r < 8) fma4(acc[r], v, w[ky]);
       }
     }
@@ -302,10 +303,13 @@ dw_tile_kernel(const __grid_constant__ DwParams p) {
     const int oy_ = hy - (Bj.kh / 2) * Bj.dh, ox_ = hx - (Bj.kw / 2) * Bj.dw;
     const float* tj = tS + (oy_ * SW + ox_) * DW_CH;
     const int co = Bj.out_c0 + wofs;
-    if (Bj.kh == 3 && Bj.kw == 3) dw_compute<3, 3>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
+    if (SHARE && Bj.kh == 3 && Bj.kw == 3 && Bj.dh == Bj.dw && Bj.dh == 1) dw_compute_col<3, 1>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
+    else if (SHARE && Bj.kh == 3 && Bj.kw == 3 && Bj.dh == Bj.dw && Bj.dh == 2) dw_compute_col<3, 2>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
+    else if (SHARE && Bj.kh == 3 && Bj.kw == 3 && Bj.dh == Bj.dw && Bj.dh == 4) dw_compute_col<3, 4>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
+    else if (Bj.kh == 3 && Bj.kw == 3) dw_compute<3, 3>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
     else if (Bj.kh == 1 && Bj.kw == 1) dw_compute<1, 1>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
-    else if (!p.sa && Bj.kh == 5 && Bj.kw == 5 && Bj.dh == 1 && Bj.dw == 1) dw_compute_col<5>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
-    else if (!p.sa && Bj.kh == 7 && Bj.kw == 7 && Bj.dh == 1 && Bj.dw == 1) dw_compute_col<7>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
+    else if (!p.sa && Bj.kh == 5 && Bj.kw == 5 && Bj.dh == 1 && Bj.dw == 1) dw_compute_col<5, 1>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
+    else if (!p.sa && Bj.kh == 7 && Bj.kw == 7 && Bj.dh == 1 && Bj.dw == 1) dw_compute_col<7, 1>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
     else dw_compute<0, 0>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
     wo += Bj.kh * Bj.kw * DW_CH;
   }
