@@ -158,6 +158,7 @@ struct StemArgs {
   const float* bias;
   int kh, kw, dh, dw, ph, pw, act;
   float slope;
+  int perm_a;            // > 0: MacPI addressing over SAI storage with dilation == perm_a (see conv_stem_macpi_kernel)
 };
 
 __global__ void __launch_bounds__(256)
@@ -199,6 +200,46 @@ conv_stem_kernel(const StemArgs a) {
       acc.z = apply_act(acc.z, a.act, a.slope); acc.w = apply_act(acc.w, a.act, a.slope);
     }
     *reinterpret_cast<float4*>(dst) = acc;
+  }
+}
+
+// MacPI-addressed stems (DistgSSR.py:21, LF_InterNet.py:24: conv d = A over SAI2MacPI(x)): a tap of dilation A moves the
+// MacPI coordinate (i*A+u, j*A+v) to (i+k)*A+u - the same view (u, v), neighbouring in-view pixel - so on the SAI
+// storage the layer is a dense 3x3 conv inside each view with zero padding at the view border. One coordinate split per
+// thread, taps are plain storage offsets; the output is written in the MacPI arrangement the trunk works in.
+__global__ void __launch_bounds__(256)
+conv_stem_macpi_kernel(const StemArgs a) {
+  const int q = threadIdx.x & 15, lx = threadIdx.x >> 4;
+  const int c = q * 4;
+  const int ox = blockIdx.x * 16 + lx, oy0 = blockIdx.y * 8, img = blockIdx.z;
+  if (c >= a.out.c || ox >= a.out.w) return;
+  const int A = a.perm_a, H = a.in.h, W = a.in.w, hh = H / A, ww = W / A;
+  const int taps = a.kh * a.kw;
+  float4 wk[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wk[t] = t < taps ? __ldg(reinterpret_cast<const float4*>(a.w + t * a.out.c + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int j = ox / A, v = ox - j * A;                  // MacPI column -> (in-view column j, view v)
+  const float* img_p = a.in.p + (size_t)img * H * W;
+  const int ymax = min(oy0 + 8, a.out.h);
+  for (int oy = oy0; oy < ymax; ++oy) {
+    const int i = oy / A, u = oy - i * A;
+    const float* vp = img_p + (u * hh) * W + v * ww;     // top-left of view (u, v) in the SAI mosaic
+    float4 acc = b;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (t >= taps) break;
+      const int ky = t / a.kw, kx = t - ky * a.kw;
+      const int ii = i + ky - a.kh / 2, jj = j + kx - a.kw / 2;
+      const bool ok = (unsigned)ii < (unsigned)hh && (unsigned)jj < (unsigned)ww;
+      const float x = ok ? __ldg(vp + ii * W + jj) : 0.f;
+      acc.x = fmaf(x, wk[t].x, acc.x); acc.y = fmaf(x, wk[t].y, acc.y); acc.z = fmaf(x, wk[t].z, acc.z); acc.w = fmaf(x, wk[t].w, acc.w);
+    }
+    if (a.act) {
+      acc.x = apply_act(acc.x, a.act, a.slope); acc.y = apply_act(acc.y, a.act, a.slope);
+      acc.z = apply_act(acc.z, a.act, a.slope); acc.w = apply_act(acc.w, a.act, a.slope);
+    }
+    *reinterpret_cast<float4*>(a.out.p + a.out.pix(img, oy, ox) + c) = acc;
   }
 }
 
@@ -304,7 +345,11 @@ extern "C" int lfsr_conv2d_stem_supported(const lfsr_tensor* in, const lfsr_tens
   if (d->kh * d->kw > 9 || d->kh < 1 || d->kw < 1) return 0;
   if (2 * d->pad_h != d->dil_h * (d->kh - 1) || 2 * d->pad_w != d->dil_w * (d->kw - 1)) return 0;
   if (out->n != in->n || out->h != in->h || out->w != in->w || out->n > 65535) return 0;
-  if (d->in_perm || in->ld != 1 || (long long)in->h * in->w >= 0x7fffffffLL) return 0;   // MacPI-addressed stems stay on the generic kernel
+  if (in->ld != 1 || (long long)in->h * in->w >= 0x7fffffffLL) return 0;
+  if (d->in_perm) {        // MacPI addressing: only the case that is a per-view dense conv (dilation == angular resolution)
+    const int A = d->perm_a;
+    if (d->in_perm != LFSR_PERM_MACPI_OVER_SAI || A < 1 || in->h % A || in->w % A || d->dil_h != A || d->dil_w != A) return 0;
+  }
   return 1;
 }
 
@@ -316,8 +361,12 @@ extern "C" int lfsr_conv2d_stem(const lfsr_tensor* in, const float* w_packed, co
   a.in = view_of(in); a.out = view_of(out);
   a.w = w_packed; a.bias = d->bias;
   a.kh = d->kh; a.kw = d->kw; a.dh = d->dil_h; a.dw = d->dil_w; a.ph = d->pad_h; a.pw = d->pad_w;
-  a.act = d->act; a.slope = d->act_slope;
+  a.act = d->act; a.slope = d->act_slope; a.perm_a = d->in_perm ? d->perm_a : 0;
   dim3 grid(ceil_div(out->w, 16), ceil_div(out->h, 8), out->n);
+  if (a.perm_a) {
+    conv_stem_macpi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("conv_stem_macpi_kernel");
+  }
   conv_stem_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return check_launch("conv_stem_kernel");
 }
