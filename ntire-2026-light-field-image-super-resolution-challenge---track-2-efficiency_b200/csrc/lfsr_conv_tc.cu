@@ -695,7 +695,11 @@ __device__ __forceinline__ void epilogue_tile_tail(const Params& p, const float*
   const float slope = p.slope;
   mbar_wait(tfull_bar, tfull_parity);
   tc_fence_after();
-  for (int sub = g_first; sub < r2; sub += g_step) {
+  // sub-pixels of this cout-chunk: all of them with one chunk, else NC / cq whole sub-pixels per chunk (host-checked)
+  const int sub0 = p.nchunks == 1 ? 0 : tc_.chunk * (p.NC / p.cq);
+  const int sub1 = p.nchunks == 1 ? r2 : min(r2, sub0 + p.NC / p.cq);
+  taddr -= sub0 * p.cq;                            // accumulator column of global output column pc0 is pc0 - sub0 * cq
+  for (int sub = sub0 + g_first; sub < sub1; sub += g_step) {
     f32x2 rp[6];                      // 12 tap responses as 6 packed pairs: the projection is FFMA2 throughout
 #pragma unroll
     for (int t = 0; t < 6; ++t) rp[t] = pack2(0.f, 0.f);
@@ -1355,7 +1359,7 @@ static bool tc_geometry_ok(const lfsr_tensor* in, const lfsr_tensor* out, const 
   if (cout < 1) return false;
   if (d->tail_w) {      // tail projection: one cout-chunk whose sub-pixel blocks stay inside a 256-column accumulator stage
     if (ry * rx < 2 || d->tail_c < 4 || d->tail_c % 4 || d->tail_taps < 1 || d->tail_taps > 12 || out->c != d->tail_taps) return false;
-    if (cout > 256 || (cout > 240 && d->tail_c % 32) || out->ld < 12 || out->ld % 4 || ((uintptr_t)out->ptr & 15) || ((uintptr_t)d->tail_w & 15)) return false;
+    if ((cout > 256 && (d->tail_c % 32 || 256 % d->tail_c)) || (cout > 240 && d->tail_c % 32) || out->ld < 12 || out->ld % 4 || ((uintptr_t)out->ptr & 15) || ((uintptr_t)d->tail_w & 15)) return false;
     if (d->res.ptr || d->mul.ptr || sh > 1 || sw > 1 || d->block_h > 0 || d->block_w > 0) return false;
   }
   const int bh = d->block_h > 0 ? d->block_h : in->h, bw = d->block_w > 0 ? d->block_w : in->w;
@@ -1414,7 +1418,10 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   p.ry = ry; p.rx = rx; p.shuf_mode = d->shuf_mode; p.cq = d->tail_w ? d->tail_c : out->c;
   p.tail_w = d->tail_w; p.tail_rows = d->tail_w ? (d->tail_c + 31) / 32 * 32 : 0;
   // (a short last block of a sub-pixel run reads up to 31 accumulator columns past it: keep that inside the 256-column stage)
-  if (d->tail_w) LFSR_REQUIRE(p.nchunks == 1 && (p.NC <= 240 || p.cq % 32 == 0), "lfsr_conv2d_tc: tail projection needs a single cout chunk");
+  if (d->tail_w)
+    LFSR_REQUIRE((p.nchunks == 1 && (p.NC <= 240 || p.cq % 32 == 0)) ||
+                     (p.nchunks > 1 && p.cq % 32 == 0 && p.NC % p.cq == 0 && p.cout == p.nchunks * p.NC),
+                 "lfsr_conv2d_tc: tail projection needs cout chunks made of whole sub-pixel channel runs");
   p.fd_cq = make_fastdiv(p.cq); p.fd_nby = make_fastdiv(p.nby); p.fd_nbx = make_fastdiv(p.nbx); p.fd_rx = make_fastdiv(rx);
   p.vec = 1;
   for (int v = 2; v <= 4; v *= 2) {

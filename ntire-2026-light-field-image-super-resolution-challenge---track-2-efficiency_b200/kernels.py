@@ -202,7 +202,8 @@ class CudaOps:
     def tail_supported(self, pc: PackedConv, cq: int, shuffle) -> bool:
         """can `pc` (a conv + PixelShuffle to cq channels) end in a tail projection on this backend?"""
         return bool(self.use_tc and pc.w_tc is not None and shuffle[0] * shuffle[1] > 1 and cq % 4 == 0
-                    and (pc.cout <= 240 or (pc.cout <= 256 and cq % 32 == 0)) and pc.stride == (1, 1))
+                    and (pc.cout <= 240 or (cq % 32 == 0 and 256 % cq == 0 and (pc.cout <= 256 or pc.cout % 256 == 0)))
+                    and pc.stride == (1, 1))
 
     def tap_gather(self, taps, kh, kw, bias, res, out):
         rt = as_tensor(res, "tap_gather.res") if res is not None else _NULL_T

@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from .. import _native as N
 from .. import kernels as K
-from .common import LFNetBase, L1Loss, slots
+from .common import LFNetBase, L1Loss, slots, tail_table
 
 
 def _c3(cin, cout):
@@ -81,6 +81,7 @@ class get_model(LFNetBase):
                 conv=[c3(af.conv[k]) for k in ("0", "2", "4")], heads=t.num_heads, E=E))
         pk["up0"] = pc(self.upsampling["0"].weight, tc=True, tc_shuffle=(self.scale, self.scale, N.SHUF_CHANNEL_MAJOR))
         pk["up3"] = pc(self.upsampling["3"].weight, pad=(1, 1), tc=True)
+        pk["tail_w"] = tail_table(self.upsampling["3"].weight, self.channels, device)
         return pk
 
     def _run(self, ops, pk, x, out):
@@ -141,9 +142,17 @@ class get_model(LFNetBase):
         # altblock(buffer) + buffer (:64): the last AltFilter already consumed its own shortcut as the
         # fused residual, so this second skip is one identity-weight 1x1 pass (0.1 GMAC/patch)
         ops.conv(cur, self._identity(pk, dev), fb, res=fa)
-        up = buf("up", H * s, W * s, C)
-        ops.conv(fb, pk["up0"], up, act=LR, slope=0.2, shuffle=(s, s, N.SHUF_CHANNEL_MAJOR))
-        ops.conv(up, pk["up3"], Y, res=Y)
+        shuffle = (s, s, N.SHUF_CHANNEL_MAJOR)
+        if ops.tail_supported(pk["up0"], C, shuffle):
+            # 1x1 C -> C*s^2 + PixelShuffle + LReLU with the 3x3 head conv's channel contraction in its epilogue, then the
+            # 9-tap gather onto the bicubic skip (EPIT.py:45-48, :64-66): the C-channel HR activation is never written
+            taps = buf("head_taps", H * s, W * s, 9)
+            ops.conv(fb, pk["up0"], taps, act=LR, slope=0.2, shuffle=shuffle, tail=(pk["tail_w"], 9, C))
+            ops.tap_gather(taps, 3, 3, None, Y, Y)
+        else:
+            up = buf("up", H * s, W * s, C)
+            ops.conv(fb, pk["up0"], up, act=LR, slope=0.2, shuffle=shuffle)
+            ops.conv(up, pk["up3"], Y, res=Y)
 
     def _identity(self, pk, dev):
         if "eye" not in pk:

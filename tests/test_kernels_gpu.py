@@ -493,6 +493,37 @@ def test_conv_tc_tail_projection_and_tap_gather(ref, cin, cq, hw, bias):
     assert (ya - y2).abs().max().item() <= 2e-3
 
 
+@pytest.mark.parametrize("cq,r,k,mode,hw", [(64, 4, 1, 1, (32, 32)), (64, 4, 1, 1, (21, 45)), (32, 4, 3, 0, (40, 40))])
+def test_conv_tc_tail_projection_many_cout_chunks(ref, cq, r, k, mode, hw):
+    """tail projection when cq*r^2 needs several 256-column cout chunks (EPIT.py:45-48: 1x1 64->1024, PixelShuffle(4),
+    LReLU(0.2), 3x3 64->1): every chunk holds whole sub-pixel channel runs and projects them independently"""
+    tc_ops = K.CudaOps(use_tc=True)
+    n, (h, w), cin = 2, hw, 64
+    g = torch.Generator().manual_seed(cq * r + k)
+    wt = (torch.rand(cq * r * r, cin, k, k, generator=g) - 0.5) * (2.0 / (cin * k * k) ** 0.5)
+    pc = K.pack_conv(wt, None, pad=(k // 2, k // 2), device=DEV, tc=True, tc_shuffle=(r, r, mode))
+    head = (torch.rand(1, cq, 3, 3, generator=g) - 0.5) * 0.2
+    tw = torch.zeros(cq, 12)
+    tw[:, :9] = head[0].reshape(cq, 9)
+    tw = tw.to(DEV)
+    x = nhwc(n, h, w, cin, seed=3)
+    assert tc_ops.tail_supported(pc, cq, (r, r, mode))
+    ta, tb = nhwc(n, h * r, w * r, 9, seed=4), nhwc(n, h * r, w * r, 9, seed=4)
+    kw = dict(act=2, slope=0.2, shuffle=(r, r, mode), tail=(tw, 9, cq))
+    l0 = tc_ops.lib.lfsr_launch_count()
+    tc_ops.conv(x, pc, ta, **kw)
+    assert tc_ops.lib.lfsr_launch_count() == l0 + 1
+    ref.conv(x, pc, tb, **kw)
+    assert (ta - tb).abs().max().item() <= 2e-3
+    ya = rnd(n, h * r, w * r, 1, seed=5)
+    tc_ops.tap_gather(ta, 3, 3, None, ya, ya)
+    full = nhwc(n, h * r, w * r, cq, seed=6)
+    ref.conv(x, pc, full, act=2, slope=0.2, shuffle=(r, r, mode))
+    y2 = rnd(n, h * r, w * r, 1, seed=5)
+    ref.conv(full, K.pack_conv(head, None, pad=(1, 1), device=DEV), y2, res=y2.clone())
+    assert (ya - y2).abs().max().item() <= 2e-3
+
+
 @pytest.mark.parametrize("cin,k,dil,hw,bias,act", [(18, 3, 5, (160, 160), True, 2), (18, 3, 5, (37, 45), False, 0), (20, 3, 1, (40, 40), True, 1),
                                                    (16, 1, 1, (40, 40), False, 0)])
 def test_conv_thin(ops, ref, cin, k, dil, hw, bias, act):
