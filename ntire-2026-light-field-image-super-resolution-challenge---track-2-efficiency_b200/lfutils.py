@@ -61,6 +61,9 @@ def LFintegrate(subLF: torch.Tensor, angRes: int, pz: int, stride: int, h: int, 
         raise ValueError(f"LFintegrate expects a 4-D or 6-D tensor, got {tuple(subLF.shape)}")
     sub = sub.contiguous()
     n1, n2 = sub.shape[:2]
+    # the reference slices [0:h, 0:w] out of the n1*stride x n2*stride stitched views (utils.py:176-178): with
+    # non-overlapping patches the grid can be smaller than the scene and the slice returns what is covered
+    h, w = min(h, n1 * stride), min(w, n2 * stride)
     mosaic = torch.empty((angRes * h, angRes * w), dtype=torch.float32, device=dev)
     ops.integrate_rows(sub, mosaic, angRes, pz, stride, h, w, n1, n2, 0, n1)
     out = mosaic.view(angRes, h, angRes, w).permute(0, 2, 1, 3)

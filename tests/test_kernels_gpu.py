@@ -53,6 +53,23 @@ def test_divide_integrate_bit_exact(ops, h0, w0):
     assert np.array_equal(want_i, np.repeat(np.repeat(views, s, axis=2), s, axis=3))
 
 
+@pytest.mark.parametrize("A,h0,w0,P,S,s", [(3, 20, 75, 32, 16, 4), (5, 17, 16, 32, 16, 2), (2, 40, 40, 16, 16, 2), (7, 33, 47, 32, 16, 1),
+                                           (5, 40, 56, 64, 32, 2)])
+def test_divide_integrate_edge_geometries(ops, A, h0, w0, P, S, s):
+    """other angular resolutions, scenes smaller than a patch (mirror padding wraps more than once per side is NOT needed:
+    bdr < h0), non-overlapping patches (the reference's (h0 - 1) // stride patch count then leaves the last rows out:
+    utils.py:156-158) - bit-exact against the oracle"""
+    scene = np.random.RandomState(h0 * 131 + w0).random_sample((A * h0, A * w0)).astype(np.float32)
+    want = lf_oracle.lfdivide(scene, A, P, S)
+    got = lfsr_b200.lfutils.LFdivide(torch.from_numpy(scene).to(DEV), A, P, S)
+    assert got.shape == want.shape and np.array_equal(got.cpu().numpy(), want)
+    up = got.view(*got.shape[:2], A, P, 1, A, P, 1).expand(-1, -1, -1, -1, s, -1, -1, s).reshape(
+        got.shape[0], got.shape[1], A * P * s, A * P * s).contiguous()
+    lf = lfsr_b200.lfutils.LFintegrate(up, A, P * s, S * s, h0 * s, w0 * s)
+    want_i = lf_oracle.lfintegrate(up.cpu().numpy(), A, P * s, S * s, h0 * s, w0 * s)
+    assert lf.shape == want_i.shape and np.array_equal(lf.cpu().numpy(), want_i)
+
+
 def test_divide_integrate_goldens(ops, golden_dir):
     g = np.load(f"{golden_dir}/pipeline.npz")
     for (h0, w0) in ((32, 32), (47, 61), (64, 40)):
