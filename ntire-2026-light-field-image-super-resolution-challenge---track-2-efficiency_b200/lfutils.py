@@ -30,6 +30,21 @@ def divide_geometry(h0: int, w0: int, patch_size: int, stride: int):
     return bdr, (h0 + bdr * 2 - 1) // stride, (w0 + bdr * 2 - 1) // stride
 
 
+def check_divide_geometry(h0: int, w0: int, patch_size: int, stride: int) -> None:
+    """The reference's LFdivide only works when its unfold yields exactly the numU x numV patches its rearrange expects
+    (utils/utils.py:152-166): ImageExtend pads bdr above and bdr + stride - 1 below out of ONE mirrored copy of the view
+    (at most n rows), unfold then gives (ext - patch) // stride + 1 windows. In practice: patch == 2 * stride and views no
+    smaller than ~patch / 2. Everything else raises inside the reference (einops shape error); same here, up front."""
+    bdr = (patch_size - stride) // 2
+    for n, what in ((h0, "height"), (w0, "width")):
+        ext = n + bdr + min(bdr + stride - 1, n)
+        windows = (ext - patch_size) // stride + 1 if ext >= patch_size else 0
+        want = (n + 2 * bdr - 1) // stride
+        if n <= 0 or bdr > n or windows < 1 or windows != want:
+            raise ValueError(f"LFdivide: view {what} {n} cannot be tiled with patch {patch_size} / stride {stride} "
+                             f"(the reference's unfold gives {windows} windows where it expects {want})")
+
+
 def LFdivide(data: torch.Tensor, angRes: int, patch_size: int, stride: int, rows=None, ops=None) -> torch.Tensor:
     """data [(a1 h0), (a2 w0)] -> subLF [numU, numV, a1*P, a2*P]  (utils/utils.py:152-166).
     rows=(u0,u1) returns only that band of the patch grid (multi-GPU scene sharding)."""
@@ -40,6 +55,7 @@ def LFdivide(data: torch.Tensor, angRes: int, patch_size: int, stride: int, rows
     src = data.to(device=dev, dtype=torch.float32).contiguous()
     H, W = src.shape
     h0, w0 = H // angRes, W // angRes
+    check_divide_geometry(h0, w0, patch_size, stride)
     _, num_u, num_v = divide_geometry(h0, w0, patch_size, stride)
     u0, u1 = (0, num_u) if rows is None else rows
     sub = torch.empty((u1 - u0, num_v, angRes * patch_size, angRes * patch_size), dtype=torch.float32, device=dev)

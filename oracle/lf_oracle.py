@@ -31,10 +31,25 @@ def divide_geometry(h0: int, w0: int, patch: int, stride: int):
     return bdr, (h0 + bdr * 2 - 1) // stride, (w0 + bdr * 2 - 1) // stride      # utils.py:156-158
 
 
+def divide_supported(h0: int, w0: int, patch: int, stride: int) -> bool:
+    """does the reference's LFdivide run on this geometry? ImageExtend (utils.py:137-149) can only pad out of one mirrored
+    copy (<= n rows per side) and F.unfold (utils.py:160) must return exactly the numU x numV windows that the rearrange
+    of utils.py:161-164 expects, else einops raises (checked against the reference in oracle/make_golden.py)."""
+    bdr = (patch - stride) // 2
+    for n in (h0, w0):
+        ext = n + bdr + min(bdr + stride - 1, n)
+        windows = (ext - patch) // stride + 1 if ext >= patch else 0
+        if n <= 0 or bdr > n or windows < 1 or windows != (n + 2 * bdr - 1) // stride:
+            return False
+    return True
+
+
 def lfdivide(scene: np.ndarray, ang: int, patch: int, stride: int) -> np.ndarray:
     """scene [(a1 h0), (a2 w0)] -> [numU, numV, (a1 P), (a2 P)]  (utils/utils.py:152-166)."""
     H, W = scene.shape
     h0, w0 = H // ang, W // ang
+    if not divide_supported(h0, w0, patch, stride):
+        raise ValueError(f"lfdivide: the reference cannot tile {h0}x{w0} views with patch {patch} / stride {stride}")
     bdr, num_u, num_v = divide_geometry(h0, w0, patch, stride)
     views = scene.reshape(ang, h0, ang, w0)
     ys = _mirror(np.arange(num_u)[:, None] * stride + np.arange(patch)[None, :] - bdr, h0)  # [numU, P]

@@ -79,6 +79,23 @@ def main():
     # ---- patch pipeline goldens from the reference's utils/utils.py ------------------------------
     import utils.utils as U  # the reference's
     from einops import rearrange
+    # domain of LFdivide: the oracle must accept exactly the geometries the reference can tile (its unfold / rearrange pair
+    # raises for the others) and agree bit for bit where it accepts; 2580 geometries
+    n_geo = 0
+    for A_ in (2, 5):
+        for (P_, S_) in ((32, 16), (16, 16), (64, 32), (32, 8), (48, 16), (32, 24), (16, 8), (64, 16), (128, 64), (8, 4)):
+            for h0 in list(range(1, 40)) + [63, 64, 65, 100]:
+                for w0 in (max(h0, 33), h0, 2 * h0 + 1):
+                    scene = np.random.RandomState(1).random_sample((A_ * h0, A_ * w0)).astype(np.float32)
+                    try:
+                        sub = U.LFdivide(torch.from_numpy(scene), A_, P_, S_).numpy()
+                    except Exception:
+                        sub = None
+                    assert (sub is not None) == lf_oracle.divide_supported(h0, w0, P_, S_), (A_, P_, S_, h0, w0)
+                    if sub is not None:
+                        assert np.array_equal(sub, lf_oracle.lfdivide(scene, A_, P_, S_)), (A_, P_, S_, h0, w0)
+                    n_geo += 1
+    print(f"LFdivide domain: oracle == reference on {n_geo} geometries")
     pipe = {}
     rs = np.random.RandomState(3)
     for (h0, w0) in ((32, 32), (47, 61), (64, 40)):

@@ -53,12 +53,11 @@ def test_divide_integrate_bit_exact(ops, h0, w0):
     assert np.array_equal(want_i, np.repeat(np.repeat(views, s, axis=2), s, axis=3))
 
 
-@pytest.mark.parametrize("A,h0,w0,P,S,s", [(3, 20, 75, 32, 16, 4), (5, 17, 16, 32, 16, 2), (2, 40, 40, 16, 16, 2), (7, 33, 47, 32, 16, 1),
-                                           (5, 40, 56, 64, 32, 2)])
+@pytest.mark.parametrize("A,h0,w0,P,S,s", [(3, 20, 75, 32, 16, 4), (7, 23, 23, 32, 16, 2), (2, 40, 56, 64, 32, 2), (2, 9, 30, 16, 8, 3),
+                                           (7, 33, 47, 32, 16, 1)])
 def test_divide_integrate_edge_geometries(ops, A, h0, w0, P, S, s):
-    """other angular resolutions, scenes smaller than a patch (mirror padding wraps more than once per side is NOT needed:
-    bdr < h0), non-overlapping patches (the reference's (h0 - 1) // stride patch count then leaves the last rows out:
-    utils.py:156-158) - bit-exact against the oracle"""
+    """other angular resolutions / patch sizes and views smaller than a patch - bit-exact against the oracle; geometries
+    the reference cannot tile (its unfold / rearrange raises: utils.py:160-164) raise here as well"""
     scene = np.random.RandomState(h0 * 131 + w0).random_sample((A * h0, A * w0)).astype(np.float32)
     want = lf_oracle.lfdivide(scene, A, P, S)
     got = lfsr_b200.lfutils.LFdivide(torch.from_numpy(scene).to(DEV), A, P, S)
@@ -68,6 +67,9 @@ def test_divide_integrate_edge_geometries(ops, A, h0, w0, P, S, s):
     lf = lfsr_b200.lfutils.LFintegrate(up, A, P * s, S * s, h0 * s, w0 * s)
     want_i = lf_oracle.lfintegrate(up.cpu().numpy(), A, P * s, S * s, h0 * s, w0 * s)
     assert lf.shape == want_i.shape and np.array_equal(lf.cpu().numpy(), want_i)
+    for bad in ((40, 40, 16, 16), (17, 16, 32, 16)):
+        with pytest.raises(ValueError):
+            lfsr_b200.lfutils.LFdivide(torch.zeros(5 * bad[0], 5 * bad[1], device=DEV), 5, bad[2], bad[3])
 
 
 def test_divide_integrate_goldens(ops, golden_dir):

@@ -37,10 +37,11 @@ def test_cal_metrics_equal_reference_outputs():
 
 
 @pytest.mark.parametrize("ang,h0,w0,patch,stride,s", [(5, 32, 32, 32, 16, 4), (5, 33, 47, 32, 16, 2), (3, 20, 75, 32, 16, 4),
-                                                     (5, 17, 16, 32, 16, 2), (2, 40, 40, 16, 16, 2), (5, 128, 128, 32, 16, 1)])
+                                                     (7, 23, 23, 32, 16, 2), (2, 40, 56, 64, 32, 2), (5, 128, 128, 32, 16, 1),
+                                                     (2, 9, 30, 16, 8, 3)])
 def test_divide_integrate_round_trip_any_size(ang, h0, w0, patch, stride, s):
-    """integrate(upsample_nearest(divide(x))) == upsample_nearest(x) for ragged, smaller-than-a-patch and
-    non-overlapping (stride == patch) geometries: every output sample comes from exactly one patch interior"""
+    """integrate(upsample_nearest(divide(x))) == upsample_nearest(x) for ragged sizes, other angular resolutions and views
+    smaller than a patch: every output sample comes from exactly one patch interior"""
     scene = np.random.RandomState(h0 * 131 + w0).random_sample((ang * h0, ang * w0)).astype(np.float32)
     sub = lf_oracle.lfdivide(scene, ang, patch, stride)
     bdr, nu, nv = lf_oracle.divide_geometry(h0, w0, patch, stride)
@@ -49,19 +50,28 @@ def test_divide_integrate_round_trip_any_size(ang, h0, w0, patch, stride, s):
     up = np.broadcast_to(up, (nu, nv, ang, patch, s, ang, patch, s)).reshape(nu, nv, ang * patch * s, ang * patch * s)
     lf = lf_oracle.lfintegrate(np.ascontiguousarray(up), ang, patch * s, stride * s, h0 * s, w0 * s)
     views = scene.reshape(ang, h0, ang, w0).transpose(0, 2, 1, 3)
-    want = np.repeat(np.repeat(views, s, axis=2), s, axis=3)
-    if bdr:
-        assert np.array_equal(lf, want)
-    else:
-        # reference quirk (utils.py:156-158, :176-178): numU = (h0 - 1) // stride patches do not reach the last rows when
-        # patches do not overlap; LFintegrate's crop to h x w then returns the covered part only
-        assert lf.shape[2:] == (nu * stride * s, nv * stride * s) and lf.shape[2] < h0 * s
-        assert np.array_equal(lf, want[:, :, :lf.shape[2], :lf.shape[3]])
+    assert np.array_equal(lf, np.repeat(np.repeat(views, s, axis=2), s, axis=3))
     assert np.array_equal(lf_oracle.to_sai(views), scene)
     # mirror padding: the first patch's top-left border is the reflected interior (utils.py:137-149)
-    if bdr:
-        p0 = sub[0, 0].reshape(ang, patch, ang, patch)
-        assert np.array_equal(p0[:, :bdr, :, bdr:bdr + 4], p0[:, 2 * bdr - 1:bdr - 1:-1, :, bdr:bdr + 4])
+    p0 = sub[0, 0].reshape(ang, patch, ang, patch)
+    assert np.array_equal(p0[:, :bdr, :, bdr:bdr + 4], p0[:, 2 * bdr - 1:bdr - 1:-1, :, bdr:bdr + 4])
+
+
+@pytest.mark.parametrize("h0,w0,patch,stride", [(40, 40, 16, 16), (17, 16, 32, 16), (64, 64, 32, 8), (64, 64, 48, 16), (4, 40, 32, 24),
+                                                (32, 7, 32, 16)])
+def test_divide_rejects_what_the_reference_cannot_tile(h0, w0, patch, stride):
+    """the reference's unfold / rearrange pair (utils.py:160-164) raises for non-overlapping patches, patch != 2 * stride in
+    general and views much smaller than a patch; oracle/make_golden.py sweeps 2580 geometries against the reference:
+    same accept / reject decision everywhere, identical values where it accepts"""
+    assert not lf_oracle.divide_supported(h0, w0, patch, stride)
+    with pytest.raises(ValueError):
+        lf_oracle.lfdivide(np.zeros((5 * h0, 5 * w0), np.float32), 5, patch, stride)
+    import lfsr_b200
+    with pytest.raises(ValueError):
+        lfsr_b200.lfutils.check_divide_geometry(h0, w0, patch, stride)
+    for ok in ((32, 32, 32, 16), (20, 75, 32, 16), (9, 30, 16, 8), (40, 56, 64, 32)):
+        assert lf_oracle.divide_supported(*ok)
+        lfsr_b200.lfutils.check_divide_geometry(*ok)
 
 
 def test_metrics_properties():
