@@ -97,7 +97,9 @@ uint64_t lfsr_launch_count(void);
 
 /* ---- patch pipeline ------------------------------------------------------------------ */
 /* LFdivide + ImageExtend (utils/utils.py:137-166): scene [A*h0, A*w0] -> [numU*numV, A*P, A*P],
- * numU = (h0 + 2*((P-S)/2) - 1)/S. Bit-exact gather with symmetric mirror padding. */
+ * numU = (h0 + 2*((P-S)/2) - 1)/S. Bit-exact gather with symmetric mirror padding. Geometries the reference's
+ * unfold / rearrange pair cannot tile (utils.py:160-164 raises: non-overlapping patches, P != 2*S in general, views much
+ * smaller than a patch) return LFSR_ERR_INVALID. */
 int lfsr_divide(const float* scene, float* patches, int ang, int h0, int w0, int patch, int stride,
                 void* stream);
 /* same, restricted to patch-grid rows [u_begin, u_end) (multi-GPU row sharding) */

@@ -95,11 +95,20 @@ extern "C" int lfsr_divide_rows(const float* scene, float* patches, int ang, int
                "lfsr_divide: bad geometry A=%d h0=%d w0=%d P=%d S=%d", ang, h0, w0, patch, stride);
   LFSR_REQUIRE(patch % 4 == 0, "lfsr_divide: patch size %d must be a multiple of 4", patch);
   const int bdr = (patch - stride) / 2;
-  // ImageExtend only mirrors one image period on each side (utils/utils.py:141-147)
-  LFSR_REQUIRE(h0 >= bdr + stride - 1 && w0 >= bdr + stride - 1 && h0 >= bdr && w0 >= bdr,
-               "lfsr_divide: view %dx%d smaller than the mirror border %d", h0, w0, bdr + stride - 1);
   const int numU = (h0 + 2 * bdr - 1) / stride, numV = (w0 + 2 * bdr - 1) / stride;
-  LFSR_REQUIRE(numU > 0 && numV > 0, "lfsr_divide: view too small for one patch");
+  // The reference pads bdr above and bdr + stride - 1 below out of ONE mirrored copy of the view (ImageExtend,
+  // utils/utils.py:141-147: at most n rows per side) and its unfold must then yield exactly numU x numV windows
+  // (utils.py:160-164), else it raises: same accept / reject rule here (oracle/make_golden.py sweeps it against the
+  // reference). Accepted geometries never index past one reflection, which is all mirror() implements.
+  auto tiles = [&](int n, int want) {
+    const int below = bdr + stride - 1 < n ? bdr + stride - 1 : n;
+    const int ext = n + bdr + below;
+    const int windows = ext >= patch ? (ext - patch) / stride + 1 : 0;
+    return n >= bdr && windows >= 1 && windows == want;
+  };
+  LFSR_REQUIRE(tiles(h0, numU) && tiles(w0, numV),
+               "lfsr_divide: %dx%d views cannot be tiled with patch %d / stride %d (the reference's LFdivide raises too)", h0,
+               w0, patch, stride);
   LFSR_REQUIRE(0 <= u_begin && u_begin <= u_end && u_end <= numU, "lfsr_divide: row shard [%d,%d) outside [0,%d)",
                u_begin, u_end, numU);
   if (u_begin == u_end) return LFSR_OK;
