@@ -808,8 +808,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kTmaWarp) {
-    // ================= TMA producer (converged warp, one elected lane issues: see elect_one()) =================
-    {
+    // ================= TMA producer: ONE elected lane runs the whole role loop (see elect_one()) =================
+    if (elect_one()) {
       int s_ring = 0;
       uint32_t ph_ring = 0;
       const int crank = p.pair ? (int)cluster_ctarank() : 0;
@@ -817,12 +817,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int m, chunk;
       if (p.resident && next_tile(p, 0, m, chunk)) {
         // one-time load of this CTA's whole weight set
-        if (elect_one()) {
-          mbar_expect_tx(bfull, (uint32_t)nks * p.b_stage_bytes);
-          for (int ks = 0; ks < nks; ++ks)
-            tma_load_2d(sB + ks * p.b_stage_bytes, &tmB, bfull, 0, (chunk * nks + ks) * p.NC);
-        }
-        __syncwarp();
+        mbar_expect_tx(bfull, (uint32_t)nks * p.b_stage_bytes);
+        for (int ks = 0; ks < nks; ++ks)
+          tma_load_2d(sB + ks * p.b_stage_bytes, &tmB, bfull, 0, (chunk * nks + ks) * p.NC);
       }
       if (CTA2) {        // stage = {own A tile, own HALF (NC/2 rows) of one (tap, channel group) of B}; bytes land on the leader's barrier
         const int crank2 = (int)cluster_ctarank();
@@ -834,13 +831,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
             const int s = s_ring++;
             mbar_wait(empty + s, ph_ring ^ 1);                // own barrier: the multicast commit arrives in both CTAs
+            if (crank2 == 0) mbar_expect_tx(full + s, 2u * kABytes + (uint32_t)p.NC * 128u);   // both CTAs' loads
             const short* to = p.tap_off[tap];
-            if (elect_one()) {
-              if (crank2 == 0) mbar_expect_tx(full + s, 2u * kABytes + (uint32_t)p.NC * 128u);   // both CTAs' loads
-              tma_load_5d_2sm(sA + s * kABytes, &tmA, full + s, cg * 32, t0.x0 + to[0], t0.vx + to[1], t0.y0 + to[2], t0.nb + to[3]);
-              tma_load_2d_2sm(sB + s * (p.b_stage_bytes >> 1), &tmBh, full + s, 0, ks * p.NC + crank2 * half_rows);
-            }
-            __syncwarp();
+            tma_load_5d_2sm(sA + s * kABytes, &tmA, full + s, cg * 32, t0.x0 + to[0], t0.vx + to[1], t0.y0 + to[2], t0.nb + to[3]);
+            tma_load_2d_2sm(sB + s * (p.b_stage_bytes >> 1), &tmBh, full + s, 0, ks * p.NC + crank2 * half_rows);
             if (++cg == p.cgs) { cg = 0; ++tap; }
           }
         }
@@ -855,14 +849,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
             const int s = s_ring++;
             mbar_wait(empty + s, ph_ring ^ 1);
+            mbar_expect_tx(full + s, 2u * kABytes + (uint32_t)p.NC * 128u);
             const short* to = p.tap_off[tap];
-            if (elect_one()) {
-              mbar_expect_tx(full + s, 2u * kABytes + (uint32_t)p.NC * 128u);
-              tma_load_5d(sA + (2 * s) * kABytes, &tmA, full + s, cg * 32, t0.x0 + to[0], t0.vx + to[1], t0.y0 + to[2], t0.nb + to[3]);
-              tma_load_5d(sA + (2 * s + 1) * kABytes, &tmA, full + s, cg * 32, t1.x0 + to[0], t1.vx + to[1], t1.y0 + to[2], t1.nb + to[3]);
-              tma_load_2d(sB + s * p.b_stage_bytes, &tmB, full + s, 0, ks * p.NC);
-            }
-            __syncwarp();
+            tma_load_5d(sA + (2 * s) * kABytes, &tmA, full + s, cg * 32, t0.x0 + to[0], t0.vx + to[1], t0.y0 + to[2], t0.nb + to[3]);
+            tma_load_5d(sA + (2 * s + 1) * kABytes, &tmA, full + s, cg * 32, t1.x0 + to[0], t1.vx + to[1], t1.y0 + to[2], t1.nb + to[3]);
+            tma_load_2d(sB + s * p.b_stage_bytes, &tmB, full + s, 0, ks * p.NC);
             if (++cg == p.cgs) { cg = 0; ++tap; }
           }
         }
@@ -882,38 +873,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(empty + s, ph_ring ^ 1);
           const int nsub = nks - ks < p.kps ? nks - ks : p.kps;
           const bool skip_a = p.dbg_skip_a == 1 ? i > 0 : (p.dbg_skip_a == 2 && tap > 0);
-          if (elect_one()) {
-            mbar_expect_tx(full + s, (uint32_t)nsub * (stage_bytes - (skip_a ? kABytes : 0)));
-            int cgl = cg, tapl = tap;
-            for (int u = 0; u < nsub; ++u) {
-              const short* to = p.tap_off[tapl];
-              const int slot = s * p.kps + u;
-              if (!skip_a) tma_load_5d(sA + slot * kABytes, &tmA, full + s, cgl * 32, b1 + to[0], b2 + to[1], b3 + to[2], b4 + to[3]);
-              if (!p.resident) {
-                if (p.pair) {        // my half of the rows, written into both CTAs of the pair
-                  const int half_rows = p.NC >> 1;
-                  tma_load_2d_mc(sB + slot * p.b_stage_bytes + crank * half_rows * 128, &tmBh, full + s, 0,
-                                 w_row0 + (ks + u) * p.NC + crank * half_rows, (uint16_t)3);
-                } else {
-                  tma_load_2d(sB + slot * p.b_stage_bytes, &tmB, full + s, 0, w_row0 + (ks + u) * p.NC);
-                }
+          mbar_expect_tx(full + s, (uint32_t)nsub * (stage_bytes - (skip_a ? kABytes : 0)));
+          for (int u = 0; u < nsub; ++u) {
+            const short* to = p.tap_off[tap];
+            const int slot = s * p.kps + u;
+            if (!skip_a) tma_load_5d(sA + slot * kABytes, &tmA, full + s, cg * 32, b1 + to[0], b2 + to[1], b3 + to[2], b4 + to[3]);
+            if (!p.resident) {
+              if (p.pair) {        // my half of the rows, written into both CTAs of the pair
+                const int half_rows = p.NC >> 1;
+                tma_load_2d_mc(sB + slot * p.b_stage_bytes + crank * half_rows * 128, &tmBh, full + s, 0,
+                               w_row0 + (ks + u) * p.NC + crank * half_rows, (uint16_t)3);
+              } else {
+                tma_load_2d(sB + slot * p.b_stage_bytes, &tmB, full + s, 0, w_row0 + (ks + u) * p.NC);
               }
-              if (++cgl == p.cgs) { cgl = 0; ++tapl; }
             }
-          }
-          __syncwarp();
-          for (int u = 0; u < nsub; ++u)
             if (++cg == p.cgs) { cg = 0; ++tap; }
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
-    // The whole warp walks the loop (uniform control flow, every lane polls the barriers) and one elected lane issues:
-    // see elect_one(). The issuing lane is in lock-step with the tensor pipe (the MMA queue is ~4 instructions deep), so
-    // everything in the issue section that is not a tcgen05.mma is overhead.
-    {
+    // The whole role loop runs in ONE lane chosen by elect.sync, inside a single elect block: no per-stage __syncwarp /
+    // re-election (probe_mma_rate2.py: leaving and re-entering the elect block costs the tensor pipe ~200 cycles per
+    // stage at N = 64) and, unlike `if (lane == 0)`, ptxas keeps the tcgen05 operands in uniform registers. That lane is in
+    // lock-step with the tensor pipe (the MMA queue is shallow), so everything here that is not a tcgen05.mma is overhead.
+    if (elect_one()) {
       long long dbg_full_wait = 0, dbg_acc_wait = 0, dbg_mma = 0;
       const long long dbg_t0 = clock64();
       uint32_t tcount = 0;
@@ -952,14 +938,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint64_t a_d = a_desc0 + (uint64_t)s * (kABytes >> 4);
               const uint64_t b_d = b_desc0 + (uint64_t)s * b_half_step;
               const int ksteps = (cg_i == p.cgs - 1) ? ksteps_last : 4;
-              if (elect_one()) {
-                if (ks == 0) umma2_tf32_c<0>(d_tmem, a_d, b_d, idesc2); else umma2_tf32_c<1>(d_tmem, a_d, b_d, idesc2);
-                for (int k = 1; k < ksteps; ++k) umma2_tf32_c<1>(d_tmem, a_d + 2 * k, b_d + 2 * k, idesc2);
-                umma2_commit_mc(empty + s);
-                if (ks + 1 == nks) umma2_commit_mc(tfull + a);
-              }
-              __syncwarp();
+              if (ks == 0) umma2_tf32_c<0>(d_tmem, a_d, b_d, idesc2); else umma2_tf32_c<1>(d_tmem, a_d, b_d, idesc2);
+              for (int k = 1; k < ksteps; ++k) umma2_tf32_c<1>(d_tmem, a_d + 2 * k, b_d + 2 * k, idesc2);
               if (++cg_i == p.cgs) cg_i = 0;
+              umma2_commit_mc(empty + s);
+              if (ks + 1 == nks) umma2_commit_mc(tfull + a);
               if (p.dbg) dbg_mma += clock64() - tw1;
             }
           }
@@ -985,27 +968,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t a_d0 = a_desc0 + (uint64_t)(2 * s) * (kABytes >> 4), a_d1 = a_d0 + (uint64_t)(kABytes >> 4);
             const uint64_t b_d = b_desc0 + (uint64_t)s * b_step;
             const int ksteps = (cg_i == p.cgs - 1) ? ksteps_last : 4;
-            if (ks == 0) {
-              if (elect_one()) umma_stage<true>(tmem_base, a_d0, b_d, idesc, ksteps);
-              __syncwarp();
-              // ... and accumulator 1 by the epilogue of its second tile
+            if (ks == 0) umma_stage<true>(tmem_base, a_d0, b_d, idesc, ksteps);
+            else umma_stage<false>(tmem_base, a_d0, b_d, idesc, ksteps);
+            if (ks == 0) {                       // ... and accumulator 1 by the epilogue of its second tile
               if (p.dbg) tw0 = clock64();
               mbar_wait(tempty + 1, aph ^ 1);
               if (p.dbg) { const long long t = clock64() - tw0; dbg_acc_wait += t; tw1 += t; }
               tc_fence_after();
-              if (elect_one()) {
-                umma_stage<true>(tmem_base + kAccStride, a_d1, b_d, idesc, ksteps);
-                umma_commit(empty + s);
-                if (nks == 1) { umma_commit(tfull + 0); umma_commit(tfull + 1); }
-              }
-            } else if (elect_one()) {
-              umma_stage<false>(tmem_base, a_d0, b_d, idesc, ksteps);
+              umma_stage<true>(tmem_base + kAccStride, a_d1, b_d, idesc, ksteps);
+            } else {
               umma_stage<false>(tmem_base + kAccStride, a_d1, b_d, idesc, ksteps);
-              umma_commit(empty + s);
-              if (ks + 1 == nks) { umma_commit(tfull + 0); umma_commit(tfull + 1); }
             }
-            __syncwarp();
             if (++cg_i == p.cgs) cg_i = 0;
+            umma_commit(empty + s);
+            if (ks + 1 == nks) { umma_commit(tfull + 0); umma_commit(tfull + 1); }
             if (p.dbg) dbg_mma += clock64() - tw1;
           }
         }
@@ -1029,39 +1005,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint64_t a_d0 = a_desc0 + (uint64_t)(s * a_stage_step);
           const uint64_t b_d0 = b_desc0 + (uint64_t)(p.resident ? ks * b_step : s * b_stage_step);
-          const int nsub = nks - ks < p.kps ? nks - ks : p.kps;
-          if (elect_one()) {
-            if (tap_stages) {              // stage == one tap with all channel groups: fully unrolled issue
-              if (ks == 0) umma_tap_dispatch<true>(p.cgs, d_tmem, a_d0, b_d0, b_step, idesc, ksteps_last);
-              else umma_tap_dispatch<false>(p.cgs, d_tmem, a_d0, b_d0, b_step, idesc, ksteps_last);
-            } else if (p.kps == 1) {       // stage == one (tap, channel group)
+          if (tap_stages) {              // stage == one tap with all channel groups: fully unrolled issue
+            if (ks == 0) umma_tap_dispatch<true>(p.cgs, d_tmem, a_d0, b_d0, b_step, idesc, ksteps_last);
+            else umma_tap_dispatch<false>(p.cgs, d_tmem, a_d0, b_d0, b_step, idesc, ksteps_last);
+          } else if (p.kps == 1) {       // stage == one (tap, channel group)
+            const int ksteps = (cg_i == p.cgs - 1) ? ksteps_last : 4;
+            if (ks == 0) umma_stage<true>(d_tmem, a_d0, b_d0, idesc, ksteps);
+            else umma_stage<false>(d_tmem, a_d0, b_d0, idesc, ksteps);
+            if (++cg_i == p.cgs) cg_i = 0;
+          } else {
+            const int nsub = nks - ks < p.kps ? nks - ks : p.kps;
+            for (int u = 0; u < nsub; ++u) {
               const int ksteps = (cg_i == p.cgs - 1) ? ksteps_last : 4;
-              if (ks == 0) umma_stage<true>(d_tmem, a_d0, b_d0, idesc, ksteps);
-              else umma_stage<false>(d_tmem, a_d0, b_d0, idesc, ksteps);
-            } else {
-              int cgl = cg_i;
-              for (int u = 0; u < nsub; ++u) {
-                const int ksteps = (cgl == p.cgs - 1) ? ksteps_last : 4;
-                const uint64_t a_d = a_d0 + (uint64_t)(u * (kABytes >> 4));
-                const uint64_t b_d = b_d0 + (uint64_t)(u * b_step);
-                if (ks + u == 0) umma_stage<true>(d_tmem, a_d, b_d, idesc, ksteps);
-                else umma_stage<false>(d_tmem, a_d, b_d, idesc, ksteps);
-                if (++cgl == p.cgs) cgl = 0;
-              }
+              const uint64_t a_d = a_d0 + (uint64_t)(u * (kABytes >> 4));
+              const uint64_t b_d = b_d0 + (uint64_t)(u * b_step);
+              if (ks + u == 0) umma_stage<true>(d_tmem, a_d, b_d, idesc, ksteps);
+              else umma_stage<false>(d_tmem, a_d, b_d, idesc, ksteps);
+              if (++cg_i == p.cgs) cg_i = 0;
             }
-            if (p.pair) umma_commit_mc(empty + s, (uint16_t)3);   // both CTAs must be done before either refills the stage
-            else umma_commit(empty + s);                       // frees the smem stage when these MMAs retire
-            if (ks + p.kps >= nks) umma_commit(tfull + a);     // accumulator complete -> epilogue
-            if (p.dbg_skip_a == 4) umma_commit(bfull);         // experiment: cost of one more commit per stage (streamed B only)
           }
-          __syncwarp();
-          if (p.dbg_skip_a == 5) { mbar_wait(full + s, ph_ring); tc_fence_after(); }   // experiment: one more (already complete) wait
-          if (p.dbg_skip_a == 6) { if (elect_one()) tc_fence_after(); __syncwarp(); }  // experiment: one more elect block
-          if (!tap_stages) cg_i = (cg_i + nsub) % p.cgs;
+          if (p.pair) umma_commit_mc(empty + s, (uint16_t)3);   // both CTAs must be done before either refills the stage
+          else umma_commit(empty + s);                       // frees the smem stage when these MMAs retire
+          if (ks + p.kps >= nks) umma_commit(tfull + a);     // accumulator complete -> epilogue
           if (p.dbg) dbg_mma += clock64() - tw1;
         }
       }
-      if (p.dbg && lane == 0) {
+      if (p.dbg) {
         p.dbg[blockIdx.x * 8 + 2] = dbg_full_wait; p.dbg[blockIdx.x * 8 + 3] = dbg_acc_wait;
         p.dbg[blockIdx.x * 8 + 4] = dbg_mma; p.dbg[blockIdx.x * 8 + 5] = clock64() - dbg_t0;
       }

@@ -8,8 +8,8 @@ fn = lib.lfsr_debug_mma_rate
 fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
-for N in (64, 224):
-    for alt in (0, 4, 8):
+for N in (32, 64, 128, 224):
+    for alt in (0, 4, 8, 16):
         for kmode in (0,):
             res = []
             for chain in (16, 64):

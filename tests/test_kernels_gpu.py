@@ -98,8 +98,11 @@ def test_divide_row_shards_and_6d(ops):
     a = lfsr_b200.lfutils.LFintegrate(full, A, P, S, 70, 52)
     b = lfsr_b200.lfutils.LFintegrate(six, A, P, S, 70, 52)
     assert torch.equal(a, b)
-    with pytest.raises(N.LfsrError):
-        lfsr_b200.lfutils.LFdivide(rnd(A * 10, A * 10), A, P, S)   # smaller than the mirror border
+    small = rnd(A * 10, A * 10)                                    # the reference's unfold finds no window here
+    with pytest.raises(ValueError):
+        lfsr_b200.lfutils.LFdivide(small, A, P, S)
+    with pytest.raises(N.LfsrError):                               # ... and the C ABI refuses it by itself
+        ops.divide_rows(small, torch.empty(1, 1, A * P, A * P, device=DEV), A, 10, 10, P, S, 0, 1)
 
 
 @pytest.mark.parametrize("mode,block", [(0, None), (0, 8), (1, None)])
