@@ -762,7 +762,8 @@ __device__ __forceinline__ void epilogue_tile_tail(const Params& p, const float*
 // (register files are allocated for 4-warp groups: 320 threads cost what 384 do, i.e. at most 168 registers each)
 // CTA2 = true is a separate instantiation: a kernel that contains cta_group::2 instructions can only be launched in
 // clusters of two, so the single-CTA paths must not see them
-template <bool CTA2>
+// DBG = false compiles the cycle counters (LFSR_TC_DBG_PTR) out of the role loops
+template <bool CTA2, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmO, const Params p) {
@@ -921,19 +922,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; next_tile(p, i, m, chunk); ++i, ++tcount) {
             const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
             long long tw0 = 0;
-            if (p.dbg) tw0 = clock64();
+            if ((DBG && p.dbg)) tw0 = clock64();
             mbar_wait(tempty + a, aph ^ 1);               // both CTAs' epilogues have drained this accumulator stage
-            if (p.dbg) dbg_acc_wait += clock64() - tw0;
+            if ((DBG && p.dbg)) dbg_acc_wait += clock64() - tw0;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + a * kAccStride;
             int cg_i = 0;
             for (int ks = 0; ks < nks; ++ks) {
               if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
               const int s = s_ring++;
-              if (p.dbg) tw0 = clock64();
+              if ((DBG && p.dbg)) tw0 = clock64();
               mbar_wait(full + s, ph_ring);
               long long tw1 = 0;
-              if (p.dbg) { tw1 = clock64(); dbg_full_wait += tw1 - tw0; }
+              if ((DBG && p.dbg)) { tw1 = clock64(); dbg_full_wait += tw1 - tw0; }
               tc_fence_after();
               const uint64_t a_d = a_desc0 + (uint64_t)s * (kABytes >> 4);
               const uint64_t b_d = b_desc0 + (uint64_t)s * b_half_step;
@@ -943,7 +944,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (++cg_i == p.cgs) cg_i = 0;
               umma2_commit_mc(empty + s);
               if (ks + 1 == nks) umma2_commit_mc(tfull + a);
-              if (p.dbg) dbg_mma += clock64() - tw1;
+              if ((DBG && p.dbg)) dbg_mma += clock64() - tw1;
             }
           }
         }
@@ -957,13 +958,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int s = s_ring++;
             long long tw0 = 0, tw1 = 0;
             if (ks == 0) {                       // accumulator 0 drained by the epilogue of the previous pair's first tile
-              if (p.dbg) tw0 = clock64();
+              if ((DBG && p.dbg)) tw0 = clock64();
               mbar_wait(tempty + 0, aph ^ 1);
-              if (p.dbg) dbg_acc_wait += clock64() - tw0;
+              if ((DBG && p.dbg)) dbg_acc_wait += clock64() - tw0;
             }
-            if (p.dbg) tw0 = clock64();
+            if ((DBG && p.dbg)) tw0 = clock64();
             mbar_wait(full + s, ph_ring);
-            if (p.dbg) { tw1 = clock64(); dbg_full_wait += tw1 - tw0; }
+            if ((DBG && p.dbg)) { tw1 = clock64(); dbg_full_wait += tw1 - tw0; }
             tc_fence_after();
             const uint64_t a_d0 = a_desc0 + (uint64_t)(2 * s) * (kABytes >> 4), a_d1 = a_d0 + (uint64_t)(kABytes >> 4);
             const uint64_t b_d = b_desc0 + (uint64_t)s * b_step;
@@ -971,9 +972,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (ks == 0) umma_stage<true>(tmem_base, a_d0, b_d, idesc, ksteps);
             else umma_stage<false>(tmem_base, a_d0, b_d, idesc, ksteps);
             if (ks == 0) {                       // ... and accumulator 1 by the epilogue of its second tile
-              if (p.dbg) tw0 = clock64();
+              if ((DBG && p.dbg)) tw0 = clock64();
               mbar_wait(tempty + 1, aph ^ 1);
-              if (p.dbg) { const long long t = clock64() - tw0; dbg_acc_wait += t; tw1 += t; }
+              if ((DBG && p.dbg)) { const long long t = clock64() - tw0; dbg_acc_wait += t; tw1 += t; }
               tc_fence_after();
               umma_stage<true>(tmem_base + kAccStride, a_d1, b_d, idesc, ksteps);
             } else {
@@ -982,26 +983,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++cg_i == p.cgs) cg_i = 0;
             umma_commit(empty + s);
             if (ks + 1 == nks) { umma_commit(tfull + 0); umma_commit(tfull + 1); }
-            if (p.dbg) dbg_mma += clock64() - tw1;
+            if ((DBG && p.dbg)) dbg_mma += clock64() - tw1;
           }
         }
       } else
       for (int i = 0; next_tile(p, i, m, chunk); ++i, ++tcount) {
         const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
         long long tw0 = 0;
-        if (p.dbg) tw0 = clock64();
+        if ((DBG && p.dbg)) tw0 = clock64();
         mbar_wait(tempty + a, aph ^ 1);
-        if (p.dbg) dbg_acc_wait += clock64() - tw0;
+        if ((DBG && p.dbg)) dbg_acc_wait += clock64() - tw0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * kAccStride;
         int cg_i = 0;
         for (int ks = 0; ks < nks; ks += p.kps) {
           if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
           const int s = s_ring++;
-          if (p.dbg) tw0 = clock64();
+          if ((DBG && p.dbg)) tw0 = clock64();
           mbar_wait(full + s, ph_ring);
           long long tw1 = 0;
-          if (p.dbg) { tw1 = clock64(); dbg_full_wait += tw1 - tw0; }
+          if ((DBG && p.dbg)) { tw1 = clock64(); dbg_full_wait += tw1 - tw0; }
           tc_fence_after();
           const uint64_t a_d0 = a_desc0 + (uint64_t)(s * a_stage_step);
           const uint64_t b_d0 = b_desc0 + (uint64_t)(p.resident ? ks * b_step : s * b_stage_step);
@@ -1027,10 +1028,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.pair) umma_commit_mc(empty + s, (uint16_t)3);   // both CTAs must be done before either refills the stage
           else umma_commit(empty + s);                       // frees the smem stage when these MMAs retire
           if (ks + p.kps >= nks) umma_commit(tfull + a);     // accumulator complete -> epilogue
-          if (p.dbg) dbg_mma += clock64() - tw1;
+          if ((DBG && p.dbg)) dbg_mma += clock64() - tw1;
         }
       }
-      if (p.dbg) {
+      if ((DBG && p.dbg)) {
         p.dbg[blockIdx.x * 8 + 2] = dbg_full_wait; p.dbg[blockIdx.x * 8 + 3] = dbg_acc_wait;
         p.dbg[blockIdx.x * 8 + 4] = dbg_mma; p.dbg[blockIdx.x * 8 + 5] = clock64() - dbg_t0;
       }
@@ -1046,7 +1047,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t tcount = 0;
     int m_, chunk_;
     long long dbg_wait = 0, dbg_t0 = 0, tw0 = 0, dbg_ld = 0, dbg_epi = 0;
-    if (p.dbg) dbg_t0 = clock64();
+    if ((DBG && p.dbg)) dbg_t0 = clock64();
     for (int i = 0; next_tile(p, i, m_, chunk_); ++i, ++tcount) {
       const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
       const TileCoord tc_ = decode_tile(p, m_, chunk_);
@@ -1055,25 +1056,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.tail_w && m_ >= 0) {
         epilogue_tile_tail(p, sTail, taddr, lane, q, tc_, half, 2, tfull + a, aph);
       } else if (p.tma_epi && m_ >= 0) {
-        if (p.dbg) tw1 = clock64();
-        epilogue_tile_tma(p, &tmO, stg, taddr, lane, q, tc_, half, 2, tfull + a, aph, p.dbg ? &dbg_ld : nullptr);
-        if (p.dbg) dbg_epi += clock64() - tw1;
+        if ((DBG && p.dbg)) tw1 = clock64();
+        epilogue_tile_tma(p, &tmO, stg, taddr, lane, q, tc_, half, 2, tfull + a, aph, (DBG && p.dbg) ? &dbg_ld : nullptr);
+        if ((DBG && p.dbg)) dbg_epi += clock64() - tw1;
       } else {
-        if (p.dbg) tw0 = clock64();
+        if ((DBG && p.dbg)) tw0 = clock64();
         mbar_wait(tfull + a, aph);
-        if (p.dbg) dbg_wait += clock64() - tw0;
+        if ((DBG && p.dbg)) dbg_wait += clock64() - tw0;
         tc_fence_after();
-        if (p.dbg) tw1 = clock64();
-        if (m_ >= 0) epilogue_tile(p, stg, taddr, lane, q, tc_, 0, half, 2, p.dbg ? &dbg_ld : nullptr);
-        if (p.dbg) dbg_epi += clock64() - tw1;
+        if ((DBG && p.dbg)) tw1 = clock64();
+        if (m_ >= 0) epilogue_tile(p, stg, taddr, lane, q, tc_, 0, half, 2, (DBG && p.dbg) ? &dbg_ld : nullptr);
+        if ((DBG && p.dbg)) dbg_epi += clock64() - tw1;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (CTA2) mbar_arrive_leader(tempty + a); else mbar_arrive(tempty + a); }
     }
     if (p.tma_epi && lane == 0) bulk_wait0();     // all of this warp's tensor stores have landed
-    if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 0] = dbg_ld;        // TMA path: cycles waiting for the store unit to release the staging buffer
-    if (p.dbg && threadIdx.x == 0) {
+    if ((DBG && p.dbg) && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 0] = dbg_ld;        // TMA path: cycles waiting for the store unit to release the staging buffer
+    if ((DBG && p.dbg) && threadIdx.x == 0) {
       p.dbg[blockIdx.x * 8 + 1] = dbg_epi;
       p.dbg[blockIdx.x * 8 + 6] = dbg_wait; p.dbg[blockIdx.x * 8 + 7] = clock64() - dbg_t0;
     }
@@ -1454,8 +1455,10 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
 
@@ -1738,8 +1741,13 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (p.pair || p.cta2) ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, tmA, tmB, tmBh, tmO, p)
-                          : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, tmA, tmB, tmBh, tmO, p);
+  cudaError_t le;
+  if (p.dbg)
+    le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, tmA, tmB, tmBh, tmO, p)
+                : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, tmA, tmB, tmBh, tmO, p);
+  else
+    le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, tmA, tmB, tmBh, tmO, p)
+                : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, tmA, tmB, tmBh, tmO, p);
   if (le != cudaSuccess) { set_error("lfsr_conv2d_tc: launch failed: %s", cudaGetErrorString(le)); return LFSR_ERR_CUDA; }
   return check_launch("conv_tc_kernel");
 }
