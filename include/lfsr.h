@@ -237,6 +237,11 @@ int lfsr_epi_attention(const float* qk, const float* v, float* out, const lfsr_e
  * acc must be zeroed by the caller (cudaMemsetAsync) - 2*A*A doubles. */
 int lfsr_metric_sums(const float* label, const float* out, int ang, int h, int w, double* acc,
                      void* stream);
+/* the same for n mosaics stored back to back (a [n,1,A*h,A*w] batch of SR patches against their HR patches, BASELINE
+ * config 5: on-GPU evaluation of a large batch): acc[(img*A*A + view)] = {sum sq. err, sum SSIM}, 2*n*A*A doubles, zeroed
+ * by the caller. */
+int lfsr_metric_sums_batched(const float* label, const float* out, int n, int ang, int h, int w, double* acc,
+                             void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,9 @@ import subprocess
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "liblfsr_b200.so")
+#: measurement scripts under profiles/ set LFSR_PROBE_LIB=1 to load the probe build instead: the same kernels compiled with
+#: -DLFSR_DEBUG_HOOKS (cycle counters, LFSR_TC_* experiment switches) plus the rate probes of csrc/lfsr_debug.cu
+PROBE_LIB_PATH = os.path.join(_PKG_DIR, "liblfsr_probe.so")
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_GELU, ACT_SILU = 0, 1, 2, 3, 4, 5
@@ -96,6 +99,7 @@ SIGNATURES = {
     "lfsr_layernorm": (_I, [_TP, _P, _P, C.c_float, _TP, _P]),
     "lfsr_epi_attention": (_I, [_P, _P, _P, C.POINTER(EpiAttnDesc), _P]),
     "lfsr_metric_sums": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "lfsr_metric_sums_batched": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
 }
 
 _lib = None
@@ -117,11 +121,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = PROBE_LIB_PATH if os.environ.get("LFSR_PROBE_LIB") == "1" else LIB_PATH
+    if not os.path.exists(path):
         raise LfsrError(
-            f"{LIB_PATH} is missing: the sm_100a CUDA extension has not been built "
+            f"{path} is missing: the sm_100a CUDA extension has not been built "
             "(run __graft_entry__.build()); there is no CPU fallback for this path")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the export is missing - intended
         fn.restype = res

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <atomic>
 #include "../../include/lfsr.h"
 
@@ -19,6 +20,55 @@ inline int check_launch(const char* what) {
     return LFSR_ERR_CUDA;
   }
   return LFSR_OK;
+}
+
+// CUDA function attributes (and SM counts) belong to a DEVICE: a process that later runs on a second GPU must opt every
+// kernel into > 48 KB of dynamic shared memory there too, so one-time setup is tracked per device and its return code is
+// checked. Usage:  static DevOnce once;  if (once.need()) { <set attributes, return on error>;  once.done(); }
+struct DevOnce {
+  std::atomic<uint64_t> mask{0};
+  int dev = 0;
+  bool need() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return !(mask.load(std::memory_order_acquire) & (1ull << (d & 63)));
+  }
+  void done() {
+    int d = 0;
+    cudaGetDevice(&d);
+    mask.fetch_or(1ull << (d & 63), std::memory_order_release);
+  }
+};
+template <class K>
+inline int opt_in_smem(K kernel, int bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %d): %s", what, bytes, cudaGetErrorString(e));
+    return LFSR_ERR_CUDA;
+  }
+  return LFSR_OK;
+}
+// SM count of the CURRENT device (cached per device ordinal)
+inline int sm_count_current() {
+  static std::atomic<int> cache[64];
+  int d = 0;
+  cudaGetDevice(&d);
+  int v = cache[d & 63].load(std::memory_order_relaxed);
+  if (v <= 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d);
+    cache[d & 63].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+// Experiment switches (profiles/ probes) are read from the environment ONLY in the probe build (-DLFSR_DEBUG_HOOKS,
+// liblfsr_probe.so): the product library ignores them, so a stray variable can neither steer nor corrupt a product run.
+inline const char* dbg_env(const char* name) {
+#ifdef LFSR_DEBUG_HOOKS
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
 }
 
 #define LFSR_REQUIRE(cond, ...)            \

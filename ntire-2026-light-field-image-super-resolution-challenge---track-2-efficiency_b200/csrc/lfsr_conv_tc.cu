@@ -873,7 +873,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int s = s_ring++;
           mbar_wait(empty + s, ph_ring ^ 1);
           const int nsub = nks - ks < p.kps ? nks - ks : p.kps;
+#ifdef LFSR_DEBUG_HOOKS
           const bool skip_a = p.dbg_skip_a == 1 ? i > 0 : (p.dbg_skip_a == 2 && tap > 0);
+#else
+          const bool skip_a = false;
+#endif
           mbar_expect_tx(full + s, (uint32_t)nsub * (stage_bytes - (skip_a ? kABytes : 0)));
           for (int u = 0; u < nsub; ++u) {
             const short* to = p.tap_off[tap];
@@ -1447,25 +1451,27 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
       break;
   }
   p.b_stage_bytes = p.NC * 128;
+#ifdef LFSR_DEBUG_HOOKS      // probe build only (liblfsr_probe.so): cycle counters / deliberately wrong experiments
   p.dbg_skip_a = getenv("LFSR_TC_DBG_SKIP_A") ? atoi(getenv("LFSR_TC_DBG_SKIP_A")) : 0;
   p.dbg = getenv("LFSR_TC_DBG_PTR") ? (long long*)strtoull(getenv("LFSR_TC_DBG_PTR"), nullptr, 0) : nullptr;
-  static int sm_count = 0;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
+#endif
+  const int sm_count = sm_count_current();
+  static DevOnce once;
+  if (once.need()) {
+    const char* w_ = "lfsr_conv2d_tc";
+    if (opt_in_smem(conv_tc_kernel<false, false>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, false>, 227 * 1024, w_) ||
+#ifdef LFSR_DEBUG_HOOKS
+        opt_in_smem(conv_tc_kernel<false, true>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, true>, 227 * 1024, w_) ||
+#endif
+        opt_in_smem(conv_tc_halo_kernel, 227 * 1024, w_))
+      return LFSR_ERR_CUDA;
+    once.done();
+  }
 
   // ---- halo-block plan: multi-tap kernels whose haloed input block fits in shared memory -------------
   // Measured on B200 (profiles/r01_notes.md): correct, but not yet faster than the per-tap kernel below - the single
   // accumulator stage at N = 224 serialises epilogue and MMAs - so it is opt-in (LFSR_TC_HALO=1) until that is fixed.
-  static const bool use_halo = getenv("LFSR_TC_HALO") != nullptr;
+  static const bool use_halo = dbg_env("LFSR_TC_HALO") != nullptr;
   if (use_halo && !d->tail_w && d->w_batch_stride <= 0 && p.kh * p.kw > 1 && p.cgs <= 2 && p.nchunks == 1) {
     const int taps = p.kh * p.kw, nks = taps * p.cgs;
     const int kSmemAvail = 227 * 1024 - 1024 - 512 - 16 * 1024;
@@ -1560,9 +1566,9 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   // Plan = (weights resident?, K-stages per smem stage). Preference: one tap with all its channel groups per stage
   // (short unrolled issue stream, fewer barrier round trips) with enough stages in flight; weights resident when
   // that still fits, else streamed next to the activations.
-  static const bool no_resident = getenv("LFSR_TC_NO_RESIDENT") != nullptr;   // tuning knobs (profiles/ experiments)
-  static const int max_stages_env = getenv("LFSR_TC_STAGES") ? atoi(getenv("LFSR_TC_STAGES")) : 0;
-  static const int kps_env = getenv("LFSR_TC_KPS") ? atoi(getenv("LFSR_TC_KPS")) : 0;
+  static const bool no_resident = dbg_env("LFSR_TC_NO_RESIDENT") != nullptr;   // tuning knobs (profiles/ experiments)
+  static const int max_stages_env = dbg_env("LFSR_TC_STAGES") ? atoi(dbg_env("LFSR_TC_STAGES")) : 0;
+  static const int kps_env = dbg_env("LFSR_TC_KPS") ? atoi(dbg_env("LFSR_TC_KPS")) : 0;
   auto stages_for = [&](bool res, int kps) -> int {
     if (res) return b_all >= kSmemMax ? 0 : (int)((kSmemMax - b_all) / ((long long)kps * kABytes));
     return (kSmemBudget - kEpiWarps * 4096 - tail_bytes) / (kps * (kABytes + p.b_stage_bytes));
@@ -1591,15 +1597,15 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   // of activations. Walking M-tile PAIRS halves the weight writes per MMA: one stage = two activation tiles + one slice.
   // CTA pairs with cta_group::2 MMAs (M = 256): each SM stages its own activation tile and HALF of the weight slice, the
   // leader's MMA thread issues for both; unlike twin tiles this keeps both accumulator stages per SM (epilogue overlapped)
-  static const bool use_cta2 = getenv("LFSR_TC_NO_CTA2") == nullptr;
+  static const bool use_cta2 = dbg_env("LFSR_TC_NO_CTA2") == nullptr;
   p.cta2 = 0;
-  static const int cta2_min_nc = getenv("LFSR_TC_CTA2_MIN_NC") ? atoi(getenv("LFSR_TC_CTA2_MIN_NC")) : 128;
+  static const int cta2_min_nc = dbg_env("LFSR_TC_CTA2_MIN_NC") ? atoi(dbg_env("LFSR_TC_CTA2_MIN_NC")) : 128;
   if (use_cta2 && !p.resident && !per_image_w && p.nchunks == 1 && p.amode == 0 && p.NC >= cta2_min_nc && p.NC % 16 == 0 &&
       p.m_tiles >= 4 && sm_count >= 2) {
     const int st = (kSmemBudget - kEpiWarps * 4096 - tail_bytes) / (kABytes + p.b_stage_bytes / 2);
     if (st >= 2) { p.cta2 = 1; p.kps = 1; p.stages = st > kMaxStages ? kMaxStages : st; }
   }
-  static const bool no_twin = getenv("LFSR_TC_NO_TWIN") != nullptr;
+  static const bool no_twin = dbg_env("LFSR_TC_NO_TWIN") != nullptr;
   p.twin = 0;
   if (!p.cta2 && !no_twin && !p.resident && !per_image_w && p.kps == 1 && p.nchunks == 1 && p.amode == 0 && p.NC >= 128 && p.m_tiles >= 4) {
     const int st = (kSmemBudget - kEpiWarps * 4096 - tail_bytes) / (2 * kABytes + p.b_stage_bytes);
@@ -1626,7 +1632,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
       box[1] = 1; box[2] = p.TW; box[3] = 1; box[4] = p.TH;
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    static const bool a_trunc = getenv("LFSR_TC_A_TRUNC") != nullptr;   // experiment: plain fp32 loads (MMA truncates)
+    static const bool a_trunc = dbg_env("LFSR_TC_A_TRUNC") != nullptr;   // experiment: plain fp32 loads (MMA truncates)
     CUresult r = encode(&tmA, a_trunc ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, in->ptr, dims,
                         strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1663,7 +1669,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   // CTA pairs with multicast weights for wide streamed layers (weights are 64 % of their L2->SM traffic)
   // (measured on B200: parity-green but no gain - 3.90 ms with and without at batch 64, the weight stages are L2 hits
   //  that were not the limiter - so it is opt-in: LFSR_TC_PAIR=1)
-  static const bool use_pair = getenv("LFSR_TC_PAIR") != nullptr;
+  static const bool use_pair = dbg_env("LFSR_TC_PAIR") != nullptr;
   p.pair = (use_pair && !p.twin && !p.cta2 && !p.resident && !per_image_w && p.NC >= 128 && p.NC % 16 == 0 && grid >= 2 && p.nchunks == 1) ? 1 : 0;
   CUtensorMap tmBh = tmB;
   if (p.pair || p.cta2) {
@@ -1682,7 +1688,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   // image*block-y), exactly the activation map's structure, so partial tiles are clipped at block edges. With one:
   // dims (c, j, x, i, image*OH + y); rows of different images share a dimension there, so tiles must not overhang
   // the image bottom (OH % TH == 0), and residual / multiplier operands stay with the per-row write-out.
-  static const bool no_tma_epi = getenv("LFSR_TC_NO_TMA_EPI") != nullptr;
+  static const bool no_tma_epi = dbg_env("LFSR_TC_NO_TMA_EPI") != nullptr;
   CUtensorMap tmO = tmA;
   {
     const int r2 = ry * rx;
@@ -1730,7 +1736,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
       p.tma_epi = 1;
     }
   }
-  static const bool verbose = getenv("LFSR_TC_VERBOSE") != nullptr;
+  static const bool verbose = dbg_env("LFSR_TC_VERBOSE") != nullptr;
   if (verbose)
     fprintf(stderr, "[lfsr tc] C=%d cout=%d NC=%d k=%dx%d tiles=%d grid=%d stages=%d kps=%d resident=%d pair=%d twin=%d cta2=%d TH=%d TW=%d vec=%d tma_epi=%d smem=%zu\n",
             p.C, p.cout, p.NC, p.kh, p.kw, p.total_tiles, grid, p.stages, p.kps, p.resident, p.pair, p.twin, p.cta2, p.TH, p.TW, p.vec, p.tma_epi, smem);
@@ -1742,10 +1748,12 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   attr[0].val.clusterDim.x = (p.pair || p.cta2) ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaError_t le;
+#ifdef LFSR_DEBUG_HOOKS
   if (p.dbg)
     le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, tmA, tmB, tmBh, tmO, p)
                 : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, tmA, tmB, tmBh, tmO, p);
   else
+#endif
     le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, tmA, tmB, tmBh, tmO, p)
                 : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, tmA, tmB, tmBh, tmO, p);
   if (le != cudaSuccess) { set_error("lfsr_conv2d_tc: launch failed: %s", cudaGetErrorString(le)); return LFSR_ERR_CUDA; }

@@ -405,7 +405,7 @@ static int dw_launch(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_d
     if (b.kh * b.kw * DW_CH > w_floats) w_floats = b.kh * b.kw * DW_CH;
   }
   p.share = 0; p.share_b = 0;
-  if (!sa && nbr > 1 && !getenv("LFSR_DW_NO_SHARE")) {
+  if (!sa && nbr > 1 && !dbg_env("LFSR_DW_NO_SHARE")) {
     bool same = true;
     size_t best = 0;
     int wsum = 0;
@@ -429,7 +429,7 @@ static int dw_launch(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_d
   p.tiles_x = ceil_div(in->w, DW_TW);
   p.w_floats = w_floats;
   p.tile_floats = (int)tile_floats;
-  static const bool no_tma = getenv("LFSR_DW_NO_TMA") != nullptr;
+  static const bool no_tma = dbg_env("LFSR_DW_NO_TMA") != nullptr;
   DwEncodeFn encode = no_tma ? nullptr : dw_get_encode();
   p.use_tma = encode != nullptr;
   for (int i = 0; i < nbr && p.use_tma; ++i) {
@@ -446,12 +446,11 @@ static int dw_launch(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_d
       p.use_tma = 0;
   }
   const size_t smem = (tile_floats + (size_t)w_floats) * sizeof(float) + 128;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(dw_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 4096);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 4096);
-    if (e != cudaSuccess) { set_error("lfsr_dwconv_multi: %s", cudaGetErrorString(e)); return LFSR_ERR_CUDA; }
-    smem_set = 200 * 1024 + 4096;
+  static DevOnce once;
+  if (smem > 48 * 1024 && once.need()) {
+    if (opt_in_smem(dw_tile_kernel<false>, 200 * 1024 + 4096, "lfsr_dwconv_multi") ||
+        opt_in_smem(dw_tile_kernel<true>, 200 * 1024 + 4096, "lfsr_dwconv_multi")) return LFSR_ERR_CUDA;
+    once.done();
   }
   dim3 grid(p.tiles_x * ceil_div(in->h, DW_TH), items, in->n);
   if (p.share) dw_tile_kernel<true><<<grid, 256, smem, st>>>(p);

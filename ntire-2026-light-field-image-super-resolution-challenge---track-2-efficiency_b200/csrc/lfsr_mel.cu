@@ -299,10 +299,10 @@ extern "C" int lfsr_conv2d_small_cout(const lfsr_tensor* in, const float* w_pack
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_SMALL(CO)                                                                                         \
   do {                                                                                                           \
-    static bool attr_done = false;                                                                               \
-    if (!attr_done) {                                                                                            \
-      cudaFuncSetAttribute(conv_small_cout_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); \
-      attr_done = true;                                                                                          \
+    static DevOnce once;                                                                                         \
+    if (once.need()) {                                                                                           \
+      if (opt_in_smem(conv_small_cout_kernel<CO>, 110 * 1024, "lfsr_conv2d_small_cout")) return LFSR_ERR_CUDA;   \
+      once.done();                                                                                               \
     }                                                                                                            \
     conv_small_cout_kernel<CO><<<blocks, 256, smem, st>>>(a, cs);                                                \
   } while (0)
@@ -331,8 +331,11 @@ extern "C" int lfsr_mel_epi_branch(const lfsr_tensor* in, const float* w_packed,
   const int halo = klen / 2 > dil ? klen / 2 : dil;
   const size_t smem = ((size_t)(2 * klen + 9 + 6 * EC) * EP_CS + (size_t)(EP_W + 2 * halo) * (EP_H + 2 * halo) * EP_CS) * sizeof(float);
   LFSR_REQUIRE(smem <= 200 * 1024, "lfsr_mel_epi_branch: kernel length / dilation too large for the staged tile");
-  static bool attr_done = false;
-  if (!attr_done) { cudaFuncSetAttribute(mel_epi_branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; }
+  static DevOnce once;
+  if (once.need()) {
+    if (opt_in_smem(mel_epi_branch_kernel, 200 * 1024, "lfsr_mel_epi_branch")) return LFSR_ERR_CUDA;
+    once.done();
+  }
   mel_epi_branch_kernel<<<in->n * a.tiles_x * a.tiles_y, 256, smem, (cudaStream_t)stream>>>(a);
   return check_launch("mel_epi_branch_kernel");
 }

@@ -706,13 +706,13 @@ extern "C" int lfsr_epi_attention(const float* qk, const float* v, float* out, c
   LFSR_REQUIRE(L <= 192, "lfsr_epi_attention: sequence length %d > 192", L);
   LFSR_REQUIRE(((uintptr_t)qk % 16 == 0) && ((uintptr_t)v % 16 == 0) && ((uintptr_t)out % 16 == 0),
                "lfsr_epi_attention: pointers must be 16-byte aligned");
-  static const bool no_att5 = getenv("LFSR_ATT_PER_QUERY") != nullptr;
+  static const bool no_att5 = dbg_env("LFSR_ATT_PER_QUERY") != nullptr;
   if (!no_att5 && d->A == ATT_NQ && d->S <= 32) {       // EPIT's 5 x 5 light fields with 32-pixel patches
-    static bool attr_done = false;
+    static DevOnce once;
     const size_t smem5 = (size_t)ATT_HPC * 2 * L * ATT_LD * sizeof(float);
-    if (!attr_done) {
-      cudaFuncSetAttribute(epi_attention5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-      attr_done = true;
+    if (once.need()) {
+      if (opt_in_smem(epi_attention5_kernel, 110 * 1024, "lfsr_epi_attention")) return LFSR_ERR_CUDA;
+      once.done();
     }
     dim3 grid5(d->nb * d->np * d->nq, ceil_div(d->heads, ATT_HPC));
     epi_attention5_kernel<<<grid5, 32 * ATT_HPC, smem5, (cudaStream_t)stream>>>(qk, v, out, *d);
@@ -726,8 +726,14 @@ extern "C" int lfsr_epi_attention(const float* qk, const float* v, float* out, c
 
 extern "C" int lfsr_metric_sums(const float* label, const float* out, int ang, int h, int w, double* acc,
                                 void* stream) {
+  return lfsr_metric_sums_batched(label, out, 1, ang, h, w, acc, stream);
+}
+
+extern "C" int lfsr_metric_sums_batched(const float* label, const float* out, int n, int ang, int h, int w, double* acc,
+                                        void* stream) {
   LFSR_REQUIRE(label && out && acc, "lfsr_metric_sums: null pointer");
   LFSR_REQUIRE(ang > 0 && h >= 11 && w >= 11, "lfsr_metric_sums: views must be at least 11x11 (skimage win_size)");
+  LFSR_REQUIRE(n > 0, "lfsr_metric_sums: empty batch");
   // scipy.ndimage._gaussian_kernel1d(sigma=1.5, order=0, radius=5): float64 weights, cast to fp32
   Gauss11 gw;
   {
@@ -736,7 +742,9 @@ extern "C" int lfsr_metric_sums(const float* label, const float* out, int ang, i
     for (int i = 0; i < 11; ++i) gw.g[i] = (float)(g[i] / s);
   }
   const int tiles_x = ceil_div(w, MT_W), tiles_y = ceil_div(h, MT_H);
-  metric_kernel<<<ang * ang * tiles_x * tiles_y, 256, 0, (cudaStream_t)stream>>>(label, out, ang, h, w, acc, tiles_x,
-                                                                                 tiles_y, gw);
+  // n mosaics stacked along y are one mosaic with n * ang view rows: view index = (img * ang + a1) * ang + a2
+  const long long blocks = (long long)n * ang * ang * tiles_x * tiles_y;
+  LFSR_REQUIRE(blocks < 0x7fffffffLL, "lfsr_metric_sums: too many tiles");
+  metric_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(label, out, ang, h, w, acc, tiles_x, tiles_y, gw);
   return check_launch("metric_kernel");
 }

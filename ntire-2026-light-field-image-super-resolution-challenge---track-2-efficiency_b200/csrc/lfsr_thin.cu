@@ -312,14 +312,14 @@ extern "C" int lfsr_conv2d_thin(const lfsr_tensor* in, const float* w_packed, co
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_THIN(CIN, PPT)                                                                                       \
   do {                                                                                                              \
-    static bool attr_done = false;                                                                                  \
-    if (!attr_done) {                                                                                               \
-      cudaFuncSetAttribute(conv_thin_kernel<CIN, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);    \
-      attr_done = true;                                                                                             \
+    static DevOnce once;                                                                                            \
+    if (once.need()) {                                                                                              \
+      if (opt_in_smem(conv_thin_kernel<CIN, PPT>, 110 * 1024, "lfsr_conv2d_thin")) return LFSR_ERR_CUDA;            \
+      once.done();                                                                                                  \
     }                                                                                                               \
     conv_thin_kernel<CIN, PPT><<<blocks, 512 / PPT, smem, st>>>(a);                                                 \
   } while (0)
-  static const int ppt = getenv("LFSR_THIN_PPT") ? atoi(getenv("LFSR_THIN_PPT")) : 2;   // measured: 0.261 ms (2) vs 0.273 ms (4) per layer
+  static const int ppt = dbg_env("LFSR_THIN_PPT") ? atoi(dbg_env("LFSR_THIN_PPT")) : 2;   // measured: 0.261 ms (2) vs 0.273 ms (4) per layer
   if (ppt == 2) {
     switch (in->c) {
       case 16: LAUNCH_THIN(16, 2); break;

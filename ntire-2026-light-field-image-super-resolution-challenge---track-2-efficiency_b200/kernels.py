@@ -62,6 +62,21 @@ class PackedConv:
     pad: Tuple[int, int] = (0, 0)
     w_tc: Optional[torch.Tensor] = None
     tc_perm_r2: int = 0   # >0: w_tc rows were permuted to factor-major for a fused nn.PixelShuffle of r2 sub-pixels
+    #: per-image gated copies of w_tc (lfsr_scale_pack_tc), keyed by batch size. Owned by the packing, so the scratch lives
+    #: exactly as long as the weights it was sized for (a cache on the backend keyed by data_ptr could match a stale entry
+    #: after the allocator reuses the address)
+    gated: Optional[dict] = None
+
+    def gated_scratch(self, nimg: int, device) -> torch.Tensor:
+        if self.gated is None:
+            self.gated = {}
+        t = self.gated.get(nimg)
+        if t is None:
+            t = torch.empty((nimg, self.w_tc.numel()), dtype=torch.float32, device=device)
+            self.gated[nimg] = t
+        if tuple(t.shape) != (nimg, self.w_tc.numel()) or t.device != self.w_tc.device:
+            raise N.LfsrError("gated weight scratch does not match its packing (stale cache)")
+        return t
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride=(1, 1), dil=(1, 1), pad=(0, 0),
@@ -104,13 +119,17 @@ class CudaOps:
         self.lib = N.load()
         self.use_tc = use_tc
         self.use_thin = True      # FFMA2 kernel for the 18 -> 20 channel layers (tests switch it off to reach the TC path)
-        self._gated = {}          # per-image gated weight scratch, keyed by (packed weights, batch)
 
     # -- helpers ---------------------------------------------------------------------------
     @staticmethod
     def _stream(t: torch.Tensor) -> int:
+        """stream the launch goes to. Kernels launch on the thread's CURRENT device, so a tensor that lives on another GPU
+        is refused here (the callers - LFNetBase.forward, lfutils, scene - enter torch.cuda.device(x.device) first)."""
         if not t.is_cuda:
             raise N.LfsrError("lfsr_b200 kernels need CUDA tensors; there is no CPU fallback")
+        if t.device.index != torch.cuda.current_device():
+            raise N.LfsrError(f"tensor on {t.device} but the current CUDA device is {torch.cuda.current_device()}: "
+                              "wrap the call in torch.cuda.device(tensor.device)")
         return torch.cuda.current_stream(t.device).cuda_stream
 
     @staticmethod
@@ -176,11 +195,7 @@ class CudaOps:
         if self.use_tc and pc.w_tc is not None and in_scale is not None:
             # per-sample gate folded into per-image weight sets (a few KB each), then the tensor-core conv
             nimg = x.shape[0]
-            key = (pc.w_tc.data_ptr(), nimg)
-            scratch = self._gated.get(key)
-            if scratch is None:
-                scratch = torch.empty((nimg, pc.w_tc.numel()), dtype=torch.float32, device=x.device)
-                self._gated[key] = scratch
+            scratch = pc.gated_scratch(nimg, x.device)
             N.check(self.lib.lfsr_scale_pack_tc(pc.w_tc.data_ptr(), in_scale.data_ptr(), d.in_scale_ld, scratch.data_ptr(),
                                                 nimg, pc.kh, pc.kw, pc.cin, pc.cout, st), "lfsr_scale_pack_tc")
             d.w_batch_stride = pc.w_tc.numel()
@@ -265,6 +280,11 @@ class CudaOps:
     def metric_sums(self, label, out, ang, h, w, acc):
         N.check(self.lib.lfsr_metric_sums(label.data_ptr(), out.data_ptr(), ang, h, w, acc.data_ptr(),
                                           self._stream(label)), "lfsr_metric_sums")
+
+    def metric_sums_batched(self, label, out, n, ang, h, w, acc):
+        """label/out [n,1,A*h,A*w] contiguous; acc [n*A*A*2] float64, zeroed by the caller"""
+        N.check(self.lib.lfsr_metric_sums_batched(label.data_ptr(), out.data_ptr(), n, ang, h, w, acc.data_ptr(),
+                                                  self._stream(label)), "lfsr_metric_sums_batched")
 
 
 _default_ops = None

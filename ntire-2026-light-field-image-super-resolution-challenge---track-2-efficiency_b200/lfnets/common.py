@@ -121,13 +121,22 @@ class LFNetBase(nn.Module):
         self._arena: Dict[tuple, torch.Tensor] = {}
         self._graphs: Dict[tuple, tuple] = {}
         self.graph_launches = 0       # kernels launched through graph replays (the C-side counter only sees direct launches)
+        # reference checkpoints arrive through load_state_dict (test.py:40-55): repack on the next forward
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
+
+    def invalidate(self) -> None:
+        """Drop the packed weights and captured graphs; the next forward repacks. Called automatically after
+        load_state_dict / .to() / set_backend and whenever a parameter's (data_ptr, _version) changes. Edits made through
+        `p.data` (e.g. `m.weight.data.normal_()`) bypass torch's version counter: call this after such edits."""
+        self._packed = None
+        self._packed_key = None
+        self._graphs = {}
 
     # -- backend ---------------------------------------------------------------------------------
     def set_backend(self, ops) -> None:
         """Tests inject tests/opref.RefOps here; the product default is kernels.CudaOps."""
         self._ops = ops
-        self._packed = None
-        self._graphs = {}
+        self.invalidate()
 
     def _backend(self, x: torch.Tensor):
         if self._ops is not None:
@@ -190,6 +199,9 @@ class LFNetBase(nn.Module):
         if H % A or W % A:
             raise ValueError(f"mosaic {H}x{W} is not divisible by angRes={A}")
         ops = self._backend(x)
+        if x.is_cuda and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):          # kernels launch on the thread's current device
+                return self.forward(x, info)
         pk = self._get_packed(x.device, ops)
         x = x.contiguous()
         if (USE_CUDA_GRAPH and self._ops is None and x.is_cuda and not torch.cuda.is_current_stream_capturing()):
@@ -199,7 +211,19 @@ class LFNetBase(nn.Module):
             self._run(ops, pk, x, out)
         return out
 
-    def _forward_graphed(self, ops, pk, x: torch.Tensor) -> torch.Tensor:
+    def forward_static(self, x: torch.Tensor) -> torch.Tensor:
+        """forward() for callers that consume the result before the next forward of the same shape (scene.SceneRunner feeds
+        it straight to LFintegrate): returns the graph's own static output buffer instead of a clone."""
+        ops = self._backend(x)
+        if not (USE_CUDA_GRAPH and self._ops is None and x.is_cuda) or torch.cuda.is_current_stream_capturing():
+            return self.forward(x)
+        if x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):
+                return self.forward_static(x)
+        pk = self._get_packed(x.device, ops)
+        return self._forward_graphed(ops, pk, x.contiguous(), clone=False)
+
+    def _forward_graphed(self, ops, pk, x: torch.Tensor, clone: bool = True) -> torch.Tensor:
         """One CUDA graph per input shape: a forward is ~100 launches of a few microseconds of host work each, which at the
         reference's minibatch sizes (train.py:303-314 feeds ONE patch per call) costs more than the kernels themselves.
         The workspace arena makes every pointer of a forward stable, so the launch sequence is captured once and replayed
@@ -225,7 +249,7 @@ class LFNetBase(nn.Module):
         sx.copy_(x)
         g.replay()
         self.graph_launches += n
-        return so.clone()
+        return so.clone() if clone else so
 
 
 class L1Loss(nn.Module):

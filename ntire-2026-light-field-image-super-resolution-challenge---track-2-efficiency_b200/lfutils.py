@@ -90,9 +90,14 @@ def metric_views(label_sai: torch.Tensor, out_sai: torch.Tensor, angRes: int, op
     """per-view PSNR / SSIM of two SAI mosaics [(a1 h), (a2 w)] -> float32 arrays [A, A]."""
     dev = _device_for(out_sai if out_sai.is_cuda else label_sai, ops)
     ops = ops or K.default_ops()
+    if label_sai.dim() != 2 or tuple(label_sai.shape) != tuple(out_sai.shape):
+        # the reference crops SR to the HR size before this point (train.py:316) and skimage raises on a mismatch
+        raise ValueError(f"cal_metrics: label {tuple(label_sai.shape)} and output {tuple(out_sai.shape)} mosaics differ")
     la = label_sai.to(device=dev, dtype=torch.float32).contiguous()
     ou = out_sai.to(device=dev, dtype=torch.float32).contiguous()
     H, W = la.shape
+    if H % angRes or W % angRes:
+        raise ValueError(f"cal_metrics: mosaic {H}x{W} is not divisible by angRes={angRes}")
     h, w = H // angRes, W // angRes
     acc = torch.zeros(2 * angRes * angRes, dtype=torch.float64, device=dev)
     ops.metric_sums(la, ou, angRes, h, w, acc)

@@ -4,6 +4,7 @@ usage: python profiles/probe_mma_rate2.py"""
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("LFSR_PROBE_LIB", "1")   # liblfsr_probe.so: probe kernels + debug hooks (not in the product library)
 import lfsr_b200
 lib = lfsr_b200._native.load()
 fn = lib.lfsr_debug_mma_rate2

@@ -5,6 +5,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
 os.environ["LFSR_TC_DBG_PTR"] = hex(dbg.data_ptr())
+os.environ.setdefault("LFSR_PROBE_LIB", "1")   # liblfsr_probe.so: probe kernels + debug hooks (not in the product library)
 import lfsr_b200
 from lfsr_b200 import kernels as K
 ops = K.CudaOps()

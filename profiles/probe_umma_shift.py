@@ -2,6 +2,7 @@
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("LFSR_PROBE_LIB", "1")   # liblfsr_probe.so: probe kernels + debug hooks (not in the product library)
 import lfsr_b200
 lib = lfsr_b200._native.load()
 fn = lib.lfsr_debug_umma_shift

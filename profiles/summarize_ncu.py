@@ -60,8 +60,37 @@ def raw(path, command, kernel, variant):
     print(json.dumps(out, indent=1))
 
 
+def zoo(path, command):
+    """every profiled launch of `ncu -i X.ncu-rep --page raw --csv`: the LAST instance of each kernel name (the launch
+    after its warm-up), selected metrics + derived DRAM GB/s."""
+    rs = rows_of(path)
+    units = rs[0]
+    last = {}
+    for r in rs[1:]:
+        last[short(r["Kernel Name"]) + " | grid " + r.get("launch__grid_size", "?") + " smem " +
+             r.get("launch__shared_mem_per_block_dynamic", "?")] = r
+    out = {"command": command, "kernels": {}}
+    for name, r in last.items():
+        ent = {}
+        for k in KEEP:
+            if k in r and r[k] != "":
+                ent[k] = {"value": r[k], "unit": units[k]}
+        try:
+            mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            tmul = {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}
+            byt = sum(float(r[k].replace(",", "")) * mult[units[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            sec = float(r["gpu__time_duration.sum"].replace(",", "")) * tmul[units["gpu__time_duration.sum"]]
+            ent["derived_dram_gbs"] = byt / sec / 1e9
+        except (KeyError, ValueError):
+            pass
+        out["kernels"][name] = ent
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "zoo":
+        zoo(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), sys.argv[5])
     else:
         raw(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])

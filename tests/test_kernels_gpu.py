@@ -320,6 +320,63 @@ def test_metrics_vs_oracle_and_golden(ops, golden_dir):
     assert np.abs(pv - po).max() <= 1e-3 and np.abs(sv - so).max() <= 1e-5
 
 
+def _sinusoid_lf(A, hv, seed):
+    """HR light field [(a1 hv), (a2 hv)] in [0,1]: a sum of seeded 2-D sinusoids with a per-view disparity shift
+    (structured content so that PSNR lands in the 20-35 dB band instead of noise-vs-noise)."""
+    rs = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:hv, 0:hv].astype(np.float64)
+    out = np.zeros((A, hv, A, hv))
+    comps = [(rs.uniform(0.01, 0.7), rs.uniform(0.01, 0.7), rs.uniform(0, 6.28), rs.uniform(0.3, 1.0)) for _ in range(12)]
+    for u in range(A):
+        for v in range(A):
+            img = np.zeros((hv, hv))
+            for fy, fx, ph, amp in comps:
+                img += amp * np.sin(fy * (yy + 0.7 * u) + fx * (xx + 0.7 * v) + ph)
+            out[u, :, v, :] = img
+    out = (out - out.min()) / (out.max() - out.min())
+    return out.reshape(A * hv, A * hv).astype(np.float32)
+
+
+@pytest.mark.parametrize("hv", [128, 256, 512])
+def test_metrics_realistic_band_large_views(ops, hv):
+    """row Q at the sizes and PSNR band of BASELINE config 5: HR views of 128^2..512^2 (x4 of 32^2..128^2 LR views), LR made
+    with the reference's own imresize (x0.25 per view), 'SR' = imresize x4 of it -> 20-35 dB. GPU kernel vs the oracle."""
+    A = 5
+    hr = _sinusoid_lf(A, hv, seed=hv)
+    sr = np.empty_like(hr)
+    for u in range(A):
+        for v in range(A):
+            view = hr[u * hv:(u + 1) * hv, v * hv:(v + 1) * hv].astype(np.float64)
+            lo = lf_oracle.imresize(view, scalar_scale=0.25)
+            sr[u * hv:(u + 1) * hv, v * hv:(v + 1) * hv] = np.clip(lf_oracle.imresize(lo, scalar_scale=4.0), 0, 1)
+    pv, sv = lfsr_b200.lfutils.metric_views(torch.from_numpy(hr).to(DEV), torch.from_numpy(sr).to(DEV), A, ops)
+    pm, sm, po, so = lf_oracle.cal_metrics(hr, sr, A)
+    print(f"metrics hv={hv}: oracle PSNR {pm:.3f} dB SSIM {sm:.5f}; max |dPSNR| {np.abs(pv - po).max():.2e} "
+          f"max |dSSIM| {np.abs(sv - so).max():.2e}")
+    assert 20.0 <= pm <= 35.0, pm
+    assert np.abs(pv - po).max() <= 1e-3 and np.abs(sv - so).max() <= 1e-5
+
+
+def test_metric_sums_batched_equals_per_mosaic(ops):
+    A, hv, n = 5, 48, 3
+    rs = np.random.RandomState(3)
+    la = torch.from_numpy(rs.random_sample((n, 1, A * hv, A * hv)).astype(np.float32)).to(DEV)
+    ou = (la + 0.03 * torch.randn_like(la)).clamp_(0, 1)
+    acc = torch.zeros(n * 2 * A * A, dtype=torch.float64, device=DEV)
+    ops.metric_sums_batched(la, ou, n, A, hv, hv, acc)
+    for i in range(n):
+        one = torch.zeros(2 * A * A, dtype=torch.float64, device=DEV)
+        ops.metric_sums(la[i, 0], ou[i, 0], A, hv, hv, one)
+        got = acc.view(n, -1)[i]
+        assert torch.allclose(got, one, rtol=1e-12, atol=0)
+
+
+def test_metric_shape_mismatch_raises(ops):
+    la = torch.rand(5 * 24, 5 * 24, device=DEV)
+    with pytest.raises(ValueError):
+        lfsr_b200.lfutils.metric_views(la, la[:-5], 5, ops)
+
+
 # ---- tcgen05 / TMEM / TMA TF32 implicit GEMM -----------------------------------------------------
 TC_CASES = [
     dict(cin=54, cout=216, k=(3, 3), pad=(1, 1), act=2, shuffle=(2, 2, 0), hw=(40, 40)),
@@ -409,7 +466,7 @@ def _run_tc_case(ref, case):
     scale = max(1.0, b.abs().max().item())
     print(f"tc conv {case}: max err {err:.3e} (ref max {scale:.3f})")
     assert lib.lfsr_launch_count() == l0 + 1
-    assert err <= 2e-3 * scale, f"max err {err}"
+    assert err <= 1e-3 * scale, f"max err {err}"        # the end-to-end budget (north_star: 1e-3 on [0,1] outputs)
 
 
 def test_mel_epi_branch(ops, ref):

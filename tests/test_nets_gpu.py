@@ -75,6 +75,73 @@ def test_forward_p32_vs_oracle(name, scale, golden_dir):
     assert dpsnr <= 0.01
 
 
+@pytest.mark.parametrize("name,scale", CASES)
+def test_forward_batch64_default_init_vs_oracle(name, scale):
+    """bench.py times seeded constructor-default weights at batch 64: the same weights, the same batch, against the oracle
+    (first, middle and last patch of the batch; 1e-3 / 0.01 dB as everywhere)."""
+    if not _have(name):
+        pytest.skip(f"{name} not built yet")
+    torch.manual_seed(1234)
+    net = lfsr_b200.load_net(name, 5, scale).eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.to(DEV)
+    B = 64
+    x = weights.synthetic_patches(B, 5, 32, seed=21)
+    y = net(x.to(DEV), [5, 5]).cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+    worst, worst_dp = 0.0, 0.0
+    for i in (0, 31, 63):
+        with torch.no_grad():
+            y_or = onets.forward(name, x[i:i + 1], sd, 5, scale)
+        worst = max(worst, float((y[i:i + 1] - y_or).abs().max()))
+        hr = np.random.RandomState(5).random_sample(y_or.shape[-2:]).astype(np.float32)
+        worst_dp = max(worst_dp, abs(lf_oracle.psnr_view(hr, y[i, 0].numpy()) - lf_oracle.psnr_view(hr, y_or[0, 0].numpy())))
+    REPORT[f"{name}_x{scale}_b64_default_init"] = dict(maxabs_vs_oracle=worst, dpsnr=worst_dp,
+                                                        out_absmax=float(y.abs().max()))
+    _dump()
+    assert worst <= TOL and worst_dp <= 0.01, (worst, worst_dp)
+
+
+def test_invalidate_after_data_edit():
+    """edits through `.data` bypass the version counter; invalidate() (also run by load_state_dict) repacks."""
+    net, sd = _net("MyEfficientLFNet", 4)
+    x = weights.synthetic_patches(1, 5, 8, seed=3).to(DEV)
+    y0 = net(x).clone()
+    for p in net.parameters():
+        p.data.mul_(0.5)
+    net.invalidate()
+    y1 = net(x).clone()
+    assert not torch.equal(y0, y1)
+    net.load_state_dict(sd)                 # post-hook invalidates
+    assert torch.equal(net(x), y0)
+
+
+def test_scene_runner_pipeline_matches_sync(golden_dir):
+    """submit()/result() with host tensors (pinned and pageable), two scenes in flight, equals the synchronous driver."""
+    net, _ = _net("MyEfficientLFNet", 4)
+    A, s, h0, w0 = 5, 4, 40, 48
+    r = lfsr_b200.scene.SceneRunner(net, A, s, h0, w0, minibatch=6, device=DEV, world=1, rank=0, depth=2)
+    scenes = []
+    for k in range(3):
+        rs = np.random.RandomState(40 + k)
+        lr = torch.from_numpy(rs.random_sample((A * h0, A * w0)).astype(np.float32))
+        hr = torch.from_numpy(rs.random_sample((A * h0 * s, A * w0 * s)).astype(np.float32))
+        scenes.append((lr.pin_memory() if k % 2 == 0 else lr, hr))
+    want = [lfsr_b200.scene.test_scene(net, lr.to(DEV), hr.to(DEV), A, s, minibatch=6) for lr, hr in scenes]
+    want = [(p, q, sr.cpu().clone()) for p, q, sr in want]
+    tickets, got = [], []
+    for lr, hr in scenes:
+        tickets.append(r.submit(lr, hr))
+        if len(tickets) == 2:
+            p, q, sr = r.result(tickets.pop(0))
+            got.append((p, q, sr.clone()))
+    while tickets:
+        p, q, sr = r.result(tickets.pop(0))
+        got.append((p, q, sr.clone()))
+    for (p0, q0, s0), (p1, q1, s1) in zip(want, got):
+        assert torch.equal(s0, s1) and abs(p0 - p1) < 1e-9 and abs(q0 - q1) < 1e-9
+
+
 def test_batch_slices_and_repeatability():
     net, _ = _net("MyEfficientLFNet", 4)
     x = weights.synthetic_patches(4, 5, 8, seed=3).to(DEV)

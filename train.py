@@ -28,8 +28,8 @@ def test(test_loader, device, net, args, save_dir=None):
     net.eval()
     for Lr_SAI_y, Hr_SAI_y, Sr_SAI_cbcr, data_info, LF_name in test_loader:
         ang = int(data_info[0][0].item()) if torch.is_tensor(data_info[0]) else int(data_info[0])
-        lr = Lr_SAI_y.squeeze().to(device, non_blocking=True)
-        hr = Hr_SAI_y.squeeze().to(device, non_blocking=True)
+        # host tensors go in as they are: the scene driver stages them through pinned buffers on its copy stream
+        lr, hr = Lr_SAI_y.squeeze(), Hr_SAI_y.squeeze()
         with torch.no_grad():
             psnr, ssim, sr = _scene.test_scene(net, lr, hr, ang, args.scale_factor, args.patch_size_for_test,
                                                args.stride_for_test, getattr(args, "minibatch", 64))
