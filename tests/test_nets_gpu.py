@@ -127,8 +127,10 @@ def test_scene_runner_pipeline_matches_sync(golden_dir):
         lr = torch.from_numpy(rs.random_sample((A * h0, A * w0)).astype(np.float32))
         hr = torch.from_numpy(rs.random_sample((A * h0 * s, A * w0 * s)).astype(np.float32))
         scenes.append((lr.pin_memory() if k % 2 == 0 else lr, hr))
-    want = [lfsr_b200.scene.test_scene(net, lr.to(DEV), hr.to(DEV), A, s, minibatch=6) for lr, hr in scenes]
-    want = [(p, q, sr.cpu().clone()) for p, q, sr in want]
+    want = []
+    for lr, hr in scenes:          # (the returned mosaic is the runner's slot buffer: copy it before the slot is reused)
+        p, q, sr = lfsr_b200.scene.test_scene(net, lr.to(DEV), hr.to(DEV), A, s, minibatch=6)
+        want.append((p, q, sr.cpu().clone()))
     tickets, got = [], []
     for lr, hr in scenes:
         tickets.append(r.submit(lr, hr))
