@@ -231,6 +231,30 @@ typedef struct {
 int lfsr_epi_attention(const float* qk, const float* v, float* out, const lfsr_epi_attn_desc* d,
                        void* stream);
 
+/* ---- EPIT BasicTrans, fused (EPIT.py:74-128: linear_in -> LayerNorm -> MultiheadAttention(q = k = norm(x), v = x, 8 heads,
+ * additive band mask of :93-108) + x -> LayerNorm -> Linear/ReLU/Linear + x -> linear_out) ----------------------------------
+ * ONE tcgen05/TMEM kernel: a CTA owns a run of query positions of one EPI sequence plus the +-half_window positions they
+ * attend (all A angular rows), <= 128 token rows; every intermediate stays in TMEM / shared memory, fp16 operands with fp32
+ * accumulation (linear_in: TF32), weights streamed by TMA. Sequences and tokens are addressed exactly like
+ * lfsr_epi_attention: token(seq, a, s) = seq_base + a*stride_a + s*stride_s, seq_base = b*stride_b + p*stride_p + q*stride_q,
+ * in pixels of the [n,h,w,64] NHWC tensors x (in) and y (out, same geometry, must not alias x). E = 128, C = 64, 8 heads. */
+typedef struct {
+  int32_t A, S, half_window, heads, E, C;
+  int32_t nb, np, nq;
+  int64_t stride_a, stride_s, stride_b, stride_p, stride_q;
+  float eps1, eps2;                                           /* of the two LayerNorms (host values) */
+  float ln1_g[128], ln1_b[128], ln2_g[128], ln2_b[128];       /* LayerNorm affine parameters (host values) */
+} lfsr_basictrans_desc;
+size_t lfsr_basictrans_packed_bytes(void);
+/* host weights in torch layout [out][in]: linear_in [128][64], attention.in_proj_weight [384][128], attention.out_proj
+ * [128][128], feed_forward.1 [256][128], feed_forward.4 [128][256], linear_out [64][128] -> packed_host (then copied to
+ * the device by the caller) */
+int lfsr_pack_basictrans(const float* w_in, const float* w_qkv, const float* w_o, const float* w_ff1, const float* w_ff2,
+                         const float* w_out, void* packed_host);
+int lfsr_basictrans_supported(const lfsr_tensor* x, const lfsr_tensor* y, const lfsr_basictrans_desc* d);
+int lfsr_epit_basictrans(const lfsr_tensor* x, const void* packed_dev, const lfsr_tensor* y, const lfsr_basictrans_desc* d,
+                         void* stream);
+
 /* ---- metrics (utils/utils.py:91-134) ------------------------------------------------------ */
 /* per-view sums for PSNR/SSIM on SAI mosaics label/out [A*h, A*w] (row stride = A*w):
  * acc[view] = { sum (a-b)^2 , sum SSIM map over the 5-px-cropped interior } as float64.

@@ -62,6 +62,17 @@ class EpiAttnDesc(C.Structure):
     ]
 
 
+class BasicTransDesc(C.Structure):
+    _fields_ = [
+        ("A", C.c_int32), ("S", C.c_int32), ("half_window", C.c_int32), ("heads", C.c_int32), ("E", C.c_int32), ("C", C.c_int32),
+        ("nb", C.c_int32), ("np", C.c_int32), ("nq", C.c_int32),
+        ("stride_a", C.c_int64), ("stride_s", C.c_int64), ("stride_b", C.c_int64), ("stride_p", C.c_int64),
+        ("stride_q", C.c_int64),
+        ("eps1", C.c_float), ("eps2", C.c_float),
+        ("ln1_g", C.c_float * 128), ("ln1_b", C.c_float * 128), ("ln2_g", C.c_float * 128), ("ln2_b", C.c_float * 128),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/lfsr.h one to one (tests check the export list)
 _P = C.c_void_p
 _I = C.c_int
@@ -98,6 +109,10 @@ SIGNATURES = {
     "lfsr_scale_add": (_I, [_TP, _TP, _TP, _TP, _P]),
     "lfsr_layernorm": (_I, [_TP, _P, _P, C.c_float, _TP, _P]),
     "lfsr_epi_attention": (_I, [_P, _P, _P, C.POINTER(EpiAttnDesc), _P]),
+    "lfsr_basictrans_packed_bytes": (C.c_size_t, []),
+    "lfsr_pack_basictrans": (_I, [_P, _P, _P, _P, _P, _P, _P]),
+    "lfsr_basictrans_supported": (_I, [_TP, _TP, C.POINTER(BasicTransDesc)]),
+    "lfsr_epit_basictrans": (_I, [_TP, _P, _TP, C.POINTER(BasicTransDesc), _P]),
     "lfsr_metric_sums": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "lfsr_metric_sums_batched": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
 }

@@ -1,0 +1,644 @@
+// EPIT's BasicTrans (EPIT.py:74-128, mask :93-108) as ONE tcgen05/TMEM kernel.
+//
+//   x [T, 64] --linear_in--> X [128] --LN--> N --(Wq, Wk)--> Q, K ;  V = X Wv^T  (v comes from the un-normed tokens, :117-122)
+//   per head (8 x 16): softmax(Q K^T / 4 + band mask) V ;  X2 = attn Wo^T + X ;  X3 = W2 relu(W1 LN(X2)) + X2 ;  y = X3 Wout^T
+//
+// Work item = HALF an EPI sequence. A sequence is L = A*S tokens (A angular x S spatial positions of one EPI line); the
+// additive mask of the reference (mask_field [2A, 11]) lets token (a, s) attend all A rows of the positions |s - s'| <= 5.
+// With the tokens ordered s-major (row = s*A + a) a tile that owns the query positions [qs0, qs1) needs only the
+// positions [qs0 - 5, qs1 + 5): for S = 32, A = 5 two tiles of 16 query positions load 21 positions = 105 token rows
+// each, which fits the 128 TMEM lanes / 128 MMA rows, so queries, keys and values of a tile are the same 105 rows and
+// nothing ever leaves the SM between linear_in and linear_out (HBM: 256 B in + 256 B out per token instead of ~13 KB
+// for the ten separate launches this replaces).
+//
+// GEMM plan per tile (M = 128 rows, accumulators in TMEM, fp32):
+//   R  [cols   0..127]  residual stream: X = x W_in^T (kind::tf32, A tile straight from TMA), then += O Wo^T, += F W2^T
+//   T1 [cols 128..255]  V^T = Wv X^T (weights as the A operand -> lanes = channels, so the epilogue writes K-major V^T rows
+//                       without a transpose), later O (8 heads x 16 columns), later y (64 columns)
+//   T2 [cols 256..511]  [Q | K], later the two ping-pong score tiles S (N = keys), later relu-input F (256 columns)
+// Every operand produced inside the kernel is written by the epilogue warps as fp16 (10-bit mantissa = TF32's precision,
+// fp32 accumulate) in the K-major SWIZZLE_128B layout the UMMA descriptors read; kind::f16 halves shared-memory bytes
+// and MMA time against tf32, which is what lets a whole tile live in 160 KB. The 304 KB of weights per tile stream
+// through a 4-slot TMA ring from L2.
+// Warps: 0..7 epilogue (two per TMEM lane quarter: they split columns / heads), 8 TMA producer, 9 MMA issuer.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <string.h>
+#include <mutex>
+#include "lfsr_common.cuh"
+#include "lfsr_ptx.cuh"
+
+namespace lfsr {
+namespace bt {
+using namespace lfsr::ptx;
+
+constexpr int kThreads = 320, kTmaWarp = 8, kMmaWarp = 9;
+constexpr int kE = 128, kC = 64, kHeads = 8, kHd = 16;
+constexpr int kRegion = 32768, kChunk = 16384, kSlot = 16384, kSlots = 4;
+constexpr int kMaxKeys = 112;             // token rows per tile (7 groups of 16 score columns kept in registers)
+constexpr int kBlocks = 19;                 // weight blocks (16 KB each) per tile, in consumption order
+constexpr int kSmemBytes = 5 * kRegion + kSlots * kSlot + 1024 /* LN exchange */ + 32 * 8 /* barriers */ + 16;
+// weight block indices
+constexpr int kWin = 0, kWv = 2, kWq = 4, kWk = 6, kWo = 8, kW1 = 10, kW2 = 14, kWout = 18;
+
+struct Params {
+  int A, S, w, SL, nrows, nkeys, nt, sq;
+  int nseq, npq, nq, total_tiles;
+  long long stride_a, stride_s, stride_b, stride_p, stride_q;      // in tokens (pixels)
+  float* y;
+  int ld_y;
+  float eps1, eps2, qscale;
+  float ln[4][kE];                       // gamma1, beta1, gamma2, beta2 (constant bank: uniform loads in the LN loops)
+};
+
+enum Bar {
+  X_FULL = 0, X_EMPTY, W_FULL, W_EMPTY = W_FULL + kSlots, R_FULL = W_EMPTY + kSlots, VT_FULL, QK_FULL, S_FULL, P_EMPTY = S_FULL + 2,
+  O_FULL = P_EMPTY + 2, F_FULL, Y_FULL = F_FULL + 2, XN_READY, QKV_READY, P_FULL, O_READY = P_FULL + 2, N2_READY, F_READY,
+  X3_READY = F_READY + 2, NUM_BARS
+};
+static_assert(NUM_BARS <= 32, "barrier block");
+
+// 64 floats -> one 128-byte K-major SWIZZLE_128B row (64 fp16) of a chunk that starts at a 1024-byte boundary
+__device__ __forceinline__ void store_row_f16(uint32_t chunk, int row, const float* v) {
+  const uint32_t rb = chunk + (uint32_t)row * 128u;
+  const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    st_shared_v4(rb + (((uint32_t)j ^ sw) << 4), pack_f16x2(v[8 * j], v[8 * j + 1]), pack_f16x2(v[8 * j + 2], v[8 * j + 3]),
+                 pack_f16x2(v[8 * j + 4], v[8 * j + 5]), pack_f16x2(v[8 * j + 6], v[8 * j + 7]));
+}
+__device__ __forceinline__ void store_row_zero(uint32_t chunk, int row) {
+  const uint32_t rb = chunk + (uint32_t)row * 128u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) st_shared_v4(rb + ((uint32_t)j << 4), 0u, 0u, 0u, 0u);
+}
+// 16 floats -> units (2*g4, 2*g4 + 1) of the row (g4 = 16-column group inside the 64-column chunk)
+__device__ __forceinline__ void store_grp_f16(uint32_t chunk, int row, int g4, const float* v) {
+  const uint32_t rb = chunk + (uint32_t)row * 128u;
+  const uint32_t sw = (uint32_t)(row & 7);
+  st_shared_v4(rb + ((((uint32_t)(2 * g4)) ^ sw) << 4), pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+               pack_f16x2(v[6], v[7]));
+  st_shared_v4(rb + ((((uint32_t)(2 * g4 + 1)) ^ sw) << 4), pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]),
+               pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
+}
+__device__ __forceinline__ void store_grp_zero(uint32_t chunk, int row, int g4) {
+  const uint32_t rb = chunk + (uint32_t)row * 128u;
+  const uint32_t sw = (uint32_t)(row & 7);
+  st_shared_v4(rb + ((((uint32_t)(2 * g4)) ^ sw) << 4), 0u, 0u, 0u, 0u);
+  st_shared_v4(rb + ((((uint32_t)(2 * g4 + 1)) ^ sw) << 4), 0u, 0u, 0u, 0u);
+}
+
+// four K-steps (one 128-byte chunk row) of a kind::f16 / kind::tf32 GEMM slice
+template <bool TF32, bool FIRST>
+__device__ __forceinline__ void mma_chunk(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc) {
+  if (TF32) {
+    umma_tf32<FIRST ? 0 : 1>(d, a, b, idesc);
+    umma_tf32<1>(d, a + 2, b + 2, idesc); umma_tf32<1>(d, a + 4, b + 4, idesc); umma_tf32<1>(d, a + 6, b + 6, idesc);
+  } else {
+    umma_f16<FIRST ? 0 : 1>(d, a, b, idesc);
+    umma_f16<1>(d, a + 2, b + 2, idesc); umma_f16<1>(d, a + 4, b + 4, idesc); umma_f16<1>(d, a + 6, b + 6, idesc);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* RA = smem;                 // x (fp32, TMA) / X fp16 / P of odd heads
+  uint8_t* RB = smem + kRegion;       // N / P of even heads / N2 / X3
+  uint8_t* RC = smem + 2 * kRegion;   // Q / O
+  uint8_t* RD = smem + 3 * kRegion;   // K / F chunks 0, 1
+  uint8_t* RE = smem + 4 * kRegion;   // V^T / F chunks 2, 3
+  uint8_t* ring = smem + 5 * kRegion;
+  float* lnx = reinterpret_cast<float*>(ring + kSlots * kSlot);       // [2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lnx + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NUM_BARS; ++i) {
+      uint32_t cnt = 1;
+      if (i == XN_READY || i == QKV_READY || i == O_READY || i == N2_READY || i == X3_READY) cnt = 8;
+      if (i == P_FULL || i == P_FULL + 1 || i == F_READY || i == F_READY + 1) cnt = 4;
+      mbar_init(bars + i, cnt);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tR = tmem, tT1 = tmem + 128, tT2 = tmem + 256;
+  const int n_my = ((int)p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+
+  if (warp == kTmaWarp) {
+    // ================= TMA producer: x tiles + the weight ring =================
+    if (elect_one()) {
+      uint32_t wcnt = 0;
+      const uint32_t x_bytes = (uint32_t)p.nrows * 128u * 2u;
+      auto load_x = [&](int tile) {
+        const int seq = tile / p.nt, t = tile - seq * p.nt;
+        const int b = seq / p.npq, pq = seq - b * p.npq;
+        int ls0 = t * p.sq - p.w;
+        if (ls0 < 0) ls0 = 0;
+        if (ls0 > p.S - p.SL) ls0 = p.S - p.SL;
+        mbar_expect_tx(bars + X_FULL, x_bytes);
+        tma_load_5d(RA, &tmX, bars + X_FULL, 0, 0, ls0, pq, b);
+        tma_load_5d(RA + kChunk, &tmX, bars + X_FULL, 32, 0, ls0, pq, b);
+      };
+      auto load_w = [&](int blk) {
+        const uint32_t slot = wcnt % kSlots, use = wcnt / kSlots;
+        mbar_wait(bars + W_EMPTY + slot, (use & 1u) ^ 1u);
+        mbar_expect_tx(bars + W_FULL + slot, kSlot);
+        tma_load_2d(ring + slot * kSlot, &tmW, bars + W_FULL + slot, 0, blk * 128);
+        ++wcnt;
+      };
+      if (n_my > 0) load_x((int)blockIdx.x);
+      for (int it = 0; it < n_my; ++it) {
+        for (int blk = 0; blk < 12; ++blk) load_w(blk);
+        if (it + 1 < n_my) {              // region RA is free once the last P.V MMA of this tile has retired
+          mbar_wait(bars + X_EMPTY, (uint32_t)it & 1u);
+          load_x((int)blockIdx.x + (it + 1) * (int)gridDim.x);
+        }
+        for (int blk = 12; blk < kBlocks; ++blk) load_w(blk);
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    // ================= MMA issuer: one elected lane walks the whole tile program =================
+    if (elect_one()) {
+      uint32_t wcnt = 0;
+      const uint32_t id_tf32 = make_idesc(2, 128), id_f16 = make_idesc(0, 128), id_s = make_idesc(0, p.nkeys),
+                     id_pv = make_idesc(0, kHd), id_out = make_idesc(0, kC);
+      const uint64_t dRA = make_smem_desc(smem_u32(RA)), dRB = make_smem_desc(smem_u32(RB)), dRC = make_smem_desc(smem_u32(RC)),
+                     dRD = make_smem_desc(smem_u32(RD)), dRE = make_smem_desc(smem_u32(RE)), dRing = make_smem_desc(smem_u32(ring));
+      constexpr uint64_t CH = kChunk >> 4;          // descriptor units (16 B) per chunk / slot
+      auto wslot = [&]() -> uint64_t {             // wait for the next weight block, return its descriptor
+        const uint32_t slot = wcnt % kSlots, use = wcnt / kSlots;
+        mbar_wait(bars + W_FULL + slot, use & 1u);
+        tc_fence_after();
+        return dRing + (uint64_t)slot * CH;
+      };
+      auto wfree = [&]() { umma_commit(bars + W_EMPTY + (wcnt % kSlots)); ++wcnt; };
+      const int pv_steps = p.nkeys >> 4;
+      for (int it = 0; it < n_my; ++it) {
+        const uint32_t par = (uint32_t)it & 1u;
+        // ---- X = x W_in^T (tf32) -> R
+        mbar_wait(bars + X_FULL, par);
+        tc_fence_after();
+        { const uint64_t b = wslot(); mma_chunk<true, true>(tR, dRA, b, id_tf32); wfree(); }
+        { const uint64_t b = wslot(); mma_chunk<true, false>(tR, dRA + CH, b, id_tf32); wfree(); }
+        umma_commit(bars + R_FULL);
+        // ---- V^T = Wv X^T -> T1 ;  Q, K = N Wq^T, N Wk^T -> T2
+        mbar_wait(bars + XN_READY, par);
+        tc_fence_after();
+        { const uint64_t a = wslot(); mma_chunk<false, true>(tT1, a, dRA, id_f16); wfree(); }
+        { const uint64_t a = wslot(); mma_chunk<false, false>(tT1, a, dRA + CH, id_f16); wfree(); }
+        umma_commit(bars + VT_FULL);
+        { const uint64_t b = wslot(); mma_chunk<false, true>(tT2, dRB, b, id_f16); wfree(); }
+        { const uint64_t b = wslot(); mma_chunk<false, false>(tT2, dRB + CH, b, id_f16); wfree(); }
+        { const uint64_t b = wslot(); mma_chunk<false, true>(tT2 + 128, dRB, b, id_f16); wfree(); }
+        { const uint64_t b = wslot(); mma_chunk<false, false>(tT2 + 128, dRB + CH, b, id_f16); wfree(); }
+        umma_commit(bars + QK_FULL);
+        // ---- attention: S_h = Q_h K_h^T (one K = 16 MMA), softmax by the epilogue, O_h = P V_h
+        mbar_wait(bars + QKV_READY, par);
+        tc_fence_after();
+        auto issue_s = [&](int h) {
+          const uint64_t off = (uint64_t)(h >> 2) * CH + (uint64_t)(2 * (h & 3));
+          umma_f16<0>(tT2 + 128 * (h & 1), dRC + off, dRD + off, id_s);
+          umma_commit(bars + S_FULL + (h & 1));
+        };
+        issue_s(0);
+        issue_s(1);
+        for (int h = 0; h < kHeads; ++h) {
+          const int j = h & 1;
+          mbar_wait(bars + P_FULL + j, (uint32_t)(h >> 1) & 1u);
+          tc_fence_after();
+          if (h + 2 < kHeads) issue_s(h + 2);
+          const uint64_t pa = j ? dRA : dRB;
+          const uint64_t vb = dRE + (uint64_t)(h * kHd * 128 >> 4);      // rows 16h.. of V^T (N = 16)
+          for (int ks = 0; ks < pv_steps; ++ks) {
+            const uint64_t off = (uint64_t)(ks >> 2) * CH + (uint64_t)(2 * (ks & 3));
+            if (ks == 0) umma_f16<0>(tT1 + h * kHd, pa + off, vb + off, id_pv);
+            else umma_f16<1>(tT1 + h * kHd, pa + off, vb + off, id_pv);
+          }
+          umma_commit(bars + P_EMPTY + j);
+        }
+        umma_commit(bars + O_FULL);
+        umma_commit(bars + X_EMPTY);
+        // ---- X2 = X + O Wo^T (accumulate into R)
+        mbar_wait(bars + O_READY, par);
+        tc_fence_after();
+        { const uint64_t b = wslot(); mma_chunk<false, false>(tR, dRC, b, id_f16); wfree(); }
+        { const uint64_t b = wslot(); mma_chunk<false, false>(tR, dRC + CH, b, id_f16); wfree(); }
+        umma_commit(bars + R_FULL);
+        // ---- F = N2 W1^T -> T2 (two halves of 128 columns)
+        mbar_wait(bars + N2_READY, par);
+        tc_fence_after();
+        for (int n = 0; n < 2; ++n) {
+          { const uint64_t b = wslot(); mma_chunk<false, true>(tT2 + 128 * n, dRB, b, id_f16); wfree(); }
+          { const uint64_t b = wslot(); mma_chunk<false, false>(tT2 + 128 * n, dRB + CH, b, id_f16); wfree(); }
+          umma_commit(bars + F_FULL + n);
+        }
+        // ---- X3 = X2 + relu(F) W2^T (accumulate into R); K = 256 in four chunks (RD, RD+16K, RE, RE+16K)
+        for (int n = 0; n < 2; ++n) {
+          mbar_wait(bars + F_READY + n, par);
+          tc_fence_after();
+          const uint64_t fa = n ? dRE : dRD;
+          { const uint64_t b = wslot(); mma_chunk<false, false>(tR, fa, b, id_f16); wfree(); }
+          { const uint64_t b = wslot(); mma_chunk<false, false>(tR, fa + CH, b, id_f16); wfree(); }
+        }
+        umma_commit(bars + R_FULL);
+        // ---- y = X3 Wout^T -> T1[0..63]; the slot holds both K-chunks of Wout (64 rows x 128 B each)
+        mbar_wait(bars + X3_READY, par);
+        tc_fence_after();
+        {
+          const uint64_t b = wslot();
+          mma_chunk<false, true>(tT1, dRB, b, id_out);
+          mma_chunk<false, false>(tT1, dRB + CH, b + (uint64_t)(8192 >> 4), id_out);
+          wfree();
+        }
+        umma_commit(bars + Y_FULL);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue warps: TMEM -> registers -> fp16 operands in shared memory / y in HBM =================
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;                       // TMEM lane = tile row (token, s-major) - or channel for V^T
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const bool row_ok = r < p.nrows;
+    const int s_loc = r / p.A, a_idx = r - s_loc * p.A;
+    // valid key columns of this query row: all A rows of the positions |s - s'| <= w that the tile holds
+    const int k_lo = (s_loc - p.w > 0 ? s_loc - p.w : 0) * p.A;
+    const int k_hi = ((s_loc + p.w < p.SL - 1 ? s_loc + p.w : p.SL - 1) + 1) * p.A;
+    const int wlo = __reduce_min_sync(0xffffffffu, row_ok ? k_lo : 0x7fffffff);
+    const int whi = __reduce_max_sync(0xffffffffu, row_ok ? k_hi : 0);
+    const uint32_t sRA = smem_u32(RA), sRB = smem_u32(RB), sRC = smem_u32(RC), sRD = smem_u32(RD), sRE = smem_u32(RE);
+    uint32_t rcnt = 0;
+    auto arrive = [&](int bar) {          // generic-proxy writes -> async proxy (UMMA), TMEM reads ordered before the handoff
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + bar);
+    };
+    // LayerNorm over the 128 columns of R: this warp owns 64 of them (half), the partner warp of the lane quarter the rest
+    auto layer_norm = [&](float* v, const float* g, const float* bta, float eps) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) s += v[i];
+      lnx[half * 128 + r] = s;
+      named_bar_sync(1 + q, 64);
+      const float mean = (lnx[r] + lnx[128 + r]) * (1.f / kE);
+      named_bar_sync(1 + q, 64);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) { const float d = v[i] - mean; ss = fmaf(d, d, ss); }
+      lnx[half * 128 + r] = ss;
+      named_bar_sync(1 + q, 64);
+      const float rstd = rsqrtf((lnx[r] + lnx[128 + r]) * (1.f / kE) + eps);
+      named_bar_sync(1 + q, 64);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = fmaf((v[i] - mean) * rstd, g[64 * half + i], bta[64 * half + i]);
+    };
+
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t par = (uint32_t)it & 1u;
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      // ---- X -> fp16 X (B operand of the V^T GEMM) and N = LN1(X) (A operand of the Q / K GEMMs)
+      mbar_wait(bars + R_FULL, rcnt++ & 1u);
+      tc_fence_after();
+      {
+        float v[64];
+        tmem_ld32(tR + lane_off + 64 * half, v);
+        tmem_ld32(tR + lane_off + 64 * half + 32, v + 32);
+        tmem_wait_ld();
+        if (row_ok) store_row_f16(sRA + half * kChunk, r, v); else store_row_zero(sRA + half * kChunk, r);
+        layer_norm(v, p.ln[0], p.ln[1], p.eps1);
+        if (row_ok) store_row_f16(sRB + half * kChunk, r, v); else store_row_zero(sRB + half * kChunk, r);
+      }
+      arrive(XN_READY);
+      // ---- V^T rows (lane = channel, columns = tokens) -> RE ; Q (scaled, exp2 domain), K -> RC, RD
+      mbar_wait(bars + VT_FULL, par);
+      tc_fence_after();
+      {
+        float v[64];
+        tmem_ld32(tT1 + lane_off + 64 * half, v);
+        tmem_ld32(tT1 + lane_off + 64 * half + 32, v + 32);
+        tmem_wait_ld();
+        store_row_f16(sRE + half * kChunk, r, v);
+      }
+      mbar_wait(bars + QK_FULL, par);
+      tc_fence_after();
+      {
+        float v[64];
+        tmem_ld32(tT2 + lane_off + 64 * half, v);
+        tmem_ld32(tT2 + lane_off + 64 * half + 32, v + 32);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] *= p.qscale;
+        store_row_f16(sRC + half * kChunk, r, v);
+        tmem_ld32(tT2 + lane_off + 128 + 64 * half, v);
+        tmem_ld32(tT2 + lane_off + 128 + 64 * half + 32, v + 32);
+        tmem_wait_ld();
+        store_row_f16(sRD + half * kChunk, r, v);
+      }
+      arrive(QKV_READY);
+      // ---- softmax of this warp's heads (half, half + 2, ...): S in TMEM -> un-normalised exp2 as fp16 P in shared memory
+      float inv_sum[4];
+      const uint32_t sP = half ? sRA : sRB;
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k) {
+        mbar_wait(bars + S_FULL + half, (uint32_t)k & 1u);
+        tc_fence_after();
+        float s[kMaxKeys];
+        // only the 16-column groups that intersect this warp's key window are loaded / exponentiated (warp-uniform tests)
+#pragma unroll
+        for (int g = 0; g < kMaxKeys / 16; ++g)
+          if (g * 16 < whi && g * 16 + 16 > wlo) tmem_ld16(tT2 + lane_off + 128 * half + g * 16, s + g * 16);
+        tmem_wait_ld();
+        float m = -1e30f;
+#pragma unroll
+        for (int g = 0; g < kMaxKeys / 16; ++g)
+          if (g * 16 < whi && g * 16 + 16 > wlo) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = g * 16 + j;
+              const float x = ((unsigned)(c - k_lo) < (unsigned)(k_hi - k_lo)) ? s[c] : -INFINITY;
+              s[c] = x;
+              m = fmaxf(m, x);
+            }
+          }
+        mbar_wait(bars + P_EMPTY + half, ((uint32_t)k & 1u) ^ 1u);      // P.V of this buffer's previous head has retired
+        float sum = 0.f;
+#pragma unroll
+        for (int g = 0; g < kMaxKeys / 16; ++g) {
+          if (g * 16 >= p.nkeys) continue;
+          if (g * 16 < whi && g * 16 + 16 > wlo) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float e = ex2_approx(s[g * 16 + j] - m);
+              s[g * 16 + j] = e;
+              sum += e;
+            }
+            store_grp_f16(sP + (g >> 2) * kChunk, r, g & 3, s + g * 16);
+          } else {
+            store_grp_zero(sP + (g >> 2) * kChunk, r, g & 3);
+          }
+        }
+        inv_sum[k] = __fdividef(1.f, sum);
+        arrive(P_FULL + half);
+      }
+      // ---- O = sum_h P_h V_h / rowsum -> fp16 O (A operand of the Wo GEMM) in RC (Q is dead)
+      mbar_wait(bars + O_FULL, par);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int h = 2 * k + half;
+        float v[16];
+        tmem_ld16(tT1 + lane_off + h * kHd, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= inv_sum[k];
+        store_grp_f16(sRC + (h >> 2) * kChunk, r, h & 3, v);
+      }
+      arrive(O_READY);
+      // ---- N2 = LN2(X2) -> RB
+      mbar_wait(bars + R_FULL, rcnt++ & 1u);
+      tc_fence_after();
+      {
+        float v[64];
+        tmem_ld32(tR + lane_off + 64 * half, v);
+        tmem_ld32(tR + lane_off + 64 * half + 32, v + 32);
+        tmem_wait_ld();
+        layer_norm(v, p.ln[2], p.ln[3], p.eps2);
+        store_row_f16(sRB + half * kChunk, r, v);
+      }
+      arrive(N2_READY);
+      // ---- relu(F): this warp's 128 of the 256 columns -> two K-chunks of RD (half 0) / RE (half 1)
+      mbar_wait(bars + F_FULL + half, par);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[64];
+        tmem_ld32(tT2 + lane_off + 128 * half + 64 * c, v);
+        tmem_ld32(tT2 + lane_off + 128 * half + 64 * c + 32, v + 32);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
+        store_row_f16((half ? sRE : sRD) + c * kChunk, r, v);
+      }
+      arrive(F_READY + half);
+      // ---- X3 -> fp16 in RB (A operand of linear_out)
+      mbar_wait(bars + R_FULL, rcnt++ & 1u);
+      tc_fence_after();
+      {
+        float v[64];
+        tmem_ld32(tR + lane_off + 64 * half, v);
+        tmem_ld32(tR + lane_off + 64 * half + 32, v + 32);
+        tmem_wait_ld();
+        store_row_f16(sRB + half * kChunk, r, v);
+      }
+      arrive(X3_READY);
+      // ---- y rows of the tile's own query positions -> HBM (32 of the 64 channels per warp half)
+      mbar_wait(bars + Y_FULL, par);
+      tc_fence_after();
+      {
+        float v[32];
+        tmem_ld32(tT1 + lane_off + 32 * half, v);
+        tmem_wait_ld();
+        const int seq = tile / p.nt, t = tile - seq * p.nt;
+        const int b = seq / p.npq, pq = seq - b * p.npq;
+        const int pi = pq / p.nq, qi = pq - pi * p.nq;
+        int ls0 = t * p.sq - p.w;
+        if (ls0 < 0) ls0 = 0;
+        if (ls0 > p.S - p.SL) ls0 = p.S - p.SL;
+        const int sg = ls0 + s_loc;
+        const int qs0 = t * p.sq, qs1 = qs0 + p.sq < p.S ? qs0 + p.sq : p.S;
+        if (row_ok && sg >= qs0 && sg < qs1) {
+          const long long tok = (long long)b * p.stride_b + (long long)pi * p.stride_p + (long long)qi * p.stride_q +
+                                (long long)a_idx * p.stride_a + (long long)sg * p.stride_s;
+          float4* dst = reinterpret_cast<float4*>(p.y + tok * p.ld_y + 32 * half);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    __syncwarp();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static float round_tf32(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;
+  u += 0xFFFu + ((u >> 13) & 1u);
+  u &= ~0x1FFFu;
+  float y;
+  memcpy(&y, &u, 4);
+  return y;
+}
+
+// tile plan: nt tiles per sequence, each owns sq query positions and loads SL positions (SL * A <= 112 rows)
+static bool plan(int A, int S, int w, int* nt_, int* sq_, int* SL_) {
+  for (int nt = 1; nt <= S; ++nt) {
+    const int sq = (S + nt - 1) / nt;
+    int SL = 0;
+    for (int t = 0; t * sq < S; ++t) {
+      const int q0 = t * sq, q1 = q0 + sq < S ? q0 + sq : S;
+      const int l0 = q0 - w > 0 ? q0 - w : 0, l1 = q1 + w < S ? q1 + w : S;
+      if (l1 - l0 > SL) SL = l1 - l0;
+    }
+    if (SL * A <= kMaxKeys) { *nt_ = (S + sq - 1) / sq; *sq_ = sq; *SL_ = SL; return true; }
+  }
+  return false;
+}
+
+static bool geometry_ok(const lfsr_tensor* x, const lfsr_tensor* y, const lfsr_basictrans_desc* d) {
+  if (!tensor_ok(x) || !tensor_ok(y) || !d) return false;
+  if (d->E != kE || d->C != kC || d->heads != kHeads) return false;
+  if (x->c != kC || y->c != kC || x->ld % 4 || y->ld % 4 || ((uintptr_t)x->ptr & 15) || ((uintptr_t)y->ptr & 15)) return false;
+  if (x->n != y->n || x->h != y->h || x->w != y->w) return false;
+  if (d->A < 1 || d->S < 1 || d->half_window < 0 || d->nb < 1 || d->np < 1 || d->nq < 1) return false;
+  if (d->stride_p != (int64_t)d->nq * d->stride_q) return false;          // (p, q) must merge into one tensor-map dimension
+  if (d->A > 256 || d->S > 4096) return false;
+  int nt, sq, SL;
+  if (!plan(d->A, d->S, d->half_window, &nt, &sq, &SL)) return false;
+  if ((long long)d->nb * d->np * d->nq * nt > 0x7fffffffLL) return false;
+  return true;
+}
+
+}  // namespace bt
+}  // namespace lfsr
+
+using namespace lfsr;
+using namespace lfsr::bt;
+
+extern "C" size_t lfsr_basictrans_packed_bytes(void) { return (size_t)kBlocks * kSlot; }
+
+// Weights in torch layout [out][in] (fp32, host): linear_in [128][64], MultiheadAttention.in_proj_weight [384][128]
+// (q | k | v), out_proj [128][128], feed_forward.1 [256][128], feed_forward.4 [128][256], linear_out [64][128] ->
+// 19 blocks of [128 rows][128 bytes] in the order the kernel consumes them (see kW* above). linear_in stays fp32 rounded
+// to TF32 (its A operand is the TMA-loaded input tile); everything else is fp16.
+extern "C" int lfsr_pack_basictrans(const float* w_in, const float* w_qkv, const float* w_o, const float* w_ff1,
+                                    const float* w_ff2, const float* w_out, void* packed_host) {
+  LFSR_REQUIRE(w_in && w_qkv && w_o && w_ff1 && w_ff2 && w_out && packed_host, "lfsr_pack_basictrans: null pointer");
+  uint8_t* out = static_cast<uint8_t*>(packed_host);
+  memset(out, 0, (size_t)kBlocks * kSlot);
+  auto blk_f32 = [&](int blk) { return reinterpret_cast<float*>(out + (size_t)blk * kSlot); };
+  auto blk_f16 = [&](int blk) { return reinterpret_cast<__half*>(out + (size_t)blk * kSlot); };
+  for (int c = 0; c < 2; ++c)                           // W_in: rows = out channel, 32 fp32 of K-chunk c
+    for (int o = 0; o < kE; ++o)
+      for (int k = 0; k < 32; ++k) blk_f32(kWin + c)[o * 32 + k] = round_tf32(w_in[o * kC + 32 * c + k]);
+  auto pack_f16 = [&](int blk0, const float* w, int row0, int rows, int in_dim, int chunks) {
+    for (int c = 0; c < chunks; ++c)
+      for (int o = 0; o < rows; ++o)
+        for (int k = 0; k < 64; ++k)
+          blk_f16(blk0 + c)[o * 64 + k] = __float2half_rn(w[(size_t)(row0 + o) * in_dim + 64 * c + k]);
+  };
+  pack_f16(kWv, w_qkv, 2 * kE, kE, kE, 2);
+  pack_f16(kWq, w_qkv, 0, kE, kE, 2);
+  pack_f16(kWk, w_qkv, kE, kE, kE, 2);
+  pack_f16(kWo, w_o, 0, kE, kE, 2);
+  pack_f16(kW1, w_ff1, 0, kE, kE, 2);
+  pack_f16(kW1 + 2, w_ff1, kE, kE, kE, 2);
+  pack_f16(kW2, w_ff2, 0, kE, 2 * kE, 4);
+  for (int c = 0; c < 2; ++c)                           // W_out: both K-chunks in one slot, 64 rows x 128 B each
+    for (int o = 0; o < kC; ++o)
+      for (int k = 0; k < 64; ++k)
+        blk_f16(kWout)[(size_t)c * 4096 + o * 64 + k] = __float2half_rn(w_out[(size_t)o * kE + 64 * c + k]);
+  return LFSR_OK;
+}
+
+extern "C" int lfsr_basictrans_supported(const lfsr_tensor* x, const lfsr_tensor* y, const lfsr_basictrans_desc* d) {
+  return geometry_ok(x, y, d) && get_encode() != nullptr ? 1 : 0;
+}
+
+extern "C" int lfsr_epit_basictrans(const lfsr_tensor* x, const void* packed, const lfsr_tensor* y,
+                                    const lfsr_basictrans_desc* d, void* stream) {
+  LFSR_REQUIRE(packed, "lfsr_epit_basictrans: null weights");
+  LFSR_REQUIRE(geometry_ok(x, y, d), "lfsr_epit_basictrans: unsupported geometry (query lfsr_basictrans_supported)");
+  LFSR_REQUIRE(x->ptr != y->ptr, "lfsr_epit_basictrans: in-place operation is not supported");
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { set_error("lfsr_epit_basictrans: cuTensorMapEncodeTiled unavailable"); return LFSR_ERR_CUDA; }
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.A = d->A; p.S = d->S; p.w = d->half_window;
+  plan(p.A, p.S, p.w, &p.nt, &p.sq, &p.SL);
+  p.nrows = p.SL * p.A;
+  p.nkeys = (p.nrows + 15) / 16 * 16;
+  p.npq = d->np * d->nq; p.nq = d->nq;
+  p.nseq = d->nb * p.npq;
+  p.total_tiles = p.nseq * p.nt;
+  p.stride_a = d->stride_a; p.stride_s = d->stride_s; p.stride_b = d->stride_b; p.stride_p = d->stride_p; p.stride_q = d->stride_q;
+  p.y = (float*)y->ptr; p.ld_y = y->ld;
+  p.eps1 = d->eps1; p.eps2 = d->eps2;
+  p.qscale = 1.4426950408889634f / sqrtf((float)kHd);
+  memcpy(p.ln[0], d->ln1_g, sizeof(float) * kE); memcpy(p.ln[1], d->ln1_b, sizeof(float) * kE);
+  memcpy(p.ln[2], d->ln2_g, sizeof(float) * kE); memcpy(p.ln[3], d->ln2_b, sizeof(float) * kE);
+  const long long T = (long long)x->n * x->h * x->w;
+  // every token the tiles touch must lie inside the tensor
+  const long long last = (long long)(d->nb - 1) * d->stride_b + (long long)(d->np - 1) * d->stride_p +
+                         (long long)(d->nq - 1) * d->stride_q + (long long)(d->A - 1) * d->stride_a +
+                         (long long)(d->S - 1) * d->stride_s;
+  LFSR_REQUIRE(last < T, "lfsr_epit_basictrans: the stride set addresses tokens outside the tensor");
+  CUtensorMap tmX, tmW;
+  {
+    const cuuint64_t ld_b = (cuuint64_t)x->ld * 4;
+    cuuint64_t dims[5] = {(cuuint64_t)kC, (cuuint64_t)p.A, (cuuint64_t)p.S, (cuuint64_t)p.npq, (cuuint64_t)d->nb};
+    cuuint64_t strides[4] = {ld_b * (cuuint64_t)d->stride_a, ld_b * (cuuint64_t)d->stride_s, ld_b * (cuuint64_t)d->stride_q,
+                             ld_b * (cuuint64_t)d->stride_b};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.A, (cuuint32_t)p.SL, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, x->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("lfsr_epit_basictrans: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return LFSR_ERR_CUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {128, (cuuint64_t)kBlocks * 128};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {128, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(packed), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("lfsr_epit_basictrans: cuTensorMapEncodeTiled(w) failed with %d", (int)r); return LFSR_ERR_CUDA; }
+  }
+  const int smem = kSmemBytes + 1024;
+  static DevOnce once;
+  if (once.need()) {
+    if (opt_in_smem(basictrans_kernel, smem, "lfsr_epit_basictrans")) return LFSR_ERR_CUDA;
+    once.done();
+  }
+  const int sms = sm_count_current();
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  basictrans_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmX, tmW, p);
+  return check_launch("basictrans_kernel");
+}

@@ -276,6 +276,39 @@ class CudaOps:
         N.check(self.lib.lfsr_epi_attention(qk.data_ptr(), v.data_ptr(), out.data_ptr(), C.byref(d), self._stream(qk)),
                 "lfsr_epi_attention")
 
+    # -- fused BasicTrans (EPIT.py:110-128) ------------------------------------------------------------------------
+    def pack_basictrans(self, w_in, w_qkv, w_o, w_ff1, w_ff2, w_out, ln1, ln2, heads, device):
+        """weights in torch layout (any device) -> (packed device buffer, descriptor template with the LayerNorm constants)"""
+        host = [t.detach().to("cpu", torch.float32).contiguous() for t in (w_in, w_qkv, w_o, w_ff1, w_ff2, w_out)]
+        E, Cc = host[0].shape
+        if (E, Cc) != (128, 64) or tuple(host[1].shape) != (3 * E, E) or tuple(host[3].shape) != (2 * E, E) or heads != 8:
+            return None
+        buf = torch.empty(self.lib.lfsr_basictrans_packed_bytes(), dtype=torch.uint8)
+        N.check(self.lib.lfsr_pack_basictrans(*[t.data_ptr() for t in host], buf.data_ptr()), "lfsr_pack_basictrans")
+        d = N.BasicTransDesc()
+        d.heads, d.E, d.C = heads, E, Cc
+        for name, t in (("ln1_g", ln1[0]), ("ln1_b", ln1[1]), ("ln2_g", ln2[0]), ("ln2_b", ln2[1])):
+            arr = getattr(d, name)
+            for i, v in enumerate(t.detach().to("cpu", torch.float32).tolist()):
+                arr[i] = v
+        d.eps1, d.eps2 = float(ln1[2]), float(ln2[2])
+        return buf.to(device), d
+
+    def basictrans(self, x, packed, desc, y, A, S, half_window, nb, np_, nq, stride_a, stride_s, stride_b, stride_p, stride_q,
+                   check_only=False):
+        """x, y: [n,h,w,64] NHWC; sequences addressed as in epi_attention. Returns False when the geometry is unsupported
+        (check_only: just answer)."""
+        d = desc
+        d.A, d.S, d.half_window, d.nb, d.np, d.nq = A, S, half_window, nb, np_, nq
+        d.stride_a, d.stride_s, d.stride_b, d.stride_p, d.stride_q = stride_a, stride_s, stride_b, stride_p, stride_q
+        tx, ty = as_tensor(x, "basictrans.x"), as_tensor(y, "basictrans.y")
+        if not self.lib.lfsr_basictrans_supported(C.byref(tx), C.byref(ty), C.byref(d)):
+            return False
+        if not check_only:
+            N.check(self.lib.lfsr_epit_basictrans(C.byref(tx), packed.data_ptr(), C.byref(ty), C.byref(d), self._stream(x)),
+                    "lfsr_epit_basictrans")
+        return True
+
     # -- metrics -----------------------------------------------------------------------------------------
     def metric_sums(self, label, out, ang, h, w, acc):
         N.check(self.lib.lfsr_metric_sums(label.data_ptr(), out.data_ptr(), ang, h, w, acc.data_ptr(),

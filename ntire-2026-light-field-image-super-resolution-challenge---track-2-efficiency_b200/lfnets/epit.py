@@ -24,6 +24,10 @@ from .. import _native as N
 from .. import kernels as K
 from .common import LFNetBase, L1Loss, slots, tail_table
 
+#: LFSR_EPIT_FUSED=0 keeps BasicTrans on the ten separate launches (comparison / debugging)
+import os
+USE_FUSED_BASICTRANS = os.environ.get("LFSR_EPIT_FUSED", "1") != "0"
+
 
 def _c3(cin, cout):
     return nn.Conv3d(cin, cout, kernel_size=(1, 3, 3), padding=(0, 1, 1), bias=False)
@@ -73,8 +77,16 @@ class get_model(LFNetBase):
             t = af.epi_trans
             E = t.norm.weight.numel()
             ipw = t.attention.in_proj_weight
+            # the whole BasicTrans as one tcgen05 kernel (lfsr_epit_basictrans) when the backend has it
+            bt = None
+            if hasattr(ops, "pack_basictrans") and getattr(ops, "use_tc", False):
+                bt = ops.pack_basictrans(t.linear_in.weight, ipw, t.attention.out_proj.weight, t.feed_forward["1"].weight,
+                                         t.feed_forward["4"].weight, t.linear_out.weight,
+                                         (t.norm.weight, t.norm.bias, t.norm.eps),
+                                         (t.feed_forward["0"].weight, t.feed_forward["0"].bias, t.feed_forward["0"].eps),
+                                         t.num_heads, device)
             pk["alt"].append(dict(
-                lin_in=lin(t.linear_in.weight), ln1=(vec(t.norm.weight), vec(t.norm.bias), t.norm.eps),
+                bt=bt, lin_in=lin(t.linear_in.weight), ln1=(vec(t.norm.weight), vec(t.norm.bias), t.norm.eps),
                 wqk=lin(ipw[:2 * E]), wv=lin(ipw[2 * E:]), wo=lin(t.attention.out_proj.weight),
                 ln2=(vec(t.feed_forward["0"].weight), vec(t.feed_forward["0"].bias), t.feed_forward["0"].eps),
                 ff1=lin(t.feed_forward["1"].weight), ff2=lin(t.feed_forward["4"].weight), lin_out=lin(t.linear_out.weight),
@@ -115,10 +127,16 @@ class get_model(LFNetBase):
         ]
         cur = fa
         ring = [buf("r0", H, W, C), buf("r1", H, W, C), buf("r2", H, W, C)]
-        ri = 0
+        state = {"ri": 0, "cur": fa}
         for al in pk["alt"]:
             short = cur
             for p in passes:
+                if al["bt"] is not None and USE_FUSED_BASICTRANS and ops.basictrans(
+                        cur, al["bt"][0], al["bt"][1], yb, p["A"], p["S"], 5, B, p["np_"], p["nq"], p["stride_a"],
+                        p["stride_s"], p["stride_b"], p["stride_p"], p["stride_q"]):
+                    self._conv_tail(ops, al, yb, t1, t2, ring, short, blk, LR, state)
+                    cur = state["cur"]
+                    continue
                 ops.conv(tok(cur), al["lin_in"], tok(X))
                 ops.layernorm(tok(X), al["ln1"][0], al["ln1"][1], al["ln1"][2], tok(Nn))
                 ops.conv(tok(Nn), al["wqk"], tok(QK))
@@ -130,15 +148,8 @@ class get_model(LFNetBase):
                 ops.conv(tok(Nn), al["ff1"], tok(F1), act=N.ACT_RELU)
                 ops.conv(tok(F1), al["ff2"], tok(X), res=tok(X2))
                 ops.conv(tok(X), al["lin_out"], tok(yb))
-                ops.conv(yb, al["conv"][0], t1, act=LR, slope=0.2, block=blk)
-                ops.conv(t1, al["conv"][1], t2, act=LR, slope=0.2, block=blk)
-                nxt = ring[ri]
-                ri = (ri + 1) % 3
-                if nxt is short:
-                    nxt = ring[ri]
-                    ri = (ri + 1) % 3
-                ops.conv(t2, al["conv"][2], nxt, res=short, block=blk)
-                cur = nxt
+                self._conv_tail(ops, al, yb, t1, t2, ring, short, blk, LR, state)
+                cur = state["cur"]
         # altblock(buffer) + buffer (:64): the last AltFilter already consumed its own shortcut as the
         # fused residual, so this second skip is one identity-weight 1x1 pass (0.1 GMAC/patch)
         ops.conv(cur, self._identity(pk, dev), fb, res=fa)
@@ -153,6 +164,20 @@ class get_model(LFNetBase):
             up = buf("up", H * s, W * s, C)
             ops.conv(fb, pk["up0"], up, act=LR, slope=0.2, shuffle=shuffle)
             ops.conv(up, pk["up3"], Y, res=Y)
+
+    @staticmethod
+    def _conv_tail(ops, al, yb, t1, t2, ring, short, blk, LR, state):
+        """the three per-view convs + shortcut that follow BasicTrans in AltFilter (EPIT.py:152-153, :160-161)"""
+        ops.conv(yb, al["conv"][0], t1, act=LR, slope=0.2, block=blk)
+        ops.conv(t1, al["conv"][1], t2, act=LR, slope=0.2, block=blk)
+        ri = state["ri"]
+        nxt = ring[ri]
+        ri = (ri + 1) % 3
+        if nxt is short:
+            nxt = ring[ri]
+            ri = (ri + 1) % 3
+        ops.conv(t2, al["conv"][2], nxt, res=short, block=blk)
+        state["ri"], state["cur"] = ri, nxt
 
     def _identity(self, pk, dev):
         if "eye" not in pk:
