@@ -32,12 +32,18 @@ namespace lfsr {
 namespace bt {
 using namespace lfsr::ptx;
 
-constexpr int kThreads = 320, kTmaWarp = 8, kMmaWarp = 9;
+constexpr int kEpiWarps = 16, kTmaWarp = 16, kMmaWarp = 17, kThreads = 32 * 18;
 constexpr int kE = 128, kC = 64, kHeads = 8, kHd = 16;
-constexpr int kRegion = 32768, kChunk = 16384, kSlot = 16384, kSlots = 4;
-constexpr int kMaxKeys = 112;             // token rows per tile (7 groups of 16 score columns kept in registers)
+constexpr int kRows = 112;                  // token rows a tile may hold (7 groups of 16 score columns)
+constexpr int kMaxKeys = kRows;
+constexpr int kGrpPerWarp = 3;              // 16-column score groups a softmax warp keeps in registers (host checks the plan)
+constexpr int kChunk = kRows * 128;         // one K-chunk (64 fp16 / 32 tf32 per row) of a token-row operand: 14 KB
+constexpr int kRegion = 2 * kChunk;         // 28 KB
+constexpr int kVtChunk = 128 * 128, kVtRegion = 2 * kVtChunk;      // V^T: rows are the 128 channels
+constexpr int kSlot = 16384, kSlots = 4;
 constexpr int kBlocks = 19;                 // weight blocks (16 KB each) per tile, in consumption order
-constexpr int kSmemBytes = 5 * kRegion + kSlots * kSlot + 1024 /* LN exchange */ + 32 * 8 /* barriers */ + 16;
+constexpr int kXchgFloats = 1024;           // LN partial sums [4][128] / softmax partial max + sum [2][2][128] x 2
+constexpr int kSmemBytes = 4 * kRegion + kVtRegion + kSlots * kSlot + kXchgFloats * 4 + 40 * 8 /* barriers */ + 16;
 // weight block indices
 constexpr int kWin = 0, kWv = 2, kWq = 4, kWk = 6, kWo = 8, kW1 = 10, kW2 = 14, kWout = 18;
 
@@ -52,40 +58,30 @@ struct Params {
 };
 
 enum Bar {
-  X_FULL = 0, X_EMPTY, W_FULL, W_EMPTY = W_FULL + kSlots, R_FULL = W_EMPTY + kSlots, VT_FULL, QK_FULL, S_FULL, P_EMPTY = S_FULL + 2,
-  O_FULL = P_EMPTY + 2, F_FULL, Y_FULL = F_FULL + 2, XN_READY, QKV_READY, P_FULL, O_READY = P_FULL + 2, N2_READY, F_READY,
-  X3_READY = F_READY + 2, NUM_BARS
+  X_FULL = 0, X_EMPTY, W_FULL, W_EMPTY = W_FULL + kSlots, R_FULL = W_EMPTY + kSlots, VT_FULL, Q_FULL, K_FULL, S_FULL,
+  P_EMPTY = S_FULL + 3, F_FULL = P_EMPTY + 2, Y_FULL = F_FULL + 2,
+  // arrivals of the epilogue warps
+  X_READY, N_READY, QKV_READY, P_FULL, O_READY = P_FULL + 2, N2_READY, F_READY, X3_READY = F_READY + 2, NUM_BARS
 };
-static_assert(NUM_BARS <= 32, "barrier block");
+static_assert(NUM_BARS <= 40, "barrier block");
 
-// 64 floats -> one 128-byte K-major SWIZZLE_128B row (64 fp16) of a chunk that starts at a 1024-byte boundary
-__device__ __forceinline__ void store_row_f16(uint32_t chunk, int row, const float* v) {
+// `n` (multiple of 8) floats -> fp16 into 16-byte units u0, u0+1, .. of one 128-byte K-major SWIZZLE_128B row; the chunk
+// starts at a 1024-byte boundary
+template <int N>
+__device__ __forceinline__ void store_f16(uint32_t chunk, int row, int u0, const float* v) {
   const uint32_t rb = chunk + (uint32_t)row * 128u;
   const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    st_shared_v4(rb + (((uint32_t)j ^ sw) << 4), pack_f16x2(v[8 * j], v[8 * j + 1]), pack_f16x2(v[8 * j + 2], v[8 * j + 3]),
+  for (int j = 0; j < N / 8; ++j)
+    st_shared_v4(rb + ((((uint32_t)(u0 + j)) ^ sw) << 4), pack_f16x2(v[8 * j], v[8 * j + 1]), pack_f16x2(v[8 * j + 2], v[8 * j + 3]),
                  pack_f16x2(v[8 * j + 4], v[8 * j + 5]), pack_f16x2(v[8 * j + 6], v[8 * j + 7]));
 }
-__device__ __forceinline__ void store_row_zero(uint32_t chunk, int row) {
+template <int N>
+__device__ __forceinline__ void store_zero(uint32_t chunk, int row, int u0) {
   const uint32_t rb = chunk + (uint32_t)row * 128u;
+  const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) st_shared_v4(rb + ((uint32_t)j << 4), 0u, 0u, 0u, 0u);
-}
-// 16 floats -> units (2*g4, 2*g4 + 1) of the row (g4 = 16-column group inside the 64-column chunk)
-__device__ __forceinline__ void store_grp_f16(uint32_t chunk, int row, int g4, const float* v) {
-  const uint32_t rb = chunk + (uint32_t)row * 128u;
-  const uint32_t sw = (uint32_t)(row & 7);
-  st_shared_v4(rb + ((((uint32_t)(2 * g4)) ^ sw) << 4), pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
-               pack_f16x2(v[6], v[7]));
-  st_shared_v4(rb + ((((uint32_t)(2 * g4 + 1)) ^ sw) << 4), pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]),
-               pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
-}
-__device__ __forceinline__ void store_grp_zero(uint32_t chunk, int row, int g4) {
-  const uint32_t rb = chunk + (uint32_t)row * 128u;
-  const uint32_t sw = (uint32_t)(row & 7);
-  st_shared_v4(rb + ((((uint32_t)(2 * g4)) ^ sw) << 4), 0u, 0u, 0u, 0u);
-  st_shared_v4(rb + ((((uint32_t)(2 * g4 + 1)) ^ sw) << 4), 0u, 0u, 0u, 0u);
+  for (int j = 0; j < N / 8; ++j) st_shared_v4(rb + ((((uint32_t)(u0 + j)) ^ sw) << 4), 0u, 0u, 0u, 0u);
 }
 
 // four K-steps (one 128-byte chunk row) of a kind::f16 / kind::tf32 GEMM slice
@@ -108,20 +104,20 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* RA = smem;                 // x (fp32, TMA) / X fp16 / P of odd heads
   uint8_t* RB = smem + kRegion;       // N / P of even heads / N2 / X3
-  uint8_t* RC = smem + 2 * kRegion;   // Q / O
+  uint8_t* RC = smem + 2 * kRegion;   // Q / O (head by head, each O_h into the slot of the dead Q_h)
   uint8_t* RD = smem + 3 * kRegion;   // K / F chunks 0, 1
-  uint8_t* RE = smem + 4 * kRegion;   // V^T / F chunks 2, 3
-  uint8_t* ring = smem + 5 * kRegion;
-  float* lnx = reinterpret_cast<float*>(ring + kSlots * kSlot);       // [2 halves][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lnx + 256);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  uint8_t* RE = smem + 4 * kRegion;   // V^T (128 channel rows) / F chunks 2, 3
+  uint8_t* ring = RE + kVtRegion;
+  float* xchg = reinterpret_cast<float*>(ring + kSlots * kSlot);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + kXchgFloats);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NUM_BARS; ++i) {
       uint32_t cnt = 1;
-      if (i == XN_READY || i == QKV_READY || i == O_READY || i == N2_READY || i == X3_READY) cnt = 8;
-      if (i == P_FULL || i == P_FULL + 1 || i == F_READY || i == F_READY + 1) cnt = 4;
+      if (i == X_READY || i == N_READY || i == QKV_READY || i == O_READY || i == N2_READY || i == X3_READY) cnt = kEpiWarps;
+      if (i == P_FULL || i == P_FULL + 1 || i == F_READY || i == F_READY + 1) cnt = kEpiWarps / 2;
       mbar_init(bars + i, cnt);
     }
     fence_barrier_init();
@@ -133,6 +129,8 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // TMEM columns: R 0..127 | T1 128..255 (V^T, then score buffer 2, then y) | T2 256..511 ([Q|K], then score buffers 0, 1 at
+  // +0 / +112 and the two 16-column O buffers at +224 / +240, then the 256 FFN columns)
   const uint32_t tR = tmem, tT1 = tmem + 128, tT2 = tmem + 256;
   const int n_my = ((int)p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
@@ -177,12 +175,12 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                      id_pv = make_idesc(0, kHd), id_out = make_idesc(0, kC);
       const uint64_t dRA = make_smem_desc(smem_u32(RA)), dRB = make_smem_desc(smem_u32(RB)), dRC = make_smem_desc(smem_u32(RC)),
                      dRD = make_smem_desc(smem_u32(RD)), dRE = make_smem_desc(smem_u32(RE)), dRing = make_smem_desc(smem_u32(ring));
-      constexpr uint64_t CH = kChunk >> 4;          // descriptor units (16 B) per chunk / slot
+      constexpr uint64_t CH = kChunk >> 4, VCH = kVtChunk >> 4, SL16 = kSlot >> 4;      // descriptor units (16 B)
       auto wslot = [&]() -> uint64_t {             // wait for the next weight block, return its descriptor
         const uint32_t slot = wcnt % kSlots, use = wcnt / kSlots;
         mbar_wait(bars + W_FULL + slot, use & 1u);
         tc_fence_after();
-        return dRing + (uint64_t)slot * CH;
+        return dRing + (uint64_t)slot * SL16;
       };
       auto wfree = [&]() { umma_commit(bars + W_EMPTY + (wcnt % kSlots)); ++wcnt; };
       const int pv_steps = p.nkeys >> 4;
@@ -194,42 +192,49 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         { const uint64_t b = wslot(); mma_chunk<true, true>(tR, dRA, b, id_tf32); wfree(); }
         { const uint64_t b = wslot(); mma_chunk<true, false>(tR, dRA + CH, b, id_tf32); wfree(); }
         umma_commit(bars + R_FULL);
-        // ---- V^T = Wv X^T -> T1 ;  Q, K = N Wq^T, N Wk^T -> T2
-        mbar_wait(bars + XN_READY, par);
+        // ---- V^T = Wv X^T -> T1 (as soon as the fp16 copy of X is written, while the epilogue still normalises)
+        mbar_wait(bars + X_READY, par);
         tc_fence_after();
         { const uint64_t a = wslot(); mma_chunk<false, true>(tT1, a, dRA, id_f16); wfree(); }
         { const uint64_t a = wslot(); mma_chunk<false, false>(tT1, a, dRA + CH, id_f16); wfree(); }
         umma_commit(bars + VT_FULL);
+        // ---- Q = N Wq^T, K = N Wk^T -> T2
+        mbar_wait(bars + N_READY, par);
+        tc_fence_after();
         { const uint64_t b = wslot(); mma_chunk<false, true>(tT2, dRB, b, id_f16); wfree(); }
         { const uint64_t b = wslot(); mma_chunk<false, false>(tT2, dRB + CH, b, id_f16); wfree(); }
+        umma_commit(bars + Q_FULL);
         { const uint64_t b = wslot(); mma_chunk<false, true>(tT2 + 128, dRB, b, id_f16); wfree(); }
         { const uint64_t b = wslot(); mma_chunk<false, false>(tT2 + 128, dRB + CH, b, id_f16); wfree(); }
-        umma_commit(bars + QK_FULL);
-        // ---- attention: S_h = Q_h K_h^T (one K = 16 MMA), softmax by the epilogue, O_h = P V_h
+        umma_commit(bars + K_FULL);
+        // ---- attention: S_h = Q_h K_h^T (one K = 16 MMA) into one of THREE score buffers, so the next head of each warp
+        // pair is always ready; softmax by the epilogue; O_h = P_h V_h into the 16-column O buffer of its warp pair
         mbar_wait(bars + QKV_READY, par);
         tc_fence_after();
         auto issue_s = [&](int h) {
+          const int b = h % 3;
           const uint64_t off = (uint64_t)(h >> 2) * CH + (uint64_t)(2 * (h & 3));
-          umma_f16<0>(tT2 + 128 * (h & 1), dRC + off, dRD + off, id_s);
-          umma_commit(bars + S_FULL + (h & 1));
+          umma_f16<0>(b == 2 ? tT1 : tT2 + 112 * b, dRC + off, dRD + off, id_s);
+          umma_commit(bars + S_FULL + b);
         };
         issue_s(0);
         issue_s(1);
+        issue_s(2);
         for (int h = 0; h < kHeads; ++h) {
           const int j = h & 1;
           mbar_wait(bars + P_FULL + j, (uint32_t)(h >> 1) & 1u);
           tc_fence_after();
-          if (h + 2 < kHeads) issue_s(h + 2);
           const uint64_t pa = j ? dRA : dRB;
           const uint64_t vb = dRE + (uint64_t)(h * kHd * 128 >> 4);      // rows 16h.. of V^T (N = 16)
           for (int ks = 0; ks < pv_steps; ++ks) {
-            const uint64_t off = (uint64_t)(ks >> 2) * CH + (uint64_t)(2 * (ks & 3));
-            if (ks == 0) umma_f16<0>(tT1 + h * kHd, pa + off, vb + off, id_pv);
-            else umma_f16<1>(tT1 + h * kHd, pa + off, vb + off, id_pv);
+            const uint64_t aoff = (uint64_t)(ks >> 2) * CH + (uint64_t)(2 * (ks & 3));
+            const uint64_t boff = (uint64_t)(ks >> 2) * VCH + (uint64_t)(2 * (ks & 3));
+            if (ks == 0) umma_f16<0>(tT2 + 224 + 16 * j, pa + aoff, vb + boff, id_pv);
+            else umma_f16<1>(tT2 + 224 + 16 * j, pa + aoff, vb + boff, id_pv);
           }
           umma_commit(bars + P_EMPTY + j);
+          if (h + 3 < kHeads) issue_s(h + 3);           // its buffer was read by the softmax of head h (done: P_h is full)
         }
-        umma_commit(bars + O_FULL);
         umma_commit(bars + X_EMPTY);
         // ---- X2 = X + O Wo^T (accumulate into R)
         mbar_wait(bars + O_READY, par);
@@ -245,7 +250,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           { const uint64_t b = wslot(); mma_chunk<false, false>(tT2 + 128 * n, dRB + CH, b, id_f16); wfree(); }
           umma_commit(bars + F_FULL + n);
         }
-        // ---- X3 = X2 + relu(F) W2^T (accumulate into R); K = 256 in four chunks (RD, RD+16K, RE, RE+16K)
+        // ---- X3 = X2 + relu(F) W2^T (accumulate into R); K = 256 in four chunks (RD, RD + chunk, RE, RE + chunk)
         for (int n = 0; n < 2; ++n) {
           mbar_wait(bars + F_READY + n, par);
           tc_fence_after();
@@ -269,16 +274,24 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     __syncwarp();
   } else {
     // ================= epilogue warps: TMEM -> registers -> fp16 operands in shared memory / y in HBM =================
-    const int q = warp & 3, half = warp >> 2;
+    // four warps per TMEM lane quarter: `part` splits columns (LN, drains); for the softmax the quarter's warps form two
+    // pairs (pair = head parity) whose two warps (sub) split the key columns of a head
+    const int q = warp & 3, part = warp >> 2, pair = part >> 1, sub = part & 1;
     const int r = q * 32 + lane;                       // TMEM lane = tile row (token, s-major) - or channel for V^T
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const bool row_ok = r < p.nrows;
+    const bool row_ok = r < p.nrows, row_st = r < kRows;      // row_st: the row exists in the 112-row operand buffers
     const int s_loc = r / p.A, a_idx = r - s_loc * p.A;
     // valid key columns of this query row: all A rows of the positions |s - s'| <= w that the tile holds
     const int k_lo = (s_loc - p.w > 0 ? s_loc - p.w : 0) * p.A;
     const int k_hi = ((s_loc + p.w < p.SL - 1 ? s_loc + p.w : p.SL - 1) + 1) * p.A;
     const int wlo = __reduce_min_sync(0xffffffffu, row_ok ? k_lo : 0x7fffffff);
     const int whi = __reduce_max_sync(0xffffffffu, row_ok ? k_hi : 0);
+    // 16-column groups of the warp's key window, split between the two warps of the pair (<= 4 groups each)
+    const int ngrp = p.nkeys >> 4;
+    int g_first = whi > wlo ? wlo >> 4 : 0, g_end = whi > wlo ? (whi + 15) >> 4 : 0;
+    const int g_mid = g_first + ((g_end - g_first + 1) >> 1);
+    const int g0 = sub ? g_mid : g_first, g1 = sub ? g_end : g_mid;          // this warp: groups [g0, g1)
+    const int z0 = sub ? g_end : 0, z1 = sub ? ngrp : g_first;               // groups it zero-fills in P
     const uint32_t sRA = smem_u32(RA), sRB = smem_u32(RB), sRC = smem_u32(RC), sRD = smem_u32(RD), sRE = smem_u32(RE);
     uint32_t rcnt = 0;
     auto arrive = [&](int bar) {          // generic-proxy writes -> async proxy (UMMA), TMEM reads ordered before the handoff
@@ -287,170 +300,191 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + bar);
     };
-    // LayerNorm over the 128 columns of R: this warp owns 64 of them (half), the partner warp of the lane quarter the rest
+    // LayerNorm over the 128 columns of R: this warp owns 32 of them, the other three warps of the lane quarter the rest
     auto layer_norm = [&](float* v, const float* g, const float* bta, float eps) {
-      float s = 0.f;
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) s += v[i];
-      lnx[half * 128 + r] = s;
-      named_bar_sync(1 + q, 64);
-      const float mean = (lnx[r] + lnx[128 + r]) * (1.f / kE);
-      named_bar_sync(1 + q, 64);
-      float ss = 0.f;
+      for (int i = 0; i < 32; i += 2) { s0 += v[i]; s1 += v[i + 1]; }
+      xchg[part * 128 + r] = s0 + s1;
+      named_bar_sync(1 + q, 128);
+      const float mean = (xchg[r] + xchg[128 + r] + xchg[256 + r] + xchg[384 + r]) * (1.f / kE);
+      named_bar_sync(1 + q, 128);
+      s0 = 0.f; s1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) { const float d = v[i] - mean; ss = fmaf(d, d, ss); }
-      lnx[half * 128 + r] = ss;
-      named_bar_sync(1 + q, 64);
-      const float rstd = rsqrtf((lnx[r] + lnx[128 + r]) * (1.f / kE) + eps);
-      named_bar_sync(1 + q, 64);
+      for (int i = 0; i < 32; i += 2) {
+        v[i] -= mean; v[i + 1] -= mean;
+        s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
+      }
+      xchg[part * 128 + r] = s0 + s1;
+      named_bar_sync(1 + q, 128);
+      const float rstd = rsqrtf((xchg[r] + xchg[128 + r] + xchg[256 + r] + xchg[384 + r]) * (1.f / kE) + eps);
+      named_bar_sync(1 + q, 128);
 #pragma unroll
-      for (int i = 0; i < 64; ++i) v[i] = fmaf((v[i] - mean) * rstd, g[64 * half + i], bta[64 * half + i]);
+      for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i] * rstd, g[32 * part + i], bta[32 * part + i]);
     };
+    const int cchunk = part >> 1, cu0 = 4 * (part & 1);   // this warp's 32 columns of a 128-column operand: chunk, first unit
 
     for (int it = 0; it < n_my; ++it) {
       const uint32_t par = (uint32_t)it & 1u;
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-      // ---- X -> fp16 X (B operand of the V^T GEMM) and N = LN1(X) (A operand of the Q / K GEMMs)
+      // ---- X -> fp16 X (B operand of the V^T GEMM), then N = LN1(X) (A operand of the Q / K GEMMs)
       mbar_wait(bars + R_FULL, rcnt++ & 1u);
       tc_fence_after();
       {
-        float v[64];
-        tmem_ld32(tR + lane_off + 64 * half, v);
-        tmem_ld32(tR + lane_off + 64 * half + 32, v + 32);
+        float v[32];
+        tmem_ld32(tR + lane_off + 32 * part, v);
         tmem_wait_ld();
-        if (row_ok) store_row_f16(sRA + half * kChunk, r, v); else store_row_zero(sRA + half * kChunk, r);
+        if (row_st) { if (row_ok) store_f16<32>(sRA + cchunk * kChunk, r, cu0, v); else store_zero<32>(sRA + cchunk * kChunk, r, cu0); }
+        arrive(X_READY);
         layer_norm(v, p.ln[0], p.ln[1], p.eps1);
-        if (row_ok) store_row_f16(sRB + half * kChunk, r, v); else store_row_zero(sRB + half * kChunk, r);
+        if (row_st) { if (row_ok) store_f16<32>(sRB + cchunk * kChunk, r, cu0, v); else store_zero<32>(sRB + cchunk * kChunk, r, cu0); }
       }
-      arrive(XN_READY);
-      // ---- V^T rows (lane = channel, columns = tokens) -> RE ; Q (scaled, exp2 domain), K -> RC, RD
+      arrive(N_READY);
+      // ---- V^T rows (lane = channel, columns = tokens) -> RE ; Q (scaled, exp2 domain) -> RC ; K -> RD
       mbar_wait(bars + VT_FULL, par);
       tc_fence_after();
       {
-        float v[64];
-        tmem_ld32(tT1 + lane_off + 64 * half, v);
-        tmem_ld32(tT1 + lane_off + 64 * half + 32, v + 32);
+        float v[32];
+        tmem_ld32(tT1 + lane_off + 32 * part, v);
         tmem_wait_ld();
-        store_row_f16(sRE + half * kChunk, r, v);
+        store_f16<32>(sRE + cchunk * kVtChunk, r, cu0, v);
       }
-      mbar_wait(bars + QK_FULL, par);
+      mbar_wait(bars + Q_FULL, par);
       tc_fence_after();
       {
-        float v[64];
-        tmem_ld32(tT2 + lane_off + 64 * half, v);
-        tmem_ld32(tT2 + lane_off + 64 * half + 32, v + 32);
+        float v[32];
+        tmem_ld32(tT2 + lane_off + 32 * part, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] *= p.qscale;
-        store_row_f16(sRC + half * kChunk, r, v);
-        tmem_ld32(tT2 + lane_off + 128 + 64 * half, v);
-        tmem_ld32(tT2 + lane_off + 128 + 64 * half + 32, v + 32);
+        for (int i = 0; i < 32; ++i) v[i] *= p.qscale;
+        if (row_st) store_f16<32>(sRC + cchunk * kChunk, r, cu0, v);
+      }
+      mbar_wait(bars + K_FULL, par);
+      tc_fence_after();
+      {
+        float v[32];
+        tmem_ld32(tT2 + lane_off + 128 + 32 * part, v);
         tmem_wait_ld();
-        store_row_f16(sRD + half * kChunk, r, v);
+        if (row_st) store_f16<32>(sRD + cchunk * kChunk, r, cu0, v);
       }
       arrive(QKV_READY);
-      // ---- softmax of this warp's heads (half, half + 2, ...): S in TMEM -> un-normalised exp2 as fp16 P in shared memory
-      float inv_sum[4];
-      const uint32_t sP = half ? sRA : sRB;
+      // ---- softmax of this pair's heads (pair, pair + 2, ..): S in TMEM -> un-normalised exp2 as fp16 P in shared memory;
+      // the O columns of the pair's previous head are drained (scaled by 1 / rowsum) as soon as its P.V has retired
+      const uint32_t sP = pair ? sRA : sRB;
+      // partial row maxima / sums of the pair's two warps: [pair][sub][128] each (the maxima reuse the LayerNorm exchange area)
+      float* const pmax = xchg + pair * 256;
+      float* const psum = xchg + 512 + pair * 256;
+      auto drain_o = [&](int h) {                         // 8 of the 16 columns of O_h per warp of the pair
+        float v[8];
+        {
+          uint32_t t[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
+                       : "r"(tT2 + lane_off + 224 + 16 * pair + 8 * sub) : "memory");
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(t[i]);
+        }
+        const float inv = __fdividef(1.f, psum[r] + psum[128 + r]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= inv;
+        if (row_st) store_f16<8>(sRC + (h >> 2) * kChunk, r, 2 * (h & 3) + sub, v);
+      };
 #pragma unroll 1
       for (int k = 0; k < 4; ++k) {
-        mbar_wait(bars + S_FULL + half, (uint32_t)k & 1u);
+        const int h = 2 * k + pair, b = h % 3;
+        // completions of score buffer b before this head: (3, 3, 2) per tile for b = (0, 1, 2)
+        mbar_wait(bars + S_FULL + b, (uint32_t)(it * (b == 2 ? 2 : 3) + h / 3) & 1u);
         tc_fence_after();
-        float s[kMaxKeys];
-        // only the 16-column groups that intersect this warp's key window are loaded / exponentiated (warp-uniform tests)
+        const uint32_t tS = (b == 2 ? tT1 : tT2 + 112 * b) + lane_off;
+        float s[16 * kGrpPerWarp];
 #pragma unroll
-        for (int g = 0; g < kMaxKeys / 16; ++g)
-          if (g * 16 < whi && g * 16 + 16 > wlo) tmem_ld16(tT2 + lane_off + 128 * half + g * 16, s + g * 16);
+        for (int i = 0; i < kGrpPerWarp; ++i)
+          if (g0 + i < g1) tmem_ld16(tS + (g0 + i) * 16, s + 16 * i);
         tmem_wait_ld();
-        float m = -1e30f;
+        float m0 = -1e30f, m1 = -1e30f;
 #pragma unroll
-        for (int g = 0; g < kMaxKeys / 16; ++g)
-          if (g * 16 < whi && g * 16 + 16 > wlo) {
+        for (int i = 0; i < kGrpPerWarp; ++i)
+          if (g0 + i < g1) {
+            const int cb = (g0 + i) * 16 - k_lo;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = g * 16 + j;
-              const float x = ((unsigned)(c - k_lo) < (unsigned)(k_hi - k_lo)) ? s[c] : -INFINITY;
-              s[c] = x;
-              m = fmaxf(m, x);
+            for (int j = 0; j < 16; j += 2) {
+              const float x0 = ((unsigned)(cb + j) < (unsigned)(k_hi - k_lo)) ? s[16 * i + j] : -INFINITY;
+              const float x1 = ((unsigned)(cb + j + 1) < (unsigned)(k_hi - k_lo)) ? s[16 * i + j + 1] : -INFINITY;
+              s[16 * i + j] = x0; s[16 * i + j + 1] = x1;
+              m0 = fmaxf(m0, x0); m1 = fmaxf(m1, x1);
             }
           }
-        mbar_wait(bars + P_EMPTY + half, ((uint32_t)k & 1u) ^ 1u);      // P.V of this buffer's previous head has retired
-        float sum = 0.f;
+        // P.V of the pair's previous head has retired: its O columns can be drained and P / the exchange slots reused
+        mbar_wait(bars + P_EMPTY + pair, ((uint32_t)k & 1u) ^ 1u);
+        tc_fence_after();
+        named_bar_sync(5 + 2 * q + pair, 64);              // the partner's psum of the previous head is visible
+        if (k > 0) drain_o(h - 2);
+        pmax[sub * 128 + r] = fmaxf(m0, m1);
+        named_bar_sync(5 + 2 * q + pair, 64);
+        const float m = fmaxf(pmax[r], pmax[128 + r]);
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int g = 0; g < kMaxKeys / 16; ++g) {
-          if (g * 16 >= p.nkeys) continue;
-          if (g * 16 < whi && g * 16 + 16 > wlo) {
+        for (int i = 0; i < kGrpPerWarp; ++i)
+          if (g0 + i < g1) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float e = ex2_approx(s[g * 16 + j] - m);
-              s[g * 16 + j] = e;
-              sum += e;
+            for (int j = 0; j < 16; j += 2) {
+              const float e0 = ex2_approx(s[16 * i + j] - m), e1 = ex2_approx(s[16 * i + j + 1] - m);
+              s[16 * i + j] = e0; s[16 * i + j + 1] = e1;
+              a0 += e0; a1 += e1;
             }
-            store_grp_f16(sP + (g >> 2) * kChunk, r, g & 3, s + g * 16);
-          } else {
-            store_grp_zero(sP + (g >> 2) * kChunk, r, g & 3);
+            if (row_st) store_f16<16>(sP + ((g0 + i) >> 2) * kChunk, r, 2 * ((g0 + i) & 3), s + 16 * i);
           }
-        }
-        inv_sum[k] = __fdividef(1.f, sum);
-        arrive(P_FULL + half);
+        for (int g = z0; g < z1; ++g)
+          if (row_st) store_zero<16>(sP + (g >> 2) * kChunk, r, 2 * (g & 3));
+        psum[sub * 128 + r] = a0 + a1;
+        arrive(P_FULL + pair);
       }
-      // ---- O = sum_h P_h V_h / rowsum -> fp16 O (A operand of the Wo GEMM) in RC (Q is dead)
-      mbar_wait(bars + O_FULL, par);
+      mbar_wait(bars + P_EMPTY + pair, 1u);                // 5th wait of the tile: completion 4*it + 3
       tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int h = 2 * k + half;
-        float v[16];
-        tmem_ld16(tT1 + lane_off + h * kHd, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= inv_sum[k];
-        store_grp_f16(sRC + (h >> 2) * kChunk, r, h & 3, v);
-      }
+      named_bar_sync(5 + 2 * q + pair, 64);                // the partner's last psum is visible
+      drain_o(6 + pair);
       arrive(O_READY);
       // ---- N2 = LN2(X2) -> RB
       mbar_wait(bars + R_FULL, rcnt++ & 1u);
       tc_fence_after();
       {
-        float v[64];
-        tmem_ld32(tR + lane_off + 64 * half, v);
-        tmem_ld32(tR + lane_off + 64 * half + 32, v + 32);
+        float v[32];
+        tmem_ld32(tR + lane_off + 32 * part, v);
         tmem_wait_ld();
         layer_norm(v, p.ln[2], p.ln[3], p.eps2);
-        store_row_f16(sRB + half * kChunk, r, v);
+        if (row_st) store_f16<32>(sRB + cchunk * kChunk, r, cu0, v);
       }
       arrive(N2_READY);
-      // ---- relu(F): this warp's 128 of the 256 columns -> two K-chunks of RD (half 0) / RE (half 1)
-      mbar_wait(bars + F_FULL + half, par);
+      // ---- relu(F): this warp's 64 of the 256 columns -> K-chunk `part` of the FFN operand (RD: 0, 1; RE: 2, 3)
+      mbar_wait(bars + F_FULL + (part >> 1), par);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        float v[64];
-        tmem_ld32(tT2 + lane_off + 128 * half + 64 * c, v);
-        tmem_ld32(tT2 + lane_off + 128 * half + 64 * c + 32, v + 32);
+        float v[32];
+        tmem_ld32(tT2 + lane_off + 64 * part + 32 * c, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
-        store_row_f16((half ? sRE : sRD) + c * kChunk, r, v);
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        if (row_st) store_f16<32>((part >> 1 ? sRE : sRD) + (part & 1) * kChunk, r, 4 * c, v);
       }
-      arrive(F_READY + half);
+      arrive(F_READY + (part >> 1));
       // ---- X3 -> fp16 in RB (A operand of linear_out)
       mbar_wait(bars + R_FULL, rcnt++ & 1u);
       tc_fence_after();
       {
-        float v[64];
-        tmem_ld32(tR + lane_off + 64 * half, v);
-        tmem_ld32(tR + lane_off + 64 * half + 32, v + 32);
+        float v[32];
+        tmem_ld32(tR + lane_off + 32 * part, v);
         tmem_wait_ld();
-        store_row_f16(sRB + half * kChunk, r, v);
+        if (row_st) store_f16<32>(sRB + cchunk * kChunk, r, cu0, v);
       }
       arrive(X3_READY);
-      // ---- y rows of the tile's own query positions -> HBM (32 of the 64 channels per warp half)
+      // ---- y rows of the tile's own query positions -> HBM (16 of the 64 channels per warp)
       mbar_wait(bars + Y_FULL, par);
       tc_fence_after();
       {
-        float v[32];
-        tmem_ld32(tT1 + lane_off + 32 * half, v);
+        float v[16];
+        tmem_ld16(tT1 + lane_off + 16 * part, v);
         tmem_wait_ld();
         const int seq = tile / p.nt, t = tile - seq * p.nt;
         const int b = seq / p.npq, pq = seq - b * p.npq;
@@ -463,9 +497,9 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (row_ok && sg >= qs0 && sg < qs1) {
           const long long tok = (long long)b * p.stride_b + (long long)pi * p.stride_p + (long long)qi * p.stride_q +
                                 (long long)a_idx * p.stride_a + (long long)sg * p.stride_s;
-          float4* dst = reinterpret_cast<float4*>(p.y + tok * p.ld_y + 32 * half);
+          float4* dst = reinterpret_cast<float4*>(p.y + tok * p.ld_y + 16 * part);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
       }
       tc_fence_before();
@@ -532,6 +566,16 @@ static bool geometry_ok(const lfsr_tensor* x, const lfsr_tensor* y, const lfsr_b
   int nt, sq, SL;
   if (!plan(d->A, d->S, d->half_window, &nt, &sq, &SL)) return false;
   if ((long long)d->nb * d->np * d->nq * nt > 0x7fffffffLL) return false;
+  // the two softmax warps of a pair keep <= kGrpPerWarp 16-column groups of their quarter's key window in registers
+  for (int q = 0; q < 4; ++q) {
+    int lo = 1 << 30, hi = 0;
+    for (int r = 32 * q; r < 32 * q + 32 && r < SL * d->A; ++r) {
+      const int sl = r / d->A, w = d->half_window;
+      const int kl = (sl - w > 0 ? sl - w : 0) * d->A, kh = ((sl + w < SL - 1 ? sl + w : SL - 1) + 1) * d->A;
+      lo = kl < lo ? kl : lo; hi = kh > hi ? kh : hi;
+    }
+    if (hi > lo && ((hi + 15) / 16 - lo / 16 + 1) / 2 > kGrpPerWarp) return false;
+  }
   return true;
 }
 
