@@ -40,10 +40,12 @@ constexpr int kGrpPerWarp = 3;              // 16-column score groups a softmax 
 constexpr int kChunk = kRows * 128;         // one K-chunk (64 fp16 / 32 tf32 per row) of a token-row operand: 14 KB
 constexpr int kRegion = 2 * kChunk;         // 28 KB
 constexpr int kVtChunk = 128 * 128, kVtRegion = 2 * kVtChunk;      // V^T: rows are the 128 channels
-constexpr int kSlot = 16384, kSlots = 4;
+constexpr int kSlot = 16384, kSlots = 3;
+constexpr int kMaskBytes = 128 * 64;        // band-mask operands: [128 rows][32 fp16], SWIZZLE_64B K-major, one for A, one for B
+constexpr float kMaskNeg = -30000.f;        // added (log2 domain) to the scores of keys outside the band: exp2 -> 0
 constexpr int kBlocks = 19;                 // weight blocks (16 KB each) per tile, in consumption order
 constexpr int kXchgFloats = 1024;           // LN partial sums [4][128] / softmax partial max + sum [2][2][128] x 2
-constexpr int kSmemBytes = 4 * kRegion + kVtRegion + kSlots * kSlot + kXchgFloats * 4 + 40 * 8 /* barriers */ + 16;
+constexpr int kSmemBytes = 4 * kRegion + kVtRegion + kSlots * kSlot + 2 * kMaskBytes + kXchgFloats * 4 + 40 * 8 /* barriers */ + 16;
 // weight block indices
 constexpr int kWin = 0, kWv = 2, kWq = 4, kWk = 6, kWo = 8, kW1 = 10, kW2 = 14, kWout = 18;
 
@@ -54,8 +56,15 @@ struct Params {
   float* y;
   int ld_y;
   float eps1, eps2, qscale;
+  long long* dbg;                        // probe build only: per-CTA cycle accounting (profiles/probe_bt_phases.py)
   float ln[4][kE];                       // gamma1, beta1, gamma2, beta2 (constant bank: uniform loads in the LN loops)
 };
+
+#ifdef LFSR_DEBUG_HOOKS
+#define BT_MWAIT(i, bar, par_) do { const long long t0_ = clock64(); mbar_wait(bar, par_); if (p.dbg) p.dbg[blockIdx.x * 64 + 32 + (i)] += clock64() - t0_; } while (0)
+#else
+#define BT_MWAIT(i, bar, par_) mbar_wait(bar, par_)
+#endif
 
 enum Bar {
   X_FULL = 0, X_EMPTY, W_FULL, W_EMPTY = W_FULL + kSlots, R_FULL = W_EMPTY + kSlots, VT_FULL, Q_FULL, K_FULL, S_FULL,
@@ -108,7 +117,9 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint8_t* RD = smem + 3 * kRegion;   // K / F chunks 0, 1
   uint8_t* RE = smem + 4 * kRegion;   // V^T (128 channel rows) / F chunks 2, 3
   uint8_t* ring = RE + kVtRegion;
-  float* xchg = reinterpret_cast<float*>(ring + kSlots * kSlot);
+  uint8_t* MA = ring + kSlots * kSlot;          // one-hot(position of the query row)            [128][32] fp16
+  uint8_t* MB = MA + kMaskBytes;                 // 0 / kMaskNeg per (key row, query position)     [128][32] fp16
+  float* xchg = reinterpret_cast<float*>(MB + kMaskBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + kXchgFloats);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
 
@@ -124,6 +135,22 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
   }
+  // The band mask rides on the tensor pipe: S_h = Q_h K_h^T + onehot(s_q) . M^T, where M[key][s] = 0 if the key's position is
+  // within half_window of s (and the key row exists), else kMaskNeg. Two extra K = 16 MMAs per head replace a compare +
+  // select per score element on the CUDA cores. Operands are constants of the launch: built once per CTA.
+  for (int i = threadIdx.x; i < 128 * 32; i += kThreads) {
+    const int row = i >> 5, k = i & 31;
+    const int sl = row / p.A;
+    const bool is_tok = row < p.nrows;
+    const float a = (is_tok && k == sl) ? 1.f : 0.f;
+    const int dk = sl - k;
+    const float b = (is_tok && k < p.SL && dk <= p.w && -dk <= p.w) ? 0.f : kMaskNeg;
+    const uint32_t off = (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 64u +
+                         ((((uint32_t)k >> 3) ^ (((uint32_t)row >> 1) & 3u)) << 4) + ((uint32_t)k & 7u) * 2u;
+    *reinterpret_cast<__half*>(MA + off) = __float2half_rn(a);
+    *reinterpret_cast<__half*>(MB + off) = __float2half_rn(b);
+  }
+  fence_proxy_async();
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -175,31 +202,40 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                      id_pv = make_idesc(0, kHd), id_out = make_idesc(0, kC);
       const uint64_t dRA = make_smem_desc(smem_u32(RA)), dRB = make_smem_desc(smem_u32(RB)), dRC = make_smem_desc(smem_u32(RC)),
                      dRD = make_smem_desc(smem_u32(RD)), dRE = make_smem_desc(smem_u32(RE)), dRing = make_smem_desc(smem_u32(ring));
+      // SWIZZLE_64B K-major descriptors of the mask operands: rows of 64 B, 8-row groups 512 B apart
+      auto desc64 = [](uint32_t saddr) -> uint64_t {
+        return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+               ((uint64_t)4 << 61);
+      };
+      const uint64_t dMA = desc64(smem_u32(MA)), dMB = desc64(smem_u32(MB));
       constexpr uint64_t CH = kChunk >> 4, VCH = kVtChunk >> 4, SL16 = kSlot >> 4;      // descriptor units (16 B)
       auto wslot = [&]() -> uint64_t {             // wait for the next weight block, return its descriptor
         const uint32_t slot = wcnt % kSlots, use = wcnt / kSlots;
-        mbar_wait(bars + W_FULL + slot, use & 1u);
+        BT_MWAIT(0, bars + W_FULL + slot, use & 1u);
         tc_fence_after();
         return dRing + (uint64_t)slot * SL16;
       };
       auto wfree = [&]() { umma_commit(bars + W_EMPTY + (wcnt % kSlots)); ++wcnt; };
       const int pv_steps = p.nkeys >> 4;
+#ifdef LFSR_DEBUG_HOOKS
+      const long long mma_t0 = clock64();
+#endif
       for (int it = 0; it < n_my; ++it) {
         const uint32_t par = (uint32_t)it & 1u;
         // ---- X = x W_in^T (tf32) -> R
-        mbar_wait(bars + X_FULL, par);
+        BT_MWAIT(1, bars + X_FULL, par);
         tc_fence_after();
         { const uint64_t b = wslot(); mma_chunk<true, true>(tR, dRA, b, id_tf32); wfree(); }
         { const uint64_t b = wslot(); mma_chunk<true, false>(tR, dRA + CH, b, id_tf32); wfree(); }
         umma_commit(bars + R_FULL);
         // ---- V^T = Wv X^T -> T1 (as soon as the fp16 copy of X is written, while the epilogue still normalises)
-        mbar_wait(bars + X_READY, par);
+        BT_MWAIT(2, bars + X_READY, par);
         tc_fence_after();
         { const uint64_t a = wslot(); mma_chunk<false, true>(tT1, a, dRA, id_f16); wfree(); }
         { const uint64_t a = wslot(); mma_chunk<false, false>(tT1, a, dRA + CH, id_f16); wfree(); }
         umma_commit(bars + VT_FULL);
         // ---- Q = N Wq^T, K = N Wk^T -> T2
-        mbar_wait(bars + N_READY, par);
+        BT_MWAIT(3, bars + N_READY, par);
         tc_fence_after();
         { const uint64_t b = wslot(); mma_chunk<false, true>(tT2, dRB, b, id_f16); wfree(); }
         { const uint64_t b = wslot(); mma_chunk<false, false>(tT2, dRB + CH, b, id_f16); wfree(); }
@@ -209,12 +245,15 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         umma_commit(bars + K_FULL);
         // ---- attention: S_h = Q_h K_h^T (one K = 16 MMA) into one of THREE score buffers, so the next head of each warp
         // pair is always ready; softmax by the epilogue; O_h = P_h V_h into the 16-column O buffer of its warp pair
-        mbar_wait(bars + QKV_READY, par);
+        BT_MWAIT(4, bars + QKV_READY, par);
         tc_fence_after();
         auto issue_s = [&](int h) {
           const int b = h % 3;
           const uint64_t off = (uint64_t)(h >> 2) * CH + (uint64_t)(2 * (h & 3));
-          umma_f16<0>(b == 2 ? tT1 : tT2 + 112 * b, dRC + off, dRD + off, id_s);
+          const uint32_t ts = b == 2 ? tT1 : tT2 + 112 * b;
+          umma_f16<0>(ts, dRC + off, dRD + off, id_s);
+          umma_f16<1>(ts, dMA, dMB, id_s);
+          umma_f16<1>(ts, dMA + 2, dMB + 2, id_s);
           umma_commit(bars + S_FULL + b);
         };
         issue_s(0);
@@ -222,7 +261,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         issue_s(2);
         for (int h = 0; h < kHeads; ++h) {
           const int j = h & 1;
-          mbar_wait(bars + P_FULL + j, (uint32_t)(h >> 1) & 1u);
+          BT_MWAIT(5, bars + P_FULL + j, (uint32_t)(h >> 1) & 1u);
           tc_fence_after();
           const uint64_t pa = j ? dRA : dRB;
           const uint64_t vb = dRE + (uint64_t)(h * kHd * 128 >> 4);      // rows 16h.. of V^T (N = 16)
@@ -237,13 +276,13 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         umma_commit(bars + X_EMPTY);
         // ---- X2 = X + O Wo^T (accumulate into R)
-        mbar_wait(bars + O_READY, par);
+        BT_MWAIT(6, bars + O_READY, par);
         tc_fence_after();
         { const uint64_t b = wslot(); mma_chunk<false, false>(tR, dRC, b, id_f16); wfree(); }
         { const uint64_t b = wslot(); mma_chunk<false, false>(tR, dRC + CH, b, id_f16); wfree(); }
         umma_commit(bars + R_FULL);
         // ---- F = N2 W1^T -> T2 (two halves of 128 columns)
-        mbar_wait(bars + N2_READY, par);
+        BT_MWAIT(7, bars + N2_READY, par);
         tc_fence_after();
         for (int n = 0; n < 2; ++n) {
           { const uint64_t b = wslot(); mma_chunk<false, true>(tT2 + 128 * n, dRB, b, id_f16); wfree(); }
@@ -252,7 +291,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         // ---- X3 = X2 + relu(F) W2^T (accumulate into R); K = 256 in four chunks (RD, RD + chunk, RE, RE + chunk)
         for (int n = 0; n < 2; ++n) {
-          mbar_wait(bars + F_READY + n, par);
+          BT_MWAIT(8, bars + F_READY + n, par);
           tc_fence_after();
           const uint64_t fa = n ? dRE : dRD;
           { const uint64_t b = wslot(); mma_chunk<false, false>(tR, fa, b, id_f16); wfree(); }
@@ -260,7 +299,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         umma_commit(bars + R_FULL);
         // ---- y = X3 Wout^T -> T1[0..63]; the slot holds both K-chunks of Wout (64 rows x 128 B each)
-        mbar_wait(bars + X3_READY, par);
+        BT_MWAIT(9, bars + X3_READY, par);
         tc_fence_after();
         {
           const uint64_t b = wslot();
@@ -270,6 +309,9 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         umma_commit(bars + Y_FULL);
       }
+#ifdef LFSR_DEBUG_HOOKS
+      if (p.dbg) { p.dbg[blockIdx.x * 64 + 32 + 15] = clock64() - mma_t0; p.dbg[blockIdx.x * 64 + 32 + 14] = n_my; }
+#endif
     }
     __syncwarp();
   } else {
@@ -302,26 +344,41 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     };
     // LayerNorm over the 128 columns of R: this warp owns 32 of them, the other three warps of the lane quarter the rest
     auto layer_norm = [&](float* v, const float* g, const float* bta, float eps) {
-      float s0 = 0.f, s1 = 0.f;
+      f2 acc = f2_pack(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) { s0 += v[i]; s1 += v[i + 1]; }
+      for (int i = 0; i < 32; i += 2) acc = f2_add(acc, f2_pack(v[i], v[i + 1]));
+      float s0, s1;
+      f2_unpack(acc, s0, s1);
       xchg[part * 128 + r] = s0 + s1;
       named_bar_sync(1 + q, 128);
       const float mean = (xchg[r] + xchg[128 + r] + xchg[256 + r] + xchg[384 + r]) * (1.f / kE);
       named_bar_sync(1 + q, 128);
-      s0 = 0.f; s1 = 0.f;
+      const f2 nm = f2_pack(-mean, -mean);
+      acc = f2_pack(0.f, 0.f);
+      f2 d[16];
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        v[i] -= mean; v[i + 1] -= mean;
-        s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
+      for (int i = 0; i < 16; ++i) {
+        d[i] = f2_add(f2_pack(v[2 * i], v[2 * i + 1]), nm);
+        acc = f2_fma(d[i], d[i], acc);
       }
+      f2_unpack(acc, s0, s1);
       xchg[part * 128 + r] = s0 + s1;
       named_bar_sync(1 + q, 128);
       const float rstd = rsqrtf((xchg[r] + xchg[128 + r] + xchg[256 + r] + xchg[384 + r]) * (1.f / kE) + eps);
       named_bar_sync(1 + q, 128);
+      const f2 rs = f2_pack(rstd, rstd);
+      const f2* g2 = reinterpret_cast<const f2*>(g + 32 * part);
+      const f2* b2 = reinterpret_cast<const f2*>(bta + 32 * part);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i] * rstd, g[32 * part + i], bta[32 * part + i]);
+      for (int i = 0; i < 16; ++i) f2_unpack(f2_fma(f2_mul(d[i], rs), g2[i], b2[i]), v[2 * i], v[2 * i + 1]);
     };
+#ifdef LFSR_DEBUG_HOOKS
+    long long t_prev = clock64();
+    const bool prober = p.dbg && warp == 0 && lane == 0;
+#define BT_TICK(i) do { if (prober) { const long long t_ = clock64(); p.dbg[blockIdx.x * 64 + (i)] += t_ - t_prev; t_prev = t_; } } while (0)
+#else
+#define BT_TICK(i) do { } while (0)
+#endif
     const int cchunk = part >> 1, cu0 = 4 * (part & 1);   // this warp's 32 columns of a 128-column operand: chunk, first unit
 
     for (int it = 0; it < n_my; ++it) {
@@ -329,6 +386,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       // ---- X -> fp16 X (B operand of the V^T GEMM), then N = LN1(X) (A operand of the Q / K GEMMs)
       mbar_wait(bars + R_FULL, rcnt++ & 1u);
+      BT_TICK(0);
       tc_fence_after();
       {
         float v[32];
@@ -340,8 +398,10 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (row_st) { if (row_ok) store_f16<32>(sRB + cchunk * kChunk, r, cu0, v); else store_zero<32>(sRB + cchunk * kChunk, r, cu0); }
       }
       arrive(N_READY);
+      BT_TICK(1);
       // ---- V^T rows (lane = channel, columns = tokens) -> RE ; Q (scaled, exp2 domain) -> RC ; K -> RD
       mbar_wait(bars + VT_FULL, par);
+      BT_TICK(2);
       tc_fence_after();
       {
         float v[32];
@@ -349,7 +409,9 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tmem_wait_ld();
         store_f16<32>(sRE + cchunk * kVtChunk, r, cu0, v);
       }
+      BT_TICK(3);
       mbar_wait(bars + Q_FULL, par);
+      BT_TICK(4);
       tc_fence_after();
       {
         float v[32];
@@ -359,7 +421,9 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int i = 0; i < 32; ++i) v[i] *= p.qscale;
         if (row_st) store_f16<32>(sRC + cchunk * kChunk, r, cu0, v);
       }
+      BT_TICK(5);
       mbar_wait(bars + K_FULL, par);
+      BT_TICK(6);
       tc_fence_after();
       {
         float v[32];
@@ -368,6 +432,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (row_st) store_f16<32>(sRD + cchunk * kChunk, r, cu0, v);
       }
       arrive(QKV_READY);
+      BT_TICK(7);
       // ---- softmax of this pair's heads (pair, pair + 2, ..): S in TMEM -> un-normalised exp2 as fp16 P in shared memory;
       // the O columns of the pair's previous head are drained (scaled by 1 / rowsum) as soon as its P.V has retired
       const uint32_t sP = pair ? sRA : sRB;
@@ -394,7 +459,9 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int k = 0; k < 4; ++k) {
         const int h = 2 * k + pair, b = h % 3;
         // completions of score buffer b before this head: (3, 3, 2) per tile for b = (0, 1, 2)
+        BT_TICK(8);
         mbar_wait(bars + S_FULL + b, (uint32_t)(it * (b == 2 ? 2 : 3) + h / 3) & 1u);
+        BT_TICK(9);
         tc_fence_after();
         const uint32_t tS = (b == 2 ? tT1 : tT2 + 112 * b) + lane_off;
         float s[16 * kGrpPerWarp];
@@ -402,51 +469,60 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int i = 0; i < kGrpPerWarp; ++i)
           if (g0 + i < g1) tmem_ld16(tS + (g0 + i) * 16, s + 16 * i);
         tmem_wait_ld();
+        // (the band mask is already in the scores: keys outside the band sit ~30000 below the row maximum)
         float m0 = -1e30f, m1 = -1e30f;
 #pragma unroll
         for (int i = 0; i < kGrpPerWarp; ++i)
           if (g0 + i < g1) {
-            const int cb = (g0 + i) * 16 - k_lo;
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              const float x0 = ((unsigned)(cb + j) < (unsigned)(k_hi - k_lo)) ? s[16 * i + j] : -INFINITY;
-              const float x1 = ((unsigned)(cb + j + 1) < (unsigned)(k_hi - k_lo)) ? s[16 * i + j + 1] : -INFINITY;
-              s[16 * i + j] = x0; s[16 * i + j + 1] = x1;
-              m0 = fmaxf(m0, x0); m1 = fmaxf(m1, x1);
+            for (int j = 0; j < 16; j += 4) {
+              m0 = fmaxf(m0, fmaxf(s[16 * i + j], s[16 * i + j + 1]));
+              m1 = fmaxf(m1, fmaxf(s[16 * i + j + 2], s[16 * i + j + 3]));
             }
           }
         // P.V of the pair's previous head has retired: its O columns can be drained and P / the exchange slots reused
+        BT_TICK(10);
         mbar_wait(bars + P_EMPTY + pair, ((uint32_t)k & 1u) ^ 1u);
+        BT_TICK(11);
         tc_fence_after();
         named_bar_sync(5 + 2 * q + pair, 64);              // the partner's psum of the previous head is visible
         if (k > 0) drain_o(h - 2);
         pmax[sub * 128 + r] = fmaxf(m0, m1);
         named_bar_sync(5 + 2 * q + pair, 64);
         const float m = fmaxf(pmax[r], pmax[128 + r]);
-        float a0 = 0.f, a1 = 0.f;
+        const f2 negm = f2_pack(-m, -m);
+        f2 acc = f2_pack(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < kGrpPerWarp; ++i)
           if (g0 + i < g1) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              const float e0 = ex2_approx(s[16 * i + j] - m), e1 = ex2_approx(s[16 * i + j + 1] - m);
+              float t0, t1;
+              f2_unpack(f2_add(f2_pack(s[16 * i + j], s[16 * i + j + 1]), negm), t0, t1);
+              const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
               s[16 * i + j] = e0; s[16 * i + j + 1] = e1;
-              a0 += e0; a1 += e1;
+              acc = f2_add(acc, f2_pack(e0, e1));
             }
             if (row_st) store_f16<16>(sP + ((g0 + i) >> 2) * kChunk, r, 2 * ((g0 + i) & 3), s + 16 * i);
           }
+        float a0, a1;
+        f2_unpack(acc, a0, a1);
         for (int g = z0; g < z1; ++g)
           if (row_st) store_zero<16>(sP + (g >> 2) * kChunk, r, 2 * (g & 3));
         psum[sub * 128 + r] = a0 + a1;
         arrive(P_FULL + pair);
       }
+      BT_TICK(8);
       mbar_wait(bars + P_EMPTY + pair, 1u);                // 5th wait of the tile: completion 4*it + 3
+      BT_TICK(12);
       tc_fence_after();
       named_bar_sync(5 + 2 * q + pair, 64);                // the partner's last psum is visible
       drain_o(6 + pair);
       arrive(O_READY);
+      BT_TICK(13);
       // ---- N2 = LN2(X2) -> RB
       mbar_wait(bars + R_FULL, rcnt++ & 1u);
+      BT_TICK(14);
       tc_fence_after();
       {
         float v[32];
@@ -456,8 +532,10 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (row_st) store_f16<32>(sRB + cchunk * kChunk, r, cu0, v);
       }
       arrive(N2_READY);
+      BT_TICK(15);
       // ---- relu(F): this warp's 64 of the 256 columns -> K-chunk `part` of the FFN operand (RD: 0, 1; RE: 2, 3)
       mbar_wait(bars + F_FULL + (part >> 1), par);
+      BT_TICK(16);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -469,8 +547,10 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (row_st) store_f16<32>((part >> 1 ? sRE : sRD) + (part & 1) * kChunk, r, 4 * c, v);
       }
       arrive(F_READY + (part >> 1));
+      BT_TICK(17);
       // ---- X3 -> fp16 in RB (A operand of linear_out)
       mbar_wait(bars + R_FULL, rcnt++ & 1u);
+      BT_TICK(18);
       tc_fence_after();
       {
         float v[32];
@@ -479,8 +559,10 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (row_st) store_f16<32>(sRB + cchunk * kChunk, r, cu0, v);
       }
       arrive(X3_READY);
+      BT_TICK(19);
       // ---- y rows of the tile's own query positions -> HBM (16 of the 64 channels per warp)
       mbar_wait(bars + Y_FULL, par);
+      BT_TICK(20);
       tc_fence_after();
       {
         float v[16];
@@ -503,6 +585,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
       }
       tc_fence_before();
+      BT_TICK(21);
     }
   }
   tc_fence_before();
@@ -645,6 +728,7 @@ extern "C" int lfsr_epit_basictrans(const lfsr_tensor* x, const void* packed, co
   p.y = (float*)y->ptr; p.ld_y = y->ld;
   p.eps1 = d->eps1; p.eps2 = d->eps2;
   p.qscale = 1.4426950408889634f / sqrtf((float)kHd);
+  p.dbg = dbg_env("LFSR_BT_DBG_PTR") ? (long long*)strtoull(dbg_env("LFSR_BT_DBG_PTR"), nullptr, 0) : nullptr;
   memcpy(p.ln[0], d->ln1_g, sizeof(float) * kE); memcpy(p.ln[1], d->ln1_b, sizeof(float) * kE);
   memcpy(p.ln[2], d->ln2_g, sizeof(float) * kE); memcpy(p.ln[3], d->ln2_b, sizeof(float) * kE);
   const long long T = (long long)x->n * x->h * x->w;
