@@ -67,7 +67,7 @@ struct Params {
 #endif
 
 enum Bar {
-  X_FULL = 0, X_EMPTY, W_FULL, W_EMPTY = W_FULL + kSlots, R_FULL = W_EMPTY + kSlots, VT_FULL, Q_FULL, K_FULL, S_FULL,
+  X_FULL = 0, X_EMPTY, W_FULL, W_EMPTY = W_FULL + kSlots, R_FULL = W_EMPTY + kSlots, VT_FULL, K_FULL, S_FULL,
   P_EMPTY = S_FULL + 3, F_FULL = P_EMPTY + 2, Y_FULL = F_FULL + 2,
   // arrivals of the epilogue warps
   X_READY, N_READY, QKV_READY, P_FULL, O_READY = P_FULL + 2, N2_READY, F_READY, X3_READY = F_READY + 2, NUM_BARS
@@ -107,7 +107,7 @@ __device__ __forceinline__ void mma_chunk(uint32_t d, uint64_t a, uint64_t b, ui
 
 __global__ void __launch_bounds__(kThreads, 1)
 basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                  const __grid_constant__ Params p) {
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -134,6 +134,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_barrier_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmY);
   }
   // The band mask rides on the tensor pipe: S_h = Q_h K_h^T + onehot(s_q) . M^T, where M[key][s] = 0 if the key's position is
   // within half_window of s (and the key row exists), else kMaskNeg. Two extra K = 16 MMAs per head replace a compare +
@@ -239,7 +240,6 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tc_fence_after();
         { const uint64_t b = wslot(); mma_chunk<false, true>(tT2, dRB, b, id_f16); wfree(); }
         { const uint64_t b = wslot(); mma_chunk<false, false>(tT2, dRB + CH, b, id_f16); wfree(); }
-        umma_commit(bars + Q_FULL);
         { const uint64_t b = wslot(); mma_chunk<false, true>(tT2 + 128, dRB, b, id_f16); wfree(); }
         { const uint64_t b = wslot(); mma_chunk<false, false>(tT2 + 128, dRB + CH, b, id_f16); wfree(); }
         umma_commit(bars + K_FULL);
@@ -259,6 +259,13 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         issue_s(0);
         issue_s(1);
         issue_s(2);
+        // X2 = X + O Wo^T is accumulated into R head by head while the attention runs: O_h (written into the slot of the
+        // dead Q_h by the warps that later arrive on P_FULL of head h + 2) times the 16 matching K-columns of Wo
+        uint64_t wo = 0;
+        auto issue_wo = [&](int hh) {
+          const uint64_t ko = (uint64_t)(2 * (hh & 3));
+          umma_f16<1>(tR, dRC + (uint64_t)(hh >> 2) * CH + ko, wo + ko, id_f16);
+        };
         for (int h = 0; h < kHeads; ++h) {
           const int j = h & 1;
           BT_MWAIT(5, bars + P_FULL + j, (uint32_t)(h >> 1) & 1u);
@@ -273,13 +280,18 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           }
           umma_commit(bars + P_EMPTY + j);
           if (h + 3 < kHeads) issue_s(h + 3);           // its buffer was read by the softmax of head h (done: P_h is full)
+          if (h >= 2) {
+            if (h == 2 || h == 6) wo = wslot();          // Wo K-chunk 0 (heads 0..3) / 1 (heads 4..7)
+            issue_wo(h - 2);
+            if (h == 5) wfree();
+          }
         }
         umma_commit(bars + X_EMPTY);
-        // ---- X2 = X + O Wo^T (accumulate into R)
         BT_MWAIT(6, bars + O_READY, par);
         tc_fence_after();
-        { const uint64_t b = wslot(); mma_chunk<false, false>(tR, dRC, b, id_f16); wfree(); }
-        { const uint64_t b = wslot(); mma_chunk<false, false>(tR, dRC + CH, b, id_f16); wfree(); }
+        issue_wo(6);
+        issue_wo(7);
+        wfree();
         umma_commit(bars + R_FULL);
         // ---- F = N2 W1^T -> T2 (two halves of 128 columns)
         BT_MWAIT(7, bars + N2_READY, par);
@@ -343,34 +355,38 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (lane == 0) mbar_arrive(bars + bar);
     };
     // LayerNorm over the 128 columns of R: this warp owns 32 of them, the other three warps of the lane quarter the rest
+    // Each warp reduces its 32 columns to (mean_i, M2_i) locally; the four partials of a row are merged like Welford / Chan
+    // (mean = sum mean_i / 4, M2 = sum M2_i + 32 sum (mean_i - mean)^2): numerically as robust as two passes over the row,
+    // with one exchange through shared memory and one named barrier instead of four.
     auto layer_norm = [&](float* v, const float* g, const float* bta, float eps) {
       f2 acc = f2_pack(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < 32; i += 2) acc = f2_add(acc, f2_pack(v[i], v[i + 1]));
       float s0, s1;
       f2_unpack(acc, s0, s1);
-      xchg[part * 128 + r] = s0 + s1;
-      named_bar_sync(1 + q, 128);
-      const float mean = (xchg[r] + xchg[128 + r] + xchg[256 + r] + xchg[384 + r]) * (1.f / kE);
-      named_bar_sync(1 + q, 128);
-      const f2 nm = f2_pack(-mean, -mean);
+      const float mloc = (s0 + s1) * (1.f / 32.f);
+      const f2 nml = f2_pack(-mloc, -mloc);
       acc = f2_pack(0.f, 0.f);
-      f2 d[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        d[i] = f2_add(f2_pack(v[2 * i], v[2 * i + 1]), nm);
-        acc = f2_fma(d[i], d[i], acc);
+        const f2 d = f2_add(f2_pack(v[2 * i], v[2 * i + 1]), nml);
+        acc = f2_fma(d, d, acc);
       }
       f2_unpack(acc, s0, s1);
-      xchg[part * 128 + r] = s0 + s1;
+      reinterpret_cast<float2*>(xchg)[part * 128 + r] = make_float2(mloc, s0 + s1);
       named_bar_sync(1 + q, 128);
-      const float rstd = rsqrtf((xchg[r] + xchg[128 + r] + xchg[256 + r] + xchg[384 + r]) * (1.f / kE) + eps);
-      named_bar_sync(1 + q, 128);
-      const f2 rs = f2_pack(rstd, rstd);
+      const float2 e0 = reinterpret_cast<const float2*>(xchg)[r], e1 = reinterpret_cast<const float2*>(xchg)[128 + r];
+      const float2 e2 = reinterpret_cast<const float2*>(xchg)[256 + r], e3 = reinterpret_cast<const float2*>(xchg)[384 + r];
+      const float mean = (e0.x + e1.x + e2.x + e3.x) * 0.25f;
+      const float d0 = e0.x - mean, d1 = e1.x - mean, d2 = e2.x - mean, d3 = e3.x - mean;
+      const float m2 = (e0.y + e1.y + e2.y + e3.y) + 32.f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
+      const float rstd = rsqrtf(m2 * (1.f / kE) + eps);
+      const f2 rs = f2_pack(rstd, rstd), nmr = f2_pack(-mean * rstd, -mean * rstd);
       const f2* g2 = reinterpret_cast<const f2*>(g + 32 * part);
       const f2* b2 = reinterpret_cast<const f2*>(bta + 32 * part);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) f2_unpack(f2_fma(f2_mul(d[i], rs), g2[i], b2[i]), v[2 * i], v[2 * i + 1]);
+      for (int i = 0; i < 16; ++i)
+        f2_unpack(f2_fma(f2_fma(f2_pack(v[2 * i], v[2 * i + 1]), rs, nmr), g2[i], b2[i]), v[2 * i], v[2 * i + 1]);
     };
 #ifdef LFSR_DEBUG_HOOKS
     long long t_prev = clock64();
@@ -394,6 +410,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tmem_wait_ld();
         if (row_st) { if (row_ok) store_f16<32>(sRA + cchunk * kChunk, r, cu0, v); else store_zero<32>(sRA + cchunk * kChunk, r, cu0); }
         arrive(X_READY);
+        if (warp == 0 && lane == 0) bulk_wait_read0();      // the y store of the previous tile has finished reading RC
         layer_norm(v, p.ln[0], p.ln[1], p.eps1);
         if (row_st) { if (row_ok) store_f16<32>(sRB + cchunk * kChunk, r, cu0, v); else store_zero<32>(sRB + cchunk * kChunk, r, cu0); }
       }
@@ -410,26 +427,17 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         store_f16<32>(sRE + cchunk * kVtChunk, r, cu0, v);
       }
       BT_TICK(3);
-      mbar_wait(bars + Q_FULL, par);
       BT_TICK(4);
-      tc_fence_after();
-      {
-        float v[32];
-        tmem_ld32(tT2 + lane_off + 32 * part, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= p.qscale;
-        if (row_st) store_f16<32>(sRC + cchunk * kChunk, r, cu0, v);
-      }
       BT_TICK(5);
       mbar_wait(bars + K_FULL, par);
       BT_TICK(6);
       tc_fence_after();
       {
-        float v[32];
-        tmem_ld32(tT2 + lane_off + 128 + 32 * part, v);
+        float v[32], u[32];
+        tmem_ld32(tT2 + lane_off + 32 * part, v);                 // Q (1/sqrt(d) and log2 e are folded into Wq)
+        tmem_ld32(tT2 + lane_off + 128 + 32 * part, u);           // K
         tmem_wait_ld();
-        if (row_st) store_f16<32>(sRD + cchunk * kChunk, r, cu0, v);
+        if (row_st) { store_f16<32>(sRC + cchunk * kChunk, r, cu0, v); store_f16<32>(sRD + cchunk * kChunk, r, cu0, u); }
       }
       arrive(QKV_READY);
       BT_TICK(7);
@@ -464,51 +472,69 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         BT_TICK(9);
         tc_fence_after();
         const uint32_t tS = (b == 2 ? tT1 : tT2 + 112 * b) + lane_off;
-        float s[16 * kGrpPerWarp];
-#pragma unroll
-        for (int i = 0; i < kGrpPerWarp; ++i)
-          if (g0 + i < g1) tmem_ld16(tS + (g0 + i) * 16, s + 16 * i);
-        tmem_wait_ld();
-        // (the band mask is already in the scores: keys outside the band sit ~30000 below the row maximum)
+        // pass 1: row maximum over this warp's key groups (the band mask is already in the scores: keys outside the band sit
+        // ~30000 below the row maximum). The scores are NOT kept: pass 2 re-reads them from TMEM group by group, so that
+        // only the packed fp16 exponentials (8 registers per group) stay live across the exchange and the P_EMPTY wait.
         float m0 = -1e30f, m1 = -1e30f;
+        {
+          float s[16 * kGrpPerWarp];
+#pragma unroll
+          for (int i = 0; i < kGrpPerWarp; ++i)       // (unconditional, clamped: keeps the array in registers)
+            tmem_ld16(tS + (g0 + i < ngrp ? g0 + i : ngrp - 1) * 16, s + 16 * i);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < kGrpPerWarp; ++i)
+            if (g0 + i < g1) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                m0 = fmaxf(m0, fmaxf(s[16 * i + j], s[16 * i + j + 1]));
+                m1 = fmaxf(m1, fmaxf(s[16 * i + j + 2], s[16 * i + j + 3]));
+              }
+            }
+        }
+        pmax[sub * 128 + r] = fmaxf(m0, m1);
+        named_bar_sync(5 + 2 * q + pair, 64);              // (also: the partner has finished the previous head entirely)
+        const float m = fmaxf(pmax[r], pmax[128 + r]);
+        const f2 negm = f2_pack(-m, -m);
+        f2 acc = f2_pack(0.f, 0.f);
+        uint32_t ph[8 * kGrpPerWarp];
+#pragma unroll
+        for (int i = 0; i < 8 * kGrpPerWarp; ++i) ph[i] = 0u;
 #pragma unroll
         for (int i = 0; i < kGrpPerWarp; ++i)
           if (g0 + i < g1) {
+            float s[16];
+            tmem_ld16(tS + (g0 + i) * 16, s);
+            tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              m0 = fmaxf(m0, fmaxf(s[16 * i + j], s[16 * i + j + 1]));
-              m1 = fmaxf(m1, fmaxf(s[16 * i + j + 2], s[16 * i + j + 3]));
+            for (int j = 0; j < 16; j += 2) {
+              float t0, t1;
+              f2_unpack(f2_add(f2_pack(s[j], s[j + 1]), negm), t0, t1);
+              const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+              ph[8 * i + (j >> 1)] = pack_f16x2(e0, e1);
+              acc = f2_add(acc, f2_pack(e0, e1));
             }
           }
-        // P.V of the pair's previous head has retired: its O columns can be drained and P / the exchange slots reused
+        float a0, a1;
+        f2_unpack(acc, a0, a1);
+        // only now is the P buffer needed: P.V of the pair's previous head has retired -> drain its O columns, reuse P / psum
         BT_TICK(10);
         mbar_wait(bars + P_EMPTY + pair, ((uint32_t)k & 1u) ^ 1u);
         BT_TICK(11);
         tc_fence_after();
-        named_bar_sync(5 + 2 * q + pair, 64);              // the partner's psum of the previous head is visible
         if (k > 0) drain_o(h - 2);
-        pmax[sub * 128 + r] = fmaxf(m0, m1);
-        named_bar_sync(5 + 2 * q + pair, 64);
-        const float m = fmaxf(pmax[r], pmax[128 + r]);
-        const f2 negm = f2_pack(-m, -m);
-        f2 acc = f2_pack(0.f, 0.f);
+        named_bar_sync(5 + 2 * q + pair, 64);              // both warps have read psum / pmax of the previous round
 #pragma unroll
         for (int i = 0; i < kGrpPerWarp; ++i)
-          if (g0 + i < g1) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              float t0, t1;
-              f2_unpack(f2_add(f2_pack(s[16 * i + j], s[16 * i + j + 1]), negm), t0, t1);
-              const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
-              s[16 * i + j] = e0; s[16 * i + j + 1] = e1;
-              acc = f2_add(acc, f2_pack(e0, e1));
-            }
-            if (row_st) store_f16<16>(sP + ((g0 + i) >> 2) * kChunk, r, 2 * ((g0 + i) & 3), s + 16 * i);
+          if (g0 + i < g1 && row_st) {
+            const uint32_t rb = sP + (uint32_t)((g0 + i) >> 2) * kChunk + (uint32_t)r * 128u;
+            const uint32_t u0 = (uint32_t)(2 * ((g0 + i) & 3)), sw = (uint32_t)(r & 7);
+            st_shared_v4(rb + ((u0 ^ sw) << 4), ph[8 * i], ph[8 * i + 1], ph[8 * i + 2], ph[8 * i + 3]);
+            st_shared_v4(rb + (((u0 + 1) ^ sw) << 4), ph[8 * i + 4], ph[8 * i + 5], ph[8 * i + 6], ph[8 * i + 7]);
           }
-        float a0, a1;
-        f2_unpack(acc, a0, a1);
-        for (int g = z0; g < z1; ++g)
-          if (row_st) store_zero<16>(sP + (g >> 2) * kChunk, r, 2 * (g & 3));
+        if (k == 0)               // key groups outside this quarter's window are only ever written here: once per tile
+          for (int g = z0; g < z1; ++g)
+            if (row_st) store_zero<16>(sP + (g >> 2) * kChunk, r, 2 * (g & 3));
         psum[sub * 128 + r] = a0 + a1;
         arrive(P_FULL + pair);
       }
@@ -560,7 +586,8 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       arrive(X3_READY);
       BT_TICK(19);
-      // ---- y rows of the tile's own query positions -> HBM (16 of the 64 channels per warp)
+      // ---- y rows of the tile's own query positions: staged as fp32 [rows][32] x 2 chunks (SWIZZLE_128B) in RC (O is dead),
+      // then ONE lane hands the two boxes to the TMA unit (same 5-D addressing as the input tile, clipped to the tensor)
       mbar_wait(bars + Y_FULL, par);
       BT_TICK(20);
       tc_fence_after();
@@ -570,24 +597,33 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tmem_wait_ld();
         const int seq = tile / p.nt, t = tile - seq * p.nt;
         const int b = seq / p.npq, pq = seq - b * p.npq;
-        const int pi = pq / p.nq, qi = pq - pi * p.nq;
         int ls0 = t * p.sq - p.w;
         if (ls0 < 0) ls0 = 0;
         if (ls0 > p.S - p.SL) ls0 = p.S - p.SL;
-        const int sg = ls0 + s_loc;
-        const int qs0 = t * p.sq, qs1 = qs0 + p.sq < p.S ? qs0 + p.sq : p.S;
-        if (row_ok && sg >= qs0 && sg < qs1) {
-          const long long tok = (long long)b * p.stride_b + (long long)pi * p.stride_p + (long long)qi * p.stride_q +
-                                (long long)a_idx * p.stride_a + (long long)sg * p.stride_s;
-          float4* dst = reinterpret_cast<float4*>(p.y + tok * p.ld_y + 16 * part);
+        const int qs0 = t * p.sq;
+        const int rq = r - (qs0 - ls0) * p.A;                 // row inside the query block
+        if (rq >= 0 && rq < p.sq * p.A) {
+          const uint32_t rb = sRC + (uint32_t)(part >> 1) * kChunk + (uint32_t)rq * 128u;
+          const uint32_t sw = (uint32_t)(rq & 7);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < 4; ++i)
+            st_shared_v4(rb + ((((uint32_t)(4 * (part & 1) + i)) ^ sw) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                         __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        named_bar_sync(13, 32 * kEpiWarps);
+        if (warp == 0 && lane == 0) {
+          tma_store_5d(&tmY, RC, 0, 0, qs0, pq, b);
+          tma_store_5d(&tmY, RC + kChunk, 32, 0, qs0, pq, b);
+          bulk_commit();
         }
       }
       tc_fence_before();
       BT_TICK(21);
     }
   }
+  if (warp == 0 && lane == 0) bulk_wait0();                 // all y stores have landed
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -691,7 +727,13 @@ extern "C" int lfsr_pack_basictrans(const float* w_in, const float* w_qkv, const
           blk_f16(blk0 + c)[o * 64 + k] = __float2half_rn(w[(size_t)(row0 + o) * in_dim + 64 * c + k]);
   };
   pack_f16(kWv, w_qkv, 2 * kE, kE, kE, 2);
-  pack_f16(kWq, w_qkv, 0, kE, kE, 2);
+  {   // Wq with 1/sqrt(head_dim) (MultiheadAttention scales q) and log2(e) (the softmax runs on exp2) folded in
+    const float qscale = 1.4426950408889634f / sqrtf((float)kHd);
+    for (int c = 0; c < 2; ++c)
+      for (int o = 0; o < kE; ++o)
+        for (int k = 0; k < 64; ++k)
+          blk_f16(kWq + c)[o * 64 + k] = __float2half_rn(w_qkv[(size_t)o * kE + 64 * c + k] * qscale);
+  }
   pack_f16(kWk, w_qkv, kE, kE, kE, 2);
   pack_f16(kWo, w_o, 0, kE, kE, 2);
   pack_f16(kW1, w_ff1, 0, kE, kE, 2);
@@ -759,6 +801,18 @@ extern "C" int lfsr_epit_basictrans(const lfsr_tensor* x, const void* packed, co
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("lfsr_epit_basictrans: cuTensorMapEncodeTiled(w) failed with %d", (int)r); return LFSR_ERR_CUDA; }
   }
+  CUtensorMap tmY;
+  {
+    const cuuint64_t ld_b = (cuuint64_t)y->ld * 4;
+    cuuint64_t dims[5] = {(cuuint64_t)kC, (cuuint64_t)p.A, (cuuint64_t)p.S, (cuuint64_t)p.npq, (cuuint64_t)d->nb};
+    cuuint64_t strides[4] = {ld_b * (cuuint64_t)d->stride_a, ld_b * (cuuint64_t)d->stride_s, ld_b * (cuuint64_t)d->stride_q,
+                             ld_b * (cuuint64_t)d->stride_b};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.A, (cuuint32_t)p.sq, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, y->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("lfsr_epit_basictrans: cuTensorMapEncodeTiled(y) failed with %d", (int)r); return LFSR_ERR_CUDA; }
+  }
   const int smem = kSmemBytes + 1024;
   static DevOnce once;
   if (once.need()) {
@@ -767,6 +821,6 @@ extern "C" int lfsr_epit_basictrans(const lfsr_tensor* x, const void* packed, co
   }
   const int sms = sm_count_current();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  basictrans_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmX, tmW, p);
+  basictrans_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmX, tmW, tmY, p);
   return check_launch("basictrans_kernel");
 }
