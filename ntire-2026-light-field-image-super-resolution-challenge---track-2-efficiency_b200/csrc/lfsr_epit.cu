@@ -40,11 +40,12 @@ constexpr int kGrpPerWarp = 3;              // 16-column score groups a softmax 
 constexpr int kChunk = kRows * 128;         // one K-chunk (64 fp16 / 32 tf32 per row) of a token-row operand: 14 KB
 constexpr int kRegion = 2 * kChunk;         // 28 KB
 constexpr int kVtChunk = 128 * 128, kVtRegion = 2 * kVtChunk;      // V^T: rows are the 128 channels
-constexpr int kSlot = 16384, kSlots = 3;
-constexpr int kMaskBytes = 128 * 64;        // band-mask operands: [128 rows][32 fp16], SWIZZLE_64B K-major, one for A, one for B
+constexpr int kSlot = 16384, kSlots = 4;
+constexpr int kMaskBytes = kRows * 64;      // band-mask operands: [112 rows][32 fp16], SWIZZLE_64B K-major, one for A, one for B
+                                            // (the M = 128 MMA reads 16 more A rows: whatever follows, they only reach unused lanes)
 constexpr float kMaskNeg = -30000.f;        // added (log2 domain) to the scores of keys outside the band: exp2 -> 0
 constexpr int kBlocks = 19;                 // weight blocks (16 KB each) per tile, in consumption order
-constexpr int kXchgFloats = 1024;           // LN partial sums [4][128] / softmax partial max + sum [2][2][128] x 2
+constexpr int kXchgFloats = 8 * kRows;      // LN partials [4 parts][112 rows] float2 / softmax partial max, sum [2 pairs][2][112] each
 constexpr int kSmemBytes = 4 * kRegion + kVtRegion + kSlots * kSlot + 2 * kMaskBytes + kXchgFloats * 4 + 40 * 8 /* barriers */ + 16;
 // weight block indices
 constexpr int kWin = 0, kWv = 2, kWq = 4, kWk = 6, kWo = 8, kW1 = 10, kW2 = 14, kWout = 18;
@@ -139,7 +140,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   // The band mask rides on the tensor pipe: S_h = Q_h K_h^T + onehot(s_q) . M^T, where M[key][s] = 0 if the key's position is
   // within half_window of s (and the key row exists), else kMaskNeg. Two extra K = 16 MMAs per head replace a compare +
   // select per score element on the CUDA cores. Operands are constants of the launch: built once per CTA.
-  for (int i = threadIdx.x; i < 128 * 32; i += kThreads) {
+  for (int i = threadIdx.x; i < kRows * 32; i += kThreads) {
     const int row = i >> 5, k = i & 31;
     const int sl = row / p.A;
     const bool is_tok = row < p.nrows;
@@ -212,7 +213,12 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       constexpr uint64_t CH = kChunk >> 4, VCH = kVtChunk >> 4, SL16 = kSlot >> 4;      // descriptor units (16 B)
       auto wslot = [&]() -> uint64_t {             // wait for the next weight block, return its descriptor
         const uint32_t slot = wcnt % kSlots, use = wcnt / kSlots;
-        BT_MWAIT(0, bars + W_FULL + slot, use & 1u);
+#ifdef LFSR_DEBUG_HOOKS
+        { const long long t0_ = clock64(); mbar_wait(bars + W_FULL + slot, use & 1u);
+          if (p.dbg) { const long long dt_ = clock64() - t0_; p.dbg[blockIdx.x * 64 + 32] += dt_; p.dbg[blockIdx.x * 64 + 44 + (wcnt % kBlocks)] += dt_; } }
+#else
+        mbar_wait(bars + W_FULL + slot, use & 1u);
+#endif
         tc_fence_after();
         return dRing + (uint64_t)slot * SL16;
       };
@@ -373,10 +379,11 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         acc = f2_fma(d, d, acc);
       }
       f2_unpack(acc, s0, s1);
-      reinterpret_cast<float2*>(xchg)[part * 128 + r] = make_float2(mloc, s0 + s1);
+      const int rx = row_st ? r : 0;                       // rows >= 112 are not tokens: they alias row 0's slot (never read back)
+      if (row_st) reinterpret_cast<float2*>(xchg)[part * kRows + rx] = make_float2(mloc, s0 + s1);
       named_bar_sync(1 + q, 128);
-      const float2 e0 = reinterpret_cast<const float2*>(xchg)[r], e1 = reinterpret_cast<const float2*>(xchg)[128 + r];
-      const float2 e2 = reinterpret_cast<const float2*>(xchg)[256 + r], e3 = reinterpret_cast<const float2*>(xchg)[384 + r];
+      const float2 e0 = reinterpret_cast<const float2*>(xchg)[rx], e1 = reinterpret_cast<const float2*>(xchg)[kRows + rx];
+      const float2 e2 = reinterpret_cast<const float2*>(xchg)[2 * kRows + rx], e3 = reinterpret_cast<const float2*>(xchg)[3 * kRows + rx];
       const float mean = (e0.x + e1.x + e2.x + e3.x) * 0.25f;
       const float d0 = e0.x - mean, d1 = e1.x - mean, d2 = e2.x - mean, d3 = e3.x - mean;
       const float m2 = (e0.y + e1.y + e2.y + e3.y) + 32.f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
@@ -445,8 +452,9 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       // the O columns of the pair's previous head are drained (scaled by 1 / rowsum) as soon as its P.V has retired
       const uint32_t sP = pair ? sRA : sRB;
       // partial row maxima / sums of the pair's two warps: [pair][sub][128] each (the maxima reuse the LayerNorm exchange area)
-      float* const pmax = xchg + pair * 256;
-      float* const psum = xchg + 512 + pair * 256;
+      float* const pmax = xchg + pair * 2 * kRows;
+      float* const psum = xchg + 4 * kRows + pair * 2 * kRows;
+      const int rx = row_st ? r : 0;
       auto drain_o = [&](int h) {                         // 8 of the 16 columns of O_h per warp of the pair
         float v[8];
         {
@@ -458,7 +466,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(t[i]);
         }
-        const float inv = __fdividef(1.f, psum[r] + psum[128 + r]);
+        const float inv = __fdividef(1.f, psum[rx] + psum[kRows + rx]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] *= inv;
         if (row_st) store_f16<8>(sRC + (h >> 2) * kChunk, r, 2 * (h & 3) + sub, v);
@@ -492,9 +500,9 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               }
             }
         }
-        pmax[sub * 128 + r] = fmaxf(m0, m1);
+        if (row_st) pmax[sub * kRows + rx] = fmaxf(m0, m1);
         named_bar_sync(5 + 2 * q + pair, 64);              // (also: the partner has finished the previous head entirely)
-        const float m = fmaxf(pmax[r], pmax[128 + r]);
+        const float m = fmaxf(pmax[rx], pmax[kRows + rx]);
         const f2 negm = f2_pack(-m, -m);
         f2 acc = f2_pack(0.f, 0.f);
         uint32_t ph[8 * kGrpPerWarp];
@@ -535,7 +543,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (k == 0)               // key groups outside this quarter's window are only ever written here: once per tile
           for (int g = z0; g < z1; ++g)
             if (row_st) store_zero<16>(sP + (g >> 2) * kChunk, r, 2 * (g & 3));
-        psum[sub * 128 + r] = a0 + a1;
+        if (row_st) psum[sub * kRows + rx] = a0 + a1;
         arrive(P_FULL + pair);
       }
       BT_TICK(8);

@@ -41,3 +41,6 @@ for i, n in enumerate(mma):
     print(f"  {n:55s} {per[32 + i].item():8.0f}")
     w += per[32 + i].item()
 print(f"  total {per[32 + 15].item():.0f} cycles per tile, of which waiting {w:.0f}")
+names = ["W_in c0", "W_in c1", "Wv c0", "Wv c1", "Wq c0", "Wq c1", "Wk c0", "Wk c1", "Wo c0", "Wo c1", "W1 n0c0", "W1 n0c1", "W1 n1c0", "W1 n1c1",
+         "W2 c0", "W2 c1", "W2 c2", "W2 c3", "Wout"]
+print("weight-ring wait per block:", ", ".join(f"{n} {per[44 + i].item():.0f}" for i, n in enumerate(names)))
