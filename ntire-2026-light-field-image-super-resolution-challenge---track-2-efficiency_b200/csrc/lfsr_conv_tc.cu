@@ -734,7 +734,13 @@ __device__ __forceinline__ void epilogue_tile_tail(const Params& p, const float*
       }
 #undef LFSR_EPI_ACT32
       // rows >= cq of the shared-memory table are zero, so the columns a short last block shares with the next
-      // sub-pixel contribute nothing
+      // sub-pixel contribute nothing - provided they are finite: past the last sub-pixel they are accumulator columns this
+      // kernel's MMAs never wrote (whatever an earlier kernel left in tensor memory, possibly NaN), so they are cleared
+      if (p.cq - c0 < 32) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (c0 + k >= p.cq) v[k] = 0.f;
+      }
       const float4* wt = reinterpret_cast<const float4*>(sTail + c0 * 12);
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
