@@ -86,6 +86,14 @@ typedef struct {
    * lfsr_tap_gather then sums over the 9 shifted positions: the widest activation of the network is never written. */
   const float* tail_w;   /* [tail_c][12] (columns >= tail_taps zero) or NULL */
   int32_t tail_taps, tail_c;
+  /* lfsr_conv2d_tc only - fp16 activations between tensor-core layers (10-bit mantissa = what the TF32 path keeps of an
+   * operand anyway; fp32 accumulation; residual / elementwise consumers keep reading the fp32 tensors):
+   *   in_f16   != 0: `in` is an fp16 NHWC view (ld in 2-byte elements, multiple of 8) and the weights were packed by
+   *                  lfsr_pack_conv_tc16: kind::f16 MMAs, half the shared-memory bytes and MMA time per MAC
+   *   out_mode 0: fp32 output only; 1: fp32 output + an fp16 copy in `out16`; 2: `out16` only (then `out` only carries the
+   *              geometry, its pointer is not written). Copies need channel counts that are multiples of 8. */
+  int32_t in_f16, out_mode;
+  lfsr_tensor out16;     /* fp16 view with out's geometry (ld in 2-byte elements) */
 } lfsr_conv_desc;
 
 const char* lfsr_last_error(void);
@@ -188,6 +196,8 @@ int lfsr_mel_epi_branch(const lfsr_tensor* in, const float* w_packed, const lfsr
  * Supports stride 1 (any dilation, "same" zero padding given by pad) and kh*kw <= 25. */
 size_t lfsr_conv2d_tc_packed_floats(int kh, int kw, int cin, int cout);
 int lfsr_pack_conv_tc(const float* w_oihw_host, float* packed_host, int kh, int kw, int cin, int cout);
+size_t lfsr_conv2d_tc16_packed_bytes(int kh, int kw, int cin, int cout);
+int lfsr_pack_conv_tc16(const float* w_oihw_host, void* packed_host, int kh, int kw, int cin, int cout);
 int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, const lfsr_tensor* out,
                    const lfsr_conv_desc* d, void* stream);
 /* per-image weight sets for a gated conv: out[img] = packed * gate[img][cin] along the input-channel axis

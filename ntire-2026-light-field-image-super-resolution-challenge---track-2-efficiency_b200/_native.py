@@ -21,6 +21,7 @@ ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_GELU, ACT_SILU = 0, 1, 2, 3, 4, 
 PERM_NONE, PERM_MACPI_OVER_SAI = 0, 1
 SHUF_CHANNEL_MAJOR, SHUF_FACTOR_MAJOR = 0, 1
 INTERP_BICUBIC, INTERP_BILINEAR = 0, 1
+OUT_F32, OUT_BOTH, OUT_F16 = 0, 1, 2       # lfsr_conv_desc.out_mode
 
 
 class LfsrError(RuntimeError):
@@ -43,6 +44,7 @@ class ConvDesc(C.Structure):
         ("bias", C.c_void_p), ("in_scale", C.c_void_p), ("in_scale_ld", C.c_int64), ("w_batch_stride", C.c_int64),
         ("mul", Tensor), ("res", Tensor),
         ("tail_w", C.c_void_p), ("tail_taps", C.c_int32), ("tail_c", C.c_int32),
+        ("in_f16", C.c_int32), ("out_mode", C.c_int32), ("out16", Tensor),
     ]
 
 
@@ -101,6 +103,8 @@ SIGNATURES = {
     "lfsr_mel_epi_branch": (_I, [_TP, _P, _TP, _I, _I, C.c_float, _P]),
     "lfsr_conv2d_tc_packed_floats": (C.c_size_t, [_I, _I, _I, _I]),
     "lfsr_pack_conv_tc": (_I, [_P, _P, _I, _I, _I, _I]),
+    "lfsr_conv2d_tc16_packed_bytes": (C.c_size_t, [_I, _I, _I, _I]),
+    "lfsr_pack_conv_tc16": (_I, [_P, _P, _I, _I, _I, _I]),
     "lfsr_scale_pack_tc": (_I, [_P, _P, C.c_int64, _P, _I, _I, _I, _I, _I, _P]),
     "lfsr_conv2d_tc": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
     "lfsr_conv2d_tc_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),

@@ -28,10 +28,17 @@ def alloc_nhwc(n: int, h: int, w: int, c: int, device, zero: bool = False) -> to
     return buf[..., :c] if ld != c else buf
 
 
-def as_tensor(t: torch.Tensor, what: str = "tensor") -> N.Tensor:
-    """Describe a 4-D fp32 NHWC view to the C ABI; rows must be dense with pixel stride ld = stride(2)."""
-    if t.dtype != torch.float32 or t.dim() != 4:
-        raise N.LfsrError(f"{what}: expected a 4-D float32 NHWC view, got {tuple(t.shape)} {t.dtype}")
+def alloc_nhwc16(n: int, h: int, w: int, c: int, device) -> torch.Tensor:
+    """fp16 NHWC buffer (operand copies between tensor-core layers): pixel stride a multiple of 8 halves (16 bytes)."""
+    ld = (c + 7) // 8 * 8
+    buf = torch.zeros((n, h, w, ld), dtype=torch.float16, device=device)
+    return buf[..., :c] if ld != c else buf
+
+
+def as_tensor(t: torch.Tensor, what: str = "tensor", f16: bool = False) -> N.Tensor:
+    """Describe a 4-D fp32 (or, with f16, fp16) NHWC view to the C ABI; rows must be dense with pixel stride ld = stride(2)."""
+    if t.dtype != (torch.float16 if f16 else torch.float32) or t.dim() != 4:
+        raise N.LfsrError(f"{what}: expected a 4-D {'float16' if f16 else 'float32'} NHWC view, got {tuple(t.shape)} {t.dtype}")
     n, h, w, c = t.shape
     s = t.stride()
     ld = s[2]
@@ -61,6 +68,7 @@ class PackedConv:
     dil: Tuple[int, int] = (1, 1)
     pad: Tuple[int, int] = (0, 0)
     w_tc: Optional[torch.Tensor] = None
+    w_tc16: Optional[torch.Tensor] = None   # fp16 packing (lfsr_pack_conv_tc16) for layers fed with fp16 activations
     tc_perm_r2: int = 0   # >0: w_tc rows were permuted to factor-major for a fused nn.PixelShuffle of r2 sub-pixels
     #: per-image gated copies of w_tc (lfsr_scale_pack_tc), keyed by batch size. Owned by the packing, so the scratch lives
     #: exactly as long as the weights it was sized for (a cache on the backend keyed by data_ptr could match a stale entry
@@ -80,7 +88,7 @@ class PackedConv:
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride=(1, 1), dil=(1, 1), pad=(0, 0),
-              device=None, tc: bool = False, tc_shuffle=(1, 1, 0)) -> PackedConv:
+              device=None, tc: bool = False, tc_shuffle=(1, 1, 0), tc16: bool = False) -> PackedConv:
     """weight is torch-layout [cout, cin, kh, kw] (any device); returns device-resident packing.
     tc_shuffle: the PixelShuffle (ry, rx, mode) this layer will always be launched with; for
     nn.PixelShuffle order the tensor-core packing stores output channels sub-pixel-major so the
@@ -91,8 +99,9 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride=
     w_f32 = w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous().to(dev)
     b = None if bias is None else bias.detach().to(torch.float32).contiguous().to(dev)
     w_tc = None
+    w_tc16 = None
     perm_r2 = 0
-    if tc:
+    if tc or tc16:
         lib = N.load()
         nfl = lib.lfsr_conv2d_tc_packed_floats(kh, kw, cin, cout)
         if nfl > 0:
@@ -104,10 +113,15 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride=
                 src = w[perm.to(w.device)]
                 perm_r2 = r2
             src = src.contiguous().cpu()
-            dst = torch.empty(nfl, dtype=torch.float32)
-            N.check(lib.lfsr_pack_conv_tc(src.data_ptr(), dst.data_ptr(), kh, kw, cin, cout), "lfsr_pack_conv_tc")
-            w_tc = dst.to(dev)
-    return PackedConv(w_f32, b, kh, kw, cin, cout, tuple(stride), tuple(dil), tuple(pad), w_tc, perm_r2)
+            if tc:
+                dst = torch.empty(nfl, dtype=torch.float32)
+                N.check(lib.lfsr_pack_conv_tc(src.data_ptr(), dst.data_ptr(), kh, kw, cin, cout), "lfsr_pack_conv_tc")
+                w_tc = dst.to(dev)
+            if tc16:
+                dst = torch.empty(lib.lfsr_conv2d_tc16_packed_bytes(kh, kw, cin, cout), dtype=torch.uint8)
+                N.check(lib.lfsr_pack_conv_tc16(src.data_ptr(), dst.data_ptr(), kh, kw, cin, cout), "lfsr_pack_conv_tc16")
+                w_tc16 = dst.to(dev)
+    return PackedConv(w_f32, b, kh, kw, cin, cout, tuple(stride), tuple(dil), tuple(pad), w_tc, w_tc16, perm_r2)
 
 
 class CudaOps:
@@ -152,9 +166,14 @@ class CudaOps:
     # -- convolutions ---------------------------------------------------------------------------
     def conv(self, x, pc: PackedConv, out, act=N.ACT_NONE, slope=0.0, alpha=1.0, mul=None, mul_act=N.ACT_NONE, res=None,
              in_scale=None,
-             in_perm=0, out_perm=0, perm_a=0, shuffle=(1, 1, 0), block=(0, 0), tail=None):
+             in_perm=0, out_perm=0, perm_a=0, shuffle=(1, 1, 0), block=(0, 0), tail=None, out16=None):
         """tail = (tail_w [c][12] device tensor, taps, c): store the projection of the shuffled activation onto `taps`
-        vectors instead of the activation (lfsr_conv_desc.tail_w); tensor-core path only."""
+        vectors instead of the activation (lfsr_conv_desc.tail_w); tensor-core path only.
+        fp16 operand path (tensor cores only, raises when the layer does not qualify): `x` may be a float16 NHWC view (then
+        pc.w_tc16 is used); `out16` is a float16 view that receives a copy of the output; `out=None` with `out16` writes the
+        fp16 tensor only."""
+        if x.dtype == torch.float16 or out16 is not None:
+            return self._conv16(x, pc, out, out16, act, slope, alpha, mul, mul_act, res, shuffle, block, tail)
         d = N.ConvDesc()
         d.kh, d.kw = pc.kh, pc.kw
         d.stride_h, d.stride_w = pc.stride
@@ -213,6 +232,42 @@ class CudaOps:
         else:
             N.check(self.lib.lfsr_conv2d_f32(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st),
                     "lfsr_conv2d_f32")
+
+    def _conv16(self, x, pc, out, out16, act, slope, alpha, mul, mul_act, res, shuffle, block, tail):
+        d = N.ConvDesc()
+        d.kh, d.kw = pc.kh, pc.kw
+        d.stride_h, d.stride_w = pc.stride
+        d.dil_h, d.dil_w = pc.dil
+        d.pad_h, d.pad_w = pc.pad
+        d.shuf_ry, d.shuf_rx, d.shuf_mode = shuffle
+        d.block_h, d.block_w = block
+        d.act, d.act_slope, d.alpha, d.mul_act = act, slope, alpha, mul_act
+        d.bias = self._ptr(pc.bias)
+        d.mul = as_tensor(mul, "conv.mul") if mul is not None else _NULL_T
+        d.res = as_tensor(res, "conv.res") if res is not None else _NULL_T
+        if tail is not None:
+            d.tail_w, d.tail_taps, d.tail_c = tail[0].data_ptr(), tail[1], tail[2]
+        in16 = x.dtype == torch.float16
+        d.in_f16 = 1 if in16 else 0
+        w = pc.w_tc16 if in16 else pc.w_tc
+        if w is None or not self.use_tc:
+            raise N.LfsrError("conv: the fp16 operand path needs tensor-core packed weights (pack_conv(tc16=True) / tc=True)")
+        r2 = shuffle[0] * shuffle[1]
+        if pc.tc_perm_r2 != (r2 if (r2 > 1 and shuffle[2] == N.SHUF_CHANNEL_MAJOR) else 0):
+            raise N.LfsrError("conv: weights were packed for a different PixelShuffle")
+        tin = as_tensor(x, "conv.in", f16=in16)
+        if out16 is not None:
+            d.out16 = as_tensor(out16, "conv.out16", f16=True)
+            d.out_mode = N.OUT_BOTH if out is not None else N.OUT_F16
+        if out is not None:
+            tout = as_tensor(out, "conv.out")
+        else:           # geometry only: the fp32 pointer is not written in OUT_F16 mode
+            tout = N.Tensor(out16.data_ptr(), out16.shape[0], out16.shape[1], out16.shape[2], out16.shape[3], out16.stride(2))
+        if x.shape[3] != pc.cin:
+            raise N.LfsrError(f"conv: input has {x.shape[3]} channels, weights expect {pc.cin}")
+        if not self.lib.lfsr_conv2d_tc_supported(C.byref(tin), C.byref(tout), C.byref(d)):
+            raise N.LfsrError("conv: this layer does not qualify for the fp16 operand path")
+        N.check(self.lib.lfsr_conv2d_tc(C.byref(tin), w.data_ptr(), C.byref(tout), C.byref(d), self._stream(x)), "lfsr_conv2d_tc")
 
     def tail_supported(self, pc: PackedConv, cq: int, shuffle) -> bool:
         """can `pc` (a conv + PixelShuffle to cq channels) end in a tail projection on this backend?"""

@@ -448,8 +448,8 @@ TC_CASES = [
     dict(cin=144, cout=64, k=(1, 1), act=2, hw=(160, 160)),
     dict(cin=64, cout=1024, k=(1, 1), act=2, shuffle=(4, 4, 0), hw=(40, 40)),
     dict(cin=64, cout=1600, k=(1, 1), shuffle=(5, 5, 0), hw=(32, 32)),
-    dict(cin=32, cout=160, k=(1, 1), act=2, shuffle=(1, 5, 1), hw=(40, 8)),
-    dict(cin=32, cout=160, k=(1, 1), act=2, shuffle=(5, 1, 1), hw=(8, 40)),
+    dict(cin=32, cout=160, k=(1, 1), act=2, shuffle=(1, 5, 1), hw=(40, 32)),
+    dict(cin=32, cout=160, k=(1, 1), act=2, shuffle=(5, 1, 1), hw=(32, 40)),
     dict(cin=128, cout=256, k=(1, 1), hw=(1, 5000)),
     dict(cin=256, cout=128, k=(1, 1), res=True, hw=(1, 5000)),
     dict(cin=64, cout=128, k=(1, 1), hw=(1, 25600)),
@@ -525,6 +525,62 @@ def _run_tc_case(ref, case):
     print(f"tc conv {case}: max err {err:.3e} (ref max {scale:.3f})")
     assert lib.lfsr_launch_count() == l0 + 1
     assert err <= 1e-3 * scale, f"max err {err}"        # the end-to-end budget (north_star: 1e-3 on [0,1] outputs)
+
+
+F16_CASES = [
+    dict(cin=64, cout=64, k=(3, 3), dil=(5, 5), pad=(5, 5), act=2, hw=(40, 40), both=True),
+    dict(cin=64, cout=64, k=(3, 3), pad=(1, 1), act=2, block=(8, 8), res=True, hw=(40, 40), both=True),
+    dict(cin=64, cout=64, k=(1, 1), act=2, hw=(40, 40)),
+    dict(cin=144, cout=64, k=(1, 1), act=2, hw=(40, 40)),
+    dict(cin=64, cout=16, k=(5, 5), stride=(5, 5), act=2, hw=(40, 40)),
+    dict(cin=64, cout=32, k=(1, 25), stride=(1, 5), pad=(0, 10), act=2, hw=(40, 40)),
+    dict(cin=64, cout=32, k=(25, 1), stride=(5, 1), pad=(10, 0), act=2, hw=(40, 40)),
+    dict(cin=16, cout=400, k=(1, 1), act=2, shuffle=(5, 5, 0), hw=(8, 8)),
+    dict(cin=32, cout=160, k=(1, 1), act=2, shuffle=(1, 5, 1), hw=(40, 32)),
+    dict(cin=32, cout=160, k=(1, 1), act=2, shuffle=(5, 1, 1), hw=(32, 40)),
+    dict(cin=128, cout=64, k=(3, 3), dil=(5, 5), pad=(5, 5), act=1, res=True, hw=(40, 40), both=True),
+    dict(cin=56, cout=224, k=(3, 3), pad=(1, 1), act=2, shuffle=(2, 2, 0), hw=(40, 40)),
+]
+
+
+@pytest.mark.parametrize("case", F16_CASES, ids=lambda c: f"{c['cin']}-{c['cout']}-{c['k'][0]}x{c['k'][1]}")
+def test_conv_tc_fp16_operands(ref, case):
+    """fp16 activations in (kind::f16 MMAs), fp16-only / fp32 + fp16 outputs, against the plain-torch conv of the SAME fp16
+    input values in fp32: only the fp16 rounding of the weights, the accumulation order and the output rounding differ."""
+    tc_ops = K.CudaOps()
+    n = 2
+    h, w = case["hw"]
+    cin, cout = case["cin"], case["cout"]
+    kh, kw = case["k"]
+    dil, pad, stride = case.get("dil", (1, 1)), case.get("pad", (0, 0)), case.get("stride", (1, 1))
+    g = torch.Generator().manual_seed(cin * 17 + cout)
+    wt = (torch.rand(cout, cin, kh, kw, generator=g) - 0.5) * (2.0 / (cin * kh * kw) ** 0.5)
+    ry, rx, sm = case.get("shuffle", (1, 1, 0))
+    pc = K.pack_conv(wt, None, stride=stride, dil=dil, pad=pad, device=DEV, tc=True, tc16=True, tc_shuffle=(ry, rx, sm))
+    assert pc.w_tc16 is not None
+    x16 = K.alloc_nhwc16(n, h, w, cin, DEV)
+    x16.copy_(nhwc(n, h, w, cin, seed=3))
+    co = cout // (ry * rx)
+    oh, ow = h // stride[0], w // stride[1]
+    kw_args = dict(act=case.get("act", 0), slope=0.1, shuffle=(ry, rx, sm), block=case.get("block", (0, 0)))
+    if case.get("res"):
+        kw_args["res"] = nhwc(n, oh * ry, ow * rx, co, seed=5)
+    want = nhwc(n, oh * ry, ow * rx, co, seed=7)
+    ref.conv(x16.float(), pc, want, **kw_args)
+    scale = max(1.0, want.abs().max().item())
+    o16 = K.alloc_nhwc16(n, oh * ry, ow * rx, co, DEV)
+    if case.get("both"):
+        o32 = torch.zeros_like(want)
+        tc_ops.conv(x16, pc, o32, out16=o16, **kw_args)
+        e32 = (o32 - want).abs().max().item()
+        assert e32 <= 1e-3 * scale, e32
+        assert torch.equal(o16, o32.half())               # the copy is the rounded fp32 result
+    else:
+        tc_ops.conv(x16, pc, None, out16=o16, **kw_args)
+    torch.cuda.synchronize()
+    e16 = (o16.float() - want).abs().max().item()
+    print(f"fp16 conv {case}: max err of the fp16 output {e16:.3e} (ref max {scale:.3f})")
+    assert e16 <= 1.5e-3 * scale, e16                    # + half an fp16 ulp of the output itself
 
 
 def test_mel_epi_branch(ops, ref):
