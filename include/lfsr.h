@@ -196,6 +196,9 @@ int lfsr_mel_epi_branch(const lfsr_tensor* in, const float* w_packed, const lfsr
  * Supports stride 1 (any dilation, "same" zero padding given by pad) and kh*kw <= 25. */
 size_t lfsr_conv2d_tc_packed_floats(int kh, int kw, int cin, int cout);
 int lfsr_pack_conv_tc(const float* w_oihw_host, float* packed_host, int kh, int kw, int cin, int cout);
+/* fp32 NHWC tensor -> its fp16 copy (round to nearest even): the operand copy of a tensor that did not come out of a
+ * tensor-core epilogue (stems). Channel count a multiple of 8. */
+int lfsr_to_f16(const lfsr_tensor* in, const lfsr_tensor* out16, void* stream);
 size_t lfsr_conv2d_tc16_packed_bytes(int kh, int kw, int cin, int cout);
 int lfsr_pack_conv_tc16(const float* w_oihw_host, void* packed_host, int kh, int kw, int cin, int cout);
 int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, const lfsr_tensor* out,

@@ -1,6 +1,7 @@
 // Reductions, the SA-modulator tail, LayerNorm, band-masked EPI attention and PSNR/SSIM sums.
 // All HBM/latency-bound fp32 kernels with warp-shuffle reductions.
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "lfsr_common.cuh"
 
 namespace lfsr {
@@ -722,6 +723,36 @@ extern "C" int lfsr_epi_attention(const float* qk, const float* v, float* out, c
   size_t smem = (size_t)2 * L * ATT_LD * sizeof(float);
   epi_attention_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(qk, v, out, *d);
   return check_launch("epi_attention_kernel");
+}
+
+namespace lfsr {
+__global__ void __launch_bounds__(256)
+to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long pixels, int c, int ld_in, int ld_out) {
+  const int c8 = c >> 3;
+  const long long total = pixels * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long px = i / c8;
+    const int k = (int)(i - px * c8) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(in + px * ld_in + k), b = *reinterpret_cast<const float4*>(in + px * ld_in + k + 4);
+    __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w), h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+    uint4 v;
+    v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
+    v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(out + px * ld_out + k) = v;
+  }
+}
+}  // namespace lfsr
+
+extern "C" int lfsr_to_f16(const lfsr_tensor* in, const lfsr_tensor* out16, void* stream) {
+  LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out16), "lfsr_to_f16: null/invalid tensor");
+  LFSR_REQUIRE(in->n == out16->n && in->h == out16->h && in->w == out16->w && in->c == out16->c, "lfsr_to_f16: shape mismatch");
+  LFSR_REQUIRE(in->c % 8 == 0 && in->ld % 4 == 0 && out16->ld % 8 == 0 && ((uintptr_t)in->ptr & 15) == 0 && ((uintptr_t)out16->ptr & 15) == 0,
+               "lfsr_to_f16: channel count must be a multiple of 8 and rows 16-byte aligned");
+  const long long pixels = (long long)in->n * in->h * in->w;
+  const long long blocks = capped_blocks(pixels * (in->c / 8));
+  lfsr::to_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)in->ptr, (__half*)out16->ptr, pixels, in->c, in->ld,
+                                                                        out16->ld);
+  return check_launch("to_f16_kernel");
 }
 
 extern "C" int lfsr_metric_sums(const float* label, const float* out, int ang, int h, int w, double* acc,

@@ -269,6 +269,10 @@ class CudaOps:
             raise N.LfsrError("conv: this layer does not qualify for the fp16 operand path")
         N.check(self.lib.lfsr_conv2d_tc(C.byref(tin), w.data_ptr(), C.byref(tout), C.byref(d), self._stream(x)), "lfsr_conv2d_tc")
 
+    def to_f16(self, x, out16):
+        N.check(self.lib.lfsr_to_f16(C.byref(as_tensor(x, "to_f16.in")), C.byref(as_tensor(out16, "to_f16.out", f16=True)),
+                                     self._stream(x)), "lfsr_to_f16")
+
     def tail_supported(self, pc: PackedConv, cq: int, shuffle) -> bool:
         """can `pc` (a conv + PixelShuffle to cq channels) end in a tail projection on this backend?"""
         return bool(self.use_tc and pc.w_tc is not None and shuffle[0] * shuffle[1] > 1 and cq % 4 == 0

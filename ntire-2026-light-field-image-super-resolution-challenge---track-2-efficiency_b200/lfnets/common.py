@@ -17,6 +17,11 @@ from .. import _native as N
 from .. import kernels as K
 
 
+#: LFSR_FP16_OPS=0 keeps every tensor-core layer on fp32 activations / TF32 operands (comparison, debugging). Default: layers
+#: whose outputs only feed other tensor-core layers exchange fp16 activations (10-bit mantissa = what TF32 keeps of an operand;
+#: fp32 accumulation; residual trunks, interpolation skips and everything a CUDA-core kernel reads stay fp32)
+USE_FP16_OPERANDS = os.environ.get("LFSR_FP16_OPS", "1") != "0"
+
 #: LFSR_CUDA_GRAPH=0 launches every kernel of a forward individually (profiling per-op, debugging)
 USE_CUDA_GRAPH = os.environ.get("LFSR_CUDA_GRAPH", "1") != "0"
 
@@ -175,6 +180,15 @@ class LFNetBase(nn.Module):
         t = self._arena.get(key)
         if t is None:
             t = K.alloc_nhwc(n, h, w, c, device, zero=True)
+            self._arena[key] = t
+        return t
+
+    def _buf16(self, name: str, n: int, h: int, w: int, c: int, device) -> torch.Tensor:
+        """fp16 NHWC operand buffer (activations that only tensor-core layers read)"""
+        key = (name, "f16", n, h, w, c, str(device))
+        t = self._arena.get(key)
+        if t is None:
+            t = K.alloc_nhwc16(n, h, w, c, device)
             self._arena[key] = t
         return t
 

@@ -67,9 +67,10 @@ class get_model(LFNetBase):
 
     def _pack(self, device, ops):
         A, s = self.angRes, self.scale
-        pc = lambda w, b=None, **kw: K.pack_conv(w, b, device=device, **kw)
+        f16 = self._fp16(ops)
+        pc = lambda w, b=None, **kw: K.pack_conv(w, b, device=device, **(dict(kw, tc16=True) if (f16 and kw.get("tc")) else kw))
         dil = dict(dil=(A, A), pad=(A, A))
-        pk = {"stem": pc(self.init_conv.weight, **dil), "groups": []}
+        pk = {"stem": pc(self.init_conv.weight, **dil), "groups": [], "f16": f16}
         for g in self.disentg.Group:
             blocks = []
             for b in g.Block:
@@ -94,7 +95,14 @@ class get_model(LFNetBase):
         pk["tail"] = pc(w_eff.float().view(s * s, -1, 1, 1), b_eff.float())
         return pk
 
+    @staticmethod
+    def _fp16(ops):
+        from . import common
+        return bool(common.USE_FP16_OPERANDS and getattr(ops, "fp16_operands", getattr(ops, "use_tc", False)) and hasattr(ops, "to_f16"))
+
     def _run(self, ops, pk, x, out):
+        if pk.get("f16"):
+            return self._run16(ops, pk, x, out)
         A, s, C = self.angRes, self.scale, self.channels
         B, _, H, W = x.shape
         dev = x.device
@@ -142,6 +150,62 @@ class get_model(LFNetBase):
             cur = nxt
         ops.conv(cur, pk["cascade"], spa1, res=buf0)
         ops.conv(spa1, pk["tail"], Y, res=Y, out_perm=N.PERM_MACPI_OVER_SAI, perm_a=A, shuffle=(s, s, N.SHUF_CHANNEL_MAJOR))
+
+
+    def _run16(self, ops, pk, x, out):
+        """the same launch plan with fp16 activations between the tensor-core layers: every intermediate of a DisentgBlock
+        (spa1, the 144-channel concat, ang1, eh / ev, f1) only ever feeds another convolution and exists in fp16 alone; the
+        residual trunk (`cur`) stays fp32 and carries an fp16 copy for the four convolutions that read it."""
+        A, s, C = self.angRes, self.scale, self.channels
+        B, _, H, W = x.shape
+        dev = x.device
+        buf = lambda name, h, w, c: self._buf(name, B, h, w, c, dev)
+        b16 = lambda name, h, w, c: self._buf16(name, B, h, w, c, dev)
+        LR = N.ACT_LRELU
+        xin = x.view(B, H, W, 1)
+        Y = out.view(B, H * s, W * s, 1)
+        ops.interp(x, out, B, H, W, s, N.INTERP_BILINEAR, H, W)
+        hA, wA = H // A, W // A
+        ang_c, epi_c = C // 4, C // 2
+        buf0, buf0h = buf("buf0", H, W, C), b16("buf0", H, W, C)
+        ops.conv(xin, pk["stem"], buf0, in_perm=N.PERM_MACPI_OVER_SAI, perm_a=A)
+        ops.to_f16(buf0, buf0h)
+        cat = b16("cat", H, W, C + ang_c + 2 * epi_c)
+        spa1, f1 = b16("spa1", H, W, C), b16("f1", H, W, C)
+        ang1 = b16("ang1", hA, wA, ang_c)
+        eh, ev = b16("eh", H, wA, epi_c), b16("ev", hA, W, epi_c)
+        ring = [(buf(f"ring{i}", H, W, C), b16(f"ring{i}", H, W, C)) for i in range(3)]
+        cur, curh, nring = buf0, buf0h, 0
+        o1, o2, o3 = C, C + ang_c, C + ang_c + epi_c
+        for g in pk["groups"]:
+            gin = cur
+            for b in g["blocks"]:
+                ops.conv(curh, b["spa0"], None, out16=spa1, act=LR, slope=0.1)
+                ops.conv(spa1, b["spa2"], None, out16=cat[..., 0:o1], act=LR, slope=0.1)
+                ops.conv(curh, b["ang0"], None, out16=ang1, act=LR, slope=0.1)
+                ops.conv(ang1, b["ang2"], None, out16=cat[..., o1:o2], act=LR, slope=0.1, shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
+                ops.conv(curh, b["epi_h"], None, out16=eh, act=LR, slope=0.1)
+                ops.conv(eh, b["epi2"], None, out16=cat[..., o2:o3], act=LR, slope=0.1, shuffle=(1, A, N.SHUF_FACTOR_MAJOR))
+                ops.conv(curh, b["epi_v"], None, out16=ev, act=LR, slope=0.1)
+                ops.conv(ev, b["epi2"], None, out16=cat[..., o3:o3 + epi_c], act=LR, slope=0.1, shuffle=(A, 1, N.SHUF_FACTOR_MAJOR))
+                ops.conv(cat, b["fuse0"], None, out16=f1, act=LR, slope=0.1)
+                nxt = ring[nring]
+                nring = (nring + 1) % 3
+                if nxt[0] is gin:              # never overwrite the group input that is still needed
+                    nxt = ring[nring]
+                    nring = (nring + 1) % 3
+                ops.conv(f1, b["fuse2"], nxt[0], out16=nxt[1], res=cur)
+                cur, curh = nxt
+            nxt = ring[nring]
+            nring = (nring + 1) % 3
+            if nxt[0] is gin:
+                nxt = ring[nring]
+                nring = (nring + 1) % 3
+            ops.conv(curh, g["conv"], nxt[0], out16=nxt[1], res=gin)
+            cur, curh = nxt
+        last = buf("spa1_f32", H, W, C)
+        ops.conv(curh, pk["cascade"], last, res=buf0)
+        ops.conv(last, pk["tail"], Y, res=Y, out_perm=N.PERM_MACPI_OVER_SAI, perm_a=A, shuffle=(s, s, N.SHUF_CHANNEL_MAJOR))
 
 
 get_loss = L1Loss

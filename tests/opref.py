@@ -37,6 +37,10 @@ def _nchw(t):
 class RefOps:
     name = "torch-ref"
 
+    def __init__(self, fp16_operands: bool = False):
+        #: True: the networks run the launch plans that exchange fp16 activations between tensor-core layers
+        self.fp16_operands = fp16_operands
+
     # -- patch pipeline ---------------------------------------------------------------------------
     def divide_rows(self, scene, patches, ang, h0, w0, patch, stride, u0, u1):
         sub = lf_oracle.lfdivide(scene.detach().cpu().numpy().reshape(ang * h0, ang * w0), ang, patch, stride)
@@ -63,9 +67,9 @@ class RefOps:
 
     # -- convolutions ------------------------------------------------------------------------------
     def conv(self, x, pc, out, act=0, slope=0.0, alpha=1.0, mul=None, mul_act=0, res=None, in_scale=None, in_perm=0, out_perm=0,
-             perm_a=0, shuffle=(1, 1, 0), block=(0, 0), tail=None):
+             perm_a=0, shuffle=(1, 1, 0), block=(0, 0), tail=None, out16=None):
         n = x.shape[0]
-        xi = _nchw(x)
+        xi = _nchw(x.float())
         if in_perm:
             xi = rearrange(xi, "b c (u h) (v w) -> b c (h u) (w v)", u=perm_a, v=perm_a)
         if in_scale is not None:
@@ -100,7 +104,13 @@ class RefOps:
         if tail is not None:
             tw, taps, c = tail
             y = torch.einsum("bchw,ct->bthw", y, tw[:c, :taps])
-        out.copy_(y.permute(0, 2, 3, 1))
+        if out is not None:
+            out.copy_(y.permute(0, 2, 3, 1))
+        if out16 is not None:          # fp16 copy of the fp32 result (the product path rounds the same way)
+            out16.copy_(y.permute(0, 2, 3, 1))
+
+    def to_f16(self, x, out16):
+        out16.copy_(x)
 
     def tail_supported(self, pc, cq, shuffle):
         return shuffle[0] * shuffle[1] > 1 and cq % 4 == 0

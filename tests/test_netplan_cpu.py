@@ -53,6 +53,22 @@ def test_launch_plan_matches_oracle_p8(name, scale):
     assert (y - y_or).abs().max().item() <= 2e-5              # launch plan == oracle
 
 
+@pytest.mark.parametrize("name,scale", [("DistgSSR", 4), ("DistgSSR", 2)])
+def test_fp16_operand_plan_matches_oracle_p8(name, scale):
+    """the launch plans that exchange fp16 activations between tensor-core layers (residual trunks stay fp32): the torch
+    backend rounds the same tensors through fp16, so the plan (which buffer feeds which layer) is checked on the CPU"""
+    net = lfsr_b200.load_net(name, 5, scale).eval()
+    sd = weights.make_state_dict(name, scale, 1234)
+    net.load_state_dict(sd, strict=True)
+    net.set_backend(RefOps(fp16_operands=True))
+    x = weights.synthetic_patches(2, 5, 8, seed=7)
+    y = net(x, [5, 5])
+    assert net._packed["f16"]
+    y_or = onets.forward(name, x, sd, 5, scale)
+    err = (y - y_or).abs().max().item()
+    assert 0 < err <= 1e-3, err                              # fp16 rounding of the operands is visible, and inside the budget
+
+
 def test_cpu_input_without_backend_raises():
     net = lfsr_b200.load_net("MyEfficientLFNet", 5, 4)
     with pytest.raises(lfsr_b200.LfsrError):
