@@ -612,7 +612,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const Params& p, const CUtenso
     if (chunk_hi - pc0 < ncols) ncols = chunk_hi - pc0;
     if (bi % g_step != g_first) continue;
     const int tcol = pc0 - chunk_lo;                           // TMEM column of the block
-    const bool tma_ok = ncols == 32 || c0 + ncols == p.cq;     // columns right of the block are clipped by the channel dim
+    // columns right of the block are clipped by the channel dim of the tensor store; fp16-only outputs are stored from
+    // registers (any block shape), so they always take the lane-per-pixel path
+    const bool tma_ok = p.out_mode == 2 || ncols == 32 || c0 + ncols == p.cq;
     float4 xv[8];
     float bcol = 0.f;
     if (tma_ok) {
@@ -1800,7 +1802,8 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
         ncols = p.cq - c0 < 32 ? p.cq - c0 : 32;
         if (hi - pc0 < ncols) ncols = hi - pc0;
         if (pc0 - lo + (ncols > 16 ? 32 : 16) > kAccStride) ok = false;
-        if (want16 && !(ncols == 32 || c0 + ncols == p.cq)) ok = false;     // fp16 copies exist only on the tensor-store path
+        if (want16 && want32 && !(ncols == 32 || c0 + ncols == p.cq)) ok = false;   // fp32 + fp16: tensor-store blocks only
+        if (want16 && (ncols % 8 || c0 % 8)) ok = false;                             // 16-byte fp16 stores
       }
     }
     if (ok) {

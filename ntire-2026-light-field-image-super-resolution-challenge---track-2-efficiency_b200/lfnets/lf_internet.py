@@ -77,9 +77,10 @@ class get_model(LFNetBase):
 
     def _pack(self, device, ops):
         A, s = self.angRes, self.scale
-        pc = lambda w, b=None, **kw: K.pack_conv(w, b, device=device, **kw)
+        f16 = self._fp16(ops)
+        pc = lambda w, b=None, **kw: K.pack_conv(w, b, device=device, **(dict(kw, tc16=True) if (f16 and kw.get("tc")) else kw))
         dil = dict(dil=(A, A), pad=(A, A))
-        pk = {"ang_fe": pc(self.AngFE["0"].weight, stride=(A, A)), "spa_fe": pc(self.SpaFE["0"].weight, **dil), "chains": []}
+        pk = {"f16": f16, "ang_fe": pc(self.AngFE["0"].weight, stride=(A, A)), "spa_fe": pc(self.SpaFE["0"].weight, **dil), "chains": []}
         for blk in self.CascadeInterBlock.body:
             pk["chains"].append([dict(s2a=pc(c.Spa2Ang.weight, stride=(A, A), tc=True), a2s=pc(c.Ang2Spa["0"].weight, tc=True, tc_shuffle=(A, A, N.SHUF_CHANNEL_MAJOR)),
                                       asq=pc(c.AngConvSq.weight, tc=True), ssq=pc(c.SpaConvSq.weight, tc=True, **dil))
@@ -95,7 +96,65 @@ class get_model(LFNetBase):
         pk["recon"] = pc(w_eff.float(), **dil)
         return pk
 
+    @staticmethod
+    def _fp16(ops):
+        from . import common
+        return bool(common.USE_FP16_OPERANDS and getattr(ops, "fp16_operands", getattr(ops, "use_tc", False)) and hasattr(ops, "to_f16"))
+
+    def _run16(self, ops, pk, x, out):
+        """the launch plan of _run with fp16 activations between the tensor-core layers: the two streams (residual trunks)
+        stay fp32 and carry fp16 copies inside fp16 [stream | scratch] windows; the scratch halves (Spa2Ang / Ang2Spa
+        outputs), the BottleNeck intermediates and the collection buffers the BottleNeck reads exist in fp16 only."""
+        A, s, C = self.angRes, self.scale, self.channels
+        B, _, H, W = x.shape
+        dev = x.device
+        buf = lambda name, h, w, c: self._buf(name, B, h, w, c, dev)
+        b16 = lambda name, h, w, c: self._buf16(name, B, h, w, c, dev)
+        RL = N.ACT_RELU
+        xin = x.view(B, H, W, 1)
+        Y = out.view(B, H * s, W * s, 1)
+        h, w = H // A, W // A
+        nb = len(pk["chains"])
+        CA, CS = buf("ca", h, w, (nb + 1) * C), buf("cs", H, W, (nb + 1) * C)
+        CAh, CSh = b16("ca", h, w, (nb + 1) * C), b16("cs", H, W, (nb + 1) * C)
+        xs0 = buf("xs0", H, W, C)
+        pa = [(buf("pa0", h, w, 2 * C), b16("pa0", h, w, 2 * C)), (buf("pa1", h, w, 2 * C), b16("pa1", h, w, 2 * C))]
+        ps = [(buf("ps0", H, W, 2 * C), b16("ps0", H, W, 2 * C)), (buf("ps1", H, W, 2 * C), b16("ps1", H, W, 2 * C))]
+        ops.conv(xin, pk["spa_fe"], xs0, in_perm=N.PERM_MACPI_OVER_SAI, perm_a=A)
+        ops.conv(xin, pk["ang_fe"], pa[0][0][..., 0:C], in_perm=N.PERM_MACPI_OVER_SAI, perm_a=A)
+        ops.to_f16(pa[0][0][..., 0:C], pa[0][1][..., 0:C])
+        wa, ws = pa[0], None          # current windows as (fp32, fp16) pairs: [..., :C] = stream, [..., C:] = scratch
+        pp = 0
+        for bi, chains in enumerate(pk["chains"]):
+            for li, c in enumerate(chains):
+                if bi == 0 and li == 0:
+                    ws = ps[0]
+                    ops.conv(xin, pk["spa_fe"], ws[0][..., 0:C], in_perm=N.PERM_MACPI_OVER_SAI, perm_a=A)
+                    ops.to_f16(ws[0][..., 0:C], ws[1][..., 0:C])
+                ops.conv(ws[1][..., 0:C], c["s2a"], None, out16=wa[1][..., C:2 * C], act=RL)                                 # Spa2Ang + ReLU
+                ops.conv(wa[1][..., 0:C], c["a2s"], None, out16=ws[1][..., C:2 * C], shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))    # Ang2Spa
+                if li == len(chains) - 1:          # block output -> its slot in the collection buffers
+                    na = (CA[..., bi * C:(bi + 2) * C], CAh[..., bi * C:(bi + 2) * C])
+                    ns = (CS[..., bi * C:(bi + 2) * C], CSh[..., bi * C:(bi + 2) * C])
+                else:
+                    pp ^= 1
+                    na, ns = pa[pp], ps[pp]
+                    if na[0] is wa[0]:
+                        pp ^= 1
+                        na, ns = pa[pp], ps[pp]
+                ops.conv(wa[1], c["asq"], na[0][..., 0:C], out16=na[1][..., 0:C], act=RL, res=wa[0][..., 0:C])
+                ops.conv(ws[1], c["ssq"], ns[0][..., 0:C], out16=ns[1][..., 0:C], act=RL, res=ws[0][..., 0:C])
+                wa, ws = na, ns
+        ab = b16("ab", h, w, C)
+        ops.conv(CAh[..., 0:nb * C], pk["bn_ang"], None, out16=ab, act=RL)
+        ops.conv(ab, pk["bn_a2s"], None, out16=CSh[..., nb * C:(nb + 1) * C], shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
+        fin = ps[0][0][..., 0:C]
+        ops.conv(CSh, pk["bn_spa"], fin, act=RL, res=xs0)
+        ops.conv(fin, pk["recon"], Y, out_perm=N.PERM_MACPI_OVER_SAI, perm_a=A, shuffle=(s, s, N.SHUF_CHANNEL_MAJOR))
+
     def _run(self, ops, pk, x, out):
+        if pk.get("f16"):
+            return self._run16(ops, pk, x, out)
         A, s, C = self.angRes, self.scale, self.channels
         B, _, H, W = x.shape
         dev = x.device
