@@ -247,10 +247,12 @@ int lfsr_epi_attention(const float* qk, const float* v, float* out, const lfsr_e
 /* ---- EPIT BasicTrans, fused (EPIT.py:74-128: linear_in -> LayerNorm -> MultiheadAttention(q = k = norm(x), v = x, 8 heads,
  * additive band mask of :93-108) + x -> LayerNorm -> Linear/ReLU/Linear + x -> linear_out) ----------------------------------
  * ONE tcgen05/TMEM kernel: a CTA owns a run of query positions of one EPI sequence plus the +-half_window positions they
- * attend (all A angular rows), <= 128 token rows; every intermediate stays in TMEM / shared memory, fp16 operands with fp32
- * accumulation (linear_in: TF32), weights streamed by TMA. Sequences and tokens are addressed exactly like
+ * attend (all A angular rows), <= 112 token rows; every intermediate stays in TMEM / shared memory, fp16 operands with fp32
+ * accumulation, weights streamed by TMA. Sequences and tokens are addressed exactly like
  * lfsr_epi_attention: token(seq, a, s) = seq_base + a*stride_a + s*stride_s, seq_base = b*stride_b + p*stride_p + q*stride_q,
- * in pixels of the [n,h,w,64] NHWC tensors x (in) and y (out, same geometry, must not alias x). E = 128, C = 64, 8 heads. */
+ * in pixels of the [n,h,w,64] NHWC tensors x (in) and y (out, same geometry, must not alias x). BOTH ARE FP16 views (ld in
+ * 2-byte elements, multiple of 8): x is the fp16 operand copy of the fp32 feature trunk (lfsr_conv_desc.out_mode / lfsr_to_f16),
+ * y only ever feeds the next tensor-core convolution. E = 128, C = 64, 8 heads. */
 typedef struct {
   int32_t A, S, half_window, heads, E, C;
   int32_t nb, np, nq;

@@ -44,11 +44,11 @@ constexpr int kSlot = 16384, kSlots = 4;
 constexpr int kMaskBytes = kRows * 64;      // band-mask operands: [112 rows][32 fp16], SWIZZLE_64B K-major, one for A, one for B
                                             // (the M = 128 MMA reads 16 more A rows: whatever follows, they only reach unused lanes)
 constexpr float kMaskNeg = -30000.f;        // added (log2 domain) to the scores of keys outside the band: exp2 -> 0
-constexpr int kBlocks = 19;                 // weight blocks (16 KB each) per tile, in consumption order
+constexpr int kBlocks = 18;                 // weight blocks (16 KB each) per tile, in consumption order
 constexpr int kXchgFloats = 8 * kRows;      // LN partials [4 parts][112 rows] float2 / softmax partial max, sum [2 pairs][2][112] each
 constexpr int kSmemBytes = 4 * kRegion + kVtRegion + kSlots * kSlot + 2 * kMaskBytes + kXchgFloats * 4 + 40 * 8 /* barriers */ + 16;
 // weight block indices
-constexpr int kWin = 0, kWv = 2, kWq = 4, kWk = 6, kWo = 8, kW1 = 10, kW2 = 14, kWout = 18;
+constexpr int kWin = 0, kWv = 1, kWq = 3, kWk = 5, kWo = 7, kW1 = 9, kW2 = 13, kWout = 17;
 
 struct Params {
   int A, S, w, SL, nrows, nkeys, nt, sq;
@@ -167,7 +167,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // ================= TMA producer: x tiles + the weight ring =================
     if (elect_one()) {
       uint32_t wcnt = 0;
-      const uint32_t x_bytes = (uint32_t)p.nrows * 128u * 2u;
+      const uint32_t x_bytes = (uint32_t)p.nrows * 128u;              // [rows][64 fp16]
       auto load_x = [&](int tile) {
         const int seq = tile / p.nt, t = tile - seq * p.nt;
         const int b = seq / p.npq, pq = seq - b * p.npq;
@@ -176,7 +176,6 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (ls0 > p.S - p.SL) ls0 = p.S - p.SL;
         mbar_expect_tx(bars + X_FULL, x_bytes);
         tma_load_5d(RA, &tmX, bars + X_FULL, 0, 0, ls0, pq, b);
-        tma_load_5d(RA + kChunk, &tmX, bars + X_FULL, 32, 0, ls0, pq, b);
       };
       auto load_w = [&](int blk) {
         const uint32_t slot = wcnt % kSlots, use = wcnt / kSlots;
@@ -187,12 +186,12 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       };
       if (n_my > 0) load_x((int)blockIdx.x);
       for (int it = 0; it < n_my; ++it) {
-        for (int blk = 0; blk < 12; ++blk) load_w(blk);
+        for (int blk = 0; blk < 11; ++blk) load_w(blk);
         if (it + 1 < n_my) {              // region RA is free once the last P.V MMA of this tile has retired
           mbar_wait(bars + X_EMPTY, (uint32_t)it & 1u);
           load_x((int)blockIdx.x + (it + 1) * (int)gridDim.x);
         }
-        for (int blk = 12; blk < kBlocks; ++blk) load_w(blk);
+        for (int blk = 11; blk < kBlocks; ++blk) load_w(blk);
       }
     }
     __syncwarp();
@@ -200,7 +199,7 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // ================= MMA issuer: one elected lane walks the whole tile program =================
     if (elect_one()) {
       uint32_t wcnt = 0;
-      const uint32_t id_tf32 = make_idesc(2, 128), id_f16 = make_idesc(0, 128), id_s = make_idesc(0, p.nkeys),
+      const uint32_t id_f16 = make_idesc(0, 128), id_s = make_idesc(0, p.nkeys),
                      id_pv = make_idesc(0, kHd), id_out = make_idesc(0, kC);
       const uint64_t dRA = make_smem_desc(smem_u32(RA)), dRB = make_smem_desc(smem_u32(RB)), dRC = make_smem_desc(smem_u32(RC)),
                      dRD = make_smem_desc(smem_u32(RD)), dRE = make_smem_desc(smem_u32(RE)), dRing = make_smem_desc(smem_u32(ring));
@@ -229,11 +228,10 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #endif
       for (int it = 0; it < n_my; ++it) {
         const uint32_t par = (uint32_t)it & 1u;
-        // ---- X = x W_in^T (tf32) -> R
+        // ---- X = x W_in^T -> R (K = 64 input channels: one chunk)
         BT_MWAIT(1, bars + X_FULL, par);
         tc_fence_after();
-        { const uint64_t b = wslot(); mma_chunk<true, true>(tR, dRA, b, id_tf32); wfree(); }
-        { const uint64_t b = wslot(); mma_chunk<true, false>(tR, dRA + CH, b, id_tf32); wfree(); }
+        { const uint64_t b = wslot(); mma_chunk<false, true>(tR, dRA, b, id_f16); wfree(); }
         umma_commit(bars + R_FULL);
         // ---- V^T = Wv X^T -> T1 (as soon as the fp16 copy of X is written, while the epilogue still normalises)
         BT_MWAIT(2, bars + X_READY, par);
@@ -610,20 +608,12 @@ basictrans_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (ls0 > p.S - p.SL) ls0 = p.S - p.SL;
         const int qs0 = t * p.sq;
         const int rq = r - (qs0 - ls0) * p.A;                 // row inside the query block
-        if (rq >= 0 && rq < p.sq * p.A) {
-          const uint32_t rb = sRC + (uint32_t)(part >> 1) * kChunk + (uint32_t)rq * 128u;
-          const uint32_t sw = (uint32_t)(rq & 7);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            st_shared_v4(rb + ((((uint32_t)(4 * (part & 1) + i)) ^ sw) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
-                         __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
-        }
+        if (rq >= 0 && rq < p.sq * p.A) store_f16<16>(sRC, rq, 2 * part, v);
         fence_proxy_async();
         tc_fence_before();
         named_bar_sync(13, 32 * kEpiWarps);
         if (warp == 0 && lane == 0) {
           tma_store_5d(&tmY, RC, 0, 0, qs0, pq, b);
-          tma_store_5d(&tmY, RC + kChunk, 32, 0, qs0, pq, b);
           bulk_commit();
         }
       }
@@ -685,7 +675,7 @@ static bool plan(int A, int S, int w, int* nt_, int* sq_, int* SL_) {
 static bool geometry_ok(const lfsr_tensor* x, const lfsr_tensor* y, const lfsr_basictrans_desc* d) {
   if (!tensor_ok(x) || !tensor_ok(y) || !d) return false;
   if (d->E != kE || d->C != kC || d->heads != kHeads) return false;
-  if (x->c != kC || y->c != kC || x->ld % 4 || y->ld % 4 || ((uintptr_t)x->ptr & 15) || ((uintptr_t)y->ptr & 15)) return false;
+  if (x->c != kC || y->c != kC || x->ld % 8 || y->ld % 8 || ((uintptr_t)x->ptr & 15) || ((uintptr_t)y->ptr & 15)) return false;
   if (x->n != y->n || x->h != y->h || x->w != y->w) return false;
   if (d->A < 1 || d->S < 1 || d->half_window < 0 || d->nb < 1 || d->np < 1 || d->nq < 1) return false;
   if (d->stride_p != (int64_t)d->nq * d->stride_q) return false;          // (p, q) must merge into one tensor-map dimension
@@ -723,17 +713,14 @@ extern "C" int lfsr_pack_basictrans(const float* w_in, const float* w_qkv, const
   LFSR_REQUIRE(w_in && w_qkv && w_o && w_ff1 && w_ff2 && w_out && packed_host, "lfsr_pack_basictrans: null pointer");
   uint8_t* out = static_cast<uint8_t*>(packed_host);
   memset(out, 0, (size_t)kBlocks * kSlot);
-  auto blk_f32 = [&](int blk) { return reinterpret_cast<float*>(out + (size_t)blk * kSlot); };
   auto blk_f16 = [&](int blk) { return reinterpret_cast<__half*>(out + (size_t)blk * kSlot); };
-  for (int c = 0; c < 2; ++c)                           // W_in: rows = out channel, 32 fp32 of K-chunk c
-    for (int o = 0; o < kE; ++o)
-      for (int k = 0; k < 32; ++k) blk_f32(kWin + c)[o * 32 + k] = round_tf32(w_in[o * kC + 32 * c + k]);
   auto pack_f16 = [&](int blk0, const float* w, int row0, int rows, int in_dim, int chunks) {
     for (int c = 0; c < chunks; ++c)
       for (int o = 0; o < rows; ++o)
         for (int k = 0; k < 64; ++k)
           blk_f16(blk0 + c)[o * 64 + k] = __float2half_rn(w[(size_t)(row0 + o) * in_dim + 64 * c + k]);
   };
+  pack_f16(kWin, w_in, 0, kE, kC, 1);
   pack_f16(kWv, w_qkv, 2 * kE, kE, kE, 2);
   {   // Wq with 1/sqrt(head_dim) (MultiheadAttention scales q) and log2(e) (the softmax runs on exp2) folded in
     const float qscale = 1.4426950408889634f / sqrtf((float)kHd);
@@ -789,13 +776,13 @@ extern "C" int lfsr_epit_basictrans(const lfsr_tensor* x, const void* packed, co
   LFSR_REQUIRE(last < T, "lfsr_epit_basictrans: the stride set addresses tokens outside the tensor");
   CUtensorMap tmX, tmW;
   {
-    const cuuint64_t ld_b = (cuuint64_t)x->ld * 4;
+    const cuuint64_t ld_b = (cuuint64_t)x->ld * 2;
     cuuint64_t dims[5] = {(cuuint64_t)kC, (cuuint64_t)p.A, (cuuint64_t)p.S, (cuuint64_t)p.npq, (cuuint64_t)d->nb};
     cuuint64_t strides[4] = {ld_b * (cuuint64_t)d->stride_a, ld_b * (cuuint64_t)d->stride_s, ld_b * (cuuint64_t)d->stride_q,
                              ld_b * (cuuint64_t)d->stride_b};
-    cuuint32_t box[5] = {32, (cuuint32_t)p.A, (cuuint32_t)p.SL, 1, 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)p.A, (cuuint32_t)p.SL, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, x->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, x->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("lfsr_epit_basictrans: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return LFSR_ERR_CUDA; }
   }
@@ -811,13 +798,13 @@ extern "C" int lfsr_epit_basictrans(const lfsr_tensor* x, const void* packed, co
   }
   CUtensorMap tmY;
   {
-    const cuuint64_t ld_b = (cuuint64_t)y->ld * 4;
+    const cuuint64_t ld_b = (cuuint64_t)y->ld * 2;
     cuuint64_t dims[5] = {(cuuint64_t)kC, (cuuint64_t)p.A, (cuuint64_t)p.S, (cuuint64_t)p.npq, (cuuint64_t)d->nb};
     cuuint64_t strides[4] = {ld_b * (cuuint64_t)d->stride_a, ld_b * (cuuint64_t)d->stride_s, ld_b * (cuuint64_t)d->stride_q,
                              ld_b * (cuuint64_t)d->stride_b};
-    cuuint32_t box[5] = {32, (cuuint32_t)p.A, (cuuint32_t)p.sq, 1, 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)p.A, (cuuint32_t)p.sq, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, y->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, y->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("lfsr_epit_basictrans: cuTensorMapEncodeTiled(y) failed with %d", (int)r); return LFSR_ERR_CUDA; }
   }

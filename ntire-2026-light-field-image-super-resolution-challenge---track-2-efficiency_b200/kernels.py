@@ -355,12 +355,12 @@ class CudaOps:
 
     def basictrans(self, x, packed, desc, y, A, S, half_window, nb, np_, nq, stride_a, stride_s, stride_b, stride_p, stride_q,
                    check_only=False):
-        """x, y: [n,h,w,64] NHWC; sequences addressed as in epi_attention. Returns False when the geometry is unsupported
-        (check_only: just answer)."""
+        """x, y: float16 [n,h,w,64] NHWC views (operand copies: the kernel reads and writes fp16); sequences addressed as in
+        epi_attention. Returns False when the geometry is unsupported (check_only: just answer)."""
         d = desc
         d.A, d.S, d.half_window, d.nb, d.np, d.nq = A, S, half_window, nb, np_, nq
         d.stride_a, d.stride_s, d.stride_b, d.stride_p, d.stride_q = stride_a, stride_s, stride_b, stride_p, stride_q
-        tx, ty = as_tensor(x, "basictrans.x"), as_tensor(y, "basictrans.y")
+        tx, ty = as_tensor(x, "basictrans.x", f16=True), as_tensor(y, "basictrans.y", f16=True)
         if not self.lib.lfsr_basictrans_supported(C.byref(tx), C.byref(ty), C.byref(d)):
             return False
         if not check_only:

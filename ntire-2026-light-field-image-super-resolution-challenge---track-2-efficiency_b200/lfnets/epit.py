@@ -67,11 +67,14 @@ class get_model(LFNetBase):
                                  3: nn.Conv2d(ch, 1, 3, padding=1, bias=False)})
 
     def _pack(self, device, ops):
+        from . import common
+        f16 = bool(common.USE_FP16_OPERANDS and USE_FUSED_BASICTRANS and hasattr(ops, "to_f16") and hasattr(ops, "pack_basictrans") and
+                   getattr(ops, "fp16_operands", getattr(ops, "use_tc", False)))
         pc = lambda w, b=None, **kw: K.pack_conv(w, b, device=device, **kw)
-        c3 = lambda m: pc(m.weight[:, :, 0], pad=(1, 1), tc=True)          # [co, ci, 1, 3, 3] -> 2-D 3x3
+        c3 = lambda m: pc(m.weight[:, :, 0], pad=(1, 1), tc=True, tc16=f16)          # [co, ci, 1, 3, 3] -> 2-D 3x3
         lin = lambda w: pc(w.reshape(w.shape[0], w.shape[1], 1, 1), tc=True)
         vec = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
-        pk = {"init0": pc(self.conv_init0["0"].weight[:, :, 0], pad=(1, 1)),
+        pk = {"f16": f16, "init0": pc(self.conv_init0["0"].weight[:, :, 0], pad=(1, 1)),
               "init": [c3(self.conv_init[k]) for k in ("0", "2", "4")], "alt": []}
         for af in self.altblock:
             t = af.epi_trans
@@ -79,7 +82,7 @@ class get_model(LFNetBase):
             ipw = t.attention.in_proj_weight
             # the whole BasicTrans as one tcgen05 kernel (lfsr_epit_basictrans) when the backend has it
             bt = None
-            if hasattr(ops, "pack_basictrans") and getattr(ops, "use_tc", False):
+            if f16:
                 bt = ops.pack_basictrans(t.linear_in.weight, ipw, t.attention.out_proj.weight, t.feed_forward["1"].weight,
                                          t.feed_forward["4"].weight, t.linear_out.weight,
                                          (t.norm.weight, t.norm.bias, t.norm.eps),
@@ -96,7 +99,94 @@ class get_model(LFNetBase):
         pk["tail_w"] = tail_table(self.upsampling["3"].weight, self.channels, device)
         return pk
 
+    def _run16(self, ops, pk, x, out):
+        """fp16 operand plan: the feature trunk (`cur`, residual of every AltFilter pass) stays fp32 and carries an fp16 copy;
+        the fused BasicTrans reads that copy and writes fp16 tokens; the two inner convolutions of each pass exchange fp16
+        only. Geometries the fused kernel does not take fall back to the separate launches on the fp32 trunk."""
+        A, s, C = self.angRes, self.scale, self.channels
+        B, _, H, W = x.shape
+        h, w = H // A, W // A
+        dev = x.device
+        buf = lambda name, hh, ww, c: self._buf(name, B, hh, ww, c, dev)
+        b16 = lambda name, hh, ww, c: self._buf16(name, B, hh, ww, c, dev)
+        LR = N.ACT_LRELU
+        blk = (h, w)
+        xin = x.view(B, H, W, 1)
+        Y = out.view(B, H * s, W * s, 1)
+        ops.interp(x, out, B, H, W, s, N.INTERP_BICUBIC, h, w)
+        f0, f0h = buf("f0", H, W, C), b16("f0", H, W, C)
+        t1h, t2h, ybh = b16("t1", H, W, C), b16("t2", H, W, C), b16("yb", H, W, C)
+        fa, fah, fb = buf("fa", H, W, C), b16("fa", H, W, C), buf("fb", H, W, C)
+        ops.conv(xin, pk["init0"], f0, block=blk)
+        ops.to_f16(f0, f0h)
+        ops.conv(f0h, pk["init"][0], None, out16=t1h, act=LR, slope=0.2, block=blk)
+        ops.conv(t1h, pk["init"][1], None, out16=t2h, act=LR, slope=0.2, block=blk)
+        ops.conv(t2h, pk["init"][2], fa, out16=fah, act=LR, slope=0.2, res=f0, block=blk)
+        hw_img = H * W
+        passes = [
+            dict(A=A, S=h, stride_a=h * W, stride_s=W, stride_b=hw_img, stride_p=w, stride_q=1, np_=A, nq=w),
+            dict(A=A, S=w, stride_a=w, stride_s=1, stride_b=hw_img, stride_p=h * W, stride_q=W, np_=A, nq=h),
+        ]
+        ring = [(buf(f"r{i}", H, W, C), b16(f"r{i}", H, W, C)) for i in range(3)]
+        cur, ri = (fa, fah), 0
+        for al in pk["alt"]:
+            short = cur[0]
+            for p in passes:
+                if not ops.basictrans(cur[1], al["bt"][0], al["bt"][1], ybh, p["A"], p["S"], 5, B, p["np_"], p["nq"], p["stride_a"],
+                                      p["stride_s"], p["stride_b"], p["stride_p"], p["stride_q"]):
+                    self._basictrans_unfused(ops, al, cur[0], p, B, H, W)
+                    ops.to_f16(self._buf("yb", B, H, W, C, dev), ybh)
+                ops.conv(ybh, al["conv"][0], None, out16=t1h, act=LR, slope=0.2, block=blk)
+                ops.conv(t1h, al["conv"][1], None, out16=t2h, act=LR, slope=0.2, block=blk)
+                nxt = ring[ri]
+                ri = (ri + 1) % 3
+                if nxt[0] is short:
+                    nxt = ring[ri]
+                    ri = (ri + 1) % 3
+                ops.conv(t2h, al["conv"][2], nxt[0], out16=nxt[1], res=short, block=blk)
+                cur = nxt
+        ops.conv(cur[0], self._identity(pk, dev), fb, res=fa)
+        self._head(ops, pk, fb, Y, B, H, W)
+
+    def _basictrans_unfused(self, ops, al, cur, p, B, H, W):
+        """BasicTrans as separate launches on the fp32 trunk -> the fp32 token buffer "yb" (EPIT.py:110-128)"""
+        A, C = self.angRes, self.channels
+        dev = cur.device
+        E = al["E"]
+        buf = lambda name, c: self._buf(name, B, H, W, c, dev)
+        T = B * H * W
+        tok = lambda t: t.view(1, 1, T, t.shape[3])
+        X, Nn, Ao, X2 = buf("X", E), buf("Nn", E), buf("Ao", E), buf("X2", E)
+        QK, F1, Vv, yb = buf("QK", 2 * E), buf("F1", 2 * E), buf("V", E), buf("yb", C)
+        ops.conv(tok(cur), al["lin_in"], tok(X))
+        ops.layernorm(tok(X), al["ln1"][0], al["ln1"][1], al["ln1"][2], tok(Nn))
+        ops.conv(tok(Nn), al["wqk"], tok(QK))
+        ops.conv(tok(X), al["wv"], tok(Vv))
+        ops.epi_attention(QK, Vv, Ao, al["heads"], E // al["heads"], p["A"], p["S"], 5, B, p["np_"], p["nq"],
+                          p["stride_a"], p["stride_s"], p["stride_b"], p["stride_p"], p["stride_q"])
+        ops.conv(tok(Ao), al["wo"], tok(X2), res=tok(X))
+        ops.layernorm(tok(X2), al["ln2"][0], al["ln2"][1], al["ln2"][2], tok(Nn))
+        ops.conv(tok(Nn), al["ff1"], tok(F1), act=N.ACT_RELU)
+        ops.conv(tok(F1), al["ff2"], tok(X), res=tok(X2))
+        ops.conv(tok(X), al["lin_out"], tok(yb))
+
+    def _head(self, ops, pk, fb, Y, B, H, W):
+        A, s, C = self.angRes, self.scale, self.channels
+        LR = N.ACT_LRELU
+        dev = fb.device
+        shuffle = (s, s, N.SHUF_CHANNEL_MAJOR)
+        if ops.tail_supported(pk["up0"], C, shuffle):
+            taps = self._buf("head_taps", B, H * s, W * s, 9, dev)
+            ops.conv(fb, pk["up0"], taps, act=LR, slope=0.2, shuffle=shuffle, tail=(pk["tail_w"], 9, C))
+            ops.tap_gather(taps, 3, 3, None, Y, Y)
+        else:
+            up = self._buf("up", B, H * s, W * s, C, dev)
+            ops.conv(fb, pk["up0"], up, act=LR, slope=0.2, shuffle=shuffle)
+            ops.conv(up, pk["up3"], Y, res=Y)
+
     def _run(self, ops, pk, x, out):
+        if pk.get("f16"):
+            return self._run16(ops, pk, x, out)
         A, s, C = self.angRes, self.scale, self.channels
         B, _, H, W = x.shape
         h, w = H // A, W // A
@@ -131,12 +221,6 @@ class get_model(LFNetBase):
         for al in pk["alt"]:
             short = cur
             for p in passes:
-                if al["bt"] is not None and USE_FUSED_BASICTRANS and ops.basictrans(
-                        cur, al["bt"][0], al["bt"][1], yb, p["A"], p["S"], 5, B, p["np_"], p["nq"], p["stride_a"],
-                        p["stride_s"], p["stride_b"], p["stride_p"], p["stride_q"]):
-                    self._conv_tail(ops, al, yb, t1, t2, ring, short, blk, LR, state)
-                    cur = state["cur"]
-                    continue
                 ops.conv(tok(cur), al["lin_in"], tok(X))
                 ops.layernorm(tok(X), al["ln1"][0], al["ln1"][1], al["ln1"][2], tok(Nn))
                 ops.conv(tok(Nn), al["wqk"], tok(QK))

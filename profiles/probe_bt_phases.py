@@ -14,7 +14,7 @@ torch.manual_seed(1234)
 net = lfsr_b200.load_net("EPIT", 5, 4).eval().to("cuda")
 al = net._get_packed(torch.device("cuda", 0), ops)["alt"][0]
 A, h, W = 5, 32, 160
-x = torch.rand(B, W, W, 64, device="cuda") - 0.5
+x = (torch.rand(B, W, W, 64, device="cuda") - 0.5).half()
 y = torch.empty_like(x)
 p = dict(A=A, S=h, stride_a=h, stride_s=1, stride_b=W * W, stride_p=h * W, stride_q=W, np_=A, nq=h)
 call = lambda: ops.basictrans(x, al["bt"][0], al["bt"][1], y, p["A"], p["S"], 5, B, p["np_"], p["nq"], p["stride_a"], p["stride_s"],

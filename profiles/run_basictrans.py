@@ -16,7 +16,7 @@ net = lfsr_b200.load_net("EPIT", 5, 4).eval().to(dev)
 pk = net._get_packed(torch.device(dev, 0), ops)
 al = pk["alt"][0]
 A, h, W = 5, 32, 160
-x = torch.rand(B, W, W, 64, device=dev) - 0.5
+x = (torch.rand(B, W, W, 64, device=dev) - 0.5).half()
 y = torch.empty_like(x)
 passes = [dict(A=A, S=h, stride_a=h * W, stride_s=W, stride_b=W * W, stride_p=h, stride_q=1, np_=A, nq=h),
           dict(A=A, S=h, stride_a=h, stride_s=1, stride_b=W * W, stride_p=h * W, stride_q=W, np_=A, nq=h)]

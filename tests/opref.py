@@ -34,6 +34,32 @@ def _nchw(t):
     return t.permute(0, 3, 1, 2)
 
 
+def basictrans_ref(x, W, ln1, ln2, A, S, hw, nb, np_, nq, sa, ss, sb, sp, sq):
+    """plain torch fp32 BasicTrans (EPIT.py:110-128) on the tokens addressed by the stride set; returns y like x"""
+    import torch.nn.functional as F
+    T = x.numel() // 64
+    xt = x.reshape(T, 64)
+    tok = xt.as_strided((nb, np_, nq, A, S, 64), (sb * 64, sp * 64, sq * 64, sa * 64, ss * 64, 1)).reshape(-1, A * S, 64)
+    X = tok @ W["in"].t()
+    Nn = F.layer_norm(X, (128,), ln1[0], ln1[1], ln1[2])
+    q, k, v = Nn @ W["qkv"][:128].t(), Nn @ W["qkv"][128:256].t(), X @ W["qkv"][256:].t()
+    hs = lambda t: t.reshape(t.shape[0], A * S, 8, 16).transpose(1, 2)
+    sc = (hs(q) @ hs(k).transpose(-1, -2)) * 0.25
+    spos = torch.arange(A * S, device=x.device) % S                          # token index = a*S + s
+    mask = (spos[:, None] - spos[None, :]).abs() > hw
+    sc = sc.masked_fill(mask, float("-inf"))
+    o = (torch.softmax(sc, -1) @ hs(v)).transpose(1, 2).reshape(-1, A * S, 128)
+    X2 = o @ W["o"].t() + X
+    N2 = F.layer_norm(X2, (128,), ln2[0], ln2[1], ln2[2])
+    X3 = torch.relu(N2 @ W["ff1"].t()) @ W["ff2"].t() + X2
+    yt = X3 @ W["out"].t()
+    y = torch.zeros_like(xt)
+    y.as_strided((nb, np_, nq, A, S, 64), (sb * 64, sp * 64, sq * 64, sa * 64, ss * 64, 1)).copy_(
+        yt.reshape(nb, np_, nq, A, S, 64))
+    return y.reshape(x.shape)
+
+
+
 class RefOps:
     name = "torch-ref"
 
@@ -111,6 +137,19 @@ class RefOps:
 
     def to_f16(self, x, out16):
         out16.copy_(x)
+
+    # -- fused BasicTrans (fp16 in / out) ----------------------------------------------------------------------------
+    def pack_basictrans(self, w_in, w_qkv, w_o, w_ff1, w_ff2, w_out, ln1, ln2, heads, device):
+        f = lambda t: t.detach().float()
+        W = {"in": f(w_in), "qkv": f(w_qkv), "o": f(w_o), "ff1": f(w_ff1), "ff2": f(w_ff2), "out": f(w_out)}
+        return W, ((f(ln1[0]), f(ln1[1]), ln1[2]), (f(ln2[0]), f(ln2[1]), ln2[2]))
+
+    def basictrans(self, x, packed, desc, y, A, S, half_window, nb, np_, nq, stride_a, stride_s, stride_b, stride_p, stride_q,
+                   check_only=False):
+        if not check_only:
+            y.copy_(basictrans_ref(x.float().contiguous(), packed, desc[0], desc[1], A, S, half_window, nb, np_, nq, stride_a,
+                                   stride_s, stride_b, stride_p, stride_q))
+        return True
 
     def tail_supported(self, pc, cq, shuffle):
         return shuffle[0] * shuffle[1] > 1 and cq % 4 == 0

@@ -298,29 +298,7 @@ def test_epi_attention(ops, ref, direction):
     assert (a - b).abs().max().item() <= 2e-5
 
 
-def _basictrans_ref(x, W, ln1, ln2, A, S, hw, nb, np_, nq, sa, ss, sb, sp, sq):
-    """plain torch fp32 BasicTrans (EPIT.py:110-128) on the tokens addressed by the stride set; returns y like x"""
-    import torch.nn.functional as F
-    T = x.numel() // 64
-    xt = x.reshape(T, 64)
-    tok = xt.as_strided((nb, np_, nq, A, S, 64), (sb * 64, sp * 64, sq * 64, sa * 64, ss * 64, 1)).reshape(-1, A * S, 64)
-    X = tok @ W["in"].t()
-    Nn = F.layer_norm(X, (128,), ln1[0], ln1[1], ln1[2])
-    q, k, v = Nn @ W["qkv"][:128].t(), Nn @ W["qkv"][128:256].t(), X @ W["qkv"][256:].t()
-    hs = lambda t: t.reshape(t.shape[0], A * S, 8, 16).transpose(1, 2)
-    sc = (hs(q) @ hs(k).transpose(-1, -2)) * 0.25
-    spos = torch.arange(A * S, device=x.device) % S                          # token index = a*S + s
-    mask = (spos[:, None] - spos[None, :]).abs() > hw
-    sc = sc.masked_fill(mask, float("-inf"))
-    o = (torch.softmax(sc, -1) @ hs(v)).transpose(1, 2).reshape(-1, A * S, 128)
-    X2 = o @ W["o"].t() + X
-    N2 = F.layer_norm(X2, (128,), ln2[0], ln2[1], ln2[2])
-    X3 = torch.relu(N2 @ W["ff1"].t()) @ W["ff2"].t() + X2
-    yt = X3 @ W["out"].t()
-    y = torch.zeros_like(xt)
-    y.as_strided((nb, np_, nq, A, S, 64), (sb * 64, sp * 64, sq * 64, sa * 64, ss * 64, 1)).copy_(
-        yt.reshape(nb, np_, nq, A, S, 64))
-    return y.reshape(x.shape)
+from opref import basictrans_ref as _basictrans_ref
 
 
 @pytest.mark.parametrize("B,hv", [(2, 8), (1, 16), (2, 32)])
@@ -337,23 +315,24 @@ def test_epit_basictrans_fused(ops, B, hv):
     ln2 = (1.0 + r(128, sc=0.2), r(128, sc=0.1), 1e-5)
     packed = ops.pack_basictrans(Wt["in"], Wt["qkv"], Wt["o"], Wt["ff1"], Wt["ff2"], Wt["out"], ln1, ln2, 8, DEV)
     assert packed is not None
-    x = (torch.rand(B, H, W, 64, generator=g) * 2 - 1).to(DEV)
+    x16 = (torch.rand(B, H, W, 64, generator=g) * 2 - 1).to(DEV).half()      # the kernel's I/O is fp16 (operand copies)
+    x = x16.float()
     hw_img = H * W
     passes = [dict(A=A, S=hv, stride_a=hv * W, stride_s=W, stride_b=hw_img, stride_p=hv, stride_q=1, np_=A, nq=hv),
               dict(A=A, S=hv, stride_a=hv, stride_s=1, stride_b=hw_img, stride_p=hv * W, stride_q=W, np_=A, nq=hv)]
     for pi, p in enumerate(passes):
-        y = torch.full_like(x, 7.0)
+        y16 = torch.full_like(x16, 7.0)
         l0 = ops.lib.lfsr_launch_count()
-        assert ops.basictrans(x, packed[0], packed[1], y, p["A"], p["S"], 5, B, p["np_"], p["nq"], p["stride_a"], p["stride_s"],
+        assert ops.basictrans(x16, packed[0], packed[1], y16, p["A"], p["S"], 5, B, p["np_"], p["nq"], p["stride_a"], p["stride_s"],
                               p["stride_b"], p["stride_p"], p["stride_q"])
         torch.cuda.synchronize()
         assert ops.lib.lfsr_launch_count() == l0 + 1
         want = _basictrans_ref(x, Wt, ln1, ln2, A, hv, 5, B, p["np_"], p["nq"], p["stride_a"], p["stride_s"], p["stride_b"],
                                p["stride_p"], p["stride_q"])
-        err = (y - want).abs().max().item()
+        err = (y16.float() - want).abs().max().item()
         scale = max(1.0, want.abs().max().item())
         print(f"basictrans B={B} hv={hv} pass {pi}: max err {err:.3e} (ref max {scale:.3f})")
-        assert err <= 1e-3 * scale, (pi, err, scale)
+        assert err <= 1.5e-3 * scale, (pi, err, scale)          # 1e-3 + half an fp16 ulp of the output
 
 
 def test_metrics_vs_oracle_and_golden(ops, golden_dir):
