@@ -30,7 +30,9 @@ def alloc_nhwc(n: int, h: int, w: int, c: int, device, zero: bool = False) -> to
 
 def alloc_nhwc16(n: int, h: int, w: int, c: int, device) -> torch.Tensor:
     """fp16 NHWC buffer (operand copies between tensor-core layers): pixel stride a multiple of 8 halves (16 bytes)."""
-    ld = (c + 7) // 8 * 8
+    ld = (c + 15) // 16 * 16 if c <= 64 else (c + 7) // 8 * 8      # rows of whole 32-byte sectors (TMA boxes are 128-byte rows)
+    if 32 < c <= 64:
+        ld = 64
     buf = torch.zeros((n, h, w, ld), dtype=torch.float16, device=device)
     return buf[..., :c] if ld != c else buf
 
@@ -173,7 +175,7 @@ class CudaOps:
         pc.w_tc16 is used); `out16` is a float16 view that receives a copy of the output; `out=None` with `out16` writes the
         fp16 tensor only."""
         if x.dtype == torch.float16 or out16 is not None:
-            return self._conv16(x, pc, out, out16, act, slope, alpha, mul, mul_act, res, shuffle, block, tail)
+            return self._conv16(x, pc, out, out16, act, slope, alpha, mul, mul_act, res, shuffle, block, tail, in_scale)
         d = N.ConvDesc()
         d.kh, d.kw = pc.kh, pc.kw
         d.stride_h, d.stride_w = pc.stride
@@ -233,7 +235,7 @@ class CudaOps:
             N.check(self.lib.lfsr_conv2d_f32(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st),
                     "lfsr_conv2d_f32")
 
-    def _conv16(self, x, pc, out, out16, act, slope, alpha, mul, mul_act, res, shuffle, block, tail):
+    def _conv16(self, x, pc, out, out16, act, slope, alpha, mul, mul_act, res, shuffle, block, tail, in_scale=None):
         d = N.ConvDesc()
         d.kh, d.kw = pc.kh, pc.kw
         d.stride_h, d.stride_w = pc.stride
@@ -252,6 +254,17 @@ class CudaOps:
         w = pc.w_tc16 if in16 else pc.w_tc
         if w is None or not self.use_tc:
             raise N.LfsrError("conv: the fp16 operand path needs tensor-core packed weights (pack_conv(tc16=True) / tc=True)")
+        if in_scale is not None:      # per-sample gate folded into per-image (TF32) weight sets; fp32 input only
+            if in16:
+                raise N.LfsrError("conv: per-sample gated weights exist for fp32 inputs only")
+            nimg = x.shape[0]
+            d.in_scale = in_scale.data_ptr()
+            d.in_scale_ld = in_scale.stride(0) if in_scale.shape[0] > 1 else pc.cin
+            scratch = pc.gated_scratch(nimg, x.device)
+            N.check(self.lib.lfsr_scale_pack_tc(pc.w_tc.data_ptr(), in_scale.data_ptr(), d.in_scale_ld, scratch.data_ptr(),
+                                                nimg, pc.kh, pc.kw, pc.cin, pc.cout, self._stream(x)), "lfsr_scale_pack_tc")
+            d.w_batch_stride = pc.w_tc.numel()
+            w = scratch
         r2 = shuffle[0] * shuffle[1]
         if pc.tc_perm_r2 != (r2 if (r2 > 1 and shuffle[2] == N.SHUF_CHANNEL_MAJOR) else 0):
             raise N.LfsrError("conv: weights were packed for a different PixelShuffle")

@@ -50,8 +50,10 @@ def tail_table(w_head: torch.Tensor, channels: int, device) -> torch.Tensor:
 def upsample_tail(net, ops, pk, cur, ch, cw, Y, width, LR, shuf_mode):
     """PixelShuffleUpsampler stages + 3x3 head + skip (MyEfficientLFNet.py:104-109, MyEfficientLFNetV4_5.py:100-109).
     The last stage does not write its `width`-channel activation: its epilogue projects every output pixel onto the 9
-    taps of the head conv and lfsr_tap_gather sums the shifted responses onto the interpolated skip already in Y."""
+    taps of the head conv and lfsr_tap_gather sums the shifted responses onto the interpolated skip already in Y.
+    With pk["f16"] the activation between two stages exists in fp16 only (it feeds nothing but the next stage's MMAs)."""
     n_up = len(pk["up"])
+    f16 = bool(pk.get("f16")) and width % 8 == 0
     for j, (pcv, r) in enumerate(pk["up"]):
         shuffle = (r, r, shuf_mode)
         if j == n_up - 1 and pk.get("tail_w") is not None and ops.tail_supported(pcv, width, shuffle):
@@ -59,10 +61,20 @@ def upsample_tail(net, ops, pk, cur, ch, cw, Y, width, LR, shuf_mode):
             ops.conv(cur, pcv, taps, act=LR, slope=0.1, shuffle=shuffle, tail=(pk["tail_w"], 9, width))
             ops.tap_gather(taps, 3, 3, pk["out"].bias, Y, Y)
             return
-        nb = net._buf(f"up{j}", cur.shape[0], ch * r, cw * r, width, cur.device)
-        ops.conv(cur, pcv, nb, act=LR, slope=0.1, shuffle=shuffle)
+        if f16 and j < n_up - 1 and pk.get("tail_w") is not None:
+            nb = net._buf16(f"up{j}", cur.shape[0], ch * r, cw * r, width, cur.device)
+            ops.conv(cur, pcv, None, out16=nb, act=LR, slope=0.1, shuffle=shuffle)
+        else:
+            nb = net._buf(f"up{j}", cur.shape[0], ch * r, cw * r, width, cur.device)
+            ops.conv(cur, pcv, nb, act=LR, slope=0.1, shuffle=shuffle)
         cur, ch, cw = nb, ch * r, cw * r
     ops.conv(cur, pk["out"], Y, res=Y)
+
+
+def fp16_plan(ops) -> bool:
+    """do this backend's tensor-core layers exchange fp16 activations? (USE_FP16_OPERANDS, CudaOps with tensor cores, or a
+    test backend that declares fp16_operands)"""
+    return bool(USE_FP16_OPERANDS and getattr(ops, "fp16_operands", getattr(ops, "use_tc", False)) and hasattr(ops, "to_f16"))
 
 
 #: LFSR_BRANCH_STREAMS=1 runs independent branches of a stage on a second stream (measured +0.6 % on the Track-2 model:

@@ -26,7 +26,7 @@ import torch.nn as nn
 
 from .. import _native as N
 from .. import kernels as K
-from .common import LFNetBase, bn_affine, slots, tail_table, upsample_tail, SideStream
+from .common import LFNetBase, bn_affine, slots, tail_table, upsample_tail, SideStream, fp16_plan
 
 
 def _conv(cin, cout, k, **kw):
@@ -181,7 +181,8 @@ class get_model(LFNetBase):
                 w = torch.cat([w, w.new_zeros((n,) + tuple(w.shape[1:]))], 0)
                 b = None if b is None else torch.cat([b.detach().float().cpu(), torch.zeros(n)])
             return w, b
-        pk = {}
+        f16 = fp16_plan(ops)
+        pk = {"f16": f16}
         w, b = self.shallow_feat.merged()
         pk["stem"] = pc(self._exp(w, 0), self._exp(b, 0), **dil)
         stages = []
@@ -225,7 +226,7 @@ class get_model(LFNetBase):
                 gb[g * gs:g * gs + n] = gate["1"].bias.detach().float().cpu()
             s["gate"] = pc(gw, gb)
             s["fus0"] = pc(*pad_out(self._exp(st.fusion["0"].weight.detach().float().cpu(), 1)), tc=True)
-            s["fus2"] = pc(self._exp(st.fusion["2"].weight.detach().float().cpu(), 0), tc=True, **dil)
+            s["fus2"] = pc(self._exp(st.fusion["2"].weight.detach().float().cpu(), 0), tc=True, tc16=f16, **dil)
             sm = st.sa_modulator
             s["sa_dw"] = dev_t(self._exp(_dw_pack(sm.spatial_mod["0"].weight, "cpu"), 1))
             sc, sh = bn_affine(sm.spatial_mod["1"])
@@ -239,7 +240,7 @@ class get_model(LFNetBase):
         pk["stages"] = stages
         pk["gf0"] = pc(*pad_out(self._exp(self.global_fusion["0"].weight.detach().float().cpu(), 1)), tc=True)
         w, b = self.global_fusion["2"].merged()
-        pk["gf2"] = pc(self._exp(w.float().cpu(), 0), self._exp(b.float().cpu(), 0), tc=True, **dil)
+        pk["gf2"] = pc(self._exp(w.float().cpu(), 0), self._exp(b.float().cpu(), 0), tc=True, tc16=f16, **dil)
         # upsampler activations carry CU = 56 channels (54 + 2 zero): 128-bit epilogue stores, and 4*56 = 224 is
         # exactly the MMA N the 216 real output channels were padded to anyway
         C = self.channels
@@ -256,7 +257,7 @@ class get_model(LFNetBase):
             w = self.upsampler.up[str(i)].weight.detach().float().cpu()
             w = self._exp(w, 1) if j == 0 else pad_ch(w, 1)          # reads the grouped trunk / the padded up buffer
             w = pad_ch(w, 0, r * r)
-            ups.append((pc(w, pad=(1, 1), tc=True, tc_shuffle=(r, r, N.SHUF_CHANNEL_MAJOR)), r))
+            ups.append((pc(w, pad=(1, 1), tc=True, tc16=f16 and j > 0, tc_shuffle=(r, r, N.SHUF_CHANNEL_MAJOR)), r))
         pk["up"] = ups
         pk["out"] = pc(pad_ch(self.output_conv.weight.detach().float().cpu(), 1), self.output_conv.bias, pad=(1, 1))
         pk["CU"] = CU
@@ -290,7 +291,10 @@ class get_model(LFNetBase):
         ang2, ang3 = buf("ang2", hA, wA, gs), buf("ang3", hA, wA, gs)
         vmean, gmean, gate = buf("vmean", A, A, CP), buf("gmean", 1, 1, CP), buf("gate", 1, 1, CP)
         CU = pk["CU"]
-        fu1, fu2 = buf("fu1", H, W, CU), buf("fu2", H, W, CP)
+        f16 = pk.get("f16")
+        # fu1 (fusion 1x1 output) feeds nothing but the 3x3 that follows: fp16 only on the fp16 operand plan
+        fu1 = self._buf16("fu1", B, H, W, CU, dev) if f16 else buf("fu1", H, W, CU)
+        fu2 = buf("fu2", H, W, CP)
         pm, am1, am = buf("pm", A, A, CP), buf("am1", A, A, C // 4), buf("am", A, A, CP)
         fork = SideStream(dev if x.is_cuda and getattr(ops, "name", "") == "cuda" else None)
         for i, st in enumerate(pk["stages"]):
@@ -315,7 +319,10 @@ class get_model(LFNetBase):
             ops.block_mean(cat, vmean, hA, wA)
             ops.block_mean(vmean, gmean, A, A)
             ops.conv(gmean, st["gate"], gate, act=N.ACT_SIGMOID)
-            ops.conv(cat, st["fus0"], fu1, act=LR, slope=0.1, in_scale=gate)
+            if f16:
+                ops.conv(cat, st["fus0"], None, out16=fu1, act=LR, slope=0.1, in_scale=gate)
+            else:
+                ops.conv(cat, st["fus0"], fu1, act=LR, slope=0.1, in_scale=gate)
             ops.conv(fu1[..., 0:C], st["fus2"], fu2)
             # SA modulator + stage residual
             ops.block_mean(fu2, pm, hA, wA)
@@ -324,7 +331,10 @@ class get_model(LFNetBase):
             nxt = pp[i & 1]
             ops.sa_modulate(fu2, st["sa_dw"], st["sa_bns"], st["sa_bnb"], am, st["sa_w"][0], st["sa_w"][1], feat, nxt, A)
             feat = nxt
-        ops.conv(feat, pk["gf0"], fu1, act=LR, slope=0.1)
+        if f16:
+            ops.conv(feat, pk["gf0"], None, out16=fu1, act=LR, slope=0.1)
+        else:
+            ops.conv(feat, pk["gf0"], fu1, act=LR, slope=0.1)
         ops.conv(fu1[..., 0:C], pk["gf2"], fu2, res=shallow)
         upsample_tail(self, ops, pk, fu2, H, W, Y, pk["CU"], LR, N.SHUF_CHANNEL_MAJOR)
 
@@ -339,8 +349,11 @@ class get_model(LFNetBase):
         A, C = self.angRes, self.channels
         pcv, r = pk["up"][-1]
         hin = A * h * (self.scale // r)
-        src = self._buf(f"up{len(pk['up']) - 2}", batch, hin, hin, pcv.cin, dev) if len(pk["up"]) > 1 else \
-            self._buf("fu2", batch, hin, hin, pcv.cin, dev)
+        if len(pk["up"]) > 1:       # the previous upsampler stage's activation: fp16 on the fp16 operand plan
+            mk = self._buf16 if (pk.get("f16") and pcv.w_tc16 is not None) else self._buf
+            src = mk(f"up{len(pk['up']) - 2}", batch, hin, hin, pcv.cin, dev)
+        else:
+            src = self._buf("fu2", batch, hin, hin, pcv.cin, dev)
         shuffle = (r, r, N.SHUF_CHANNEL_MAJOR)
         conv_bytes = batch * (hin * hin * C + hin * r * hin * r * C) * 4 + pcv.kh * pcv.kw * C * C * r * r * 4
         info = {

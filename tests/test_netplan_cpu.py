@@ -53,7 +53,8 @@ def test_launch_plan_matches_oracle_p8(name, scale):
     assert (y - y_or).abs().max().item() <= 2e-5              # launch plan == oracle
 
 
-@pytest.mark.parametrize("name,scale", [("DistgSSR", 4), ("DistgSSR", 2), ("LF_InterNet", 4), ("EPIT", 4)])
+@pytest.mark.parametrize("name,scale", [("DistgSSR", 4), ("DistgSSR", 2), ("LF_InterNet", 4), ("EPIT", 4), ("MyEfficientLFNet", 4),
+                                         ("MyEfficientLFNet", 2)])
 def test_fp16_operand_plan_matches_oracle_p8(name, scale):
     """the launch plans that exchange fp16 activations between tensor-core layers (residual trunks stay fp32): the torch
     backend rounds the same tensors through fp16, so the plan (which buffer feeds which layer) is checked on the CPU"""
