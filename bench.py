@@ -410,15 +410,21 @@ def main():
         except (OSError, KeyError, ValueError):
             pass
         # this kernel moves 0.2x its per-layer bytes through DRAM (the head conv's input never exists) and keeps the tensor
-        # pipe busy: it is tensor / shared-memory bound, so the yardstick is the measured TF32 matmul peak
-        roof = {"bound": "tensor", "achieved": tfl, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tfl / tf32_peak,
+        # pipe busy: it is tensor / shared-memory bound. Its operands are fp16 on the fp16 operand plan (kind::f16 MMAs, fp32
+        # accumulate), TF32 otherwise: the yardstick is the measured dense peak of THAT operand type
+        f16_dom = bool(net._packed and net._packed.get("f16"))
+        peak_t = float(peaks.get("bf16_tflops", 1590.0)) if f16_dom else tf32_peak
+        roof = {"bound": "tensor", "achieved": tfl, "peak": peak_t, "unit": "TFLOP/s", "frac": tfl / peak_t,
                 "traffic": traffic, "kernel": info["name"], "kernel_ms": kms, "flops_per_launch": info["flops"],
-                "peak_source": "torch.matmul fp32 inputs, allow_tf32, 8192^3, best of 10, measured in this run "
-                               "(MEASURED_PEAKS protocol)",
-                "bf16_peak_for_scale": peaks.get("bf16_tflops"),
+                "operands": "fp16 (kind::f16), fp32 accumulate" if f16_dom else "tf32 (kind::tf32), fp32 accumulate",
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops (16-bit dense tensor peak, burst: kernel timed alone)" if f16_dom else
+                                "torch.matmul fp32 inputs, allow_tf32, 8192^3, best of 10, measured in this run (MEASURED_PEAKS "
+                                "protocol)") if peaks or not f16_dom else "fallback 1590 TFLOP/s (B200_PROFILING.md)",
+                "frac_of_tf32_peak": tfl / tf32_peak, "tf32_peak_tflops": tf32_peak, "fp16_peak_tflops": peaks.get("bf16_tflops"),
                 "hbm": {"per_layer_bytes": info["bytes"], "per_layer_gbs": gbs, "per_layer_frac": gbs / hbm_peak,
                         "conv_layer_only_frac": (info["bytes_conv_layer_only"] / (kms * 1e-3) / 1e9 / hbm_peak
                                                  if "bytes_conv_layer_only" in info else None),
+                        "dram_traffic_note": "traffic = DRAM bytes of the committed ncu capture of this kernel",
                         "dram_traffic_gbs": traffic / (kms * 1e-3) / 1e9 if traffic else None,
                         "dram_frac": traffic / (kms * 1e-3) / 1e9 / hbm_peak if traffic else None,
                         "peak": hbm_peak, "peak_source": peak_src}}
@@ -433,8 +439,12 @@ def main():
         if tf32_peak:
             w["achieved_tensor_frac_tf32"] = rate * pp["flops"] / 1e12 / tf32_peak
         if "basictrans_flops" in pp and tf32_peak:
+            # BasicTrans FLOPs as the reference counts them (dense 160 x 160 attention) over the whole forward's time: a lower
+            # bound of the fused kernel's own rate (profiles/run_basictrans.py times it alone)
             w["basictrans_tflops"] = rate * pp["basictrans_flops"] / 1e12
             w["basictrans_tensor_frac_tf32"] = rate * pp["basictrans_flops"] / 1e12 / tf32_peak
+            if peaks.get("bf16_tflops"):
+                w["basictrans_tensor_frac_fp16"] = rate * pp["basictrans_flops"] / 1e12 / float(peaks["bf16_tflops"])
         return w
 
     # ---- the other BASELINE configs (rank 0 of a 1-GPU run; multi-GPU runs only add config 5's reduction) ----
@@ -522,8 +532,12 @@ def main():
         print(json.dumps({
             "metric": "LF patches/sec (5x5x32x32 x%d SR)" % s, "value": value, "unit": "patches/s", "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if ops.use_tc else "f32", "data": "synthetic",
-            "config": cfg,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": ("f16/tf32" if (net._packed and net._packed.get("f16")) else "tf32") if ops.use_tc else "f32",
+            "dtype_note": "tensor-core operands: fp16 between tensor-core layers (10-bit mantissa = TF32's), TF32 where a layer is fed "
+                          "fp32; fp32 accumulation, fp32 residual trunks / CUDA-core kernels; outputs within 1e-3 of the fp32 reference "
+                          "(parity object)",
+            "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / a.steps, "ratio_to_value": e2e / value,
                     "api": "lfsr_b200.scene.SceneRunner.submit(lr_host, hr_host) / result() - the driver train.test() runs on",

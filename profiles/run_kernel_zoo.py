@@ -14,7 +14,7 @@ ops = K.CudaOps()
 rows = []
 
 
-def run(name, fn, nbytes, flops=0.0, reps=5):
+def run(name, fn, nbytes, flops=0.0, reps=int(os.environ.get("LFSR_ZOO_REPS", "5"))):
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
