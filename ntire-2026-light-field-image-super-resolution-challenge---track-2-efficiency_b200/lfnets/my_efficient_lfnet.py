@@ -355,8 +355,11 @@ class get_model(LFNetBase):
         else:
             src = self._buf("fu2", batch, hin, hin, pcv.cin, dev)
         shuffle = (r, r, N.SHUF_CHANNEL_MAJOR)
+        # (per-layer bytes as SURVEY 8d counts them: fp32 in + out + weights of the real 54 / 216-channel layer)
         conv_bytes = batch * (hin * hin * C + hin * r * hin * r * C) * 4 + pcv.kh * pcv.kw * C * C * r * r * 4
+        f16_in = src.dtype == torch.float16
         info = {
+            "ncu_json": "r02_dominant_kernel_ncu.json" if f16_in else "r01_dominant_kernel_ncu.json",
             "name": "conv3x3 %d->%d + PixelShuffle(%d) + LReLU @%dx%d (upsampler.up.%s)" % (C, C * r * r, r, hin, hin,
                                                                                         self.upsampler.steps[-1][0]),
             # algorithmic figures use the reference layer's real 54 -> 216 channels, not the padded buffers
