@@ -177,7 +177,8 @@ int lfsr_conv2d_thin_supported(const lfsr_tensor* in, const lfsr_tensor* out, co
 int lfsr_conv2d_thin(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out,
                      const lfsr_conv_desc* d, void* stream);
 /* stems: 1 input channel -> <= 64 output channels (multiple of 4), <= 9 taps, stride 1, "same" padding; bias +
- * activation fused (MyEfficientLFNet.py:40-43, MyEfficientLFNetV4_5.py:42), optionally MacPI-addressed with dilation ==
+ * activation fused (MyEfficientLFNet.py:40-43, MyEfficientLFNetV4_5.py:42), optionally view-blocked (block_h / block_w: EPIT.py:24)
+ * or MacPI-addressed with dilation ==
  * perm_a (DistgSSR.py:21, LF_InterNet.py:24). Weights packed as for lfsr_conv2d_f32. */
 int lfsr_conv2d_stem_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);
 int lfsr_conv2d_stem(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out,

@@ -159,6 +159,8 @@ struct StemArgs {
   int kh, kw, dh, dw, ph, pw, act;
   float slope;
   int perm_a;            // > 0: MacPI addressing over SAI storage with dilation == perm_a (see conv_stem_macpi_kernel)
+  int bh, bw;            // view blocking (EPIT's per-view Conv3d(1,3,3), EPIT.py:24): taps that leave the bh x bw block of
+                         // the output pixel read zero; bh = H, bw = W without blocking
 };
 
 __global__ void __launch_bounds__(256)
@@ -171,14 +173,15 @@ conv_stem_kernel(const StemArgs a) {
   const int H = a.in.h, W = a.in.w;
   float4 wk[9];
   int off[9], dy[9];
-  unsigned xmask = 0;                  // taps whose column lies inside the image (fixed per thread)
+  unsigned xmask = 0;                  // taps whose column lies inside the image / the pixel's view (fixed per thread)
+  const int bx0 = ox / a.bw * a.bw;    // first column of the block that holds this pixel
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     const int ky = t / a.kw, kx = t - ky * a.kw;
     const int dx = kx * a.dw - a.pw;
     dy[t] = ky * a.dh - a.ph;
     off[t] = dy[t] * W + dx;
-    if (t < taps && ox + dx >= 0 && ox + dx < W) xmask |= 1u << t;
+    if (t < taps && ox + dx >= bx0 && ox + dx < bx0 + a.bw) xmask |= 1u << t;
     wk[t] = t < taps ? __ldg(reinterpret_cast<const float4*>(a.w + t * a.out.c + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float4 b = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -189,9 +192,10 @@ conv_stem_kernel(const StemArgs a) {
   for (int oy = oy0; oy < ymax; ++oy, dst += orow) {
     float4 acc = b;
     const float* rowp = colp + oy * W;
+    const int by0 = oy / a.bh * a.bh;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const bool ok = ((xmask >> t) & 1u) && (unsigned)(oy + dy[t]) < (unsigned)H;
+      const bool ok = ((xmask >> t) & 1u) && (unsigned)(oy + dy[t] - by0) < (unsigned)a.bh;
       const float v = ok ? __ldg(rowp + off[t]) : 0.f;
       acc.x = fmaf(v, wk[t].x, acc.x); acc.y = fmaf(v, wk[t].y, acc.y); acc.z = fmaf(v, wk[t].z, acc.z); acc.w = fmaf(v, wk[t].w, acc.w);
     }
@@ -341,7 +345,9 @@ extern "C" int lfsr_conv2d_stem_supported(const lfsr_tensor* in, const lfsr_tens
   if (!tensor_ok(in) || !tensor_ok(out) || !d) return 0;
   if (in->c != 1 || out->c > 64 || out->c % 4 || out->ld % 4 || ((uintptr_t)out->ptr & 15)) return 0;
   if (d->stride_h != 1 || d->stride_w != 1 || d->out_perm || d->mul.ptr || d->res.ptr || d->in_scale || d->tail_w) return 0;
-  if (d->shuf_ry > 1 || d->shuf_rx > 1 || d->block_h > 0 || d->block_w > 0 || d->alpha != 1.f) return 0;
+  if (d->shuf_ry > 1 || d->shuf_rx > 1 || d->alpha != 1.f) return 0;
+  if ((d->block_h > 0 || d->block_w > 0) &&
+      (d->in_perm || (d->block_h > 0 && in->h % d->block_h) || (d->block_w > 0 && in->w % d->block_w))) return 0;
   if (d->kh * d->kw > 9 || d->kh < 1 || d->kw < 1) return 0;
   if (2 * d->pad_h != d->dil_h * (d->kh - 1) || 2 * d->pad_w != d->dil_w * (d->kw - 1)) return 0;
   if (out->n != in->n || out->h != in->h || out->w != in->w || out->n > 65535) return 0;
@@ -362,6 +368,7 @@ extern "C" int lfsr_conv2d_stem(const lfsr_tensor* in, const float* w_packed, co
   a.w = w_packed; a.bias = d->bias;
   a.kh = d->kh; a.kw = d->kw; a.dh = d->dil_h; a.dw = d->dil_w; a.ph = d->pad_h; a.pw = d->pad_w;
   a.act = d->act; a.slope = d->act_slope; a.perm_a = d->in_perm ? d->perm_a : 0;
+  a.bh = d->block_h > 0 ? d->block_h : in->h; a.bw = d->block_w > 0 ? d->block_w : in->w;
   dim3 grid(ceil_div(out->w, 16), ceil_div(out->h, 8), out->n);
   if (a.perm_a) {
     conv_stem_macpi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
