@@ -197,6 +197,17 @@ int lfsr_mel_epi_branch(const lfsr_tensor* in, const float* w_packed, const lfsr
  * Supports stride 1 (any dilation, "same" zero padding given by pad) and kh*kw <= 25. */
 size_t lfsr_conv2d_tc_packed_floats(int kh, int kw, int cin, int cout);
 int lfsr_pack_conv_tc(const float* w_oihw_host, float* packed_host, int kh, int kw, int cin, int cout);
+/* x = hi + lo with hi = x rounded to TF32 (exactly representable, so the tensor-core path reads it unchanged) and lo the
+ * remainder: conv(hi, w_hi) + conv(lo, w_hi) + conv(hi, w_lo) on the TF32 tensor cores equals the fp32 convolution to ~2^-21.
+ * Used for the last, image-producing convolution of LF-InterNet, whose rounding error would otherwise reach the output directly.
+ * Dense buffers of n floats. */
+int lfsr_split_tf32(const float* in, float* hi, float* lo, long long n, void* stream);
+/* MacPI2SAI + PixelShuffle(r) of a 1-channel reconstruction (DistgSSR.py:34-35, LF_InterNet.py:137-141 after the algebraic
+ * composition of the last two layers): in [n, H, W, r*r] holds, for the MacPI pixel (i*A+u, j*A+v), the r x r
+ * sub-pixel values of SAI pixel (u*H/A + i, v*W/A + j); out [n, H*r, W*r] is the high-resolution SAI image. accumulate != 0
+ * adds onto `out` (the interpolation skip already there). Lets the reconstruction conv run on the tensor cores, which do not
+ * address MacPI-permuted outputs. r in {2, 4}. */
+int lfsr_macpi_unshuffle(const lfsr_tensor* in, float* out, int ang, int r, int accumulate, void* stream);
 /* fp32 NHWC tensor -> its fp16 copy (round to nearest even): the operand copy of a tensor that did not come out of a
  * tensor-core epilogue (stems). Channel count a multiple of 8. */
 int lfsr_to_f16(const lfsr_tensor* in, const lfsr_tensor* out16, void* stream);

@@ -104,6 +104,8 @@ SIGNATURES = {
     "lfsr_conv2d_tc_packed_floats": (C.c_size_t, [_I, _I, _I, _I]),
     "lfsr_pack_conv_tc": (_I, [_P, _P, _I, _I, _I, _I]),
     "lfsr_to_f16": (_I, [_TP, _TP, _P]),
+    "lfsr_split_tf32": (_I, [_P, _P, _P, C.c_longlong, _P]),
+    "lfsr_macpi_unshuffle": (_I, [_TP, _P, _I, _I, _I, _P]),
     "lfsr_conv2d_tc16_packed_bytes": (C.c_size_t, [_I, _I, _I, _I]),
     "lfsr_pack_conv_tc16": (_I, [_P, _P, _I, _I, _I, _I]),
     "lfsr_scale_pack_tc": (_I, [_P, _P, C.c_int64, _P, _I, _I, _I, _I, _I, _P]),

@@ -743,6 +743,73 @@ to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long 
 }
 }  // namespace lfsr
 
+namespace lfsr {
+// thread = one SAI pixel (sy, sx) of the low-resolution mosaic: reads its r*r sub-pixel values from the MacPI-arranged tensor and
+// writes the r x r block of the high-resolution SAI image (consecutive threads -> consecutive 4r-byte runs of an output row)
+template <int R>
+__global__ void __launch_bounds__(256)
+macpi_unshuffle_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int A, int ld, int accumulate) {
+  const int sx = blockIdx.x * blockDim.x + threadIdx.x, sy = blockIdx.y, img = blockIdx.z;
+  if (sx >= W) return;
+  const int hh = H / A, ww = W / A;
+  const int u = sy / hh, i = sy - u * hh, v = sx / ww, j = sx - v * ww;
+  const float* src = in + ((size_t)((size_t)img * H + (i * A + u)) * W + (j * A + v)) * ld;
+  float vals[R * R];
+  if (R == 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 t = *reinterpret_cast<const float4*>(src + 4 * k);
+      vals[4 * k] = t.x; vals[4 * k + 1] = t.y; vals[4 * k + 2] = t.z; vals[4 * k + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < R * R; ++k) vals[k] = src[k];
+  }
+  float* dst = out + ((size_t)((size_t)img * H + sy) * R) * ((size_t)W * R) + (size_t)sx * R;
+#pragma unroll
+  for (int a = 0; a < R; ++a) {
+    float* row = dst + (size_t)a * W * R;
+#pragma unroll
+    for (int b = 0; b < R; ++b) row[b] = accumulate ? row[b] + vals[a * R + b] : vals[a * R + b];
+  }
+}
+}  // namespace lfsr
+
+namespace lfsr {
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = reinterpret_cast<const float4*>(in)[i];
+    float4 h, l;
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.x)); h.x = __uint_as_float(t); l.x = x.x - h.x;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.y)); h.y = __uint_as_float(t); l.y = x.y - h.y;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.z)); h.z = __uint_as_float(t); l.z = x.z - h.z;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.w)); h.w = __uint_as_float(t); l.w = x.w - h.w;
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+  }
+}
+}  // namespace lfsr
+
+extern "C" int lfsr_split_tf32(const float* in, float* hi, float* lo, long long n, void* stream) {
+  LFSR_REQUIRE(in && hi && lo && n > 0 && n % 4 == 0 && (((uintptr_t)in | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0,
+               "lfsr_split_tf32: 16-byte aligned buffers with a multiple of 4 elements required");
+  lfsr::split_tf32_kernel<<<(unsigned)capped_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(in, hi, lo, n / 4);
+  return check_launch("split_tf32_kernel");
+}
+
+extern "C" int lfsr_macpi_unshuffle(const lfsr_tensor* in, float* out, int ang, int r, int accumulate, void* stream) {
+  LFSR_REQUIRE(tensor_ok(in) && out, "lfsr_macpi_unshuffle: null/invalid tensor");
+  LFSR_REQUIRE(ang > 0 && in->h % ang == 0 && in->w % ang == 0 && in->c == r * r && (r == 2 || r == 4) && in->n <= 65535 && in->h <= 65535,
+               "lfsr_macpi_unshuffle: needs r in {2, 4}, r*r channels and a mosaic divisible by the angular resolution");
+  LFSR_REQUIRE(in->ld % 4 == 0 && ((uintptr_t)in->ptr & 15) == 0, "lfsr_macpi_unshuffle: 16-byte aligned pixels required");
+  dim3 grid(ceil_div(in->w, 256), in->h, in->n);
+  if (r == 4) lfsr::macpi_unshuffle_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in->ptr, out, in->h, in->w, ang, in->ld, accumulate);
+  else lfsr::macpi_unshuffle_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in->ptr, out, in->h, in->w, ang, in->ld, accumulate);
+  return check_launch("macpi_unshuffle_kernel");
+}
+
 extern "C" int lfsr_to_f16(const lfsr_tensor* in, const lfsr_tensor* out16, void* stream) {
   LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out16), "lfsr_to_f16: null/invalid tensor");
   LFSR_REQUIRE(in->n == out16->n && in->h == out16->h && in->w == out16->w && in->c == out16->c, "lfsr_to_f16: shape mismatch");

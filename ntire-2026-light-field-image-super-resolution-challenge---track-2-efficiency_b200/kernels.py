@@ -282,6 +282,17 @@ class CudaOps:
             raise N.LfsrError("conv: this layer does not qualify for the fp16 operand path")
         N.check(self.lib.lfsr_conv2d_tc(C.byref(tin), w.data_ptr(), C.byref(tout), C.byref(d), self._stream(x)), "lfsr_conv2d_tc")
 
+    def split_tf32(self, x, hi, lo):
+        """dense fp32 tensors: hi = tf32(x), lo = x - hi"""
+        if not (x.is_contiguous() and hi.is_contiguous() and lo.is_contiguous()):
+            raise N.LfsrError("split_tf32: dense tensors required")
+        N.check(self.lib.lfsr_split_tf32(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), self._stream(x)), "lfsr_split_tf32")
+
+    def macpi_unshuffle(self, x, out, ang, r, accumulate):
+        """x [n,H,W,r*r] (MacPI arrangement) -> out [n,1,H*r,W*r] SAI image (+= when accumulate)"""
+        N.check(self.lib.lfsr_macpi_unshuffle(C.byref(as_tensor(x, "unshuffle.in")), out.data_ptr(), ang, r, 1 if accumulate else 0,
+                                              self._stream(x)), "lfsr_macpi_unshuffle")
+
     def to_f16(self, x, out16):
         N.check(self.lib.lfsr_to_f16(C.byref(as_tensor(x, "to_f16.in")), C.byref(as_tensor(out16, "to_f16.out", f16=True)),
                                      self._stream(x)), "lfsr_to_f16")

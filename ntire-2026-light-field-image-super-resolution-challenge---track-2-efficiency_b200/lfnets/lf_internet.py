@@ -93,7 +93,12 @@ class get_model(LFNetBase):
         wf = self.ReconBlock.FinalConv.weight.detach().double()[0, :, 0, 0]       # [64]
         ch = wf.numel()
         w_eff = torch.einsum("c,crikl->rikl", wf, wp.view(ch, s * s, *wp.shape[1:]))
-        pk["recon"] = pc(w_eff.float(), **dil)
+        # the image-producing conv: TF32 tensor cores with hi / lo splits of weights and activations (3 passes ~ fp32 accuracy)
+        w_eff = w_eff.float()
+        w_hi = (w_eff.contiguous().view(torch.int32) + 0x1000 & ~0x1FFF).view(torch.float32)
+        pk["recon"] = pc(w_eff, **dil)
+        pk["recon_hi"] = pc(w_hi, tc=True, **dil)
+        pk["recon_lo"] = pc(w_eff - w_hi, tc=True, **dil)
         return pk
 
     @staticmethod
@@ -148,9 +153,9 @@ class get_model(LFNetBase):
         ab = b16("ab", h, w, C)
         ops.conv(CAh[..., 0:nb * C], pk["bn_ang"], None, out16=ab, act=RL)
         ops.conv(ab, pk["bn_a2s"], None, out16=CSh[..., nb * C:(nb + 1) * C], shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
-        fin = ps[0][0][..., 0:C]
+        fin = buf("fin", H, W, C)
         ops.conv(CSh, pk["bn_spa"], fin, act=RL, res=xs0)
-        ops.conv(fin, pk["recon"], Y, out_perm=N.PERM_MACPI_OVER_SAI, perm_a=A, shuffle=(s, s, N.SHUF_CHANNEL_MAJOR))
+        self._recon(ops, pk, fin, out, B, H, W)
 
     def _run(self, ops, pk, x, out):
         if pk.get("f16"):
@@ -202,10 +207,26 @@ class get_model(LFNetBase):
         ab = buf("ab", h, w, C)
         ops.conv(CA[..., 0:nb * C], pk["bn_ang"], ab, act=RL)
         ops.conv(ab, pk["bn_a2s"], CS[..., nb * C:(nb + 1) * C], shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
-        fin = ps[0][..., 0:C]
+        fin = buf("fin", H, W, C)
         ops.conv(CS, pk["bn_spa"], fin, act=RL, res=xs0)
-        # composed ReconBlock: 3x3 d=A 64->s^2, MacPI->SAI, PixelShuffle(s)
-        ops.conv(fin, pk["recon"], Y, out_perm=N.PERM_MACPI_OVER_SAI, perm_a=A, shuffle=(s, s, N.SHUF_CHANNEL_MAJOR))
+        self._recon(ops, pk, fin, out, B, H, W)
+
+    def _recon(self, ops, pk, fin, out, B, H, W):
+        """composed ReconBlock: 3x3 d=A 64->s^2 (tensor cores, MacPI arrangement), then MacPI->SAI + PixelShuffle(s) as one
+        addressing pass (the tensor-core epilogue does not address permuted outputs)"""
+        A, s = self.angRes, self.scale
+        if hasattr(ops, "macpi_unshuffle") and hasattr(ops, "split_tf32") and s in (2, 4) and getattr(ops, "use_tc", True):
+            C = self.channels
+            rec = self._buf("recon", B, H, W, s * s, fin.device)
+            hi, lo = self._buf("fin_hi", B, H, W, C, fin.device), self._buf("fin_lo", B, H, W, C, fin.device)
+            ops.split_tf32(fin, hi, lo)
+            ops.conv(hi, pk["recon_hi"], rec)
+            ops.conv(lo, pk["recon_hi"], rec, res=rec)
+            ops.conv(hi, pk["recon_lo"], rec, res=rec)
+            ops.macpi_unshuffle(rec, out, A, s, False)
+        else:
+            Y = out.view(B, H * s, W * s, 1)
+            ops.conv(fin, pk["recon"], Y, out_perm=N.PERM_MACPI_OVER_SAI, perm_a=A, shuffle=(s, s, N.SHUF_CHANNEL_MAJOR))
 
 
 get_loss = L1Loss

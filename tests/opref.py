@@ -135,6 +135,18 @@ class RefOps:
         if out16 is not None:          # fp16 copy of the fp32 result (the product path rounds the same way)
             out16.copy_(y.permute(0, 2, 3, 1))
 
+    def split_tf32(self, x, hi, lo):
+        h = (x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF          # round the magnitude to 10 mantissa bits (ties away)
+        hi.copy_(h.view(torch.float32).view_as(x))
+        lo.copy_(x - hi)
+
+    def macpi_unshuffle(self, x, out, ang, r, accumulate):
+        n, H, W, _ = x.shape
+        y = rearrange(_nchw(x), "b c (h u) (w v) -> b c (u h) (v w)", u=ang, v=ang)            # MacPI -> SAI
+        y = F.pixel_shuffle(y, r).reshape(n, 1, H * r, W * r)
+        o = out.view(n, 1, H * r, W * r)
+        o.copy_(o + y if accumulate else y)
+
     def to_f16(self, x, out16):
         out16.copy_(x)
 

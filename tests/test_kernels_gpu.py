@@ -255,6 +255,30 @@ def test_sa_modulate(ops, ref, c, h, w):
     assert (a - b).abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("r", [2, 4])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_macpi_unshuffle_bit_exact(ops, ref, r, accumulate):
+    """MacPI2SAI + PixelShuffle(r) of the reconstruction (LF_InterNet.py:150-158, DistgSSR.py:42-46): pure index work"""
+    n, A, h = 3, 5, 8
+    x = nhwc(n, A * h, A * h, r * r, seed=5)
+    a = torch.randn(n, 1, A * h * r, A * h * r, device="cuda")
+    b = a.clone()
+    ops.macpi_unshuffle(x, a, A, r, accumulate)
+    ref.macpi_unshuffle(x, b, A, r, accumulate)
+    assert torch.equal(a, b)
+
+
+def test_split_tf32_exact(ops, ref):
+    """hi is TF32-representable, hi + lo == x exactly, and both match the integer restatement"""
+    x = torch.randn(5, 8, 8, 64, device="cuda") * torch.logspace(-6, 3, 64, device="cuda")
+    hi, lo, hr, lr = (torch.empty_like(x) for _ in range(4))
+    ops.split_tf32(x, hi, lo)
+    ref.split_tf32(x, hr, lr)
+    assert torch.equal(hi, hr) and torch.equal(lo, lr)
+    assert torch.equal(hi + lo, x)
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
 @pytest.mark.parametrize("c,sliced,with_res", [(64, False, True), (64, True, True), (54, False, False), (18, True, True)])
 def test_scale_add(ops, ref, c, sliced, with_res):
     """out = x * scale[n, c] + res (ChannelAttention + block residual, MyEfficientLFNetV4_5.py:147-148, :297-299)"""
