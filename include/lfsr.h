@@ -102,6 +102,8 @@ int lfsr_abi_version(void);
 int lfsr_built_for_sm100a(void);
 /* number of kernel launches issued by this library in the calling process since load */
 uint64_t lfsr_launch_count(void);
+/* how many lfsr_conv2d_tc calls took the two-CTAs-per-SM kernel for narrow fp16 layers (tests assert the path taken) */
+uint64_t lfsr_conv_tc_lean_count(void);
 
 /* ---- patch pipeline ------------------------------------------------------------------ */
 /* LFdivide + ImageExtend (utils/utils.py:137-166): scene [A*h0, A*w0] -> [numU*numV, A*P, A*P],

@@ -84,6 +84,7 @@ SIGNATURES = {
     "lfsr_abi_version": (_I, []),
     "lfsr_built_for_sm100a": (_I, []),
     "lfsr_launch_count": (C.c_uint64, []),
+    "lfsr_conv_tc_lean_count": (C.c_uint64, []),
     "lfsr_divide": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "lfsr_divide_rows": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "lfsr_integrate_rows": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

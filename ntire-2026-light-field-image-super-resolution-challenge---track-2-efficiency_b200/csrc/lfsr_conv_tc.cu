@@ -15,6 +15,7 @@
 //     stages let the epilogue of tile i overlap the MMAs of tile i+1. Persistent CTAs, one per SM.
 // TF32: activations are converted by the TMA unit (tensor map type TFLOAT32), weights are rounded
 // to nearest-even at pack time; accumulation is fp32.
+#include <atomic>
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -25,6 +26,7 @@
 namespace lfsr {
 namespace tc {
 
+static std::atomic<uint64_t> g_lean_launches{0};   // launches that took conv_tc_lean_kernel (tests assert the path)
 constexpr int kThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
 constexpr int kEpiWarps = 8;
 constexpr int kTmaWarp = 8, kMmaWarp = 9;
@@ -605,12 +607,15 @@ __device__ __forceinline__ void epilogue_tile_tma(const Params& p, const CUtenso
   const int chunk_lo = tc_.chunk * p.NC;
   const int chunk_hi = chunk_lo + p.NC < p.cout ? chunk_lo + p.NC : p.cout;
   int bi = 0;
+  long long tp = 0;
+#define LFSR_EPI_TICK(i) if (dbg_rd) { const long long t_ = clock64(); dbg_rd[i] += t_ - tp; tp = t_; }
   for (int pc0 = chunk_lo, ncols = 0; pc0 < chunk_hi; pc0 += ncols, ++bi) {
     int sub = 0, c0 = pc0;
     if (r2 > 1) { sub = fdiv(pc0, p.fd_cq); c0 = pc0 - sub * p.cq; }
     ncols = p.cq - c0 < 32 ? p.cq - c0 : 32;
     if (chunk_hi - pc0 < ncols) ncols = chunk_hi - pc0;
     if (bi % g_step != g_first) continue;
+    if (dbg_rd) tp = clock64();
     const int tcol = pc0 - chunk_lo;                           // TMEM column of the block
     // columns right of the block are clipped by the channel dim of the tensor store; fp16-only outputs are stored from
     // registers (any block shape), so they always take the lane-per-pixel path
@@ -640,7 +645,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const Params& p, const CUtenso
         }
       }
     }
+    LFSR_EPI_TICK(1)
     if (!waited) { mbar_wait(tfull_bar, tfull_parity); tc_fence_after(); waited = true; }
+    LFSR_EPI_TICK(2)
     float v[32];
     tmem_ld16(taddr + tcol, v);
     if (ncols > 16) tmem_ld16(taddr + tcol + 16, v + 16);
@@ -648,6 +655,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const Params& p, const CUtenso
 #pragma unroll
       for (int k = 16; k < 32; ++k) v[k] = 0.f;
     }
+    LFSR_EPI_TICK(3)
     if (tma_ok) {
       if (p.bias) {
 #pragma unroll
@@ -683,13 +691,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const Params& p, const CUtenso
         v[4 * k + 2] = fmaf(v[4 * k + 2], alpha, xv[k].z); v[4 * k + 3] = fmaf(v[4 * k + 3], alpha, xv[k].w);
       }
     }
-    long long trd = 0;
-    if (dbg_rd) trd = clock64();
+    LFSR_EPI_TICK(4)
     if (p.out_mode != 2) {
       if (lane == 0) bulk_wait_read0();        // the TMA unit has finished reading the previous block out of `stg`
       __syncwarp();
     }
-    if (dbg_rd) *dbg_rd += clock64() - trd;
+    LFSR_EPI_TICK(0)
     if (p.out_mode != 2) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -707,6 +714,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const Params& p, const CUtenso
               make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]), pack_h2(v[8 * j + 4], v[8 * j + 5]),
                          pack_h2(v[8 * j + 6], v[8 * j + 7]));
     }
+    LFSR_EPI_TICK(5)
     if (tma_ok) {
       if (p.out_mode != 2) { fence_proxy_async(); __syncwarp(); }
       if (lane == 0 && p.out_mode != 2) {
@@ -725,7 +733,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const Params& p, const CUtenso
       else epi_writeout_act<1>(p, stg, lane, q, tc_, pc0, ncols, 0);
       __syncwarp();
     }
+    LFSR_EPI_TICK(6)
   }
+#undef LFSR_EPI_TICK
   if (!waited) { mbar_wait(tfull_bar, tfull_parity); tc_fence_after(); }
 }
 
@@ -1101,7 +1111,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* stg = sEpi + warp * 1024;
     uint32_t tcount = 0;
     int m_, chunk_;
-    long long dbg_wait = 0, dbg_t0 = 0, tw0 = 0, dbg_ld = 0, dbg_epi = 0;
+    long long dbg_wait = 0, dbg_t0 = 0, tw0 = 0, dbg_epi = 0;
+    long long dbg_seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long& dbg_ld = dbg_seg[0];
     if ((DBG && p.dbg)) dbg_t0 = clock64();
     for (int i = 0; next_tile(p, i, m_, chunk_); ++i, ++tcount) {
       const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
@@ -1112,7 +1124,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         epilogue_tile_tail(p, sTail, taddr, lane, q, tc_, half, 2, tfull + a, aph);
       } else if (p.tma_epi && m_ >= 0) {
         if ((DBG && p.dbg)) tw1 = clock64();
-        epilogue_tile_tma(p, &tmO, stg, taddr, lane, q, tc_, half, 2, tfull + a, aph, (DBG && p.dbg) ? &dbg_ld : nullptr);
+        epilogue_tile_tma(p, &tmO, stg, taddr, lane, q, tc_, half, 2, tfull + a, aph, (DBG && p.dbg) ? dbg_seg : nullptr);
         if ((DBG && p.dbg)) dbg_epi += clock64() - tw1;
       } else {
         if ((DBG && p.dbg)) tw0 = clock64();
@@ -1132,6 +1144,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if ((DBG && p.dbg) && threadIdx.x == 0) {
       p.dbg[blockIdx.x * 8 + 1] = dbg_epi;
       p.dbg[blockIdx.x * 8 + 6] = dbg_wait; p.dbg[blockIdx.x * 8 + 7] = clock64() - dbg_t0;
+      for (int k = 1; k < 7; ++k) p.dbg[gridDim.x * 8 + blockIdx.x * 8 + k] = dbg_seg[k];     // (second table: phases inside the TMA-store epilogue)
     }
   }
   __syncthreads();
@@ -1139,6 +1152,240 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == kMmaWarp) {
     __syncwarp();
     if (CTA2) tmem_dealloc2(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+
+// ======================= lean kernel: narrow fp16 layers, TWO CTAs per SM ===========================================
+// probe_tc_roles16.py / the ncu source view of the N <= 64 layers on fp16 operands: nothing is saturated (tensor pipe 22 %,
+// L2 -> SM 32 %, shared memory 32 %); a tile is a chain of dependent latencies - TMA round trip per 2-stage ring, ~300 cycles
+// per stage boundary of the issuing lane, and a ~3-4 k-cycle epilogue per 32 x 32 block on 2 warps per scheduler. Two
+// independent CTAs per SM overlap each other's bubbles. That needs <= 80 registers (2 x 12 allocated warps) and <= 113 KB /
+// 256 TMEM columns per CTA: this kernel keeps only what those layers use - same-size / strided fp16 activations through the
+// same tensor maps and stage ring, N <= 64 in one chunk, no PixelShuffle / multiplier / tail projection, bias from shared
+// memory, activation none / ReLU / LeakyReLU as one select, residual prefetched before the accumulator wait, the 32-column
+// block handled as two 16-column halves (16 live accumulators), output fp32 through the tensor store and / or fp16 from
+// registers (OUT_MODE = lfsr_conv_desc.out_mode).
+constexpr int kLeanTmemCols = 256;
+constexpr int kLeanAccStride = 128;
+constexpr int kLeanSmem = 112 * 1024;
+
+// (register files are allocated per 4-warp group: the bound is stated for 384 threads so that ptxas budgets 2 x 12 warps)
+template <int OUT_MODE, bool HAS_RES>
+__global__ void __launch_bounds__(384, 2)
+conv_tc_lean_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmO, const Params p) {
+  constexpr int CG = 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const int nks = p.kh * p.kw * p.cgs;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + p.stages * p.kps * kABytes;
+  float* sEpi = reinterpret_cast<float*>(sB + (p.resident ? nks : p.stages * p.kps) * p.b_stage_bytes);
+  float* sBias = sEpi + (OUT_MODE != 2 ? kEpiWarps * 1024 : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 64);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 64) sBias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.cout) ? __ldg(p.bias + threadIdx.x) : 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, kEpiWarps); }
+    mbar_init(bfull, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (OUT_MODE != 2) tma_prefetch_desc(&tmO);
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, kLeanTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int G = (int)gridDim.x;
+
+  if (warp == kTmaWarp) {
+    if (elect_one()) {
+      int s_ring = 0;
+      uint32_t ph_ring = 0;
+      const uint32_t stage_bytes = kABytes + (p.resident ? 0 : p.NC * 128);
+      if (p.resident && (int)blockIdx.x < p.m_tiles) {
+        mbar_expect_tx(bfull, (uint32_t)nks * p.b_stage_bytes);
+        for (int ks = 0; ks < nks; ++ks) tma_load_2d(sB + ks * p.b_stage_bytes, &tmB, bfull, 0, ks * p.NC);
+      }
+      for (int m = blockIdx.x; m < p.m_tiles; m += G) {
+        const TileCoord tc_ = decode_tile(p, m, 0);
+        int cg = 0, tap = 0;
+        int b1, b2, b3, b4;
+        if (p.amode == 0) { b1 = tc_.x0; b2 = tc_.vx; b3 = tc_.y0; b4 = tc_.nb; }
+        else if (p.amode == 1) { b1 = 0; b2 = tc_.x0; b3 = tc_.y0; b4 = tc_.nb; }
+        else if (p.amode == 2) { b1 = tc_.x0; b2 = 0; b3 = tc_.y0; b4 = tc_.nb; }
+        else { b1 = 0; b2 = tc_.x0; b3 = 0; b4 = tc_.nb * p.out_rows_per_img + tc_.y0; }
+        for (int ks = 0; ks < nks; ks += p.kps) {
+          if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
+          const int s = s_ring++;
+          mbar_wait(empty + s, ph_ring ^ 1);
+          const int nsub = nks - ks < p.kps ? nks - ks : p.kps;
+          mbar_expect_tx(full + s, (uint32_t)nsub * stage_bytes);
+          for (int u = 0; u < nsub; ++u) {
+            const short* to = p.tap_off[tap];
+            const int slot = s * p.kps + u;
+            tma_load_5d(sA + slot * kABytes, &tmA, full + s, cg * CG, b1 + to[0], b2 + to[1], b3 + to[2], b4 + to[3]);
+            if (!p.resident) tma_load_2d(sB + slot * p.b_stage_bytes, &tmB, full + s, 0, (ks + u) * p.NC);
+            if (++cg == p.cgs) { cg = 0; ++tap; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    if (elect_one()) {
+      uint32_t tcount = 0;
+      int s_ring = 0;
+      uint32_t ph_ring = 0;
+      const uint32_t idesc = make_idesc(p.NC, 0u);
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(sA)), b_desc0 = make_smem_desc(smem_u32(sB));
+      const int rem_last = p.C - (p.cgs - 1) * CG;
+      const int ksteps_last = rem_last >= CG ? 4 : (rem_last + 15) >> 4;
+      const uint32_t b_step = (uint32_t)(p.b_stage_bytes >> 4);
+      const uint32_t a_stage_step = (uint32_t)(p.kps * (kABytes >> 4)), b_stage_step = (uint32_t)p.kps * b_step;
+      const bool tap_stages = p.kps == p.cgs;
+      if (p.resident && (int)blockIdx.x < p.m_tiles) mbar_wait(bfull, 0);
+      for (int m = blockIdx.x; m < p.m_tiles; m += G, ++tcount) {
+        const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(tempty + a, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * kLeanAccStride;
+        int cg_i = 0;
+        for (int ks = 0; ks < nks; ks += p.kps) {
+          if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
+          const int s = s_ring++;
+          mbar_wait(full + s, ph_ring);
+          tc_fence_after();
+          const uint64_t a_d0 = a_desc0 + (uint64_t)(s * a_stage_step);
+          const uint64_t b_d0 = b_desc0 + (uint64_t)(p.resident ? ks * b_step : s * b_stage_step);
+          if (tap_stages) {
+            if (ks == 0) umma_tap_dispatch<true, true>(p.cgs, d_tmem, a_d0, b_d0, b_step, idesc, ksteps_last);
+            else umma_tap_dispatch<false, true>(p.cgs, d_tmem, a_d0, b_d0, b_step, idesc, ksteps_last);
+          } else {
+            const int nsub = nks - ks < p.kps ? nks - ks : p.kps;
+            for (int u = 0; u < nsub; ++u) {
+              const int ksteps = (cg_i == p.cgs - 1) ? ksteps_last : 4;
+              const uint64_t a_d = a_d0 + (uint64_t)(u * (kABytes >> 4));
+              const uint64_t b_d = b_d0 + (uint64_t)(u * b_step);
+              if (ks + u == 0) umma_stage<true, true>(d_tmem, a_d, b_d, idesc, ksteps);
+              else umma_stage<false, true>(d_tmem, a_d, b_d, idesc, ksteps);
+              if (++cg_i == p.cgs) cg_i = 0;
+            }
+          }
+          umma_commit(empty + s);
+          if (ks + p.kps >= nks) umma_commit(tfull + a);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: warp w <-> TMEM lane quarter w & 3, column block w >> 2 (32 columns); a lane owns one pixel ----
+    const int q = warp & 3;
+    const int pc0 = (warp >> 2) * 32;
+    const int ncols = p.cout - pc0 < 32 ? p.cout - pc0 : 32;         // <= 0: this warp only keeps the barrier phases
+    float* stg = sEpi + warp * 1024;
+    const int tw_mask = p.TW - 1;
+    const int mpx = q * 32 + lane;
+    const int ty = mpx >> p.tw_shift, tx = mpx & tw_mask;
+    const int ty_w = (q * 32) >> p.tw_shift, tx_w = (q * 32) & tw_mask;
+    const float slope = p.act == LFSR_ACT_NONE ? 1.f : (p.act == LFSR_ACT_RELU ? 0.f : p.slope);
+    const float alpha = p.alpha;
+    uint32_t tcount = 0;
+    for (int m = blockIdx.x; m < p.m_tiles; m += G, ++tcount) {
+      const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+      if (ncols > 0) {
+        const TileCoord tc_ = decode_tile(p, m, 0);
+        const bool pix_ok = tc_.y0 + ty < p.bh && tc_.x0 + tx < p.bw;
+        const int img = fdiv(tc_.nb, p.fd_nby);
+        const int Y = (tc_.nb - img * p.nby) * p.bh + tc_.y0 + ty, X = tc_.vx * p.bw + tc_.x0 + tx;
+        float4 xv[8];
+        if (HAS_RES) {
+          const float* rp = p.res.p + p.res.pix(img, Y, X) + pc0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            xv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pix_ok && 4 * k < ncols) xv[k] = *reinterpret_cast<const float4*>(rp + 4 * k);
+          }
+        }
+        __half* dst16 = nullptr;
+        if (OUT_MODE != 0) dst16 = p.out16 + ((size_t)((size_t)img * p.out16_h + Y) * p.out16_w + X) * (size_t)p.out16_ld + pc0;
+        mbar_wait(tfull + a, aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kLeanAccStride + pc0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h * 16 < ncols) {
+            float v[16];
+            tmem_ld16(taddr + h * 16, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = *reinterpret_cast<const float4*>(sBias + pc0 + h * 16 + 4 * j);
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
+            if (HAS_RES) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 r = xv[4 * h + j];
+                v[4 * j] = fmaf(v[4 * j], alpha, r.x); v[4 * j + 1] = fmaf(v[4 * j + 1], alpha, r.y);
+                v[4 * j + 2] = fmaf(v[4 * j + 2], alpha, r.z); v[4 * j + 3] = fmaf(v[4 * j + 3], alpha, r.w);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) v[k] *= alpha;
+            }
+            if (OUT_MODE != 2) {
+              if (h == 0) {
+                if (lane == 0) bulk_wait_read0();        // the TMA unit has finished reading the previous block out of `stg`
+                __syncwarp();
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(stg + lane * 32 + (((4 * h + j) ^ (lane & 7)) << 2)) =
+                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (OUT_MODE != 0 && pix_ok) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<uint4*>(dst16 + h * 16 + 8 * j) =
+                    make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]),
+                               pack_h2(v[8 * j + 4], v[8 * j + 5]), pack_h2(v[8 * j + 6], v[8 * j + 7]));
+            }
+          }
+        }
+        if (OUT_MODE != 2) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_5d(&tmO, stg, pc0, tc_.x0 + tx_w, tc_.vx, tc_.y0 + ty_w, tc_.nb);
+            bulk_commit();
+          }
+        }
+      } else {
+        mbar_wait(tfull + a, aph);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + a);
+    }
+    if (OUT_MODE != 2 && lane == 0) bulk_wait0();
+  }
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, kLeanTmemCols);
   }
 }
 
@@ -1549,6 +1796,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
         opt_in_smem(conv_tc_kernel<false, false, true>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, false, true>, 227 * 1024, w_) ||
 #ifdef LFSR_DEBUG_HOOKS
         opt_in_smem(conv_tc_kernel<false, true, false>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, true, false>, 227 * 1024, w_) ||
+        opt_in_smem(conv_tc_kernel<false, true, true>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, true, true>, 227 * 1024, w_) ||
 #endif
         opt_in_smem(conv_tc_halo_kernel, 227 * 1024, w_))
       return LFSR_ERR_CUDA;
@@ -1837,6 +2085,61 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
                                        "multiples of 8, 16-byte aligned rows, no residual + multiplier pair)");
   }
   static const bool verbose = dbg_env("LFSR_TC_VERBOSE") != nullptr;
+  // ---- lean path (conv_tc_lean_kernel): narrow fp16 layers run as two independent CTAs per SM -------------------------
+  {
+    static const bool no_lean = dbg_env("LFSR_TC_NO_LEAN") != nullptr;
+    const bool act_ok = p.act == LFSR_ACT_NONE || p.act == LFSR_ACT_RELU || p.act == LFSR_ACT_LRELU;
+    bool lean = f16 && !no_lean && !p.cta2 && !p.twin && !p.pair && !per_image_w && !p.tail_w && p.tma_epi && ry * rx == 1 &&
+                !d->mul.ptr && act_ok && p.nchunks == 1 && p.NC <= 64 && p.cout % 16 == 0 && !p.dbg && p.m_tiles >= 2 * sm_count;
+    int l_kps = 0, l_stages = 0, l_res = 0;
+    size_t l_smem = 0;
+    if (lean) {
+      const int stg = d->out_mode != 2 ? kEpiWarps * 4096 : 0;
+      const long long fixed = 1024 + stg + 256 + (2 * kMaxStages + 6) * 8 + 16;
+      const long long b_all = (long long)nks * p.b_stage_bytes;
+      int kps_hi = kps_env > 0 ? kps_env : (p.cgs <= 2 ? 4 / p.cgs * p.cgs : p.cgs);
+      if (kps_hi > nks) kps_hi = nks;
+      for (int kps = kps_hi; kps >= 1 && !l_stages; --kps) {
+        if (kps_env > 0 && kps != kps_env) break;
+        for (int res = no_resident ? 0 : 1; res >= 0 && !l_stages; --res) {
+          const long long per_stage = (long long)kps * (kABytes + (res ? 0 : p.b_stage_bytes));
+          const long long left = kLeanSmem - fixed - (res ? b_all : 0);
+          int st = left > 0 ? (int)(left / per_stage) : 0;
+          if (st > kMaxStages) st = kMaxStages;
+          if (st >= 2) { l_kps = kps; l_stages = st; l_res = res; l_smem = (size_t)(fixed + (res ? b_all : 0) + st * per_stage); }
+        }
+      }
+      lean = l_stages >= 2;
+    }
+    if (lean) {
+      p.kps = l_kps; p.stages = l_stages; p.resident = l_res;
+      static DevOnce once_lean;
+      if (once_lean.need()) {
+        const char* w_ = "lfsr_conv2d_tc (lean)";
+        if (opt_in_smem(conv_tc_lean_kernel<0, false>, kLeanSmem, w_) || opt_in_smem(conv_tc_lean_kernel<0, true>, kLeanSmem, w_) ||
+            opt_in_smem(conv_tc_lean_kernel<1, false>, kLeanSmem, w_) || opt_in_smem(conv_tc_lean_kernel<1, true>, kLeanSmem, w_) ||
+            opt_in_smem(conv_tc_lean_kernel<2, false>, kLeanSmem, w_) || opt_in_smem(conv_tc_lean_kernel<2, true>, kLeanSmem, w_))
+          return LFSR_ERR_CUDA;
+        once_lean.done();
+      }
+      const int lgrid = p.m_tiles < 2 * sm_count ? p.m_tiles : 2 * sm_count;
+      if (verbose)
+        fprintf(stderr, "[lfsr tc lean] C=%d cout=%d NC=%d k=%dx%d tiles=%d grid=%d stages=%d kps=%d resident=%d out_mode=%d res=%d smem=%zu\n",
+                p.C, p.cout, p.NC, p.kh, p.kw, p.m_tiles, lgrid, p.stages, p.kps, p.resident, d->out_mode, d->res.ptr ? 1 : 0, l_smem);
+      cudaStream_t st_ = (cudaStream_t)stream;
+      const bool hr = d->res.ptr != nullptr;
+      switch (d->out_mode * 2 + (hr ? 1 : 0)) {
+        case 0: conv_tc_lean_kernel<0, false><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p); break;
+        case 1: conv_tc_lean_kernel<0, true><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p); break;
+        case 2: conv_tc_lean_kernel<1, false><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p); break;
+        case 3: conv_tc_lean_kernel<1, true><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p); break;
+        case 4: conv_tc_lean_kernel<2, false><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p); break;
+        default: conv_tc_lean_kernel<2, true><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p); break;
+      }
+      g_lean_launches.fetch_add(1);
+      return check_launch("conv_tc_lean_kernel");
+    }
+  }
   if (verbose)
     fprintf(stderr, "[lfsr tc] C=%d cout=%d NC=%d k=%dx%d tiles=%d grid=%d stages=%d kps=%d resident=%d pair=%d twin=%d cta2=%d TH=%d TW=%d vec=%d tma_epi=%d smem=%zu\n",
             p.C, p.cout, p.NC, p.kh, p.kw, p.total_tiles, grid, p.stages, p.kps, p.resident, p.pair, p.twin, p.cta2, p.TH, p.TW, p.vec, p.tma_epi, smem);
@@ -1852,6 +2155,9 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   if (p.dbg && !f16)
     le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, false>, tmA, tmB, tmBh, tmO, p)
                 : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, false>, tmA, tmB, tmBh, tmO, p);
+  else if (p.dbg)
+    le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, true>, tmA, tmB, tmBh, tmO, p)
+                : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, true>, tmA, tmB, tmBh, tmO, p);
   else
 #endif
   if (f16)
@@ -1863,3 +2169,5 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   if (le != cudaSuccess) { set_error("lfsr_conv2d_tc: launch failed: %s", cudaGetErrorString(le)); return LFSR_ERR_CUDA; }
   return check_launch("conv_tc_kernel");
 }
+
+extern "C" uint64_t lfsr_conv_tc_lean_count(void) { return lfsr::tc::g_lean_launches.load(); }

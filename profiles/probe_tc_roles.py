@@ -3,7 +3,7 @@ usage: python profiles/probe_tc_roles.py [batch]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
 os.environ["LFSR_TC_DBG_PTR"] = hex(dbg.data_ptr())
 os.environ.setdefault("LFSR_PROBE_LIB", "1")   # liblfsr_probe.so: probe kernels + debug hooks (not in the product library)
 import lfsr_b200
@@ -22,7 +22,7 @@ for (cin, cout, hw, k, dil, res) in ((64, 64, 160, 1, 1, False), (64, 64, 160, 1
     for _ in range(2):
         ops.conv(x, pc, y, res=r)
     torch.cuda.synchronize()
-    d = dbg.view(148, 8).double().mean(0).tolist()
+    d = dbg[:148 * 8].view(148, 8).double().mean(0).tolist()
     ntile = B * hw * hw / 128 / 148
     print(f"{k}x{k} {cin}->{cout} @{hw} d{dil} res={int(res)}: tiles/CTA {ntile:.0f} | "
           f"MMA thread: wait-full {d[2]/ntile:.0f}, wait-acc {d[3]/ntile:.0f}, issue {d[4]/ntile:.0f} of {d[5]/ntile:.0f} cyc/tile | "

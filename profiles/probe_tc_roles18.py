@@ -2,7 +2,7 @@
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
 os.environ["LFSR_TC_DBG_PTR"] = hex(dbg.data_ptr())
 os.environ["LFSR_TC_VERBOSE"] = "1"
 os.environ.setdefault("LFSR_PROBE_LIB", "1")   # liblfsr_probe.so: probe kernels + debug hooks (not in the product library)
@@ -28,7 +28,7 @@ for (cin, cout, k, dil, src, dst) in ((18, 18, 3, 5, trunk[..., 0:18], cat[..., 
         ops.conv(src, pc, dst, act=2, slope=0.1)
     e1.record()
     torch.cuda.synchronize()
-    d = dbg.view(148, 8).double().mean(0).tolist()
+    d = dbg[:148 * 8].view(148, 8).double().mean(0).tolist()
     ntile = B * 160 * 160 / 128 / 148
     print(f"{k}x{k} d{dil} {cin}->{cout}: {e0.elapsed_time(e1) / 10:.3f} ms | tiles/CTA {ntile:.0f} | MMA thread: wait-full {d[2]/ntile:.0f}, "
           f"wait-acc {d[3]/ntile:.0f}, issue {d[4]/ntile:.0f} of {d[5]/ntile:.0f} cyc/tile | epilogue: wait {d[6]/ntile:.0f}, work {d[1]/ntile:.0f} of {d[7]/ntile:.0f}")

@@ -546,6 +546,70 @@ F16_CASES = [
 ]
 
 
+LEAN_CASES = [
+    # (cin, cout, k, dil, stride, hw, n, mode, res, bias, act)       mode: 0 fp32 out, 1 fp32 + fp16, 2 fp16 only
+    (64, 64, 3, 5, 1, (160, 160), 2, 1, True, True, 2),
+    (64, 64, 3, 1, 1, (150, 150), 3, 2, False, False, 2),           # clipped tiles on both edges
+    (64, 64, 3, 5, 1, (160, 160), 2, 0, False, True, 1),
+    (64, 64, 1, 1, 1, (160, 160), 2, 0, True, False, 0),
+    (144, 64, 1, 1, 1, (160, 160), 2, 2, False, True, 2),            # three channel groups, the last one 16 wide
+    (128, 64, 3, 5, 1, (160, 160), 2, 1, True, False, 1),
+    (64, 16, 1, 1, 1, (160, 160), 2, 2, False, False, 2),            # one 16-column half block, warps 4..7 idle
+    (64, 48, 3, 1, 1, (160, 160), 2, 1, True, True, 2),              # second block half full
+    (64, 32, 1, 1, 1, (200, 160), 3, 0, False, True, 2),
+    (64, 16, 5, 1, 5, (400, 400), 8, 2, False, False, 2),            # DistgSSR AngConv: 5x5 stride 5
+]
+
+
+@pytest.mark.parametrize("case", LEAN_CASES, ids=lambda c: f"{c[0]}-{c[1]}-k{c[2]}d{c[3]}s{c[4]}-m{c[7]}")
+def test_conv_tc_lean_two_ctas_per_sm(ref, case):
+    """the narrow-layer kernel (two CTAs per SM, 16-column half blocks, bias from shared memory): same contract as the
+    general tcgen05 kernel, and the test asserts that this kernel is the one that ran"""
+    cin, cout, k, dil, stride, (h, w), n, mode, has_res, has_bias, act = case
+    tc_ops = K.CudaOps()
+    g = torch.Generator().manual_seed(cin * 31 + cout * 7 + k)
+    wt = (torch.rand(cout, cin, k, k, generator=g) - 0.5) * (2.0 / (cin * k * k) ** 0.5)
+    bias = (torch.rand(cout, generator=g) - 0.5) if has_bias else None
+    pad = (dil * (k // 2),) * 2 if stride == 1 else (0, 0)
+    pc = K.pack_conv(wt, bias, stride=(stride, stride), dil=(dil, dil), pad=pad, device=DEV, tc=True, tc16=True)
+    x16 = K.alloc_nhwc16(n, h, w, cin, DEV)
+    x16.copy_(nhwc(n, h, w, cin, seed=3))
+    oh, ow = h // stride, w // stride
+    kw_args = dict(act=act, slope=0.1)
+    if has_res:
+        kw_args["res"] = nhwc(n, oh, ow, cout, seed=5)
+    want = nhwc(n, oh, ow, cout, seed=7)
+    ref.conv(x16.float(), pc, want, **kw_args)
+    scale = max(1.0, want.abs().max().item())
+    o16 = K.alloc_nhwc16(n, oh, ow, cout, DEV)
+    o16.fill_(7.0)
+    o32 = torch.full_like(want, 7.0)
+    c0 = tc_ops.lib.lfsr_conv_tc_lean_count()
+    if mode == 0:
+        tc_ops.conv(x16, pc, o32, **kw_args)
+    elif mode == 1:
+        tc_ops.conv(x16, pc, o32, out16=o16, **kw_args)
+    else:
+        tc_ops.conv(x16, pc, None, out16=o16, **kw_args)
+    torch.cuda.synchronize()
+    assert tc_ops.lib.lfsr_conv_tc_lean_count() == c0 + 1, "the lean kernel did not take this layer"
+    if mode != 2:
+        e32 = (o32 - want).abs().max().item()
+        assert e32 <= 1e-3 * scale, e32
+    if mode == 1:
+        assert torch.equal(o16, o32.half())
+    if mode == 2:
+        e16 = (o16.float() - want).abs().max().item()
+        assert e16 <= 1e-3 * scale + scale * 2 ** -10, e16
+    # in-place residual (the trunk update of the networks): out aliases res
+    if has_res and mode != 2:
+        r2 = kw_args["res"].clone()
+        kw2 = dict(kw_args); kw2["res"] = r2
+        tc_ops.conv(x16, pc, r2, **kw2) if mode == 0 else tc_ops.conv(x16, pc, r2, out16=o16, **kw2)
+        torch.cuda.synchronize()
+        assert torch.equal(r2, o32)
+
+
 @pytest.mark.parametrize("case", F16_CASES, ids=lambda c: f"{c['cin']}-{c['cout']}-{c['k'][0]}x{c['k'][1]}")
 def test_conv_tc_fp16_operands(ref, case):
     """fp16 activations in (kind::f16 MMAs), fp16-only / fp32 + fp16 outputs, against the plain-torch conv of the SAME fp16
