@@ -823,11 +823,16 @@ __device__ __forceinline__ void epilogue_tile_tail(const Params& p, const float*
 // DBG = false compiles the cycle counters (LFSR_TC_DBG_PTR) out of the role loops
 // F16 = true: the activation tensor is fp16 NHWC (channel groups of 64 = one 128-byte row) and the weights are packed
 // as fp16: kind::f16 MMAs, K = 16 per instruction over the same bytes - half the shared-memory traffic and MMA time per MAC
-template <bool CTA2, bool DBG, bool F16>
-__global__ void __launch_bounds__(kThreads, 1)
+// T16 = true (tail-projection layers): SIXTEEN epilogue warps, one PixelShuffle sub-pixel each - the projection epilogue
+// (~1.8 k dependent-latency-bound instructions per warp and tile on 8 warps) bounded the dominant kernel, not the MMAs;
+// the other write-outs are compiled out, which keeps the 20 allocated warps inside 96 registers
+template <bool CTA2, bool DBG, bool F16, bool T16 = false>
+__global__ void __launch_bounds__(T16 ? 640 : kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmO, const Params p) {
   constexpr int CG = F16 ? 64 : 32;            // channels per 128-byte row / channel group
+  constexpr int kEpiW = T16 ? 16 : kEpiWarps;  // epilogue warps; the TMA producer and the MMA issuer are the two warps after them
+  constexpr int kTmaWarp = kEpiW, kMmaWarp = kEpiW + 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -835,7 +840,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sB = smem + p.stages * (p.twin ? 2 : p.kps) * kABytes;
   const int taps = p.kh * p.kw;
   const int nks = taps * p.cgs;
-  float* sEpi = reinterpret_cast<float*>(sB + (CTA2 ? p.stages * (p.b_stage_bytes >> 1)                 // (half slices)
+  float* sEpi = reinterpret_cast<float*>(sB + (CTA2 ? p.stages * p.kps * (p.b_stage_bytes >> 1)         // (half slices)
                                                       : (p.resident ? nks : p.stages * p.kps) * p.b_stage_bytes));   // 8 warps x 4 KB
   float* sTail = sEpi + kEpiWarps * 1024;                                                                  // tail_rows x 12
   uint64_t* bars = reinterpret_cast<uint64_t*>(sTail + p.tail_rows * 12);
@@ -848,10 +853,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < p.tail_rows * 12; i += kThreads) sTail[i] = i < p.cq * 12 ? __ldg(p.tail_w + i) : 0.f;
+  for (int i = threadIdx.x; i < p.tail_rows * 12; i += (int)blockDim.x) sTail[i] = i < p.cq * 12 ? __ldg(p.tail_w + i) : 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, p.pair ? 2 : 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, CTA2 ? 2 * kEpiWarps : kEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, CTA2 ? 2 * kEpiW : kEpiW); }
     mbar_init(bfull, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
@@ -889,15 +894,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; next_tile(p, i, m, chunk); ++i) {
           const TileCoord t0 = decode_tile(p, m, 0);
           int cg = 0, tap = 0;
-          for (int ks = 0; ks < nks; ++ks) {
+          for (int ks = 0; ks < nks; ks += p.kps) {           // a smem stage holds kps K-stages (fewer barrier round trips per tile)
             if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
             const int s = s_ring++;
             mbar_wait(empty + s, ph_ring ^ 1);                // own barrier: the multicast commit arrives in both CTAs
-            if (crank2 == 0) mbar_expect_tx(full + s, 2u * kABytes + (uint32_t)p.NC * 128u);   // both CTAs' loads
-            const short* to = p.tap_off[tap];
-            tma_load_5d_2sm(sA + s * kABytes, &tmA, full + s, cg * CG, t0.x0 + to[0], t0.vx + to[1], t0.y0 + to[2], t0.nb + to[3]);
-            tma_load_2d_2sm(sB + s * (p.b_stage_bytes >> 1), &tmBh, full + s, 0, ks * p.NC + crank2 * half_rows);
-            if (++cg == p.cgs) { cg = 0; ++tap; }
+            const int nsub = nks - ks < p.kps ? nks - ks : p.kps;
+            if (crank2 == 0) mbar_expect_tx(full + s, (uint32_t)nsub * (2u * kABytes + (uint32_t)p.NC * 128u));   // both CTAs' loads
+            for (int u = 0; u < nsub; ++u) {
+              const short* to = p.tap_off[tap];
+              const int slot = s * p.kps + u;
+              tma_load_5d_2sm(sA + slot * kABytes, &tmA, full + s, cg * CG, t0.x0 + to[0], t0.vx + to[1], t0.y0 + to[2], t0.nb + to[3]);
+              tma_load_2d_2sm(sB + slot * (p.b_stage_bytes >> 1), &tmBh, full + s, 0, (ks + u) * p.NC + crank2 * half_rows);
+              if (++cg == p.cgs) { cg = 0; ++tap; }
+            }
           }
         }
       } else
@@ -993,7 +1002,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + a * kAccStride;
             int cg_i = 0;
-            for (int ks = 0; ks < nks; ++ks) {
+            for (int ks = 0; ks < nks; ks += p.kps) {
               if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
               const int s = s_ring++;
               if ((DBG && p.dbg)) tw0 = clock64();
@@ -1001,14 +1010,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               long long tw1 = 0;
               if ((DBG && p.dbg)) { tw1 = clock64(); dbg_full_wait += tw1 - tw0; }
               tc_fence_after();
-              const uint64_t a_d = a_desc0 + (uint64_t)s * (kABytes >> 4);
-              const uint64_t b_d = b_desc0 + (uint64_t)s * b_half_step;
-              const int ksteps = (cg_i == p.cgs - 1) ? ksteps_last : 4;
-              if (ks == 0) umma2_tf32_c<0, F16>(d_tmem, a_d, b_d, idesc2); else umma2_tf32_c<1, F16>(d_tmem, a_d, b_d, idesc2);
-              for (int k = 1; k < ksteps; ++k) umma2_tf32_c<1, F16>(d_tmem, a_d + 2 * k, b_d + 2 * k, idesc2);
-              if (++cg_i == p.cgs) cg_i = 0;
+              const int nsub = nks - ks < p.kps ? nks - ks : p.kps;
+              uint64_t a_d = a_desc0 + (uint64_t)(s * p.kps) * (kABytes >> 4);
+              uint64_t b_d = b_desc0 + (uint64_t)(s * p.kps) * b_half_step;
+              for (int u = 0; u < nsub; ++u) {
+                const int ksteps = (cg_i == p.cgs - 1) ? ksteps_last : 4;
+                if (ks + u == 0) umma2_tf32_c<0, F16>(d_tmem, a_d, b_d, idesc2); else umma2_tf32_c<1, F16>(d_tmem, a_d, b_d, idesc2);
+                if (ksteps == 4) {
+                  umma2_tf32_c<1, F16>(d_tmem, a_d + 2, b_d + 2, idesc2);
+                  umma2_tf32_c<1, F16>(d_tmem, a_d + 4, b_d + 4, idesc2);
+                  umma2_tf32_c<1, F16>(d_tmem, a_d + 6, b_d + 6, idesc2);
+                } else {
+                  for (int k = 1; k < ksteps; ++k) umma2_tf32_c<1, F16>(d_tmem, a_d + 2 * k, b_d + 2 * k, idesc2);
+                }
+                if (++cg_i == p.cgs) cg_i = 0;
+                a_d += (uint64_t)(kABytes >> 4); b_d += (uint64_t)b_half_step;
+              }
               umma2_commit_mc(empty + s);
-              if (ks + 1 == nks) umma2_commit_mc(tfull + a);
+              if (ks + p.kps >= nks) umma2_commit_mc(tfull + a);
               if ((DBG && p.dbg)) dbg_mma += clock64() - tw1;
             }
           }
@@ -1108,7 +1127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // coalesced vector stores (consecutive lanes write consecutive bytes of a pixel's channel run).
     const int q = warp & 3;
     const int half = warp >> 2;                // the two warps of a lane quarter split the 32-column groups
-    float* stg = sEpi + warp * 1024;
+    float* stg = sEpi + (T16 ? 0 : warp * 1024);
     uint32_t tcount = 0;
     int m_, chunk_;
     long long dbg_wait = 0, dbg_t0 = 0, tw0 = 0, dbg_epi = 0;
@@ -1120,7 +1139,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const TileCoord tc_ = decode_tile(p, m_, chunk_);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccStride;
       long long tw1 = 0;
-      if (p.tail_w && m_ >= 0) {
+      if (T16) {
+        if (m_ >= 0) epilogue_tile_tail(p, sTail, taddr, lane, q, tc_, half, 4, tfull + a, aph);
+        else { mbar_wait(tfull + a, aph); tc_fence_after(); }
+      } else if (p.tail_w && m_ >= 0) {
         epilogue_tile_tail(p, sTail, taddr, lane, q, tc_, half, 2, tfull + a, aph);
       } else if (p.tma_epi && m_ >= 0) {
         if ((DBG && p.dbg)) tw1 = clock64();
@@ -1171,11 +1193,11 @@ constexpr int kLeanAccStride = 128;
 constexpr int kLeanSmem = 112 * 1024;
 
 // (register files are allocated per 4-warp group: the bound is stated for 384 threads so that ptxas budgets 2 x 12 warps)
-template <int OUT_MODE, bool HAS_RES>
+template <int OUT_MODE, bool HAS_RES, bool F16>
 __global__ void __launch_bounds__(384, 2)
 conv_tc_lean_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const Params p) {
-  constexpr int CG = 64;
+  constexpr int CG = F16 ? 64 : 32;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -1226,6 +1248,7 @@ conv_tc_lean_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         else if (p.amode == 1) { b1 = 0; b2 = tc_.x0; b3 = tc_.y0; b4 = tc_.nb; }
         else if (p.amode == 2) { b1 = tc_.x0; b2 = 0; b3 = tc_.y0; b4 = tc_.nb; }
         else { b1 = 0; b2 = tc_.x0; b3 = 0; b4 = tc_.nb * p.out_rows_per_img + tc_.y0; }
+        const int w_row0 = p.w_img_rows ? fdiv(tc_.nb, p.fd_nby) * p.w_img_rows : 0;       // per-image (gated) weight sets
         for (int ks = 0; ks < nks; ks += p.kps) {
           if (s_ring == p.stages) { s_ring = 0; ph_ring ^= 1; }
           const int s = s_ring++;
@@ -1236,7 +1259,7 @@ conv_tc_lean_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const short* to = p.tap_off[tap];
             const int slot = s * p.kps + u;
             tma_load_5d(sA + slot * kABytes, &tmA, full + s, cg * CG, b1 + to[0], b2 + to[1], b3 + to[2], b4 + to[3]);
-            if (!p.resident) tma_load_2d(sB + slot * p.b_stage_bytes, &tmB, full + s, 0, (ks + u) * p.NC);
+            if (!p.resident) tma_load_2d(sB + slot * p.b_stage_bytes, &tmB, full + s, 0, w_row0 + (ks + u) * p.NC);
             if (++cg == p.cgs) { cg = 0; ++tap; }
           }
         }
@@ -1248,10 +1271,10 @@ conv_tc_lean_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t tcount = 0;
       int s_ring = 0;
       uint32_t ph_ring = 0;
-      const uint32_t idesc = make_idesc(p.NC, 0u);
+      const uint32_t idesc = make_idesc(p.NC, F16 ? 0u : 2u);
       const uint64_t a_desc0 = make_smem_desc(smem_u32(sA)), b_desc0 = make_smem_desc(smem_u32(sB));
       const int rem_last = p.C - (p.cgs - 1) * CG;
-      const int ksteps_last = rem_last >= CG ? 4 : (rem_last + 15) >> 4;
+      const int ksteps_last = rem_last >= CG ? 4 : (F16 ? (rem_last + 15) >> 4 : (rem_last + 7) >> 3);
       const uint32_t b_step = (uint32_t)(p.b_stage_bytes >> 4);
       const uint32_t a_stage_step = (uint32_t)(p.kps * (kABytes >> 4)), b_stage_step = (uint32_t)p.kps * b_step;
       const bool tap_stages = p.kps == p.cgs;
@@ -1270,16 +1293,16 @@ conv_tc_lean_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t a_d0 = a_desc0 + (uint64_t)(s * a_stage_step);
           const uint64_t b_d0 = b_desc0 + (uint64_t)(p.resident ? ks * b_step : s * b_stage_step);
           if (tap_stages) {
-            if (ks == 0) umma_tap_dispatch<true, true>(p.cgs, d_tmem, a_d0, b_d0, b_step, idesc, ksteps_last);
-            else umma_tap_dispatch<false, true>(p.cgs, d_tmem, a_d0, b_d0, b_step, idesc, ksteps_last);
+            if (ks == 0) umma_tap_dispatch<true, F16>(p.cgs, d_tmem, a_d0, b_d0, b_step, idesc, ksteps_last);
+            else umma_tap_dispatch<false, F16>(p.cgs, d_tmem, a_d0, b_d0, b_step, idesc, ksteps_last);
           } else {
             const int nsub = nks - ks < p.kps ? nks - ks : p.kps;
             for (int u = 0; u < nsub; ++u) {
               const int ksteps = (cg_i == p.cgs - 1) ? ksteps_last : 4;
               const uint64_t a_d = a_d0 + (uint64_t)(u * (kABytes >> 4));
               const uint64_t b_d = b_d0 + (uint64_t)(u * b_step);
-              if (ks + u == 0) umma_stage<true, true>(d_tmem, a_d, b_d, idesc, ksteps);
-              else umma_stage<false, true>(d_tmem, a_d, b_d, idesc, ksteps);
+              if (ks + u == 0) umma_stage<true, F16>(d_tmem, a_d, b_d, idesc, ksteps);
+              else umma_stage<false, F16>(d_tmem, a_d, b_d, idesc, ksteps);
               if (++cg_i == p.cgs) cg_i = 0;
             }
           }
@@ -1359,7 +1382,8 @@ conv_tc_lean_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (OUT_MODE != 0 && pix_ok) {
 #pragma unroll
               for (int j = 0; j < 2; ++j)
-                *reinterpret_cast<uint4*>(dst16 + h * 16 + 8 * j) =
+                if (h * 16 + 8 * j < ncols)
+                  *reinterpret_cast<uint4*>(dst16 + h * 16 + 8 * j) =
                     make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]),
                                pack_h2(v[8 * j + 4], v[8 * j + 5]), pack_h2(v[8 * j + 6], v[8 * j + 7]));
             }
@@ -1794,9 +1818,11 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
     const char* w_ = "lfsr_conv2d_tc";
     if (opt_in_smem(conv_tc_kernel<false, false, false>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, false, false>, 227 * 1024, w_) ||
         opt_in_smem(conv_tc_kernel<false, false, true>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, false, true>, 227 * 1024, w_) ||
+        opt_in_smem(conv_tc_kernel<true, false, true, true>, 227 * 1024, w_) ||
 #ifdef LFSR_DEBUG_HOOKS
         opt_in_smem(conv_tc_kernel<false, true, false>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, true, false>, 227 * 1024, w_) ||
         opt_in_smem(conv_tc_kernel<false, true, true>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, true, true>, 227 * 1024, w_) ||
+        opt_in_smem(conv_tc_kernel<true, true, true, true>, 227 * 1024, w_) ||
 #endif
         opt_in_smem(conv_tc_halo_kernel, 227 * 1024, w_))
       return LFSR_ERR_CUDA;
@@ -1938,8 +1964,15 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   static const int cta2_min_nc = dbg_env("LFSR_TC_CTA2_MIN_NC") ? atoi(dbg_env("LFSR_TC_CTA2_MIN_NC")) : 128;
   if (use_cta2 && !p.resident && !per_image_w && p.nchunks == 1 && p.amode == 0 && p.NC >= cta2_min_nc && p.NC % 16 == 0 &&
       p.m_tiles >= 4 && sm_count >= 2) {
-    const int st = (kSmemBudget - kEpiWarps * 4096 - tail_bytes - epi16_bytes) / (kABytes + p.b_stage_bytes / 2);
-    if (st >= 2) { p.cta2 = 1; p.kps = 1; p.stages = st > kMaxStages ? kMaxStages : st; }
+    const int per = kABytes + p.b_stage_bytes / 2;
+    const int avail = kSmemBudget - kEpiWarps * 4096 - tail_bytes - epi16_bytes;
+    const int st = avail / per;
+    if (st >= 2) {
+      p.cta2 = 1; p.kps = 1; p.stages = st > kMaxStages ? kMaxStages : st;
+      // two K-stages per smem stage when three such stages still fit: the issuing lane pays ~290 cycles per stage boundary
+      static const int cta2_kps = dbg_env("LFSR_TC_CTA2_KPS") ? atoi(dbg_env("LFSR_TC_CTA2_KPS")) : 2;
+      if (cta2_kps > 1 && nks >= cta2_kps && avail / (cta2_kps * per) >= 3) { p.kps = cta2_kps; p.stages = avail / (cta2_kps * per); if (p.stages > kMaxStages) p.stages = kMaxStages; }
+    }
   }
   static const bool no_twin = dbg_env("LFSR_TC_NO_TWIN") != nullptr;
   p.twin = 0;
@@ -1992,7 +2025,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
     if (r != CUDA_SUCCESS) { set_error("lfsr_conv2d_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return LFSR_ERR_CUDA; }
   }
   const size_t smem = 1024 + (size_t)p.stages * (p.twin ? 2 : p.kps) * kABytes +
-                      (p.cta2 ? (size_t)p.stages * (p.b_stage_bytes / 2) : (size_t)(p.resident ? nks : p.stages * p.kps) * p.b_stage_bytes) +
+                      (p.cta2 ? (size_t)p.stages * p.kps * (p.b_stage_bytes / 2) : (size_t)(p.resident ? nks : p.stages * p.kps) * p.b_stage_bytes) +
                       kEpiWarps * 4096 + (size_t)tail_bytes + (size_t)epi16_bytes + (2 * kMaxStages + 5) * 8 + 16;
   LFSR_REQUIRE(smem <= 227 * 1024, "lfsr_conv2d_tc: shared memory plan too large");
   int grid = p.total_tiles < sm_count ? p.total_tiles : sm_count;
@@ -2089,8 +2122,14 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   {
     static const bool no_lean = dbg_env("LFSR_TC_NO_LEAN") != nullptr;
     const bool act_ok = p.act == LFSR_ACT_NONE || p.act == LFSR_ACT_RELU || p.act == LFSR_ACT_LRELU;
-    bool lean = f16 && !no_lean && !p.cta2 && !p.twin && !p.pair && !per_image_w && !p.tail_w && p.tma_epi && ry * rx == 1 &&
-                !d->mul.ptr && act_ok && p.nchunks == 1 && p.NC <= 64 && p.cout % 16 == 0 && !p.dbg && p.m_tiles >= 2 * sm_count;
+    // (a short last block is clipped by the output tensor map; the fp16 copy is stored as 16-byte runs of 8 channels)
+    const bool cout_ok = d->out_mode == 0 ? p.cout % 4 == 0 : p.cout % 8 == 0;
+    bool lean = !no_lean && !p.cta2 && !p.twin && !p.pair && !p.tail_w && p.tma_epi && ry * rx == 1 && !d->mul.ptr && act_ok &&
+                p.nchunks == 1 && p.NC <= 64 && cout_ok && !p.dbg && p.m_tiles >= 2 * sm_count;
+    if (verbose && !lean)
+      fprintf(stderr, "[lfsr tc lean] not eligible: cta2 %d twin %d pair %d tail %d tma_epi %d r2 %d mul %d act %d nchunks %d NC %d cout_ok %d dbg %d tiles %d\n",
+              p.cta2, p.twin, p.pair, p.tail_w != nullptr, p.tma_epi, ry * rx, d->mul.ptr != nullptr, p.act, p.nchunks, p.NC, (int)cout_ok,
+              p.dbg != nullptr, p.m_tiles);
     int l_kps = 0, l_stages = 0, l_res = 0;
     size_t l_smem = 0;
     if (lean) {
@@ -2101,7 +2140,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
       if (kps_hi > nks) kps_hi = nks;
       for (int kps = kps_hi; kps >= 1 && !l_stages; --kps) {
         if (kps_env > 0 && kps != kps_env) break;
-        for (int res = no_resident ? 0 : 1; res >= 0 && !l_stages; --res) {
+        for (int res = (no_resident || per_image_w) ? 0 : 1; res >= 0 && !l_stages; --res) {
           const long long per_stage = (long long)kps * (kABytes + (res ? 0 : p.b_stage_bytes));
           const long long left = kLeanSmem - fixed - (res ? b_all : 0);
           int st = left > 0 ? (int)(left / per_stage) : 0;
@@ -2116,10 +2155,11 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
       static DevOnce once_lean;
       if (once_lean.need()) {
         const char* w_ = "lfsr_conv2d_tc (lean)";
-        if (opt_in_smem(conv_tc_lean_kernel<0, false>, kLeanSmem, w_) || opt_in_smem(conv_tc_lean_kernel<0, true>, kLeanSmem, w_) ||
-            opt_in_smem(conv_tc_lean_kernel<1, false>, kLeanSmem, w_) || opt_in_smem(conv_tc_lean_kernel<1, true>, kLeanSmem, w_) ||
-            opt_in_smem(conv_tc_lean_kernel<2, false>, kLeanSmem, w_) || opt_in_smem(conv_tc_lean_kernel<2, true>, kLeanSmem, w_))
+#define LFSR_LEAN_OPT(M, R) opt_in_smem(conv_tc_lean_kernel<M, R, true>, kLeanSmem, w_) || opt_in_smem(conv_tc_lean_kernel<M, R, false>, kLeanSmem, w_)
+        if (LFSR_LEAN_OPT(0, false) || LFSR_LEAN_OPT(0, true) || LFSR_LEAN_OPT(1, false) || LFSR_LEAN_OPT(1, true) ||
+            LFSR_LEAN_OPT(2, false) || LFSR_LEAN_OPT(2, true))
           return LFSR_ERR_CUDA;
+#undef LFSR_LEAN_OPT
         once_lean.done();
       }
       const int lgrid = p.m_tiles < 2 * sm_count ? p.m_tiles : 2 * sm_count;
@@ -2128,14 +2168,20 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
                 p.C, p.cout, p.NC, p.kh, p.kw, p.m_tiles, lgrid, p.stages, p.kps, p.resident, d->out_mode, d->res.ptr ? 1 : 0, l_smem);
       cudaStream_t st_ = (cudaStream_t)stream;
       const bool hr = d->res.ptr != nullptr;
+#define LFSR_LEAN_GO(M, R)                                                                            \
+  do {                                                                                                \
+    if (f16) conv_tc_lean_kernel<M, R, true><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p);     \
+    else conv_tc_lean_kernel<M, R, false><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p);        \
+  } while (0)
       switch (d->out_mode * 2 + (hr ? 1 : 0)) {
-        case 0: conv_tc_lean_kernel<0, false><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p); break;
-        case 1: conv_tc_lean_kernel<0, true><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p); break;
-        case 2: conv_tc_lean_kernel<1, false><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p); break;
-        case 3: conv_tc_lean_kernel<1, true><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p); break;
-        case 4: conv_tc_lean_kernel<2, false><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p); break;
-        default: conv_tc_lean_kernel<2, true><<<lgrid, kThreads, l_smem, st_>>>(tmA, tmB, tmO, p); break;
+        case 0: LFSR_LEAN_GO(0, false); break;
+        case 1: LFSR_LEAN_GO(0, true); break;
+        case 2: LFSR_LEAN_GO(1, false); break;
+        case 3: LFSR_LEAN_GO(1, true); break;
+        case 4: LFSR_LEAN_GO(2, false); break;
+        default: LFSR_LEAN_GO(2, true); break;
       }
+#undef LFSR_LEAN_GO
       g_lean_launches.fetch_add(1);
       return check_launch("conv_tc_lean_kernel");
     }
@@ -2143,6 +2189,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   if (verbose)
     fprintf(stderr, "[lfsr tc] C=%d cout=%d NC=%d k=%dx%d tiles=%d grid=%d stages=%d kps=%d resident=%d pair=%d twin=%d cta2=%d TH=%d TW=%d vec=%d tma_epi=%d smem=%zu\n",
             p.C, p.cout, p.NC, p.kh, p.kw, p.total_tiles, grid, p.stages, p.kps, p.resident, p.pair, p.twin, p.cta2, p.TH, p.TW, p.vec, p.tma_epi, smem);
+  static const bool no_t16 = dbg_env("LFSR_TC_NO_T16") != nullptr;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
@@ -2155,12 +2202,18 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   if (p.dbg && !f16)
     le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, false>, tmA, tmB, tmBh, tmO, p)
                 : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, false>, tmA, tmB, tmBh, tmO, p);
-  else if (p.dbg)
+  else if (p.dbg && p.cta2 && p.tail_w && ry * rx == 4 && p.nchunks == 1 && !no_t16) {
+    cfg.blockDim = dim3(18 * 32);
+    le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, true, true>, tmA, tmB, tmBh, tmO, p);
+  } else if (p.dbg)
     le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, true>, tmA, tmB, tmBh, tmO, p)
                 : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, true>, tmA, tmB, tmBh, tmO, p);
   else
 #endif
-  if (f16)
+  if (f16 && p.cta2 && p.tail_w && ry * rx == 4 && p.nchunks == 1 && !no_t16) {     // one sub-pixel per epilogue warp
+    cfg.blockDim = dim3(18 * 32);
+    le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, true, true>, tmA, tmB, tmBh, tmO, p);
+  } else if (f16)
     le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, true>, tmA, tmB, tmBh, tmO, p)
                 : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, true>, tmA, tmB, tmBh, tmO, p);
   else

@@ -558,6 +558,10 @@ LEAN_CASES = [
     (64, 48, 3, 1, 1, (160, 160), 2, 1, True, True, 2),              # second block half full
     (64, 32, 1, 1, 1, (200, 160), 3, 0, False, True, 2),
     (64, 16, 5, 1, 5, (400, 400), 8, 2, False, False, 2),            # DistgSSR AngConv: 5x5 stride 5
+    (56, 60, 3, 5, 1, (160, 160), 2, 0, False, True, 0),             # Track-2 fus2: 60 output channels, clipped last block
+    (60, 56, 1, 1, 1, (160, 160), 2, 2, False, False, 2, True),      # fp32 input (TF32 MMAs) -> fp16 only (Track-2 fus0 shape)
+    (64, 64, 3, 1, 1, (160, 160), 2, 0, True, True, 1, True),        # fp32 input, fp32 output + residual
+    (96, 64, 1, 1, 1, (150, 150), 3, 1, False, True, 2, True),       # fp32 input, three 32-channel groups
 ]
 
 
@@ -565,15 +569,19 @@ LEAN_CASES = [
 def test_conv_tc_lean_two_ctas_per_sm(ref, case):
     """the narrow-layer kernel (two CTAs per SM, 16-column half blocks, bias from shared memory): same contract as the
     general tcgen05 kernel, and the test asserts that this kernel is the one that ran"""
-    cin, cout, k, dil, stride, (h, w), n, mode, has_res, has_bias, act = case
+    cin, cout, k, dil, stride, (h, w), n, mode, has_res, has_bias, act = case[:11]
+    f32in = len(case) > 11 and case[11]
     tc_ops = K.CudaOps()
     g = torch.Generator().manual_seed(cin * 31 + cout * 7 + k)
     wt = (torch.rand(cout, cin, k, k, generator=g) - 0.5) * (2.0 / (cin * k * k) ** 0.5)
     bias = (torch.rand(cout, generator=g) - 0.5) if has_bias else None
     pad = (dil * (k // 2),) * 2 if stride == 1 else (0, 0)
     pc = K.pack_conv(wt, bias, stride=(stride, stride), dil=(dil, dil), pad=pad, device=DEV, tc=True, tc16=True)
-    x16 = K.alloc_nhwc16(n, h, w, cin, DEV)
-    x16.copy_(nhwc(n, h, w, cin, seed=3))
+    if f32in:
+        x16 = nhwc(n, h, w, cin, seed=3)
+    else:
+        x16 = K.alloc_nhwc16(n, h, w, cin, DEV)
+        x16.copy_(nhwc(n, h, w, cin, seed=3))
     oh, ow = h // stride, w // stride
     kw_args = dict(act=act, slope=0.1)
     if has_res:
@@ -751,6 +759,32 @@ def test_conv_tc_tail_projection_and_tap_gather(ref, cin, cq, hw, bias):
     y2 = rnd(n, h * r, w * r, 1, seed=5)
     ref.conv(full, K.pack_conv(head, hb, pad=(1, 1), device=DEV), y2, res=y2.clone())
     assert (ya - y2).abs().max().item() <= 2e-3
+
+
+@pytest.mark.parametrize("cin,cq,hw,n,bias", [(56, 56, (80, 80), 2, True), (64, 64, (40, 48), 3, False), (56, 56, (37, 45), 2, False),
+                                              (56, 56, (160, 160), 3, True)])
+def test_conv_tc_tail_projection_fp16_sixteen_epilogue_warps(ref, cin, cq, hw, n, bias):
+    """the dominant layer's configuration: fp16 activations, CTA pairs, tail projection with one sub-pixel per epilogue
+    warp (16 epilogue warps) - against the plain conv of the same fp16 input values"""
+    tc_ops = K.CudaOps(use_tc=True)
+    (h, w), r = hw, 2
+    g = torch.Generator().manual_seed(cin * 3 + cq)
+    wt = (torch.rand(cq * r * r, cin, 3, 3, generator=g) - 0.5) * (2.0 / (cin * 9) ** 0.5)
+    b = (torch.rand(cq * r * r, generator=g) - 0.5) if bias else None
+    pc = K.pack_conv(wt, b, pad=(1, 1), device=DEV, tc=True, tc16=True, tc_shuffle=(r, r, 0))
+    head = (torch.rand(1, cq, 3, 3, generator=g) - 0.5) * 0.2
+    tw = torch.zeros(cq, 12)
+    tw[:, :9] = head[0].reshape(cq, 9)
+    tw = tw.to(DEV)
+    x16 = K.alloc_nhwc16(n, h, w, cin, DEV)
+    x16.copy_(nhwc(n, h, w, cin, seed=3))
+    ta, tb = nhwc(n, h * r, w * r, 9, seed=4), nhwc(n, h * r, w * r, 9, seed=4)
+    kw = dict(act=2, slope=0.1, shuffle=(r, r, 0), tail=(tw, 9, cq))
+    l0 = tc_ops.lib.lfsr_launch_count()
+    tc_ops.conv(x16, pc, ta, **kw)
+    assert tc_ops.lib.lfsr_launch_count() == l0 + 1
+    ref.conv(x16.float(), pc, tb, **kw)
+    assert (ta - tb).abs().max().item() <= 2e-3
 
 
 @pytest.mark.parametrize("cq,r,k,mode,hw", [(64, 4, 1, 1, (32, 32)), (64, 4, 1, 1, (21, 45)), (32, 4, 3, 0, (40, 40))])
