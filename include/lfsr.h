@@ -236,6 +236,12 @@ int lfsr_sa_modulate(const lfsr_tensor* x, const float* dw_w, const float* bn_sc
                      const float* bn_shift, const lfsr_tensor* amod, float w0, float w1,
                      const lfsr_tensor* res, const lfsr_tensor* out, int dil, void* stream);
 
+/* the same, plus an fp16 copy of output channels [0, out16->c) (fp16 NHWC view, c a multiple of 4): the operand of the
+ * tensor-core layers that read this trunk next (Track-2 spatial branch). Tiled kernel only; errors when it does not apply. */
+int lfsr_sa_modulate16(const lfsr_tensor* x, const float* dw_w, const float* bn_scale,
+                       const float* bn_shift, const lfsr_tensor* amod, float w0, float w1,
+                       const lfsr_tensor* res, const lfsr_tensor* out, const lfsr_tensor* out16, int dil, void* stream);
+
 /* out = x * scale[n][c] + res  (ChannelAttention + block residual, MyEfficientLFNetV4_5.py:148,291-299);
  * scale is an [n,1,1,c] tensor view, res may be NULL. */
 int lfsr_scale_add(const lfsr_tensor* x, const lfsr_tensor* scale, const lfsr_tensor* res, const lfsr_tensor* out,

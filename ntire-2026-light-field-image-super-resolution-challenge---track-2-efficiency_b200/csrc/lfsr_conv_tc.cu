@@ -1818,7 +1818,8 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
     const char* w_ = "lfsr_conv2d_tc";
     if (opt_in_smem(conv_tc_kernel<false, false, false>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, false, false>, 227 * 1024, w_) ||
         opt_in_smem(conv_tc_kernel<false, false, true>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, false, true>, 227 * 1024, w_) ||
-        opt_in_smem(conv_tc_kernel<true, false, true, true>, 227 * 1024, w_) ||
+        opt_in_smem(conv_tc_kernel<true, false, true, true>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<false, false, true, true>, 227 * 1024, w_) ||
+        opt_in_smem(conv_tc_kernel<false, false, false, true>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, false, false, true>, 227 * 1024, w_) ||
 #ifdef LFSR_DEBUG_HOOKS
         opt_in_smem(conv_tc_kernel<false, true, false>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, true, false>, 227 * 1024, w_) ||
         opt_in_smem(conv_tc_kernel<false, true, true>, 227 * 1024, w_) || opt_in_smem(conv_tc_kernel<true, true, true>, 227 * 1024, w_) ||
@@ -2190,6 +2191,9 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
     fprintf(stderr, "[lfsr tc] C=%d cout=%d NC=%d k=%dx%d tiles=%d grid=%d stages=%d kps=%d resident=%d pair=%d twin=%d cta2=%d TH=%d TW=%d vec=%d tma_epi=%d smem=%zu\n",
             p.C, p.cout, p.NC, p.kh, p.kw, p.total_tiles, grid, p.stages, p.kps, p.resident, p.pair, p.twin, p.cta2, p.TH, p.TW, p.vec, p.tma_epi, smem);
   static const bool no_t16 = dbg_env("LFSR_TC_NO_T16") != nullptr;
+  // sub-pixels per cout-chunk (all r2 of them with one chunk): a multiple of 4 keeps the four warp groups balanced
+  const int subs_per_chunk = p.nchunks == 1 ? ry * rx : (p.cq > 0 ? p.NC / p.cq : 0);
+  const bool t16 = p.tail_w && !no_t16 && !p.twin && !p.pair && subs_per_chunk >= 4 && subs_per_chunk % 4 == 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
@@ -2202,7 +2206,7 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
   if (p.dbg && !f16)
     le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, false>, tmA, tmB, tmBh, tmO, p)
                 : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, false>, tmA, tmB, tmBh, tmO, p);
-  else if (p.dbg && p.cta2 && p.tail_w && ry * rx == 4 && p.nchunks == 1 && !no_t16) {
+  else if (p.dbg && f16 && p.cta2 && t16) {
     cfg.blockDim = dim3(18 * 32);
     le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, true, true>, tmA, tmB, tmBh, tmO, p);
   } else if (p.dbg)
@@ -2210,9 +2214,12 @@ extern "C" int lfsr_conv2d_tc(const lfsr_tensor* in, const float* w_packed_tc, c
                 : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, true>, tmA, tmB, tmBh, tmO, p);
   else
 #endif
-  if (f16 && p.cta2 && p.tail_w && ry * rx == 4 && p.nchunks == 1 && !no_t16) {     // one sub-pixel per epilogue warp
+  if (t16) {     // tail projection with 16 epilogue warps: every warp group owns whole sub-pixels of the chunk
     cfg.blockDim = dim3(18 * 32);
-    le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, true, true>, tmA, tmB, tmBh, tmO, p);
+    if (f16) le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, true, true>, tmA, tmB, tmBh, tmO, p)
+                         : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, true, true>, tmA, tmB, tmBh, tmO, p);
+    else le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, false, true>, tmA, tmB, tmBh, tmO, p)
+                     : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, false, true>, tmA, tmB, tmBh, tmO, p);
   } else if (f16)
     le = p.cta2 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, true>, tmA, tmB, tmBh, tmO, p)
                 : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, true>, tmA, tmB, tmBh, tmO, p);

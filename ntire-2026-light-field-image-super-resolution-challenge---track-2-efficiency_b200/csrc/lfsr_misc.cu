@@ -605,7 +605,7 @@ extern "C" int lfsr_block_mean(const lfsr_tensor* in, const lfsr_tensor* out, in
 
 int lfsr_sa_modulate_tiled(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
                            const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res, const lfsr_tensor* out, int dil,
-                           int* handled, void* stream);     // lfsr_dw.cu
+                           int* handled, void* stream, const lfsr_tensor* out16 = nullptr);     // lfsr_dw.cu
 
 extern "C" int lfsr_sa_modulate(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
                                 const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res,
@@ -646,6 +646,26 @@ extern "C" int lfsr_sa_modulate(const lfsr_tensor* x, const float* dw_w, const f
   else if (V == 2) sa_modulate_kernel<2><<<blocks, 256, 0, st>>>(view_of(x), dw_w, bn_scale, bn_shift, view_of(amod), w0, w1, r, view_of(out), dil);
   else sa_modulate_kernel<1><<<blocks, 256, 0, st>>>(view_of(x), dw_w, bn_scale, bn_shift, view_of(amod), w0, w1, r, view_of(out), dil);
   return check_launch("sa_modulate_kernel");
+}
+
+extern "C" int lfsr_sa_modulate16(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
+                                  const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res,
+                                  const lfsr_tensor* out, const lfsr_tensor* out16, int dil, void* stream) {
+  LFSR_REQUIRE(tensor_ok(x) && tensor_ok(out) && tensor_ok(amod) && dw_w && bn_scale && bn_shift && out16 && out16->ptr,
+               "lfsr_sa_modulate16: null/invalid tensor");
+  LFSR_REQUIRE(out->n == x->n && out->h == x->h && out->w == x->w && out->c == x->c, "lfsr_sa_modulate16: out shape");
+  LFSR_REQUIRE(amod->n == x->n && amod->c == x->c && x->h % amod->h == 0 && x->w % amod->w == 0, "lfsr_sa_modulate16: amod shape");
+  LFSR_REQUIRE(out16->n == x->n && out16->h == x->h && out16->w == x->w && out16->c > 0 && out16->c <= x->c && out16->c % 4 == 0 &&
+                   out16->ld % 4 == 0 && (((uintptr_t)out16->ptr) & 7) == 0,
+               "lfsr_sa_modulate16: the fp16 copy holds the first c16 channels (a multiple of 4, 8-byte aligned pixels)");
+  if (res && res->ptr)
+    LFSR_REQUIRE(res->n == x->n && res->h == x->h && res->w == x->w && res->c == x->c, "lfsr_sa_modulate16: res shape");
+  LFSR_REQUIRE(x->n <= 65535, "lfsr_sa_modulate16: batch too large");
+  int handled = 0;
+  int rc = lfsr_sa_modulate_tiled(x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil, &handled, stream, out16);
+  if (rc != LFSR_OK) return rc;
+  LFSR_REQUIRE(handled, "lfsr_sa_modulate16: these tensors do not qualify for the tiled kernel (16-byte aligned 4-channel groups)");
+  return LFSR_OK;
 }
 
 extern "C" int lfsr_scale_add(const lfsr_tensor* x, const lfsr_tensor* scale, const lfsr_tensor* res, const lfsr_tensor* out,

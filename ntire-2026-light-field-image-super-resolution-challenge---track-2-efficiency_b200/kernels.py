@@ -335,8 +335,14 @@ class CudaOps:
         N.check(self.lib.lfsr_block_mean(C.byref(as_tensor(x, "block_mean.in")), C.byref(as_tensor(out, "block_mean.out")),
                                          bh, bw, self._stream(x)), "lfsr_block_mean")
 
-    def sa_modulate(self, x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil):
+    def sa_modulate(self, x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil, out16=None):
         rt = as_tensor(res, "sa.res") if res is not None else _NULL_T
+        if out16 is not None:
+            N.check(self.lib.lfsr_sa_modulate16(C.byref(as_tensor(x, "sa.x")), dw_w.data_ptr(), bn_scale.data_ptr(),
+                                                bn_shift.data_ptr(), C.byref(as_tensor(amod, "sa.amod")), w0, w1, C.byref(rt),
+                                                C.byref(as_tensor(out, "sa.out")), C.byref(as_tensor(out16, "sa.out16", f16=True)),
+                                                dil, self._stream(x)), "lfsr_sa_modulate16")
+            return
         N.check(self.lib.lfsr_sa_modulate(C.byref(as_tensor(x, "sa.x")), dw_w.data_ptr(), bn_scale.data_ptr(),
                                           bn_shift.data_ptr(), C.byref(as_tensor(amod, "sa.amod")), w0, w1, C.byref(rt),
                                           C.byref(as_tensor(out, "sa.out")), dil, self._stream(x)), "lfsr_sa_modulate")

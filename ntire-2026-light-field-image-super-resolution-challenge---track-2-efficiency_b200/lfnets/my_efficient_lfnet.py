@@ -192,6 +192,15 @@ class get_model(LFNetBase):
             w, b = st.spatial_branch["0"].merged()
             s["spa0"] = pc(*pad_out(w, b), tc=True, **dil)
             s["spa2"] = pc(*pad_out(st.spatial_branch["2"].weight), tc=True, **dil)
+            if f16:
+                # fp16 operand plan: both 18-channel convs on the tensor cores over 32-channel fp16 pixels (64 contiguous bytes:
+                # a TMA box row of 18 or 24 channels is 2.4x slower, run_thin_vs_lean.py); input channels 18..31 carry zero
+                # weights (they are the next group's channels / the zero pad), 0.25 -> 0.15 ms per layer against the FFMA2 kernel
+                def pad_in(wb, to=32):
+                    w_, b_ = wb
+                    return torch.cat([w_, w_.new_zeros((w_.shape[0], to - w_.shape[1]) + tuple(w_.shape[2:]))], 1), b_
+                s["spa0h"] = pc(*pad_in(pad_out(w, b, to=24)), tc=True, tc16=True, **dil)
+                s["spa2h"] = pc(*pad_in(pad_out(st.spatial_branch["2"].weight)), tc=True, tc16=True, **dil)
             ab = st.angular_branch
             # the small angular-resolution tensors are all 20-float pixels (real channels + zeros): every layer of the
             # attention runs on the thin FFMA2 kernel / the tiled depthwise kernel
@@ -295,13 +304,21 @@ class get_model(LFNetBase):
         # fu1 (fusion 1x1 output) feeds nothing but the 3x3 that follows: fp16 only on the fp16 operand plan
         fu1 = self._buf16("fu1", B, H, W, CU, dev) if f16 else buf("fu1", H, W, CU)
         fu2 = buf("fu2", H, W, CP)
+        if f16:
+            xs16, t18h = self._buf16("xs16", B, H, W, 32, dev), self._buf16("t18h", B, H, W, 32, dev)
         pm, am1, am = buf("pm", A, A, CP), buf("am1", A, A, C // 4), buf("am", A, A, CP)
         fork = SideStream(dev if x.is_cuda and getattr(ops, "name", "") == "cuda" else None)
         for i, st in enumerate(pk["stages"]):
             xs, xa, xe = feat[..., sl[0]], feat[..., sl[1]], feat[..., sl[2]]
             # spatial branch
-            ops.conv(xs, st["spa0"], t18, act=LR, slope=0.1)
-            ops.conv(t18[..., 0:c0], st["spa2"], cat[..., 0:gs])
+            if f16 and gs + 12 <= CP:
+                if i == 0:          # later stages: the SA modulator of the previous stage wrote the copy next to the trunk
+                    ops.to_f16(feat[..., 0:32], xs16)
+                ops.conv(xs16, st["spa0h"], None, out16=t18h[..., 0:24], act=LR, slope=0.1)
+                ops.conv(t18h, st["spa2h"], cat[..., 0:gs])
+            else:
+                ops.conv(xs, st["spa0"], t18, act=LR, slope=0.1)
+                ops.conv(t18[..., 0:c0], st["spa2"], cat[..., 0:gs])
             # angular branch: six small launches on 32x32 maps that do not fill the GPU - on a side stream (when the backend
             # is the CUDA one) they run under the spatial / EPI kernels; the three branches write disjoint slots of `cat`
             with fork():
@@ -329,7 +346,10 @@ class get_model(LFNetBase):
             ops.conv(pm, st["sa_c0"], am1, act=N.ACT_RELU)
             ops.conv(am1, st["sa_c2"], am, act=N.ACT_SIGMOID)
             nxt = pp[i & 1]
-            ops.sa_modulate(fu2, st["sa_dw"], st["sa_bns"], st["sa_bnb"], am, st["sa_w"][0], st["sa_w"][1], feat, nxt, A)
+            if f16 and gs + 12 <= CP and i + 1 < len(pk["stages"]):
+                ops.sa_modulate(fu2, st["sa_dw"], st["sa_bns"], st["sa_bnb"], am, st["sa_w"][0], st["sa_w"][1], feat, nxt, A, out16=xs16)
+            else:
+                ops.sa_modulate(fu2, st["sa_dw"], st["sa_bns"], st["sa_bnb"], am, st["sa_w"][0], st["sa_w"][1], feat, nxt, A)
             feat = nxt
         if f16:
             ops.conv(feat, pk["gf0"], None, out16=fu1, act=LR, slope=0.1)

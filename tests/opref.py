@@ -215,7 +215,7 @@ class RefOps:
         n, h, w, c = x.shape
         out.copy_(x.reshape(n, h // bh, bh, w // bw, bw, c).mean(dim=(2, 4)))
 
-    def sa_modulate(self, x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil):
+    def sa_modulate(self, x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil, out16=None):
         n, h, w, c = x.shape
         xi = _nchw(x)
         s = F.conv2d(xi, dw_w.t().reshape(c, 1, 3, 3), None, 1, dil, dil, c)
@@ -225,6 +225,8 @@ class RefOps:
         if res is not None:
             y = y + _nchw(res)
         out.copy_(y.permute(0, 2, 3, 1))
+        if out16 is not None:
+            out16.copy_(out[..., :out16.shape[3]])
 
     def scale_add(self, x, scale, res, out):
         y = x * scale

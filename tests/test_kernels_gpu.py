@@ -255,6 +255,23 @@ def test_sa_modulate(ops, ref, c, h, w):
     assert (a - b).abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("c,c16,h,w", [(60, 32, 40, 40), (60, 20, 45, 35), (64, 64, 160, 160)])
+def test_sa_modulate_with_fp16_copy(ops, ref, c, c16, h, w):
+    """the SA tail also stores the first c16 output channels as fp16 (operand of the next stage's spatial-branch convs):
+    the copy is exactly the rounded fp32 output, pad channels of the fp16 buffer stay untouched"""
+    n, A = 2, 5
+    x, res = nhwc(n, h, w, c, seed=1), nhwc(n, h, w, c, seed=2)
+    dw, bs, bb = rnd(9, c, seed=3), rnd(c, seed=4, lo=0.5, hi=1.5), rnd(c, seed=5)
+    am = nhwc(n, A, A, c, seed=6)
+    a, b = nhwc(n, h, w, c, seed=7), nhwc(n, h, w, c, seed=7)
+    full16 = torch.full((n, h, w, 64), 3.0, dtype=torch.float16, device=DEV)
+    ops.sa_modulate(x, dw, bs, bb, am, 0.4, 0.6, res, a, A, out16=full16[..., :c16])
+    ref.sa_modulate(x, dw, bs, bb, am, 0.4, 0.6, res, b, A)
+    assert (a - b).abs().max().item() <= 1e-5
+    assert torch.equal(full16[..., :c16], a[..., :c16].half())
+    assert bool((full16[..., c16:] == 3.0).all())
+
+
 @pytest.mark.parametrize("r", [2, 4])
 @pytest.mark.parametrize("accumulate", [False, True])
 def test_macpi_unshuffle_bit_exact(ops, ref, r, accumulate):
