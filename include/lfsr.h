@@ -195,6 +195,11 @@ int lfsr_conv2d_small_cout(const lfsr_tensor* in, const float* w_packed, const l
  * w_packed = dw_h[klen][18] | dw_v[klen][18] | dw_d[9][18] | pw_h[18 in][18 out] | pw_v | pw_d | fuse[54 in][18 out]. */
 int lfsr_mel_epi_branch(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out, int klen, int dil,
                         float slope, void* stream);
+/* The same block with its four 1x1 contractions on the tensor cores (tcgen05, fp16 operands written by the CTA itself,
+ * fp32 accumulation in tensor memory); the depthwise taps stay fp32 on the CUDA cores. Same arguments and weight packing;
+ * results differ from lfsr_mel_epi_branch by the fp16 rounding of the contraction operands (~1e-3 relative). */
+int lfsr_mel_epi_branch_tc(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out, int klen, int dil,
+                           float slope, void* stream);
 /* TF32 tcgen05/TMEM implicit GEMM fed by TMA (sm_100a); weights packed by lfsr_pack_conv_tc.
  * Supports stride 1 (any dilation, "same" zero padding given by pad) and kh*kw <= 25. */
 size_t lfsr_conv2d_tc_packed_floats(int kh, int kw, int cin, int cout);

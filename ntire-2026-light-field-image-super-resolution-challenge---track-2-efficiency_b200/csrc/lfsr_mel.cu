@@ -5,6 +5,7 @@
 //   * mel_epi_branch: the whole MultiScaleEPIBlock (MyEfficientLFNet.py:278-327) in one pass:
 //     dw 1xK / Kx1 / 3x3-dilated -> 1x1 + LReLU each -> concat -> 1x1 + LReLU. One thread per pixel.
 #include "lfsr_common.cuh"
+#include "lfsr_ptx.cuh"
 
 namespace lfsr {
 
@@ -257,6 +258,229 @@ mel_epi_branch_kernel(const EpiArgs a) {
   }
 }
 
+
+// ---- fused MultiScaleEPIBlock, pointwise contractions on the tensor cores -----------------------------------
+// Same block as mel_epi_branch_kernel, but only the depthwise taps stay on the CUDA cores. The 1x1 convolutions are two
+// tcgen05 GEMMs per 128-pixel row block whose A operands the CTA writes itself:
+//   stage 1   T[128 px][54 = 3 x 18 depthwise results, fp16] x blockdiag(pw_h, pw_v, pw_d)  -> TMEM (64 fp32 columns)
+//   stage 2   LReLU(stage 1) as fp16, written over T                       x fuse[54 -> 18] -> TMEM (32 columns, reused)
+// (K = 54 padded to 64 fp16 = one 128-byte SWIZZLE_128B row per pixel, so each GEMM is four K = 16 MMAs.) The block-
+// diagonal zeros triple the MMA work, which is still < 2 % of the tensor pipe; what the kernel saves is the 108 broadcast
+// weight rows (540 LDS.128) and 972 FFMA2 per pixel the CUDA-core version spends on the contractions.
+// CTA = 256 threads = 32 x 8 pixels = two M = 128 blocks (thread t <-> row t & 127 of block t >> 7 <-> TMEM lane t & 127).
+// The A rows alias the staged input tile (dead after the depthwise phase), so 3 CTAs still fit one SM.
+namespace et {
+using namespace ptx;
+constexpr int kA = 16384;            // one M = 128 operand block: 128 rows x 128 B
+constexpr int kB1 = 8192, kB2 = 4096;
+
+__device__ __forceinline__ void store_row(uint32_t a_row, uint32_t sw, const uint32_t* pk) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    st_shared_v4(a_row + ((((uint32_t)u) ^ sw) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+}
+}  // namespace et
+
+__global__ void __launch_bounds__(256, 3)
+mel_epi_branch_tc_kernel(const EpiArgs a) {
+  using namespace et;
+  extern __shared__ uint8_t et_raw[];
+  const uint32_t raw = smem_u32(et_raw);
+  uint8_t* smem = et_raw + (((raw + 1023u) & ~1023u) - raw);
+  const int KL = a.KL, half = KL / 2;
+  const int halo = half > a.dil ? half : a.dil;
+  const int hw = EP_W + 2 * halo, hh = EP_H + 2 * halo;
+  const int n_rows = 2 * KL + 9;                         // depthwise tap rows: dw_h | dw_v | dw_d
+  int tile_bytes = hh * hw * EP_CS * 4;
+  if (tile_bytes < 2 * kA) tile_bytes = 2 * kA;
+  uint8_t* B1 = smem;                                    // [64 out][64 in] fp16, K-major SWIZZLE_128B
+  uint8_t* B2 = smem + kB1;                              // [32 out][64 in]
+  float* tile = reinterpret_cast<float*>(smem + kB1 + kB2);     // [hh*hw][EP_CS]; later the two A blocks
+  float* sw = reinterpret_cast<float*>(smem + kB1 + kB2 + tile_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sw + ((n_rows * EP_CS + 3) & ~3));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  int t_ = blockIdx.x;
+  const int tx0 = (t_ % a.tiles_x) * EP_W; t_ /= a.tiles_x;
+  const int ty0 = (t_ % a.tiles_y) * EP_H;
+  const int img = t_ / a.tiles_y;
+  // input tile with halo (zero filled outside the image)
+  for (int i = tid; i < hh * hw * 5; i += 256) {
+    const int ch = i % 5, pix = i / 5;
+    const int ly = pix / hw, lx = pix - ly * hw;
+    const int iy = ty0 - halo + ly, ix = tx0 - halo + lx;
+    const bool inside = iy >= 0 && iy < a.in.h && ix >= 0 && ix < a.in.w;
+    const float* src = a.in.p + (inside ? a.in.pix(img, iy, ix) : 0) + ch * 4;
+    const uint32_t dst = smem_u32(tile + pix * EP_CS + ch * 4);
+    const int nbytes = inside ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (tid == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, 128);
+  }
+  for (int i = tid; i < n_rows * EP_CS; i += 256) {       // tap rows re-pitched from EC to EP_CS floats
+    const int r = i / EP_CS, c = i - r * EP_CS;
+    sw[i] = c < EC ? __ldg(a.w + r * EC + c) : 0.f;
+  }
+  // B operands, one 16-byte unit (8 input channels of one output row) at a time
+  const float* pwg = a.w + n_rows * EC;                   // 3 x [EC in][EC out]
+  const float* fug = pwg + 3 * EC * EC;                   // [3*EC in][EC out]
+  for (int i = tid; i < (64 + 32) * 8; i += 256) {
+    const int n = i >> 3, u = i & 7;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = 8 * u + j;
+      float x = 0.f;
+      if (k < 3 * EC) {
+        if (n < 64) {
+          const int brk = k / EC, c = k - brk * EC;
+          if (n < 3 * EC && n / EC == brk) x = __ldg(pwg + brk * EC * EC + c * EC + (n - brk * EC));
+        } else if (n - 64 < EC) {
+          x = __ldg(fug + k * EC + (n - 64));
+        }
+      }
+      v[j] = x;
+    }
+    const int row = n < 64 ? n : n - 64;
+    const uint32_t base = smem_u32(n < 64 ? B1 : B2) + (uint32_t)row * 128u;
+    st_shared_v4(base + ((((uint32_t)u) ^ ((uint32_t)row & 7u)) << 4), pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]),
+                 pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float* dwh = sw;
+  const float* dwv = dwh + KL * EP_CS;
+  const float* dwd = dwv + KL * EP_CS;
+  const int lx = tid & 31, ly = tid >> 5;
+  const int ox = tx0 + lx, oy = ty0 + ly;
+  const float* centre = tile + ((ly + halo) * hw + lx + halo) * EP_CS;
+  constexpr int NP = EC / 2;
+  uint32_t pk[32];                                        // this pixel's A row: 54 fp16 + 10 zeros
+#pragma unroll
+  for (int i = 3 * NP; i < 32; ++i) pk[i] = 0u;
+#pragma unroll
+  for (int br = 0; br < 3; ++br) {
+    f32x2 t2[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) t2[i] = pack2(0.f, 0.f);
+    const int ntap = br == 2 ? 9 : KL;
+    const float* dwb = br == 0 ? dwh : (br == 1 ? dwv : dwd);
+#pragma unroll 1
+    for (int k = 0; k < ntap; ++k) {
+      int dy = 0, dx = 0;
+      if (br == 0) dx = k - half;
+      else if (br == 1) dy = k - half;
+      else { dy = (k / 3 - 1) * a.dil; dx = (k % 3 - 1) * a.dil; }
+      f32x2 v[NP], w[NP];
+      ldrow9(centre + (dy * hw + dx) * EP_CS, v);          // out-of-image pixels were zero-filled
+      ldrow9(dwb + k * EP_CS, w);
+#pragma unroll
+      for (int i = 0; i < NP; ++i) t2[i] = fma2(v[i], w[i], t2[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      float x0, x1;
+      unpack2(t2[i], x0, x1);
+      pk[br * NP + i] = pack_f16x2(x0, x1);
+    }
+  }
+  __syncthreads();                                         // every thread is done with the input tile
+  const uint32_t a_blk = smem_u32(tile) + (uint32_t)(tid >> 7) * kA;
+  const uint32_t a_row = a_blk + (uint32_t)(tid & 127) * 128u;
+  const uint32_t swz = (uint32_t)tid & 7u;
+  store_row(a_row, swz, pk);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    if (elect_one()) {
+      tc_fence_after();
+      const uint32_t id1 = make_idesc(0, 64);
+      const uint64_t db = make_smem_desc(smem_u32(B1));
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const uint64_t da = make_smem_desc(smem_u32(tile) + m * kA);
+        umma_f16<0>(tmem + m * 64, da, db, id1);
+        umma_f16<1>(tmem + m * 64, da + 2, db + 2, id1);
+        umma_f16<1>(tmem + m * 64, da + 4, db + 4, id1);
+        umma_f16<1>(tmem + m * 64, da + 6, db + 6, id1);
+      }
+      umma_commit(bars);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bars, 0);
+  tc_fence_after();
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tid >> 7) * 64u;
+  {
+    float s[32];
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      tmem_ld32(tlane + hlf * 32, s);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x0 = s[2 * i], x1 = s[2 * i + 1];
+        x0 = x0 > 0.f ? x0 : x0 * a.slope;
+        x1 = x1 > 0.f ? x1 : x1 * a.slope;
+        pk[hlf * 16 + i] = pack_f16x2(x0, x1);
+      }
+    }
+  }
+  store_row(a_row, swz, pk);                               // stage-1 MMAs have retired: the row is rewritten in place
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    if (elect_one()) {
+      tc_fence_after();
+      const uint32_t id2 = make_idesc(0, 32);
+      const uint64_t db = make_smem_desc(smem_u32(B2));
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const uint64_t da = make_smem_desc(smem_u32(tile) + m * kA);
+        umma_f16<0>(tmem + m * 64, da, db, id2);
+        umma_f16<1>(tmem + m * 64, da + 2, db + 2, id2);
+        umma_f16<1>(tmem + m * 64, da + 4, db + 4, id2);
+        umma_f16<1>(tmem + m * 64, da + 6, db + 6, id2);
+      }
+      umma_commit(bars + 1);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bars + 1, 0);
+  tc_fence_after();
+  {
+    float o[32];
+    tmem_ld32(tlane, o);
+    tmem_wait_ld();
+    if (ox < a.in.w && oy < a.in.h) {
+      float* dst = a.out.p + a.out.pix(img, oy, ox);
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        float x0 = o[2 * i], x1 = o[2 * i + 1];
+        x0 = x0 > 0.f ? x0 : x0 * a.slope;
+        x1 = x1 > 0.f ? x1 : x1 * a.slope;
+        reinterpret_cast<float2*>(dst)[i] = make_float2(x0, x1);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
 }  // namespace lfsr
 
 using namespace lfsr;
@@ -338,4 +562,35 @@ extern "C" int lfsr_mel_epi_branch(const lfsr_tensor* in, const float* w_packed,
   }
   mel_epi_branch_kernel<<<in->n * a.tiles_x * a.tiles_y, 256, smem, (cudaStream_t)stream>>>(a);
   return check_launch("mel_epi_branch_kernel");
+}
+
+static size_t epi_tc_smem(int klen, int dil) {
+  const int halo = klen / 2 > dil ? klen / 2 : dil;
+  size_t tile = (size_t)(EP_W + 2 * halo) * (EP_H + 2 * halo) * EP_CS * sizeof(float);
+  if (tile < 2 * et::kA) tile = 2 * et::kA;
+  const size_t taps = (size_t)(((2 * klen + 9) * EP_CS + 3) & ~3) * sizeof(float);
+  return 1024 + et::kB1 + et::kB2 + tile + taps + 32;
+}
+
+extern "C" int lfsr_mel_epi_branch_tc(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out, int klen, int dil,
+                                      float slope, void* stream) {
+  LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && w_packed, "lfsr_mel_epi_branch_tc: null/invalid tensor");
+  LFSR_REQUIRE(in->c == EC && out->c == EC, "lfsr_mel_epi_branch_tc: built for %d-channel EPI splits, got %d", EC, in->c);
+  LFSR_REQUIRE(in->n == out->n && in->h == out->h && in->w == out->w, "lfsr_mel_epi_branch_tc: shape mismatch");
+  LFSR_REQUIRE(klen > 0 && (klen & 1) && klen <= 31 && dil > 0, "lfsr_mel_epi_branch_tc: bad kernel length");
+  LFSR_REQUIRE(in->ld % 4 == 0 && in->ld >= EC + 2 && ((uintptr_t)in->ptr & 15) == 0,
+               "lfsr_mel_epi_branch_tc: input slice must be 16-byte aligned with 2 readable pad floats (grouped trunk layout)");
+  LFSR_REQUIRE(out->ld % 2 == 0 && ((uintptr_t)out->ptr & 7) == 0, "lfsr_mel_epi_branch_tc: 8-byte aligned output slice required");
+  EpiArgs a;
+  a.in = view_of(in); a.out = view_of(out); a.w = w_packed; a.KL = klen; a.dil = dil; a.slope = slope;
+  a.tiles_x = ceil_div(in->w, EP_W); a.tiles_y = ceil_div(in->h, EP_H);
+  const size_t smem = epi_tc_smem(klen, dil);
+  LFSR_REQUIRE(smem <= 200 * 1024, "lfsr_mel_epi_branch_tc: kernel length / dilation too large for the staged tile");
+  static DevOnce once;
+  if (once.need()) {
+    if (opt_in_smem(mel_epi_branch_tc_kernel, 200 * 1024, "lfsr_mel_epi_branch_tc")) return LFSR_ERR_CUDA;
+    once.done();
+  }
+  mel_epi_branch_tc_kernel<<<in->n * a.tiles_x * a.tiles_y, 256, smem, (cudaStream_t)stream>>>(a);
+  return check_launch("mel_epi_branch_tc_kernel");
 }

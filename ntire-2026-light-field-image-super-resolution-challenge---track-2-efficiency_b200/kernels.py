@@ -325,10 +325,11 @@ class CudaOps:
         N.check(self.lib.lfsr_dwconv_multi(C.byref(as_tensor(x, "dwconv_multi.in")), C.byref(as_tensor(out, "dwconv_multi.out")),
                                            arr, len(branches), self._stream(x)), "lfsr_dwconv_multi")
 
-    def mel_epi_branch(self, x, w_packed, out, klen, dil, slope):
-        N.check(self.lib.lfsr_mel_epi_branch(C.byref(as_tensor(x, "epi.in")), w_packed.data_ptr(),
-                                             C.byref(as_tensor(out, "epi.out")), klen, dil, slope, self._stream(x)),
-                "lfsr_mel_epi_branch")
+    def mel_epi_branch(self, x, w_packed, out, klen, dil, slope, tc=False):
+        """tc=True: the 1x1 contractions on the tensor cores (fp16 operands), used on the fp16 operand plan"""
+        fn = self.lib.lfsr_mel_epi_branch_tc if (tc and self.use_tc) else self.lib.lfsr_mel_epi_branch
+        N.check(fn(C.byref(as_tensor(x, "epi.in")), w_packed.data_ptr(), C.byref(as_tensor(out, "epi.out")), klen, dil, slope,
+                   self._stream(x)), "lfsr_mel_epi_branch")
 
     # -- reductions / gates -------------------------------------------------------------------------
     def block_mean(self, x, out, bh, bw):

@@ -330,7 +330,7 @@ class get_model(LFNetBase):
                 ops.conv(ang5[..., 0:c0], st["ang_ex"], cat[..., gs:2 * gs], act=LR, slope=0.1, alpha=st["ang_scale"],
                          res=feat[..., gs:2 * gs], shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
             # EPI branch: three depthwise+pointwise paths and their fuse conv in one kernel
-            ops.mel_epi_branch(xe, st["epi_w"], cat[..., sl[2]], st["epi_klen"], A, 0.1)
+            ops.mel_epi_branch(xe, st["epi_w"], cat[..., sl[2]], st["epi_klen"], A, 0.1, tc=bool(f16))
             fork.join()
             # gates -> per-sample channel scale of the fusion 1x1
             ops.block_mean(cat, vmean, hA, wA)

@@ -191,7 +191,7 @@ class RefOps:
             self.dwconv(x[..., i0:i0 + c], b["w"], out[..., o0:o0 + c], b["kh"], b["kw"], b.get("dil", (1, 1)),
                         b.get("scale"), b.get("shift"), b.get("act", 0), b.get("slope", 0.0))
 
-    def mel_epi_branch(self, x, w_packed, out, klen, dil, slope):
+    def mel_epi_branch(self, x, w_packed, out, klen, dil, slope, tc=False):
         c = x.shape[3]
         o = 0
         def take(n, shape):
