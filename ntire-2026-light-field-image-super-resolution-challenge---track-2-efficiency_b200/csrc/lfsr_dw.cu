@@ -281,6 +281,20 @@ dw_tile_kernel(const __grid_constant__ DwParams p) {
                    ::"r"(dw_smem_u32(tS)), "l"(&p.tm[b]), "r"(dw_smem_u32(&bar)), "r"(cin0), "r"(tx0 - hx), "r"(ty0 - hy), "r"(img)
                    : "memory");
     }
+    if (p.sa && p.res.p) {
+      // SA tail: the residual rows this thread will add are requested into L2 now, while the tile is in flight. The row loop
+      // cannot hoist its residual loads over the stores of the row before (they may alias), so without this every row
+      // pays a full DRAM round trip in sequence: 8 rows x ~1.5 us was the whole lifetime of a CTA.
+      const int q = tid & 3, lx = (tid >> 2) & 31;
+      const int ox = tx0 + lx;
+      if (ox < W && wofs + q * 4 < B.c && !(q & 1)) {          // one request per 32-byte sector
+#pragma unroll
+        for (int r = tid >> 7; r < DW_TH; r += 2) {
+          const int oy = ty0 + r;
+          if (oy < H) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res.p + p.res.pix(img, oy, ox) + cout0 + q * 4));
+        }
+      }
+    }
     dw_stage_taps(p, B, wS, wofs, tid);
     __syncthreads();                   // taps visible; the barrier was initialised before anybody polls it
     dw_mbar_wait(&bar, 0);
@@ -321,6 +335,125 @@ dw_tile_kernel(const __grid_constant__ DwParams p) {
     else if (!p.sa && Bj.kh == 7 && Bj.kw == 7 && Bj.dh == 1 && Bj.dw == 1) dw_compute_col<7, 1>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
     else dw_compute<0, 0>(p, Bj, wS + wo, tj, SW, img, ty0, tx0, co, wofs);
     wo += Bj.kh * Bj.kw * DW_CH;
+  }
+}
+
+// SA-modulator tail (MyEfficientLFNet.py:495-515, :207) as its own lean kernel: out = x * (w0 * sigmoid(BN(dw3x3(x))) + w1 * amod[view])
+// + res, optional fp16 copy of the first o16_c channels. Same tiling and TMA staging as dw_tile_kernel, but the row loop is written
+// for exactly this case: the nine tap weights, the BN affine and w1 * amod live in registers, addresses advance by a
+// constant per row (32-bit), the residual and modulation of the NEXT row are loaded before the current row is stored (and all
+// residual rows are requested into L2 while the tile is still in flight), and the sigmoid is ex2 + rcp. The generic kernel
+// spent ~300 issued instructions per output row and quad on this tail (switch on the activation, 64-bit pixel offsets per
+// row, a spilled loop counter); this one ~80.
+__device__ __forceinline__ float sa_sigmoid(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
+
+__global__ void __launch_bounds__(256, 3)
+sa_tile_kernel(const __grid_constant__ DwParams p) {
+  extern __shared__ __align__(16) float dw_smem[];
+  const int tid = threadIdx.x;
+  const DwBranch& B = p.br[0];
+  const int wofs = (int)blockIdx.y * DW_CH;
+  const int cin0 = B.in_c0 + wofs, cout0 = B.out_c0 + wofs;
+  const int d = B.dh;
+  const int SH = DW_TH + 2 * d, SW = DW_TW + 2 * d;
+  const int img = blockIdx.z;
+  const int tyi = blockIdx.x / p.tiles_x;
+  const int ty0 = tyi * DW_TH, tx0 = (blockIdx.x - tyi * p.tiles_x) * DW_TW;
+  float* tS = dw_smem + ((128u - (dw_smem_u32(dw_smem) & 127u)) & 127u) / 4;
+  float* wS = tS + p.tile_floats;
+  __shared__ uint64_t bar;
+  const int H = p.in.h, W = p.in.w;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dw_smem_u32(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dw_smem_u32(&bar)), "r"(SH * SW * DW_CH * 4) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dw_smem_u32(tS)), "l"(&p.tm[0]), "r"(dw_smem_u32(&bar)), "r"(cin0), "r"(tx0 - d), "r"(ty0 - d), "r"(img)
+                 : "memory");
+  }
+  const int q = tid & 3, lx = (tid >> 2) & 31, ly0 = tid >> 7;
+  const int ox = tx0 + lx;
+  const bool live = ox < W && wofs + q * 4 < B.c;
+  const int c4 = cout0 + q * 4;
+  // per-image bases (64-bit once), then 32-bit element offsets inside the image
+  const float* resI = p.res.p ? p.res.p + (size_t)img * p.res.h * p.res.w * p.res.ld : nullptr;
+  float* outI = p.out.p + (size_t)img * p.out.h * p.out.w * p.out.ld;
+  const float* amI = p.amod.p + (size_t)img * p.amod.h * p.amod.w * p.amod.ld;
+  const int rows_here = min(DW_TH, H - ty0);
+  if (live && resI && !(q & 1)) {
+#pragma unroll
+    for (int r = ly0; r < DW_TH; r += 2)
+      if (r < rows_here) asm volatile("prefetch.global.L2 [%0];" ::"l"(resI + ((ty0 + r) * p.res.w + ox) * p.res.ld + c4));
+  }
+  // taps with the BatchNorm scale folded in (BN(dw(x)) = sum (scale * w) x + shift); read back per row as 16-byte loads that
+  // only differ between the four channel quads of a warp
+  for (int i = tid; i < 9 * DW_CH; i += 256) {
+    const int c = wofs + (i & 15);
+    wS[i] = c < B.c ? __ldg(B.w + (i >> 4) * B.c + c) * __ldg(B.scale + c) : 0.f;
+  }
+  __syncthreads();
+  dw_mbar_wait(&bar, 0);
+  if (!live) return;
+  const float* wq = wS + q * 4;
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(B.shift + wofs + q * 4));
+  const f32x2 shlo = pack2(sh.x, sh.y), shhi = pack2(sh.z, sh.w);
+  const int row_f = SW * DW_CH;
+  const int dyf = d * row_f, dxf = d * DW_CH;
+  const int vh = H / p.amod.h;
+  const int am_x = (ox / (W / p.amod.w)) * p.amod.ld + c4;
+  const float w0 = p.sa_w0, w1 = p.sa_w1;
+  const int res_step = 2 * p.res.w * p.res.ld, out_step = 2 * p.out.w * p.out.ld;
+  int res_o = ((ty0 + ly0) * p.res.w + ox) * p.res.ld + c4;
+  int out_o = ((ty0 + ly0) * p.out.w + ox) * p.out.ld + c4;
+  const bool do16 = p.o16 && c4 < p.o16_c;
+  __half* o16I = p.o16 + (size_t)img * p.out.h * p.out.w * p.o16_ld;
+  int o16_o = ((ty0 + ly0) * p.out.w + ox) * p.o16_ld + c4;
+  const int o16_step = 2 * p.out.w * p.o16_ld;
+  const float* base = tS + ly0 * row_f + lx * DW_CH + q * 4;
+  float4 rn = make_float4(0.f, 0.f, 0.f, 0.f), an;
+  if (ly0 < rows_here) {
+    if (resI) rn = *reinterpret_cast<const float4*>(resI + res_o);
+    an = __ldg(reinterpret_cast<const float4*>(amI + ((ty0 + ly0) / vh) * p.amod.w * p.amod.ld + am_x));
+  }
+#pragma unroll 1
+  for (int r = ly0; r < rows_here; r += 2) {
+    const float4 rc = rn, ac = an;
+    if (r + 2 < rows_here) {                 // next row's residual and modulation: in flight across this row's arithmetic
+      if (resI) rn = *reinterpret_cast<const float4*>(resI + res_o + res_step);
+      an = __ldg(reinterpret_cast<const float4*>(amI + ((ty0 + r + 2) / vh) * p.amod.w * p.amod.ld + am_x));
+    }
+    f32x2 alo = shlo, ahi = shhi;
+    float4 xc;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4 v = *reinterpret_cast<const float4*>(base + ky * dyf + kx * dxf);
+        const float4 w = *reinterpret_cast<const float4*>(wq + (ky * 3 + kx) * DW_CH);
+        if (ky == 1 && kx == 1) xc = v;
+        alo = fma2(pack2(v.x, v.y), pack2(w.x, w.y), alo);
+        ahi = fma2(pack2(v.z, v.w), pack2(w.z, w.w), ahi);
+      }
+    float4 a;
+    unpack2(alo, a.x, a.y);
+    unpack2(ahi, a.z, a.w);
+    a.x = fmaf(xc.x, fmaf(w0, sa_sigmoid(a.x), w1 * ac.x), rc.x);
+    a.y = fmaf(xc.y, fmaf(w0, sa_sigmoid(a.y), w1 * ac.y), rc.y);
+    a.z = fmaf(xc.z, fmaf(w0, sa_sigmoid(a.z), w1 * ac.z), rc.z);
+    a.w = fmaf(xc.w, fmaf(w0, sa_sigmoid(a.w), w1 * ac.w), rc.w);
+    *reinterpret_cast<float4*>(outI + out_o) = a;
+    if (do16) {
+      const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+      uint2 v;
+      v.x = *reinterpret_cast<const uint32_t*>(&h0); v.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(o16I + o16_o) = v;
+    }
+    base += 2 * row_f; res_o += res_step; out_o += out_step; o16_o += o16_step;
   }
 }
 
@@ -464,6 +597,17 @@ static int dw_launch(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_d
     once.done();
   }
   dim3 grid(p.tiles_x * ceil_div(in->h, DW_TH), items, in->n);
+  if (sa && p.use_tma && nbr == 1 && br[0].kh == 3 && br[0].kw == 3 && br[0].dil_h == br[0].dil_w && br[0].scale &&
+      br[0].act == LFSR_ACT_SIGMOID && in->h % p.amod.h == 0 && in->w % p.amod.w == 0 &&
+      (!p.res.p || (p.res.h == in->h && p.res.w == in->w))) {
+    static DevOnce once_sa;
+    if (once_sa.need()) {
+      if (opt_in_smem(sa_tile_kernel, 200 * 1024 + 4096, "lfsr_sa_modulate")) return LFSR_ERR_CUDA;
+      once_sa.done();
+    }
+    sa_tile_kernel<<<grid, 256, smem, st>>>(p);
+    return check_launch("sa_tile_kernel");
+  }
   if (p.share) dw_tile_kernel<true><<<grid, 256, smem, st>>>(p);
   else dw_tile_kernel<false><<<grid, 256, smem, st>>>(p);
   return check_launch("dw_tile_kernel");
