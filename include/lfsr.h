@@ -234,6 +234,13 @@ int lfsr_conv2d_tc_supported(const lfsr_tensor* in, const lfsr_tensor* out, cons
 /* mean over each (block_h x block_w) block: in [n,h,w,c] -> out [n, h/block_h, w/block_w, c] */
 int lfsr_block_mean(const lfsr_tensor* in, const lfsr_tensor* out, int block_h, int block_w,
                     void* stream);
+/* Chains of 1x1 convolutions on a handful of positions per image, one launch per chain: the channel gates of a Track-2 stage
+ * (MyEfficientLFNet.py:159-173: AdaptiveAvgPool -> 1x1 + bias -> sigmoid; pool = 1) and the angular half of the SA modulator
+ * (:505-511: 1x1 -> ReLU -> 1x1 -> sigmoid on the per-view means; pool = 0).
+ *   x = pool ? mean over the h*w positions of `in` : in;  h = act1(b1 + x . w1);  out = w2 ? act2(b2 + h . w2) : h
+ * w1 is [in->c][c1], w2 [c1][c2] (the lfsr_conv2d_f32 packing of a 1x1 kernel); b1 / b2 / w2 may be null. */
+int lfsr_pooled_mlp(const lfsr_tensor* in, int pool, const float* w1, const float* b1, int c1, int act1, const float* w2,
+                    const float* b2, int c2, int act2, const lfsr_tensor* out, void* stream);
 /* SAModulator tail (MyEfficientLFNet.py:495-515) fused with the stage residual:
  *   s = sigmoid(bn_scale*dw3x3_dil(x) + bn_shift); a = amod[n][y/(h/A)][x/(w/A)][c]
  *   out = x * (w0*s + w1*a) + res */

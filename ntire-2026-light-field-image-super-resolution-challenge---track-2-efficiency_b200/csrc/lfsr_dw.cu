@@ -352,7 +352,8 @@ __device__ __forceinline__ float sa_sigmoid(float v) {
   return r;
 }
 
-__global__ void __launch_bounds__(256, 3)
+constexpr int SA_THREADS = 512;
+__global__ void __launch_bounds__(SA_THREADS, 2)
 sa_tile_kernel(const __grid_constant__ DwParams p) {
   extern __shared__ __align__(16) float dw_smem[];
   const int tid = threadIdx.x;
@@ -376,83 +377,82 @@ sa_tile_kernel(const __grid_constant__ DwParams p) {
                  ::"r"(dw_smem_u32(tS)), "l"(&p.tm[0]), "r"(dw_smem_u32(&bar)), "r"(cin0), "r"(tx0 - d), "r"(ty0 - d), "r"(img)
                  : "memory");
   }
-  const int q = tid & 3, lx = (tid >> 2) & 31, ly0 = tid >> 7;
+  // thread = one channel PAIR of one pixel column, every second row of the tile: the nine tap pairs then fit in registers
+  // (18) at two 512-thread CTAs per SM, so the only shared-memory reads of the row loop are the nine tile taps. (With
+  // channel quads the 36 tap registers did not fit next to three CTAs per SM, and re-reading them from shared memory per
+  // row doubled the load wavefronts: the kernel sat at 87 % of the L1/shared data pipe.)
+  const int q = tid & 7, lx = (tid >> 3) & 31, ly0 = tid >> 8;
   const int ox = tx0 + lx;
-  const bool live = ox < W && wofs + q * 4 < B.c;
-  const int c4 = cout0 + q * 4;
+  const bool live = ox < W && wofs + q * 2 < B.c;
+  const int c2 = cout0 + q * 2;
   // per-image bases (64-bit once), then 32-bit element offsets inside the image
   const float* resI = p.res.p ? p.res.p + (size_t)img * p.res.h * p.res.w * p.res.ld : nullptr;
   float* outI = p.out.p + (size_t)img * p.out.h * p.out.w * p.out.ld;
   const float* amI = p.amod.p + (size_t)img * p.amod.h * p.amod.w * p.amod.ld;
   const int rows_here = min(DW_TH, H - ty0);
-  if (live && resI && !(q & 1)) {
+  if (live && resI && !(q & 3)) {                      // one request per 32-byte sector
 #pragma unroll
     for (int r = ly0; r < DW_TH; r += 2)
-      if (r < rows_here) asm volatile("prefetch.global.L2 [%0];" ::"l"(resI + ((ty0 + r) * p.res.w + ox) * p.res.ld + c4));
+      if (r < rows_here) asm volatile("prefetch.global.L2 [%0];" ::"l"(resI + ((ty0 + r) * p.res.w + ox) * p.res.ld + c2));
   }
-  // taps with the BatchNorm scale folded in (BN(dw(x)) = sum (scale * w) x + shift); read back per row as 16-byte loads that
-  // only differ between the four channel quads of a warp
-  for (int i = tid; i < 9 * DW_CH; i += 256) {
+  // taps with the BatchNorm scale folded in: BN(dw(x)) = sum (scale * w) x + shift
+  for (int i = tid; i < 9 * DW_CH; i += SA_THREADS) {
     const int c = wofs + (i & 15);
     wS[i] = c < B.c ? __ldg(B.w + (i >> 4) * B.c + c) * __ldg(B.scale + c) : 0.f;
   }
   __syncthreads();
   dw_mbar_wait(&bar, 0);
   if (!live) return;
-  const float* wq = wS + q * 4;
-  const float4 sh = __ldg(reinterpret_cast<const float4*>(B.shift + wofs + q * 4));
-  const f32x2 shlo = pack2(sh.x, sh.y), shhi = pack2(sh.z, sh.w);
+  f32x2 w[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) w[t] = *reinterpret_cast<const f32x2*>(wS + t * DW_CH + q * 2);
+  const f32x2 sh = *reinterpret_cast<const f32x2*>(B.shift + wofs + q * 2);
   const int row_f = SW * DW_CH;
   const int dyf = d * row_f, dxf = d * DW_CH;
   const int vh = H / p.amod.h;
-  const int am_x = (ox / (W / p.amod.w)) * p.amod.ld + c4;
+  const int am_x = (ox / (W / p.amod.w)) * p.amod.ld + c2;
+  const int am_row = p.amod.w * p.amod.ld;
   const float w0 = p.sa_w0, w1 = p.sa_w1;
   const int res_step = 2 * p.res.w * p.res.ld, out_step = 2 * p.out.w * p.out.ld;
-  int res_o = ((ty0 + ly0) * p.res.w + ox) * p.res.ld + c4;
-  int out_o = ((ty0 + ly0) * p.out.w + ox) * p.out.ld + c4;
-  const bool do16 = p.o16 && c4 < p.o16_c;
+  int res_o = ((ty0 + ly0) * p.res.w + ox) * p.res.ld + c2;
+  int out_o = ((ty0 + ly0) * p.out.w + ox) * p.out.ld + c2;
+  const bool do16 = p.o16 && c2 < p.o16_c;
   __half* o16I = p.o16 + (size_t)img * p.out.h * p.out.w * p.o16_ld;
-  int o16_o = ((ty0 + ly0) * p.out.w + ox) * p.o16_ld + c4;
+  int o16_o = ((ty0 + ly0) * p.out.w + ox) * p.o16_ld + c2;
   const int o16_step = 2 * p.out.w * p.o16_ld;
-  const float* base = tS + ly0 * row_f + lx * DW_CH + q * 4;
-  float4 rn = make_float4(0.f, 0.f, 0.f, 0.f), an;
+  const float* base = tS + ly0 * row_f + lx * DW_CH + q * 2;
+  // view row of the current output row, stepped without a division per row
+  int ay = (ty0 + ly0) / vh, arem = (ty0 + ly0) - ay * vh;
+  float2 rn = make_float2(0.f, 0.f), an = make_float2(0.f, 0.f);
   if (ly0 < rows_here) {
-    if (resI) rn = *reinterpret_cast<const float4*>(resI + res_o);
-    an = __ldg(reinterpret_cast<const float4*>(amI + ((ty0 + ly0) / vh) * p.amod.w * p.amod.ld + am_x));
+    if (resI) rn = *reinterpret_cast<const float2*>(resI + res_o);
+    an = __ldg(reinterpret_cast<const float2*>(amI + ay * am_row + am_x));
   }
 #pragma unroll 1
   for (int r = ly0; r < rows_here; r += 2) {
-    const float4 rc = rn, ac = an;
+    const float2 rc = rn, ac = an;
     if (r + 2 < rows_here) {                 // next row's residual and modulation: in flight across this row's arithmetic
-      if (resI) rn = *reinterpret_cast<const float4*>(resI + res_o + res_step);
-      an = __ldg(reinterpret_cast<const float4*>(amI + ((ty0 + r + 2) / vh) * p.amod.w * p.amod.ld + am_x));
+      if (resI) rn = *reinterpret_cast<const float2*>(resI + res_o + res_step);
+      arem += 2;
+      while (arem >= vh) { arem -= vh; ++ay; }
+      an = __ldg(reinterpret_cast<const float2*>(amI + ay * am_row + am_x));
     }
-    f32x2 alo = shlo, ahi = shhi;
-    float4 xc;
+    f32x2 acc = sh;
+    float2 xc;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const float4 v = *reinterpret_cast<const float4*>(base + ky * dyf + kx * dxf);
-        const float4 w = *reinterpret_cast<const float4*>(wq + (ky * 3 + kx) * DW_CH);
-        if (ky == 1 && kx == 1) xc = v;
-        alo = fma2(pack2(v.x, v.y), pack2(w.x, w.y), alo);
-        ahi = fma2(pack2(v.z, v.w), pack2(w.z, w.w), ahi);
+        const f32x2 v = *reinterpret_cast<const f32x2*>(base + ky * dyf + kx * dxf);
+        if (ky == 1 && kx == 1) unpack2(v, xc.x, xc.y);
+        acc = fma2(v, w[ky * 3 + kx], acc);
       }
-    float4 a;
-    unpack2(alo, a.x, a.y);
-    unpack2(ahi, a.z, a.w);
+    float2 a;
+    unpack2(acc, a.x, a.y);
     a.x = fmaf(xc.x, fmaf(w0, sa_sigmoid(a.x), w1 * ac.x), rc.x);
     a.y = fmaf(xc.y, fmaf(w0, sa_sigmoid(a.y), w1 * ac.y), rc.y);
-    a.z = fmaf(xc.z, fmaf(w0, sa_sigmoid(a.z), w1 * ac.z), rc.z);
-    a.w = fmaf(xc.w, fmaf(w0, sa_sigmoid(a.w), w1 * ac.w), rc.w);
-    *reinterpret_cast<float4*>(outI + out_o) = a;
-    if (do16) {
-      const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
-      uint2 v;
-      v.x = *reinterpret_cast<const uint32_t*>(&h0); v.y = *reinterpret_cast<const uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(o16I + o16_o) = v;
-    }
+    *reinterpret_cast<float2*>(outI + out_o) = a;
+    if (do16) *reinterpret_cast<__half2*>(o16I + o16_o) = __floats2half2_rn(a.x, a.y);
     base += 2 * row_f; res_o += res_step; out_o += out_step; o16_o += o16_step;
   }
 }
@@ -605,7 +605,7 @@ static int dw_launch(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_d
       if (opt_in_smem(sa_tile_kernel, 200 * 1024 + 4096, "lfsr_sa_modulate")) return LFSR_ERR_CUDA;
       once_sa.done();
     }
-    sa_tile_kernel<<<grid, 256, smem, st>>>(p);
+    sa_tile_kernel<<<grid, SA_THREADS, smem, st>>>(p);
     return check_launch("sa_tile_kernel");
   }
   if (p.share) dw_tile_kernel<true><<<grid, 256, smem, st>>>(p);

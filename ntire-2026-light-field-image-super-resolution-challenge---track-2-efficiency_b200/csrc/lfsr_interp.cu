@@ -68,6 +68,57 @@ interp_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int 
   }
 }
 
+// Bicubic, scale S in {2, 4}: one thread per output row and INPUT column k writes the S outputs S*k .. S*k+S-1. Their taps
+// all lie in input columns k-2 .. k+2, so a thread reads 5 x 4 values for S outputs (16 per output in the generic kernel),
+// does its index arithmetic once and stores one 8/16-byte vector. Same expression per output as interp_kernel.
+template <int S>
+__global__ void __launch_bounds__(256)
+interp_bicubic_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w, int bh, int bw) {
+  const int oh = h * S, ow = w * S;
+  const float rs = 1.0f / (float)S;
+  const int img = blockIdx.y;
+  out += (size_t)img * oh * ow;
+  in += (size_t)img * h * w;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < oh * w; t += gridDim.x * blockDim.x) {
+    const int kx = t % w;                      // input column
+    const int oy = t / w;
+    const int vby = oy / (bh * S), ly = oy - vby * bh * S;
+    const int vbx = kx / bw, k = kx - vbx * bw;
+    const float* base = in + (size_t)vby * bh * w + (size_t)vbx * bw;
+    const float ry = rs * ((float)ly + 0.5f) - 0.5f;
+    const float fy = floorf(ry);
+    const int iy = (int)fy;
+    float cy[4];
+    cubic_coeffs(ry - fy, cy);
+    float v[4][5];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* row = base + (size_t)clampi(iy - 1 + j, 0, bh - 1) * w;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) v[j][i] = __ldg(row + clampi(k - 2 + i, 0, bw - 1));
+    }
+    float o[S];
+#pragma unroll
+    for (int u = 0; u < S; ++u) {
+      const float rx = rs * ((float)(k * S + u) + 0.5f) - 0.5f;
+      const float fx = floorf(rx);
+      float cx[4];
+      cubic_coeffs(rx - fx, cx);
+      const int off = u < S / 2 ? 0 : 1;       // floor(rx) = k - 1 for the first half of the S outputs, k for the second
+      float val = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float rsum = v[j][off] * cx[0] + v[j][off + 1] * cx[1] + v[j][off + 2] * cx[2] + v[j][off + 3] * cx[3];
+        val += rsum * cy[j];
+      }
+      o[u] = val;
+    }
+    float* dst = out + (size_t)oy * ow + (size_t)kx * S;
+    if (S == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    else *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[S - 1]);
+  }
+}
+
 }  // namespace lfsr
 
 using namespace lfsr;
@@ -80,6 +131,13 @@ extern "C" int lfsr_interp(const float* in, float* out, int n, int h, int w, int
   LFSR_REQUIRE(block_h > 0 && block_w > 0 && h % block_h == 0 && w % block_w == 0,
                "lfsr_interp: block %dx%d does not tile %dx%d", block_h, block_w, h, w);
   LFSR_REQUIRE(n <= 65535 && (long long)h * scale * w * scale < 0x7fffffffLL, "lfsr_interp: image too large");
+  if (mode == LFSR_INTERP_BICUBIC && (scale == 2 || scale == 4) && ((uintptr_t)out & 15) == 0) {
+    const int per_t = h * scale * w;
+    dim3 g2(ceil_div(per_t, 256) < 1184 ? ceil_div(per_t, 256) : 1184, n);
+    if (scale == 4) interp_bicubic_kernel<4><<<g2, 256, 0, (cudaStream_t)stream>>>(in, out, h, w, block_h, block_w);
+    else interp_bicubic_kernel<2><<<g2, 256, 0, (cudaStream_t)stream>>>(in, out, h, w, block_h, block_w);
+    return check_launch("interp_bicubic_kernel");
+  }
   const int per = h * scale * w * scale;
   dim3 grid(ceil_div(per, 256) < 1184 ? ceil_div(per, 256) : 1184, n);
   interp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, n, h, w, scale, mode, block_h, block_w);

@@ -603,6 +603,68 @@ extern "C" int lfsr_block_mean(const lfsr_tensor* in, const lfsr_tensor* out, in
   return check_launch("block_mean_kernel");
 }
 
+// ---- tiny per-image MLPs of the Track-2 stages ------------------------------------------------------------------
+// The channel gates (MyEfficientLFNet.py:159-173: mean over the views -> 1x1 conv + bias -> sigmoid) and the angular part of
+// the SA modulator (:505-511: per-view means -> 1x1 -> ReLU -> 1x1 -> sigmoid) are chains of 1x1 convolutions on 1..25
+// positions per image. As separate launches of the general conv kernels they cost 17-35 us each - launch- and
+// latency-bound, ~0.5 ms per forward; here each chain is one launch with one CTA per image.
+//   x[p][c]  = in[img][p][c]                        (pool: x[0][c] = mean over the h*w positions, one position left)
+//   h[p][j]  = act1(b1[j] + sum_c x[p][c] w1[c][j])                     w1: [cin][c1]  (lfsr_conv2d_f32 packing of a 1x1)
+//   out[p][o] = act2(b2[o] + sum_j h[p][j] w2[j][o])   (w2 == null: out = h)
+namespace lfsr {
+__global__ void __launch_bounds__(256)
+pooled_mlp_kernel(TView in, TView out, int pool, const float* __restrict__ w1, const float* __restrict__ b1, int c1, int act1,
+                  const float* __restrict__ w2, const float* __restrict__ b2, int c2, int act2) {
+  extern __shared__ float pm_s[];
+  const int img = blockIdx.x, tid = threadIdx.x;
+  const int P = in.h * in.w, C = in.c;
+  const int Pq = pool ? 1 : P;
+  float* x = pm_s;                 // [Pq][C]
+  float* h = pm_s + Pq * C;        // [Pq][c1]
+  const float* src = in.p + (size_t)img * P * in.ld;
+  if (pool) {
+    const float inv = 1.f / (float)P;
+    for (int c = tid; c < C; c += 256) {
+      float acc = 0.f;
+      for (int q = 0; q < P; ++q) acc += src[q * in.ld + c];
+      x[c] = acc * inv;
+    }
+  } else {
+    for (int i = tid; i < P * C; i += 256) { const int q = i / C, c = i - q * C; x[i] = src[q * in.ld + c]; }
+  }
+  __syncthreads();
+  float* dst = out.p + (size_t)img * Pq * out.ld;
+  for (int i = tid; i < Pq * c1; i += 256) {
+    const int q = i / c1, j = i - q * c1;
+    float acc = b1 ? __ldg(b1 + j) : 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(x[q * C + c], __ldg(w1 + c * c1 + j), acc);
+    acc = apply_act(acc, act1, 0.f);
+    if (w2) h[i] = acc; else dst[q * out.ld + j] = acc;
+  }
+  if (!w2) return;
+  __syncthreads();
+  for (int i = tid; i < Pq * c2; i += 256) {
+    const int q = i / c2, o = i - q * c2;
+    float acc = b2 ? __ldg(b2 + o) : 0.f;
+    for (int j = 0; j < c1; ++j) acc = fmaf(h[q * c1 + j], __ldg(w2 + j * c2 + o), acc);
+    dst[q * out.ld + o] = apply_act(acc, act2, 0.f);
+  }
+}
+}  // namespace lfsr
+
+extern "C" int lfsr_pooled_mlp(const lfsr_tensor* in, int pool, const float* w1, const float* b1, int c1, int act1, const float* w2,
+                               const float* b2, int c2, int act2, const lfsr_tensor* out, void* stream) {
+  LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && w1 && c1 > 0, "lfsr_pooled_mlp: null/invalid argument");
+  LFSR_REQUIRE(!w2 || c2 > 0, "lfsr_pooled_mlp: second layer without a width");
+  const int P = in->h * in->w, Pq = pool ? 1 : P, cout = w2 ? c2 : c1;
+  LFSR_REQUIRE(out->n == in->n && out->h * out->w == Pq && out->c == cout, "lfsr_pooled_mlp: out shape mismatch");
+  const size_t smem = (size_t)Pq * (in->c + c1) * sizeof(float);
+  LFSR_REQUIRE(smem <= 48 * 1024 && in->n <= 0x7fffffff, "lfsr_pooled_mlp: positions x channels too large for one CTA");
+  pooled_mlp_kernel<<<in->n, 256, smem, (cudaStream_t)stream>>>(view_of(in), view_of(out), pool ? 1 : 0, w1, b1, c1, act1, w2, b2,
+                                                               c2, act2);
+  return check_launch("pooled_mlp_kernel");
+}
+
 int lfsr_sa_modulate_tiled(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
                            const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res, const lfsr_tensor* out, int dil,
                            int* handled, void* stream, const lfsr_tensor* out16 = nullptr);     // lfsr_dw.cu

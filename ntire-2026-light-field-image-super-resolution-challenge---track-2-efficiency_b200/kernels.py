@@ -336,6 +336,16 @@ class CudaOps:
         N.check(self.lib.lfsr_block_mean(C.byref(as_tensor(x, "block_mean.in")), C.byref(as_tensor(out, "block_mean.out")),
                                          bh, bw, self._stream(x)), "lfsr_block_mean")
 
+    def pooled_mlp(self, x, out, pc1: PackedConv, act1, pc2: Optional[PackedConv] = None, act2=N.ACT_NONE, pool=False):
+        """one launch for a chain of 1x1 convs on the few positions of `x` [n,h,w,c] (pool: on their mean): the stage gates
+        and the SA modulator's angular MLP of the Track-2 model"""
+        if pc1.kh != 1 or pc1.kw != 1 or pc1.cin != x.shape[3] or (pc2 is not None and (pc2.kh != 1 or pc2.kw != 1 or pc2.cin != pc1.cout)):
+            raise N.LfsrError("pooled_mlp: 1x1 layers whose widths chain are required")
+        N.check(self.lib.lfsr_pooled_mlp(C.byref(as_tensor(x, "mlp.in")), 1 if pool else 0, pc1.w_f32.data_ptr(), self._ptr(pc1.bias),
+                                         pc1.cout, act1, None if pc2 is None else pc2.w_f32.data_ptr(),
+                                         None if pc2 is None else self._ptr(pc2.bias), 0 if pc2 is None else pc2.cout, act2,
+                                         C.byref(as_tensor(out, "mlp.out")), self._stream(x)), "lfsr_pooled_mlp")
+
     def sa_modulate(self, x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil, out16=None):
         rt = as_tensor(res, "sa.res") if res is not None else _NULL_T
         if out16 is not None:

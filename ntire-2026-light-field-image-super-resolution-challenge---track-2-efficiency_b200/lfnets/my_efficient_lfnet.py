@@ -249,7 +249,10 @@ class get_model(LFNetBase):
         pk["stages"] = stages
         pk["gf0"] = pc(*pad_out(self._exp(self.global_fusion["0"].weight.detach().float().cpu(), 1)), tc=True)
         w, b = self.global_fusion["2"].merged()
-        pk["gf2"] = pc(self._exp(w.float().cpu(), 0), self._exp(b.float().cpu(), 0), tc=True, tc16=f16, **dil)
+        # fp16 operand plan: 64 output channels (60 + 4 zero rows), so the layer can write the fp16-only tensor the first
+        # upsampler conv reads (fp16 outputs need whole 16-byte channel groups)
+        pk["gf2"] = pc(*pad_out(self._exp(w.float().cpu(), 0), self._exp(b.float().cpu(), 0), to=64 if f16 else None), tc=True,
+                       tc16=f16, **dil)
         # upsampler activations carry CU = 56 channels (54 + 2 zero): 128-bit epilogue stores, and 4*56 = 224 is
         # exactly the MMA N the 216 real output channels were padded to anyway
         C = self.channels
@@ -265,8 +268,10 @@ class get_model(LFNetBase):
         for j, (i, r) in enumerate(self.upsampler.steps):
             w = self.upsampler.up[str(i)].weight.detach().float().cpu()
             w = self._exp(w, 1) if j == 0 else pad_ch(w, 1)          # reads the grouped trunk / the padded up buffer
+            if j == 0 and f16:                                      # ... as the 64-channel fp16 tensor of the fp16 operand plan
+                w = torch.cat([w, w.new_zeros((w.shape[0], 64 - w.shape[1]) + tuple(w.shape[2:]))], 1)
             w = pad_ch(w, 0, r * r)
-            ups.append((pc(w, pad=(1, 1), tc=True, tc16=f16 and j > 0, tc_shuffle=(r, r, N.SHUF_CHANNEL_MAJOR)), r))
+            ups.append((pc(w, pad=(1, 1), tc=True, tc16=f16, tc_shuffle=(r, r, N.SHUF_CHANNEL_MAJOR)), r))
         pk["up"] = ups
         pk["out"] = pc(pad_ch(self.output_conv.weight.detach().float().cpu(), 1), self.output_conv.bias, pad=(1, 1))
         pk["CU"] = CU
@@ -288,7 +293,10 @@ class get_model(LFNetBase):
         Y = out.view(B, H * s, W * s, 1)
         ops.interp(x, out, B, H, W, s, N.INTERP_BICUBIC, H, W)
 
-        shallow = buf("shallow", H, W, CP)
+        f16 = pk.get("f16")
+        # (fp16 operand plan: pixel stride 64 with zero pad floats, so the same buffer is the 64-channel residual of gf2)
+        shallow64 = buf("shallow64", H, W, 64) if f16 else None
+        shallow = shallow64[..., 0:CP] if f16 else buf("shallow", H, W, CP)
         ops.conv(xin, pk["stem"], shallow)
         feat = shallow
         pp = [buf("feat_a", H, W, CP), buf("feat_b", H, W, CP)]
@@ -334,8 +342,7 @@ class get_model(LFNetBase):
             fork.join()
             # gates -> per-sample channel scale of the fusion 1x1
             ops.block_mean(cat, vmean, hA, wA)
-            ops.block_mean(vmean, gmean, A, A)
-            ops.conv(gmean, st["gate"], gate, act=N.ACT_SIGMOID)
+            ops.pooled_mlp(vmean, gate, st["gate"], N.ACT_SIGMOID, pool=True)      # mean over the views -> FC + sigmoid
             if f16:
                 ops.conv(cat, st["fus0"], None, out16=fu1, act=LR, slope=0.1, in_scale=gate)
             else:
@@ -343,8 +350,7 @@ class get_model(LFNetBase):
             ops.conv(fu1[..., 0:C], st["fus2"], fu2)
             # SA modulator + stage residual
             ops.block_mean(fu2, pm, hA, wA)
-            ops.conv(pm, st["sa_c0"], am1, act=N.ACT_RELU)
-            ops.conv(am1, st["sa_c2"], am, act=N.ACT_SIGMOID)
+            ops.pooled_mlp(pm, am, st["sa_c0"], N.ACT_RELU, st["sa_c2"], N.ACT_SIGMOID)
             nxt = pp[i & 1]
             if f16 and gs + 12 <= CP and i + 1 < len(pk["stages"]):
                 ops.sa_modulate(fu2, st["sa_dw"], st["sa_bns"], st["sa_bnb"], am, st["sa_w"][0], st["sa_w"][1], feat, nxt, A, out16=xs16)
@@ -355,8 +361,15 @@ class get_model(LFNetBase):
             ops.conv(feat, pk["gf0"], None, out16=fu1, act=LR, slope=0.1)
         else:
             ops.conv(feat, pk["gf0"], fu1, act=LR, slope=0.1)
-        ops.conv(fu1[..., 0:C], pk["gf2"], fu2, res=shallow)
-        upsample_tail(self, ops, pk, fu2, H, W, Y, pk["CU"], LR, N.SHUF_CHANNEL_MAJOR)
+        if f16:
+            # the trunk's last tensor feeds nothing but the first upsampler conv: written as fp16 only, so that layer runs on
+            # kind::f16 operands like the second one
+            fu2h = self._buf16("fu2h", B, H, W, 64, dev)
+            ops.conv(fu1[..., 0:C], pk["gf2"], None, out16=fu2h, res=shallow64)
+            upsample_tail(self, ops, pk, fu2h, H, W, Y, pk["CU"], LR, N.SHUF_CHANNEL_MAJOR)
+        else:
+            ops.conv(fu1[..., 0:C], pk["gf2"], fu2, res=shallow)
+            upsample_tail(self, ops, pk, fu2, H, W, Y, pk["CU"], LR, N.SHUF_CHANNEL_MAJOR)
 
     # -- measurement hook --------------------------------------------------------------------------
     def dominant_kernel(self, batch: int, h: int = 32):

@@ -28,7 +28,9 @@ class ProfilingOps(K.CudaOps):
 
     def conv(self, x, pc, out, **kw):
         tc = "tc" if (pc.w_tc is not None) else "f32"
-        label = f"conv {pc.kh}x{pc.kw} {pc.cin}->{pc.cout} s{pc.stride[0]} d{pc.dil[0]} @{x.shape[1]}x{x.shape[2]} [{tc}]"
+        io = ("h" if x.dtype == torch.float16 else "f") + ">" + ("f" if out is not None else "") + ("h" if kw.get("out16") is not None else "")
+        extra = "".join(f" +{k}" for k in ("res", "mul", "in_scale", "tail") if kw.get(k) is not None) + (" +shuffle" if kw.get("shuffle", (1, 1, 0))[0] > 1 else "")
+        label = f"conv {pc.kh}x{pc.kw} {pc.cin}->{pc.cout} s{pc.stride[0]} d{pc.dil[0]} @{x.shape[1]}x{x.shape[2]} [{tc} {io}]{extra}"
         self._wrap("conv", lambda: K.CudaOps.conv(self, x, pc, out, **kw), label)
 
     def dwconv(self, x, w, out, kh, kw, **k2):
@@ -38,14 +40,17 @@ class ProfilingOps(K.CudaOps):
         lab = "+".join(f"{b['kh']}x{b['kw']}d{b.get('dil', (1, 1))[0]}c{b['c']}" for b in branches)
         self._wrap("dwconv_multi", lambda: K.CudaOps.dwconv_multi(self, x, out, branches), f"dwconv_multi {lab} @{x.shape[1]}x{x.shape[2]}")
 
-    def mel_epi_branch(self, x, w, out, klen, dil, slope):
-        self._wrap("mel_epi_branch", lambda: K.CudaOps.mel_epi_branch(self, x, w, out, klen, dil, slope), f"mel_epi_branch c{x.shape[3]} @{x.shape[1]}x{x.shape[2]}")
+    def mel_epi_branch(self, x, w, out, klen, dil, slope, tc=False):
+        self._wrap("mel_epi_branch", lambda: K.CudaOps.mel_epi_branch(self, x, w, out, klen, dil, slope, tc=tc), f"mel_epi_branch{'_tc' if tc else ''} c{x.shape[3]} @{x.shape[1]}x{x.shape[2]}")
 
     def block_mean(self, x, out, bh, bw):
         self._wrap("block_mean", lambda: K.CudaOps.block_mean(self, x, out, bh, bw), f"block_mean {bh}x{bw} c{x.shape[3]} @{x.shape[1]}")
 
-    def sa_modulate(self, *a):
-        self._wrap("sa_modulate", lambda: K.CudaOps.sa_modulate(self, *a), "sa_modulate")
+    def sa_modulate(self, *a, **kw):
+        self._wrap("sa_modulate", lambda: K.CudaOps.sa_modulate(self, *a, **kw), "sa_modulate" + (" + fp16 copy" if kw.get("out16") is not None else ""))
+
+    def to_f16(self, *a):
+        self._wrap("to_f16", lambda: K.CudaOps.to_f16(self, *a), "to_f16")
 
     def scale_add(self, *a):
         self._wrap("scale_add", lambda: K.CudaOps.scale_add(self, *a), f"scale_add c{a[0].shape[3]} @{a[0].shape[1]}")

@@ -210,6 +210,22 @@ class RefOps:
         y = F.leaky_relu(F.conv2d(torch.cat(outs, 1), fu.t().reshape(c, 3 * c, 1, 1)), slope)
         out.copy_(y.permute(0, 2, 3, 1))
 
+    def pooled_mlp(self, x, out, pc1, act1, pc2=None, act2=0, pool=False):
+        n, h, w, c = x.shape
+        t = x.float().reshape(n, h * w, c)
+        if pool:
+            t = t.mean(1, keepdim=True)
+        t = t @ pc1.w_f32.view(pc1.cin, pc1.cout)
+        if pc1.bias is not None:
+            t = t + pc1.bias
+        t = _act(t, act1, 0.0)
+        if pc2 is not None:
+            t = t @ pc2.w_f32.view(pc2.cin, pc2.cout)
+            if pc2.bias is not None:
+                t = t + pc2.bias
+            t = _act(t, act2, 0.0)
+        out.copy_(t.reshape(out.shape))
+
     # -- reductions / gates --------------------------------------------------------------------------
     def block_mean(self, x, out, bh, bw):
         n, h, w, c = x.shape

@@ -243,6 +243,23 @@ def test_block_mean(ops, ref, h, w, c, bh, bw):
     assert (a - b).abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("pool,two", [(True, False), (False, True), (True, True), (False, False)])
+def test_pooled_mlp(ops, ref, pool, two):
+    """the stage gates (pooled, one layer + bias) and the SA modulator's angular MLP (two layers) as one launch each"""
+    n, A, c, hid = 5, 5, 60, 13
+    full = nhwc(n, A, A, 64, seed=1)
+    x = full[..., :c]
+    g = torch.Generator().manual_seed(3)
+    pc1 = K.pack_conv((torch.rand(hid if two else c, c, 1, 1, generator=g) - 0.5) * 0.5,
+                      None if two else torch.rand(c, generator=g) - 0.5, device=DEV)
+    pc2 = K.pack_conv((torch.rand(c, hid, 1, 1, generator=g) - 0.5) * 0.5, None, device=DEV) if two else None
+    shape = (n, 1, 1, c) if pool else (n, A, A, c)
+    a, b = nhwc(*shape, seed=2), nhwc(*shape, seed=2)
+    ops.pooled_mlp(x, a, pc1, N.ACT_RELU if two else N.ACT_SIGMOID, pc2, N.ACT_SIGMOID, pool=pool)
+    ref.pooled_mlp(x, b, pc1, N.ACT_RELU if two else N.ACT_SIGMOID, pc2, N.ACT_SIGMOID, pool=pool)
+    assert (a - b).abs().max().item() <= 2e-6
+
+
 @pytest.mark.parametrize("c,h,w", [(54, 40, 40), (60, 40, 40), (60, 45, 35), (64, 160, 160)])
 def test_sa_modulate(ops, ref, c, h, w):
     n, A = 2, 5
