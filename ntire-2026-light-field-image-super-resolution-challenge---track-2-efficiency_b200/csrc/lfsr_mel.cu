@@ -4,6 +4,7 @@
 //     weights broadcast from shared memory, residual add fused (in place on the interpolation skip).
 //   * mel_epi_branch: the whole MultiScaleEPIBlock (MyEfficientLFNet.py:278-327) in one pass:
 //     dw 1xK / Kx1 / 3x3-dilated -> 1x1 + LReLU each -> concat -> 1x1 + LReLU. One thread per pixel.
+#include <string.h>
 #include "lfsr_common.cuh"
 #include "lfsr_ptx.cuh"
 
@@ -481,6 +482,240 @@ mel_epi_branch_tc_kernel(const EpiArgs a) {
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+
+// ---- fused MultiScaleEPIBlock, depthwise taps AND pointwise contractions on the tensor cores -------------------------
+// dw_b followed by pw_b is linear, so stage 1 of the block is a sum over the 31 taps of
+//     X[pixel + tap shift][c] . (dw_b[tap][c] * pw_b[c][o])
+// i.e. one tcgen05 MMA (M = 128 pixels, N = 32, K = 16 channels) per tap whose A operand is the SAME shared-memory tile read
+// at a shifted row: the input tile with halo is staged once as fp16 pixels of 32 bytes (channels 0..15, K-major
+// SWIZZLE_32B) and a tap shift is just a descriptor start address (the swizzle is a function of the absolute address).
+// MMA rows are consecutive positions of the PADDED tile (pitch P = 32 + 2 halo), so ~25 % of them are halo columns whose
+// results are dropped. Channels 16 and 17 do not fit the K = 16 instruction: their three depthwise sums are computed on
+// the CUDA cores (31 FFMA2 per pixel) and enter stage 1 through one extra K = 16 MMA. Stage 2 (LReLU, fuse 1x1, LReLU) is
+// the same as in mel_epi_branch_tc_kernel. All B operands come pre-swizzled from lfsr_mel_epi_pack (one bulk copy).
+// Per pixel the CUDA cores now do ~90 shared-memory wavefronts instead of ~925; the tensor pipe reads 4 KB per tap and
+// 128-row block.
+namespace em {
+using namespace ptx;
+constexpr int TW = 32;               // output tile width
+constexpr int kTapB = 1024;          // one tap's B operand: [32 out][16 in] fp16, SWIZZLE_32B
+constexpr int kBex = 96 * 32;        // extra-channel B operand: [96 out][16 in]
+constexpr int kB2 = 4096;            // fuse B operand: [32 out][64 in], SWIZZLE_128B
+constexpr int kA2 = 16384;           // stage-2 A block: [128][64] fp16, SWIZZLE_128B
+constexpr int kAex = 4096;           // extra-channel A block: [128][16] fp16, SWIZZLE_32B
+constexpr int kMaxTaps = 40;
+
+// K-major SWIZZLE_32B operand: rows of 32 bytes, 8-row groups 256 bytes apart; any 32-byte aligned start
+__device__ __forceinline__ uint64_t desc32(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)6 << 61);
+}
+// byte address of 16-byte unit u (0/1) of the 32-byte row starting at absolute shared address `row`
+__device__ __forceinline__ uint32_t unit32(uint32_t row, uint32_t u) { return row + ((u ^ ((row >> 7) & 1u)) << 4); }
+
+__host__ __device__ inline int b2_offset(int ntap) { const int o = ntap * kTapB + kBex; return o; }
+__host__ __device__ inline int image_bytes(int ntap) { return ntap * kTapB + kBex + kB2 + ((ntap * 8 + 255) & ~255); }
+}  // namespace em
+
+struct EpiMmaArgs {
+  TView in, out;
+  const uint8_t* packed;     // lfsr_mel_epi_pack image (device)
+  int KL, dil, halo, ntap;
+  int P, G0, R, npx;         // padded pitch, first MMA row (flattened padded position), output rows per tile, staged pixels
+  float slope;
+  int tiles_x, tiles_y;
+};
+
+__global__ void __launch_bounds__(256, 2)
+mel_epi_branch_mma_kernel(const EpiMmaArgs a) {
+  using namespace em;
+  extern __shared__ uint8_t em_raw[];
+  const uint32_t raw = smem_u32(em_raw);
+  uint8_t* smem = em_raw + (((raw + 1023u) & ~1023u) - raw);
+  const int ntap = a.ntap;
+  const int img_bytes = image_bytes(ntap);
+  uint8_t* Bt = smem;                                  // taps | extra | fuse | extra-channel tap weights (float2 per tap)
+  uint8_t* Bex = Bt + ntap * kTapB;
+  uint8_t* B2 = Bt + b2_offset(ntap);
+  const float2* exw = reinterpret_cast<const float2*>(B2 + kB2);
+  uint8_t* T16 = smem + ((img_bytes + 1023) & ~1023);  // [npx][16 fp16]
+  float2* T2 = reinterpret_cast<float2*>(T16 + a.npx * 32);      // [npx] channels 16, 17 (fp32)
+  uint8_t* Aex = reinterpret_cast<uint8_t*>(T2 + a.npx);         // 2 x [128][16 fp16]   (npx is a multiple of 32: 256-byte aligned)
+  uint8_t* A2 = smem + (((uint32_t)(Aex + 2 * kAex - smem) + 1023u) & ~1023u);     // 2 x [128][64 fp16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(A2 + 2 * kA2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  int t_ = blockIdx.x;
+  const int tx0 = (t_ % a.tiles_x) * TW; t_ /= a.tiles_x;
+  const int ty0 = (t_ % a.tiles_y) * a.R;
+  const int img = t_ / a.tiles_y;
+  if (tid == 0) {
+    mbar_init(bars, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 1);
+    fence_barrier_init();
+    mbar_expect_tx(bars + 2, (uint32_t)img_bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(Bt)), "l"(a.packed), "r"((uint32_t)img_bytes), "r"(smem_u32(bars + 2)) : "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+  }
+  // input tile with halo: fp32 pixels of the trunk -> 16 fp16 channels (MMA operand rows) + channels 16, 17 in fp32
+  const int P = a.P, halo = a.halo;
+  const int rows_staged = a.R + 2 * halo;
+  const uint32_t t16 = smem_u32(T16);
+  for (int i = tid; i < a.npx; i += 256) {
+    const int ly = i / P, lx = i - ly * P;
+    const int iy = ty0 - halo + ly, ix = tx0 - halo + lx;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
+    float2 e = make_float2(0.f, 0.f);
+    if (ly < rows_staged && iy >= 0 && iy < a.in.h && ix >= 0 && ix < a.in.w) {
+      const float4* src = reinterpret_cast<const float4*>(a.in.p + a.in.pix(img, iy, ix));
+      v0 = __ldg(src); v1 = __ldg(src + 1); v2 = __ldg(src + 2); v3 = __ldg(src + 3);
+      e = __ldg(reinterpret_cast<const float2*>(src + 4));
+    }
+    const uint32_t row = t16 + (uint32_t)i * 32u;
+    st_shared_v4(unit32(row, 0), pack_f16x2(v0.x, v0.y), pack_f16x2(v0.z, v0.w), pack_f16x2(v1.x, v1.y), pack_f16x2(v1.z, v1.w));
+    st_shared_v4(unit32(row, 1), pack_f16x2(v2.x, v2.y), pack_f16x2(v2.z, v2.w), pack_f16x2(v3.x, v3.y), pack_f16x2(v3.z, v3.w));
+    T2[i] = e;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int half = a.KL / 2;
+  // ---- stage 1, taps: issued by one lane; the other threads meanwhile do channels 16, 17 on the CUDA cores
+  if (warp == 0) {
+    if (tid == 0) {      // always the same lane: tcgen05.commit tracks the MMAs of the committing thread
+      mbar_wait(bars + 2, 0);                          // operand image has landed
+      const uint32_t id1 = make_idesc(0, 32);
+      const uint32_t a0 = t16 + (uint32_t)a.G0 * 32u;
+#pragma unroll 1
+      for (int m = 0; m < 2; ++m) {
+        const uint32_t am = a0 + (uint32_t)m * 128u * 32u;
+#pragma unroll 1
+        for (int t = 0; t < ntap; ++t) {
+          int br, dy = 0, dx = 0, first;
+          if (t < a.KL) { br = 0; dx = t - half; first = t == 0; }
+          else if (t < 2 * a.KL) { br = 1; dy = t - a.KL - half; first = t == a.KL; }
+          else { br = 2; const int k = t - 2 * a.KL; dy = (k / 3 - 1) * a.dil; dx = (k % 3 - 1) * a.dil; first = k == 0; }
+          const uint64_t da = desc32(am + (uint32_t)((dy * P + dx) * 32));
+          const uint64_t db = desc32(smem_u32(Bt) + (uint32_t)t * kTapB);
+          const uint32_t d = tmem + (uint32_t)(m * 96 + br * 32);
+          if (first) umma_f16<0>(d, da, db, id1); else umma_f16<1>(d, da, db, id1);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  const int m_blk = tid >> 7, r_blk = tid & 127;
+  const int g = a.G0 + m_blk * 128 + r_blk;           // flattened padded position of this thread's pixel (= its MMA row)
+  {
+    mbar_wait(bars + 2, 0);                            // exw lives in the operand image
+    f32x2 acc[3];
+    acc[0] = acc[1] = acc[2] = pack2(0.f, 0.f);
+    for (int t = 0; t < ntap; ++t) {
+      int br, dy = 0, dx = 0;
+      if (t < a.KL) { br = 0; dx = t - half; }
+      else if (t < 2 * a.KL) { br = 1; dy = t - a.KL - half; }
+      else { br = 2; const int k = t - 2 * a.KL; dy = (k / 3 - 1) * a.dil; dx = (k % 3 - 1) * a.dil; }
+      const f32x2 v = *reinterpret_cast<const f32x2*>(T2 + g + dy * P + dx);
+      const f32x2 w = *reinterpret_cast<const f32x2*>(exw + t);
+      if (br == 0) acc[0] = fma2(v, w, acc[0]);
+      else if (br == 1) acc[1] = fma2(v, w, acc[1]);
+      else acc[2] = fma2(v, w, acc[2]);
+    }
+    float x0, x1, x2, x3, x4, x5;
+    unpack2(acc[0], x0, x1); unpack2(acc[1], x2, x3); unpack2(acc[2], x4, x5);
+    const uint32_t row = smem_u32(Aex) + (uint32_t)m_blk * kAex + (uint32_t)r_blk * 32u;
+    st_shared_v4(unit32(row, 0), pack_f16x2(x0, x1), pack_f16x2(x2, x3), pack_f16x2(x4, x5), 0u);
+    st_shared_v4(unit32(row, 1), 0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    if (tid == 0) {      // always the same lane: tcgen05.commit tracks the MMAs of the committing thread
+      tc_fence_after();
+      const uint32_t idx = make_idesc(0, 96);
+      const uint64_t db = desc32(smem_u32(Bex));
+#pragma unroll
+      for (int m = 0; m < 2; ++m) umma_f16<1>(tmem + (uint32_t)(m * 96), desc32(smem_u32(Aex) + (uint32_t)m * kAex), db, idx);
+      umma_commit(bars);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bars, 0);
+  tc_fence_after();
+  // ---- stage 2: LReLU, fp16, fuse GEMM
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)m_blk * 96u;
+  const uint32_t a2_row = smem_u32(A2) + (uint32_t)m_blk * kA2 + (uint32_t)r_blk * 128u;
+  const uint32_t swz = (uint32_t)r_blk & 7u;
+  {
+    uint32_t pk[32];
+#pragma unroll
+    for (int i = 27; i < 32; ++i) pk[i] = 0u;
+#pragma unroll
+    for (int br = 0; br < 3; ++br) {
+      float s[32];
+      tmem_ld32(tlane + br * 32, s);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        float x0 = s[2 * i], x1 = s[2 * i + 1];
+        x0 = x0 > 0.f ? x0 : x0 * a.slope;
+        x1 = x1 > 0.f ? x1 : x1 * a.slope;
+        pk[br * 9 + i] = pack_f16x2(x0, x1);
+      }
+    }
+    et::store_row(a2_row, swz, pk);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    if (tid == 0) {      // always the same lane: tcgen05.commit tracks the MMAs of the committing thread
+      tc_fence_after();
+      const uint32_t id2 = make_idesc(0, 32);
+      const uint64_t db = make_smem_desc(smem_u32(B2));
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const uint64_t da = make_smem_desc(smem_u32(A2) + m * kA2);
+        umma_f16<0>(tmem + m * 96, da, db, id2);
+        umma_f16<1>(tmem + m * 96, da + 2, db + 2, id2);
+        umma_f16<1>(tmem + m * 96, da + 4, db + 4, id2);
+        umma_f16<1>(tmem + m * 96, da + 6, db + 6, id2);
+      }
+      umma_commit(bars + 1);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bars + 1, 0);
+  tc_fence_after();
+  {
+    float o[32];
+    tmem_ld32(tlane, o);
+    tmem_wait_ld();
+    const int gy = g / P, gx = g - gy * P;
+    const int ty = gy - halo, tx = gx - halo;
+    const int oy = ty0 + ty, ox = tx0 + tx;
+    if (tx >= 0 && tx < TW && ty >= 0 && ty < a.R && ox < a.in.w && oy < a.in.h) {
+      float* dst = a.out.p + a.out.pix(img, oy, ox);
+#pragma unroll
+      for (int i = 0; i < EC / 2; ++i) {
+        float x0 = o[2 * i], x1 = o[2 * i + 1];
+        x0 = x0 > 0.f ? x0 : x0 * a.slope;
+        x1 = x1 > 0.f ? x1 : x1 * a.slope;
+        reinterpret_cast<float2*>(dst)[i] = make_float2(x0, x1);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 }  // namespace lfsr
 
 using namespace lfsr;
@@ -593,4 +828,99 @@ extern "C" int lfsr_mel_epi_branch_tc(const lfsr_tensor* in, const float* w_pack
   }
   mel_epi_branch_tc_kernel<<<in->n * a.tiles_x * a.tiles_y, 256, smem, (cudaStream_t)stream>>>(a);
   return check_launch("mel_epi_branch_tc_kernel");
+}
+
+// ---- operand image of the all-tensor-core EPI kernel (host side) ----------------------------------------------------
+static uint16_t f32_to_f16_bits(float f) {       // round to nearest even, saturating to the finite range, denormals kept
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  x &= 0x7fffffffu;
+  if (x >= 0x7f800000u) return (uint16_t)(sign | (x > 0x7f800000u ? 0x7e00u : 0x7bffu));
+  if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);
+  if (x < 0x38800000u) {                          // subnormal half
+    if (x < 0x33000000u) return (uint16_t)sign;
+    const int e = (int)(x >> 23);
+    uint32_t m = (x & 0x7fffffu) | 0x800000u;
+    const int shift = 126 - e;                    // 14 .. 24
+    const uint32_t r = m >> shift, rem = m & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+    return (uint16_t)(sign | (r + ((rem > halfway || (rem == halfway && (r & 1))) ? 1 : 0)));
+  }
+  const uint32_t r = x - 0x38000000u;
+  const uint32_t rem = r & 0x1fffu;
+  uint32_t h = r >> 13;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) ++h;
+  return (uint16_t)(sign | h);
+}
+
+extern "C" size_t lfsr_mel_epi_pack_bytes(int klen) {
+  if (klen <= 0 || !(klen & 1) || 2 * klen + 9 > em::kMaxTaps) return 0;
+  return (size_t)em::image_bytes(2 * klen + 9);
+}
+
+extern "C" int lfsr_mel_epi_pack(const float* w, void* out, int klen) {
+  LFSR_REQUIRE(w && out && lfsr_mel_epi_pack_bytes(klen) > 0, "lfsr_mel_epi_pack: bad arguments (klen must be odd, 2 klen + 9 <= %d)", em::kMaxTaps);
+  const int ntap = 2 * klen + 9;
+  uint8_t* img = (uint8_t*)out;
+  memset(img, 0, lfsr_mel_epi_pack_bytes(klen));
+  const float* dw = w;                              // [ntap][EC]: dw_h | dw_v | dw_d
+  const float* pw = w + ntap * EC;                  // 3 x [EC in][EC out]
+  const float* fu = pw + 3 * EC * EC;               // [3*EC in][EC out]
+  auto put32 = [](uint8_t* blk, int n, int k, float v) {       // [rows][16] fp16, SWIZZLE_32B (block 256-byte aligned)
+    const uint32_t row = (uint32_t)n * 32u;
+    const uint32_t off = row + ((((uint32_t)k >> 3) ^ ((row >> 7) & 1u)) << 4) + ((uint32_t)k & 7u) * 2u;
+    const uint16_t h = f32_to_f16_bits(v);
+    memcpy(blk + off, &h, 2);
+  };
+  for (int t = 0; t < ntap; ++t) {
+    const int br = t < klen ? 0 : (t < 2 * klen ? 1 : 2);
+    uint8_t* blk = img + (size_t)t * em::kTapB;
+    for (int o = 0; o < EC; ++o)
+      for (int c = 0; c < 16; ++c) put32(blk, o, c, dw[t * EC + c] * pw[br * EC * EC + c * EC + o]);
+  }
+  uint8_t* bex = img + (size_t)ntap * em::kTapB;
+  for (int br = 0; br < 3; ++br)
+    for (int o = 0; o < EC; ++o)
+      for (int j = 0; j < 2; ++j) put32(bex, 32 * br + o, 2 * br + j, pw[br * EC * EC + (16 + j) * EC + o]);
+  uint8_t* b2 = img + em::b2_offset(ntap);
+  for (int n = 0; n < EC; ++n)
+    for (int k = 0; k < 3 * EC; ++k) {                // [32 out][64 in] fp16, SWIZZLE_128B
+      const uint32_t off = (uint32_t)n * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)n & 7u)) << 4) + ((uint32_t)k & 7u) * 2u;
+      const uint16_t h = f32_to_f16_bits(fu[k * EC + n]);
+      memcpy(b2 + off, &h, 2);
+    }
+  float* exw = (float*)(b2 + em::kB2);
+  for (int t = 0; t < ntap; ++t) { exw[2 * t] = dw[t * EC + 16]; exw[2 * t + 1] = dw[t * EC + 17]; }
+  return LFSR_OK;
+}
+
+extern "C" int lfsr_mel_epi_branch_mma(const lfsr_tensor* in, const void* packed, const lfsr_tensor* out, int klen, int dil,
+                                       float slope, void* stream) {
+  LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && packed, "lfsr_mel_epi_branch_mma: null/invalid tensor");
+  LFSR_REQUIRE(in->c == EC && out->c == EC, "lfsr_mel_epi_branch_mma: built for %d-channel EPI splits, got %d", EC, in->c);
+  LFSR_REQUIRE(in->n == out->n && in->h == out->h && in->w == out->w, "lfsr_mel_epi_branch_mma: shape mismatch");
+  LFSR_REQUIRE(lfsr_mel_epi_pack_bytes(klen) > 0 && dil > 0, "lfsr_mel_epi_branch_mma: bad kernel length");
+  LFSR_REQUIRE(in->ld % 4 == 0 && in->ld >= EC + 2 && ((uintptr_t)in->ptr & 15) == 0 && ((uintptr_t)packed & 15) == 0,
+               "lfsr_mel_epi_branch_mma: input slice must be 16-byte aligned with 2 readable pad floats (grouped trunk layout)");
+  LFSR_REQUIRE(out->ld % 2 == 0 && ((uintptr_t)out->ptr & 7) == 0, "lfsr_mel_epi_branch_mma: 8-byte aligned output slice required");
+  EpiMmaArgs a;
+  a.in = view_of(in); a.out = view_of(out); a.packed = (const uint8_t*)packed; a.KL = klen; a.dil = dil; a.slope = slope;
+  a.halo = klen / 2 > dil ? klen / 2 : dil;
+  a.ntap = 2 * klen + 9;
+  a.P = em::TW + 2 * a.halo;
+  a.G0 = a.halo * a.P + a.halo;
+  a.R = (256 - em::TW) / a.P + 1;                    // output rows whose 32 pixels all lie inside the 256 MMA rows
+  LFSR_REQUIRE(a.R >= 1, "lfsr_mel_epi_branch_mma: halo too large");
+  a.npx = (2 * a.G0 + 256 + 31) & ~31;               // last MMA row + largest shift, rounded up
+  a.tiles_x = ceil_div(in->w, em::TW); a.tiles_y = ceil_div(in->h, a.R);
+  const size_t img_b = ((size_t)em::image_bytes(a.ntap) + 1023) & ~(size_t)1023;
+  const size_t smem = 1024 + img_b + (((size_t)a.npx * 40 + 2 * em::kAex + 1023) & ~(size_t)1023) + 2 * em::kA2 + 64;
+  LFSR_REQUIRE(smem <= 113 * 1024, "lfsr_mel_epi_branch_mma: kernel length / dilation too large for the staged tile");
+  static DevOnce once;
+  if (once.need()) {
+    if (opt_in_smem(mel_epi_branch_mma_kernel, 113 * 1024, "lfsr_mel_epi_branch_mma")) return LFSR_ERR_CUDA;
+    once.done();
+  }
+  mel_epi_branch_mma_kernel<<<in->n * a.tiles_x * a.tiles_y, 256, smem, (cudaStream_t)stream>>>(a);
+  return check_launch("mel_epi_branch_mma_kernel");
 }

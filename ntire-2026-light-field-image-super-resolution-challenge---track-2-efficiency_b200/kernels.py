@@ -331,6 +331,20 @@ class CudaOps:
         N.check(fn(C.byref(as_tensor(x, "epi.in")), w_packed.data_ptr(), C.byref(as_tensor(out, "epi.out")), klen, dil, slope,
                    self._stream(x)), "lfsr_mel_epi_branch")
 
+    def mel_epi_pack(self, w_packed: torch.Tensor, klen: int, device) -> Optional[torch.Tensor]:
+        """operand image of lfsr_mel_epi_branch_mma for the packed EPI-block weights (None: kernel length not supported)"""
+        nbytes = self.lib.lfsr_mel_epi_pack_bytes(klen)
+        if not (self.use_tc and nbytes):
+            return None
+        w = w_packed.detach().to("cpu", torch.float32).contiguous()
+        img = torch.zeros(nbytes, dtype=torch.uint8)
+        N.check(self.lib.lfsr_mel_epi_pack(w.data_ptr(), img.data_ptr(), klen), "lfsr_mel_epi_pack")
+        return img.to(device)
+
+    def mel_epi_branch_mma(self, x, image, out, klen, dil, slope):
+        N.check(self.lib.lfsr_mel_epi_branch_mma(C.byref(as_tensor(x, "epi.in")), image.data_ptr(), C.byref(as_tensor(out, "epi.out")),
+                                                 klen, dil, slope, self._stream(x)), "lfsr_mel_epi_branch_mma")
+
     # -- reductions / gates -------------------------------------------------------------------------
     def block_mean(self, x, out, bh, bw):
         N.check(self.lib.lfsr_block_mean(C.byref(as_tensor(x, "block_mean.in")), C.byref(as_tensor(out, "block_mean.out")),

@@ -225,6 +225,8 @@ class get_model(LFNetBase):
                                     pw_t(eb.epi_h["1"]), pw_t(eb.epi_v["1"]), pw_t(eb.epi_diag["1"]),
                                     pw_t(eb.fuse["0"])]).to(device)
             s["epi_klen"] = eb.epi_h["0"].weight.shape[-1]
+            # fp16 operand plan: pre-swizzled tensor-core operands of the all-MMA EPI kernel (None: not available)
+            s["epi_img"] = ops.mel_epi_pack(s["epi_w"], s["epi_klen"], device) if (f16 and hasattr(ops, "mel_epi_pack")) else None
             # three gate FCs as one block-diagonal 1x1 over the grouped layout (MyEfficientLFNet.py:159-173)
             sp, gs = self._groups()
             CP = gs * len(sp)
@@ -338,7 +340,10 @@ class get_model(LFNetBase):
                 ops.conv(ang5[..., 0:c0], st["ang_ex"], cat[..., gs:2 * gs], act=LR, slope=0.1, alpha=st["ang_scale"],
                          res=feat[..., gs:2 * gs], shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
             # EPI branch: three depthwise+pointwise paths and their fuse conv in one kernel
-            ops.mel_epi_branch(xe, st["epi_w"], cat[..., sl[2]], st["epi_klen"], A, 0.1, tc=bool(f16))
+            if st.get("epi_img") is not None:
+                ops.mel_epi_branch_mma(xe, st["epi_img"], cat[..., sl[2]], st["epi_klen"], A, 0.1)
+            else:
+                ops.mel_epi_branch(xe, st["epi_w"], cat[..., sl[2]], st["epi_klen"], A, 0.1, tc=bool(f16))
             fork.join()
             # gates -> per-sample channel scale of the fusion 1x1
             ops.block_mean(cat, vmean, hA, wA)

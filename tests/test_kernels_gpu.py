@@ -721,6 +721,26 @@ def test_mel_epi_branch_tc(ops, ref, n, h, w):
     assert torch.equal(a_full[..., 58:], b_full[..., 58:]) and torch.equal(a_full[..., :40], b_full[..., :40])
 
 
+@pytest.mark.parametrize("n,h,w", [(2, 40, 40), (3, 37, 70), (64, 160, 160)])
+def test_mel_epi_branch_mma(ops, ref, n, h, w):
+    """the block with the depthwise taps as shifted-row tcgen05 MMAs (pre-swizzled operand image) vs the fp32 formulation"""
+    c, klen, A = 18, 11, 5
+    full = nhwc(n, h, w, 60, seed=1)
+    x = full[..., 40:58]
+    wts = rnd((2 * klen + 9) * c + 6 * c * c, seed=2) * 0.3
+    a_full, b_full = nhwc(n, h, w, 60, seed=3), nhwc(n, h, w, 60, seed=3)
+    tc_ops = K.CudaOps(use_tc=True)
+    img = tc_ops.mel_epi_pack(wts, klen, DEV)
+    assert img is not None and img.numel() == tc_ops.lib.lfsr_mel_epi_pack_bytes(klen)
+    tc_ops.mel_epi_branch_mma(x, img, a_full[..., 40:58], klen, A, 0.1)
+    ops.mel_epi_branch(x, wts, b_full[..., 40:58], klen, A, 0.1) if n > 8 else ref.mel_epi_branch(x, wts, b_full[..., 40:58], klen, A, 0.1)
+    scale = max(1.0, b_full[..., 40:58].abs().max().item())
+    err = (a_full - b_full).abs().max().item()
+    print(f"mel_epi_branch_mma {n}x{h}x{w}: max err {err:.3e} (ref max {scale:.3f})")
+    assert 0.0 < err <= 2e-3 * scale, err
+    assert torch.equal(a_full[..., 58:], b_full[..., 58:]) and torch.equal(a_full[..., :40], b_full[..., :40])
+
+
 @pytest.mark.parametrize("cin,cout,k,dil", [(54, 1, 3, 1), (64, 1, 3, 1), (64, 3, 3, 5), (18, 2, 1, 1), (60, 4, 3, 1)])
 def test_conv_small_cout(ops, ref, cin, cout, k, dil):
     n, h, w = 2, 50, 70
