@@ -75,6 +75,7 @@ struct DwParams {
   // x tile+halo, out-of-image elements zero filled) instead of ~25 cp.async per thread: staging cost as many
   // instructions as the stencil itself and the kernel is issue-bound at its low (shared-memory limited) occupancy
   int use_tma, tile_floats;
+  int res_tma;                 // sa_tile_kernel: the residual tile is fetched through tm[1] next to the input tile
   // share: all branches read the same channel window (FastConvSSM's four dilations of one tensor): a CTA stages ONE tile
   // with the largest halo (branch share_b) and runs every branch on it; grid.y then enumerates channel chunks only
   int share, share_b;
@@ -358,7 +359,7 @@ sa_tile_kernel(const __grid_constant__ DwParams p) {
   extern __shared__ __align__(16) float dw_smem[];
   const int tid = threadIdx.x;
   const DwBranch& B = p.br[0];
-  const int wofs = (int)blockIdx.y * DW_CH;
+  const int wofs = (int)blockIdx.y * DW_CH;      // (channel chunk as the FASTEST grid index was tried: 0.332 vs 0.320 ms)
   const int cin0 = B.in_c0 + wofs, cout0 = B.out_c0 + wofs;
   const int d = B.dh;
   const int SH = DW_TH + 2 * d, SW = DW_TW + 2 * d;
@@ -366,16 +367,22 @@ sa_tile_kernel(const __grid_constant__ DwParams p) {
   const int tyi = blockIdx.x / p.tiles_x;
   const int ty0 = tyi * DW_TH, tx0 = (blockIdx.x - tyi * p.tiles_x) * DW_TW;
   float* tS = dw_smem + ((128u - (dw_smem_u32(dw_smem) & 127u)) & 127u) / 4;
-  float* wS = tS + p.tile_floats;
+  float* wS = tS + p.tile_floats + (p.res_tma ? DW_TH * DW_TW * DW_CH : 0);
   __shared__ uint64_t bar;
   const int H = p.in.h, W = p.in.w;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dw_smem_u32(&bar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dw_smem_u32(&bar)), "r"(SH * SW * DW_CH * 4) : "memory");
+    const int res_bytes = p.res_tma ? DW_TH * DW_TW * DW_CH * 4 : 0;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dw_smem_u32(&bar)), "r"(SH * SW * DW_CH * 4 + res_bytes) : "memory");
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dw_smem_u32(tS)), "l"(&p.tm[0]), "r"(dw_smem_u32(&bar)), "r"(cin0), "r"(tx0 - d), "r"(ty0 - d), "r"(img)
                  : "memory");
+    // the residual tile rides on the same barrier: no residual load (and no DRAM round trip) is left in the row loop
+    if (p.res_tma)
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                   ::"r"(dw_smem_u32(tS + p.tile_floats)), "l"(&p.tm[1]), "r"(dw_smem_u32(&bar)), "r"(cout0), "r"(tx0), "r"(ty0), "r"(img)
+                   : "memory");
   }
   // thread = one channel PAIR of one pixel column, every second row of the tile: the nine tap pairs then fit in registers
   // (18) at two 512-thread CTAs per SM, so the only shared-memory reads of the row loop are the nine tile taps. (With
@@ -390,7 +397,7 @@ sa_tile_kernel(const __grid_constant__ DwParams p) {
   float* outI = p.out.p + (size_t)img * p.out.h * p.out.w * p.out.ld;
   const float* amI = p.amod.p + (size_t)img * p.amod.h * p.amod.w * p.amod.ld;
   const int rows_here = min(DW_TH, H - ty0);
-  if (live && resI && !(q & 3)) {                      // one request per 32-byte sector
+  if (live && resI && !p.res_tma && !(q & 3)) {        // one request per 32-byte sector
 #pragma unroll
     for (int r = ly0; r < DW_TH; r += 2)
       if (r < rows_here) asm volatile("prefetch.global.L2 [%0];" ::"l"(resI + ((ty0 + r) * p.res.w + ox) * p.res.ld + c2));
@@ -423,16 +430,20 @@ sa_tile_kernel(const __grid_constant__ DwParams p) {
   const float* base = tS + ly0 * row_f + lx * DW_CH + q * 2;
   // view row of the current output row, stepped without a division per row
   int ay = (ty0 + ly0) / vh, arem = (ty0 + ly0) - ay * vh;
+  const float* resS = tS + p.tile_floats + (ly0 * DW_TW + lx) * DW_CH + q * 2;      // staged residual tile [16][32][16]
+  const bool res_g = resI && !p.res_tma;
   float2 rn = make_float2(0.f, 0.f), an = make_float2(0.f, 0.f);
   if (ly0 < rows_here) {
-    if (resI) rn = *reinterpret_cast<const float2*>(resI + res_o);
+    if (res_g) rn = *reinterpret_cast<const float2*>(resI + res_o);
     an = __ldg(reinterpret_cast<const float2*>(amI + ay * am_row + am_x));
   }
 #pragma unroll 1
   for (int r = ly0; r < rows_here; r += 2) {
-    const float2 rc = rn, ac = an;
+    float2 rc = rn;
+    const float2 ac = an;
+    if (p.res_tma) rc = *reinterpret_cast<const float2*>(resS + (r - ly0) * DW_TW * DW_CH);
     if (r + 2 < rows_here) {                 // next row's residual and modulation: in flight across this row's arithmetic
-      if (resI) rn = *reinterpret_cast<const float2*>(resI + res_o + res_step);
+      if (res_g) rn = *reinterpret_cast<const float2*>(resI + res_o + res_step);
       arem += 2;
       while (arem >= vh) { arem -= vh; ++ay; }
       an = __ldg(reinterpret_cast<const float2*>(amI + ay * am_row + am_x));
@@ -548,7 +559,7 @@ static int dw_launch(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_d
     if (tf > tile_floats) tile_floats = tf;
     if (b.kh * b.kw * DW_CH > w_floats) w_floats = b.kh * b.kw * DW_CH;
   }
-  p.share = 0; p.share_b = 0;
+  p.share = 0; p.share_b = 0; p.res_tma = 0;
   if (!sa && nbr > 1 && !dbg_env("LFSR_DW_NO_SHARE")) {
     bool same = true;
     size_t best = 0;
@@ -600,12 +611,26 @@ static int dw_launch(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_d
   if (sa && p.use_tma && nbr == 1 && br[0].kh == 3 && br[0].kw == 3 && br[0].dil_h == br[0].dil_w && br[0].scale &&
       br[0].act == LFSR_ACT_SIGMOID && in->h % p.amod.h == 0 && in->w % p.amod.w == 0 &&
       (!p.res.p || (p.res.h == in->h && p.res.w == in->w))) {
+    size_t smem_sa = smem;
+    if (p.res.p && smem + DW_TH * DW_TW * DW_CH * 4 <= 110 * 1024) {        // residual tile by TMA (still two CTAs per SM)
+      const lfsr_tensor* rt = sa->res;
+      const cuuint64_t ld_b = (cuuint64_t)rt->ld * 4;
+      cuuint64_t dims[4] = {(cuuint64_t)rt->c, (cuuint64_t)rt->w, (cuuint64_t)rt->h, (cuuint64_t)rt->n};
+      cuuint64_t strides[3] = {ld_b, ld_b * rt->w, ld_b * rt->w * rt->h};
+      cuuint32_t box[4] = {(cuuint32_t)DW_CH, (cuuint32_t)DW_TW, (cuuint32_t)DW_TH, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      if (encode(&p.tm[1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rt->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+        p.res_tma = 1;
+        smem_sa += DW_TH * DW_TW * DW_CH * 4;
+      }
+    }
     static DevOnce once_sa;
     if (once_sa.need()) {
       if (opt_in_smem(sa_tile_kernel, 200 * 1024 + 4096, "lfsr_sa_modulate")) return LFSR_ERR_CUDA;
       once_sa.done();
     }
-    sa_tile_kernel<<<grid, SA_THREADS, smem, st>>>(p);
+    sa_tile_kernel<<<grid, SA_THREADS, smem_sa, st>>>(p);
     return check_launch("sa_tile_kernel");
   }
   if (p.share) dw_tile_kernel<true><<<grid, 256, smem, st>>>(p);

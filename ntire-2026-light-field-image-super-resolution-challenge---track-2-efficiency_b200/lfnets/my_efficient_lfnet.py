@@ -21,12 +21,17 @@ torch.cat / torch.split never materialise: branches read and write channel slice
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
 from .. import _native as N
 from .. import kernels as K
 from .common import LFNetBase, bn_affine, slots, tail_table, upsample_tail, SideStream, fp16_plan
+
+
+USE_EPI_MMA = os.environ.get("LFSR_EPI_MMA", "0") == "1"
 
 
 def _conv(cin, cout, k, **kw):
@@ -226,7 +231,9 @@ class get_model(LFNetBase):
                                     pw_t(eb.fuse["0"])]).to(device)
             s["epi_klen"] = eb.epi_h["0"].weight.shape[-1]
             # fp16 operand plan: pre-swizzled tensor-core operands of the all-MMA EPI kernel (None: not available)
-            s["epi_img"] = ops.mel_epi_pack(s["epi_w"], s["epi_klen"], device) if (f16 and hasattr(ops, "mel_epi_pack")) else None
+            # (measured slower than the hybrid kernel - 0.48 vs 0.34 ms at batch 64 - so it is opt-in: LFSR_EPI_MMA=1)
+            s["epi_img"] = (ops.mel_epi_pack(s["epi_w"], s["epi_klen"], device)
+                            if (f16 and USE_EPI_MMA and hasattr(ops, "mel_epi_pack")) else None)
             # three gate FCs as one block-diagonal 1x1 over the grouped layout (MyEfficientLFNet.py:159-173)
             sp, gs = self._groups()
             CP = gs * len(sp)
