@@ -202,12 +202,13 @@ int lfsr_mel_epi_branch_tc(const lfsr_tensor* in, const float* w_packed, const l
                            float slope, void* stream);
 /* The same block with the depthwise taps on the tensor cores as well: dw_b . pw_b is one tcgen05 MMA per tap whose A operand is
  * the fp16 input tile read at a shifted row (channels 0..15; channels 16, 17 go through the CUDA cores and one extra MMA).
+ * `in16` is the fp16 copy of `in` (ptr = __half*, >= 16 channels) the producer of `in` wrote next to it: the tile is one TMA load.
  * lfsr_mel_epi_pack (host) turns w_packed into the pre-swizzled operand image the kernel loads with one bulk copy;
  * lfsr_mel_epi_pack_bytes is its size (0: this kernel length is not supported, use lfsr_mel_epi_branch_tc). */
 size_t lfsr_mel_epi_pack_bytes(int klen);
 int lfsr_mel_epi_pack(const float* w_packed_host, void* image_host, int klen);
-int lfsr_mel_epi_branch_mma(const lfsr_tensor* in, const void* image_dev, const lfsr_tensor* out, int klen, int dil, float slope,
-                            void* stream);
+int lfsr_mel_epi_branch_mma(const lfsr_tensor* in, const lfsr_tensor* in16, const void* image_dev, const lfsr_tensor* out, int klen,
+                            int dil, float slope, void* stream);
 /* TF32 tcgen05/TMEM implicit GEMM fed by TMA (sm_100a); weights packed by lfsr_pack_conv_tc.
  * Supports stride 1 (any dilation, "same" zero padding given by pad) and kh*kw <= 25. */
 size_t lfsr_conv2d_tc_packed_floats(int kh, int kw, int cin, int cout);

@@ -105,7 +105,7 @@ SIGNATURES = {
     "lfsr_mel_epi_branch_tc": (_I, [_TP, _P, _TP, _I, _I, C.c_float, _P]),
     "lfsr_mel_epi_pack_bytes": (C.c_size_t, [_I]),
     "lfsr_mel_epi_pack": (_I, [_P, _P, _I]),
-    "lfsr_mel_epi_branch_mma": (_I, [_TP, _P, _TP, _I, _I, C.c_float, _P]),
+    "lfsr_mel_epi_branch_mma": (_I, [_TP, _TP, _P, _TP, _I, _I, C.c_float, _P]),
     "lfsr_conv2d_tc_packed_floats": (C.c_size_t, [_I, _I, _I, _I]),
     "lfsr_pack_conv_tc": (_I, [_P, _P, _I, _I, _I, _I]),
     "lfsr_to_f16": (_I, [_TP, _TP, _P]),

@@ -4,7 +4,9 @@
 //     weights broadcast from shared memory, residual add fused (in place on the interpolation skip).
 //   * mel_epi_branch: the whole MultiScaleEPIBlock (MyEfficientLFNet.py:278-327) in one pass:
 //     dw 1xK / Kx1 / 3x3-dilated -> 1x1 + LReLU each -> concat -> 1x1 + LReLU. One thread per pixel.
+#include <cuda.h>
 #include <string.h>
+#include <mutex>
 #include "lfsr_common.cuh"
 #include "lfsr_ptx.cuh"
 
@@ -526,8 +528,20 @@ struct EpiMmaArgs {
   int tiles_x, tiles_y;
 };
 
-__global__ void __launch_bounds__(256, 2)
-mel_epi_branch_mma_kernel(const EpiMmaArgs a) {
+// 9 warps: 0..7 = workers (thread t <-> MMA row t & 127 of block t >> 7), 8 = MMA issuer. The issuer runs its whole program
+// inside ONE elect block (tcgen05 instructions issued from `if (lane == 0)` are wrapped in ELECT/branch loops by ptxas, and
+// tcgen05.commit only tracks the MMAs of the committing thread); hand-offs are mbarriers, never __syncthreads.
+#ifdef LFSR_DEBUG_HOOKS
+__device__ long long* g_em_dbg = nullptr;        // probe build: per-CTA phase time stamps (profiles/probe_epi_phases.py)
+#define EM_STAMP(slot) do { if (g_em_dbg && blockIdx.x < 4096) g_em_dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+#else
+#define EM_STAMP(slot) do { } while (0)
+#endif
+constexpr int kEmThreads = 288;
+enum EmBar { EB_IMG = 0, EB_X, EB_IN, EB_D1, EB_A2 = EB_D1 + 2, EB_D2 = EB_A2 + 2, EB_COUNT = EB_D2 + 2 };
+
+__global__ void __launch_bounds__(384, 2)      // (9 warps are allocated registers like 12: cap at 80 so two CTAs fit)
+mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const EpiMmaArgs a) {
   using namespace em;
   extern __shared__ uint8_t em_raw[];
   const uint32_t raw = smem_u32(em_raw);
@@ -543,177 +557,208 @@ mel_epi_branch_mma_kernel(const EpiMmaArgs a) {
   uint8_t* Aex = reinterpret_cast<uint8_t*>(T2 + a.npx);         // 2 x [128][16 fp16]   (npx is a multiple of 32: 256-byte aligned)
   uint8_t* A2 = smem + (((uint32_t)(Aex + 2 * kAex - smem) + 1023u) & ~1023u);     // 2 x [128][64 fp16]
   uint64_t* bars = reinterpret_cast<uint64_t*>(A2 + 2 * kA2);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + EB_COUNT);
+  int* tapoff = reinterpret_cast<int*>(tmem_slot + 1);           // byte shift of the A view per tap
+  uint64_t* adesc = reinterpret_cast<uint64_t*>(bars + 32);      // [2][kMaxTaps] A descriptors of the tap MMAs (precomputed: the
+                                                                 // issuing lane retires ~1 dependent instruction per 5 cycles)
   const int tid = threadIdx.x, warp = tid >> 5;
   int t_ = blockIdx.x;
   const int tx0 = (t_ % a.tiles_x) * TW; t_ /= a.tiles_x;
   const int ty0 = (t_ % a.tiles_y) * a.R;
   const int img = t_ / a.tiles_y;
+  const int P = a.P, halo = a.halo, half = a.KL / 2;
   if (tid == 0) {
-    mbar_init(bars, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 1);
+    EM_STAMP(0);
+    mbar_init(bars + EB_IMG, 1);
+    mbar_init(bars + EB_X, 1);
+    mbar_init(bars + EB_IN, 256);
+    for (int m = 0; m < 2; ++m) { mbar_init(bars + EB_D1 + m, 1); mbar_init(bars + EB_A2 + m, 128); mbar_init(bars + EB_D2 + m, 1); }
     fence_barrier_init();
-    mbar_expect_tx(bars + 2, (uint32_t)img_bytes);
+    mbar_expect_tx(bars + EB_IMG, (uint32_t)img_bytes);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(Bt)), "l"(a.packed), "r"((uint32_t)img_bytes), "r"(smem_u32(bars + 2)) : "memory");
+                 ::"r"(smem_u32(Bt)), "l"(a.packed), "r"((uint32_t)img_bytes), "r"(smem_u32(bars + EB_IMG)) : "memory");
+    // the fp16 input tile with halo: channels 0..15 of the (R + 2 halo) x P pixels, one tensor load, out-of-image pixels
+    // zero filled (= the depthwise convs' padding), 32-byte pixel rows swizzled as the MMA descriptors expect
+    mbar_expect_tx(bars + EB_X, (uint32_t)((a.R + 2 * halo) * P * 32));
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(T16)), "l"(&tmX), "r"(smem_u32(bars + EB_X)), "r"(0), "r"(tx0 - halo), "r"(ty0 - halo), "r"(img)
+                 : "memory");
   }
-  if (warp == 0) {
-    __syncwarp();
-    tmem_alloc(tmem_slot, 256);
+  if (tid < ntap) {
+    int dy = 0, dx = 0;
+    if (tid < a.KL) dx = tid - half;
+    else if (tid < 2 * a.KL) dy = tid - a.KL - half;
+    else { const int k = tid - 2 * a.KL; dy = (k / 3 - 1) * a.dil; dx = (k % 3 - 1) * a.dil; }
+    tapoff[tid] = (dy * P + dx) * 32;
+    const uint32_t a0 = smem_u32(T16) + (uint32_t)a.G0 * 32u + (uint32_t)((dy * P + dx) * 32);
+    adesc[tid] = desc32(a0);
+    adesc[kMaxTaps + tid] = desc32(a0 + 128u * 32u);
   }
-  // input tile with halo: fp32 pixels of the trunk -> 16 fp16 channels (MMA operand rows) + channels 16, 17 in fp32
-  const int P = a.P, halo = a.halo;
-  const int rows_staged = a.R + 2 * halo;
-  const uint32_t t16 = smem_u32(T16);
-  for (int i = tid; i < a.npx; i += 256) {
-    const int ly = i / P, lx = i - ly * P;
-    const int iy = ty0 - halo + ly, ix = tx0 - halo + lx;
-    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
-    float2 e = make_float2(0.f, 0.f);
-    if (ly < rows_staged && iy >= 0 && iy < a.in.h && ix >= 0 && ix < a.in.w) {
-      const float4* src = reinterpret_cast<const float4*>(a.in.p + a.in.pix(img, iy, ix));
-      v0 = __ldg(src); v1 = __ldg(src + 1); v2 = __ldg(src + 2); v3 = __ldg(src + 3);
-      e = __ldg(reinterpret_cast<const float2*>(src + 4));
-    }
-    const uint32_t row = t16 + (uint32_t)i * 32u;
-    st_shared_v4(unit32(row, 0), pack_f16x2(v0.x, v0.y), pack_f16x2(v0.z, v0.w), pack_f16x2(v1.x, v1.y), pack_f16x2(v1.z, v1.w));
-    st_shared_v4(unit32(row, 1), pack_f16x2(v2.x, v2.y), pack_f16x2(v2.z, v2.w), pack_f16x2(v3.x, v3.y), pack_f16x2(v3.z, v3.w));
-    T2[i] = e;
-  }
-  fence_proxy_async();
+  if (warp == 8) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int half = a.KL / 2;
-  // ---- stage 1, taps: issued by one lane; the other threads meanwhile do channels 16, 17 on the CUDA cores
-  if (warp == 0) {
-    if (tid == 0) {      // always the same lane: tcgen05.commit tracks the MMAs of the committing thread
-      mbar_wait(bars + 2, 0);                          // operand image has landed
-      const uint32_t id1 = make_idesc(0, 32);
-      const uint32_t a0 = t16 + (uint32_t)a.G0 * 32u;
+  const uint32_t t16 = smem_u32(T16);
+  if (tid == 0) EM_STAMP(1);
+
+  if (warp == 8) {
+    // ================= MMA issuer =================
+    if (elect_one()) {
+      const uint32_t id1 = make_idesc(0, 32), idx = make_idesc(0, 96);
+      const uint64_t dbt = desc32(smem_u32(Bt)), dbx = desc32(smem_u32(Bex)), db2 = make_smem_desc(smem_u32(B2));
+      const int KL = a.KL;
+      mbar_wait(bars + EB_IMG, 0);
+      EM_STAMP(8);
+      mbar_wait(bars + EB_X, 0);
+      EM_STAMP(9);
+      mbar_wait(bars + EB_IN, 0);
+      EM_STAMP(10);
+      tc_fence_after();
 #pragma unroll 1
       for (int m = 0; m < 2; ++m) {
-        const uint32_t am = a0 + (uint32_t)m * 128u * 32u;
+        const uint64_t* ad = adesc + m * kMaxTaps;
+        const uint32_t d0 = tmem + (uint32_t)(m * 96);
+        int t = 0;
 #pragma unroll 1
-        for (int t = 0; t < ntap; ++t) {
-          int br, dy = 0, dx = 0, first;
-          if (t < a.KL) { br = 0; dx = t - half; first = t == 0; }
-          else if (t < 2 * a.KL) { br = 1; dy = t - a.KL - half; first = t == a.KL; }
-          else { br = 2; const int k = t - 2 * a.KL; dy = (k / 3 - 1) * a.dil; dx = (k % 3 - 1) * a.dil; first = k == 0; }
-          const uint64_t da = desc32(am + (uint32_t)((dy * P + dx) * 32));
-          const uint64_t db = desc32(smem_u32(Bt) + (uint32_t)t * kTapB);
-          const uint32_t d = tmem + (uint32_t)(m * 96 + br * 32);
-          if (first) umma_f16<0>(d, da, db, id1); else umma_f16<1>(d, da, db, id1);
+        for (int br = 0; br < 3; ++br) {
+          const int n = br == 2 ? 9 : KL;
+          const uint32_t d = d0 + (uint32_t)(br * 32);
+          umma_f16<0>(d, ad[t], dbt + (uint64_t)(t * (kTapB >> 4)), id1);
+          ++t;
+#pragma unroll 4
+          for (int k = 1; k < n; ++k, ++t) umma_f16<1>(d, ad[t], dbt + (uint64_t)(t * (kTapB >> 4)), id1);
+        }
+        umma_f16<1>(d0, desc32(smem_u32(Aex) + (uint32_t)m * kAex), dbx, idx);
+        umma_commit(bars + EB_D1 + m);
+        EM_STAMP(11 + m);
+      }
+#pragma unroll 1
+      for (int m = 0; m < 2; ++m) {
+        mbar_wait(bars + EB_A2 + m, 0);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc(smem_u32(A2) + m * kA2);
+        const uint32_t d = tmem + (uint32_t)(m * 96);
+        umma_f16<0>(d, da, db2, id1);
+        umma_f16<1>(d, da + 2, db2 + 2, id1);
+        umma_f16<1>(d, da + 4, db2 + 4, id1);
+        umma_f16<1>(d, da + 6, db2 + 6, id1);
+        umma_commit(bars + EB_D2 + m);
+        EM_STAMP(13 + m);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= workers =================
+    // channels 16, 17 of the tile in fp32 (the fp16 MMA operand rows come by TMA); rows past the staged ones only feed
+    // MMA rows whose results are dropped
+    const int rows_staged = a.R + 2 * halo;
+#pragma unroll 1
+    for (int i0 = tid; i0 < a.npx; i0 += 4 * 256) {       // four pixels per pass: their loads are in flight together
+      float2 e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        const int ly = i / P, lx = i - ly * P;
+        const int iy = ty0 - halo + ly, ix = tx0 - halo + lx;
+        e[u] = make_float2(0.f, 0.f);
+        if (i < a.npx && ly < rows_staged && iy >= 0 && iy < a.in.h && ix >= 0 && ix < a.in.w)
+          e[u] = __ldg(reinterpret_cast<const float2*>(a.in.p + a.in.pix(img, iy, ix) + 16));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * 256 < a.npx) T2[i0 + u * 256] = e[u];
+    }
+    if (tid == 0) EM_STAMP(2);
+    named_bar_sync(1, 256);                            // T2 complete (the fp16 tile is only read by the MMAs)
+    const int m_blk = tid >> 7, r_blk = tid & 127;
+    const int g = a.G0 + m_blk * 128 + r_blk;         // flattened padded position of this thread's pixel (= its MMA row)
+    {
+      mbar_wait(bars + EB_IMG, 0);                     // the extra-channel tap weights live in the operand image
+      f32x2 acc[3];
+      acc[0] = acc[1] = acc[2] = pack2(0.f, 0.f);
+      const float2* tp = T2 + g;
+      int t = 0;
+#pragma unroll
+      for (int br = 0; br < 3; ++br) {
+        const int n = br == 2 ? 9 : a.KL;
+        f32x2 s0 = pack2(0.f, 0.f), s1 = s0;
+        int k = 0;
+#pragma unroll 4
+        for (; k + 1 < n; k += 2, t += 2) {        // two independent chains, loads of several taps in flight
+          s0 = fma2(*reinterpret_cast<const f32x2*>(tp + (tapoff[t] >> 5)), *reinterpret_cast<const f32x2*>(exw + t), s0);
+          s1 = fma2(*reinterpret_cast<const f32x2*>(tp + (tapoff[t + 1] >> 5)), *reinterpret_cast<const f32x2*>(exw + t + 1), s1);
+        }
+        if (k < n) { s0 = fma2(*reinterpret_cast<const f32x2*>(tp + (tapoff[t] >> 5)), *reinterpret_cast<const f32x2*>(exw + t), s0); ++t; }
+        float a0, a1, b0, b1;
+        unpack2(s0, a0, a1); unpack2(s1, b0, b1);
+        acc[br] = pack2(a0 + b0, a1 + b1);
+      }
+      float x0, x1, x2, x3, x4, x5;
+      unpack2(acc[0], x0, x1); unpack2(acc[1], x2, x3); unpack2(acc[2], x4, x5);
+      const uint32_t row = smem_u32(Aex) + (uint32_t)m_blk * kAex + (uint32_t)r_blk * 32u;
+      st_shared_v4(unit32(row, 0), pack_f16x2(x0, x1), pack_f16x2(x2, x3), pack_f16x2(x4, x5), 0u);
+      st_shared_v4(unit32(row, 1), 0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+    if (tid == 0) EM_STAMP(3);
+    mbar_arrive(bars + EB_IN);
+    // ---- stage 2 operand: LReLU(stage 1) as fp16
+    mbar_wait(bars + EB_D1 + m_blk, 0);
+    if (tid == 0) EM_STAMP(4);
+    tc_fence_after();
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)m_blk * 96u;
+    const uint32_t a2_row = smem_u32(A2) + (uint32_t)m_blk * kA2 + (uint32_t)r_blk * 128u;
+    const uint32_t swz = (uint32_t)r_blk & 7u;
+    {
+      uint32_t pk[32];
+#pragma unroll
+      for (int i = 27; i < 32; ++i) pk[i] = 0u;
+#pragma unroll
+      for (int br = 0; br < 3; ++br) {
+        float s[32];
+        tmem_ld32(tlane + br * 32, s);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          float x0 = s[2 * i], x1 = s[2 * i + 1];
+          x0 = x0 > 0.f ? x0 : x0 * a.slope;
+          x1 = x1 > 0.f ? x1 : x1 * a.slope;
+          pk[br * 9 + i] = pack_f16x2(x0, x1);
+        }
+      }
+      et::store_row(a2_row, swz, pk);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    if (tid == 0) EM_STAMP(5);
+    mbar_arrive(bars + EB_A2 + m_blk);
+    mbar_wait(bars + EB_D2 + m_blk, 0);
+    if (tid == 0) EM_STAMP(6);
+    tc_fence_after();
+    {
+      float o[32];
+      tmem_ld32(tlane, o);
+      tmem_wait_ld();
+      const int gy = g / P, gx = g - gy * P;
+      const int ty = gy - halo, tx = gx - halo;
+      const int oy = ty0 + ty, ox = tx0 + tx;
+      if (tx >= 0 && tx < TW && ty >= 0 && ty < a.R && ox < a.in.w && oy < a.in.h) {
+        float* dst = a.out.p + a.out.pix(img, oy, ox);
+#pragma unroll
+        for (int i = 0; i < EC / 2; ++i) {
+          float x0 = o[2 * i], x1 = o[2 * i + 1];
+          x0 = x0 > 0.f ? x0 : x0 * a.slope;
+          x1 = x1 > 0.f ? x1 : x1 * a.slope;
+          reinterpret_cast<float2*>(dst)[i] = make_float2(x0, x1);
         }
       }
     }
-    __syncwarp();
-  }
-  const int m_blk = tid >> 7, r_blk = tid & 127;
-  const int g = a.G0 + m_blk * 128 + r_blk;           // flattened padded position of this thread's pixel (= its MMA row)
-  {
-    mbar_wait(bars + 2, 0);                            // exw lives in the operand image
-    f32x2 acc[3];
-    acc[0] = acc[1] = acc[2] = pack2(0.f, 0.f);
-    for (int t = 0; t < ntap; ++t) {
-      int br, dy = 0, dx = 0;
-      if (t < a.KL) { br = 0; dx = t - half; }
-      else if (t < 2 * a.KL) { br = 1; dy = t - a.KL - half; }
-      else { br = 2; const int k = t - 2 * a.KL; dy = (k / 3 - 1) * a.dil; dx = (k % 3 - 1) * a.dil; }
-      const f32x2 v = *reinterpret_cast<const f32x2*>(T2 + g + dy * P + dx);
-      const f32x2 w = *reinterpret_cast<const f32x2*>(exw + t);
-      if (br == 0) acc[0] = fma2(v, w, acc[0]);
-      else if (br == 1) acc[1] = fma2(v, w, acc[1]);
-      else acc[2] = fma2(v, w, acc[2]);
-    }
-    float x0, x1, x2, x3, x4, x5;
-    unpack2(acc[0], x0, x1); unpack2(acc[1], x2, x3); unpack2(acc[2], x4, x5);
-    const uint32_t row = smem_u32(Aex) + (uint32_t)m_blk * kAex + (uint32_t)r_blk * 32u;
-    st_shared_v4(unit32(row, 0), pack_f16x2(x0, x1), pack_f16x2(x2, x3), pack_f16x2(x4, x5), 0u);
-    st_shared_v4(unit32(row, 1), 0u, 0u, 0u, 0u);
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    if (tid == 0) {      // always the same lane: tcgen05.commit tracks the MMAs of the committing thread
-      tc_fence_after();
-      const uint32_t idx = make_idesc(0, 96);
-      const uint64_t db = desc32(smem_u32(Bex));
-#pragma unroll
-      for (int m = 0; m < 2; ++m) umma_f16<1>(tmem + (uint32_t)(m * 96), desc32(smem_u32(Aex) + (uint32_t)m * kAex), db, idx);
-      umma_commit(bars);
-    }
-    __syncwarp();
-  }
-  mbar_wait(bars, 0);
-  tc_fence_after();
-  // ---- stage 2: LReLU, fp16, fuse GEMM
-  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)m_blk * 96u;
-  const uint32_t a2_row = smem_u32(A2) + (uint32_t)m_blk * kA2 + (uint32_t)r_blk * 128u;
-  const uint32_t swz = (uint32_t)r_blk & 7u;
-  {
-    uint32_t pk[32];
-#pragma unroll
-    for (int i = 27; i < 32; ++i) pk[i] = 0u;
-#pragma unroll
-    for (int br = 0; br < 3; ++br) {
-      float s[32];
-      tmem_ld32(tlane + br * 32, s);
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        float x0 = s[2 * i], x1 = s[2 * i + 1];
-        x0 = x0 > 0.f ? x0 : x0 * a.slope;
-        x1 = x1 > 0.f ? x1 : x1 * a.slope;
-        pk[br * 9 + i] = pack_f16x2(x0, x1);
-      }
-    }
-    et::store_row(a2_row, swz, pk);
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    if (tid == 0) {      // always the same lane: tcgen05.commit tracks the MMAs of the committing thread
-      tc_fence_after();
-      const uint32_t id2 = make_idesc(0, 32);
-      const uint64_t db = make_smem_desc(smem_u32(B2));
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        const uint64_t da = make_smem_desc(smem_u32(A2) + m * kA2);
-        umma_f16<0>(tmem + m * 96, da, db, id2);
-        umma_f16<1>(tmem + m * 96, da + 2, db + 2, id2);
-        umma_f16<1>(tmem + m * 96, da + 4, db + 4, id2);
-        umma_f16<1>(tmem + m * 96, da + 6, db + 6, id2);
-      }
-      umma_commit(bars + 1);
-    }
-    __syncwarp();
-  }
-  mbar_wait(bars + 1, 0);
-  tc_fence_after();
-  {
-    float o[32];
-    tmem_ld32(tlane, o);
-    tmem_wait_ld();
-    const int gy = g / P, gx = g - gy * P;
-    const int ty = gy - halo, tx = gx - halo;
-    const int oy = ty0 + ty, ox = tx0 + tx;
-    if (tx >= 0 && tx < TW && ty >= 0 && ty < a.R && ox < a.in.w && oy < a.in.h) {
-      float* dst = a.out.p + a.out.pix(img, oy, ox);
-#pragma unroll
-      for (int i = 0; i < EC / 2; ++i) {
-        float x0 = o[2 * i], x1 = o[2 * i + 1];
-        x0 = x0 > 0.f ? x0 : x0 * a.slope;
-        x1 = x1 > 0.f ? x1 : x1 * a.slope;
-        reinterpret_cast<float2*>(dst)[i] = make_float2(x0, x1);
-      }
-    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (tid == 0) EM_STAMP(7);
+  if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
 }  // namespace lfsr
@@ -894,9 +939,28 @@ extern "C" int lfsr_mel_epi_pack(const float* w, void* out, int klen) {
   return LFSR_OK;
 }
 
-extern "C" int lfsr_mel_epi_branch_mma(const lfsr_tensor* in, const void* packed, const lfsr_tensor* out, int klen, int dil,
-                                       float slope, void* stream) {
-  LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && packed, "lfsr_mel_epi_branch_mma: null/invalid tensor");
+typedef CUresult (*EmEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EmEncodeFn em_get_encode() {
+  static EmEncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EmEncodeFn>(p);
+  });
+  return fn;
+}
+
+extern "C" int lfsr_mel_epi_branch_mma(const lfsr_tensor* in, const lfsr_tensor* in16, const void* packed, const lfsr_tensor* out,
+                                       int klen, int dil, float slope, void* stream) {
+  LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && tensor_ok(in16) && packed, "lfsr_mel_epi_branch_mma: null/invalid tensor");
+  LFSR_REQUIRE(in16->n == in->n && in16->h == in->h && in16->w == in->w && in16->c >= 16 && in16->ld % 8 == 0 &&
+                   ((uintptr_t)in16->ptr & 15) == 0,
+               "lfsr_mel_epi_branch_mma: in16 must be the fp16 copy of `in` (>= 16 channels, 16-byte aligned pixels)");
   LFSR_REQUIRE(in->c == EC && out->c == EC, "lfsr_mel_epi_branch_mma: built for %d-channel EPI splits, got %d", EC, in->c);
   LFSR_REQUIRE(in->n == out->n && in->h == out->h && in->w == out->w, "lfsr_mel_epi_branch_mma: shape mismatch");
   LFSR_REQUIRE(lfsr_mel_epi_pack_bytes(klen) > 0 && dil > 0, "lfsr_mel_epi_branch_mma: bad kernel length");
@@ -914,13 +978,33 @@ extern "C" int lfsr_mel_epi_branch_mma(const lfsr_tensor* in, const void* packed
   a.npx = (2 * a.G0 + 256 + 31) & ~31;               // last MMA row + largest shift, rounded up
   a.tiles_x = ceil_div(in->w, em::TW); a.tiles_y = ceil_div(in->h, a.R);
   const size_t img_b = ((size_t)em::image_bytes(a.ntap) + 1023) & ~(size_t)1023;
-  const size_t smem = 1024 + img_b + (((size_t)a.npx * 40 + 2 * em::kAex + 1023) & ~(size_t)1023) + 2 * em::kA2 + 64;
+  const size_t smem = 1024 + img_b + (((size_t)a.npx * 40 + 2 * em::kAex + 1023) & ~(size_t)1023) + 2 * em::kA2 + 128 + em::kMaxTaps * 4 + 2 * em::kMaxTaps * 8;
   LFSR_REQUIRE(smem <= 113 * 1024, "lfsr_mel_epi_branch_mma: kernel length / dilation too large for the staged tile");
   static DevOnce once;
   if (once.need()) {
     if (opt_in_smem(mel_epi_branch_mma_kernel, 113 * 1024, "lfsr_mel_epi_branch_mma")) return LFSR_ERR_CUDA;
     once.done();
   }
-  mel_epi_branch_mma_kernel<<<in->n * a.tiles_x * a.tiles_y, 256, smem, (cudaStream_t)stream>>>(a);
+  EmEncodeFn encode = em_get_encode();
+  LFSR_REQUIRE(encode, "lfsr_mel_epi_branch_mma: cuTensorMapEncodeTiled is not available");
+  CUtensorMap tmX;
+  {
+    const cuuint64_t ld_b = (cuuint64_t)in16->ld * 2;
+    cuuint64_t dims[4] = {16, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
+    cuuint64_t strides[3] = {ld_b, ld_b * in->w, ld_b * in->w * in->h};
+    cuuint32_t box[4] = {16, (cuuint32_t)a.P, (cuuint32_t)(a.R + 2 * a.halo), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    LFSR_REQUIRE(box[1] <= 256 && box[2] <= 256, "lfsr_mel_epi_branch_mma: tile too large for one tensor load");
+    CUresult r = encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, in16->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("lfsr_mel_epi_branch_mma: cuTensorMapEncodeTiled failed with %d", (int)r); return LFSR_ERR_CUDA; }
+  }
+  mel_epi_branch_mma_kernel<<<in->n * a.tiles_x * a.tiles_y, kEmThreads, smem, (cudaStream_t)stream>>>(tmX, a);
   return check_launch("mel_epi_branch_mma_kernel");
 }
+
+#ifdef LFSR_DEBUG_HOOKS
+extern "C" int lfsr_debug_set_em_dbg(long long* dev_ptr) {
+  return cudaMemcpyToSymbol(lfsr::g_em_dbg, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? LFSR_OK : LFSR_ERR_CUDA;
+}
+#endif

@@ -24,7 +24,9 @@ template <bool VEC4>
 __global__ void __launch_bounds__(256)
 block_mean_kernel(TView in, TView out, int bh, int bw) {
   __shared__ float red[16][68];
-  int blk = blockIdx.x;
+  // blocks in REVERSE order: the producer of `in` (a persistent conv / a tiled kernel walking the images forward) has just
+  // finished with the LAST images, and those are what is still in L2
+  int blk = gridDim.x - 1 - blockIdx.x;
   const int nbx = in.w / bw, nby = in.h / bh;
   const int bx = blk % nbx; blk /= nbx;
   const int by = blk % nby;

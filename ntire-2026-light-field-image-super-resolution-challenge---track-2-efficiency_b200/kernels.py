@@ -341,9 +341,11 @@ class CudaOps:
         N.check(self.lib.lfsr_mel_epi_pack(w.data_ptr(), img.data_ptr(), klen), "lfsr_mel_epi_pack")
         return img.to(device)
 
-    def mel_epi_branch_mma(self, x, image, out, klen, dil, slope):
-        N.check(self.lib.lfsr_mel_epi_branch_mma(C.byref(as_tensor(x, "epi.in")), image.data_ptr(), C.byref(as_tensor(out, "epi.out")),
-                                                 klen, dil, slope, self._stream(x)), "lfsr_mel_epi_branch_mma")
+    def mel_epi_branch_mma(self, x, x16, image, out, klen, dil, slope):
+        """x16: the fp16 copy of x (same pixels, >= 16 channels) written by x's producer"""
+        N.check(self.lib.lfsr_mel_epi_branch_mma(C.byref(as_tensor(x, "epi.in")), C.byref(as_tensor(x16, "epi.in16", f16=True)),
+                                                 image.data_ptr(), C.byref(as_tensor(out, "epi.out")), klen, dil, slope,
+                                                 self._stream(x)), "lfsr_mel_epi_branch_mma")
 
     # -- reductions / gates -------------------------------------------------------------------------
     def block_mean(self, x, out, bh, bw):

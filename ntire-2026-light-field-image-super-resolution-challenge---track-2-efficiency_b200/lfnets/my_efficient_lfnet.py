@@ -348,7 +348,10 @@ class get_model(LFNetBase):
                          res=feat[..., gs:2 * gs], shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
             # EPI branch: three depthwise+pointwise paths and their fuse conv in one kernel
             if st.get("epi_img") is not None:
-                ops.mel_epi_branch_mma(xe, st["epi_img"], cat[..., sl[2]], st["epi_klen"], A, 0.1)
+                # experiment (LFSR_EPI_MMA=1): depthwise taps as shifted-row MMAs over an fp16 copy of the EPI group
+                xe16 = self._buf16("xe16", B, H, W, 32, dev)
+                ops.to_f16(feat[..., 2 * gs:2 * gs + 16], xe16[..., 0:16])
+                ops.mel_epi_branch_mma(xe, xe16[..., 0:sp[2]], st["epi_img"], cat[..., sl[2]], st["epi_klen"], A, 0.1)
             else:
                 ops.mel_epi_branch(xe, st["epi_w"], cat[..., sl[2]], st["epi_klen"], A, 0.1, tc=bool(f16))
             fork.join()

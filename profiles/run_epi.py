@@ -24,14 +24,16 @@ for tc in ([False, True] if which == "both" else [which == "tc"]):
     print(f"mel_epi_branch{'_tc' if tc else ''} batch {B}: {e0.elapsed_time(e1) / 10:.3f} ms")
 # all-tensor-core variant (depthwise taps as shifted-row MMAs)
 img = ops.mel_epi_pack(w, 11, "cuda")
+trunk16 = K.alloc_nhwc16(B, 160, 160, 64, "cuda")
+trunk16[..., :60].copy_(trunk)
 if img is not None:
     for _ in range(3):
-        ops.mel_epi_branch_mma(trunk[..., 40:58], img, cat[..., 40:58], 11, 5, 0.1)
+        ops.mel_epi_branch_mma(trunk[..., 40:58], trunk16[..., 40:58], img, cat[..., 40:58], 11, 5, 0.1)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        ops.mel_epi_branch_mma(trunk[..., 40:58], img, cat[..., 40:58], 11, 5, 0.1)
+        ops.mel_epi_branch_mma(trunk[..., 40:58], trunk16[..., 40:58], img, cat[..., 40:58], 11, 5, 0.1)
     e1.record()
     torch.cuda.synchronize()
     print(f"mel_epi_branch_mma batch {B}: {e0.elapsed_time(e1) / 10:.3f} ms")

@@ -732,7 +732,9 @@ def test_mel_epi_branch_mma(ops, ref, n, h, w):
     tc_ops = K.CudaOps(use_tc=True)
     img = tc_ops.mel_epi_pack(wts, klen, DEV)
     assert img is not None and img.numel() == tc_ops.lib.lfsr_mel_epi_pack_bytes(klen)
-    tc_ops.mel_epi_branch_mma(x, img, a_full[..., 40:58], klen, A, 0.1)
+    full16 = K.alloc_nhwc16(n, h, w, 64, DEV)
+    full16[..., :60].copy_(full)
+    tc_ops.mel_epi_branch_mma(x, full16[..., 40:58], img, a_full[..., 40:58], klen, A, 0.1)
     ops.mel_epi_branch(x, wts, b_full[..., 40:58], klen, A, 0.1) if n > 8 else ref.mel_epi_branch(x, wts, b_full[..., 40:58], klen, A, 0.1)
     scale = max(1.0, b_full[..., 40:58].abs().max().item())
     err = (a_full - b_full).abs().max().item()

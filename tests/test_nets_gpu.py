@@ -102,6 +102,22 @@ def test_forward_batch64_default_init_vs_oracle(name, scale):
     assert worst <= TOL and worst_dp <= 0.01, (worst, worst_dp)
 
 
+def test_epi_branch_all_mma_variant_matches_default(monkeypatch):
+    """LFSR_EPI_MMA=1 (depthwise taps of the EPI block as shifted-row tcgen05 MMAs) is an opt-in experiment: same network
+    output as the default plan to well inside the parity tolerance"""
+    import sys
+    torch.manual_seed(1234)
+    net = lfsr_b200.load_net("MyEfficientLFNet", 5, 4).eval().to(DEV)
+    mod = sys.modules[type(net).__module__]          # (the package is importable under two names)
+    x = weights.synthetic_patches(4, 5, 32, seed=9).to(DEV)
+    y0 = net(x, [5, 5]).clone()
+    monkeypatch.setattr(mod, "USE_EPI_MMA", True)
+    net.invalidate()
+    y1 = net(x, [5, 5]).clone()
+    d = float((y0 - y1).abs().max())
+    assert 0.0 < d <= 3e-4, d
+
+
 def test_invalidate_after_data_edit():
     """edits through `.data` bypass the version counter; invalidate() (also run by load_state_dict) repacks."""
     net, sd = _net("MyEfficientLFNet", 4)
