@@ -250,6 +250,11 @@ int lfsr_block_mean(const lfsr_tensor* in, const lfsr_tensor* out, int block_h, 
  * w1 is [in->c][c1], w2 [c1][c2] (the lfsr_conv2d_f32 packing of a 1x1 kernel); b1 / b2 / w2 may be null. */
 int lfsr_pooled_mlp(const lfsr_tensor* in, int pool, const float* w1, const float* b1, int c1, int act1, const float* w2,
                     const float* b2, int c2, int act2, const lfsr_tensor* out, void* stream);
+/* AngularAttention.expand + PixelShuffle(A) + activation, * alpha, + residual (MyEfficientLFNet.py:262-275) as one streaming
+ * kernel: out[n, A*Y+i, A*X+j, c] = res[...] + alpha * act(sum_k in[n, Y, X, k] * w[i][j][k][c]).
+ * w is [A][A][in->c][out->c] (out->c a multiple of 4: pad channels carry zero weights); in->c is 16, 18 or 20; res may be null. */
+int lfsr_ang_expand(const lfsr_tensor* in, const float* w, const lfsr_tensor* res, const lfsr_tensor* out, int A, int act,
+                    float slope, float alpha, void* stream);
 /* SAModulator tail (MyEfficientLFNet.py:495-515) fused with the stage residual:
  *   s = sigmoid(bn_scale*dw3x3_dil(x) + bn_shift); a = amod[n][y/(h/A)][x/(w/A)][c]
  *   out = x * (w0*s + w1*a) + res */

@@ -118,6 +118,7 @@ SIGNATURES = {
     "lfsr_conv2d_tc_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),
     "lfsr_block_mean": (_I, [_TP, _TP, _I, _I, _P]),
     "lfsr_pooled_mlp": (_I, [_TP, _I, _P, _P, _I, _I, _P, _P, _I, _I, _TP, _P]),
+    "lfsr_ang_expand": (_I, [_TP, _P, _TP, _TP, _I, _I, C.c_float, C.c_float, _P]),
     "lfsr_sa_modulate": (_I, [_TP, _P, _P, _P, _TP, C.c_float, C.c_float, _TP, _TP, _I, _P]),
     "lfsr_sa_modulate16": (_I, [_TP, _P, _P, _P, _TP, C.c_float, C.c_float, _TP, _TP, _TP, _I, _P]),
     "lfsr_scale_add": (_I, [_TP, _TP, _TP, _TP, _P]),

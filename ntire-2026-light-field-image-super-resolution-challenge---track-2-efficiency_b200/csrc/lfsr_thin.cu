@@ -377,3 +377,123 @@ extern "C" int lfsr_conv2d_stem(const lfsr_tensor* in, const float* w_packed, co
   conv_stem_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return check_launch("conv_stem_kernel");
 }
+
+// ---- angular expand: 1x1 conv cin -> cq*A*A + PixelShuffle(A) + activation * alpha + residual ---------------------------
+// (MyEfficientLFNet.py:262-275: AngularAttention.expand, the LReLU, `x + scale * out`.) Per low-resolution pixel this reads
+// cin <= 20 values and writes A*A pixels of cq channels: 2916 MACs for 2 KB of output - streaming work. On the tensor-core
+// conv it was bound by its epilogue (one residual round trip per 32-pixel block and warp, 0.19 ms at batch 64); here a
+// thread owns one (sub-pixel column j, channel quad q) with its cin x 4 weights in registers and walks the low-resolution
+// pixels of `yg` rows, every output a coalesced 16-byte store, the residuals of a row loaded together up front.
+namespace lfsr {
+struct AngExpArgs {
+  TView in, res, out;
+  const float* w;      // [A][A][cin][cq]  (sub-pixel row i, column j)
+  int A, cq4, act, yg, groups;
+  float slope, alpha;
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(256, 2)
+ang_expand_kernel(const AngExpArgs a) {
+  extern __shared__ __align__(16) float ae_s[];        // [yg][w][20] staged low-resolution rows
+  const int tid = threadIdx.x;
+  int b = blockIdx.x;
+  const int g = b % a.groups; b /= a.groups;
+  const int i = b % a.A;
+  const int img = b / a.A;
+  const int wl = a.in.w, cq = a.cq4 * 4;
+  const int y0 = g * a.yg;
+  const int rows = min(a.yg, a.in.h - y0);
+  // (requesting the CTA's residual rows into L2 up front was tried: 0.170 vs 0.160 ms - the kernel is not latency-bound on them)
+  for (int t = tid; t < rows * wl * 5; t += 256) {       // 20 floats per pixel (cin real + zeros)
+    const int u = t % 5, px = t / 5;
+    const int yy = px / wl, xx = px - yy * wl;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* src = a.in.p + a.in.pix(img, y0 + yy, xx);
+    if (4 * u + 3 < CIN) v = __ldg(reinterpret_cast<const float4*>(src + 4 * u));
+    else {
+      if (4 * u < CIN) v.x = __ldg(src + 4 * u);
+      if (4 * u + 1 < CIN) v.y = __ldg(src + 4 * u + 1);
+      if (4 * u + 2 < CIN) v.z = __ldg(src + 4 * u + 2);
+    }
+    reinterpret_cast<float4*>(ae_s)[t] = v;
+  }
+  const int combos = a.A * a.cq4;
+  const int XG = 256 / combos;
+  const int xg = tid / combos, r = tid - xg * combos;
+  const int j = r / a.cq4, q = r - j * a.cq4;
+  float4 w[CIN];
+  if (xg < XG) {
+    const float* wp = a.w + ((size_t)(i * a.A + j) * CIN) * cq + 4 * q;
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) w[k] = __ldg(reinterpret_cast<const float4*>(wp + k * cq));
+  }
+  __syncthreads();
+  if (xg >= XG) return;
+  constexpr int NX = 4;                                  // low-resolution pixels per thread and pass
+  for (int yy = 0; yy < rows; ++yy) {
+    const int oy = (y0 + yy) * a.A + i;
+    const size_t orow = a.out.pix(img, oy, 0), rrow = a.res.p ? a.res.pix(img, oy, 0) : 0;
+    for (int x0 = xg; x0 < wl; x0 += NX * XG) {
+      float4 rv[NX];
+#pragma unroll
+      for (int u = 0; u < NX; ++u) {
+        const int X = x0 + u * XG;
+        rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.res.p && X < wl) rv[u] = *reinterpret_cast<const float4*>(a.res.p + rrow + (size_t)(X * a.A + j) * a.res.ld + 4 * q);
+      }
+#pragma unroll
+      for (int u = 0; u < NX; ++u) {
+        const int X = x0 + u * XG;
+        if (X >= wl) break;
+        const float4* xp = reinterpret_cast<const float4*>(ae_s + (yy * wl + X) * 20);
+        float xin[20];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { const float4 t4 = xp[c]; xin[4 * c] = t4.x; xin[4 * c + 1] = t4.y; xin[4 * c + 2] = t4.z; xin[4 * c + 3] = t4.w; }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < CIN; ++k) {
+          acc.x = fmaf(xin[k], w[k].x, acc.x); acc.y = fmaf(xin[k], w[k].y, acc.y);
+          acc.z = fmaf(xin[k], w[k].z, acc.z); acc.w = fmaf(xin[k], w[k].w, acc.w);
+        }
+        acc.x = fmaf(apply_act(acc.x, a.act, a.slope), a.alpha, rv[u].x); acc.y = fmaf(apply_act(acc.y, a.act, a.slope), a.alpha, rv[u].y);
+        acc.z = fmaf(apply_act(acc.z, a.act, a.slope), a.alpha, rv[u].z); acc.w = fmaf(apply_act(acc.w, a.act, a.slope), a.alpha, rv[u].w);
+        *reinterpret_cast<float4*>(a.out.p + orow + (size_t)(X * a.A + j) * a.out.ld + 4 * q) = acc;
+      }
+    }
+  }
+}
+}  // namespace lfsr
+
+extern "C" int lfsr_ang_expand(const lfsr_tensor* in, const float* w, const lfsr_tensor* res, const lfsr_tensor* out, int A, int act,
+                               float slope, float alpha, void* stream) {
+  LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && w && A >= 1, "lfsr_ang_expand: null/invalid argument");
+  LFSR_REQUIRE(out->n == in->n && out->h == in->h * A && out->w == in->w * A, "lfsr_ang_expand: out must be A x the input size");
+  LFSR_REQUIRE(out->c % 4 == 0 && out->ld % 4 == 0 && ((uintptr_t)out->ptr & 15) == 0 && ((uintptr_t)w & 15) == 0,
+               "lfsr_ang_expand: output channels in 16-byte aligned quads");
+  LFSR_REQUIRE(in->ld % 4 == 0 && ((uintptr_t)in->ptr & 15) == 0 && in->ld >= ((in->c + 3) & ~3),
+               "lfsr_ang_expand: input pixels must be 16-byte aligned with readable pad floats");
+  LFSR_REQUIRE(A * (out->c / 4) <= 256, "lfsr_ang_expand: A x channel quads must fit one CTA");
+  const bool has_res = res && res->ptr;
+  if (has_res)
+    LFSR_REQUIRE(res->n == out->n && res->h == out->h && res->w == out->w && res->c == out->c && res->ld % 4 == 0 &&
+                     ((uintptr_t)res->ptr & 15) == 0, "lfsr_ang_expand: res shape / alignment");
+  lfsr::AngExpArgs a;
+  a.in = view_of(in); a.out = view_of(out); a.res = has_res ? view_of(res) : null_view();
+  a.w = w; a.A = A; a.cq4 = out->c / 4; a.act = act; a.slope = slope; a.alpha = alpha;
+  a.yg = 8;
+  while (a.yg > 1 && (size_t)a.yg * in->w * 20 * 4 > 40 * 1024) a.yg >>= 1;
+  LFSR_REQUIRE((size_t)a.yg * in->w * 20 * 4 <= 40 * 1024, "lfsr_ang_expand: input rows too wide");
+  a.groups = ceil_div(in->h, a.yg);
+  const size_t smem = (size_t)a.yg * in->w * 20 * 4;
+  const long long grid = (long long)in->n * A * a.groups;
+  LFSR_REQUIRE(grid <= 0x7fffffffLL, "lfsr_ang_expand: grid too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (in->c) {
+    case 16: lfsr::ang_expand_kernel<16><<<(unsigned)grid, 256, smem, st>>>(a); break;
+    case 18: lfsr::ang_expand_kernel<18><<<(unsigned)grid, 256, smem, st>>>(a); break;
+    case 20: lfsr::ang_expand_kernel<20><<<(unsigned)grid, 256, smem, st>>>(a); break;
+    default: LFSR_REQUIRE(false, "lfsr_ang_expand: built for 16 / 18 / 20 input channels, got %d", in->c);
+  }
+  return check_launch("ang_expand_kernel");
+}

@@ -352,6 +352,13 @@ class CudaOps:
         N.check(self.lib.lfsr_block_mean(C.byref(as_tensor(x, "block_mean.in")), C.byref(as_tensor(out, "block_mean.out")),
                                          bh, bw, self._stream(x)), "lfsr_block_mean")
 
+    def ang_expand(self, x, w, res, out, A, act=N.ACT_NONE, slope=0.0, alpha=1.0):
+        """out[n, A*Y+i, A*X+j, :] = res + alpha * act(x[n, Y, X, :] @ w[i][j]); w is [A, A, cin, cout] on the device"""
+        rt = as_tensor(res, "ang_expand.res") if res is not None else _NULL_T
+        N.check(self.lib.lfsr_ang_expand(C.byref(as_tensor(x, "ang_expand.in")), w.data_ptr(), C.byref(rt),
+                                         C.byref(as_tensor(out, "ang_expand.out")), A, act, slope, alpha, self._stream(x)),
+                "lfsr_ang_expand")
+
     def pooled_mlp(self, x, out, pc1: PackedConv, act1, pc2: Optional[PackedConv] = None, act2=N.ACT_NONE, pool=False):
         """one launch for a chain of 1x1 convs on the few positions of `x` [n,h,w,c] (pool: on their mean): the stage gates
         and the SA modulator's angular MLP of the Track-2 model"""

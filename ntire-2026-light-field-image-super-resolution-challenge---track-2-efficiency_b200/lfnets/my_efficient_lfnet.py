@@ -222,6 +222,10 @@ class get_model(LFNetBase):
             ce = we.shape[0] // (A * A)
             we = torch.cat([we.view(ce, A * A, *we.shape[1:]), we.new_zeros((gs_ - ce, A * A) + tuple(we.shape[1:]))], 0)
             s["ang_ex"] = pc(we.reshape(gs_ * A * A, *we.shape[2:]), tc=True, tc_shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
+            # the same layer for the streaming kernel (lfsr_ang_expand): [A][A][cin][cout padded to gs], nn.PixelShuffle order
+            wx = ab.expand["0"].weight.detach().float().cpu()[:, :, 0, 0]            # [c*A*A + i*A + j, cin]
+            wx = wx.view(ce, A, A, wx.shape[1]).permute(1, 2, 3, 0)                   # [i, j, cin, c]
+            s["ang_exw"] = torch.cat([wx, wx.new_zeros(A, A, wx.shape[2], gs_ - ce)], 3).contiguous().to(device)
             s["ang_scale"] = float(ab.scale.detach().item())
             eb = st.epi_branch
             pw_t = lambda m: m.weight.detach().float()[:, :, 0, 0].t().contiguous().reshape(-1).cpu()   # [in][out]
@@ -344,8 +348,12 @@ class get_model(LFNetBase):
                 ops.dwconv(ang2, st["ang_a2"], ang3, 3, 3, act=N.ACT_RELU)
                 ops.conv(ang3[..., 0:hid], st["ang_a4"], ang4, act=N.ACT_SIGMOID, mul=ang1)
                 ops.conv(ang4[..., 0:c0], st["ang_cv"], ang5, act=LR, slope=0.1)
-                ops.conv(ang5[..., 0:c0], st["ang_ex"], cat[..., gs:2 * gs], act=LR, slope=0.1, alpha=st["ang_scale"],
-                         res=feat[..., gs:2 * gs], shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
+                if hasattr(ops, "ang_expand"):
+                    ops.ang_expand(ang5[..., 0:c0], st["ang_exw"], feat[..., gs:2 * gs], cat[..., gs:2 * gs], A, LR, 0.1,
+                                   st["ang_scale"])
+                else:
+                    ops.conv(ang5[..., 0:c0], st["ang_ex"], cat[..., gs:2 * gs], act=LR, slope=0.1, alpha=st["ang_scale"],
+                             res=feat[..., gs:2 * gs], shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
             # EPI branch: three depthwise+pointwise paths and their fuse conv in one kernel
             if st.get("epi_img") is not None:
                 # experiment (LFSR_EPI_MMA=1): depthwise taps as shifted-row MMAs over an fp16 copy of the EPI group

@@ -49,6 +49,12 @@ class ProfilingOps(K.CudaOps):
     def sa_modulate(self, *a, **kw):
         self._wrap("sa_modulate", lambda: K.CudaOps.sa_modulate(self, *a, **kw), "sa_modulate" + (" + fp16 copy" if kw.get("out16") is not None else ""))
 
+    def ang_expand(self, x, w, res, out, A, *a, **kw):
+        self._wrap("ang_expand", lambda: K.CudaOps.ang_expand(self, x, w, res, out, A, *a, **kw), f"ang_expand c{x.shape[3]}->{out.shape[3]} x{A}x{A} @{x.shape[1]}x{x.shape[2]}")
+
+    def pooled_mlp(self, x, out, *a, **kw):
+        self._wrap("pooled_mlp", lambda: K.CudaOps.pooled_mlp(self, x, out, *a, **kw), f"pooled_mlp c{x.shape[3]} @{x.shape[1]}x{x.shape[2]}{' pooled' if kw.get('pool') else ''}")
+
     def to_f16(self, *a):
         self._wrap("to_f16", lambda: K.CudaOps.to_f16(self, *a), "to_f16")
 

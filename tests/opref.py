@@ -210,6 +210,15 @@ class RefOps:
         y = F.leaky_relu(F.conv2d(torch.cat(outs, 1), fu.t().reshape(c, 3 * c, 1, 1)), slope)
         out.copy_(y.permute(0, 2, 3, 1))
 
+    def ang_expand(self, x, w, res, out, A, act=0, slope=0.0, alpha=1.0):
+        n, h, wd, c = x.shape
+        y = torch.einsum("nyxk,ijkc->nyixjc", x.float(), w)                  # [n, h, A, w, A, cout]
+        y = _act(y, act, slope) * alpha
+        y = y.reshape(n, h * A, wd * A, w.shape[3])
+        if res is not None:
+            y = y + res
+        out.copy_(y)
+
     def pooled_mlp(self, x, out, pc1, act1, pc2=None, act2=0, pool=False):
         n, h, w, c = x.shape
         t = x.float().reshape(n, h * w, c)

@@ -243,6 +243,28 @@ def test_block_mean(ops, ref, h, w, c, bh, bw):
     assert (a - b).abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("n,h,w,cin,with_res", [(2, 8, 8, 18, True), (3, 32, 32, 18, True), (2, 7, 9, 20, False), (2, 8, 8, 16, True)])
+def test_ang_expand(ops, ref, n, h, w, cin, with_res):
+    """AngularAttention.expand + PixelShuffle(5) + LReLU * alpha + residual as one streaming kernel, and == the conv path"""
+    A, cq = 5, 20
+    full = nhwc(n, h, w, 20, seed=1)
+    x = full[..., :cin]
+    wts = rnd(A, A, cin, cq, seed=2) * 0.3
+    trunk = nhwc(n, h * A, w * A, 60, seed=3)
+    a_full, b_full = nhwc(n, h * A, w * A, 60, seed=4), nhwc(n, h * A, w * A, 60, seed=4)
+    res = trunk[..., 20:40] if with_res else None
+    ops.ang_expand(x, wts, res, a_full[..., 20:40], A, N.ACT_LRELU, 0.1, 0.37)
+    ref.ang_expand(x, wts, res, b_full[..., 20:40], A, N.ACT_LRELU, 0.1, 0.37)
+    assert (a_full - b_full).abs().max().item() <= 2e-5
+    assert torch.equal(a_full[..., 40:], b_full[..., 40:]) and torch.equal(a_full[..., :20], b_full[..., :20])
+    if cin == 18 and with_res:       # the conv formulation of the same layer (nn.PixelShuffle channel order)
+        wc = wts.permute(3, 0, 1, 2).reshape(cq * A * A, cin, 1, 1).cpu()
+        pc = K.pack_conv(wc, device=DEV)
+        c_full = nhwc(n, h * A, w * A, 60, seed=4)
+        ref.conv(x, pc, c_full[..., 20:40], act=N.ACT_LRELU, slope=0.1, alpha=0.37, res=res, shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
+        assert (a_full - c_full).abs().max().item() <= 2e-5
+
+
 @pytest.mark.parametrize("pool,two", [(True, False), (False, True), (True, True), (False, False)])
 def test_pooled_mlp(ops, ref, pool, two):
     """the stage gates (pooled, one layer + bias) and the SA modulator's angular MLP (two layers) as one launch each"""
