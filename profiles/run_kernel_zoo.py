@@ -69,11 +69,26 @@ cat = torch.zeros(B, 160, 160, 60, device=dev)
 wep = (torch.rand((2 * 11 + 9) * 18 + 6 * 18 * 18, device=dev) - 0.5) * 0.3
 run("mel_epi_branch @160", lambda: ops.mel_epi_branch(trunk[..., 40:58], wep, cat[..., 40:58], 11, 5, 0.1),
     B * 160 * 160 * 4 * 36, 2.0 * B * 160 * 160 * (18 * 31 + 6 * 18 * 18))
+run("mel_epi_branch_tc @160 (1x1s on tcgen05)", lambda: ops.mel_epi_branch(trunk[..., 40:58], wep, cat[..., 40:58], 11, 5, 0.1, tc=True),
+    B * 160 * 160 * 4 * 36, 2.0 * B * 160 * 160 * (18 * 31 + 6 * 18 * 18))
+epi_img = ops.mel_epi_pack(wep, 11, dev)
+trunk16 = K.alloc_nhwc16(B, 160, 160, 64, dev)
+trunk16[..., :60].copy_(trunk)
+run("mel_epi_branch_mma @160 (taps as shifted-row MMAs, opt-in)",
+    lambda: ops.mel_epi_branch_mma(trunk[..., 40:58], trunk16[..., 40:58], epi_img, cat[..., 40:58], 11, 5, 0.1),
+    B * 160 * 160 * (2 * 18 + 4 * 18), 2.0 * B * 160 * 160 * (18 * 31 + 6 * 18 * 18))
+ang5 = torch.rand(B, 32, 32, 20, device=dev)
+wex = (torch.rand(5, 5, 18, 20, device=dev) - 0.5) * 0.3
+run("ang_expand 18->20 x5x5 + residual @32 -> @160", lambda: ops.ang_expand(ang5[..., :18], wex, trunk[..., 20:40], cat[..., 20:40], 5, N.ACT_LRELU, 0.1, 0.1),
+    B * 160 * 160 * 4 * 36 + B * 32 * 32 * 72, 2.0 * B * 160 * 160 * 18 * 18)
 res, out = torch.rand_like(trunk), torch.empty_like(trunk)
 dw, bs, bb = torch.rand(9, 60, device=dev), torch.rand(60, device=dev) + 0.5, torch.rand(60, device=dev)
 am = torch.rand(B, 5, 5, 60, device=dev)
-run("dw_tile (SA modulator tail) c54 d5 @160", lambda: ops.sa_modulate(trunk, dw, bs, bb, am, 0.4, 0.6, res, out, 5),
+run("sa_tile (SA modulator tail) c54 d5 @160", lambda: ops.sa_modulate(trunk, dw, bs, bb, am, 0.4, 0.6, res, out, 5),
     3 * B * 160 * 160 * 54 * 4)
+xs16 = K.alloc_nhwc16(B, 160, 160, 32, dev)
+run("sa_tile (SA modulator tail + fp16 copy of 32 channels)", lambda: ops.sa_modulate(trunk, dw, bs, bb, am, 0.4, 0.6, res, out, 5, out16=xs16),
+    3 * B * 160 * 160 * 54 * 4 + B * 160 * 160 * 64)
 vm = torch.empty(B, 5, 5, 60, device=dev)
 run("block_mean 32x32 c54 @160", lambda: ops.block_mean(trunk, vm, 32, 32), B * 160 * 160 * 54 * 4)
 x1 = torch.rand(B, 160, 160, 1, device=dev)
