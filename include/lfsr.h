@@ -272,6 +272,9 @@ int lfsr_sa_modulate16(const lfsr_tensor* x, const float* dw_w, const float* bn_
  * scale is an [n,1,1,c] tensor view, res may be NULL. */
 int lfsr_scale_add(const lfsr_tensor* x, const lfsr_tensor* scale, const lfsr_tensor* res, const lfsr_tensor* out,
                    void* stream);
+/* the same with an fp16 result (a tensor that only a tensor-core layer reads): out16->ptr is __half*, ld in halves, c % 8 == 0 */
+int lfsr_scale_add16(const lfsr_tensor* x, const lfsr_tensor* scale, const lfsr_tensor* res, const lfsr_tensor* out16,
+                     void* stream);
 
 /* ---- EPIT token ops (EPIT.py:74-128) ------------------------------------------------------ */
 /* LayerNorm over c (eps, affine) for every pixel/token */

@@ -122,6 +122,7 @@ SIGNATURES = {
     "lfsr_sa_modulate": (_I, [_TP, _P, _P, _P, _TP, C.c_float, C.c_float, _TP, _TP, _I, _P]),
     "lfsr_sa_modulate16": (_I, [_TP, _P, _P, _P, _TP, C.c_float, C.c_float, _TP, _TP, _TP, _I, _P]),
     "lfsr_scale_add": (_I, [_TP, _TP, _TP, _TP, _P]),
+    "lfsr_scale_add16": (_I, [_TP, _TP, _TP, _TP, _P]),
     "lfsr_layernorm": (_I, [_TP, _P, _P, C.c_float, _TP, _P]),
     "lfsr_epi_attention": (_I, [_P, _P, _P, C.POINTER(EpiAttnDesc), _P]),
     "lfsr_basictrans_packed_bytes": (C.c_size_t, []),

@@ -232,6 +232,36 @@ scale_add_kernel(TView x, const float* __restrict__ scale, int scale_ld, TView r
   }
 }
 
+// the same with an fp16 result (the tensor only feeds a tensor-core layer): 8 channels per thread, one 16-byte store
+__global__ void __launch_bounds__(256)
+scale_add16_kernel(TView x, const float* __restrict__ scale, int scale_ld, TView res, __half* __restrict__ out, int out_ld) {
+  const int CV = x.c / 8;
+  const int img = blockIdx.y;
+  const int per = x.h * x.w * CV;
+  const float* sc = scale + (size_t)img * scale_ld;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per; t += gridDim.x * blockDim.x) {
+    const int c = (t % CV) * 8;
+    const int r = t / CV;
+    const int px = r % x.w, py = r / x.w;
+    const float* src = x.p + x.pix(img, py, px) + c;
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(src)), a1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= __ldg(sc + c + e);
+    if (res.p) {
+      const float4* rs = reinterpret_cast<const float4*>(res.p + res.pix(img, py, px) + c);
+      const float4 r0 = __ldg(rs), r1 = __ldg(rs + 1);
+      v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+    }
+    const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]), h2 = __floats2half2_rn(v[4], v[5]),
+                  h3 = __floats2half2_rn(v[6], v[7]);
+    uint4 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
+    o.z = *reinterpret_cast<const uint32_t*>(&h2); o.w = *reinterpret_cast<const uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(out + ((size_t)((size_t)img * x.h + py) * x.w + px) * (size_t)out_ld + c) = o;
+  }
+}
+
 // ---- second half of a KxK conv to one channel: sum of the per-tap responses at the shifted positions
 __global__ void __launch_bounds__(256)
 tap_gather_kernel(TView taps, TView res, TView out, int kh, int kw, const float* __restrict__ bias) {
@@ -750,6 +780,27 @@ extern "C" int lfsr_scale_add(const lfsr_tensor* x, const lfsr_tensor* scale, co
   if (v4) scale_add_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(view_of(x), (const float*)scale->ptr, scale->ld, r, view_of(out));
   else scale_add_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(view_of(x), (const float*)scale->ptr, scale->ld, r, view_of(out));
   return check_launch("scale_add_kernel");
+}
+
+extern "C" int lfsr_scale_add16(const lfsr_tensor* x, const lfsr_tensor* scale, const lfsr_tensor* res, const lfsr_tensor* out16,
+                                void* stream) {
+  LFSR_REQUIRE(tensor_ok(x) && tensor_ok(scale) && tensor_ok(out16), "lfsr_scale_add16: null/invalid tensor");
+  LFSR_REQUIRE(out16->n == x->n && out16->h == x->h && out16->w == x->w && out16->c == x->c, "lfsr_scale_add16: out shape");
+  LFSR_REQUIRE(scale->n == x->n && scale->h == 1 && scale->w == 1 && scale->c == x->c, "lfsr_scale_add16: scale must be [n,1,1,c]");
+  LFSR_REQUIRE(x->n <= 65535 && x->c % 8 == 0 && x->ld % 4 == 0 && ((uintptr_t)x->ptr & 15) == 0 && out16->ld % 8 == 0 &&
+                   ((uintptr_t)out16->ptr & 15) == 0,
+               "lfsr_scale_add16: channels in groups of 8 on 16-byte aligned pixels");
+  TView r = null_view();
+  if (res && res->ptr) {
+    LFSR_REQUIRE(res->n == x->n && res->h == x->h && res->w == x->w && res->c == x->c && res->ld % 4 == 0 &&
+                     ((uintptr_t)res->ptr & 15) == 0, "lfsr_scale_add16: res shape / alignment");
+    r = view_of(res);
+  }
+  const int per = x->h * x->w * (x->c / 8);
+  dim3 blocks(ceil_div(per, 256), x->n);
+  scale_add16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(view_of(x), (const float*)scale->ptr, scale->ld, r, (__half*)out16->ptr,
+                                                              out16->ld);
+  return check_launch("scale_add16_kernel");
 }
 
 extern "C" int lfsr_tap_gather(const lfsr_tensor* taps, int kh, int kw, const float* bias, const lfsr_tensor* res,

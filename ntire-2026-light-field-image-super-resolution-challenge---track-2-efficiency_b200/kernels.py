@@ -381,8 +381,14 @@ class CudaOps:
                                           bn_shift.data_ptr(), C.byref(as_tensor(amod, "sa.amod")), w0, w1, C.byref(rt),
                                           C.byref(as_tensor(out, "sa.out")), dil, self._stream(x)), "lfsr_sa_modulate")
 
-    def scale_add(self, x, scale, res, out):
+    def scale_add(self, x, scale, res, out, out16=None):
+        """out = x * scale[n][c] + res; with out16 (and out=None) the result is written as fp16 only"""
         rt = as_tensor(res, "scale_add.res") if res is not None else _NULL_T
+        if out16 is not None:
+            N.check(self.lib.lfsr_scale_add16(C.byref(as_tensor(x, "scale_add.x")), C.byref(as_tensor(scale, "scale_add.scale")),
+                                              C.byref(rt), C.byref(as_tensor(out16, "scale_add.out16", f16=True)), self._stream(x)),
+                    "lfsr_scale_add16")
+            return
         N.check(self.lib.lfsr_scale_add(C.byref(as_tensor(x, "scale_add.x")), C.byref(as_tensor(scale, "scale_add.scale")),
                                         C.byref(rt), C.byref(as_tensor(out, "scale_add.out")), self._stream(x)),
                 "lfsr_scale_add")

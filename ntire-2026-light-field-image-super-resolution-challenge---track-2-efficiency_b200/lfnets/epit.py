@@ -94,7 +94,7 @@ class get_model(LFNetBase):
                 ln2=(vec(t.feed_forward["0"].weight), vec(t.feed_forward["0"].bias), t.feed_forward["0"].eps),
                 ff1=lin(t.feed_forward["1"].weight), ff2=lin(t.feed_forward["4"].weight), lin_out=lin(t.linear_out.weight),
                 conv=[c3(af.conv[k]) for k in ("0", "2", "4")], heads=t.num_heads, E=E))
-        pk["up0"] = pc(self.upsampling["0"].weight, tc=True, tc_shuffle=(self.scale, self.scale, N.SHUF_CHANNEL_MAJOR))
+        pk["up0"] = pc(self.upsampling["0"].weight, tc=True, tc16=f16, tc_shuffle=(self.scale, self.scale, N.SHUF_CHANNEL_MAJOR))
         pk["up3"] = pc(self.upsampling["3"].weight, pad=(1, 1), tc=True)
         pk["tail_w"] = tail_table(self.upsampling["3"].weight, self.channels, device)
         return pk
@@ -147,8 +147,14 @@ class get_model(LFNetBase):
                 cur = nxt
         # altblock(buffer) + buffer (:64): the last AltFilter already consumed its own shortcut as the fused residual; this
         # second skip is an exact fp32 add on the elementwise kernel
-        ops.scale_add(cur[0], self._ones(pk, B, dev), fa, fb)
-        self._head(ops, pk, fb, Y, B, H, W)
+        # (fb feeds nothing but the upsampling conv: written as fp16 only, that conv then runs on kind::f16 operands)
+        if pk["up0"].w_tc16 is not None:
+            fbh = self._buf16("fbh", B, H, W, C, dev)
+            ops.scale_add(cur[0], self._ones(pk, B, dev), fa, None, out16=fbh)
+            self._head(ops, pk, fbh, Y, B, H, W)
+        else:
+            ops.scale_add(cur[0], self._ones(pk, B, dev), fa, fb)
+            self._head(ops, pk, fb, Y, B, H, W)
 
     def _basictrans_unfused(self, ops, al, cur, p, B, H, W):
         """BasicTrans as separate launches on the fp32 trunk -> the fp32 token buffer "yb" (EPIT.py:110-128)"""

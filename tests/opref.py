@@ -253,11 +253,11 @@ class RefOps:
         if out16 is not None:
             out16.copy_(out[..., :out16.shape[3]])
 
-    def scale_add(self, x, scale, res, out):
+    def scale_add(self, x, scale, res, out, out16=None):
         y = x * scale
         if res is not None:
             y = y + res
-        out.copy_(y)
+        (out16 if out16 is not None else out).copy_(y)
 
     # -- EPIT token ops ---------------------------------------------------------------------------------
     def layernorm(self, x, gamma, beta, eps, out):
