@@ -121,6 +121,9 @@ def test_interp(ops, ref, mode, block, scale):
 CONV_CASES = [
     # cin cout kh kw stride dil pad extra
     dict(cin=1, cout=54, k=(3, 3), dil=(5, 5), pad=(5, 5), bias=True),
+    dict(cin=1, cout=60, k=(3, 3), dil=(5, 5), pad=(5, 5), bias=True),              # stem, tiled kernel
+    dict(cin=1, cout=64, k=(3, 3), pad=(1, 1), block=(8, 40), act=2),               # ... with view blocking (rows)
+    dict(cin=1, cout=64, k=(3, 3), pad=(1, 1), block=(8, 8)),                       # ... blocks narrower than a tile: per-tap predicates
     dict(cin=18, cout=18, k=(3, 3), dil=(5, 5), pad=(5, 5), bias=True, act=2),
     dict(cin=18, cout=18, k=(5, 5), stride=(5, 5)),
     dict(cin=18, cout=16, k=(1, 1), act=1),
