@@ -653,12 +653,19 @@ pooled_mlp_kernel(TView in, TView out, int pool, const float* __restrict__ w1, c
   const int Pq = pool ? 1 : P;
   float* x = pm_s;                 // [Pq][C]
   float* h = pm_s + Pq * C;        // [Pq][c1]
+  float* ws1 = h + Pq * c1;        // [C][c1] and [c1][c2]: staged with coalesced loads (a dependent chain of ~60 global
+  float* ws2 = ws1 + C * c1;       // loads per output was most of this kernel's 13 us)
+  for (int i = tid; i < C * c1; i += 256) ws1[i] = __ldg(w1 + i);
+  if (w2) for (int i = tid; i < c1 * c2; i += 256) ws2[i] = __ldg(w2 + i);
   const float* src = in.p + (size_t)img * P * in.ld;
+  float* xs = ws2 + (w2 ? c1 * c2 : 0);        // [P][C] raw positions (pool only)
   if (pool) {
+    for (int i = tid; i < P * C; i += 256) { const int q = i / C, c = i - q * C; xs[i] = src[q * in.ld + c]; }
+    __syncthreads();
     const float inv = 1.f / (float)P;
     for (int c = tid; c < C; c += 256) {
       float acc = 0.f;
-      for (int q = 0; q < P; ++q) acc += src[q * in.ld + c];
+      for (int q = 0; q < P; ++q) acc += xs[q * C + c];
       x[c] = acc * inv;
     }
   } else {
@@ -669,7 +676,8 @@ pooled_mlp_kernel(TView in, TView out, int pool, const float* __restrict__ w1, c
   for (int i = tid; i < Pq * c1; i += 256) {
     const int q = i / c1, j = i - q * c1;
     float acc = b1 ? __ldg(b1 + j) : 0.f;
-    for (int c = 0; c < C; ++c) acc = fmaf(x[q * C + c], __ldg(w1 + c * c1 + j), acc);
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) acc = fmaf(x[q * C + c], ws1[c * c1 + j], acc);
     acc = apply_act(acc, act1, 0.f);
     if (w2) h[i] = acc; else dst[q * out.ld + j] = acc;
   }
@@ -678,7 +686,8 @@ pooled_mlp_kernel(TView in, TView out, int pool, const float* __restrict__ w1, c
   for (int i = tid; i < Pq * c2; i += 256) {
     const int q = i / c2, o = i - q * c2;
     float acc = b2 ? __ldg(b2 + o) : 0.f;
-    for (int j = 0; j < c1; ++j) acc = fmaf(h[q * c1 + j], __ldg(w2 + j * c2 + o), acc);
+#pragma unroll 4
+    for (int j = 0; j < c1; ++j) acc = fmaf(h[q * c1 + j], ws2[j * c2 + o], acc);
     dst[q * out.ld + o] = apply_act(acc, act2, 0.f);
   }
 }
@@ -690,7 +699,8 @@ extern "C" int lfsr_pooled_mlp(const lfsr_tensor* in, int pool, const float* w1,
   LFSR_REQUIRE(!w2 || c2 > 0, "lfsr_pooled_mlp: second layer without a width");
   const int P = in->h * in->w, Pq = pool ? 1 : P, cout = w2 ? c2 : c1;
   LFSR_REQUIRE(out->n == in->n && out->h * out->w == Pq && out->c == cout, "lfsr_pooled_mlp: out shape mismatch");
-  const size_t smem = (size_t)Pq * (in->c + c1) * sizeof(float);
+  const size_t smem = ((size_t)Pq * (in->c + c1) + (size_t)in->c * c1 + (w2 ? (size_t)c1 * c2 : 0) + (pool ? (size_t)P * in->c : 0)) *
+                      sizeof(float);
   LFSR_REQUIRE(smem <= 48 * 1024 && in->n <= 0x7fffffff, "lfsr_pooled_mlp: positions x channels too large for one CTA");
   pooled_mlp_kernel<<<in->n, 256, smem, (cudaStream_t)stream>>>(view_of(in), view_of(out), pool ? 1 : 0, w1, b1, c1, act1, w2, b2,
                                                                c2, act2);
