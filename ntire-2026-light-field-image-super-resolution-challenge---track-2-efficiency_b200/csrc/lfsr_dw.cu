@@ -468,6 +468,118 @@ sa_tile_kernel(const __grid_constant__ DwParams p) {
   }
 }
 
+// The same tail as a PERSISTENT kernel: one 512-thread CTA per SM walks the (image, channel chunk, tile) list with two tile
+// buffers, so the TMA loads of tile i+1 (input tile with halo + residual tile) are in flight while tile i is computed. In
+// sa_tile_kernel 30 % of the warp stall samples sit on the barrier of the tile load: two single-buffered CTAs per SM cannot
+// cover a ~2 us load in front of ~2 us of arithmetic.
+constexpr int SA_PTHREADS = 512;        // (1024 threads = four row phases per column: 0.346 vs 0.294 ms - the per-tile setup is paid per thread)
+__global__ void __launch_bounds__(SA_PTHREADS, 1)
+sa_tile_persist_kernel(const __grid_constant__ DwParams p, int tiles_xy, int items, int total) {
+  extern __shared__ __align__(16) float dw_smem[];
+  const int tid = threadIdx.x;
+  const DwBranch& B = p.br[0];
+  const int d = B.dh;
+  const int SH = DW_TH + 2 * d, SW = DW_TW + 2 * d;
+  constexpr int RES_F = DW_TH * DW_TW * DW_CH;
+  const int buf_f = p.tile_floats + (p.res_tma ? RES_F : 0);
+  float* tS0 = dw_smem + ((128u - (dw_smem_u32(dw_smem) & 127u)) & 127u) / 4;
+  float* wS = tS0 + 2 * buf_f;                         // [items][9][16] taps with the BatchNorm scale folded in
+  __shared__ uint64_t bars[2];
+  const int H = p.in.h, W = p.in.w;
+  const uint32_t tx_bytes = (uint32_t)(SH * SW * DW_CH * 4 + (p.res_tma ? RES_F * 4 : 0));
+  auto issue = [&](int t, int b) {                     // one thread: both tensor loads of tile t into buffer b
+    const int xy = t % tiles_xy; const int r_ = t / tiles_xy;
+    const int chunk = r_ % items, img = r_ / items;
+    const int tyi = xy / p.tiles_x;
+    const int ty0 = tyi * DW_TH, tx0 = (xy - tyi * p.tiles_x) * DW_TW;
+    float* dst = tS0 + b * buf_f;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dw_smem_u32(&bars[b])), "r"(tx_bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dw_smem_u32(dst)), "l"(&p.tm[0]), "r"(dw_smem_u32(&bars[b])), "r"(B.in_c0 + chunk * DW_CH), "r"(tx0 - d),
+                   "r"(ty0 - d), "r"(img) : "memory");
+    if (p.res_tma)
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                   ::"r"(dw_smem_u32(dst + p.tile_floats)), "l"(&p.tm[1]), "r"(dw_smem_u32(&bars[b])), "r"(B.out_c0 + chunk * DW_CH),
+                     "r"(tx0), "r"(ty0), "r"(img) : "memory");
+  };
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dw_smem_u32(&bars[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dw_smem_u32(&bars[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if ((int)blockIdx.x < total) issue((int)blockIdx.x, 0);
+  }
+  for (int i = tid; i < items * 9 * DW_CH; i += SA_PTHREADS) {
+    const int c = (i / (9 * DW_CH)) * DW_CH + (i & 15), tap = (i >> 4) % 9;
+    wS[i] = c < B.c ? __ldg(B.w + tap * B.c + c) * __ldg(B.scale + c) : 0.f;
+  }
+  __syncthreads();
+  const int q = tid & 7, lx = (tid >> 3) & 31, ly0 = tid >> 8;
+  const int row_f = SW * DW_CH;
+  const int dyf = d * row_f, dxf = d * DW_CH;
+  const int vh = H / p.amod.h, vw = W / p.amod.w;
+  const int am_row = p.amod.w * p.amod.ld;
+  const float w0 = p.sa_w0, w1 = p.sa_w1;
+  constexpr int RS = SA_PTHREADS / 256;            // row phases
+  const int out_step = RS * p.out.w * p.out.ld, o16_step = RS * p.out.w * p.o16_ld;
+  int it = 0;
+  for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    const int b = it & 1;
+    if (tid == 0 && t + (int)gridDim.x < total) issue(t + (int)gridDim.x, b ^ 1);
+    const int xy = t % tiles_xy; const int r_ = t / tiles_xy;
+    const int chunk = r_ % items, img = r_ / items;
+    const int tyi = xy / p.tiles_x;
+    const int ty0 = tyi * DW_TH, tx0 = (xy - tyi * p.tiles_x) * DW_TW;
+    const int wofs = chunk * DW_CH;
+    const int ox = tx0 + lx;
+    const bool live = ox < W && wofs + q * 2 < B.c;
+    const int c2 = B.out_c0 + wofs + q * 2;
+    const float* tS = tS0 + b * buf_f;
+    dw_mbar_wait(&bars[b], (uint32_t)(it >> 1) & 1u);
+    if (live) {
+      f32x2 w[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) w[k] = *reinterpret_cast<const f32x2*>(wS + (chunk * 9 + k) * DW_CH + q * 2);
+      const f32x2 sh = *reinterpret_cast<const f32x2*>(B.shift + wofs + q * 2);
+      float* outI = p.out.p + (size_t)img * p.out.h * p.out.w * p.out.ld;
+      const float* amI = p.amod.p + (size_t)img * p.amod.h * p.amod.w * p.amod.ld + (ox / vw) * p.amod.ld + c2;
+      const int rows_here = min(DW_TH, H - ty0);
+      int out_o = ((ty0 + ly0) * p.out.w + ox) * p.out.ld + c2;
+      const bool do16 = p.o16 && c2 < p.o16_c;
+      __half* o16I = p.o16 + (size_t)img * p.out.h * p.out.w * p.o16_ld;
+      int o16_o = ((ty0 + ly0) * p.out.w + ox) * p.o16_ld + c2;
+      const float* base = tS + ly0 * row_f + lx * DW_CH + q * 2;
+      const float* resS = tS + p.tile_floats + (ly0 * DW_TW + lx) * DW_CH + q * 2;
+      int ay = (ty0 + ly0) / vh, arem = (ty0 + ly0) - ay * vh;
+#pragma unroll 2
+      for (int r = ly0; r < rows_here; r += RS) {
+        const float2 ac = __ldg(reinterpret_cast<const float2*>(amI + ay * am_row));
+        float2 rc = make_float2(0.f, 0.f);
+        if (p.res_tma) rc = *reinterpret_cast<const float2*>(resS);
+        f32x2 acc = sh;
+        float2 xc;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const f32x2 v = *reinterpret_cast<const f32x2*>(base + ky * dyf + kx * dxf);
+            if (ky == 1 && kx == 1) unpack2(v, xc.x, xc.y);
+            acc = fma2(v, w[ky * 3 + kx], acc);
+          }
+        float2 a;
+        unpack2(acc, a.x, a.y);
+        a.x = fmaf(xc.x, fmaf(w0, sa_sigmoid(a.x), w1 * ac.x), rc.x);
+        a.y = fmaf(xc.y, fmaf(w0, sa_sigmoid(a.y), w1 * ac.y), rc.y);
+        *reinterpret_cast<float2*>(outI + out_o) = a;
+        if (do16) *reinterpret_cast<__half2*>(o16I + o16_o) = __floats2half2_rn(a.x, a.y);
+        base += RS * row_f; resS += RS * DW_TW * DW_CH; out_o += out_step; o16_o += o16_step;
+        arem += RS;
+        while (arem >= vh) { arem -= vh; ++ay; }
+      }
+    }
+    __syncthreads();          // buffer b is free for the load issued at the top of the next iteration
+  }
+}
+
 typedef CUresult (*DwEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -623,6 +735,23 @@ static int dw_launch(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_d
                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
         p.res_tma = 1;
         smem_sa += DW_TH * DW_TW * DW_CH * 4;
+      }
+    }
+    const int items_sa = ceil_div(br[0].c, DW_CH);
+    const size_t smem_p = 2 * ((size_t)tile_floats + (p.res_tma ? DW_TH * DW_TW * DW_CH : 0)) * 4 + (size_t)items_sa * 9 * DW_CH * 4 + 128;
+    if ((p.res_tma || !p.res.p) && smem_p <= 225 * 1024 && !dbg_env("LFSR_SA_NO_PERSIST")) {
+      static DevOnce once_sp;
+      if (once_sp.need()) {
+        if (opt_in_smem(sa_tile_persist_kernel, 225 * 1024, "lfsr_sa_modulate")) return LFSR_ERR_CUDA;
+        once_sp.done();
+      }
+      const int tiles_xy = p.tiles_x * ceil_div(in->h, DW_TH);
+      const long long total = (long long)tiles_xy * items_sa * in->n;
+      if (total <= 0x7fffffffLL) {
+        const int nsm = sm_count_current();
+        const int g = total < nsm ? (int)total : nsm;
+        sa_tile_persist_kernel<<<g, SA_PTHREADS, smem_p, st>>>(p, tiles_xy, items_sa, (int)total);
+        return check_launch("sa_tile_persist_kernel");
       }
     }
     static DevOnce once_sa;
