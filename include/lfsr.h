@@ -267,6 +267,11 @@ int lfsr_sa_modulate(const lfsr_tensor* x, const float* dw_w, const float* bn_sc
 int lfsr_sa_modulate16(const lfsr_tensor* x, const float* dw_w, const float* bn_scale,
                        const float* bn_shift, const lfsr_tensor* amod, float w0, float w1,
                        const lfsr_tensor* res, const lfsr_tensor* out, const lfsr_tensor* out16, int dil, void* stream);
+/* the same, leaving channels [skip_lo, skip_hi) (whole quads) out of the fp16 copy: the Track-2 plan keeps ONE fp16 copy of the
+ * trunk of which only channels 0..17 (spatial branch) and 40..57 (EPI branch) are ever read */
+int lfsr_sa_modulate16w(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
+                        const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res, const lfsr_tensor* out,
+                        const lfsr_tensor* out16, int skip_lo, int skip_hi, int dil, void* stream);
 
 /* out = x * scale[n][c] + res  (ChannelAttention + block residual, MyEfficientLFNetV4_5.py:148,291-299);
  * scale is an [n,1,1,c] tensor view, res may be NULL. */

@@ -121,6 +121,7 @@ SIGNATURES = {
     "lfsr_ang_expand": (_I, [_TP, _P, _TP, _TP, _I, _I, C.c_float, C.c_float, _P]),
     "lfsr_sa_modulate": (_I, [_TP, _P, _P, _P, _TP, C.c_float, C.c_float, _TP, _TP, _I, _P]),
     "lfsr_sa_modulate16": (_I, [_TP, _P, _P, _P, _TP, C.c_float, C.c_float, _TP, _TP, _TP, _I, _P]),
+    "lfsr_sa_modulate16w": (_I, [_TP, _P, _P, _P, _TP, C.c_float, C.c_float, _TP, _TP, _TP, _I, _I, _I, _P]),
     "lfsr_scale_add": (_I, [_TP, _TP, _TP, _TP, _P]),
     "lfsr_scale_add16": (_I, [_TP, _TP, _TP, _TP, _P]),
     "lfsr_layernorm": (_I, [_TP, _P, _P, C.c_float, _TP, _P]),

@@ -70,6 +70,7 @@ struct DwParams {
   float sa_w0, sa_w1;
   __half* o16;                 // SA tail: optional fp16 copy of output channels [0, o16_c) (operand of the next tensor-core layer)
   int o16_ld, o16_c;
+  int o16_skip_lo, o16_skip_hi;   // channels in [lo, hi) are left out of the fp16 copy (nobody reads them)
   TView amod, res;
   // use_tma: the halo'd tile of branch b is fetched by ONE thread with a 4-D tensor load through tm[b] (box = 16 channels
   // x tile+halo, out-of-image elements zero filled) instead of ~25 cp.async per thread: staging cost as many
@@ -174,7 +175,7 @@ __device__ __forceinline__ void dw_compute(const DwParams& p, const DwBranch& B,
       }
     }
     *reinterpret_cast<float4*>(p.out.p + p.out.pix(img, oy, ox) + cout0 + q * 4) = acc;
-    if (p.o16 && cout0 + q * 4 < p.o16_c) {
+    if (p.o16 && cout0 + q * 4 < p.o16_c && !(cout0 + q * 4 >= p.o16_skip_lo && cout0 + q * 4 < p.o16_skip_hi)) {
       const __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
       uint2 v;
       v.x = *reinterpret_cast<const uint32_t*>(&h0); v.y = *reinterpret_cast<const uint32_t*>(&h1);
@@ -423,7 +424,7 @@ sa_tile_kernel(const __grid_constant__ DwParams p) {
   const int res_step = 2 * p.res.w * p.res.ld, out_step = 2 * p.out.w * p.out.ld;
   int res_o = ((ty0 + ly0) * p.res.w + ox) * p.res.ld + c2;
   int out_o = ((ty0 + ly0) * p.out.w + ox) * p.out.ld + c2;
-  const bool do16 = p.o16 && c2 < p.o16_c;
+  const bool do16 = p.o16 && c2 < p.o16_c && !(c2 >= p.o16_skip_lo && c2 < p.o16_skip_hi);
   __half* o16I = p.o16 + (size_t)img * p.out.h * p.out.w * p.o16_ld;
   int o16_o = ((ty0 + ly0) * p.out.w + ox) * p.o16_ld + c2;
   const int o16_step = 2 * p.out.w * p.o16_ld;
@@ -544,7 +545,7 @@ sa_tile_persist_kernel(const __grid_constant__ DwParams p, int tiles_xy, int ite
       const float* amI = p.amod.p + (size_t)img * p.amod.h * p.amod.w * p.amod.ld + (ox / vw) * p.amod.ld + c2;
       const int rows_here = min(DW_TH, H - ty0);
       int out_o = ((ty0 + ly0) * p.out.w + ox) * p.out.ld + c2;
-      const bool do16 = p.o16 && c2 < p.o16_c;
+      const bool do16 = p.o16 && c2 < p.o16_c && !(c2 >= p.o16_skip_lo && c2 < p.o16_skip_hi);
       __half* o16I = p.o16 + (size_t)img * p.out.h * p.out.w * p.o16_ld;
       int o16_o = ((ty0 + ly0) * p.out.w + ox) * p.o16_ld + c2;
       const float* base = tS + ly0 * row_f + lx * DW_CH + q * 2;
@@ -615,7 +616,7 @@ static bool dw_tile_ok(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr
 using namespace lfsr;
 
 // shared by lfsr_dwconv_multi and lfsr_sa_modulate (sa != null: the SA-modulator tail on a single branch)
-struct SaTail { float w0, w1; const lfsr_tensor* amod; const lfsr_tensor* res; const lfsr_tensor* out16; };
+struct SaTail { float w0, w1; const lfsr_tensor* amod; const lfsr_tensor* res; const lfsr_tensor* out16; int skip_lo, skip_hi; };
 static int dw_launch(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_dw_branch* br, int nbr, const SaTail* sa,
                      bool* used_tile, void* stream) {
   LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && br && nbr > 0, "lfsr_dwconv_multi: null/invalid argument");
@@ -654,8 +655,8 @@ static int dw_launch(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_d
   p.sa_w0 = sa ? sa->w0 : 0.f; p.sa_w1 = sa ? sa->w1 : 0.f;
   p.amod = sa ? view_of(sa->amod) : null_view();
   p.res = sa && sa->res && sa->res->ptr ? view_of(sa->res) : null_view();
-  p.o16 = nullptr; p.o16_ld = 0; p.o16_c = 0;
-  if (sa && sa->out16 && sa->out16->ptr) { p.o16 = (__half*)sa->out16->ptr; p.o16_ld = (int)sa->out16->ld; p.o16_c = sa->out16->c; }
+  p.o16 = nullptr; p.o16_ld = 0; p.o16_c = 0; p.o16_skip_lo = p.o16_skip_hi = 0;
+  if (sa && sa->out16 && sa->out16->ptr) { p.o16 = (__half*)sa->out16->ptr; p.o16_ld = (int)sa->out16->ld; p.o16_c = sa->out16->c; p.o16_skip_lo = sa->skip_lo; p.o16_skip_hi = sa->skip_hi; }
   int items = 0, w_floats = 0;
   size_t tile_floats = 0;
   for (int i = 0; i < nbr; ++i) {
@@ -775,7 +776,7 @@ extern "C" int lfsr_dwconv_multi(const lfsr_tensor* in, const lfsr_tensor* out, 
 // SA-modulator tail on the tiled depthwise kernel; *handled = 0 when the tensors do not qualify (caller falls back)
 int lfsr_sa_modulate_tiled(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
                            const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res, const lfsr_tensor* out, int dil,
-                           int* handled, void* stream, const lfsr_tensor* out16) {
+                           int* handled, void* stream, const lfsr_tensor* out16, int skip_lo, int skip_hi) {
   lfsr_dw_branch b;
   b.w = dw_w; b.scale = bn_scale; b.shift = bn_shift;
   b.kh = 3; b.kw = 3; b.dil_h = dil; b.dil_w = dil;
@@ -784,7 +785,7 @@ int lfsr_sa_modulate_tiled(const lfsr_tensor* x, const float* dw_w, const float*
   auto al = [](const lfsr_tensor* t) { return t && t->ptr && t->ld % 4 == 0 && (((uintptr_t)t->ptr) & 15) == 0; };
   *handled = 0;
   if (!al(amod) || (res && res->ptr && !al(res))) return LFSR_OK;
-  SaTail sa{w0, w1, amod, res, out16};
+  SaTail sa{w0, w1, amod, res, out16, skip_lo, skip_hi};
   bool used = false;
   int rc = dw_launch(x, out, &b, 1, &sa, &used, stream);
   *handled = used ? 1 : 0;

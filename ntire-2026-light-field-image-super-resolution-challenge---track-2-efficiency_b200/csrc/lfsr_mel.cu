@@ -5,6 +5,7 @@
 //   * mel_epi_branch: the whole MultiScaleEPIBlock (MyEfficientLFNet.py:278-327) in one pass:
 //     dw 1xK / Kx1 / 3x3-dilated -> 1x1 + LReLU each -> concat -> 1x1 + LReLU. One thread per pixel.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <string.h>
 #include <mutex>
 #include "lfsr_common.cuh"
@@ -525,23 +526,37 @@ struct EpiMmaArgs {
   int KL, dil, halo, ntap;
   int P, G0, R, npx;         // padded pitch, first MMA row (flattened padded position), output rows per tile, staged pixels
   float slope;
-  int tiles_x, tiles_y;
+  int tiles_x, tiles_y, total_tiles;
 };
 
-// 9 warps: 0..7 = workers (thread t <-> MMA row t & 127 of block t >> 7), 8 = MMA issuer. The issuer runs its whole program
-// inside ONE elect block (tcgen05 instructions issued from `if (lane == 0)` are wrapped in ELECT/branch loops by ptxas, and
-// tcgen05.commit only tracks the MMAs of the committing thread); hand-offs are mbarriers, never __syncthreads.
+// Persistent, one CTA per SM, 10 warps: 0..7 = workers (thread t <-> MMA row t & 127 of block t >> 7), 8 = MMA issuer, 9 = TMA
+// producer. The issuer and the producer run their whole programs inside ONE elect block each (tcgen05 instructions issued from
+// `if (lane == 0)` are wrapped in ELECT/branch loops by ptxas, and tcgen05.commit only tracks the MMAs of the committing
+// thread); every hand-off is an mbarrier. Two input buffers and two halves of tensor memory: the tap MMAs of tile i+1 run
+// while the workers drain tile i, and the TMA loads of tile i+2 are issued as soon as the MMAs of tile i have retired.
+//   issuer, tile i:   taps(i) -> [stage 2 of tile i-1] -> extra(i) + commit D1(i) -> commit "buffer free"
+//   workers, tile i:  extras(i) -> [epilogue 2 of tile i-1] -> epilogue 1 of tile i
 #ifdef LFSR_DEBUG_HOOKS
-__device__ long long* g_em_dbg = nullptr;        // probe build: per-CTA phase time stamps (profiles/probe_epi_phases.py)
-#define EM_STAMP(slot) do { if (g_em_dbg && blockIdx.x < 4096) g_em_dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+__device__ long long* g_em_dbg = nullptr;        // probe build: time stamps of the issuer at the start of its first 16 tiles
+#define EM_STAMP(slot) do { if (g_em_dbg && blockIdx.x < 4096 && (slot) < 16) g_em_dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
 #else
 #define EM_STAMP(slot) do { } while (0)
 #endif
-constexpr int kEmThreads = 288;
-enum EmBar { EB_IMG = 0, EB_X, EB_IN, EB_D1, EB_A2 = EB_D1 + 2, EB_D2 = EB_A2 + 2, EB_COUNT = EB_D2 + 2 };
+constexpr int kEmThreads = 320;
+enum EmBar { EB_IMG = 0, EB_XF, EB_XE = EB_XF + 2, EB_AEX = EB_XE + 2, EB_D1, EB_A2 = EB_D1 + 2, EB_D2 = EB_A2 + 2, EB_TE = EB_D2 + 2,
+             EB_COUNT = EB_TE + 2 };
 
-__global__ void __launch_bounds__(384, 2)      // (9 warps are allocated registers like 12: cap at 80 so two CTAs fit)
-mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const EpiMmaArgs a) {
+struct EmTile { int img, ty0, tx0; };
+__device__ __forceinline__ EmTile em_decode(const EpiMmaArgs& a, int t) {
+  EmTile e;
+  e.tx0 = (t % a.tiles_x) * em::TW; t /= a.tiles_x;
+  e.ty0 = (t % a.tiles_y) * a.R;
+  e.img = t / a.tiles_y;
+  return e;
+}
+
+__global__ void __launch_bounds__(384, 1)
+mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmE, const EpiMmaArgs a) {
   using namespace em;
   extern __shared__ uint8_t em_raw[];
   const uint32_t raw = smem_u32(em_raw);
@@ -552,37 +567,31 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const EpiMmaA
   uint8_t* Bex = Bt + ntap * kTapB;
   uint8_t* B2 = Bt + b2_offset(ntap);
   const float2* exw = reinterpret_cast<const float2*>(B2 + kB2);
-  uint8_t* T16 = smem + ((img_bytes + 1023) & ~1023);  // [npx][16 fp16]
-  float2* T2 = reinterpret_cast<float2*>(T16 + a.npx * 32);      // [npx] channels 16, 17 (fp32)
-  uint8_t* Aex = reinterpret_cast<uint8_t*>(T2 + a.npx);         // 2 x [128][16 fp16]   (npx is a multiple of 32: 256-byte aligned)
-  uint8_t* A2 = smem + (((uint32_t)(Aex + 2 * kAex - smem) + 1023u) & ~1023u);     // 2 x [128][64 fp16]
+  const int t16_bytes = (a.npx * 32 + 1023) & ~1023, t2_bytes = (a.npx * 16 + 1023) & ~1023;
+  uint8_t* T16 = smem + ((img_bytes + 1023) & ~1023);  // 2 x [npx][16 fp16]  channels 0..15, SWIZZLE_32B rows
+  uint8_t* T2h = T16 + 2 * t16_bytes;                  // 2 x [npx][8 fp16]   channels 16..23 (16, 17 used)
+  uint8_t* Aex = T2h + 2 * t2_bytes;                   // 2 blocks x [128][16 fp16]
+  uint8_t* A2 = Aex + 2 * kAex;                        // 2 blocks x [128][64 fp16]
   uint64_t* bars = reinterpret_cast<uint64_t*>(A2 + 2 * kA2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + EB_COUNT);
   int* tapoff = reinterpret_cast<int*>(tmem_slot + 1);           // byte shift of the A view per tap
-  uint64_t* adesc = reinterpret_cast<uint64_t*>(bars + 32);      // [2][kMaxTaps] A descriptors of the tap MMAs (precomputed: the
-                                                                 // issuing lane retires ~1 dependent instruction per 5 cycles)
+  uint64_t* adesc = reinterpret_cast<uint64_t*>(bars + 48);      // [2 buffers][2 blocks][kMaxTaps] A descriptors of the tap MMAs
   const int tid = threadIdx.x, warp = tid >> 5;
-  int t_ = blockIdx.x;
-  const int tx0 = (t_ % a.tiles_x) * TW; t_ /= a.tiles_x;
-  const int ty0 = (t_ % a.tiles_y) * a.R;
-  const int img = t_ / a.tiles_y;
   const int P = a.P, halo = a.halo, half = a.KL / 2;
+  const int total = a.total_tiles;
+  const int n_my = ((int)total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (tid == 0) {
-    EM_STAMP(0);
     mbar_init(bars + EB_IMG, 1);
-    mbar_init(bars + EB_X, 1);
-    mbar_init(bars + EB_IN, 256);
-    for (int m = 0; m < 2; ++m) { mbar_init(bars + EB_D1 + m, 1); mbar_init(bars + EB_A2 + m, 128); mbar_init(bars + EB_D2 + m, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bars + EB_XF + i, 1); mbar_init(bars + EB_XE + i, 1);
+      mbar_init(bars + EB_D1 + i, 1); mbar_init(bars + EB_A2 + i, 128); mbar_init(bars + EB_D2 + i, 1);
+      mbar_init(bars + EB_TE + i, 256);
+    }
+    mbar_init(bars + EB_AEX, 256);
     fence_barrier_init();
     mbar_expect_tx(bars + EB_IMG, (uint32_t)img_bytes);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(Bt)), "l"(a.packed), "r"((uint32_t)img_bytes), "r"(smem_u32(bars + EB_IMG)) : "memory");
-    // the fp16 input tile with halo: channels 0..15 of the (R + 2 halo) x P pixels, one tensor load, out-of-image pixels
-    // zero filled (= the depthwise convs' padding), 32-byte pixel rows swizzled as the MMA descriptors expect
-    mbar_expect_tx(bars + EB_X, (uint32_t)((a.R + 2 * halo) * P * 32));
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(smem_u32(T16)), "l"(&tmX), "r"(smem_u32(bars + EB_X)), "r"(0), "r"(tx0 - halo), "r"(ty0 - halo), "r"(img)
-                 : "memory");
   }
   if (tid < ntap) {
     int dy = 0, dx = 0;
@@ -590,175 +599,193 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const EpiMmaA
     else if (tid < 2 * a.KL) dy = tid - a.KL - half;
     else { const int k = tid - 2 * a.KL; dy = (k / 3 - 1) * a.dil; dx = (k % 3 - 1) * a.dil; }
     tapoff[tid] = (dy * P + dx) * 32;
-    const uint32_t a0 = smem_u32(T16) + (uint32_t)a.G0 * 32u + (uint32_t)((dy * P + dx) * 32);
-    adesc[tid] = desc32(a0);
-    adesc[kMaxTaps + tid] = desc32(a0 + 128u * 32u);
+    for (int bf = 0; bf < 2; ++bf)
+      for (int m = 0; m < 2; ++m)
+        adesc[(bf * 2 + m) * kMaxTaps + tid] =
+            desc32(smem_u32(T16) + (uint32_t)(bf * t16_bytes) + (uint32_t)(a.G0 + m * 128) * 32u + (uint32_t)((dy * P + dx) * 32));
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t t16 = smem_u32(T16);
-  if (tid == 0) EM_STAMP(1);
 
-  if (warp == 8) {
+  if (warp == 9) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      const uint32_t tx = (uint32_t)((a.R + 2 * halo) * P * (32 + 16));
+      for (int i = 0; i < n_my; ++i) {
+        const int bf = i & 1;
+        const EmTile e = em_decode(a, (int)blockIdx.x + i * (int)gridDim.x);
+        mbar_wait(bars + EB_XE + bf, (((uint32_t)i >> 1) & 1u) ^ 1u);        // the MMAs that read this buffer have retired
+        mbar_expect_tx(bars + EB_XF + bf, tx);
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(smem_u32(T16 + bf * t16_bytes)), "l"(&tmX), "r"(smem_u32(bars + EB_XF + bf)), "r"(0), "r"(e.tx0 - halo),
+                       "r"(e.ty0 - halo), "r"(e.img) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(smem_u32(T2h + bf * t2_bytes)), "l"(&tmE), "r"(smem_u32(bars + EB_XF + bf)), "r"(0), "r"(e.tx0 - halo),
+                       "r"(e.ty0 - halo), "r"(e.img) : "memory");
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
     // ================= MMA issuer =================
     if (elect_one()) {
       const uint32_t id1 = make_idesc(0, 32), idx = make_idesc(0, 96);
       const uint64_t dbt = desc32(smem_u32(Bt)), dbx = desc32(smem_u32(Bex)), db2 = make_smem_desc(smem_u32(B2));
       const int KL = a.KL;
-      mbar_wait(bars + EB_IMG, 0);
-      EM_STAMP(8);
-      mbar_wait(bars + EB_X, 0);
-      EM_STAMP(9);
-      mbar_wait(bars + EB_IN, 0);
-      EM_STAMP(10);
-      tc_fence_after();
+      auto stage2 = [&](int i) {                     // fuse GEMM of tile i, block by block as its operand rows arrive
+        const uint32_t th = tmem + (uint32_t)((i & 1) * 256);
 #pragma unroll 1
-      for (int m = 0; m < 2; ++m) {
-        const uint64_t* ad = adesc + m * kMaxTaps;
-        const uint32_t d0 = tmem + (uint32_t)(m * 96);
-        int t = 0;
-#pragma unroll 1
-        for (int br = 0; br < 3; ++br) {
-          const int n = br == 2 ? 9 : KL;
-          const uint32_t d = d0 + (uint32_t)(br * 32);
-          umma_f16<0>(d, ad[t], dbt + (uint64_t)(t * (kTapB >> 4)), id1);
-          ++t;
-#pragma unroll 4
-          for (int k = 1; k < n; ++k, ++t) umma_f16<1>(d, ad[t], dbt + (uint64_t)(t * (kTapB >> 4)), id1);
+        for (int m = 0; m < 2; ++m) {
+          mbar_wait(bars + EB_A2 + m, (uint32_t)i & 1u);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(A2) + m * kA2);
+          const uint32_t d = th + (uint32_t)(m * 96);
+          umma_f16<0>(d, da, db2, id1);
+          umma_f16<1>(d, da + 2, db2 + 2, id1);
+          umma_f16<1>(d, da + 4, db2 + 4, id1);
+          umma_f16<1>(d, da + 6, db2 + 6, id1);
+          umma_commit(bars + EB_D2 + m);
         }
-        umma_f16<1>(d0, desc32(smem_u32(Aex) + (uint32_t)m * kAex), dbx, idx);
-        umma_commit(bars + EB_D1 + m);
-        EM_STAMP(11 + m);
-      }
-#pragma unroll 1
-      for (int m = 0; m < 2; ++m) {
-        mbar_wait(bars + EB_A2 + m, 0);
+      };
+      mbar_wait(bars + EB_IMG, 0);
+      for (int i = 0; i < n_my; ++i) {
+        const int bf = i & 1;
+        const uint32_t th = tmem + (uint32_t)(bf * 256);
+        EM_STAMP(i);
+        mbar_wait(bars + EB_XF + bf, ((uint32_t)i >> 1) & 1u);              // input tile landed
+        mbar_wait(bars + EB_TE + bf, (((uint32_t)i >> 1) & 1u) ^ 1u);        // this half of tensor memory was drained (tile i-2)
         tc_fence_after();
-        const uint64_t da = make_smem_desc(smem_u32(A2) + m * kA2);
-        const uint32_t d = tmem + (uint32_t)(m * 96);
-        umma_f16<0>(d, da, db2, id1);
-        umma_f16<1>(d, da + 2, db2 + 2, id1);
-        umma_f16<1>(d, da + 4, db2 + 4, id1);
-        umma_f16<1>(d, da + 6, db2 + 6, id1);
-        umma_commit(bars + EB_D2 + m);
-        EM_STAMP(13 + m);
+#pragma unroll 1
+        for (int m = 0; m < 2; ++m) {
+          const uint64_t* ad = adesc + (bf * 2 + m) * kMaxTaps;
+          const uint32_t d0 = th + (uint32_t)(m * 96);
+          int t = 0;
+#pragma unroll 1
+          for (int br = 0; br < 3; ++br) {
+            const int n = br == 2 ? 9 : KL;
+            const uint32_t d = d0 + (uint32_t)(br * 32);
+            umma_f16<0>(d, ad[t], dbt + (uint64_t)(t * (kTapB >> 4)), id1);
+            ++t;
+#pragma unroll 4
+            for (int k = 1; k < n; ++k, ++t) umma_f16<1>(d, ad[t], dbt + (uint64_t)(t * (kTapB >> 4)), id1);
+          }
+        }
+        if (i > 0) stage2(i - 1);
+        mbar_wait(bars + EB_AEX, (uint32_t)i & 1u);                          // channels 16, 17 of this tile are in Aex
+        tc_fence_after();
+#pragma unroll 1
+        for (int m = 0; m < 2; ++m) {
+          umma_f16<1>(th + (uint32_t)(m * 96), desc32(smem_u32(Aex) + (uint32_t)m * kAex), dbx, idx);
+          umma_commit(bars + EB_D1 + m);
+        }
+        umma_commit(bars + EB_XE + bf);                                      // input buffer free once all of this has retired
       }
+      if (n_my > 0) stage2(n_my - 1);
     }
     __syncwarp();
   } else {
     // ================= workers =================
-    // channels 16, 17 of the tile in fp32 (the fp16 MMA operand rows come by TMA); rows past the staged ones only feed
-    // MMA rows whose results are dropped
-    const int rows_staged = a.R + 2 * halo;
-#pragma unroll 1
-    for (int i0 = tid; i0 < a.npx; i0 += 4 * 256) {       // four pixels per pass: their loads are in flight together
-      float2 e[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * 256;
-        const int ly = i / P, lx = i - ly * P;
-        const int iy = ty0 - halo + ly, ix = tx0 - halo + lx;
-        e[u] = make_float2(0.f, 0.f);
-        if (i < a.npx && ly < rows_staged && iy >= 0 && iy < a.in.h && ix >= 0 && ix < a.in.w)
-          e[u] = __ldg(reinterpret_cast<const float2*>(a.in.p + a.in.pix(img, iy, ix) + 16));
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (i0 + u * 256 < a.npx) T2[i0 + u * 256] = e[u];
-    }
-    if (tid == 0) EM_STAMP(2);
-    named_bar_sync(1, 256);                            // T2 complete (the fp16 tile is only read by the MMAs)
     const int m_blk = tid >> 7, r_blk = tid & 127;
     const int g = a.G0 + m_blk * 128 + r_blk;         // flattened padded position of this thread's pixel (= its MMA row)
-    {
-      mbar_wait(bars + EB_IMG, 0);                     // the extra-channel tap weights live in the operand image
-      f32x2 acc[3];
-      acc[0] = acc[1] = acc[2] = pack2(0.f, 0.f);
-      const float2* tp = T2 + g;
-      int t = 0;
-#pragma unroll
-      for (int br = 0; br < 3; ++br) {
-        const int n = br == 2 ? 9 : a.KL;
-        f32x2 s0 = pack2(0.f, 0.f), s1 = s0;
-        int k = 0;
-#pragma unroll 4
-        for (; k + 1 < n; k += 2, t += 2) {        // two independent chains, loads of several taps in flight
-          s0 = fma2(*reinterpret_cast<const f32x2*>(tp + (tapoff[t] >> 5)), *reinterpret_cast<const f32x2*>(exw + t), s0);
-          s1 = fma2(*reinterpret_cast<const f32x2*>(tp + (tapoff[t + 1] >> 5)), *reinterpret_cast<const f32x2*>(exw + t + 1), s1);
-        }
-        if (k < n) { s0 = fma2(*reinterpret_cast<const f32x2*>(tp + (tapoff[t] >> 5)), *reinterpret_cast<const f32x2*>(exw + t), s0); ++t; }
-        float a0, a1, b0, b1;
-        unpack2(s0, a0, a1); unpack2(s1, b0, b1);
-        acc[br] = pack2(a0 + b0, a1 + b1);
-      }
-      float x0, x1, x2, x3, x4, x5;
-      unpack2(acc[0], x0, x1); unpack2(acc[1], x2, x3); unpack2(acc[2], x4, x5);
-      const uint32_t row = smem_u32(Aex) + (uint32_t)m_blk * kAex + (uint32_t)r_blk * 32u;
-      st_shared_v4(unit32(row, 0), pack_f16x2(x0, x1), pack_f16x2(x2, x3), pack_f16x2(x4, x5), 0u);
-      st_shared_v4(unit32(row, 1), 0u, 0u, 0u, 0u);
-    }
-    fence_proxy_async();
-    if (tid == 0) EM_STAMP(3);
-    mbar_arrive(bars + EB_IN);
-    // ---- stage 2 operand: LReLU(stage 1) as fp16
-    mbar_wait(bars + EB_D1 + m_blk, 0);
-    if (tid == 0) EM_STAMP(4);
-    tc_fence_after();
-    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)m_blk * 96u;
+    const int gy = g / P, gx = g - gy * P;
+    const int ty = gy - halo, tx = gx - halo;
+    const bool in_tile = tx >= 0 && tx < TW && ty >= 0 && ty < a.R;
     const uint32_t a2_row = smem_u32(A2) + (uint32_t)m_blk * kA2 + (uint32_t)r_blk * 128u;
     const uint32_t swz = (uint32_t)r_blk & 7u;
-    {
-      uint32_t pk[32];
-#pragma unroll
-      for (int i = 27; i < 32; ++i) pk[i] = 0u;
-#pragma unroll
-      for (int br = 0; br < 3; ++br) {
-        float s[32];
-        tmem_ld32(tlane + br * 32, s);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          float x0 = s[2 * i], x1 = s[2 * i + 1];
-          x0 = x0 > 0.f ? x0 : x0 * a.slope;
-          x1 = x1 > 0.f ? x1 : x1 * a.slope;
-          pk[br * 9 + i] = pack_f16x2(x0, x1);
-        }
-      }
-      et::store_row(a2_row, swz, pk);
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    if (tid == 0) EM_STAMP(5);
-    mbar_arrive(bars + EB_A2 + m_blk);
-    mbar_wait(bars + EB_D2 + m_blk, 0);
-    if (tid == 0) EM_STAMP(6);
-    tc_fence_after();
-    {
+    const uint32_t aex_row = smem_u32(Aex) + (uint32_t)m_blk * kAex + (uint32_t)r_blk * 32u;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)m_blk * 96u;
+    auto epilogue2 = [&](int i) {                      // LReLU(fuse) of tile i -> global
+      const EmTile e = em_decode(a, (int)blockIdx.x + i * (int)gridDim.x);
+      mbar_wait(bars + EB_D2 + m_blk, (uint32_t)i & 1u);
+      tc_fence_after();
       float o[32];
-      tmem_ld32(tlane, o);
+      tmem_ld32(lane_base + (uint32_t)((i & 1) * 256), o);
       tmem_wait_ld();
-      const int gy = g / P, gx = g - gy * P;
-      const int ty = gy - halo, tx = gx - halo;
-      const int oy = ty0 + ty, ox = tx0 + tx;
-      if (tx >= 0 && tx < TW && ty >= 0 && ty < a.R && ox < a.in.w && oy < a.in.h) {
-        float* dst = a.out.p + a.out.pix(img, oy, ox);
+      tc_fence_before();
+      mbar_arrive(bars + EB_TE + (i & 1));             // this half of tensor memory may be overwritten
+      const int oy = e.ty0 + ty, ox = e.tx0 + tx;
+      if (in_tile && ox < a.in.w && oy < a.in.h) {
+        float* dst = a.out.p + a.out.pix(e.img, oy, ox);
 #pragma unroll
-        for (int i = 0; i < EC / 2; ++i) {
-          float x0 = o[2 * i], x1 = o[2 * i + 1];
+        for (int k = 0; k < EC / 2; ++k) {
+          float x0 = o[2 * k], x1 = o[2 * k + 1];
           x0 = x0 > 0.f ? x0 : x0 * a.slope;
           x1 = x1 > 0.f ? x1 : x1 * a.slope;
-          reinterpret_cast<float2*>(dst)[i] = make_float2(x0, x1);
+          reinterpret_cast<float2*>(dst)[k] = make_float2(x0, x1);
         }
       }
+    };
+    mbar_wait(bars + EB_IMG, 0);                       // the extra-channel tap weights live in the operand image
+    for (int i = 0; i < n_my; ++i) {
+      const int bf = i & 1;
+      // ---- channels 16, 17 on the CUDA cores
+      mbar_wait(bars + EB_XF + bf, ((uint32_t)i >> 1) & 1u);
+      {
+        const __half2* tp = reinterpret_cast<const __half2*>(T2h + bf * t2_bytes) + (size_t)g * 4;     // 8 halves per pixel
+        f32x2 acc[3];
+        int t = 0;
+#pragma unroll
+        for (int br = 0; br < 3; ++br) {
+          const int n = br == 2 ? 9 : a.KL;
+          f32x2 s0 = pack2(0.f, 0.f), s1 = s0;
+          int k = 0;
+#pragma unroll 4
+          for (; k + 1 < n; k += 2, t += 2) {
+            const float2 v0 = __half22float2(tp[(tapoff[t] >> 5) * 4]), v1 = __half22float2(tp[(tapoff[t + 1] >> 5) * 4]);
+            s0 = fma2(pack2(v0.x, v0.y), *reinterpret_cast<const f32x2*>(exw + t), s0);
+            s1 = fma2(pack2(v1.x, v1.y), *reinterpret_cast<const f32x2*>(exw + t + 1), s1);
+          }
+          if (k < n) {
+            const float2 v0 = __half22float2(tp[(tapoff[t] >> 5) * 4]);
+            s0 = fma2(pack2(v0.x, v0.y), *reinterpret_cast<const f32x2*>(exw + t), s0);
+            ++t;
+          }
+          float a0, a1, b0, b1;
+          unpack2(s0, a0, a1); unpack2(s1, b0, b1);
+          acc[br] = pack2(a0 + b0, a1 + b1);
+        }
+        float x0, x1, x2, x3, x4, x5;
+        unpack2(acc[0], x0, x1); unpack2(acc[1], x2, x3); unpack2(acc[2], x4, x5);
+        st_shared_v4(unit32(aex_row, 0), pack_f16x2(x0, x1), pack_f16x2(x2, x3), pack_f16x2(x4, x5), 0u);
+        st_shared_v4(unit32(aex_row, 1), 0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async();
+      mbar_arrive(bars + EB_AEX);
+      if (i > 0) epilogue2(i - 1);
+      // ---- stage 2 operand: LReLU(stage 1) as fp16
+      mbar_wait(bars + EB_D1 + m_blk, (uint32_t)i & 1u);
+      tc_fence_after();
+      {
+        const uint32_t tlane = lane_base + (uint32_t)(bf * 256);
+        uint32_t pk[32];
+#pragma unroll
+        for (int k = 27; k < 32; ++k) pk[k] = 0u;
+#pragma unroll
+        for (int br = 0; br < 3; ++br) {
+          float s[32];
+          tmem_ld32(tlane + br * 32, s);
+          tmem_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            float x0 = s[2 * k], x1 = s[2 * k + 1];
+            x0 = x0 > 0.f ? x0 : x0 * a.slope;
+            x1 = x1 > 0.f ? x1 : x1 * a.slope;
+            pk[br * 9 + k] = pack_f16x2(x0, x1);
+          }
+        }
+        et::store_row(a2_row, swz, pk);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bars + EB_A2 + m_blk);
     }
+    if (n_my > 0) epilogue2(n_my - 1);
   }
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) EM_STAMP(7);
-  if (warp == 8) tmem_dealloc(tmem, 256);
+  if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace lfsr
@@ -958,9 +985,9 @@ static EmEncodeFn em_get_encode() {
 extern "C" int lfsr_mel_epi_branch_mma(const lfsr_tensor* in, const lfsr_tensor* in16, const void* packed, const lfsr_tensor* out,
                                        int klen, int dil, float slope, void* stream) {
   LFSR_REQUIRE(tensor_ok(in) && tensor_ok(out) && tensor_ok(in16) && packed, "lfsr_mel_epi_branch_mma: null/invalid tensor");
-  LFSR_REQUIRE(in16->n == in->n && in16->h == in->h && in16->w == in->w && in16->c >= 16 && in16->ld % 8 == 0 &&
+  LFSR_REQUIRE(in16->n == in->n && in16->h == in->h && in16->w == in->w && in16->c >= EC && in16->ld % 8 == 0 && in16->ld >= 24 &&
                    ((uintptr_t)in16->ptr & 15) == 0,
-               "lfsr_mel_epi_branch_mma: in16 must be the fp16 copy of `in` (>= 16 channels, 16-byte aligned pixels)");
+               "lfsr_mel_epi_branch_mma: in16 must be the fp16 copy of `in` (18 channels + readable pad up to 24, 16-byte aligned pixels)");
   LFSR_REQUIRE(in->c == EC && out->c == EC, "lfsr_mel_epi_branch_mma: built for %d-channel EPI splits, got %d", EC, in->c);
   LFSR_REQUIRE(in->n == out->n && in->h == out->h && in->w == out->w, "lfsr_mel_epi_branch_mma: shape mismatch");
   LFSR_REQUIRE(lfsr_mel_epi_pack_bytes(klen) > 0 && dil > 0, "lfsr_mel_epi_branch_mma: bad kernel length");
@@ -977,12 +1004,16 @@ extern "C" int lfsr_mel_epi_branch_mma(const lfsr_tensor* in, const lfsr_tensor*
   LFSR_REQUIRE(a.R >= 1, "lfsr_mel_epi_branch_mma: halo too large");
   a.npx = (2 * a.G0 + 256 + 31) & ~31;               // last MMA row + largest shift, rounded up
   a.tiles_x = ceil_div(in->w, em::TW); a.tiles_y = ceil_div(in->h, a.R);
+  const long long total = (long long)in->n * a.tiles_x * a.tiles_y;
+  LFSR_REQUIRE(total <= 0x7fffffffLL, "lfsr_mel_epi_branch_mma: too many tiles");
+  a.total_tiles = (int)total;
   const size_t img_b = ((size_t)em::image_bytes(a.ntap) + 1023) & ~(size_t)1023;
-  const size_t smem = 1024 + img_b + (((size_t)a.npx * 40 + 2 * em::kAex + 1023) & ~(size_t)1023) + 2 * em::kA2 + 128 + em::kMaxTaps * 4 + 2 * em::kMaxTaps * 8;
-  LFSR_REQUIRE(smem <= 113 * 1024, "lfsr_mel_epi_branch_mma: kernel length / dilation too large for the staged tile");
+  const size_t t16_b = ((size_t)a.npx * 32 + 1023) & ~(size_t)1023, t2_b = ((size_t)a.npx * 16 + 1023) & ~(size_t)1023;
+  const size_t smem = 1024 + img_b + 2 * t16_b + 2 * t2_b + 2 * em::kAex + 2 * em::kA2 + 384 + 4 * em::kMaxTaps * 8 + 64;
+  LFSR_REQUIRE(smem <= 225 * 1024, "lfsr_mel_epi_branch_mma: kernel length / dilation too large for the staged tile");
   static DevOnce once;
   if (once.need()) {
-    if (opt_in_smem(mel_epi_branch_mma_kernel, 113 * 1024, "lfsr_mel_epi_branch_mma")) return LFSR_ERR_CUDA;
+    if (opt_in_smem(mel_epi_branch_mma_kernel, 225 * 1024, "lfsr_mel_epi_branch_mma")) return LFSR_ERR_CUDA;
     once.done();
   }
   EmEncodeFn encode = em_get_encode();
@@ -999,7 +1030,21 @@ extern "C" int lfsr_mel_epi_branch_mma(const lfsr_tensor* in, const lfsr_tensor*
                         CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("lfsr_mel_epi_branch_mma: cuTensorMapEncodeTiled failed with %d", (int)r); return LFSR_ERR_CUDA; }
   }
-  mel_epi_branch_mma_kernel<<<in->n * a.tiles_x * a.tiles_y, kEmThreads, smem, (cudaStream_t)stream>>>(tmX, a);
+  CUtensorMap tmE;
+  {
+    const cuuint64_t ld_b = (cuuint64_t)in16->ld * 2;
+    cuuint64_t dims[4] = {8, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
+    cuuint64_t strides[3] = {ld_b, ld_b * in->w, ld_b * in->w * in->h};
+    cuuint32_t box[4] = {8, (cuuint32_t)a.P, (cuuint32_t)(a.R + 2 * a.halo), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmE, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (char*)in16->ptr + 32, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("lfsr_mel_epi_branch_mma: cuTensorMapEncodeTiled(extra channels) failed with %d", (int)r); return LFSR_ERR_CUDA; }
+  }
+  const int nsm = sm_count_current();
+  const int grid = a.total_tiles < nsm ? a.total_tiles : nsm;
+  mel_epi_branch_mma_kernel<<<grid, kEmThreads, smem, (cudaStream_t)stream>>>(tmX, tmE, a);
   return check_launch("mel_epi_branch_mma_kernel");
 }
 

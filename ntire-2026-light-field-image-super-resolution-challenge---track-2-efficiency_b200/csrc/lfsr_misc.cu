@@ -709,7 +709,7 @@ extern "C" int lfsr_pooled_mlp(const lfsr_tensor* in, int pool, const float* w1,
 
 int lfsr_sa_modulate_tiled(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
                            const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res, const lfsr_tensor* out, int dil,
-                           int* handled, void* stream, const lfsr_tensor* out16 = nullptr);     // lfsr_dw.cu
+                           int* handled, void* stream, const lfsr_tensor* out16 = nullptr, int skip_lo = 0, int skip_hi = 0);     // lfsr_dw.cu
 
 extern "C" int lfsr_sa_modulate(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
                                 const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res,
@@ -752,9 +752,19 @@ extern "C" int lfsr_sa_modulate(const lfsr_tensor* x, const float* dw_w, const f
   return check_launch("sa_modulate_kernel");
 }
 
+extern "C" int lfsr_sa_modulate16w(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
+                                   const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res, const lfsr_tensor* out,
+                                   const lfsr_tensor* out16, int skip_lo, int skip_hi, int dil, void* stream);
 extern "C" int lfsr_sa_modulate16(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
                                   const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res,
                                   const lfsr_tensor* out, const lfsr_tensor* out16, int dil, void* stream) {
+  return lfsr_sa_modulate16w(x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, out16, 0, 0, dil, stream);
+}
+
+extern "C" int lfsr_sa_modulate16w(const lfsr_tensor* x, const float* dw_w, const float* bn_scale, const float* bn_shift,
+                                   const lfsr_tensor* amod, float w0, float w1, const lfsr_tensor* res, const lfsr_tensor* out,
+                                   const lfsr_tensor* out16, int skip_lo, int skip_hi, int dil, void* stream) {
+  LFSR_REQUIRE(skip_lo >= 0 && skip_hi >= skip_lo && skip_lo % 4 == 0 && skip_hi % 4 == 0, "lfsr_sa_modulate16w: the skipped channel window must be whole quads");
   LFSR_REQUIRE(tensor_ok(x) && tensor_ok(out) && tensor_ok(amod) && dw_w && bn_scale && bn_shift && out16 && out16->ptr,
                "lfsr_sa_modulate16: null/invalid tensor");
   LFSR_REQUIRE(out->n == x->n && out->h == x->h && out->w == x->w && out->c == x->c, "lfsr_sa_modulate16: out shape");
@@ -766,7 +776,7 @@ extern "C" int lfsr_sa_modulate16(const lfsr_tensor* x, const float* dw_w, const
     LFSR_REQUIRE(res->n == x->n && res->h == x->h && res->w == x->w && res->c == x->c, "lfsr_sa_modulate16: res shape");
   LFSR_REQUIRE(x->n <= 65535, "lfsr_sa_modulate16: batch too large");
   int handled = 0;
-  int rc = lfsr_sa_modulate_tiled(x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil, &handled, stream, out16);
+  int rc = lfsr_sa_modulate_tiled(x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil, &handled, stream, out16, skip_lo, skip_hi);
   if (rc != LFSR_OK) return rc;
   LFSR_REQUIRE(handled, "lfsr_sa_modulate16: these tensors do not qualify for the tiled kernel (16-byte aligned 4-channel groups)");
   return LFSR_OK;

@@ -369,13 +369,14 @@ class CudaOps:
                                          None if pc2 is None else self._ptr(pc2.bias), 0 if pc2 is None else pc2.cout, act2,
                                          C.byref(as_tensor(out, "mlp.out")), self._stream(x)), "lfsr_pooled_mlp")
 
-    def sa_modulate(self, x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil, out16=None):
+    def sa_modulate(self, x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil, out16=None, skip16=(0, 0)):
+        """out16: fp16 copy of the first out16.shape[3] output channels, minus the channel window skip16 = (lo, hi)"""
         rt = as_tensor(res, "sa.res") if res is not None else _NULL_T
         if out16 is not None:
-            N.check(self.lib.lfsr_sa_modulate16(C.byref(as_tensor(x, "sa.x")), dw_w.data_ptr(), bn_scale.data_ptr(),
-                                                bn_shift.data_ptr(), C.byref(as_tensor(amod, "sa.amod")), w0, w1, C.byref(rt),
-                                                C.byref(as_tensor(out, "sa.out")), C.byref(as_tensor(out16, "sa.out16", f16=True)),
-                                                dil, self._stream(x)), "lfsr_sa_modulate16")
+            N.check(self.lib.lfsr_sa_modulate16w(C.byref(as_tensor(x, "sa.x")), dw_w.data_ptr(), bn_scale.data_ptr(),
+                                                 bn_shift.data_ptr(), C.byref(as_tensor(amod, "sa.amod")), w0, w1, C.byref(rt),
+                                                 C.byref(as_tensor(out, "sa.out")), C.byref(as_tensor(out16, "sa.out16", f16=True)),
+                                                 skip16[0], skip16[1], dil, self._stream(x)), "lfsr_sa_modulate16w")
             return
         N.check(self.lib.lfsr_sa_modulate(C.byref(as_tensor(x, "sa.x")), dw_w.data_ptr(), bn_scale.data_ptr(),
                                           bn_shift.data_ptr(), C.byref(as_tensor(amod, "sa.amod")), w0, w1, C.byref(rt),

@@ -31,7 +31,9 @@ from .. import kernels as K
 from .common import LFNetBase, bn_affine, slots, tail_table, upsample_tail, SideStream, fp16_plan
 
 
-USE_EPI_MMA = os.environ.get("LFSR_EPI_MMA", "0") == "1"
+#: the EPI block with its depthwise taps as shifted-row tcgen05 MMAs (persistent kernel, 0.27 ms per stage at batch 64 against 0.34
+#: for the hybrid kernel); LFSR_EPI_MMA=0 keeps the hybrid (CUDA-core taps + tensor-core 1x1s)
+USE_EPI_MMA = os.environ.get("LFSR_EPI_MMA", "1") == "1"
 
 
 def _conv(cin, cout, k, **kw):
@@ -235,7 +237,6 @@ class get_model(LFNetBase):
                                     pw_t(eb.fuse["0"])]).to(device)
             s["epi_klen"] = eb.epi_h["0"].weight.shape[-1]
             # fp16 operand plan: pre-swizzled tensor-core operands of the all-MMA EPI kernel (None: not available)
-            # (measured slower than the hybrid kernel - 0.48 vs 0.34 ms at batch 64 - so it is opt-in: LFSR_EPI_MMA=1)
             s["epi_img"] = (ops.mel_epi_pack(s["epi_w"], s["epi_klen"], device)
                             if (f16 and USE_EPI_MMA and hasattr(ops, "mel_epi_pack")) else None)
             # three gate FCs as one block-diagonal 1x1 over the grouped layout (MyEfficientLFNet.py:159-173)
@@ -326,7 +327,12 @@ class get_model(LFNetBase):
         fu1 = self._buf16("fu1", B, H, W, CU, dev) if f16 else buf("fu1", H, W, CU)
         fu2 = buf("fu2", H, W, CP)
         if f16:
-            xs16, t18h = self._buf16("xs16", B, H, W, 32, dev), self._buf16("t18h", B, H, W, 32, dev)
+            # fp16 copy of the whole trunk (64-half pixels), written by the stem conversion / the SA tail of the previous stage:
+            # channels 0..31 feed the spatial branch's tensor-core convs, 40..57 the all-MMA EPI kernel
+            epi_mma = pk["stages"][0].get("epi_img") is not None and gs + 12 <= CP
+            trunk16 = self._buf16("trunk16", B, H, W, 64, dev) if epi_mma else None
+            xs16 = trunk16[..., 0:32] if epi_mma else self._buf16("xs16", B, H, W, 32, dev)
+            t18h = self._buf16("t18h", B, H, W, 32, dev)
         pm, am1, am = buf("pm", A, A, CP), buf("am1", A, A, C // 4), buf("am", A, A, CP)
         fork = SideStream(dev if x.is_cuda and getattr(ops, "name", "") == "cuda" else None)
         for i, st in enumerate(pk["stages"]):
@@ -334,7 +340,10 @@ class get_model(LFNetBase):
             # spatial branch
             if f16 and gs + 12 <= CP:
                 if i == 0:          # later stages: the SA modulator of the previous stage wrote the copy next to the trunk
-                    ops.to_f16(feat[..., 0:32], xs16)
+                    if epi_mma:
+                        ops.to_f16(shallow64, trunk16)
+                    else:
+                        ops.to_f16(feat[..., 0:32], xs16)
                 ops.conv(xs16, st["spa0h"], None, out16=t18h[..., 0:24], act=LR, slope=0.1)
                 ops.conv(t18h, st["spa2h"], cat[..., 0:gs])
             else:
@@ -355,11 +364,8 @@ class get_model(LFNetBase):
                     ops.conv(ang5[..., 0:c0], st["ang_ex"], cat[..., gs:2 * gs], act=LR, slope=0.1, alpha=st["ang_scale"],
                              res=feat[..., gs:2 * gs], shuffle=(A, A, N.SHUF_CHANNEL_MAJOR))
             # EPI branch: three depthwise+pointwise paths and their fuse conv in one kernel
-            if st.get("epi_img") is not None:
-                # experiment (LFSR_EPI_MMA=1): depthwise taps as shifted-row MMAs over an fp16 copy of the EPI group
-                xe16 = self._buf16("xe16", B, H, W, 32, dev)
-                ops.to_f16(feat[..., 2 * gs:2 * gs + 16], xe16[..., 0:16])
-                ops.mel_epi_branch_mma(xe, xe16[..., 0:sp[2]], st["epi_img"], cat[..., sl[2]], st["epi_klen"], A, 0.1)
+            if f16 and epi_mma:
+                ops.mel_epi_branch_mma(xe, trunk16[..., 2 * gs:2 * gs + sp[2]], st["epi_img"], cat[..., sl[2]], st["epi_klen"], A, 0.1)
             else:
                 ops.mel_epi_branch(xe, st["epi_w"], cat[..., sl[2]], st["epi_klen"], A, 0.1, tc=bool(f16))
             fork.join()
@@ -376,7 +382,10 @@ class get_model(LFNetBase):
             ops.pooled_mlp(pm, am, st["sa_c0"], N.ACT_RELU, st["sa_c2"], N.ACT_SIGMOID)
             nxt = pp[i & 1]
             if f16 and gs + 12 <= CP and i + 1 < len(pk["stages"]):
-                ops.sa_modulate(fu2, st["sa_dw"], st["sa_bns"], st["sa_bnb"], am, st["sa_w"][0], st["sa_w"][1], feat, nxt, A, out16=xs16)
+                ops.sa_modulate(fu2, st["sa_dw"], st["sa_bns"], st["sa_bnb"], am, st["sa_w"][0], st["sa_w"][1], feat, nxt, A,
+                                out16=trunk16[..., 0:CP] if epi_mma else xs16)
+                # (leaving the unread channels 20..39 out of the copy - skip16=(gs, 2 * gs) - was SLOWER, 0.397 vs 0.347 ms per
+                # call: the copy then ends in 8- and 16-byte pieces of 32-byte sectors)
             else:
                 ops.sa_modulate(fu2, st["sa_dw"], st["sa_bns"], st["sa_bnb"], am, st["sa_w"][0], st["sa_w"][1], feat, nxt, A)
             feat = nxt

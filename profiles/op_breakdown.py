@@ -43,10 +43,13 @@ class ProfilingOps(K.CudaOps):
     def mel_epi_branch(self, x, w, out, klen, dil, slope, tc=False):
         self._wrap("mel_epi_branch", lambda: K.CudaOps.mel_epi_branch(self, x, w, out, klen, dil, slope, tc=tc), f"mel_epi_branch{'_tc' if tc else ''} c{x.shape[3]} @{x.shape[1]}x{x.shape[2]}")
 
+    def mel_epi_branch_mma(self, x, x16, img, out, klen, dil, slope):
+        self._wrap("mel_epi_branch_mma", lambda: K.CudaOps.mel_epi_branch_mma(self, x, x16, img, out, klen, dil, slope), f"mel_epi_branch_mma c{x.shape[3]} @{x.shape[1]}x{x.shape[2]}")
+
     def block_mean(self, x, out, bh, bw):
         self._wrap("block_mean", lambda: K.CudaOps.block_mean(self, x, out, bh, bw), f"block_mean {bh}x{bw} c{x.shape[3]} @{x.shape[1]}")
 
-    def sa_modulate(self, *a, **kw):
+    def sa_modulate(self, *a, **kw):  # noqa
         self._wrap("sa_modulate", lambda: K.CudaOps.sa_modulate(self, *a, **kw), "sa_modulate" + (" + fp16 copy" if kw.get("out16") is not None else ""))
 
     def ang_expand(self, x, w, res, out, A, *a, **kw):

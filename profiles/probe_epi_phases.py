@@ -1,4 +1,5 @@
-"""Per-CTA phase time stamps of mel_epi_branch_mma_kernel (probe build, LFSR_PROBE_LIB=1): where a CTA's lifetime goes."""
+"""Issuer time stamps of the persistent mel_epi_branch_mma_kernel (probe build, LFSR_PROBE_LIB=1): cycles per tile.
+(The per-phase stamps of the first, non-persistent version are in git history: commit "All-MMA EPI kernel v2".)"""
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -25,14 +26,7 @@ assert fn(dbg.data_ptr()) == 0
 run()
 torch.cuda.synchronize()
 fn(None)
-d = dbg.view(4096, 16).cpu().double()
-names = ["start", "after setup sync", "ch16/17 staged", "extras done (arrive IN)", "D1 ready (worker 0)", "A2 written", "D2 ready",
-         "all done", "MMA: image landed", "MMA: tile landed", "MMA: workers ready", "MMA: block 0 issued", "MMA: block 1 issued",
-         "MMA: stage 2 block 0 issued", "MMA: stage 2 block 1 issued"]
-rel = d[:, 1:15] - d[:, 0:1]
-sel = rel[300:4000]          # steady state (CTAs that started behind others)
-print("median cycles since CTA start (CTAs 300..4000):")
-for i, nme in enumerate(names[1:]):
-    print(f"  {nme:32s} {sel[:, i].median().item():9.0f}")
-life = (d[:, 7] - d[:, 0])[300:4000]
-print(f"CTA lifetime median {life.median().item():.0f}, p90 {life.quantile(0.9).item():.0f} cycles")
+d = dbg.view(4096, 16).cpu().double()[:148]
+per = (d[:, 1:12] - d[:, 0:11])            # cycles between the issuer's tile starts (persistent kernel, tiles 0..11 of each CTA)
+print("issuer: cycles per tile, median over the CTAs, tiles 1..11:", [int(per[:, i].median().item()) for i in range(11)])
+print(f"steady state (tiles 4..11): {per[:, 3:].median().item():.0f} cycles per tile")

@@ -240,7 +240,7 @@ class RefOps:
         n, h, w, c = x.shape
         out.copy_(x.reshape(n, h // bh, bh, w // bw, bw, c).mean(dim=(2, 4)))
 
-    def sa_modulate(self, x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil, out16=None):
+    def sa_modulate(self, x, dw_w, bn_scale, bn_shift, amod, w0, w1, res, out, dil, out16=None, skip16=(0, 0)):
         n, h, w, c = x.shape
         xi = _nchw(x)
         s = F.conv2d(xi, dw_w.t().reshape(c, 1, 3, 3), None, 1, dil, dil, c)
@@ -251,7 +251,10 @@ class RefOps:
             y = y + _nchw(res)
         out.copy_(y.permute(0, 2, 3, 1))
         if out16 is not None:
-            out16.copy_(out[..., :out16.shape[3]])
+            c16 = out16.shape[3]
+            lo, hi = min(skip16[0], c16), min(skip16[1], c16)
+            out16[..., :lo].copy_(out[..., :lo])
+            out16[..., hi:].copy_(out[..., hi:c16])
 
     def scale_add(self, x, scale, res, out, out16=None):
         y = x * scale

@@ -312,6 +312,11 @@ def test_sa_modulate_with_fp16_copy(ops, ref, c, c16, h, w):
     assert (a - b).abs().max().item() <= 1e-5
     assert torch.equal(full16[..., :c16], a[..., :c16].half())
     assert bool((full16[..., c16:] == 3.0).all())
+    # a skipped channel window stays untouched as well
+    full16.fill_(3.0)
+    ops.sa_modulate(x, dw, bs, bb, am, 0.4, 0.6, res, a, A, out16=full16[..., :c16], skip16=(8, 16))
+    assert torch.equal(full16[..., :8], a[..., :8].half()) and torch.equal(full16[..., 16:c16], a[..., 16:c16].half())
+    assert bool((full16[..., 8:16] == 3.0).all()) and bool((full16[..., c16:] == 3.0).all())
 
 
 @pytest.mark.parametrize("r", [2, 4])
