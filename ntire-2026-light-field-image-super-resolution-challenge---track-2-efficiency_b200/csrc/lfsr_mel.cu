@@ -529,21 +529,21 @@ struct EpiMmaArgs {
   int tiles_x, tiles_y, total_tiles;
 };
 
-// Persistent, one CTA per SM, 10 warps: 0..7 = workers (thread t <-> MMA row t & 127 of block t >> 7), 8 = MMA issuer, 9 = TMA
-// producer. The issuer and the producer run their whole programs inside ONE elect block each (tcgen05 instructions issued from
+// Persistent, one CTA per SM, 14 warps: 0..7 = epilogue workers (thread t <-> MMA row t & 127 of block t >> 7), 8 = MMA issuer,
+// 9 = TMA producer, 10..13 = the CUDA-core side channel for channels 16, 17 (runs a tile ahead of the epilogues). The issuer and the producer run their whole programs inside ONE elect block each (tcgen05 instructions issued from
 // `if (lane == 0)` are wrapped in ELECT/branch loops by ptxas, and tcgen05.commit only tracks the MMAs of the committing
 // thread); every hand-off is an mbarrier. Two input buffers and two halves of tensor memory: the tap MMAs of tile i+1 run
 // while the workers drain tile i, and the TMA loads of tile i+2 are issued as soon as the MMAs of tile i have retired.
 //   issuer, tile i:   taps(i) -> [stage 2 of tile i-1] -> extra(i) + commit D1(i) -> commit "buffer free"
-//   workers, tile i:  extras(i) -> [epilogue 2 of tile i-1] -> epilogue 1 of tile i
+//   workers, tile i:  [epilogue 2 of tile i-1] -> epilogue 1 of tile i          side channel, tile i: extras(i)
 #ifdef LFSR_DEBUG_HOOKS
 __device__ long long* g_em_dbg = nullptr;        // probe build: time stamps of the issuer at the start of its first 16 tiles
 #define EM_STAMP(slot) do { if (g_em_dbg && blockIdx.x < 4096 && (slot) < 16) g_em_dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
 #else
 #define EM_STAMP(slot) do { } while (0)
 #endif
-constexpr int kEmThreads = 320;
-enum EmBar { EB_IMG = 0, EB_XF, EB_XE = EB_XF + 2, EB_AEX = EB_XE + 2, EB_D1, EB_A2 = EB_D1 + 2, EB_D2 = EB_A2 + 2, EB_TE = EB_D2 + 2,
+constexpr int kEmThreads = 448;
+enum EmBar { EB_IMG = 0, EB_XF, EB_XE = EB_XF + 2, EB_AEX = EB_XE + 2, EB_D1 = EB_AEX + 2, EB_A2 = EB_D1 + 2, EB_D2 = EB_A2 + 2, EB_TE = EB_D2 + 2,
              EB_COUNT = EB_TE + 2 };
 
 struct EmTile { int img, ty0, tx0; };
@@ -555,7 +555,7 @@ __device__ __forceinline__ EmTile em_decode(const EpiMmaArgs& a, int t) {
   return e;
 }
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(kEmThreads, 1)
 mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmE, const EpiMmaArgs a) {
   using namespace em;
   extern __shared__ uint8_t em_raw[];
@@ -570,8 +570,8 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   const int t16_bytes = (a.npx * 32 + 1023) & ~1023, t2_bytes = (a.npx * 16 + 1023) & ~1023;
   uint8_t* T16 = smem + ((img_bytes + 1023) & ~1023);  // 2 x [npx][16 fp16]  channels 0..15, SWIZZLE_32B rows
   uint8_t* T2h = T16 + 2 * t16_bytes;                  // 2 x [npx][8 fp16]   channels 16..23 (16, 17 used)
-  uint8_t* Aex = T2h + 2 * t2_bytes;                   // 2 blocks x [128][16 fp16]
-  uint8_t* A2 = Aex + 2 * kAex;                        // 2 blocks x [128][64 fp16]
+  uint8_t* Aex = T2h + 2 * t2_bytes;                   // 2 buffers x 2 blocks x [128][16 fp16]
+  uint8_t* A2 = Aex + 4 * kAex;                        // 2 blocks x [128][64 fp16]
   uint64_t* bars = reinterpret_cast<uint64_t*>(A2 + 2 * kA2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + EB_COUNT);
   int* tapoff = reinterpret_cast<int*>(tmem_slot + 1);           // byte shift of the A view per tap
@@ -586,8 +586,8 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       mbar_init(bars + EB_XF + i, 1); mbar_init(bars + EB_XE + i, 1);
       mbar_init(bars + EB_D1 + i, 1); mbar_init(bars + EB_A2 + i, 128); mbar_init(bars + EB_D2 + i, 1);
       mbar_init(bars + EB_TE + i, 256);
+      mbar_init(bars + EB_AEX + i, 128);      // one per input buffer: the side channel may finish tile i+1 before the issuer asks for tile i
     }
-    mbar_init(bars + EB_AEX, 256);
     fence_barrier_init();
     mbar_expect_tx(bars + EB_IMG, (uint32_t)img_bytes);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -673,11 +673,11 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
           }
         }
         if (i > 0) stage2(i - 1);
-        mbar_wait(bars + EB_AEX, (uint32_t)i & 1u);                          // channels 16, 17 of this tile are in Aex
+        mbar_wait(bars + EB_AEX + bf, ((uint32_t)i >> 1) & 1u);              // channels 16, 17 of this tile are in Aex
         tc_fence_after();
 #pragma unroll 1
         for (int m = 0; m < 2; ++m) {
-          umma_f16<1>(th + (uint32_t)(m * 96), desc32(smem_u32(Aex) + (uint32_t)m * kAex), dbx, idx);
+          umma_f16<1>(th + (uint32_t)(m * 96), desc32(smem_u32(Aex) + (uint32_t)(bf * 2 + m) * kAex), dbx, idx);
           umma_commit(bars + EB_D1 + m);
         }
         umma_commit(bars + EB_XE + bf);                                      // input buffer free once all of this has retired
@@ -685,8 +685,8 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       if (n_my > 0) stage2(n_my - 1);
     }
     __syncwarp();
-  } else {
-    // ================= workers =================
+  } else if (warp < 8) {
+    // ================= workers: the two epilogues =================
     const int m_blk = tid >> 7, r_blk = tid & 127;
     const int g = a.G0 + m_blk * 128 + r_blk;         // flattened padded position of this thread's pixel (= its MMA row)
     const int gy = g / P, gx = g - gy * P;
@@ -694,7 +694,6 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     const bool in_tile = tx >= 0 && tx < TW && ty >= 0 && ty < a.R;
     const uint32_t a2_row = smem_u32(A2) + (uint32_t)m_blk * kA2 + (uint32_t)r_blk * 128u;
     const uint32_t swz = (uint32_t)r_blk & 7u;
-    const uint32_t aex_row = smem_u32(Aex) + (uint32_t)m_blk * kAex + (uint32_t)r_blk * 32u;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)m_blk * 96u;
     auto epilogue2 = [&](int i) {                      // LReLU(fuse) of tile i -> global
       const EmTile e = em_decode(a, (int)blockIdx.x + i * (int)gridDim.x);
@@ -717,42 +716,8 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         }
       }
     };
-    mbar_wait(bars + EB_IMG, 0);                       // the extra-channel tap weights live in the operand image
     for (int i = 0; i < n_my; ++i) {
       const int bf = i & 1;
-      // ---- channels 16, 17 on the CUDA cores
-      mbar_wait(bars + EB_XF + bf, ((uint32_t)i >> 1) & 1u);
-      {
-        const __half2* tp = reinterpret_cast<const __half2*>(T2h + bf * t2_bytes) + (size_t)g * 4;     // 8 halves per pixel
-        f32x2 acc[3];
-        int t = 0;
-#pragma unroll
-        for (int br = 0; br < 3; ++br) {
-          const int n = br == 2 ? 9 : a.KL;
-          f32x2 s0 = pack2(0.f, 0.f), s1 = s0;
-          int k = 0;
-#pragma unroll 4
-          for (; k + 1 < n; k += 2, t += 2) {
-            const float2 v0 = __half22float2(tp[(tapoff[t] >> 5) * 4]), v1 = __half22float2(tp[(tapoff[t + 1] >> 5) * 4]);
-            s0 = fma2(pack2(v0.x, v0.y), *reinterpret_cast<const f32x2*>(exw + t), s0);
-            s1 = fma2(pack2(v1.x, v1.y), *reinterpret_cast<const f32x2*>(exw + t + 1), s1);
-          }
-          if (k < n) {
-            const float2 v0 = __half22float2(tp[(tapoff[t] >> 5) * 4]);
-            s0 = fma2(pack2(v0.x, v0.y), *reinterpret_cast<const f32x2*>(exw + t), s0);
-            ++t;
-          }
-          float a0, a1, b0, b1;
-          unpack2(s0, a0, a1); unpack2(s1, b0, b1);
-          acc[br] = pack2(a0 + b0, a1 + b1);
-        }
-        float x0, x1, x2, x3, x4, x5;
-        unpack2(acc[0], x0, x1); unpack2(acc[1], x2, x3); unpack2(acc[2], x4, x5);
-        st_shared_v4(unit32(aex_row, 0), pack_f16x2(x0, x1), pack_f16x2(x2, x3), pack_f16x2(x4, x5), 0u);
-        st_shared_v4(unit32(aex_row, 1), 0u, 0u, 0u, 0u);
-      }
-      fence_proxy_async();
-      mbar_arrive(bars + EB_AEX);
       if (i > 0) epilogue2(i - 1);
       // ---- stage 2 operand: LReLU(stage 1) as fp16
       mbar_wait(bars + EB_D1 + m_blk, (uint32_t)i & 1u);
@@ -782,6 +747,49 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       mbar_arrive(bars + EB_A2 + m_blk);
     }
     if (n_my > 0) epilogue2(n_my - 1);
+  } else {
+    // ================= side channel (4 warps): channels 16, 17 on the CUDA cores, one tile ahead of the epilogues =================
+    const int r_e = tid - 320;                         // 0..127: row r_e of both 128-row blocks
+    mbar_wait(bars + EB_IMG, 0);                       // the extra-channel tap weights live in the operand image
+    for (int i = 0; i < n_my; ++i) {
+      const int bf = i & 1;
+      mbar_wait(bars + EB_XF + bf, ((uint32_t)i >> 1) & 1u);
+      // (Aex[bf] was last read by the extra MMA of tile i-2, which retired before this tile's input buffer was refilled)
+#pragma unroll 1
+      for (int m = 0; m < 2; ++m) {
+        const int g = a.G0 + m * 128 + r_e;
+        const __half2* tp = reinterpret_cast<const __half2*>(T2h + bf * t2_bytes) + (size_t)g * 4;     // 8 halves per pixel
+        f32x2 acc[3];
+        int t = 0;
+#pragma unroll
+        for (int br = 0; br < 3; ++br) {
+          const int n = br == 2 ? 9 : a.KL;
+          f32x2 s0 = pack2(0.f, 0.f), s1 = s0;
+          int k = 0;
+#pragma unroll 4
+          for (; k + 1 < n; k += 2, t += 2) {
+            const float2 v0 = __half22float2(tp[(tapoff[t] >> 5) * 4]), v1 = __half22float2(tp[(tapoff[t + 1] >> 5) * 4]);
+            s0 = fma2(pack2(v0.x, v0.y), *reinterpret_cast<const f32x2*>(exw + t), s0);
+            s1 = fma2(pack2(v1.x, v1.y), *reinterpret_cast<const f32x2*>(exw + t + 1), s1);
+          }
+          if (k < n) {
+            const float2 v0 = __half22float2(tp[(tapoff[t] >> 5) * 4]);
+            s0 = fma2(pack2(v0.x, v0.y), *reinterpret_cast<const f32x2*>(exw + t), s0);
+            ++t;
+          }
+          float a0, a1, b0, b1;
+          unpack2(s0, a0, a1); unpack2(s1, b0, b1);
+          acc[br] = pack2(a0 + b0, a1 + b1);
+        }
+        float x0, x1, x2, x3, x4, x5;
+        unpack2(acc[0], x0, x1); unpack2(acc[1], x2, x3); unpack2(acc[2], x4, x5);
+        const uint32_t aex_row = smem_u32(Aex) + (uint32_t)(bf * 2 + m) * kAex + (uint32_t)r_e * 32u;
+        st_shared_v4(unit32(aex_row, 0), pack_f16x2(x0, x1), pack_f16x2(x2, x3), pack_f16x2(x4, x5), 0u);
+        st_shared_v4(unit32(aex_row, 1), 0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async();
+      mbar_arrive(bars + EB_AEX + bf);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1009,7 +1017,7 @@ extern "C" int lfsr_mel_epi_branch_mma(const lfsr_tensor* in, const lfsr_tensor*
   a.total_tiles = (int)total;
   const size_t img_b = ((size_t)em::image_bytes(a.ntap) + 1023) & ~(size_t)1023;
   const size_t t16_b = ((size_t)a.npx * 32 + 1023) & ~(size_t)1023, t2_b = ((size_t)a.npx * 16 + 1023) & ~(size_t)1023;
-  const size_t smem = 1024 + img_b + 2 * t16_b + 2 * t2_b + 2 * em::kAex + 2 * em::kA2 + 384 + 4 * em::kMaxTaps * 8 + 64;
+  const size_t smem = 1024 + img_b + 2 * t16_b + 2 * t2_b + 4 * em::kAex + 2 * em::kA2 + 384 + 4 * em::kMaxTaps * 8 + 64;
   LFSR_REQUIRE(smem <= 225 * 1024, "lfsr_mel_epi_branch_mma: kernel length / dilation too large for the staged tile");
   static DevOnce once;
   if (once.need()) {
