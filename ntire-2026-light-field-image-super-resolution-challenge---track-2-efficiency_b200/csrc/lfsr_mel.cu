@@ -539,8 +539,12 @@ struct EpiMmaArgs {
 #ifdef LFSR_DEBUG_HOOKS
 __device__ long long* g_em_dbg = nullptr;        // probe build: time stamps of the issuer at the start of its first 16 tiles
 #define EM_STAMP(slot) do { if (g_em_dbg && blockIdx.x < 4096 && (slot) < 16) g_em_dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+// phases inside tile `EM_T` (second block of the buffer): issuer 0..4, epilogue worker 0 8..12, side channel 14, 15
+#define EM_T 8
+#define EM_PHASE(i, slot) do { if (g_em_dbg && (i) == EM_T && blockIdx.x < 4096) g_em_dbg[65536 + blockIdx.x * 16 + (slot)] = clock64(); } while (0)
 #else
 #define EM_STAMP(slot) do { } while (0)
+#define EM_PHASE(i, slot) do { } while (0)
 #endif
 constexpr int kEmThreads = 448;
 enum EmBar { EB_IMG = 0, EB_XF, EB_XE = EB_XF + 2, EB_AEX = EB_XE + 2, EB_D1 = EB_AEX + 2, EB_A2 = EB_D1 + 2, EB_D2 = EB_A2 + 2, EB_TE = EB_D2 + 2,
@@ -657,6 +661,7 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         mbar_wait(bars + EB_XF + bf, ((uint32_t)i >> 1) & 1u);              // input tile landed
         mbar_wait(bars + EB_TE + bf, (((uint32_t)i >> 1) & 1u) ^ 1u);        // this half of tensor memory was drained (tile i-2)
         tc_fence_after();
+        EM_PHASE(i, 0);
 #pragma unroll 1
         for (int m = 0; m < 2; ++m) {
           const uint64_t* ad = adesc + (bf * 2 + m) * kMaxTaps;
@@ -672,8 +677,11 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
             for (int k = 1; k < n; ++k, ++t) umma_f16<1>(d, ad[t], dbt + (uint64_t)(t * (kTapB >> 4)), id1);
           }
         }
+        EM_PHASE(i, 1);
         if (i > 0) stage2(i - 1);
+        EM_PHASE(i, 2);
         mbar_wait(bars + EB_AEX + bf, ((uint32_t)i >> 1) & 1u);              // channels 16, 17 of this tile are in Aex
+        EM_PHASE(i, 3);
         tc_fence_after();
 #pragma unroll 1
         for (int m = 0; m < 2; ++m) {
@@ -681,6 +689,7 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
           umma_commit(bars + EB_D1 + m);
         }
         umma_commit(bars + EB_XE + bf);                                      // input buffer free once all of this has retired
+        EM_PHASE(i, 4);
       }
       if (n_my > 0) stage2(n_my - 1);
     }
@@ -718,9 +727,12 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     };
     for (int i = 0; i < n_my; ++i) {
       const int bf = i & 1;
+      if (tid == 0) EM_PHASE(i, 8);
       if (i > 0) epilogue2(i - 1);
+      if (tid == 0) EM_PHASE(i, 9);
       // ---- stage 2 operand: LReLU(stage 1) as fp16
       mbar_wait(bars + EB_D1 + m_blk, (uint32_t)i & 1u);
+      if (tid == 0) EM_PHASE(i, 10);
       tc_fence_after();
       {
         const uint32_t tlane = lane_base + (uint32_t)(bf * 256);
@@ -745,6 +757,7 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bars + EB_A2 + m_blk);
+      if (tid == 0) EM_PHASE(i, 11);
     }
     if (n_my > 0) epilogue2(n_my - 1);
   } else {
@@ -754,6 +767,7 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     for (int i = 0; i < n_my; ++i) {
       const int bf = i & 1;
       mbar_wait(bars + EB_XF + bf, ((uint32_t)i >> 1) & 1u);
+      if (tid == 320) EM_PHASE(i, 14);
       // (Aex[bf] was last read by the extra MMA of tile i-2, which retired before this tile's input buffer was refilled)
 #pragma unroll 1
       for (int m = 0; m < 2; ++m) {
@@ -788,6 +802,7 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         st_shared_v4(unit32(aex_row, 1), 0u, 0u, 0u, 0u);
       }
       fence_proxy_async();
+      if (tid == 320) EM_PHASE(i, 15);
       mbar_arrive(bars + EB_AEX + bf);
     }
   }
