@@ -547,7 +547,8 @@ __device__ long long* g_em_dbg = nullptr;        // probe build: time stamps of 
 #define EM_PHASE(i, slot) do { } while (0)
 #endif
 constexpr int kEmThreads = 448;
-enum EmBar { EB_IMG = 0, EB_XF, EB_XE = EB_XF + 2, EB_AEX = EB_XE + 2, EB_D1 = EB_AEX + 2, EB_A2 = EB_D1 + 2, EB_D2 = EB_A2 + 2, EB_TE = EB_D2 + 2,
+constexpr int kEmBufs = 3;            // input buffers: the side channel (and the TMA loads) run up to two tiles ahead of the MMAs
+enum EmBar { EB_IMG = 0, EB_XF, EB_XE = EB_XF + kEmBufs, EB_AEX = EB_XE + kEmBufs, EB_D1 = EB_AEX + kEmBufs, EB_A2 = EB_D1 + 2, EB_D2 = EB_A2 + 2, EB_TE = EB_D2 + 2,
              EB_COUNT = EB_TE + 2 };
 
 struct EmTile { int img, ty0, tx0; };
@@ -573,9 +574,9 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   const float2* exw = reinterpret_cast<const float2*>(B2 + kB2);
   const int t16_bytes = (a.npx * 32 + 1023) & ~1023, t2_bytes = (a.npx * 16 + 1023) & ~1023;
   uint8_t* T16 = smem + ((img_bytes + 1023) & ~1023);  // 2 x [npx][16 fp16]  channels 0..15, SWIZZLE_32B rows
-  uint8_t* T2h = T16 + 2 * t16_bytes;                  // 2 x [npx][8 fp16]   channels 16..23 (16, 17 used)
-  uint8_t* Aex = T2h + 2 * t2_bytes;                   // 2 buffers x 2 blocks x [128][16 fp16]
-  uint8_t* A2 = Aex + 4 * kAex;                        // 2 blocks x [128][64 fp16]
+  uint8_t* T2h = T16 + kEmBufs * t16_bytes;            // x [npx][8 fp16]   channels 16..23 (16, 17 used)
+  uint8_t* Aex = T2h + kEmBufs * t2_bytes;             // buffers x 2 blocks x [128][16 fp16]
+  uint8_t* A2 = Aex + 2 * kEmBufs * kAex;                        // 2 blocks x [128][64 fp16]
   uint64_t* bars = reinterpret_cast<uint64_t*>(A2 + 2 * kA2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + EB_COUNT);
   int* tapoff = reinterpret_cast<int*>(tmem_slot + 1);           // byte shift of the A view per tap
@@ -586,11 +587,13 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   const int n_my = ((int)total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (tid == 0) {
     mbar_init(bars + EB_IMG, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kEmBufs; ++i) {
       mbar_init(bars + EB_XF + i, 1); mbar_init(bars + EB_XE + i, 1);
+      mbar_init(bars + EB_AEX + i, 128);      // one per input buffer: the side channel may finish tile i+1 before the issuer asks for tile i
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(bars + EB_D1 + i, 1); mbar_init(bars + EB_A2 + i, 128); mbar_init(bars + EB_D2 + i, 1);
       mbar_init(bars + EB_TE + i, 256);
-      mbar_init(bars + EB_AEX + i, 128);      // one per input buffer: the side channel may finish tile i+1 before the issuer asks for tile i
     }
     fence_barrier_init();
     mbar_expect_tx(bars + EB_IMG, (uint32_t)img_bytes);
@@ -603,7 +606,7 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     else if (tid < 2 * a.KL) dy = tid - a.KL - half;
     else { const int k = tid - 2 * a.KL; dy = (k / 3 - 1) * a.dil; dx = (k % 3 - 1) * a.dil; }
     tapoff[tid] = (dy * P + dx) * 32;
-    for (int bf = 0; bf < 2; ++bf)
+    for (int bf = 0; bf < kEmBufs; ++bf)
       for (int m = 0; m < 2; ++m)
         adesc[(bf * 2 + m) * kMaxTaps + tid] =
             desc32(smem_u32(T16) + (uint32_t)(bf * t16_bytes) + (uint32_t)(a.G0 + m * 128) * 32u + (uint32_t)((dy * P + dx) * 32));
@@ -619,9 +622,9 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     if (elect_one()) {
       const uint32_t tx = (uint32_t)((a.R + 2 * halo) * P * (32 + 16));
       for (int i = 0; i < n_my; ++i) {
-        const int bf = i & 1;
+        const int bf = i % kEmBufs;
         const EmTile e = em_decode(a, (int)blockIdx.x + i * (int)gridDim.x);
-        mbar_wait(bars + EB_XE + bf, (((uint32_t)i >> 1) & 1u) ^ 1u);        // the MMAs that read this buffer have retired
+        mbar_wait(bars + EB_XE + bf, (((uint32_t)(i / kEmBufs)) & 1u) ^ 1u);  // the MMAs that read this buffer have retired
         mbar_expect_tx(bars + EB_XF + bf, tx);
         asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                      ::"r"(smem_u32(T16 + bf * t16_bytes)), "l"(&tmX), "r"(smem_u32(bars + EB_XF + bf)), "r"(0), "r"(e.tx0 - halo),
@@ -655,11 +658,11 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       };
       mbar_wait(bars + EB_IMG, 0);
       for (int i = 0; i < n_my; ++i) {
-        const int bf = i & 1;
-        const uint32_t th = tmem + (uint32_t)(bf * 256);
+        const int bf = i % kEmBufs, hp = i & 1;
+        const uint32_t th = tmem + (uint32_t)(hp * 256);
         EM_STAMP(i);
-        mbar_wait(bars + EB_XF + bf, ((uint32_t)i >> 1) & 1u);              // input tile landed
-        mbar_wait(bars + EB_TE + bf, (((uint32_t)i >> 1) & 1u) ^ 1u);        // this half of tensor memory was drained (tile i-2)
+        mbar_wait(bars + EB_XF + bf, ((uint32_t)(i / kEmBufs)) & 1u);        // input tile landed
+        mbar_wait(bars + EB_TE + hp, (((uint32_t)i >> 1) & 1u) ^ 1u);        // this half of tensor memory was drained (tile i-2)
         tc_fence_after();
         EM_PHASE(i, 0);
 #pragma unroll 1
@@ -680,7 +683,7 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         EM_PHASE(i, 1);
         if (i > 0) stage2(i - 1);
         EM_PHASE(i, 2);
-        mbar_wait(bars + EB_AEX + bf, ((uint32_t)i >> 1) & 1u);              // channels 16, 17 of this tile are in Aex
+        mbar_wait(bars + EB_AEX + bf, ((uint32_t)(i / kEmBufs)) & 1u);       // channels 16, 17 of this tile are in Aex
         EM_PHASE(i, 3);
         tc_fence_after();
 #pragma unroll 1
@@ -726,7 +729,7 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       }
     };
     for (int i = 0; i < n_my; ++i) {
-      const int bf = i & 1;
+      const int bf = i & 1;                            // half of tensor memory
       if (tid == 0) EM_PHASE(i, 8);
       if (i > 0) epilogue2(i - 1);
       if (tid == 0) EM_PHASE(i, 9);
@@ -765,10 +768,10 @@ mel_epi_branch_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     const int r_e = tid - 320;                         // 0..127: row r_e of both 128-row blocks
     mbar_wait(bars + EB_IMG, 0);                       // the extra-channel tap weights live in the operand image
     for (int i = 0; i < n_my; ++i) {
-      const int bf = i & 1;
-      mbar_wait(bars + EB_XF + bf, ((uint32_t)i >> 1) & 1u);
+      const int bf = i % kEmBufs;
+      mbar_wait(bars + EB_XF + bf, ((uint32_t)(i / kEmBufs)) & 1u);
       if (tid == 320) EM_PHASE(i, 14);
-      // (Aex[bf] was last read by the extra MMA of tile i-2, which retired before this tile's input buffer was refilled)
+      // (Aex[bf] was last read by the extra MMA of tile i-3, which retired before this tile's input buffer was refilled)
 #pragma unroll 1
       for (int m = 0; m < 2; ++m) {
         const int g = a.G0 + m * 128 + r_e;
@@ -1032,7 +1035,7 @@ extern "C" int lfsr_mel_epi_branch_mma(const lfsr_tensor* in, const lfsr_tensor*
   a.total_tiles = (int)total;
   const size_t img_b = ((size_t)em::image_bytes(a.ntap) + 1023) & ~(size_t)1023;
   const size_t t16_b = ((size_t)a.npx * 32 + 1023) & ~(size_t)1023, t2_b = ((size_t)a.npx * 16 + 1023) & ~(size_t)1023;
-  const size_t smem = 1024 + img_b + 2 * t16_b + 2 * t2_b + 4 * em::kAex + 2 * em::kA2 + 384 + 4 * em::kMaxTaps * 8 + 64;
+  const size_t smem = 1024 + img_b + kEmBufs * (t16_b + t2_b + 2 * em::kAex) + 2 * em::kA2 + 384 + 2 * kEmBufs * em::kMaxTaps * 8 + 64;
   LFSR_REQUIRE(smem <= 225 * 1024, "lfsr_mel_epi_branch_mma: kernel length / dilation too large for the staged tile");
   static DevOnce once;
   if (once.need()) {
