@@ -11,6 +11,7 @@
 //   makes the per-lane 128-bit tile reads bank-conflict free; weights [tap][cin][20] sit in shared memory.
 // Results are fp32-exact (no TF32 rounding), summed tap by tap, input channel by input channel.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <mutex>
 #include "lfsr_common.cuh"
@@ -161,6 +162,8 @@ struct StemArgs {
   int perm_a;            // > 0: MacPI addressing over SAI storage with dilation == perm_a (see conv_stem_macpi_kernel)
   int bh, bw;            // view blocking (EPIT's per-view Conv3d(1,3,3), EPIT.py:24): taps that leave the bh x bw block of
                          // the output pixel read zero; bh = H, bw = W without blocking
+  __half* o16;           // conv_stem_tile_kernel: optional fp16 copy of the output (lfsr_conv_desc.out_mode 1): the operand of
+  int o16_ld;            // the first tensor-core layer, so that no separate conversion pass re-reads the fp32 tensor
 };
 
 __global__ void __launch_bounds__(256)
@@ -262,6 +265,12 @@ conv_stem_tile_kernel(const StemArgs a) {
       acc.z = apply_act(acc.z, a.act, a.slope); acc.w = apply_act(acc.w, a.act, a.slope);
     }
     *reinterpret_cast<float4*>(dst) = acc;
+    if (a.o16) {
+      const __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
+      uint2 v;
+      v.x = *reinterpret_cast<const uint32_t*>(&h0); v.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(a.o16 + ((size_t)((size_t)img * a.out.h + oy0 + r) * a.out.w + ox) * (size_t)a.o16_ld + c) = v;
+    }
   }
 }
 
@@ -404,6 +413,14 @@ extern "C" int lfsr_conv2d_stem_supported(const lfsr_tensor* in, const lfsr_tens
   if (in->c != 1 || out->c > 64 || out->c % 4 || out->ld % 4 || ((uintptr_t)out->ptr & 15)) return 0;
   if (d->stride_h != 1 || d->stride_w != 1 || d->out_perm || d->mul.ptr || d->res.ptr || d->in_scale || d->tail_w) return 0;
   if (d->shuf_ry > 1 || d->shuf_rx > 1 || d->alpha != 1.f) return 0;
+  if (d->out_mode != 0) {          // fp32 + fp16 copy: the tiled kernel only (same conditions as at launch), never fp16 alone
+    const lfsr_tensor* o = &d->out16;
+    if (d->out_mode != 1 || d->in_perm || !tensor_ok(o) || o->n != out->n || o->h != out->h || o->w != out->w || o->c != out->c ||
+        o->ld % 4 || ((uintptr_t)o->ptr & 7)) return 0;
+    const int bh = d->block_h > 0 ? d->block_h : in->h, bw = d->block_w > 0 ? d->block_w : in->w;
+    if (!((bw == in->w || bw % 16 == 0) && (bh == in->h || bh % 8 == 0))) return 0;
+    if ((size_t)(8 + 2 * d->pad_h) * (16 + 2 * d->pad_w) * sizeof(float) > 40 * 1024) return 0;
+  }
   if ((d->block_h > 0 || d->block_w > 0) &&
       (d->in_perm || (d->block_h > 0 && in->h % d->block_h) || (d->block_w > 0 && in->w % d->block_w))) return 0;
   if (d->kh * d->kw > 9 || d->kh < 1 || d->kw < 1) return 0;
@@ -427,6 +444,8 @@ extern "C" int lfsr_conv2d_stem(const lfsr_tensor* in, const float* w_packed, co
   a.kh = d->kh; a.kw = d->kw; a.dh = d->dil_h; a.dw = d->dil_w; a.ph = d->pad_h; a.pw = d->pad_w;
   a.act = d->act; a.slope = d->act_slope; a.perm_a = d->in_perm ? d->perm_a : 0;
   a.bh = d->block_h > 0 ? d->block_h : in->h; a.bw = d->block_w > 0 ? d->block_w : in->w;
+  a.o16 = d->out_mode == 1 ? (__half*)d->out16.ptr : nullptr;
+  a.o16_ld = d->out_mode == 1 ? (int)d->out16.ld : 0;
   dim3 grid(ceil_div(out->w, 16), ceil_div(out->h, 8), out->n);
   if (a.perm_a) {
     conv_stem_macpi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);

@@ -174,6 +174,28 @@ class CudaOps:
         fp16 operand path (tensor cores only, raises when the layer does not qualify): `x` may be a float16 NHWC view (then
         pc.w_tc16 is used); `out16` is a float16 view that receives a copy of the output; `out=None` with `out16` writes the
         fp16 tensor only."""
+        if (pc.cin == 1 and out16 is not None and out is not None and x.dtype == torch.float32 and mul is None and res is None
+                and in_scale is None and tail is None and not in_perm and not out_perm):
+            # 1-channel stem that also writes the fp16 operand copy of its output (no separate conversion pass)
+            d = N.ConvDesc()
+            d.kh, d.kw = pc.kh, pc.kw
+            d.stride_h, d.stride_w = pc.stride
+            d.dil_h, d.dil_w = pc.dil
+            d.pad_h, d.pad_w = pc.pad
+            d.shuf_ry, d.shuf_rx, d.shuf_mode = shuffle
+            d.block_h, d.block_w = block
+            d.act, d.act_slope, d.alpha = act, slope, alpha
+            d.bias = self._ptr(pc.bias)
+            d.out16 = as_tensor(out16, "conv.out16", f16=True)
+            d.out_mode = N.OUT_BOTH
+            tin, tout = as_tensor(x, "conv.in"), as_tensor(out, "conv.out")
+            if self.lib.lfsr_conv2d_stem_supported(C.byref(tin), C.byref(tout), C.byref(d)):
+                N.check(self.lib.lfsr_conv2d_stem(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), self._stream(x)),
+                        "lfsr_conv2d_stem")
+                return
+            self.conv(x, pc, out, act=act, slope=slope, alpha=alpha, shuffle=shuffle, block=block)      # stem, then the conversion
+            self.to_f16(out, out16)
+            return
         if x.dtype == torch.float16 or out16 is not None:
             return self._conv16(x, pc, out, out16, act, slope, alpha, mul, mul_act, res, shuffle, block, tail, in_scale)
         d = N.ConvDesc()

@@ -117,8 +117,7 @@ class get_model(LFNetBase):
         f0, f0h = buf("f0", H, W, C), b16("f0", H, W, C)
         t1h, t2h, ybh = b16("t1", H, W, C), b16("t2", H, W, C), b16("yb", H, W, C)
         fa, fah, fb = buf("fa", H, W, C), b16("fa", H, W, C), buf("fb", H, W, C)
-        ops.conv(xin, pk["init0"], f0, block=blk)
-        ops.to_f16(f0, f0h)
+        ops.conv(xin, pk["init0"], f0, out16=f0h, block=blk)             # the stem kernel writes the fp16 operand copy itself
         ops.conv(f0h, pk["init"][0], None, out16=t1h, act=LR, slope=0.2, block=blk)
         ops.conv(t1h, pk["init"][1], None, out16=t2h, act=LR, slope=0.2, block=blk)
         ops.conv(t2h, pk["init"][2], fa, out16=fah, act=LR, slope=0.2, res=f0, block=blk)

@@ -311,7 +311,14 @@ class get_model(LFNetBase):
         # (fp16 operand plan: pixel stride 64 with zero pad floats, so the same buffer is the 64-channel residual of gf2)
         shallow64 = buf("shallow64", H, W, 64) if f16 else None
         shallow = shallow64[..., 0:CP] if f16 else buf("shallow", H, W, CP)
-        ops.conv(xin, pk["stem"], shallow)
+        # fp16 copy of the whole trunk (64-half pixels), written by the stem / the SA tail of the previous stage: channels 0..31 feed
+        # the spatial branch's tensor-core convs, 40..57 the all-MMA EPI kernel
+        epi_mma = bool(f16) and pk["stages"][0].get("epi_img") is not None and gs + 12 <= CP
+        trunk16 = self._buf16("trunk16", B, H, W, 64, dev) if epi_mma else None
+        if epi_mma:
+            ops.conv(xin, pk["stem"], shallow, out16=trunk16[..., 0:CP])      # (the stem kernel writes the copy itself)
+        else:
+            ops.conv(xin, pk["stem"], shallow)
         feat = shallow
         pp = [buf("feat_a", H, W, CP), buf("feat_b", H, W, CP)]
         hA, wA = H // A, W // A
@@ -327,10 +334,6 @@ class get_model(LFNetBase):
         fu1 = self._buf16("fu1", B, H, W, CU, dev) if f16 else buf("fu1", H, W, CU)
         fu2 = buf("fu2", H, W, CP)
         if f16:
-            # fp16 copy of the whole trunk (64-half pixels), written by the stem conversion / the SA tail of the previous stage:
-            # channels 0..31 feed the spatial branch's tensor-core convs, 40..57 the all-MMA EPI kernel
-            epi_mma = pk["stages"][0].get("epi_img") is not None and gs + 12 <= CP
-            trunk16 = self._buf16("trunk16", B, H, W, 64, dev) if epi_mma else None
             xs16 = trunk16[..., 0:32] if epi_mma else self._buf16("xs16", B, H, W, 32, dev)
             t18h = self._buf16("t18h", B, H, W, 32, dev)
         pm, am1, am = buf("pm", A, A, CP), buf("am1", A, A, C // 4), buf("am", A, A, CP)
@@ -340,9 +343,7 @@ class get_model(LFNetBase):
             # spatial branch
             if f16 and gs + 12 <= CP:
                 if i == 0:          # later stages: the SA modulator of the previous stage wrote the copy next to the trunk
-                    if epi_mma:
-                        ops.to_f16(shallow64, trunk16)
-                    else:
+                    if not epi_mma:
                         ops.to_f16(feat[..., 0:32], xs16)
                 ops.conv(xs16, st["spa0h"], None, out16=t18h[..., 0:24], act=LR, slope=0.1)
                 ops.conv(t18h, st["spa2h"], cat[..., 0:gs])

@@ -186,6 +186,23 @@ def test_conv_f32(ops, ref, case):
     assert err <= 2e-5, f"max err {err}"
 
 
+@pytest.mark.parametrize("block", [(0, 0), (8, 40), (8, 8)])
+def test_stem_with_fp16_copy(ops, ref, block):
+    """1-channel stem that also writes the fp16 operand copy of its output (tiled kernel; blocks narrower than a tile fall back to
+    stem + conversion): fp32 output unchanged, the copy is exactly its rounding, pad halves stay untouched"""
+    n, h, w, cout = 2, 40, 40, 56
+    g = torch.Generator().manual_seed(5)
+    pad = (1, 1) if block != (0, 0) else (5, 5)
+    pc = K.pack_conv((torch.rand(cout, 1, 3, 3, generator=g) - 0.5) * 0.6, torch.rand(cout, generator=g) - 0.5, dil=pad, pad=pad, device=DEV)
+    x = nhwc(n, h, w, 1, seed=3)
+    a, b = nhwc(n, h, w, 64, seed=7), nhwc(n, h, w, 64, seed=7)
+    full16 = torch.full((n, h, w, 64), 3.0, dtype=torch.float16, device=DEV)
+    ops.conv(x, pc, a[..., :cout], out16=full16[..., :cout], block=block)
+    ref.conv(x, pc, b[..., :cout], block=block)
+    assert (a - b).abs().max().item() <= 2e-5
+    assert torch.equal(full16[..., :cout], a[..., :cout].half()) and bool((full16[..., cout:] == 3.0).all())
+
+
 def test_conv_residual_in_place(ops, ref):
     n, h, w, c = 1, 24, 24, 54
     wt = (torch.rand(1, c, 3, 3) - 0.5) * 0.1
