@@ -202,7 +202,8 @@ int lfsr_mel_epi_branch_tc(const lfsr_tensor* in, const float* w_packed, const l
                            float slope, void* stream);
 /* The same block with the depthwise taps on the tensor cores as well: dw_b . pw_b is one tcgen05 MMA per tap whose A operand is
  * the fp16 input tile read at a shifted row (channels 0..15; channels 16, 17 go through the CUDA cores and one extra MMA).
- * `in16` is the fp16 copy of `in` (ptr = __half*, >= 16 channels) the producer of `in` wrote next to it: the tile is one TMA load.
+ * `in16` is the fp16 copy of `in` (ptr = __half*, the same 18 channels; the 6 halves behind them must be readable inside the pixel,
+ * i.e. the slice starts at least 24 halves before the end of a pixel row) that the producer of `in` wrote: the tile is two TMA loads.
  * lfsr_mel_epi_pack (host) turns w_packed into the pre-swizzled operand image the kernel loads with one bulk copy;
  * lfsr_mel_epi_pack_bytes is its size (0: this kernel length is not supported, use lfsr_mel_epi_branch_tc). */
 size_t lfsr_mel_epi_pack_bytes(int klen);
