@@ -225,11 +225,28 @@ conv_stem_tile_kernel(const StemArgs a) {
   const int SW = 16 + 2 * a.pw, SH = 8 + 2 * a.ph;
   const int bx0 = ox0 / a.bw * a.bw, by0 = oy0 / a.bh * a.bh;     // the view block of this tile
   const float* src = a.in.p + (size_t)img * H * W;
-  for (int i = threadIdx.x; i < SH * SW; i += 256) {
-    const int ly = i / SW, lxx = i - ly * SW;
-    const int iy = oy0 - a.ph + ly, ix = ox0 - a.pw + lxx;
-    const bool ok = iy >= by0 && iy < by0 + a.bh && iy < H && ix >= bx0 && ix < bx0 + a.bw && ix < W;
-    st_in[i] = ok ? __ldg(src + iy * W + ix) : 0.f;
+  if (a.perm_a) {
+    // MacPI addressing over SAI storage (DistgSSR.py:21, LF_InterNet.py:24): the tile is staged in MacPI coordinates, a MacPI
+    // position (i*A+u, j*A+v) reading pixel (i, j) of view (u, v); outside the MacPI image = outside the view = zero. The layer
+    // is then the same dilation-A conv as the SAI stems.
+    const int A = a.perm_a, hh = H / A, ww = W / A;
+    for (int i = threadIdx.x; i < SH * SW; i += 256) {
+      const int ly = i / SW, lxx = i - ly * SW;
+      const int Y = oy0 - a.ph + ly, X = ox0 - a.pw + lxx;
+      float v = 0.f;
+      if (Y >= 0 && Y < H && X >= 0 && X < W) {
+        const int ii = Y / A, u = Y - ii * A, jj = X / A, vv = X - jj * A;
+        v = __ldg(src + (u * hh + ii) * W + vv * ww + jj);
+      }
+      st_in[i] = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < SH * SW; i += 256) {
+      const int ly = i / SW, lxx = i - ly * SW;
+      const int iy = oy0 - a.ph + ly, ix = ox0 - a.pw + lxx;
+      const bool ok = iy >= by0 && iy < by0 + a.bh && iy < H && ix >= bx0 && ix < bx0 + a.bw && ix < W;
+      st_in[i] = ok ? __ldg(src + iy * W + ix) : 0.f;
+    }
   }
   __syncthreads();
   const int ox = ox0 + lx;
@@ -448,6 +465,11 @@ extern "C" int lfsr_conv2d_stem(const lfsr_tensor* in, const float* w_packed, co
   a.o16_ld = d->out_mode == 1 ? (int)d->out16.ld : 0;
   dim3 grid(ceil_div(out->w, 16), ceil_div(out->h, 8), out->n);
   if (a.perm_a) {
+    const size_t tile_m = (size_t)(8 + 2 * a.ph) * (16 + 2 * a.pw) * sizeof(float);
+    if (a.bh == in->h && a.bw == in->w && a.ph == a.dh * (a.kh / 2) && a.pw == a.dw * (a.kw / 2) && tile_m <= 40 * 1024) {
+      conv_stem_tile_kernel<<<grid, 256, tile_m, (cudaStream_t)stream>>>(a);
+      return check_launch("conv_stem_tile_kernel");
+    }
     conv_stem_macpi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     return check_launch("conv_stem_macpi_kernel");
   }
