@@ -185,6 +185,10 @@ int lfsr_conv2d_thin(const lfsr_tensor* in, const float* w_packed, const lfsr_te
 int lfsr_conv2d_stem_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);
 int lfsr_conv2d_stem(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out,
                      const lfsr_conv_desc* d, void* stream);
+/* fp32 1x1 conv to 8 or 16 output channels (DistgSSR's composed reconstruction tail 64 -> s^2, DistgSSR.py:24-27): dense NHWC in / out,
+ * weights packed as for lfsr_conv2d_f32 ([cin][cout]); bias and activation fused. */
+int lfsr_conv1x1_few_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);
+int lfsr_conv1x1_few(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out, const lfsr_conv_desc* d, void* stream);
 /* direct conv for 1..4 output channels (reconstruction heads 54->1 / 64->1: MyEfficientLFNet.py:70-73,
  * EPIT.py:48): stride 1, "same" padding; weights packed as for lfsr_conv2d_f32; bias/act/alpha/res fused. */
 int lfsr_conv2d_small_cout_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d);

@@ -99,6 +99,8 @@ SIGNATURES = {
     "lfsr_conv2d_stem": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
     "lfsr_conv2d_thin_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),
     "lfsr_conv2d_thin": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
+    "lfsr_conv1x1_few_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),
+    "lfsr_conv1x1_few": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
     "lfsr_conv2d_small_cout_supported": (_I, [_TP, _TP, C.POINTER(ConvDesc)]),
     "lfsr_conv2d_small_cout": (_I, [_TP, _P, _TP, C.POINTER(ConvDesc), _P]),
     "lfsr_mel_epi_branch": (_I, [_TP, _P, _TP, _I, _I, C.c_float, _P]),

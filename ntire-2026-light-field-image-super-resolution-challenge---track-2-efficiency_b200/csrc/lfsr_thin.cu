@@ -602,3 +602,87 @@ extern "C" int lfsr_ang_expand(const lfsr_tensor* in, const float* w, const lfsr
   }
   return check_launch("ang_expand_kernel");
 }
+
+
+// ---- 1x1 conv to 8 / 16 output channels, fp32 --------------------------------------------------------------------------
+// DistgSSR's composed reconstruction tail (DistgSSR.py:24-27 folded to one 1x1 64 -> s^2, see lfnets/distgssr.py) produces
+// the image itself, so it stays fp32; on the general fp32 implicit GEMM it took 0.6 ms at batch 64 for 1.7 GFLOP. Here a
+// thread owns two pixels (one weight read feeds both), weights [cin][cout] are broadcast from shared memory, packed FFMA2.
+namespace lfsr {
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv1x1_few_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ bias, int act, float slope,
+                   long long pixels) {
+  extern __shared__ __align__(16) float cf_w[];        // [cin][COUT]
+  const int C = in.c;
+  for (int i = threadIdx.x; i < C * COUT; i += 256) cf_w[i] = __ldg(w + i);
+  __syncthreads();
+  const long long half = (pixels + 1) / 2;
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < half; t += (long long)gridDim.x * 256) {
+    const long long p0 = t, p1 = t + half;            // two pixels half the tensor apart: both streams stay coalesced
+    const bool two = p1 < pixels;
+    const float* s0 = in.p + p0 * in.ld;
+    const float* s1 = in.p + (two ? p1 : p0) * in.ld;
+    f32x2 a0[COUT / 2], a1[COUT / 2];
+#pragma unroll
+    for (int o = 0; o < COUT / 2; ++o) {
+      const f32x2 b = bias ? pack2(__ldg(bias + 2 * o), __ldg(bias + 2 * o + 1)) : pack2(0.f, 0.f);
+      a0[o] = b; a1[o] = b;
+    }
+    for (int c = 0; c < C; c += 4) {
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(s0 + c)), x1 = __ldg(reinterpret_cast<const float4*>(s1 + c));
+      const float xs0[4] = {x0.x, x0.y, x0.z, x0.w}, xs1[4] = {x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4* wr = reinterpret_cast<const float4*>(cf_w + (c + k) * COUT);
+        const f32x2 v0 = pack2(xs0[k], xs0[k]), v1 = pack2(xs1[k], xs1[k]);
+#pragma unroll
+        for (int q = 0; q < COUT / 4; ++q) {
+          const float4 ww = wr[q];
+          const f32x2 wl = pack2(ww.x, ww.y), wh = pack2(ww.z, ww.w);
+          a0[2 * q] = fma2(v0, wl, a0[2 * q]); a0[2 * q + 1] = fma2(v0, wh, a0[2 * q + 1]);
+          a1[2 * q] = fma2(v1, wl, a1[2 * q]); a1[2 * q + 1] = fma2(v1, wh, a1[2 * q + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < COUT / 4; ++q) {
+      float4 r0, r1;
+      unpack2(a0[2 * q], r0.x, r0.y); unpack2(a0[2 * q + 1], r0.z, r0.w);
+      unpack2(a1[2 * q], r1.x, r1.y); unpack2(a1[2 * q + 1], r1.z, r1.w);
+      if (act) {
+        r0.x = apply_act(r0.x, act, slope); r0.y = apply_act(r0.y, act, slope); r0.z = apply_act(r0.z, act, slope); r0.w = apply_act(r0.w, act, slope);
+        r1.x = apply_act(r1.x, act, slope); r1.y = apply_act(r1.y, act, slope); r1.z = apply_act(r1.z, act, slope); r1.w = apply_act(r1.w, act, slope);
+      }
+      *reinterpret_cast<float4*>(out.p + p0 * out.ld + 4 * q) = r0;
+      if (two) *reinterpret_cast<float4*>(out.p + p1 * out.ld + 4 * q) = r1;
+    }
+  }
+}
+}  // namespace lfsr
+
+extern "C" int lfsr_conv1x1_few_supported(const lfsr_tensor* in, const lfsr_tensor* out, const lfsr_conv_desc* d) {
+  if (!tensor_ok(in) || !tensor_ok(out) || !d) return 0;
+  if (d->kh != 1 || d->kw != 1 || d->stride_h != 1 || d->stride_w != 1 || d->pad_h || d->pad_w) return 0;
+  if (d->in_perm || d->out_perm || d->mul.ptr || d->res.ptr || d->in_scale || d->tail_w || d->out_mode || d->in_f16) return 0;
+  if (d->shuf_ry > 1 || d->shuf_rx > 1 || d->block_h > 0 || d->block_w > 0 || d->alpha != 1.f) return 0;
+  if (out->n != in->n || out->h != in->h || out->w != in->w) return 0;
+  if ((out->c != 8 && out->c != 16) || in->c % 4 || in->c > 256 || in->ld % 4 || out->ld % 4) return 0;
+  if (((uintptr_t)in->ptr & 15) || ((uintptr_t)out->ptr & 15)) return 0;
+  return 1;
+}
+
+extern "C" int lfsr_conv1x1_few(const lfsr_tensor* in, const float* w_packed, const lfsr_tensor* out, const lfsr_conv_desc* d,
+                                void* stream) {
+  LFSR_REQUIRE(w_packed && lfsr_conv1x1_few_supported(in, out, d), "lfsr_conv1x1_few: unsupported problem");
+  const long long pixels = (long long)in->n * in->h * in->w;
+  long long blocks = ((pixels + 1) / 2 + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  const size_t smem = (size_t)in->c * out->c * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out->c == 16)
+    lfsr::conv1x1_few_kernel<16><<<(unsigned)blocks, 256, smem, st>>>(view_of(in), view_of(out), w_packed, d->bias, d->act, d->act_slope, pixels);
+  else
+    lfsr::conv1x1_few_kernel<8><<<(unsigned)blocks, 256, smem, st>>>(view_of(in), view_of(out), w_packed, d->bias, d->act, d->act_slope, pixels);
+  return check_launch("conv1x1_few_kernel");
+}

@@ -231,6 +231,9 @@ class CudaOps:
                 self.lib.lfsr_conv2d_thin_supported(C.byref(tin), C.byref(tout), C.byref(d))):
             N.check(self.lib.lfsr_conv2d_thin(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st), "lfsr_conv2d_thin")
             return
+        if pc.cout in (8, 16) and pc.w_tc is None and self.lib.lfsr_conv1x1_few_supported(C.byref(tin), C.byref(tout), C.byref(d)):
+            N.check(self.lib.lfsr_conv1x1_few(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st), "lfsr_conv1x1_few")
+            return
         if pc.cout <= 4 and self.lib.lfsr_conv2d_small_cout_supported(C.byref(tin), C.byref(tout), C.byref(d)):
             N.check(self.lib.lfsr_conv2d_small_cout(C.byref(tin), pc.w_f32.data_ptr(), C.byref(tout), C.byref(d), st),
                     "lfsr_conv2d_small_cout")

@@ -186,6 +186,22 @@ def test_conv_f32(ops, ref, case):
     assert err <= 2e-5, f"max err {err}"
 
 
+@pytest.mark.parametrize("cin,cout,act", [(64, 16, 0), (64, 8, 2), (60, 16, 0)])
+def test_conv1x1_few(ops, ref, cin, cout, act):
+    """fp32 1x1 conv to 8 / 16 channels (DistgSSR's reconstruction tail): exact fp32, odd pixel counts, strided views"""
+    n, h, w = 3, 37, 45
+    g = torch.Generator().manual_seed(cin + cout)
+    pc = K.pack_conv((torch.rand(cout, cin, 1, 1, generator=g) - 0.5) * 0.3, torch.rand(cout, generator=g) - 0.5, device=DEV)
+    xfull = nhwc(n, h, w, 64, seed=3)
+    x = xfull[..., :cin]
+    a, b = nhwc(n, h, w, cout, seed=7), nhwc(n, h, w, cout, seed=7)
+    before = ops.lib.lfsr_launch_count()
+    ops.conv(x, pc, a, act=act, slope=0.1)
+    assert ops.lib.lfsr_launch_count() == before + 1
+    ref.conv(x, pc, b, act=act, slope=0.1)
+    assert (a - b).abs().max().item() <= 2e-5
+
+
 @pytest.mark.parametrize("block", [(0, 0), (8, 40), (8, 8)])
 def test_stem_with_fp16_copy(ops, ref, block):
     """1-channel stem that also writes the fp16 operand copy of its output (tiled kernel; blocks narrower than a tile fall back to
